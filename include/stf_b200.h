@@ -1,0 +1,227 @@
+/*
+ * stf_b200.h -- C ABI of libstf_b200.so: the B200 (sm_100a) implementation of the STF / WACNN
+ * data-parallel hot path.  This header is the drop-in boundary: plain
+ * pointers and sizes, no torch / C++ types, no exceptions across it.
+ *
+ * Conventions (all entry points)
+ *   - return 0 on success; < 0 = argument / shape error (STF_E_*); > 0 = cudaError_t.
+ *   - device pointers are raw CUDA device addresses, fp32 / int32, contiguous, 16-byte aligned.
+ *   - the caller owns every buffer (outputs and workspaces included); the library allocates no
+ *     device memory and keeps no mutable global state, so calls are thread-safe.
+ *   - all GPU work is enqueued on `stream` (a cudaStream_t passed as void*); no host sync.
+ *   - kernels are deterministic run-to-run and batch-invariant (no atomics, fixed reduction
+ *     order): decode must rebuild the encoder's indexes bit-for-bit (reference stf.py:767).
+ *
+ * Each function cites the reference interface it replaces (paths relative to the reference
+ * repository memory4963/STF).  The reference has no FFI for this path -- it is PyTorch eager
+ * plus two pybind11 modules -- so the binding a maintainer adds is the ctypes stub shown in
+ * INTEGRATION.md (stf_b200/_C.py is that stub).
+ */
+#ifndef STF_B200_H
+#define STF_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define STF_OK 0
+#define STF_E_ARG (-1)       /* null pointer / negative size */
+#define STF_E_SHAPE (-2)     /* unsupported or inconsistent shape */
+#define STF_E_ALIGN (-3)     /* pointer not 16-byte aligned */
+#define STF_E_TABLE (-4)     /* invalid CDF / scale table */
+#define STF_E_OVERFLOW (-5)  /* output buffer too small */
+#define STF_E_STREAM (-6)    /* corrupt / truncated bitstream */
+
+/* Library / build identification: "stf_b200 <ver> sm_100a". */
+const char *stf_version(void);
+/* Number of CUDA kernels this library has launched in the calling process (for bench.py's
+ * gpu_launches claim).  Monotonic, relaxed atomic. */
+int64_t stf_launch_count(void);
+
+/* ------------------------------------------------------------------------------------------
+ * Entropy-model element-wise kernels (HBM-bound).
+ * ------------------------------------------------------------------------------------------ */
+
+/* GaussianConditional.build_indexes (compressai/entropy_models/entropy_models.py:661-666):
+ *   sigma = max(scales, scale_bound);  idx = (levels-1) - #{ i < levels-1 : sigma <= table[i] }
+ * NaN -> levels-1.  `table_host` is a HOST array of `levels` (<= 64) fp32 values.  8 B/element. */
+int stf_build_indexes(const float *scales, int32_t *indexes, int64_t n, const float *table_host,
+                      int levels, float scale_bound, void *stream);
+
+/* One compress step of the slice loop (stf.py:717-719 / cnn.py:246-248) fused:
+ *   indexes = build_indexes(scales); symbols = int32(round_half_even(y - means));
+ *   y_hat = float(symbols) + means
+ * y may be a channel slice of a larger NCHW tensor: element (b, c, p) is read at
+ * y[b * y_batch_stride + c * plane + p] with c < channels, p < plane; scales / means / y_hat are
+ * dense (batch, channels, plane).  symbols / indexes are written at
+ * out[b * out_batch_stride + c * plane + p] so that all slices of one image land contiguously in
+ * the reference's coding order (slice-major, then channel, row, column; stf.py:721-722).
+ * Any of symbols / indexes / y_hat may be NULL.  24 B/element with all three outputs. */
+int stf_gaussian_compress_step(const float *y, int64_t y_batch_stride, const float *scales,
+                               const float *means, int32_t *symbols, int32_t *indexes,
+                               int64_t out_batch_stride, float *y_hat, int batch, int channels,
+                               int64_t plane, const float *table_host, int levels,
+                               float scale_bound, void *stream);
+
+/* EntropyModel.quantize(x, "symbols", means) (entropy_models.py:126-150); means may be NULL. */
+int stf_quantize_symbols(const float *x, const float *means, int32_t *symbols, int64_t n,
+                         void *stream);
+
+/* EntropyModel.dequantize (entropy_models.py:158-165) for one decoded slice:
+ *   y_hat[b,c,p] = float(symbols[b * sym_batch_stride + c * plane + p]) + means[b,c,p] */
+int stf_dequantize(const int32_t *symbols, int64_t sym_batch_stride, const float *means,
+                   float *y_hat, int batch, int channels, int64_t plane, void *stream);
+
+/* GaussianConditional.forward in eval mode fused with the caller's ste_round
+ * (entropy_models.py:645-659, 626-643; stf.py:623-626):
+ *   y_hat = round_half_even(y - means) + means
+ *   v = |y_hat - means|; sigma = max(scales, scale_bound)
+ *   lik = max( 0.5*erfc(-(0.5 - v)/sigma/sqrt2) - 0.5*erfc(-(-0.5 - v)/sigma/sqrt2), lik_bound )
+ * y is addressed like in stf_gaussian_compress_step; y_hat may be NULL.  16-20 B/element. */
+int stf_gaussian_likelihood(const float *y, int64_t y_batch_stride, const float *scales,
+                            const float *means, float *y_hat, float *likelihood, int batch,
+                            int channels, int64_t plane, float scale_bound, float lik_bound,
+                            void *stream);
+
+/* EntropyBottleneck.forward in eval mode (entropy_models.py:446-489, 400-433) without the two
+ * permutes: z is (batch, channels, plane) NCHW.  `params` is a device array of
+ * channels * STF_EB_PARAMS floats packed per channel by stf_b200/entropy_models.py:
+ *   [softplus(M0) 3][b0 3][tanh(f0) 3] [softplus(M1) 9][b1 3][tanh(f1) 3] ... [softplus(M4) 3][b4 1]
+ *   (58 values) then [median][0 pad] -> STF_EB_PARAMS = 60 floats per channel
+ *   z_hat = round_half_even(z - median) + median;  lik = max(|sig(s*u) - sig(s*l)|, lik_bound)
+ * Optionally also emits int32 symbols = round(z - median) (EntropyBottleneck.compress path,
+ * entropy_models.py:508-515).  z_hat / likelihood / symbols may each be NULL. */
+#define STF_EB_PARAMS 60
+#define STF_EB_MEDIAN_SLOT 58
+int stf_entropy_bottleneck(const float *z, const float *params, float *z_hat, float *likelihood,
+                           int32_t *symbols, int batch, int channels, int64_t plane,
+                           float lik_bound, void *stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Window-attention path (tensor-core bound).
+ *
+ * One tcgen05 / TMEM GEMM kernel  Y = epilogue( prologue(X) . W^T )  with TF32 operands and fp32
+ * accumulation covers qkv, proj, fc1, fc2, PatchMerging and PatchSplit; the prologue does the
+ * LayerNorm and the window-partition / cyclic-shift / 2x2-merge gathers as index math, the
+ * epilogue does bias, q-scaling, exact-erf GELU, residual add and the window-reverse /
+ * un-shift / pixel-shuffle scatters.  A second kernel does the per-window softmax(QK^T+B+mask)V.
+ * ------------------------------------------------------------------------------------------ */
+
+/* Re-pack a torch Linear weight W[N][K] (row-major fp32) into the tile image the GEMM kernel
+ * streams with 1-D bulk TMA copies: [N / n_tile][K / 4][n_tile][4] floats, rounded to TF32
+ * (round-to-nearest, ties away).  n_tile = stf_linear_n_tile(N).  `packed` holds N*K floats. */
+int stf_linear_n_tile(int N);
+int stf_pack_linear_weight(const float *weight, float *packed, int N, int K, void *stream);
+
+/* Row gather applied to X before the GEMM (what each of the 128 rows of an M-tile reads). */
+enum {
+  STF_ROWS_DENSE = 0,   /* row r = X[r, :K]                                                      */
+  STF_ROWS_WINDOW = 1,  /* row g (window order) = token after cyclic shift + window partition;    */
+                        /* pad tokens (h >= H or w >= W) are zero AFTER the LayerNorm             */
+                        /* (stf.py:155-175: norm1, F.pad, torch.roll, window_partition)           */
+  STF_ROWS_MERGE = 2    /* row = concat of the 2x2 neighbourhood (x0,x1,x2,x3), zero pad BEFORE   */
+                        /* the LayerNorm (stf.py:218-232)                                         */
+};
+/* Epilogue applied to the fp32 accumulator before the store. */
+enum {
+  STF_EPI_STORE = 0,        /* Y[r, n] = acc (+bias)                                              */
+  STF_EPI_QKV = 1,          /* (+bias), columns < q_cols scaled by q_scale (stf.py:97-100)        */
+  STF_EPI_GELU = 2,         /* exact-erf GELU(acc + bias) (stf.py:35-36)                          */
+  STF_EPI_RESIDUAL = 3,     /* Y[r] = residual[r] + acc + bias  (stf.py:197)                      */
+  STF_EPI_WINDOW_RESIDUAL = 4, /* row g -> token t via window_reverse + un-shift, pad rows dropped:*/
+                            /* Y[t] = residual[t] + acc + bias (stf.py:181-196)                   */
+  STF_EPI_PIXEL_SHUFFLE = 5 /* PatchSplit: feature f of token (h,w) -> token (2h+(f%4)/2,         */
+                            /* 2w+f%2), channel f/4 (stf.py:256-259)                              */
+};
+
+typedef struct {
+  /* problem */
+  int M;            /* rows of the GEMM (tokens; for WINDOW: B * nWh * nWw * ws * ws incl. pad) */
+  int N;            /* output features */
+  int K;            /* input features (for MERGE: 4 * C) */
+  const float *x;   /* input activations (token-major, row stride = ldx floats) */
+  int ldx;
+  const float *w_packed; /* from stf_pack_linear_weight */
+  const float *bias;     /* N floats or NULL */
+  float *y;         /* output */
+  int ldy;
+  /* prologue */
+  int rows;               /* STF_ROWS_* */
+  const float *ln_gamma;  /* K floats or NULL = no LayerNorm */
+  const float *ln_beta;
+  float ln_eps;
+  /* epilogue */
+  int epilogue;           /* STF_EPI_* */
+  const float *residual;  /* for the two residual epilogues (row stride ldy) */
+  int q_cols;             /* STF_EPI_QKV */
+  float q_scale;
+  /* geometry for WINDOW / MERGE / PIXEL_SHUFFLE: feature map of `batch` images H x W tokens */
+  int batch, H, W;
+  int window;             /* window size ws (WINDOW) */
+  int shift;              /* cyclic shift (0 or ws/2) */
+} stf_linear_args;
+
+/* Fused linear layer on tcgen05 tensor cores.  Replaces, depending on the arguments:
+ * norm1+pad+roll+window_partition+qkv (stf.py:155-175,97), proj+window_reverse+roll+residual
+ * (stf.py:119,181-196), norm2+fc1+GELU (stf.py:197,35-36), fc2+residual (stf.py:38,197),
+ * PatchMerging (stf.py:209-235) and PatchSplit (stf.py:251-260). */
+int stf_linear(const stf_linear_args *args, void *stream);
+
+/* Per-window multi-head attention core (stf.py:100-118 / layers/win_attention.py:94-112):
+ *   S = q k^T + table[rel_idx(n,m)][head] (+ mask(n,m));  P = softmax_m(S);  O = P v
+ * qkv: (num_windows_total * N, 3*C) rows in window order, features [3][heads][d], q already
+ * scaled; out: (num_windows_total * N, C) head-major concat.  N = ws*ws in {16, 64},
+ * d = C / heads in {16, 24, 32, 40}.  The shifted-window mask ({0,-100}, stf.py:316-334) is
+ * computed analytically from the window position when shift > 0: windows are numbered
+ * image-major then row-major over the (Hp/ws, Wp/ws) grid. */
+int stf_window_attention(const float *qkv, float *out, const float *bias_table, int64_t num_windows,
+                         int C, int heads, int ws, int shift, int Hp, int Wp, void *stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Host-side rANS codec (CPU; replaces compressai.ans, cpp_exts/rans/rans_interface.cpp:99-350,
+ * bit-exact streams, no Python lists, LUT symbol search, thread-parallel over streams).
+ * ------------------------------------------------------------------------------------------ */
+
+typedef struct stf_rans_table stf_rans_table;
+
+/* Prepare a CDF table set: cdf is (rows, row_stride) int32, sizes[r] = valid entries of row r
+ * (cdf_length), offsets[r] = symbol offset.  Precision is 16 bits.  Returns NULL on a malformed
+ * table (row not starting at 0, not ending at 65536, or not strictly increasing). */
+stf_rans_table *stf_rans_table_create(const int32_t *cdf, int rows, int row_stride,
+                                      const int32_t *sizes, const int32_t *offsets);
+void stf_rans_table_destroy(stf_rans_table *t);
+
+/* RansEncoder.encode_with_indexes (rans_interface.cpp:193-204): returns the stream length in
+ * bytes (written to out[0..)), or STF_E_OVERFLOW / STF_E_ARG.  stf_rans_encode_bound(n) bytes
+ * of `out` are always sufficient. */
+int64_t stf_rans_encode_bound(int64_t n);
+int64_t stf_rans_encode(const stf_rans_table *t, const int32_t *symbols, const int32_t *indexes,
+                        int64_t n, uint8_t *out, int64_t out_cap);
+
+/* Encode `count` independent streams on up to `threads` host threads (one image each).
+ * out_lens[i] receives the byte length or a negative error. */
+int stf_rans_encode_batch(const stf_rans_table *t, int count, const int32_t *const *symbols,
+                          const int32_t *const *indexes, const int64_t *n, uint8_t *const *out,
+                          const int64_t *out_cap, int64_t *out_lens, int threads);
+
+/* RansDecoder (rans_interface.cpp:277-350): set_stream + repeated decode_stream calls. */
+typedef struct stf_rans_decoder stf_rans_decoder;
+stf_rans_decoder *stf_rans_decoder_create(const uint8_t *stream, int64_t nbytes);
+void stf_rans_decoder_destroy(stf_rans_decoder *d);
+int stf_rans_decode(stf_rans_decoder *d, const stf_rans_table *t, const int32_t *indexes,
+                    int64_t n, int32_t *symbols_out);
+/* Decode the next n[i] symbols of `count` independent decoders in parallel. */
+int stf_rans_decode_batch(stf_rans_decoder *const *d, const stf_rans_table *t, int count,
+                          const int32_t *const *indexes, const int64_t *n,
+                          int32_t *const *symbols_out, int threads);
+
+/* compressai._CXX.pmf_to_quantized_cdf (cpp_exts/ops/ops.cpp:24-81): cdf_out has n+1 entries. */
+int stf_pmf_to_quantized_cdf(const float *pmf, int n, int precision, uint32_t *cdf_out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* STF_B200_H */

@@ -1,0 +1,174 @@
+"""Drop-in for the reference's `compressai.ans` pybind11 module, backed by the host rANS codec in
+libstf_b200.so (stf_b200/csrc/rans_host.cpp).  Same class and method names, same argument order
+and the same bytes out (reference compressai/cpp_exts/rans/rans_interface.cpp:352-372):
+
+    BufferedRansEncoder().encode_with_indexes(symbols, indexes, cdfs, cdfs_sizes, offsets); .flush()
+    RansEncoder().encode_with_indexes(symbols, indexes, cdfs, cdfs_sizes, offsets) -> bytes
+    RansDecoder().set_stream(b); .decode_stream(indexes, cdfs, cdfs_sizes, offsets) -> list[int]
+    RansDecoder().decode_with_indexes(b, indexes, cdfs, cdfs_sizes, offsets) -> list[int]
+
+Beyond the reference: every sequence argument may be an int32 numpy array / CPU torch tensor
+(zero-copy), `cdfs` may be a prepared `RansTable` (then sizes / offsets are ignored), decoders
+have `decode_stream_array` returning numpy, and `encode_batch` / `decode_batch` code one stream
+per image on several host threads.
+"""
+import ctypes
+import os
+
+import numpy as np
+
+from . import _C
+
+
+def _as_i32(a):
+    """int32, C-contiguous numpy view of a list / numpy array / CPU torch tensor."""
+    if hasattr(a, "detach"):
+        a = a.detach().cpu().numpy()
+    return np.ascontiguousarray(a, dtype=np.int32)
+
+
+class RansTable:
+    """Prepared CDF table set (encoder reciprocals + decoder LUTs), reusable across calls."""
+
+    def __init__(self, cdfs, cdfs_sizes, offsets):
+        cdf = _as_i32(cdfs)
+        if cdf.ndim != 2:
+            raise ValueError(f"Invalid CDF size {cdf.shape}")
+        sizes, offs = _as_i32(cdfs_sizes).reshape(-1), _as_i32(offsets).reshape(-1)
+        if sizes.size != cdf.shape[0] or offs.size != cdf.shape[0]:
+            raise ValueError("cdfs, cdfs_sizes and offsets disagree on the number of rows")
+        L = _C.lib()
+        self._h = L.stf_rans_table_create(cdf.ctypes.data_as(_C._i32p), cdf.shape[0], cdf.shape[1],
+                                          sizes.ctypes.data_as(_C._i32p), offs.ctypes.data_as(_C._i32p))
+        if not self._h:
+            raise ValueError("malformed CDF table (rows must start at 0, end at 65536 and increase strictly)")
+        self.rows = cdf.shape[0]
+
+    def __del__(self):
+        h, self._h = getattr(self, "_h", None), None
+        if h:
+            _C.lib().stf_rans_table_destroy(h)
+
+
+def _table(cdfs, sizes, offsets):
+    return cdfs if isinstance(cdfs, RansTable) else RansTable(cdfs, sizes, offsets)
+
+
+def encode_array(table: RansTable, symbols, indexes) -> bytes:
+    s, ix = _as_i32(symbols).reshape(-1), _as_i32(indexes).reshape(-1)
+    if s.size != ix.size:
+        raise ValueError("symbols and indexes differ in length")
+    L = _C.lib()
+    cap = L.stf_rans_encode_bound(s.size)
+    out = np.empty(cap, dtype=np.uint8)
+    n = L.stf_rans_encode(table._h, s.ctypes.data, ix.ctypes.data, s.size, out.ctypes.data, cap)
+    if n < 0:
+        _C.check(int(n), "stf_rans_encode")
+    return out[:n].tobytes()
+
+
+def default_threads():
+    return max(1, min(32, (os.cpu_count() or 1)))
+
+
+def encode_batch(table: RansTable, symbols, indexes, threads=None):
+    """symbols / indexes: sequences (or 2-D arrays) of per-image int32 arrays -> list[bytes]."""
+    syms = [_as_i32(s).reshape(-1) for s in symbols]
+    idxs = [_as_i32(i).reshape(-1) for i in indexes]
+    count = len(syms)
+    if count == 0:
+        return []
+    L = _C.lib()
+    caps = [int(L.stf_rans_encode_bound(s.size)) for s in syms]
+    outs = [np.empty(c, dtype=np.uint8) for c in caps]
+    VP, I64 = ctypes.c_void_p * count, ctypes.c_int64 * count
+    lens = I64()
+    rc = L.stf_rans_encode_batch(table._h, count, VP(*[s.ctypes.data for s in syms]), VP(*[i.ctypes.data for i in idxs]),
+                                 I64(*[s.size for s in syms]), VP(*[o.ctypes.data for o in outs]), I64(*caps), lens,
+                                 threads or default_threads())
+    _C.check(rc, "stf_rans_encode_batch")
+    return [outs[i][: lens[i]].tobytes() for i in range(count)]
+
+
+class RansEncoder:
+    def encode_with_indexes(self, symbols, indexes, cdfs, cdfs_sizes=None, offsets=None) -> bytes:
+        return encode_array(_table(cdfs, cdfs_sizes, offsets), symbols, indexes)
+
+
+class BufferedRansEncoder:
+    """Accumulates (symbols, indexes) chunks; flush() codes them as ONE stream in push order."""
+
+    def __init__(self):
+        self._sym, self._idx, self._tab = [], [], None
+
+    def encode_with_indexes(self, symbols, indexes, cdfs, cdfs_sizes=None, offsets=None):
+        self._tab = _table(cdfs, cdfs_sizes, offsets)
+        self._sym.append(_as_i32(symbols).reshape(-1))
+        self._idx.append(_as_i32(indexes).reshape(-1))
+
+    def flush(self) -> bytes:
+        if self._tab is None:
+            raise ValueError("flush() before encode_with_indexes()")
+        out = encode_array(self._tab, np.concatenate(self._sym), np.concatenate(self._idx))
+        self._sym, self._idx = [], []
+        return out
+
+
+class RansDecoder:
+    def __init__(self):
+        self._h = None
+
+    def __del__(self):
+        self._close()
+
+    def _close(self):
+        h, self._h = getattr(self, "_h", None), None
+        if h:
+            _C.lib().stf_rans_decoder_destroy(h)
+
+    def set_stream(self, encoded: bytes):
+        self._close()
+        buf = np.frombuffer(bytes(encoded), dtype=np.uint8)
+        self._h = _C.lib().stf_rans_decoder_create(buf.ctypes.data, buf.size)
+        if not self._h:
+            raise ValueError("invalid rANS stream (need a multiple of 4 bytes, at least 8)")
+
+    def decode_stream_array(self, indexes, cdfs, cdfs_sizes=None, offsets=None) -> np.ndarray:
+        if not self._h:
+            raise ValueError("set_stream() first")
+        tab = _table(cdfs, cdfs_sizes, offsets)
+        ix = _as_i32(indexes).reshape(-1)
+        out = np.empty(ix.size, dtype=np.int32)
+        _C.check(_C.lib().stf_rans_decode(self._h, tab._h, ix.ctypes.data, ix.size, out.ctypes.data), "stf_rans_decode")
+        return out
+
+    def decode_stream(self, indexes, cdfs, cdfs_sizes=None, offsets=None):
+        return self.decode_stream_array(indexes, cdfs, cdfs_sizes, offsets).tolist()
+
+    def decode_with_indexes(self, encoded, indexes, cdfs, cdfs_sizes=None, offsets=None):
+        self.set_stream(encoded)
+        return self.decode_stream(indexes, cdfs, cdfs_sizes, offsets)
+
+
+def decode_batch(decoders, table: RansTable, indexes, outs=None, threads=None):
+    """Advance each decoder by len(indexes[i]) symbols in parallel; returns list of int32 arrays."""
+    count = len(decoders)
+    idxs = [_as_i32(i).reshape(-1) for i in indexes]
+    if outs is None:
+        outs = [np.empty(i.size, dtype=np.int32) for i in idxs]
+    VP, I64 = ctypes.c_void_p * count, ctypes.c_int64 * count
+    rc = _C.lib().stf_rans_decode_batch(VP(*[d._h for d in decoders]), table._h, count, VP(*[i.ctypes.data for i in idxs]),
+                                        I64(*[i.size for i in idxs]), VP(*[o.ctypes.data for o in outs]),
+                                        threads or default_threads())
+    _C.check(rc, "stf_rans_decode_batch")
+    return outs
+
+
+def pmf_to_quantized_cdf(pmf, precision: int = 16):
+    """compressai._CXX.pmf_to_quantized_cdf (cpp_exts/ops/ops.cpp:24-81): list[float] -> list[int]."""
+    p = np.ascontiguousarray(np.asarray(pmf, dtype=np.float32))
+    out = np.zeros(p.size + 1, dtype=np.uint32)
+    rc = _C.lib().stf_pmf_to_quantized_cdf(p.ctypes.data_as(_C._f32p), p.size, precision,
+                                           out.ctypes.data_as(ctypes.POINTER(ctypes.c_uint32)))
+    _C.check(rc, "stf_pmf_to_quantized_cdf")
+    return out.tolist()

@@ -1,0 +1,402 @@
+// Entropy-model element-wise kernels: single pass, HBM-bound,
+// 128-bit coalesced streaming accesses, no atomics (deterministic, batch-invariant).
+//
+//   stf_build_indexes            GaussianConditional.build_indexes  entropy_models.py:661-666
+//   stf_gaussian_compress_step   build_indexes + quantize("symbols") + dequantize, stf.py:717-719
+//   stf_quantize_symbols         EntropyModel.quantize               entropy_models.py:126-150
+//   stf_dequantize               EntropyModel.dequantize             entropy_models.py:158-165
+//   stf_gaussian_likelihood      GaussianConditional.forward (eval)  entropy_models.py:645-659
+//   stf_entropy_bottleneck       EntropyBottleneck.forward (eval)    entropy_models.py:446-489
+#include <math.h>
+
+#include "common.cuh"
+
+namespace stf {
+
+std::atomic<int64_t> g_launches{0};
+
+namespace {
+
+constexpr int kThreads = 256;
+constexpr int kVecPerThread = 4;  // 4 x float4 in flight per thread per stream
+
+// sigma = torch.max(x, bound): NaN propagates (fmaxf would drop it).
+__device__ __forceinline__ float lower_bound_f(float x, float bound) { return x < bound ? bound : x; }
+
+// idx = #{ i < levels-1 : table[i] < sigma }  ==  (levels-1) - #{ i : sigma <= table[i] }.
+// Monotone tables: 6-step branch-free binary search in shared memory; otherwise linear count.
+template <bool kMonotone>
+__device__ __forceinline__ int scale_index(float sigma, const float *__restrict__ t, int levels) {
+  const int last = levels - 1;
+  if (sigma != sigma) return last;
+  if (kMonotone) {
+    int lo = 0;
+#pragma unroll
+    for (int step = 32; step >= 1; step >>= 1) {
+      int probe = lo + step;
+      if (probe <= last && t[probe - 1] < sigma) lo = probe;
+    }
+    return lo;
+  } else {
+    int c = 0;
+    for (int i = 0; i < last; ++i) c += (t[i] < sigma) ? 1 : 0;
+    return c;
+  }
+}
+
+__device__ __forceinline__ int round_to_symbol(float v) { return __float2int_rn(v); }  // half-to-even
+
+struct SliceGeom {
+  int64_t inner;           // channels * plane, contiguous per batch element
+  int64_t y_batch_stride;  // of the (possibly larger) source tensor
+  int64_t out_batch_stride;
+};
+
+// ---------------------------------------------------------------------------------------------
+// compress step: (y, mu, scale) -> (symbols, indexes, y_hat)
+// ---------------------------------------------------------------------------------------------
+template <bool kVec, bool kMonotone>
+__global__ void __launch_bounds__(kThreads)
+compress_step_kernel(const float *__restrict__ y, const float *__restrict__ scales,
+                     const float *__restrict__ means, int32_t *__restrict__ symbols,
+                     int32_t *__restrict__ indexes, float *__restrict__ y_hat, SliceGeom g,
+                     float scale_bound, const __grid_constant__ ScaleTable table) {
+  __shared__ float t[64];
+  if (threadIdx.x < 64) t[threadIdx.x] = table.v[threadIdx.x < table.levels ? threadIdx.x : table.levels - 1];
+  __syncthreads();
+  const int b = blockIdx.y;
+  const float *yb = y ? y + (int64_t)b * g.y_batch_stride : nullptr;
+  const float *sb = scales ? scales + (int64_t)b * g.inner : nullptr;
+  const float *mb = means ? means + (int64_t)b * g.inner : nullptr;
+  int32_t *symb = symbols ? symbols + (int64_t)b * g.out_batch_stride : nullptr;
+  int32_t *idxb = indexes ? indexes + (int64_t)b * g.out_batch_stride : nullptr;
+  float *yhb = y_hat ? y_hat + (int64_t)b * g.inner : nullptr;
+
+  if (kVec) {
+    const int64_t nvec = g.inner >> 2;
+    const int64_t stride = (int64_t)gridDim.x * kThreads;
+    for (int64_t v0 = (int64_t)blockIdx.x * kThreads + threadIdx.x; v0 < nvec; v0 += stride * kVecPerThread) {
+      float4 yy[kVecPerThread], mm[kVecPerThread], ss[kVecPerThread];
+#pragma unroll
+      for (int u = 0; u < kVecPerThread; ++u) {
+        int64_t v = v0 + u * stride;
+        if (v < nvec) {
+          if (yb) yy[u] = ldg_stream(reinterpret_cast<const float4 *>(yb) + v);
+          mm[u] = mb ? ldg_stream(reinterpret_cast<const float4 *>(mb) + v) : make_float4(0.f, 0.f, 0.f, 0.f);
+          if (sb) ss[u] = ldg_stream(reinterpret_cast<const float4 *>(sb) + v);
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < kVecPerThread; ++u) {
+        int64_t v = v0 + u * stride;
+        if (v >= nvec) continue;
+        if (yb) {
+          int4 q;
+          q.x = round_to_symbol(yy[u].x - mm[u].x);
+          q.y = round_to_symbol(yy[u].y - mm[u].y);
+          q.z = round_to_symbol(yy[u].z - mm[u].z);
+          q.w = round_to_symbol(yy[u].w - mm[u].w);
+          if (symb) stg_stream(reinterpret_cast<int4 *>(symb) + v, q);
+          if (yhb)
+            stg_stream(reinterpret_cast<float4 *>(yhb) + v,
+                       make_float4((float)q.x + mm[u].x, (float)q.y + mm[u].y, (float)q.z + mm[u].z,
+                                   (float)q.w + mm[u].w));
+        }
+        if (sb && idxb) {
+          int4 ix;
+          ix.x = scale_index<kMonotone>(lower_bound_f(ss[u].x, scale_bound), t, table.levels);
+          ix.y = scale_index<kMonotone>(lower_bound_f(ss[u].y, scale_bound), t, table.levels);
+          ix.z = scale_index<kMonotone>(lower_bound_f(ss[u].z, scale_bound), t, table.levels);
+          ix.w = scale_index<kMonotone>(lower_bound_f(ss[u].w, scale_bound), t, table.levels);
+          stg_stream(reinterpret_cast<int4 *>(idxb) + v, ix);
+        }
+      }
+    }
+  } else {
+    const int64_t stride = (int64_t)gridDim.x * kThreads;
+    for (int64_t i = (int64_t)blockIdx.x * kThreads + threadIdx.x; i < g.inner; i += stride) {
+      float m = mb ? mb[i] : 0.f;
+      if (yb) {
+        int q = round_to_symbol(yb[i] - m);
+        if (symb) symb[i] = q;
+        if (yhb) yhb[i] = (float)q + m;
+      }
+      if (sb && idxb) idxb[i] = scale_index<kMonotone>(lower_bound_f(sb[i], scale_bound), t, table.levels);
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// dequantize: int32 symbols (+ strided batch) + means -> y_hat
+// ---------------------------------------------------------------------------------------------
+template <bool kVec>
+__global__ void __launch_bounds__(kThreads)
+dequantize_kernel(const int32_t *__restrict__ symbols, const float *__restrict__ means,
+                  float *__restrict__ y_hat, SliceGeom g) {
+  const int b = blockIdx.y;
+  const int32_t *sb = symbols + (int64_t)b * g.y_batch_stride;
+  const float *mb = means ? means + (int64_t)b * g.inner : nullptr;
+  float *ob = y_hat + (int64_t)b * g.inner;
+  const int64_t stride = (int64_t)gridDim.x * kThreads;
+  if (kVec) {
+    const int64_t nvec = g.inner >> 2;
+    for (int64_t v = (int64_t)blockIdx.x * kThreads + threadIdx.x; v < nvec; v += stride) {
+      int4 q = ldg_stream(reinterpret_cast<const int4 *>(sb) + v);
+      float4 m = mb ? ldg_stream(reinterpret_cast<const float4 *>(mb) + v) : make_float4(0.f, 0.f, 0.f, 0.f);
+      stg_stream(reinterpret_cast<float4 *>(ob) + v,
+                 make_float4((float)q.x + m.x, (float)q.y + m.y, (float)q.z + m.z, (float)q.w + m.w));
+    }
+  } else {
+    for (int64_t i = (int64_t)blockIdx.x * kThreads + threadIdx.x; i < g.inner; i += stride)
+      ob[i] = (float)sb[i] + (mb ? mb[i] : 0.f);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Gaussian likelihood (eval) fused with ste_round
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ float gauss_lik(float y, float mu, float scale, float scale_bound,
+                                           float lik_bound, float *y_hat_out) {
+  const float kNegInvSqrt2 = -0.70710678118654752440f;  // float(-(2 ** -0.5))
+  float yh = rintf(y - mu) + mu;                        // quantize(., "dequantize", means)
+  *y_hat_out = yh;
+  float v = fabsf(yh - mu);
+  float s = lower_bound_f(scale, scale_bound);
+  float upper = 0.5f * erfcf(kNegInvSqrt2 * ((0.5f - v) / s));
+  float lower = 0.5f * erfcf(kNegInvSqrt2 * ((-0.5f - v) / s));
+  return lower_bound_f(upper - lower, lik_bound);
+}
+
+template <bool kVec>
+__global__ void __launch_bounds__(kThreads)
+gaussian_likelihood_kernel(const float *__restrict__ y, const float *__restrict__ scales,
+                           const float *__restrict__ means, float *__restrict__ y_hat,
+                           float *__restrict__ lik, SliceGeom g, float scale_bound, float lik_bound) {
+  const int b = blockIdx.y;
+  const float *yb = y + (int64_t)b * g.y_batch_stride;
+  const float *sb = scales + (int64_t)b * g.inner;
+  const float *mb = means ? means + (int64_t)b * g.inner : nullptr;
+  float *yhb = y_hat ? y_hat + (int64_t)b * g.inner : nullptr;
+  float *lb = lik + (int64_t)b * g.inner;
+  const int64_t stride = (int64_t)gridDim.x * kThreads;
+  if (kVec) {
+    const int64_t nvec = g.inner >> 2;
+    constexpr int U = 2;
+    for (int64_t v0 = (int64_t)blockIdx.x * kThreads + threadIdx.x; v0 < nvec; v0 += stride * U) {
+      float4 yy[U], mm[U], ss[U];
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        int64_t v = v0 + u * stride;
+        if (v < nvec) {
+          yy[u] = ldg_stream(reinterpret_cast<const float4 *>(yb) + v);
+          ss[u] = ldg_stream(reinterpret_cast<const float4 *>(sb) + v);
+          mm[u] = mb ? ldg_stream(reinterpret_cast<const float4 *>(mb) + v) : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        int64_t v = v0 + u * stride;
+        if (v >= nvec) continue;
+        float4 h, l;
+        l.x = gauss_lik(yy[u].x, mm[u].x, ss[u].x, scale_bound, lik_bound, &h.x);
+        l.y = gauss_lik(yy[u].y, mm[u].y, ss[u].y, scale_bound, lik_bound, &h.y);
+        l.z = gauss_lik(yy[u].z, mm[u].z, ss[u].z, scale_bound, lik_bound, &h.z);
+        l.w = gauss_lik(yy[u].w, mm[u].w, ss[u].w, scale_bound, lik_bound, &h.w);
+        stg_stream(reinterpret_cast<float4 *>(lb) + v, l);
+        if (yhb) stg_stream(reinterpret_cast<float4 *>(yhb) + v, h);
+      }
+    }
+  } else {
+    for (int64_t i = (int64_t)blockIdx.x * kThreads + threadIdx.x; i < g.inner; i += stride) {
+      float h;
+      lb[i] = gauss_lik(yb[i], mb ? mb[i] : 0.f, sb[i], scale_bound, lik_bound, &h);
+      if (yhb) yhb[i] = h;
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Entropy bottleneck (factorised prior), eval mode.  One block = one (batch, channel) plane tile;
+// the 58 pre-activated parameters (+ median) of the channel sit in shared memory.
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ float eb_logits(float x, const float *__restrict__ p) {
+  // layer 0: 1 -> 3
+  float h0 = fmaf(p[0], x, p[3]), h1 = fmaf(p[1], x, p[4]), h2 = fmaf(p[2], x, p[5]);
+  h0 = fmaf(p[6], tanhf(h0), h0);
+  h1 = fmaf(p[7], tanhf(h1), h1);
+  h2 = fmaf(p[8], tanhf(h2), h2);
+  p += 9;
+#pragma unroll
+  for (int l = 0; l < 3; ++l) {  // layers 1..3: 3 -> 3
+    float g0 = p[0] * h0 + p[1] * h1 + p[2] * h2 + p[9];
+    float g1 = p[3] * h0 + p[4] * h1 + p[5] * h2 + p[10];
+    float g2 = p[6] * h0 + p[7] * h1 + p[8] * h2 + p[11];
+    h0 = fmaf(p[12], tanhf(g0), g0);
+    h1 = fmaf(p[13], tanhf(g1), g1);
+    h2 = fmaf(p[14], tanhf(g2), g2);
+    p += 15;
+  }
+  return p[0] * h0 + p[1] * h1 + p[2] * h2 + p[3];  // layer 4: 3 -> 1
+}
+
+__device__ __forceinline__ float sigmoidf_(float x) { return 1.0f / (1.0f + expf(-x)); }
+
+__global__ void __launch_bounds__(128)
+entropy_bottleneck_kernel(const float *__restrict__ z, const float *__restrict__ params,
+                          float *__restrict__ z_hat, float *__restrict__ lik,
+                          int32_t *__restrict__ symbols, int channels, int64_t plane, float lik_bound) {
+  __shared__ float p[STF_EB_PARAMS];
+  const int c = blockIdx.y, b = blockIdx.z;
+  if (threadIdx.x < STF_EB_PARAMS) p[threadIdx.x] = params[(int64_t)c * STF_EB_PARAMS + threadIdx.x];
+  __syncthreads();
+  const float median = p[STF_EB_MEDIAN_SLOT];
+  const int64_t base = ((int64_t)b * channels + c) * plane;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < plane; i += (int64_t)gridDim.x * blockDim.x) {
+    float r = rintf(z[base + i] - median);
+    float v = r + median;
+    if (symbols) symbols[base + i] = __float2int_rn(r);
+    if (z_hat) z_hat[base + i] = v;
+    if (lik) {
+      float lo = eb_logits(v - 0.5f, p), hi = eb_logits(v + 0.5f, p);
+      float sum = lo + hi;
+      float sgn = sum > 0.f ? -1.f : (sum < 0.f ? 1.f : 0.f);  // -torch.sign(lo + hi)
+      float l = fabsf(sigmoidf_(sgn * hi) - sigmoidf_(sgn * lo));
+      lik[base + i] = lower_bound_f(l, lik_bound);
+    }
+  }
+}
+
+__global__ void __launch_bounds__(kThreads)
+quantize_symbols_kernel(const float *__restrict__ x, const float *__restrict__ means,
+                        int32_t *__restrict__ symbols, int64_t n) {
+  const int64_t stride = (int64_t)gridDim.x * kThreads;
+  for (int64_t i = (int64_t)blockIdx.x * kThreads + threadIdx.x; i < n; i += stride)
+    symbols[i] = round_to_symbol(x[i] - (means ? means[i] : 0.f));
+}
+
+int fill_table(ScaleTable *t, const float *table_host, int levels) {
+  if (!table_host || levels < 1 || levels > 64) return STF_E_TABLE;
+  t->levels = levels;
+  t->monotone = 1;
+  for (int i = 0; i < 64; ++i) t->v[i] = table_host[i < levels ? i : levels - 1];
+  for (int i = 1; i < levels; ++i)
+    if (!(table_host[i] >= table_host[i - 1])) t->monotone = 0;
+  return STF_OK;
+}
+
+inline unsigned grid_x(int64_t work_items, int per_block, int batch) {
+  int64_t blocks = (work_items + per_block - 1) / per_block;
+  // enough CTAs to cover every SM several times, without one-vector-per-CTA grids on huge inputs
+  int64_t cap = (int64_t)kNumSMs * 16 / (batch > 0 ? batch : 1);
+  if (cap < 1) cap = 1;
+  if (blocks > cap) blocks = cap;
+  if (blocks < 1) blocks = 1;
+  return (unsigned)blocks;
+}
+
+bool vec_ok(int64_t inner, int64_t s1, int64_t s2, const void *a, const void *b, const void *c,
+            const void *d, const void *e, const void *f) {
+  return (inner % 4 == 0) && (s1 % 4 == 0) && (s2 % 4 == 0) && aligned16(a) && aligned16(b) &&
+         aligned16(c) && aligned16(d) && aligned16(e) && aligned16(f);
+}
+
+}  // namespace
+}  // namespace stf
+
+using namespace stf;
+
+extern "C" const char *stf_version(void) { return "stf_b200 0.1.0 sm_100a"; }
+extern "C" int64_t stf_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }
+
+extern "C" int stf_gaussian_compress_step(const float *y, int64_t y_batch_stride, const float *scales,
+                                          const float *means, int32_t *symbols, int32_t *indexes,
+                                          int64_t out_batch_stride, float *y_hat, int batch,
+                                          int channels, int64_t plane, const float *table_host,
+                                          int levels, float scale_bound, void *stream) {
+  if (batch < 0 || channels < 0 || plane < 0) return STF_E_ARG;
+  if (!y && !scales) return STF_E_ARG;
+  if (scales && indexes == nullptr && y == nullptr) return STF_E_ARG;
+  ScaleTable t;
+  if (scales) {
+    int rc = fill_table(&t, table_host, levels);
+    if (rc) return rc;
+  } else {
+    t.levels = 1;
+    t.monotone = 1;
+    for (float &v : t.v) v = 0.f;
+  }
+  SliceGeom g{(int64_t)channels * plane, y_batch_stride, out_batch_stride};
+  if (g.inner == 0 || batch == 0) return STF_OK;
+  bool vec = vec_ok(g.inner, y_batch_stride, out_batch_stride, y, scales, means, symbols, indexes, y_hat);
+  dim3 grid(grid_x(vec ? g.inner / 4 : g.inner, kThreads * (vec ? kVecPerThread : 1), batch), batch);
+  cudaStream_t st = (cudaStream_t)stream;
+#define LAUNCH(V, M) \
+  compress_step_kernel<V, M><<<grid, kThreads, 0, st>>>(y, scales, means, symbols, indexes, y_hat, g, scale_bound, t)
+  if (vec) {
+    if (t.monotone) LAUNCH(true, true); else LAUNCH(true, false);
+  } else {
+    if (t.monotone) LAUNCH(false, true); else LAUNCH(false, false);
+  }
+#undef LAUNCH
+  return check_launch();
+}
+
+extern "C" int stf_build_indexes(const float *scales, int32_t *indexes, int64_t n, const float *table_host,
+                                 int levels, float scale_bound, void *stream) {
+  if (!scales || !indexes || n < 0) return STF_E_ARG;
+  // one "batch" of n elements; chunk so that `plane` stays below 2^31 per call
+  return stf_gaussian_compress_step(nullptr, 0, scales, nullptr, nullptr, indexes, 0, nullptr, 1, 1, n,
+                                    table_host, levels, scale_bound, stream);
+}
+
+extern "C" int stf_quantize_symbols(const float *x, const float *means, int32_t *symbols, int64_t n,
+                                    void *stream) {
+  if (!x || !symbols || n < 0) return STF_E_ARG;
+  if (n == 0) return STF_OK;
+  quantize_symbols_kernel<<<grid_x(n, kThreads, 1), kThreads, 0, (cudaStream_t)stream>>>(x, means, symbols, n);
+  return check_launch();
+}
+
+extern "C" int stf_dequantize(const int32_t *symbols, int64_t sym_batch_stride, const float *means,
+                              float *y_hat, int batch, int channels, int64_t plane, void *stream) {
+  if (!symbols || !y_hat || batch < 0 || channels < 0 || plane < 0) return STF_E_ARG;
+  SliceGeom g{(int64_t)channels * plane, sym_batch_stride, 0};
+  if (g.inner == 0 || batch == 0) return STF_OK;
+  bool vec = vec_ok(g.inner, sym_batch_stride, 0, symbols, means, y_hat, nullptr, nullptr, nullptr);
+  dim3 grid(grid_x(vec ? g.inner / 4 : g.inner, kThreads, batch), batch);
+  if (vec)
+    dequantize_kernel<true><<<grid, kThreads, 0, (cudaStream_t)stream>>>(symbols, means, y_hat, g);
+  else
+    dequantize_kernel<false><<<grid, kThreads, 0, (cudaStream_t)stream>>>(symbols, means, y_hat, g);
+  return check_launch();
+}
+
+extern "C" int stf_gaussian_likelihood(const float *y, int64_t y_batch_stride, const float *scales,
+                                       const float *means, float *y_hat, float *likelihood, int batch,
+                                       int channels, int64_t plane, float scale_bound, float lik_bound,
+                                       void *stream) {
+  if (!y || !scales || !likelihood || batch < 0 || channels < 0 || plane < 0) return STF_E_ARG;
+  SliceGeom g{(int64_t)channels * plane, y_batch_stride, 0};
+  if (g.inner == 0 || batch == 0) return STF_OK;
+  bool vec = vec_ok(g.inner, y_batch_stride, 0, y, scales, means, y_hat, likelihood, nullptr);
+  dim3 grid(grid_x(vec ? g.inner / 4 : g.inner, kThreads * (vec ? 2 : 1), batch), batch);
+  if (vec)
+    gaussian_likelihood_kernel<true><<<grid, kThreads, 0, (cudaStream_t)stream>>>(
+        y, scales, means, y_hat, likelihood, g, scale_bound, lik_bound);
+  else
+    gaussian_likelihood_kernel<false><<<grid, kThreads, 0, (cudaStream_t)stream>>>(
+        y, scales, means, y_hat, likelihood, g, scale_bound, lik_bound);
+  return check_launch();
+}
+
+extern "C" int stf_entropy_bottleneck(const float *z, const float *params, float *z_hat, float *likelihood,
+                                      int32_t *symbols, int batch, int channels, int64_t plane,
+                                      float lik_bound, void *stream) {
+  if (!z || !params || batch < 0 || channels < 0 || plane < 0) return STF_E_ARG;
+  if (batch == 0 || channels == 0 || plane == 0) return STF_OK;
+  if (channels > 65535 || batch > 65535) return STF_E_SHAPE;
+  dim3 grid((unsigned)((plane + 127) / 128 > 64 ? 64 : (plane + 127) / 128), channels, batch);
+  entropy_bottleneck_kernel<<<grid, 128, 0, (cudaStream_t)stream>>>(z, params, z_hat, likelihood, symbols,
+                                                                   channels, plane, lik_bound);
+  return check_launch();
+}

@@ -1,0 +1,334 @@
+// Host-side rANS codec of libstf_b200 (CPU by design: rANS is a sequential integer state machine
+// and stays on the host in the reference too -- SURVEY.md section 2.1 / 8(f) rank 1).
+//
+// Bit-exact replacement of compressai.ans:
+//   BufferedRansEncoder / RansEncoder   compressai/cpp_exts/rans/rans_interface.cpp:99-204
+//   RansDecoder                         compressai/cpp_exts/rans/rans_interface.cpp:206-350
+//   rANS64 state machine                third_party/ryg_rans/rans64.h:59-142
+//   pmf_to_quantized_cdf                compressai/cpp_exts/ops/ops.cpp:24-81
+//
+// What differs from the reference (the stream does not):
+//   - int32 buffers in, bytes out: no Python lists, no per-call conversion of the 64x3133 table;
+//   - the encoder walks the symbols backwards and emits directly (no staged symbol vector);
+//   - x / freq is an exact multiply-shift with a per-symbol 64-bit reciprocal;
+//   - the decoder finds the symbol through a 256-bucket LUT per CDF row instead of a linear scan;
+//   - independent streams (one per image) are coded on separate host threads.
+#include <stdlib.h>
+#include <string.h>
+
+#include <cmath>
+#include <new>
+#include <thread>
+#include <vector>
+
+#include "../../include/stf_b200.h"
+
+namespace {
+
+constexpr uint32_t kProbBits = 16;
+constexpr uint32_t kProbScale = 1u << kProbBits;
+constexpr uint32_t kNibbleBits = 4;
+constexpr int32_t kNibbleMax = 15;
+constexpr uint64_t kLow = 1ull << 31;  // RANS64_L
+constexpr int kLutBits = 8;
+
+struct EncEntry {
+  uint64_t rcp;       // ceil(2^(63+shift) / freq), freq >= 2
+  uint32_t x_max_hi;  // renormalise when (x >> 47) >= freq  <=>  x >= 2^47 * freq
+  uint32_t start;
+  uint32_t cmpl;      // 65536 - freq
+  uint32_t shift;     // ceil(log2 freq) - 1; 0xFFFFFFFF marks freq == 1
+};
+
+}  // namespace
+
+struct stf_rans_table {
+  int rows = 0;
+  std::vector<int32_t> sizes, offsets;
+  std::vector<uint32_t> base;   // first entry of each row in enc / cdf
+  std::vector<EncEntry> enc;    // one per (row, symbol)
+  std::vector<uint32_t> cdf;    // flattened valid CDF entries, row r: cdf[base[r] + r .. + sizes[r])
+  std::vector<uint32_t> cbase;  // first cdf entry of each row
+  std::vector<uint16_t> lut;    // rows * 256: symbol holding cumulative value (bucket << 8)
+};
+
+struct stf_rans_decoder {
+  uint64_t x = 0;
+  const uint32_t *w = nullptr, *end = nullptr;
+  std::vector<uint32_t> words;
+};
+
+namespace {
+
+inline void make_entry(EncEntry *e, uint32_t start, uint32_t freq) {
+  e->start = start;
+  e->cmpl = kProbScale - freq;
+  e->x_max_hi = freq;
+  if (freq < 2) {
+    e->rcp = 0;
+    e->shift = 0xFFFFFFFFu;
+    return;
+  }
+  uint32_t sh = 0;
+  while (freq > (1u << sh)) ++sh;  // sh = ceil(log2 freq) >= 1
+  unsigned __int128 num = ((unsigned __int128)1 << (63 + sh)) + (freq - 1);
+  e->rcp = (uint64_t)(num / freq);
+  e->shift = sh - 1;
+}
+
+// x <- C(s, x) for a modelled symbol; identical state sequence to Rans64EncPut (rans64.h:77-93).
+inline void put_symbol(uint64_t &x, uint32_t *&w, const EncEntry &e) {
+  if ((x >> 47) >= e.x_max_hi) {  // x >= ((L >> 16) << 32) * freq
+    *--w = (uint32_t)x;
+    x >>= 32;
+  }
+  uint64_t q;
+  if (e.shift == 0xFFFFFFFFu)
+    q = x;
+  else
+    q = (uint64_t)(((unsigned __int128)x * e.rcp) >> 64) >> e.shift;
+  x = x + e.start + q * e.cmpl;
+}
+
+// Raw 4-bit value (Rans64EncPutBits, rans_interface.cpp:59-77): freq = 2^12, x_max = 2^59.
+inline void put_nibble(uint64_t &x, uint32_t *&w, uint32_t val) {
+  if (x >= (1ull << 59)) {
+    *--w = (uint32_t)x;
+    x >>= 32;
+  }
+  x = (x << kNibbleBits) | val;
+}
+
+int64_t encode_into(const stf_rans_table *t, const int32_t *symbols, const int32_t *indexes, int64_t n,
+                    uint32_t *buf_end) {
+  uint32_t *w = buf_end;
+  uint64_t x = kLow;
+  for (int64_t i = n - 1; i >= 0; --i) {
+    const int32_t row = indexes[i];
+    if (row < 0 || row >= t->rows) return STF_E_ARG;
+    const int32_t escape = t->sizes[row] - 2;
+    int32_t v = symbols[i] - t->offsets[row];
+    if (v >= 0 && v < escape) {
+      put_symbol(x, w, t->enc[t->base[row] + v]);
+      continue;
+    }
+    // escape: staged order is [escape symbol][count nibbles][value nibbles]; emit it reversed
+    uint32_t raw = v < 0 ? (uint32_t)(-2 * v - 1) : (uint32_t)(2 * (v - escape));
+    int32_t nn = 0;
+    while ((raw >> (nn * kNibbleBits)) != 0) ++nn;
+    for (int32_t j = nn - 1; j >= 0; --j) put_nibble(x, w, (raw >> (j * kNibbleBits)) & kNibbleMax);
+    int32_t full = nn / kNibbleMax, rest = nn % kNibbleMax;  // count = 15,15,...,rest
+    put_nibble(x, w, (uint32_t)rest);
+    for (int32_t j = 0; j < full; ++j) put_nibble(x, w, kNibbleMax);
+    put_symbol(x, w, t->enc[t->base[row] + escape]);
+  }
+  *--w = (uint32_t)(x >> 32);  // Rans64EncFlush: low word first in memory
+  *--w = (uint32_t)x;
+  return (int64_t)(buf_end - w) * 4;
+}
+
+inline bool refill(stf_rans_decoder *d, uint64_t &x) {
+  if (x < kLow) {
+    if (d->w >= d->end) return false;
+    x = (x << 32) | *d->w++;
+  }
+  return true;
+}
+
+inline bool get_nibble(stf_rans_decoder *d, uint64_t &x, int32_t *val) {
+  *val = (int32_t)(x & ((1u << kNibbleBits) - 1));
+  x >>= kNibbleBits;
+  return refill(d, x);
+}
+
+int decode_run(stf_rans_decoder *d, const stf_rans_table *t, const int32_t *indexes, int64_t n, int32_t *out) {
+  uint64_t x = d->x;
+  for (int64_t i = 0; i < n; ++i) {
+    const int32_t row = indexes[i];
+    if (row < 0 || row >= t->rows) return STF_E_ARG;
+    const uint32_t *cdf = t->cdf.data() + t->cbase[row];
+    const int32_t escape = t->sizes[row] - 2;
+    const uint32_t cum = (uint32_t)x & (kProbScale - 1);
+    uint32_t s = t->lut[(size_t)row * (1 << kLutBits) + (cum >> (kProbBits - kLutBits))];
+    while (cdf[s + 1] <= cum) ++s;
+    const uint32_t start = cdf[s], freq = cdf[s + 1] - start;
+    x = freq * (x >> kProbBits) + cum - start;  // Rans64DecAdvance, rans64.h:126-142
+    if (!refill(d, x)) return STF_E_STREAM;
+    int32_t v = (int32_t)s;
+    if (v == escape) {  // rans_interface.cpp:320-343
+      int32_t nib, nn;
+      if (!get_nibble(d, x, &nib)) return STF_E_STREAM;
+      nn = nib;
+      while (nib == kNibbleMax) {
+        if (!get_nibble(d, x, &nib)) return STF_E_STREAM;
+        nn += nib;
+      }
+      int32_t raw = 0;
+      for (int32_t j = 0; j < nn; ++j) {
+        if (!get_nibble(d, x, &nib)) return STF_E_STREAM;
+        if (j < 8) raw |= nib << (j * kNibbleBits);
+      }
+      v = raw >> 1;
+      v = (raw & 1) ? -v - 1 : v + escape;
+    }
+    out[i] = v + t->offsets[row];
+  }
+  d->x = x;
+  return STF_OK;
+}
+
+template <class F>
+void parallel_for(int count, int threads, F f) {
+  if (threads > count) threads = count;
+  if (threads <= 1) {
+    for (int i = 0; i < count; ++i) f(i);
+    return;
+  }
+  std::vector<std::thread> pool;
+  pool.reserve(threads);
+  for (int tid = 0; tid < threads; ++tid)
+    pool.emplace_back([=] {
+      for (int i = tid; i < count; i += threads) f(i);
+    });
+  for (auto &th : pool) th.join();
+}
+
+}  // namespace
+
+extern "C" stf_rans_table *stf_rans_table_create(const int32_t *cdf, int rows, int row_stride,
+                                                 const int32_t *sizes, const int32_t *offsets) {
+  if (!cdf || !sizes || !offsets || rows <= 0 || row_stride < 2) return nullptr;
+  stf_rans_table *t = new (std::nothrow) stf_rans_table;
+  if (!t) return nullptr;
+  t->rows = rows;
+  t->sizes.assign(sizes, sizes + rows);
+  t->offsets.assign(offsets, offsets + rows);
+  t->base.resize(rows);
+  t->cbase.resize(rows);
+  t->lut.assign((size_t)rows << kLutBits, 0);
+  for (int r = 0; r < rows; ++r) {
+    const int32_t *c = cdf + (size_t)r * row_stride;
+    const int sz = sizes[r];
+    bool ok = sz >= 2 && sz <= row_stride && sz <= 65537 && c[0] == 0 && c[sz - 1] == (int32_t)kProbScale;
+    for (int j = 0; ok && j + 1 < sz; ++j) ok = c[j + 1] > c[j];
+    if (!ok) {
+      delete t;
+      return nullptr;
+    }
+    t->base[r] = (uint32_t)t->enc.size();
+    t->cbase[r] = (uint32_t)t->cdf.size();
+    for (int j = 0; j < sz; ++j) t->cdf.push_back((uint32_t)c[j]);
+    for (int j = 0; j + 1 < sz; ++j) {
+      EncEntry e;
+      make_entry(&e, (uint32_t)c[j], (uint32_t)(c[j + 1] - c[j]));
+      t->enc.push_back(e);
+    }
+    uint32_t s = 0;
+    for (uint32_t b = 0; b < (1u << kLutBits); ++b) {
+      const uint32_t cum = b << (kProbBits - kLutBits);
+      while ((uint32_t)c[s + 1] <= cum) ++s;
+      t->lut[((size_t)r << kLutBits) + b] = (uint16_t)s;
+    }
+  }
+  return t;
+}
+
+extern "C" void stf_rans_table_destroy(stf_rans_table *t) { delete t; }
+
+extern "C" int64_t stf_rans_encode_bound(int64_t n) { return n < 0 ? STF_E_ARG : 8 * n + 64; }
+
+extern "C" int64_t stf_rans_encode(const stf_rans_table *t, const int32_t *symbols, const int32_t *indexes,
+                                   int64_t n, uint8_t *out, int64_t out_cap) {
+  if (!t || !out || n < 0 || (n > 0 && (!symbols || !indexes))) return STF_E_ARG;
+  const int64_t bound = stf_rans_encode_bound(n);
+  if (out_cap >= bound && ((uintptr_t)out & 3u) == 0) {  // code straight into the caller's buffer
+    uint32_t *end = reinterpret_cast<uint32_t *>(out) + out_cap / 4;
+    int64_t nb = encode_into(t, symbols, indexes, n, end);
+    if (nb < 0) return nb;
+    memmove(out, reinterpret_cast<uint8_t *>(end) - nb, (size_t)nb);
+    return nb;
+  }
+  std::vector<uint32_t> tmp((size_t)bound / 4);
+  int64_t nb = encode_into(t, symbols, indexes, n, tmp.data() + tmp.size());
+  if (nb < 0) return nb;
+  if (nb > out_cap) return STF_E_OVERFLOW;
+  memcpy(out, reinterpret_cast<uint8_t *>(tmp.data() + tmp.size()) - nb, (size_t)nb);
+  return nb;
+}
+
+extern "C" int stf_rans_encode_batch(const stf_rans_table *t, int count, const int32_t *const *symbols,
+                                     const int32_t *const *indexes, const int64_t *n, uint8_t *const *out,
+                                     const int64_t *out_cap, int64_t *out_lens, int threads) {
+  if (!t || count < 0 || !symbols || !indexes || !n || !out || !out_cap || !out_lens) return STF_E_ARG;
+  parallel_for(count, threads,
+               [&](int i) { out_lens[i] = stf_rans_encode(t, symbols[i], indexes[i], n[i], out[i], out_cap[i]); });
+  for (int i = 0; i < count; ++i)
+    if (out_lens[i] < 0) return (int)out_lens[i];
+  return STF_OK;
+}
+
+extern "C" stf_rans_decoder *stf_rans_decoder_create(const uint8_t *stream, int64_t nbytes) {
+  if (!stream || nbytes < 8 || (nbytes & 3)) return nullptr;
+  stf_rans_decoder *d = new (std::nothrow) stf_rans_decoder;
+  if (!d) return nullptr;
+  d->words.resize((size_t)nbytes / 4);
+  memcpy(d->words.data(), stream, (size_t)nbytes);
+  d->w = d->words.data();
+  d->end = d->w + d->words.size();
+  d->x = (uint64_t)d->w[0] | ((uint64_t)d->w[1] << 32);  // Rans64DecInit, rans64.h:107-115
+  d->w += 2;
+  return d;
+}
+
+extern "C" void stf_rans_decoder_destroy(stf_rans_decoder *d) { delete d; }
+
+extern "C" int stf_rans_decode(stf_rans_decoder *d, const stf_rans_table *t, const int32_t *indexes, int64_t n,
+                               int32_t *symbols_out) {
+  if (!d || !t || n < 0 || (n > 0 && (!indexes || !symbols_out))) return STF_E_ARG;
+  return decode_run(d, t, indexes, n, symbols_out);
+}
+
+extern "C" int stf_rans_decode_batch(stf_rans_decoder *const *d, const stf_rans_table *t, int count,
+                                     const int32_t *const *indexes, const int64_t *n,
+                                     int32_t *const *symbols_out, int threads) {
+  if (!d || !t || count < 0 || !indexes || !n || !symbols_out) return STF_E_ARG;
+  std::vector<int> rc((size_t)count, 0);
+  parallel_for(count, threads, [&](int i) { rc[i] = stf_rans_decode(d[i], t, indexes[i], n[i], symbols_out[i]); });
+  for (int i = 0; i < count; ++i)
+    if (rc[i]) return rc[i];
+  return STF_OK;
+}
+
+extern "C" int stf_pmf_to_quantized_cdf(const float *pmf, int n, int precision, uint32_t *cdf) {
+  if (!pmf || !cdf || n < 1 || precision < 1 || precision > 16) return STF_E_ARG;
+  const int m = n + 1;
+  const uint32_t scale = 1u << precision;
+  cdf[0] = 0;
+  uint32_t total = 0;
+  for (int i = 0; i < n; ++i) {
+    cdf[i + 1] = (uint32_t)std::round(pmf[i] * (float)scale);
+    total += cdf[i + 1];
+  }
+  if (total == 0) return STF_E_TABLE;
+  uint32_t run = 0;
+  for (int i = 0; i < m; ++i) {
+    run += (uint32_t)(((uint64_t)scale * cdf[i]) / total);
+    cdf[i] = run;
+  }
+  cdf[m - 1] = scale;
+  for (int i = 0; i + 1 < m; ++i) {
+    if (cdf[i] != cdf[i + 1]) continue;
+    uint32_t best = ~0u;  // cheapest donor with more than one count (ops.cpp:52-60)
+    int donor = -1;
+    for (int j = 0; j + 1 < m; ++j) {
+      uint32_t f = cdf[j + 1] - cdf[j];
+      if (f > 1 && f < best) best = f, donor = j;
+    }
+    if (donor < 0) return STF_E_TABLE;
+    if (donor < i)
+      for (int j = donor + 1; j <= i; ++j) cdf[j]--;
+    else
+      for (int j = i + 1; j <= donor; ++j) cdf[j]++;
+  }
+  return STF_OK;
+}
