@@ -70,6 +70,10 @@ int stf_gaussian_compress_step(const float *y, int64_t y_batch_stride, const flo
 int stf_quantize_symbols(const float *x, const float *means, int32_t *symbols, int64_t n,
                          void *stream);
 
+/* EntropyModel.quantize(x, "dequantize", means): out = round_half_even(x - means) + means, kept in
+ * fp32 (no int32 round trip, like torch.round; entropy_models.py:137-146); means may be NULL. */
+int stf_quantize_dequantize(const float *x, const float *means, float *out, int64_t n, void *stream);
+
 /* EntropyModel.dequantize (entropy_models.py:158-165) for one decoded slice:
  *   y_hat[b,c,p] = float(symbols[b * sym_batch_stride + c * plane + p]) + means[b,c,p] */
 int stf_dequantize(const int32_t *symbols, int64_t sym_batch_stride, const float *means,
@@ -80,11 +84,14 @@ int stf_dequantize(const int32_t *symbols, int64_t sym_batch_stride, const float
  *   y_hat = round_half_even(y - means) + means
  *   v = |y_hat - means|; sigma = max(scales, scale_bound)
  *   lik = max( 0.5*erfc(-(0.5 - v)/sigma/sqrt2) - 0.5*erfc(-(-0.5 - v)/sigma/sqrt2), lik_bound )
- * y is addressed like in stf_gaussian_compress_step; y_hat may be NULL.  16-20 B/element. */
+ * y is addressed like in stf_gaussian_compress_step; y_hat may be NULL.  16-20 B/element.
+ * ste_round != 0: y_hat is the forward value of `ste_round(y - means) + means`, i.e.
+ * ((round(t) - t) + t) + means evaluated left to right (ops/ops.py:34), which can differ from
+ * round(t) + means in the last bit; the likelihood always uses round(t) + means. */
 int stf_gaussian_likelihood(const float *y, int64_t y_batch_stride, const float *scales,
                             const float *means, float *y_hat, float *likelihood, int batch,
                             int channels, int64_t plane, float scale_bound, float lik_bound,
-                            void *stream);
+                            int ste_round, void *stream);
 
 /* EntropyBottleneck.forward in eval mode (entropy_models.py:446-489, 400-433) without the two
  * permutes: z is (batch, channels, plane) NCHW.  `params` is a device array of
@@ -93,12 +100,13 @@ int stf_gaussian_likelihood(const float *y, int64_t y_batch_stride, const float 
  *   (58 values) then [median][0 pad] -> STF_EB_PARAMS = 60 floats per channel
  *   z_hat = round_half_even(z - median) + median;  lik = max(|sig(s*u) - sig(s*l)|, lik_bound)
  * Optionally also emits int32 symbols = round(z - median) (EntropyBottleneck.compress path,
- * entropy_models.py:508-515).  z_hat / likelihood / symbols may each be NULL. */
+ * entropy_models.py:508-515).  z_hat / likelihood / symbols may each be NULL.  ste_round as in
+ * stf_gaussian_likelihood (stf.py:602-604). */
 #define STF_EB_PARAMS 60
 #define STF_EB_MEDIAN_SLOT 58
 int stf_entropy_bottleneck(const float *z, const float *params, float *z_hat, float *likelihood,
                            int32_t *symbols, int batch, int channels, int64_t plane,
-                           float lik_bound, void *stream);
+                           float lik_bound, int ste_round, void *stream);
 
 /* ------------------------------------------------------------------------------------------
  * Window-attention path (tensor-core bound).
@@ -176,9 +184,12 @@ int stf_linear(const stf_linear_args *args, void *stream);
  * scaled; out: (num_windows_total * N, C) head-major concat.  N = ws*ws in {16, 64},
  * d = C / heads in {16, 24, 32, 40}.  The shifted-window mask ({0,-100}, stf.py:316-334) is
  * computed analytically from the window position when shift > 0: windows are numbered
- * image-major then row-major over the (Hp/ws, Wp/ws) grid. */
-int stf_window_attention(const float *qkv, float *out, const float *bias_table, int64_t num_windows,
-                         int C, int heads, int ws, int shift, int Hp, int Wp, void *stream);
+ * image-major then row-major over the (Hp/ws, Wp/ws) grid.  Independently, `mask` may point to an
+ * explicit additive (mask_windows, N, N) fp32 tensor applied as mask[window % mask_windows]
+ * (the WindowAttention.forward(x, mask) signature, stf.py:108-110); NULL = none. */
+int stf_window_attention(const float *qkv, float *out, const float *bias_table, const float *mask,
+                         int mask_windows, int64_t num_windows, int C, int heads, int ws, int shift,
+                         int Hp, int Wp, void *stream);
 
 /* ------------------------------------------------------------------------------------------
  * Host-side rANS codec (CPU; replaces compressai.ans, cpp_exts/rans/rans_interface.cpp:99-350,

@@ -45,13 +45,14 @@ SIGNATURES = {
     "stf_gaussian_compress_step": (c_int, [c_vp, c_i64, c_vp, c_vp, c_vp, c_vp, c_i64, c_vp, c_int, c_int, c_i64,
                                            _f32p, c_int, c_f32, c_vp]),
     "stf_quantize_symbols": (c_int, [c_vp, c_vp, c_vp, c_i64, c_vp]),
+    "stf_quantize_dequantize": (c_int, [c_vp, c_vp, c_vp, c_i64, c_vp]),
     "stf_dequantize": (c_int, [c_vp, c_i64, c_vp, c_vp, c_int, c_int, c_i64, c_vp]),
-    "stf_gaussian_likelihood": (c_int, [c_vp, c_i64, c_vp, c_vp, c_vp, c_vp, c_int, c_int, c_i64, c_f32, c_f32, c_vp]),
-    "stf_entropy_bottleneck": (c_int, [c_vp, c_vp, c_vp, c_vp, c_vp, c_int, c_int, c_i64, c_f32, c_vp]),
+    "stf_gaussian_likelihood": (c_int, [c_vp, c_i64, c_vp, c_vp, c_vp, c_vp, c_int, c_int, c_i64, c_f32, c_f32, c_int, c_vp]),
+    "stf_entropy_bottleneck": (c_int, [c_vp, c_vp, c_vp, c_vp, c_vp, c_int, c_int, c_i64, c_f32, c_int, c_vp]),
     "stf_linear_n_tile": (c_int, [c_int]),
     "stf_pack_linear_weight": (c_int, [c_vp, c_vp, c_int, c_int, c_vp]),
     "stf_linear": (c_int, [ctypes.POINTER(LinearArgs), c_vp]),
-    "stf_window_attention": (c_int, [c_vp, c_vp, c_vp, c_i64, c_int, c_int, c_int, c_int, c_int, c_int, c_vp]),
+    "stf_window_attention": (c_int, [c_vp, c_vp, c_vp, c_vp, c_int, c_i64, c_int, c_int, c_int, c_int, c_int, c_int, c_vp]),
     "stf_rans_table_create": (c_vp, [_i32p, c_int, c_int, _i32p, _i32p]),
     "stf_rans_table_destroy": (None, [c_vp]),
     "stf_rans_encode_bound": (c_i64, [c_i64]),
@@ -81,11 +82,6 @@ def lib():
         for name, (res, args) in SIGNATURES.items():
             fn = getattr(L, name)
             fn.restype, fn.argtypes = res, args
-        try:
-            dbg = L.stf_linear_debug
-            dbg.restype, dbg.argtypes = c_int, [ctypes.POINTER(LinearArgs), c_int, c_vp]
-        except AttributeError:
-            pass
         _lib = L
     return _lib
 

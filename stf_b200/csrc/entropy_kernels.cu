@@ -155,11 +155,15 @@ dequantize_kernel(const int32_t *__restrict__ symbols, const float *__restrict__
 // ---------------------------------------------------------------------------------------------
 // Gaussian likelihood (eval) fused with ste_round
 // ---------------------------------------------------------------------------------------------
+template <bool kSte>
 __device__ __forceinline__ float gauss_lik(float y, float mu, float scale, float scale_bound,
                                            float lik_bound, float *y_hat_out) {
   const float kNegInvSqrt2 = -0.70710678118654752440f;  // float(-(2 ** -0.5))
-  float yh = rintf(y - mu) + mu;                        // quantize(., "dequantize", means)
-  *y_hat_out = yh;
+  const float t = y - mu;
+  const float r = rintf(t);
+  float yh = r + mu;                                    // quantize(., "dequantize", means)
+  // ste_round(t) + mu evaluates round(t) - t + t left to right (ops/ops.py:34, stf.py:626)
+  *y_hat_out = kSte ? ((r - t) + t) + mu : yh;
   float v = fabsf(yh - mu);
   float s = lower_bound_f(scale, scale_bound);
   float upper = 0.5f * erfcf(kNegInvSqrt2 * ((0.5f - v) / s));
@@ -167,7 +171,7 @@ __device__ __forceinline__ float gauss_lik(float y, float mu, float scale, float
   return lower_bound_f(upper - lower, lik_bound);
 }
 
-template <bool kVec>
+template <bool kVec, bool kSte>
 __global__ void __launch_bounds__(kThreads)
 gaussian_likelihood_kernel(const float *__restrict__ y, const float *__restrict__ scales,
                            const float *__restrict__ means, float *__restrict__ y_hat,
@@ -198,10 +202,10 @@ gaussian_likelihood_kernel(const float *__restrict__ y, const float *__restrict_
         int64_t v = v0 + u * stride;
         if (v >= nvec) continue;
         float4 h, l;
-        l.x = gauss_lik(yy[u].x, mm[u].x, ss[u].x, scale_bound, lik_bound, &h.x);
-        l.y = gauss_lik(yy[u].y, mm[u].y, ss[u].y, scale_bound, lik_bound, &h.y);
-        l.z = gauss_lik(yy[u].z, mm[u].z, ss[u].z, scale_bound, lik_bound, &h.z);
-        l.w = gauss_lik(yy[u].w, mm[u].w, ss[u].w, scale_bound, lik_bound, &h.w);
+        l.x = gauss_lik<kSte>(yy[u].x, mm[u].x, ss[u].x, scale_bound, lik_bound, &h.x);
+        l.y = gauss_lik<kSte>(yy[u].y, mm[u].y, ss[u].y, scale_bound, lik_bound, &h.y);
+        l.z = gauss_lik<kSte>(yy[u].z, mm[u].z, ss[u].z, scale_bound, lik_bound, &h.z);
+        l.w = gauss_lik<kSte>(yy[u].w, mm[u].w, ss[u].w, scale_bound, lik_bound, &h.w);
         stg_stream(reinterpret_cast<float4 *>(lb) + v, l);
         if (yhb) stg_stream(reinterpret_cast<float4 *>(yhb) + v, h);
       }
@@ -209,7 +213,7 @@ gaussian_likelihood_kernel(const float *__restrict__ y, const float *__restrict_
   } else {
     for (int64_t i = (int64_t)blockIdx.x * kThreads + threadIdx.x; i < g.inner; i += stride) {
       float h;
-      lb[i] = gauss_lik(yb[i], mb ? mb[i] : 0.f, sb[i], scale_bound, lik_bound, &h);
+      lb[i] = gauss_lik<kSte>(yb[i], mb ? mb[i] : 0.f, sb[i], scale_bound, lik_bound, &h);
       if (yhb) yhb[i] = h;
     }
   }
@@ -244,7 +248,8 @@ __device__ __forceinline__ float sigmoidf_(float x) { return 1.0f / (1.0f + expf
 __global__ void __launch_bounds__(128)
 entropy_bottleneck_kernel(const float *__restrict__ z, const float *__restrict__ params,
                           float *__restrict__ z_hat, float *__restrict__ lik,
-                          int32_t *__restrict__ symbols, int channels, int64_t plane, float lik_bound) {
+                          int32_t *__restrict__ symbols, int channels, int64_t plane, float lik_bound,
+                          int ste_round) {
   __shared__ float p[STF_EB_PARAMS];
   const int c = blockIdx.y, b = blockIdx.z;
   if (threadIdx.x < STF_EB_PARAMS) p[threadIdx.x] = params[(int64_t)c * STF_EB_PARAMS + threadIdx.x];
@@ -252,10 +257,11 @@ entropy_bottleneck_kernel(const float *__restrict__ z, const float *__restrict__
   const float median = p[STF_EB_MEDIAN_SLOT];
   const int64_t base = ((int64_t)b * channels + c) * plane;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < plane; i += (int64_t)gridDim.x * blockDim.x) {
-    float r = rintf(z[base + i] - median);
+    const float t = z[base + i] - median;
+    float r = rintf(t);
     float v = r + median;
     if (symbols) symbols[base + i] = __float2int_rn(r);
-    if (z_hat) z_hat[base + i] = v;
+    if (z_hat) z_hat[base + i] = ste_round ? ((r - t) + t) + median : v;  // ops/ops.py:34, stf.py:602-604
     if (lik) {
       float lo = eb_logits(v - 0.5f, p), hi = eb_logits(v + 0.5f, p);
       float sum = lo + hi;
@@ -272,6 +278,16 @@ quantize_symbols_kernel(const float *__restrict__ x, const float *__restrict__ m
   const int64_t stride = (int64_t)gridDim.x * kThreads;
   for (int64_t i = (int64_t)blockIdx.x * kThreads + threadIdx.x; i < n; i += stride)
     symbols[i] = round_to_symbol(x[i] - (means ? means[i] : 0.f));
+}
+
+__global__ void __launch_bounds__(kThreads)
+quantize_dequantize_kernel(const float *__restrict__ x, const float *__restrict__ means,
+                           float *__restrict__ out, int64_t n) {
+  const int64_t stride = (int64_t)gridDim.x * kThreads;
+  for (int64_t i = (int64_t)blockIdx.x * kThreads + threadIdx.x; i < n; i += stride) {
+    const float m = means ? means[i] : 0.f;
+    out[i] = rintf(x[i] - m) + m;
+  }
 }
 
 int fill_table(ScaleTable *t, const float *table_host, int levels) {
@@ -357,6 +373,14 @@ extern "C" int stf_quantize_symbols(const float *x, const float *means, int32_t 
   return check_launch();
 }
 
+extern "C" int stf_quantize_dequantize(const float *x, const float *means, float *out, int64_t n,
+                                       void *stream) {
+  if (!x || !out || n < 0) return STF_E_ARG;
+  if (n == 0) return STF_OK;
+  quantize_dequantize_kernel<<<grid_x(n, kThreads, 1), kThreads, 0, (cudaStream_t)stream>>>(x, means, out, n);
+  return check_launch();
+}
+
 extern "C" int stf_dequantize(const int32_t *symbols, int64_t sym_batch_stride, const float *means,
                               float *y_hat, int batch, int channels, int64_t plane, void *stream) {
   if (!symbols || !y_hat || batch < 0 || channels < 0 || plane < 0) return STF_E_ARG;
@@ -374,29 +398,32 @@ extern "C" int stf_dequantize(const int32_t *symbols, int64_t sym_batch_stride, 
 extern "C" int stf_gaussian_likelihood(const float *y, int64_t y_batch_stride, const float *scales,
                                        const float *means, float *y_hat, float *likelihood, int batch,
                                        int channels, int64_t plane, float scale_bound, float lik_bound,
-                                       void *stream) {
+                                       int ste_round, void *stream) {
   if (!y || !scales || !likelihood || batch < 0 || channels < 0 || plane < 0) return STF_E_ARG;
   SliceGeom g{(int64_t)channels * plane, y_batch_stride, 0};
   if (g.inner == 0 || batch == 0) return STF_OK;
   bool vec = vec_ok(g.inner, y_batch_stride, 0, y, scales, means, y_hat, likelihood, nullptr);
   dim3 grid(grid_x(vec ? g.inner / 4 : g.inner, kThreads * (vec ? 2 : 1), batch), batch);
-  if (vec)
-    gaussian_likelihood_kernel<true><<<grid, kThreads, 0, (cudaStream_t)stream>>>(
-        y, scales, means, y_hat, likelihood, g, scale_bound, lik_bound);
-  else
-    gaussian_likelihood_kernel<false><<<grid, kThreads, 0, (cudaStream_t)stream>>>(
-        y, scales, means, y_hat, likelihood, g, scale_bound, lik_bound);
+#define LAUNCH(V, S)                                                              \
+  gaussian_likelihood_kernel<V, S><<<grid, kThreads, 0, (cudaStream_t)stream>>>( \
+      y, scales, means, y_hat, likelihood, g, scale_bound, lik_bound)
+  if (vec) {
+    if (ste_round) LAUNCH(true, true); else LAUNCH(true, false);
+  } else {
+    if (ste_round) LAUNCH(false, true); else LAUNCH(false, false);
+  }
+#undef LAUNCH
   return check_launch();
 }
 
 extern "C" int stf_entropy_bottleneck(const float *z, const float *params, float *z_hat, float *likelihood,
                                       int32_t *symbols, int batch, int channels, int64_t plane,
-                                      float lik_bound, void *stream) {
+                                      float lik_bound, int ste_round, void *stream) {
   if (!z || !params || batch < 0 || channels < 0 || plane < 0) return STF_E_ARG;
   if (batch == 0 || channels == 0 || plane == 0) return STF_OK;
   if (channels > 65535 || batch > 65535) return STF_E_SHAPE;
   dim3 grid((unsigned)((plane + 127) / 128 > 64 ? 64 : (plane + 127) / 128), channels, batch);
   entropy_bottleneck_kernel<<<grid, 128, 0, (cudaStream_t)stream>>>(z, params, z_hat, likelihood, symbols,
-                                                                   channels, plane, lik_bound);
+                                                                   channels, plane, lik_bound, ste_round);
   return check_launch();
 }

@@ -43,7 +43,6 @@ struct LinearParams {
   int k_blocks;
   int tmem_cols;
   uint32_t idesc;
-  int debug_flags;  // bit0: swap LBO/SBO (bring-up probe only)
   // window geometry
   int Hp, Wp, nWw, nW;  // padded size, windows per row, windows per image
 };
@@ -278,10 +277,10 @@ linear_tf32_kernel(const __grid_constant__ LinearParams P) {
   } else if (warp == 4) {
     // =========================== MMA issuer ===========================
     if (lane == 0) {
-      const uint32_t a_lbo = (P.debug_flags & 1) ? 128u : (uint32_t)(kTileM * 16);
-      const uint32_t a_sbo = (P.debug_flags & 1) ? (uint32_t)(kTileM * 16) : 128u;
-      const uint32_t b_lbo = (P.debug_flags & 1) ? 128u : (uint32_t)(NT * 16);
-      const uint32_t b_sbo = (P.debug_flags & 1) ? (uint32_t)(NT * 16) : 128u;
+      // K-major, no swizzle: LBO = distance between the two 16-byte K chunks of one MMA,
+      // SBO = distance between consecutive 8-row core matrices (verified on B200 at bring-up).
+      const uint32_t a_lbo = (uint32_t)(kTileM * 16), a_sbo = 128u;
+      const uint32_t b_lbo = (uint32_t)(NT * 16), b_sbo = 128u;
       for (int kb = 0; kb < P.k_blocks; ++kb) {
         const int s = kb % kStages;
         const uint32_t it = (uint32_t)(kb / kStages);
@@ -341,7 +340,7 @@ size_t linear_smem_bytes(int n_tile) {
   return 128 + (size_t)kStages * (kChunks * kTileM * 16 + kChunks * n_tile * 16);
 }
 
-int launch_linear(const stf_linear_args *args, int debug_flags, void *stream) {
+int launch_linear(const stf_linear_args *args, void *stream) {
   if (!args) return STF_E_ARG;
   const stf_linear_args &a = *args;
   if (!a.x || !a.w_packed || !a.y || a.M < 0 || a.N <= 0 || a.K <= 0) return STF_E_ARG;
@@ -365,7 +364,6 @@ int launch_linear(const stf_linear_args *args, int debug_flags, void *stream) {
   P.tmem_cols = 32;
   while (P.tmem_cols < P.n_tile) P.tmem_cols <<= 1;
   P.idesc = umma_idesc_tf32(kTileM, P.n_tile);
-  P.debug_flags = debug_flags;
   P.Hp = P.Wp = P.nWw = P.nW = 0;
   const bool windowed = a.rows == STF_ROWS_WINDOW || a.epilogue == STF_EPI_WINDOW_RESIDUAL;
   if (windowed) {
@@ -422,9 +420,4 @@ extern "C" int stf_pack_linear_weight(const float *weight, float *packed, int N,
   return check_launch();
 }
 
-extern "C" int stf_linear(const stf_linear_args *args, void *stream) { return launch_linear(args, 0, stream); }
-
-// Bring-up probe (tests only, not in the public header): same as stf_linear with debug flags.
-extern "C" int stf_linear_debug(const stf_linear_args *args, int flags, void *stream) {
-  return launch_linear(args, flags, stream);
-}
+extern "C" int stf_linear(const stf_linear_args *args, void *stream) { return launch_linear(args, stream); }

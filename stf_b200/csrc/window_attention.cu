@@ -28,8 +28,8 @@ constexpr float kMaskValue = -100.0f;  // stf.py:334
 template <int WS, int D>
 __global__ void __launch_bounds__(kThreads)
 window_attention_kernel(const float *__restrict__ qkv, float *__restrict__ out,
-                        const float *__restrict__ bias_table, int64_t num_pairs, int C, int heads,
-                        int shift, int Hp, int Wp) {
+                        const float *__restrict__ bias_table, const float *__restrict__ mask, int mask_windows,
+                        int64_t num_pairs, int C, int heads, int shift, int Hp, int Wp) {
   constexpr int N = WS * WS;
   constexpr int PAIRS = kThreads / N;
   const int n = threadIdx.x % N;
@@ -80,6 +80,7 @@ window_attention_kernel(const float *__restrict__ qkv, float *__restrict__ out,
       const int lab = 3 * (hs < Hp - WS ? 0 : (hs < Hp - shift ? 1 : 2)) + (wsft < Wp - WS ? 0 : (wsft < Wp - shift ? 1 : 2));
       if (lab != my_label) acc += kMaskValue;
     }
+    if (mask) acc += __ldg(mask + ((int64_t)(win % mask_windows) * N + n) * N + m);  // explicit mask (stf.py:108-110)
     s[m] = acc;
     smax = fmaxf(smax, acc);
   }
@@ -113,13 +114,13 @@ window_attention_kernel(const float *__restrict__ qkv, float *__restrict__ out,
 }
 
 template <int WS, int D>
-int launch(const float *qkv, float *out, const float *bias_table, int64_t num_windows, int C, int heads,
-           int shift, int Hp, int Wp, cudaStream_t st) {
+int launch(const float *qkv, float *out, const float *bias_table, const float *mask, int mask_windows,
+           int64_t num_windows, int C, int heads, int shift, int Hp, int Wp, cudaStream_t st) {
   constexpr int PAIRS = kThreads / (WS * WS);
   const int64_t pairs = num_windows * heads;
   const int64_t blocks = (pairs + PAIRS - 1) / PAIRS;
   if (blocks > 0x7fffffffLL) return STF_E_SHAPE;
-  window_attention_kernel<WS, D><<<(unsigned)blocks, kThreads, 0, st>>>(qkv, out, bias_table, pairs, C, heads, shift, Hp, Wp);
+  window_attention_kernel<WS, D><<<(unsigned)blocks, kThreads, 0, st>>>(qkv, out, bias_table, mask, mask_windows, pairs, C, heads, shift, Hp, Wp);
   return check_launch();
 }
 
@@ -128,17 +129,19 @@ int launch(const float *qkv, float *out, const float *bias_table, int64_t num_wi
 
 using namespace stf;
 
-extern "C" int stf_window_attention(const float *qkv, float *out, const float *bias_table, int64_t num_windows,
-                                    int C, int heads, int ws, int shift, int Hp, int Wp, void *stream) {
+extern "C" int stf_window_attention(const float *qkv, float *out, const float *bias_table, const float *mask,
+                                    int mask_windows, int64_t num_windows, int C, int heads, int ws, int shift,
+                                    int Hp, int Wp, void *stream) {
   if (!qkv || !out || !bias_table || num_windows < 0 || C <= 0 || heads <= 0) return STF_E_ARG;
   if (num_windows == 0) return STF_OK;
   if (C % heads != 0 || shift < 0 || shift >= ws) return STF_E_SHAPE;
   if (shift > 0 && (Hp <= 0 || Wp <= 0 || Hp % ws != 0 || Wp % ws != 0)) return STF_E_SHAPE;
+  if (mask && (mask_windows <= 0 || num_windows % mask_windows != 0)) return STF_E_SHAPE;
   if (!aligned16(qkv) || !aligned16(out)) return STF_E_ALIGN;
   const int d = C / heads;
   cudaStream_t st = (cudaStream_t)stream;
 #define CASE(WS_, D_) \
-  if (ws == WS_ && d == D_) return launch<WS_, D_>(qkv, out, bias_table, num_windows, C, heads, shift, Hp, Wp, st)
+  if (ws == WS_ && d == D_) return launch<WS_, D_>(qkv, out, bias_table, mask, mask_windows, num_windows, C, heads, shift, Hp, Wp, st)
   CASE(4, 16);
   CASE(4, 24);
   CASE(4, 32);

@@ -1,0 +1,357 @@
+"""Host-side mirror of the reference's window-attention modules, running on libstf_b200 kernels.
+
+Same class names, constructor arguments, parameter / buffer names (checkpoint key space) and call
+signatures as the reference:
+
+  Mlp, window_partition, window_reverse, WindowAttention, SwinTransformerBlock, PatchMerging,
+  PatchSplit, BasicLayer, PatchEmbed           compressai/models/stf.py:25-381
+  WinBasedAttention                            compressai/layers/win_attention.py:118-207
+  Win_noShift_Attention, conv helpers          compressai/layers/layers.py:29-90
+
+What runs underneath (inference / eval mode): a Swin block is five
+kernel launches instead of ~40 --
+  1. norm1 + pad + roll + window_partition + qkv Linear + q*scale     -> stf_linear (WINDOW rows, LN, QKV epilogue)
+  2. softmax(q k^T + bias[rel] + analytic shift mask) v                 -> stf_window_attention
+  3. proj Linear + window_reverse + roll + crop + shortcut              -> stf_linear (WINDOW_RESIDUAL epilogue)
+  4. norm2 + fc1 + exact GELU                                           -> stf_linear (LN, GELU epilogue)
+  5. fc2 + residual                                                     -> stf_linear (RESIDUAL epilogue)
+No mask tensor, no rolled / partitioned copies and no (B_, nH, N, N) score tensor are materialised.
+There is no eager fallback: CPU tensors raise, training-mode forward raises (backward kernels are
+not part of this round).
+"""
+import math
+
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+from . import _C, ops
+
+
+def to_2tuple(x):
+    return tuple(x) if isinstance(x, (tuple, list)) else (x, x)
+
+
+def _require_eval(mod):
+    if mod.training and torch.is_grad_enabled():
+        raise NotImplementedError(
+            f"{type(mod).__name__}: stf_b200 implements the inference path (call .eval() or use torch.no_grad()); "
+            "training-mode kernels (backward) are not built yet")
+
+
+class _PackCache:
+    """Caches the tcgen05 weight image of a Linear; rebuilt when the parameter storage or version changes."""
+
+    def __init__(self):
+        self._key, self._val = None, None
+
+    def get(self, weight, bias=None):
+        key = (weight.data_ptr(), weight._version, None if bias is None else (bias.data_ptr(), bias._version))
+        if key != self._key:
+            self._val = ops.PackedLinear(weight, bias)
+            self._key = key
+        return self._val
+
+
+def window_partition(x, window_size):
+    """(B, H, W, C) -> (B * nW, ws, ws, C)  (stf.py:42-46).  Layout helper kept for API parity; the
+    kernels never call it (partitioning is index math in stf_linear)."""
+    B, H, W, C = x.shape
+    x = x.reshape(B, H // window_size, window_size, W // window_size, window_size, C)
+    return x.permute(0, 1, 3, 2, 4, 5).reshape(-1, window_size, window_size, C)
+
+
+def window_reverse(windows, window_size, H, W):
+    """Inverse of window_partition (stf.py:49-53)."""
+    B = windows.shape[0] // ((H // window_size) * (W // window_size))
+    x = windows.reshape(B, H // window_size, W // window_size, window_size, window_size, -1)
+    return x.permute(0, 1, 3, 2, 4, 5).reshape(B, H, W, -1)
+
+
+class Mlp(nn.Module):
+    """fc2(GELU(fc1(x)))  (stf.py:25-40); dropout is 0 in every reference config."""
+
+    def __init__(self, in_features, hidden_features=None, out_features=None, act_layer=nn.GELU, drop=0.0):
+        super().__init__()
+        out_features = out_features or in_features
+        hidden_features = hidden_features or in_features
+        self.fc1 = nn.Linear(in_features, hidden_features)
+        self.act = act_layer()
+        self.fc2 = nn.Linear(hidden_features, out_features)
+        self.drop = nn.Dropout(drop)
+        self._p1, self._p2 = _PackCache(), _PackCache()
+
+    def forward(self, x, ln=None, residual=None):
+        _require_eval(self)
+        shape = x.shape
+        x2 = x.reshape(-1, shape[-1])
+        h = ops.linear(x2, self._p1.get(self.fc1.weight, self.fc1.bias), ln=ln, epilogue=_C.EPI_GELU)
+        if residual is None:
+            y = ops.linear(h, self._p2.get(self.fc2.weight, self.fc2.bias))
+        else:
+            y = ops.linear(h, self._p2.get(self.fc2.weight, self.fc2.bias), epilogue=_C.EPI_RESIDUAL,
+                           residual=residual.reshape(-1, residual.shape[-1]))
+        return y.reshape(*shape[:-1], y.shape[-1])
+
+
+class WindowAttention(nn.Module):
+    """Window multi-head self-attention with relative position bias (stf.py:55-121)."""
+
+    def __init__(self, dim, window_size, num_heads, qkv_bias=True, qk_scale=None, attn_drop=0.0, proj_drop=0.0):
+        super().__init__()
+        self.dim = dim
+        self.window_size = to_2tuple(window_size)
+        if self.window_size[0] != self.window_size[1]:
+            raise ValueError("stf_b200: square windows only (every reference config uses them)")
+        self.num_heads = num_heads
+        head_dim = dim // num_heads
+        self.scale = qk_scale or head_dim ** -0.5
+        ws = self.window_size[0]
+        self.relative_position_bias_table = nn.Parameter(torch.zeros((2 * ws - 1) * (2 * ws - 1), num_heads))
+        r = torch.arange(ws)
+        hh, ww = torch.meshgrid(r, r, indexing="ij")
+        hh, ww = hh.reshape(-1), ww.reshape(-1)
+        index = (hh[:, None] - hh[None, :] + ws - 1) * (2 * ws - 1) + (ww[:, None] - ww[None, :] + ws - 1)
+        self.register_buffer("relative_position_index", index)   # checkpoint key; the kernel recomputes it
+        self.qkv = nn.Linear(dim, dim * 3, bias=qkv_bias)
+        self.attn_drop = nn.Dropout(attn_drop)
+        self.proj = nn.Linear(dim, dim)
+        self.proj_drop = nn.Dropout(proj_drop)
+        nn.init.trunc_normal_(self.relative_position_bias_table, std=0.02)
+        self.softmax = nn.Softmax(dim=-1)
+        self._pq, self._pp = _PackCache(), _PackCache()
+
+    def packed_qkv(self):
+        return self._pq.get(self.qkv.weight, self.qkv.bias)
+
+    def packed_proj(self):
+        return self._pp.get(self.proj.weight, self.proj.bias)
+
+    def forward(self, x, mask=None):
+        """x: (num_windows*B, N, C) already partitioned; mask: (nW, N, N) additive or None."""
+        _require_eval(self)
+        B_, N, C = x.shape
+        ws = self.window_size[0]
+        qkv = ops.linear(x.reshape(-1, C), self.packed_qkv(), epilogue=_C.EPI_QKV, q_cols=C, q_scale=self.scale)
+        o = ops.window_attention_core(qkv, self.relative_position_bias_table, B_, C, self.num_heads, ws, 0,
+                                      mask=mask)
+        y = ops.linear(o, self.packed_proj())
+        return y.reshape(B_, N, C)
+
+
+class SwinTransformerBlock(nn.Module):
+    """LN -> (S)W-MSA -> +shortcut -> LN -> MLP -> +residual  (stf.py:124-199)."""
+
+    def __init__(self, dim, num_heads, window_size=7, shift_size=0, mlp_ratio=4.0, qkv_bias=True, qk_scale=None,
+                 drop=0.0, attn_drop=0.0, drop_path=0.0, act_layer=nn.GELU, norm_layer=nn.LayerNorm, inverse=False):
+        super().__init__()
+        self.dim = dim
+        self.num_heads = num_heads
+        self.window_size = window_size
+        self.shift_size = shift_size
+        self.mlp_ratio = mlp_ratio
+        assert 0 <= self.shift_size < self.window_size, "shift_size must in 0-window_size"
+        self.norm1 = norm_layer(dim)
+        self.attn = WindowAttention(dim, window_size=to_2tuple(window_size), num_heads=num_heads, qkv_bias=qkv_bias,
+                                    qk_scale=qk_scale, attn_drop=attn_drop, proj_drop=drop)
+        self.drop_path_rate = drop_path          # stochastic depth is identity in eval
+        self.drop_path = nn.Identity()
+        self.norm2 = norm_layer(dim)
+        self.mlp = Mlp(in_features=dim, hidden_features=int(dim * mlp_ratio), act_layer=act_layer, drop=drop)
+        self.H = None
+        self.W = None
+
+    def forward(self, x, mask_matrix=None):
+        """x: (B, H*W, C).  `mask_matrix` is accepted for signature parity and ignored: the
+        shifted-window mask is computed analytically inside the attention kernel."""
+        _require_eval(self)
+        B, L, C = x.shape
+        H, W = self.H, self.W
+        assert L == H * W, "input feature has wrong size"
+        ws, shift = self.window_size, self.shift_size
+        Hp, Wp = ops.ceil_to(H, ws), ops.ceil_to(W, ws)
+        geom = (B, H, W, ws, shift)
+        x2 = x.reshape(B * L, C)
+        n1 = (self.norm1.weight, self.norm1.bias, self.norm1.eps)
+        qkv = ops.linear(x2, self.attn.packed_qkv(), M=B * Hp * Wp, rows=_C.ROWS_WINDOW, ln=n1,
+                         epilogue=_C.EPI_QKV, q_cols=C, q_scale=self.attn.scale, geom=geom)
+        o = ops.window_attention_core(qkv, self.attn.relative_position_bias_table, B * (Hp // ws) * (Wp // ws), C,
+                                      self.num_heads, ws, shift, Hp, Wp)
+        x1 = ops.linear(o, self.attn.packed_proj(), epilogue=_C.EPI_WINDOW_RESIDUAL, residual=x2, geom=geom,
+                        out_rows=B * L)
+        n2 = (self.norm2.weight, self.norm2.bias, self.norm2.eps)
+        y = self.mlp(x1, ln=n2, residual=x1)
+        return y.reshape(B, L, C)
+
+
+class PatchMerging(nn.Module):
+    """2x2 gather-concat -> LN(4C) -> Linear(4C -> 2C, no bias)  (stf.py:202-235), one launch."""
+
+    def __init__(self, dim, norm_layer=nn.LayerNorm):
+        super().__init__()
+        self.dim = dim
+        self.reduction = nn.Linear(4 * dim, 2 * dim, bias=False)
+        self.norm = norm_layer(4 * dim)
+        self._p = _PackCache()
+
+    def forward(self, x, H, W):
+        _require_eval(self)
+        B, L, C = x.shape
+        assert L == H * W, "input feature has wrong size"
+        H2, W2 = (H + 1) // 2, (W + 1) // 2
+        y = ops.linear(x.reshape(B * L, C), self._p.get(self.reduction.weight), M=B * H2 * W2, rows=_C.ROWS_MERGE,
+                       ln=(self.norm.weight, self.norm.bias, self.norm.eps), geom=(B, H, W, 0, 0))
+        return y.reshape(B, H2 * W2, 2 * C)
+
+
+class PatchSplit(nn.Module):
+    """LN(C) -> Linear(C -> 2C, no bias) -> PixelShuffle(2) in token layout  (stf.py:238-260), one launch."""
+
+    def __init__(self, dim, norm_layer=nn.LayerNorm):
+        super().__init__()
+        self.dim = dim
+        self.reduction = nn.Linear(dim, dim * 2, bias=False)
+        self.norm = norm_layer(dim)
+        self.shuffle = nn.PixelShuffle(2)
+        self._p = _PackCache()
+
+    def forward(self, x, H, W):
+        _require_eval(self)
+        B, L, C = x.shape
+        assert L == H * W, "input feature has wrong size"
+        y = ops.linear(x.reshape(B * L, C), self._p.get(self.reduction.weight), epilogue=_C.EPI_PIXEL_SHUFFLE,
+                       ln=(self.norm.weight, self.norm.bias, self.norm.eps), geom=(B, H, W, 0, 0),
+                       out_rows=4 * B * L, out_cols=C // 2)
+        return y.reshape(B, 4 * L, C // 2)
+
+
+class BasicLayer(nn.Module):
+    """`depth` Swin blocks alternating W-MSA / SW-MSA + optional resampling  (stf.py:262-347)."""
+
+    def __init__(self, dim, depth, num_heads, window_size=7, mlp_ratio=4.0, qkv_bias=True, qk_scale=None, drop=0.0,
+                 attn_drop=0.0, drop_path=0.0, norm_layer=nn.LayerNorm, downsample=None, use_checkpoint=False,
+                 inverse=False):
+        super().__init__()
+        self.window_size = window_size
+        self.shift_size = window_size // 2
+        self.depth = depth
+        self.use_checkpoint = use_checkpoint
+        self.blocks = nn.ModuleList([
+            SwinTransformerBlock(dim=dim, num_heads=num_heads, window_size=window_size,
+                                 shift_size=0 if i % 2 == 0 else window_size // 2, mlp_ratio=mlp_ratio,
+                                 qkv_bias=qkv_bias, qk_scale=qk_scale, drop=drop, attn_drop=attn_drop,
+                                 drop_path=drop_path[i] if isinstance(drop_path, list) else drop_path,
+                                 norm_layer=norm_layer, inverse=inverse)
+            for i in range(depth)])
+        self.downsample = downsample(dim=dim, norm_layer=norm_layer) if downsample is not None else None
+
+    def forward(self, x, H, W):
+        # the (nW, N, N) attention mask of stf.py:316-334 is never built: see stf_window_attention
+        for blk in self.blocks:
+            blk.H, blk.W = H, W
+            x = blk(x, None)
+        if self.downsample is None:
+            return x, H, W
+        x = self.downsample(x, H, W)
+        if isinstance(self.downsample, PatchMerging):
+            return x, (H + 1) // 2, (W + 1) // 2
+        return x, H * 2, W * 2
+
+
+class PatchEmbed(nn.Module):
+    """Conv2d(k=s=patch) + LayerNorm over channels (stf.py:350-381).  The 2x2 stride-2 convolution is a
+    cuDNN call (adjacent to the hot path)."""
+
+    def __init__(self, patch_size=4, in_chans=3, embed_dim=96, norm_layer=None):
+        super().__init__()
+        self.patch_size = to_2tuple(patch_size)
+        self.in_chans = in_chans
+        self.embed_dim = embed_dim
+        self.proj = nn.Conv2d(in_chans, embed_dim, kernel_size=self.patch_size, stride=self.patch_size)
+        self.norm = norm_layer(embed_dim) if norm_layer is not None else None
+
+    def forward(self, x):
+        _, _, H, W = x.shape
+        ph, pw = self.patch_size
+        if W % pw != 0:
+            x = F.pad(x, (0, pw - W % pw))
+        if H % ph != 0:
+            x = F.pad(x, (0, 0, 0, ph - H % ph))
+        x = self.proj(x)
+        if self.norm is not None:
+            Wh, Ww = x.shape[2], x.shape[3]
+            x = self.norm(x.flatten(2).transpose(1, 2))
+            x = x.transpose(1, 2).reshape(-1, self.embed_dim, Wh, Ww)
+        return x
+
+
+class WinBasedAttention(nn.Module):
+    """NCHW (shifted-)window attention with residual, no LN / MLP  (layers/win_attention.py:118-207)."""
+
+    def __init__(self, dim=192, num_heads=8, window_size=8, shift_size=0, qkv_bias=True, qk_scale=None, drop=0.0,
+                 attn_drop=0.0, drop_path=0.0):
+        super().__init__()
+        self.dim = dim
+        self.num_heads = num_heads
+        self.window_size = window_size
+        self.shift_size = shift_size
+        assert 0 <= self.shift_size < self.window_size, "shift_size must in 0-window_size"
+        self.attn = WindowAttention(dim, window_size=to_2tuple(window_size), num_heads=num_heads, qkv_bias=qkv_bias,
+                                    qk_scale=qk_scale, attn_drop=attn_drop, proj_drop=drop)
+        self.drop_path = nn.Identity()
+
+    def forward(self, x):
+        _require_eval(self)
+        B, C, H, W = x.shape
+        ws, shift = self.window_size, self.shift_size
+        if H % ws or W % ws:
+            raise RuntimeError(f"WinBasedAttention: {H}x{W} is not a multiple of window {ws} "
+                               "(the reference's view() fails on this input too, win_attention.py:11)")
+        # NCHW -> token-major once; shift / partition / reverse / residual happen inside the kernels
+        t = x.permute(0, 2, 3, 1).contiguous().reshape(B * H * W, C)
+        geom = (B, H, W, ws, shift)
+        qkv = ops.linear(t, self.attn.packed_qkv(), rows=_C.ROWS_WINDOW, epilogue=_C.EPI_QKV, q_cols=C,
+                         q_scale=self.attn.scale, geom=geom)
+        o = ops.window_attention_core(qkv, self.attn.relative_position_bias_table, B * (H // ws) * (W // ws), C,
+                                      self.num_heads, ws, shift, H, W)
+        y = ops.linear(o, self.attn.packed_proj(), epilogue=_C.EPI_WINDOW_RESIDUAL, residual=t, geom=geom)
+        return y.reshape(B, H, W, C).permute(0, 3, 1, 2).contiguous()
+
+
+def conv3x3(in_ch, out_ch, stride=1):
+    return nn.Conv2d(in_ch, out_ch, kernel_size=3, stride=stride, padding=1)
+
+
+def conv1x1(in_ch, out_ch, stride=1):
+    return nn.Conv2d(in_ch, out_ch, kernel_size=1, stride=stride)
+
+
+def subpel_conv3x3(in_ch, out_ch, r=1):
+    return nn.Sequential(nn.Conv2d(in_ch, out_ch * r ** 2, kernel_size=3, padding=1), nn.PixelShuffle(r))
+
+
+class Win_noShift_Attention(nn.Module):
+    """a(x) * sigmoid(b(x)) + x with b starting with WinBasedAttention  (layers/layers.py:45-90).
+    The residual-unit convolutions are cuDNN calls (adjacent)."""
+
+    def __init__(self, dim, num_heads=8, window_size=8, shift_size=0):
+        super().__init__()
+        N = dim
+
+        class ResidualUnit(nn.Module):
+            def __init__(self):
+                super().__init__()
+                self.conv = nn.Sequential(conv1x1(N, N // 2), nn.GELU(), conv3x3(N // 2, N // 2), nn.GELU(),
+                                          conv1x1(N // 2, N))
+                self.relu = nn.GELU()
+
+            def forward(self, x):
+                return self.relu(self.conv(x) + x)
+
+        self.conv_a = nn.Sequential(ResidualUnit(), ResidualUnit(), ResidualUnit())
+        self.conv_b = nn.Sequential(WinBasedAttention(dim=dim, num_heads=num_heads, window_size=window_size,
+                                                      shift_size=shift_size),
+                                    ResidualUnit(), ResidualUnit(), ResidualUnit(), conv1x1(N, N))
+
+    def forward(self, x):
+        return self.conv_a(x) * torch.sigmoid(self.conv_b(x)) + x

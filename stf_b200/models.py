@@ -1,0 +1,429 @@
+"""Host-side mirror of the reference's two codecs on libstf_b200 kernels.
+
+  SymmetricalTransFormer   compressai/models/stf.py:384-788   (zoo name "stf")
+  WACNN                    compressai/models/cnn.py:23-332     (zoo name "cnn")
+  CompressionModel         compressai/models/base.py:13-70
+
+Constructor arguments, module tree / checkpoint keys, and forward / compress / decompress / update /
+load_state_dict / aux_loss signatures are the reference's.  What runs underneath in eval mode:
+  * every Swin block, PatchMerging / PatchSplit and WinBasedAttention -> the fused tcgen05 linear kernel +
+    the window-attention core (stf_b200/layers.py);
+  * EntropyBottleneck / GaussianConditional quantize, likelihood, build_indexes, dequantize -> one
+    kernel per slice step (stf_b200/entropy_models.py, ops.gaussian_compress_step);
+  * symbols and indexes of ALL slices are written by the kernels straight into one (B, M*h*w) int32
+    device buffer in the reference's coding order and cross PCIe once, instead of 24 `.tolist()` syncs;
+  * rANS runs on the host codec of the same library, one stream per image per host thread.
+Convolution stacks (hyperprior, cc_mean / cc_scale / lrp, PatchEmbed, end_conv, WACNN's g_a / g_s convs,
+GDN) are cuDNN calls through torch: adjacent to the hot path.
+
+Batch semantics: the reference's compress() concatenates a whole batch into one y-string that its own
+decompress() cannot decode.  Here strings[0] holds ONE y-string PER IMAGE, each
+byte-identical to what the reference emits for that image alone; for batch 1 the return value has
+exactly the reference's structure.
+"""
+import math
+
+import numpy as np
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+from . import ans, ops
+from .entropy_models import EntropyBottleneck, GaussianConditional, LowerBound
+from .layers import (BasicLayer, PatchEmbed, PatchMerging, PatchSplit, Win_noShift_Attention, conv3x3,
+                     subpel_conv3x3)
+
+SCALES_MIN, SCALES_MAX, SCALES_LEVELS = 0.11, 256, 64   # stf.py:16-18
+
+
+def get_scale_table(min=SCALES_MIN, max=SCALES_MAX, levels=SCALES_LEVELS):
+    return torch.exp(torch.linspace(math.log(min), math.log(max), levels))
+
+
+def conv(in_channels, out_channels, kernel_size=5, stride=2):
+    return nn.Conv2d(in_channels, out_channels, kernel_size=kernel_size, stride=stride, padding=kernel_size // 2)
+
+
+def deconv(in_channels, out_channels, kernel_size=5, stride=2):
+    return nn.ConvTranspose2d(in_channels, out_channels, kernel_size=kernel_size, stride=stride,
+                              output_padding=stride - 1, padding=kernel_size // 2)
+
+
+def _resize_buffers(module, prefix, names, state_dict):
+    """Entropy-model tables have data-dependent sizes: give the registered (empty) buffers the
+    checkpoint's shapes before nn.Module.load_state_dict (models/utils.py:46-111, policy resize_if_empty)."""
+    for name in names:
+        key = f"{prefix}.{name}"
+        if key not in state_dict:
+            continue
+        buf = getattr(module, name)
+        if buf.numel() == 0:
+            setattr(module, name, buf.new_zeros(state_dict[key].shape))
+
+
+class CompressionModel(nn.Module):
+    def __init__(self, init_weights=True):
+        super().__init__()
+        # The reference runs its kaiming pass here, before any sub-module exists, so it is a no-op
+        # (SURVEY.md section 8d); layers keep PyTorch's default init.  Kept a no-op on purpose.
+
+    def aux_loss(self):
+        return sum(m.loss() for m in self.modules() if isinstance(m, EntropyBottleneck))
+
+    def update(self, force=False):
+        updated = False
+        for m in self.children():
+            if isinstance(m, EntropyBottleneck):
+                updated |= m.update(force=force)
+        return updated
+
+    def load_state_dict(self, state_dict, strict=True):
+        _resize_buffers(self.entropy_bottleneck, "entropy_bottleneck", ["_quantized_cdf", "_offset", "_cdf_length"],
+                        state_dict)
+        return super().load_state_dict(state_dict, strict=strict)
+
+
+def _stack5(c_in):
+    """The five-layer 3x3 stack shared by cc_mean / cc_scale / lrp transforms (stf.py:510-548)."""
+    return nn.Sequential(conv(c_in, 224, stride=1, kernel_size=3), nn.GELU(), conv(224, 176, stride=1, kernel_size=3),
+                         nn.GELU(), conv(176, 128, stride=1, kernel_size=3), nn.GELU(),
+                         conv(128, 64, stride=1, kernel_size=3), nn.GELU(), conv(64, 32, stride=1, kernel_size=3))
+
+
+class _SliceCodec(CompressionModel):
+    """Hyperprior + channel-conditional slice loop shared by STF and WACNN
+    (stf.py:600-636, 687-735, 737-779 == cnn.py:144-183, 223-267, 289-327)."""
+
+    slice_channels = 32
+
+    # supplied by subclasses -----------------------------------------------------------------
+    def _analysis(self, x):
+        raise NotImplementedError
+
+    def _synthesis(self, y_hat):
+        raise NotImplementedError
+
+    # shared ---------------------------------------------------------------------------------
+    def update(self, scale_table=None, force=False):
+        if scale_table is None:
+            scale_table = get_scale_table()
+        updated = self.gaussian_conditional.update_scale_table(scale_table, force=force)
+        updated |= super().update(force=force)
+        return updated
+
+    def load_state_dict(self, state_dict, strict=True):
+        _resize_buffers(self.gaussian_conditional, "gaussian_conditional",
+                        ["_quantized_cdf", "_offset", "_cdf_length", "scale_table"], state_dict)
+        return super().load_state_dict(state_dict, strict=strict)
+
+    @classmethod
+    def from_state_dict(cls, state_dict):
+        net = cls()
+        net.load_state_dict(state_dict)
+        return net
+
+    def _require_inference(self):
+        if self.training and torch.is_grad_enabled():
+            raise NotImplementedError("stf_b200 implements the inference path: call .eval() / torch.no_grad(). "
+                                      "The training step (config 5) needs backward kernels that are not built yet.")
+
+    def _slice_params(self, i, latent_means, latent_scales, y_hat_slices, hw):
+        support = y_hat_slices if self.max_support_slices < 0 else y_hat_slices[: self.max_support_slices]
+        mean_support = torch.cat([latent_means] + support, dim=1)
+        mu = self.cc_mean_transforms[i](mean_support)[:, :, : hw[0], : hw[1]].contiguous()
+        scale_support = torch.cat([latent_scales] + support, dim=1)
+        scale = self.cc_scale_transforms[i](scale_support)[:, :, : hw[0], : hw[1]].contiguous()
+        return mean_support, mu, scale
+
+    def _lrp(self, i, mean_support, y_hat_slice):
+        lrp = self.lrp_transforms[i](torch.cat([mean_support, y_hat_slice], dim=1))
+        return y_hat_slice + 0.5 * torch.tanh(lrp)
+
+    def _needed_as_support(self, i):
+        return self.max_support_slices < 0 or i < self.max_support_slices
+
+    @torch.no_grad()
+    def forward(self, x):
+        self._require_inference()
+        y = self._analysis(x)
+        hw = y.shape[2:]
+        z = self.h_a(y)
+        eb = self.entropy_bottleneck
+        z_hat, z_likelihoods, _ = ops.entropy_bottleneck(z.contiguous(), eb.packed_params(),
+                                                         lik_bound=eb._likelihood_bound, ste_round=True)
+        latent_scales = self.h_scale_s(z_hat)
+        latent_means = self.h_mean_s(z_hat)
+        gc = self.gaussian_conditional
+        Cs = self.slice_channels
+        y_hat_slices, y_likelihood = [], []
+        for i in range(self.num_slices):
+            mean_support, mu, scale = self._slice_params(i, latent_means, latent_scales, y_hat_slices, hw)
+            y_hat_i, lik = ops.gaussian_likelihood(y, i * Cs, scale, mu, scale_bound=gc.scale_bound_value(),
+                                                   lik_bound=gc._likelihood_bound, ste_round=True)
+            y_likelihood.append(lik)
+            y_hat_slices.append(self._lrp(i, mean_support, y_hat_i))
+        y_hat = torch.cat(y_hat_slices, dim=1)
+        out = {"x_hat": self._synthesis(y_hat),
+               "likelihoods": {"y": torch.cat(y_likelihood, dim=1), "z": z_likelihoods}}
+        if hasattr(self, "is_teacher"):
+            out["y"] = y if self.is_teacher else None
+        return out
+
+    @torch.no_grad()
+    def compress(self, x, debug=None):
+        self._require_inference()
+        gc = self.gaussian_conditional
+        y_table = gc.rans_table()
+        y = self._analysis(x)
+        B, M, h, w = y.shape
+        z = self.h_a(y)
+        # EntropyBottleneck.compress + decompress (stf.py:688-689): decompress(z_strings) is
+        # dequantize(symbols, medians), which the same kernel emits -- no need to decode our own stream
+        eb = self.entropy_bottleneck
+        z_hat, _, z_sym = ops.entropy_bottleneck(z.contiguous(), eb.packed_params(), want_lik=False, want_symbols=True)
+        z_strings = eb.encode_symbols(z_sym)
+        latent_scales = self.h_scale_s(z_hat)
+        latent_means = self.h_mean_s(z_hat)
+        Cs, plane = self.slice_channels, h * w
+        total = M * plane
+        sym = torch.empty((B, total), dtype=torch.int32, device=y.device)
+        idx = torch.empty((B, total), dtype=torch.int32, device=y.device)
+        table = gc.host_scale_table()
+        y_hat_slices = []
+        for i in range(self.num_slices):
+            mean_support, mu, scale = self._slice_params(i, latent_means, latent_scales, y_hat_slices, (h, w))
+            need = self._needed_as_support(i) or debug is not None
+            y_hat_i = ops.gaussian_compress_step(y, i * Cs, scale, mu, table, sym, idx, i * Cs * plane,
+                                                 scale_bound=gc.scale_bound_value(), want_y_hat=need)
+            if need:   # later slices are never read again in compress(): their LRP stacks are dead work
+                y_hat_slices.append(self._lrp(i, mean_support, y_hat_i))
+        sym_h = torch.empty(sym.shape, dtype=torch.int32, pin_memory=True)
+        idx_h = torch.empty(idx.shape, dtype=torch.int32, pin_memory=True)
+        sym_h.copy_(sym, non_blocking=True)
+        idx_h.copy_(idx, non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+        if debug is not None:
+            debug.update(y=y, z=z, symbols=sym_h.clone(), indexes=idx_h.clone(), y_hat=torch.cat(y_hat_slices, 1))
+        s_np, i_np = sym_h.numpy(), idx_h.numpy()
+        y_strings = ans.encode_batch(y_table, [s_np[b] for b in range(B)], [i_np[b] for b in range(B)])
+        return {"strings": [y_strings, z_strings], "shape": z.size()[-2:]}
+
+    @torch.no_grad()
+    def decompress(self, strings, shape):
+        self._require_inference()
+        assert isinstance(strings, list) and len(strings) == 2
+        gc = self.gaussian_conditional
+        y_table = gc.rans_table()
+        z_hat = self.entropy_bottleneck.decompress(strings[1], shape)
+        B = z_hat.shape[0]
+        if len(strings[0]) != B:
+            raise ValueError(f"{len(strings[0])} y-strings for {B} z-strings (one y-string per image expected)")
+        latent_scales = self.h_scale_s(z_hat)
+        latent_means = self.h_mean_s(z_hat)
+        h, w = z_hat.shape[2] * 4, z_hat.shape[3] * 4
+        Cs, plane = self.slice_channels, h * w
+        n = Cs * plane
+        decoders = []
+        for s in strings[0]:
+            d = ans.RansDecoder()
+            d.set_stream(s)
+            decoders.append(d)
+        idx_h = torch.empty((B, n), dtype=torch.int32, pin_memory=True)
+        sym_h = torch.empty((B, n), dtype=torch.int32, pin_memory=True)
+        idx_np, sym_np = idx_h.numpy(), sym_h.numpy()
+        table = gc.host_scale_table()
+        stream = torch.cuda.current_stream()
+        y_hat_slices = []
+        for i in range(self.num_slices):
+            mean_support, mu, scale = self._slice_params(i, latent_means, latent_scales, y_hat_slices, (h, w))
+            idx = ops.build_indexes(scale, table, gc.scale_bound_value())
+            idx_h.copy_(idx.reshape(B, n), non_blocking=True)
+            stream.synchronize()
+            ans.decode_batch(decoders, y_table, [idx_np[b] for b in range(B)], outs=[sym_np[b] for b in range(B)])
+            sym = sym_h.to(z_hat.device, non_blocking=True)
+            y_hat_i = ops.dequantize(sym, 0, mu)
+            y_hat_slices.append(self._lrp(i, mean_support, y_hat_i))
+        y_hat = torch.cat(y_hat_slices, dim=1)
+        return {"x_hat": self._synthesis(y_hat).clamp_(0, 1)}
+
+
+class SymmetricalTransFormer(_SliceCodec):
+    """STF: PatchEmbed -> 4 Swin stages -> hyperprior + 12-slice entropy model -> 4 Swin stages -> end_conv."""
+
+    def __init__(self, pretrain_img_size=256, patch_size=2, in_chans=3, embed_dim=48, depths=[2, 2, 6, 2],
+                 num_heads=[3, 6, 12, 24], window_size=4, num_slices=12, mlp_ratio=4.0, qkv_bias=True, qk_scale=None,
+                 drop_rate=0.0, attn_drop_rate=0.0, drop_path_rate=0.2, norm_layer=nn.LayerNorm, patch_norm=True,
+                 frozen_stages=-1, use_checkpoint=False, is_teacher=False):
+        super().__init__()
+        self.pretrain_img_size = pretrain_img_size
+        self.num_layers = len(depths)
+        self.embed_dim = embed_dim
+        self.patch_norm = patch_norm
+        self.frozen_stages = frozen_stages
+        self.num_slices = num_slices
+        self.max_support_slices = num_slices // 2
+        self.is_teacher = is_teacher
+        self.patch_embed = PatchEmbed(patch_size=patch_size, in_chans=in_chans, embed_dim=embed_dim,
+                                      norm_layer=norm_layer if patch_norm else None)
+        self.pos_drop = nn.Dropout(p=drop_rate)
+        dpr = [v.item() for v in torch.linspace(0, drop_path_rate, sum(depths))]
+
+        def stage(dim, i, depths_, heads_, resample, inverse):
+            return BasicLayer(dim=dim, depth=depths_[i], num_heads=heads_[i], window_size=window_size,
+                              mlp_ratio=mlp_ratio, qkv_bias=qkv_bias, qk_scale=qk_scale, drop=drop_rate,
+                              attn_drop=attn_drop_rate, drop_path=dpr[sum(depths_[:i]):sum(depths_[:i + 1])],
+                              norm_layer=norm_layer, downsample=resample if i < self.num_layers - 1 else None,
+                              use_checkpoint=use_checkpoint, inverse=inverse)
+
+        self.layers = nn.ModuleList(stage(int(embed_dim * 2 ** i), i, depths, num_heads, PatchMerging, False)
+                                    for i in range(self.num_layers))
+        rd, rh = depths[::-1], num_heads[::-1]
+        self.syn_layers = nn.ModuleList(stage(int(embed_dim * 2 ** (3 - i)), i, rd, rh, PatchSplit, True)
+                                        for i in range(self.num_layers))
+        self.end_conv = nn.Sequential(
+            nn.Conv2d(embed_dim, embed_dim * patch_size ** 2, kernel_size=5, stride=1, padding=2),
+            nn.PixelShuffle(patch_size), nn.Conv2d(embed_dim, 3, kernel_size=3, stride=1, padding=1))
+        self.num_features = [int(embed_dim * 2 ** i) for i in range(self.num_layers)]
+        self.g_a = None
+        self.g_s = None
+        M = embed_dim * 8
+        self.h_a = nn.Sequential(conv3x3(M, 384), nn.GELU(), conv3x3(384, 336), nn.GELU(),
+                                 conv3x3(336, 288, stride=2), nn.GELU(), conv3x3(288, 240), nn.GELU(),
+                                 conv3x3(240, 192, stride=2))
+
+        def hyper_synthesis():
+            return nn.Sequential(conv3x3(192, 240), nn.GELU(), subpel_conv3x3(240, 288, 2), nn.GELU(),
+                                 conv3x3(288, 336), nn.GELU(), subpel_conv3x3(336, 384, 2), nn.GELU(),
+                                 conv3x3(384, M))
+
+        self.h_mean_s = hyper_synthesis()
+        self.h_scale_s = hyper_synthesis()
+        ms = self.max_support_slices
+        self.cc_mean_transforms = nn.ModuleList(_stack5(M + 32 * min(i, ms)) for i in range(num_slices))
+        self.cc_scale_transforms = nn.ModuleList(_stack5(M + 32 * min(i, ms)) for i in range(num_slices))
+        self.lrp_transforms = nn.ModuleList(_stack5(M + 32 * min(i + 1, ms + 1)) for i in range(num_slices))
+        self.entropy_bottleneck = EntropyBottleneck(embed_dim * 4)
+        self.gaussian_conditional = GaussianConditional(None)
+        self._freeze_stages()
+
+    def _freeze_stages(self):
+        if self.frozen_stages >= 0:
+            self.patch_embed.eval()
+            for p in self.patch_embed.parameters():
+                p.requires_grad = False
+        if self.frozen_stages >= 2:
+            self.pos_drop.eval()
+            for i in range(self.frozen_stages - 1):
+                self.layers[i].eval()
+                for p in self.layers[i].parameters():
+                    p.requires_grad = False
+
+    def init_weights(self):
+        """stf.py:570-582 (never called by the constructor, kept for API parity)."""
+        for m in self.modules():
+            if isinstance(m, (nn.Conv2d, nn.ConvTranspose2d)):
+                nn.init.kaiming_normal_(m.weight)
+                if m.bias is not None:
+                    nn.init.zeros_(m.bias)
+            elif isinstance(m, nn.Linear):
+                nn.init.trunc_normal_(m.weight, std=0.02)
+                if m.bias is not None:
+                    nn.init.constant_(m.bias, 0)
+            elif isinstance(m, nn.LayerNorm):
+                nn.init.constant_(m.bias, 0)
+                nn.init.constant_(m.weight, 1.0)
+
+    def _analysis(self, x):
+        t = self.patch_embed(x)
+        Wh, Ww = t.shape[2], t.shape[3]
+        t = t.flatten(2).transpose(1, 2).contiguous()
+        for layer in self.layers:
+            t, Wh, Ww = layer(t, Wh, Ww)
+        C = self.embed_dim * 8
+        return t.reshape(-1, Wh, Ww, C).permute(0, 3, 1, 2).contiguous()
+
+    def _synthesis(self, y_hat):
+        B, C, Wh, Ww = y_hat.shape
+        t = y_hat.permute(0, 2, 3, 1).contiguous().reshape(B, Wh * Ww, C)
+        for layer in self.syn_layers:
+            t, Wh, Ww = layer(t, Wh, Ww)
+        return self.end_conv(t.reshape(B, Wh, Ww, self.embed_dim).permute(0, 3, 1, 2).contiguous())
+
+
+class _NonNegativeParametrizer(nn.Module):
+    """compressai/ops/parametrizers.py:23-49."""
+
+    def __init__(self, minimum=0.0, reparam_offset=2 ** -18):
+        super().__init__()
+        self.minimum, self.reparam_offset = float(minimum), float(reparam_offset)
+        self.register_buffer("pedestal", torch.Tensor([self.reparam_offset ** 2]))
+        self.lower_bound = LowerBound((self.minimum + self.reparam_offset ** 2) ** 0.5)
+
+    def init(self, x):
+        return torch.sqrt(torch.max(x + self.pedestal, self.pedestal))
+
+    def forward(self, x):
+        return self.lower_bound(x) ** 2 - self.pedestal
+
+
+class GDN(nn.Module):
+    """Generalised divisive normalisation (layers/gdn.py:26-75): a 1x1 convolution on x^2 (cuDNN) + rsqrt.
+    Adjacent to the hot path (out of scope for custom kernels)."""
+
+    def __init__(self, in_channels, inverse=False, beta_min=1e-6, gamma_init=0.1):
+        super().__init__()
+        self.inverse = bool(inverse)
+        self.beta_reparam = _NonNegativeParametrizer(minimum=float(beta_min))
+        self.beta = nn.Parameter(self.beta_reparam.init(torch.ones(in_channels)))
+        self.gamma_reparam = _NonNegativeParametrizer()
+        self.gamma = nn.Parameter(self.gamma_reparam.init(float(gamma_init) * torch.eye(in_channels)))
+
+    def forward(self, x):
+        C = x.shape[1]
+        norm = F.conv2d(x ** 2, self.gamma_reparam(self.gamma).reshape(C, C, 1, 1), self.beta_reparam(self.beta))
+        return x * (torch.sqrt(norm) if self.inverse else torch.rsqrt(norm))
+
+
+class WACNN(_SliceCodec):
+    """CNN codec with window-attention blocks at 1/4 and 1/16 resolution (cnn.py:23-332)."""
+
+    def __init__(self, N=192, M=320, **kwargs):
+        super().__init__(**kwargs)
+        self.num_slices = 10
+        self.max_support_slices = 5
+        self.g_a = nn.Sequential(
+            conv(3, N), GDN(N), conv(N, N), GDN(N),
+            Win_noShift_Attention(dim=N, num_heads=8, window_size=8, shift_size=4),
+            conv(N, N), GDN(N), conv(N, M),
+            Win_noShift_Attention(dim=M, num_heads=8, window_size=4, shift_size=2))
+        self.g_s = nn.Sequential(
+            Win_noShift_Attention(dim=M, num_heads=8, window_size=4, shift_size=2),
+            deconv(M, N), GDN(N, inverse=True), deconv(N, N), GDN(N, inverse=True),
+            Win_noShift_Attention(dim=N, num_heads=8, window_size=8, shift_size=4),
+            deconv(N, N), GDN(N, inverse=True), deconv(N, 3))
+        self.h_a = nn.Sequential(conv3x3(M, 320), nn.GELU(), conv3x3(320, 288), nn.GELU(),
+                                 conv3x3(288, 256, stride=2), nn.GELU(), conv3x3(256, 224), nn.GELU(),
+                                 conv3x3(224, 192, stride=2))
+
+        def hyper_synthesis():
+            return nn.Sequential(conv3x3(192, 192), nn.GELU(), subpel_conv3x3(192, 224, 2), nn.GELU(),
+                                 conv3x3(224, 256), nn.GELU(), subpel_conv3x3(256, 288, 2), nn.GELU(),
+                                 conv3x3(288, M))
+
+        self.h_mean_s = hyper_synthesis()
+        self.h_scale_s = hyper_synthesis()
+        ms = self.max_support_slices
+        self.cc_mean_transforms = nn.ModuleList(_stack5(M + 32 * min(i, ms)) for i in range(self.num_slices))
+        self.cc_scale_transforms = nn.ModuleList(_stack5(M + 32 * min(i, ms)) for i in range(self.num_slices))
+        self.lrp_transforms = nn.ModuleList(_stack5(M + 32 * min(i + 1, ms + 1)) for i in range(self.num_slices))
+        self.entropy_bottleneck = EntropyBottleneck(N)
+        self.gaussian_conditional = GaussianConditional(None)
+
+    def _analysis(self, x):
+        return self.g_a(x).contiguous()
+
+    def _synthesis(self, y_hat):
+        return self.g_s(y_hat)
+
+
+models = {"stf": SymmetricalTransFormer, "cnn": WACNN}   # compressai/zoo/__init__.py:20-27 (in-scope entries)

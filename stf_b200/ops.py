@@ -1,0 +1,224 @@
+"""Tensor-level wrappers over the C ABI (include/stf_b200.h).  Each function allocates its outputs
+with torch, passes raw device pointers + the current CUDA stream through ctypes and raises on a
+non-zero status.  No CPU / eager fallback: CPU tensors are rejected.
+"""
+import ctypes
+import math
+
+import numpy as np
+import torch
+
+from . import _C
+
+_f32p = ctypes.POINTER(ctypes.c_float)
+
+
+def _dev(t, name, dtype=torch.float32):
+    if t is None:
+        return None
+    if not t.is_cuda:
+        raise RuntimeError(f"stf_b200: `{name}` must be a CUDA tensor (there is no CPU path)")
+    if t.dtype != dtype:
+        raise TypeError(f"stf_b200: `{name}` must be {dtype}, got {t.dtype}")
+    if not t.is_contiguous():
+        raise ValueError(f"stf_b200: `{name}` must be contiguous")
+    return t
+
+
+def _host_table(table):
+    """fp32 host copy of a scale table + ctypes pointer (kept alive by the returned array)."""
+    if isinstance(table, torch.Tensor):
+        table = table.detach().cpu().numpy()
+    arr = np.ascontiguousarray(table, dtype=np.float32).reshape(-1)
+    return arr, arr.ctypes.data_as(_f32p)
+
+
+# ------------------------------------------------------------------------------------ entropy
+
+def build_indexes(scales, table, scale_bound=0.11):
+    """GaussianConditional.build_indexes (reference entropy_models.py:661-666) -> int32."""
+    s = _dev(scales.contiguous() if scales.is_cuda else scales, "scales")
+    out = torch.empty(s.shape, dtype=torch.int32, device=s.device)
+    arr, p = _host_table(table)
+    rc = _C.lib().stf_build_indexes(s.data_ptr(), out.data_ptr(), s.numel(), p, arr.size, float(scale_bound),
+                                    _C.stream())
+    _C.check(rc, "stf_build_indexes")
+    return out
+
+
+def quantize_symbols(x, means=None):
+    """EntropyModel.quantize(x, "symbols", means) (reference entropy_models.py:126-150)."""
+    x = _dev(x, "inputs")
+    m = None
+    if means is not None:
+        m = _dev(means.expand_as(x).contiguous(), "means")
+    out = torch.empty(x.shape, dtype=torch.int32, device=x.device)
+    _C.check(_C.lib().stf_quantize_symbols(x.data_ptr(), _C.ptr(m), out.data_ptr(), x.numel(), _C.stream()),
+             "stf_quantize_symbols")
+    return out
+
+
+def quantize_dequantize(x, means=None):
+    """EntropyModel.quantize(x, "dequantize", means): round_half_even(x - means) + means, in fp32."""
+    x = _dev(x, "inputs")
+    m = None
+    if means is not None:
+        m = _dev(means.expand_as(x).contiguous(), "means")
+    out = torch.empty_like(x)
+    _C.check(_C.lib().stf_quantize_dequantize(x.data_ptr(), _C.ptr(m), out.data_ptr(), x.numel(), _C.stream()),
+             "stf_quantize_dequantize")
+    return out
+
+
+def _slice_geom(y, channel_offset, channels):
+    """(B, Ctot, h, w) contiguous tensor -> base pointer of the channel slice, batch stride, plane."""
+    B, Ctot = y.shape[0], y.shape[1]
+    plane = int(np.prod(y.shape[2:])) if y.dim() > 2 else 1
+    if channel_offset < 0 or channel_offset + channels > Ctot:
+        raise ValueError("channel slice out of range")
+    return y.data_ptr() + 4 * channel_offset * plane, Ctot * plane, plane, B
+
+
+def gaussian_compress_step(y, channel_offset, scales, means, table, symbols_out, indexes_out, out_offset,
+                           scale_bound=0.11, want_y_hat=True):
+    """Fused build_indexes + quantize("symbols") + dequantize of one slice (stf.py:717-719).
+
+    y: full (B, M, h, w) latent; the slice is channels [channel_offset, channel_offset + C_s).
+    scales / means: dense (B, C_s, h, w).  symbols_out / indexes_out: (B, total) int32 buffers; the
+    slice is written at element offset `out_offset` of every row (reference coding order)."""
+    y = _dev(y, "y")
+    scales, means = _dev(scales, "scales"), _dev(means, "means")
+    Cs = scales.shape[1]
+    yp, ystride, plane, B = _slice_geom(y, channel_offset, Cs)
+    symbols_out, indexes_out = _dev(symbols_out, "symbols", torch.int32), _dev(indexes_out, "indexes", torch.int32)
+    total = symbols_out.shape[1]
+    if out_offset + Cs * plane > total:
+        raise ValueError("symbol buffer too small")
+    y_hat = torch.empty_like(scales) if want_y_hat else None
+    arr, p = _host_table(table)
+    rc = _C.lib().stf_gaussian_compress_step(
+        yp, ystride, scales.data_ptr(), means.data_ptr(), symbols_out.data_ptr() + 4 * out_offset,
+        indexes_out.data_ptr() + 4 * out_offset, total, _C.ptr(y_hat), B, Cs, plane, p, arr.size,
+        float(scale_bound), _C.stream())
+    _C.check(rc, "stf_gaussian_compress_step")
+    return y_hat
+
+
+def dequantize(symbols, sym_offset, means):
+    """EntropyModel.dequantize for one decoded slice: symbols (B, total) int32 device buffer, the slice
+    starts at element `sym_offset` of each row; means (B, C_s, h, w) -> y_hat like means."""
+    symbols = _dev(symbols, "symbols", torch.int32)
+    means = _dev(means, "means")
+    B, Cs = means.shape[0], means.shape[1]
+    plane = means[0, 0].numel()
+    out = torch.empty_like(means)
+    rc = _C.lib().stf_dequantize(symbols.data_ptr() + 4 * sym_offset, symbols.shape[1], means.data_ptr(),
+                                 out.data_ptr(), B, Cs, plane, _C.stream())
+    _C.check(rc, "stf_dequantize")
+    return out
+
+
+def gaussian_likelihood(y, channel_offset, scales, means, scale_bound=0.11, lik_bound=1e-9, want_y_hat=True,
+                        ste_round=False):
+    """GaussianConditional.forward (eval) + ste_round of the slice (entropy_models.py:645-659, stf.py:623-626).
+    Returns (y_hat or None, likelihood)."""
+    y = _dev(y, "y")
+    scales = _dev(scales, "scales")
+    means = _dev(means, "means") if means is not None else None
+    Cs = scales.shape[1]
+    yp, ystride, plane, B = _slice_geom(y, channel_offset, Cs)
+    lik = torch.empty_like(scales)
+    y_hat = torch.empty_like(scales) if want_y_hat else None
+    rc = _C.lib().stf_gaussian_likelihood(yp, ystride, scales.data_ptr(), _C.ptr(means), _C.ptr(y_hat),
+                                          lik.data_ptr(), B, Cs, plane, float(scale_bound), float(lik_bound),
+                                          int(bool(ste_round)), _C.stream())
+    _C.check(rc, "stf_gaussian_likelihood")
+    return y_hat, lik
+
+
+def entropy_bottleneck(z, params, lik_bound=1e-9, want_z_hat=True, want_lik=True, want_symbols=False,
+                       ste_round=False):
+    """EntropyBottleneck.forward (eval) without the permutes; params: (C, 60) packed (see header)."""
+    z = _dev(z, "z")
+    params = _dev(params, "params")
+    B, C = z.shape[0], z.shape[1]
+    plane = z[0, 0].numel()
+    z_hat = torch.empty_like(z) if want_z_hat else None
+    lik = torch.empty_like(z) if want_lik else None
+    sym = torch.empty(z.shape, dtype=torch.int32, device=z.device) if want_symbols else None
+    rc = _C.lib().stf_entropy_bottleneck(z.data_ptr(), params.data_ptr(), _C.ptr(z_hat), _C.ptr(lik), _C.ptr(sym),
+                                         B, C, plane, float(lik_bound), int(bool(ste_round)), _C.stream())
+    _C.check(rc, "stf_entropy_bottleneck")
+    return z_hat, lik, sym
+
+
+# ------------------------------------------------------------------------------------ tensor-core linear
+
+class PackedLinear:
+    """A torch Linear weight (N, K) re-packed for the tcgen05 kernel (+ optional bias)."""
+
+    def __init__(self, weight, bias=None):
+        w = _dev(weight.detach().contiguous(), "weight")
+        self.N, self.K = w.shape
+        self.packed = torch.empty_like(w)
+        _C.check(_C.lib().stf_pack_linear_weight(w.data_ptr(), self.packed.data_ptr(), self.N, self.K, _C.stream()),
+                 "stf_pack_linear_weight")
+        self.bias = None if bias is None else _dev(bias.detach().contiguous(), "bias")
+
+
+def linear(x, lin, *, M=None, rows=_C.ROWS_DENSE, ln=None, epilogue=_C.EPI_STORE, residual=None, q_cols=0,
+           q_scale=1.0, geom=None, out=None, out_rows=None, out_cols=None):
+    """Y = epilogue(prologue(X) . W^T)   (stf_linear in include/stf_b200.h).
+
+    x: (rows_in, ldx) fp32; ln: (gamma, beta, eps) or None; geom: (batch, H, W, window, shift)."""
+    x = _dev(x, "x")
+    x2 = x.reshape(-1, x.shape[-1])
+    if x2.shape[1] * (4 if rows == _C.ROWS_MERGE else 1) != lin.K:
+        raise ValueError(f"stf_linear: input features {x2.shape[1]} do not match the weight's K={lin.K}")
+    a = _C.LinearArgs()
+    a.M = x2.shape[0] if M is None else int(M)
+    a.N, a.K = lin.N, lin.K
+    a.x, a.ldx = x2.data_ptr(), x2.shape[1]
+    a.w_packed, a.bias = lin.packed.data_ptr(), _C.ptr(lin.bias)
+    if out is None:
+        out = torch.empty((a.M if out_rows is None else out_rows, lin.N if out_cols is None else out_cols),
+                          dtype=torch.float32, device=x.device)
+    out = _dev(out, "out")
+    a.y, a.ldy = out.data_ptr(), out.shape[-1]
+    a.rows = rows
+    if ln is not None:
+        g, b, eps = ln
+        g, b = _dev(g.detach(), "ln.weight"), _dev(b.detach(), "ln.bias")
+        a.ln_gamma, a.ln_beta, a.ln_eps = g.data_ptr(), b.data_ptr(), float(eps)
+    a.epilogue = epilogue
+    if residual is not None:
+        residual = _dev(residual, "residual")
+        a.residual = residual.data_ptr()
+    a.q_cols, a.q_scale = int(q_cols), float(q_scale)
+    if geom is not None:
+        a.batch, a.H, a.W, a.window, a.shift = (int(v) for v in geom)
+    _C.check(_C.lib().stf_linear(ctypes.byref(a), _C.stream()), "stf_linear")
+    return out
+
+
+def window_attention_core(qkv, bias_table, num_windows, C, heads, ws, shift, Hp=0, Wp=0, mask=None):
+    """softmax(q k^T + B + mask) v per (window, head); qkv (num_windows*ws*ws, 3C), q pre-scaled."""
+    qkv = _dev(qkv, "qkv")
+    bias_table = _dev(bias_table.detach(), "relative_position_bias_table")
+    out = torch.empty((qkv.shape[0], C), dtype=torch.float32, device=qkv.device)
+    mw = 0
+    if mask is not None:
+        mask = _dev(mask.contiguous(), "mask")
+        mw = mask.shape[0]
+    rc = _C.lib().stf_window_attention(qkv.data_ptr(), out.data_ptr(), bias_table.data_ptr(), _C.ptr(mask), mw,
+                                       int(num_windows), C, heads, ws, shift, Hp, Wp, _C.stream())
+    _C.check(rc, "stf_window_attention")
+    return out
+
+
+def launch_count():
+    return int(_C.lib().stf_launch_count())
+
+
+def ceil_to(v, m):
+    return int(math.ceil(v / m)) * m

@@ -1,0 +1,147 @@
+"""CPU: the C-ABI library loads and exports every symbol include/stf_b200.h declares, the ctypes
+stub agrees with the header, and the HOST-side rANS codec (the part of the library that runs on the
+CPU by design) is bit-exact against the oracle and the reference's recorded streams.  No CUDA
+compute entry point is called here."""
+import ctypes
+import hashlib
+import json
+import os
+import re
+
+import numpy as np
+import pytest
+
+from oracle import entropy as OE
+from stf_b200 import _C, ans
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def header_functions():
+    src = open(os.path.join(ROOT, "include", "stf_b200.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(stf_[a-z0-9_]+)\s*\(", src)))
+
+
+def test_library_exports_every_declared_symbol():
+    names = header_functions()
+    assert len(names) >= 20
+    L = ctypes.CDLL(_C.LIB_PATH)
+    for n in names:
+        assert hasattr(L, n), f"{n} declared in include/stf_b200.h but not exported"
+    assert sorted(_C.SIGNATURES) == names, "stf_b200/_C.py and include/stf_b200.h disagree"
+    assert b"sm_100a" in _C.lib().stf_version()
+
+
+def test_library_contains_sm100a_tcgen05_code():
+    """The shipped .so carries sm_100a SASS with tcgen05 (UTC*MMA) and bulk-TMA (UBLKCP) instructions."""
+    import shutil
+    import subprocess
+    cuobjdump = shutil.which("cuobjdump") or "/usr/local/cuda/bin/cuobjdump"
+    if not os.path.exists(cuobjdump):
+        pytest.skip("cuobjdump not available")
+    sass = subprocess.run([cuobjdump, "-sass", _C.LIB_PATH], capture_output=True, text=True).stdout
+    assert "sm_100a" in sass
+    assert re.search(r"UTC\w*MMA", sass), "no tcgen05.mma in SASS"
+    assert "UBLKCP" in sass and "LDTM" in sass
+
+
+@pytest.fixture(scope="module")
+def tables():
+    cdf, lens, offs = OE.gaussian_tables()
+    return cdf, lens, offs, ans.RansTable(cdf, lens, offs)
+
+
+def test_rans_kat_bytes(tables, golden_dir):
+    cdf, lens, offs, tab = tables
+    r = json.load(open(os.path.join(golden_dir, "kat.json")))["rans"]
+    b = ans.RansEncoder().encode_with_indexes(r["symbols"], r["indexes"], cdf.tolist(), lens.tolist(), offs.tolist())
+    assert b.hex() == r["bytes_hex"]
+    assert ans.RansDecoder().decode_with_indexes(b, r["indexes"], cdf.tolist(), lens.tolist(), offs.tolist()) == r["symbols"]
+    enc = ans.BufferedRansEncoder()
+    enc.encode_with_indexes(r["symbols"][:4], r["indexes"][:4], tab)
+    enc.encode_with_indexes(r["symbols"][4:], r["indexes"][4:], tab)
+    assert enc.flush().hex() == r["bytes_hex"]
+
+
+def test_rans_reference_streams(tables, golden_dir):
+    cdf, lens, offs, tab = tables
+    kat = json.load(open(os.path.join(golden_dir, "kat.json")))
+    rng = np.random.default_rng(kat["rans_streams_seed"])
+    table = OE.scale_table().numpy()
+    for rec in kat["rans_streams"]:
+        n, spread = rec["n"], rec["spread"]
+        ix = rng.integers(0, 64, size=n).astype(np.int32)
+        sy = np.rint(rng.standard_normal(n) * table[ix] * spread).astype(np.int32)
+        if n < 4:
+            sy = np.array([70000], dtype=np.int32)[:n]
+        b = ans.encode_array(tab, sy, ix)
+        assert hashlib.sha256(b).hexdigest() == rec["sha256"], f"n={n}"
+        d = ans.RansDecoder()
+        d.set_stream(b)
+        half = n // 2
+        out = np.concatenate([d.decode_stream_array(ix[:half], tab), d.decode_stream_array(ix[half:], tab)])
+        assert np.array_equal(out, sy)
+
+
+@pytest.mark.parametrize("n", [0, 1, 2, 3, 17, 4096, 200000])
+def test_rans_vs_oracle_random(tables, n):
+    cdf, lens, offs, tab = tables
+    rng = np.random.default_rng(n + 5)
+    ix = rng.integers(0, 64, size=n).astype(np.int32)
+    sy = np.rint(rng.standard_normal(n) * OE.scale_table().numpy()[ix] * 2.5).astype(np.int32)
+    if n >= 17:
+        sy[::7] = rng.integers(-5000, 5000, size=sy[::7].size)      # force escapes of several nibble counts
+    b = ans.encode_array(tab, sy, ix)
+    assert b == OE.rans_encode(sy, ix, cdf, lens, offs)
+    assert len(b) % 4 == 0 and len(b) >= 8
+    d = ans.RansDecoder()
+    d.set_stream(b)
+    assert np.array_equal(d.decode_stream_array(ix, tab), sy)
+
+
+def test_rans_batch_threads_identical(tables):
+    cdf, lens, offs, tab = tables
+    rng = np.random.default_rng(3)
+    syms, idxs = [], []
+    for i in range(6):
+        n = 1000 + 977 * i
+        ix = rng.integers(0, 64, size=n).astype(np.int32)
+        idxs.append(ix)
+        syms.append(np.rint(rng.standard_normal(n) * OE.scale_table().numpy()[ix]).astype(np.int32))
+    single = [ans.encode_array(tab, s, i) for s, i in zip(syms, idxs)]
+    assert ans.encode_batch(tab, syms, idxs, threads=4) == single
+    decs = []
+    for b in single:
+        d = ans.RansDecoder()
+        d.set_stream(b)
+        decs.append(d)
+    outs = ans.decode_batch(decs, tab, idxs, threads=3)
+    assert all(np.array_equal(o, s) for o, s in zip(outs, syms))
+
+
+def test_rans_error_paths(tables):
+    cdf, lens, offs, tab = tables
+    with pytest.raises(ValueError):
+        ans.RansTable(np.zeros((2, 5), np.int32), [5, 5], [0, 0])          # rows do not end at 65536
+    with pytest.raises(ValueError):
+        ans.encode_array(tab, [0, 1], [0])
+    with pytest.raises(ValueError):
+        ans.encode_array(tab, [0], [64])                                      # index out of range
+    d = ans.RansDecoder()
+    with pytest.raises(ValueError):
+        d.set_stream(b"\0\0\0")
+    d.set_stream(ans.encode_array(tab, [1, 2, 3], [3, 3, 3]))
+    with pytest.raises(ValueError):
+        d.decode_stream_array(np.zeros(100000, np.int32) + 63, tab)          # runs off the end of the stream
+
+
+def test_pmf_to_quantized_cdf_matches_oracle():
+    rng = np.random.default_rng(0)
+    for n in (1, 2, 5, 23, 400):
+        p = rng.random(n).astype(np.float32) ** 4
+        p /= p.sum()
+        assert ans.pmf_to_quantized_cdf(p) == OE.pmf_to_quantized_cdf(p).tolist()
+    spike = np.zeros(300, np.float32)
+    spike[150] = 1.0                                                          # many zero-mass symbols -> stealing
+    assert ans.pmf_to_quantized_cdf(spike) == OE.pmf_to_quantized_cdf(spike).tolist()

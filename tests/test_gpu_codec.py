@@ -1,0 +1,136 @@
+"""GPU parity, end to end: SymmetricalTransFormer / WACNN forward, compress and decompress on the
+CUDA path against the CPU oracle (same synthetic weights, same images) and the recorded reference
+bitstreams.
+
+What can and cannot be bit-exact: a round() sits in the middle of the path, so any
+change of summation order upstream (here: tensor-core GEMMs) flips the symbols whose pre-round value
+lies within eps of .5.  Hence:
+  * bit-exact: build_indexes / symbols given identical inputs (tests/test_gpu_entropy.py) and the
+    rANS bitstream given identical symbols (below, and tests/test_cabi_host.py);
+  * end to end: symbol flip rate, tolerance on non-flipped y_hat, PSNR between reconstructions,
+    bitstream length;
+  * exact self-consistency: decompress(compress(x)) reproduces the encoder's own reconstruction."""
+import hashlib
+import json
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import codec as OC
+from stf_b200.synth import synthetic_image, synthetic_state_dict
+
+pytestmark = pytest.mark.gpu
+
+
+def _spec(golden_dir, name):
+    return {k: (tuple(s), getattr(torch, d.split(".")[-1])) for k, (s, d) in
+            json.load(open(os.path.join(golden_dir, f"{name}_spec.json"))).items()}
+
+
+def _build(golden_dir, name, seed=0):
+    from stf_b200.models import models
+    net = models[name]()
+    spec = _spec(golden_dir, name)
+    ours = {k: (tuple(v.shape), v.dtype) for k, v in net.state_dict().items()}
+    assert set(ours) == set(spec), "checkpoint key space differs from the reference"
+    assert all(ours[k][0] == spec[k][0] for k in spec if spec[k][0] != (0,)), "parameter shapes differ"
+    sd = synthetic_state_dict(spec, seed)
+    torch.nn.Module.load_state_dict(net, sd, strict=False)
+    net = net.cuda().eval()
+    net.update(force=True)
+    return net, sd
+
+
+def psnr(a, b):
+    return float(10 * torch.log10(1.0 / torch.mean((a.float() - b.float()) ** 2).clamp_min(1e-20)))
+
+
+@pytest.mark.parametrize("name,Ora,case_i", [("stf", OC.StfOracle, 0), ("stf", OC.StfOracle, 1), ("cnn", OC.WacnnOracle, 0)])
+def test_codec_vs_oracle_and_golden(golden_dir, name, Ora, case_i):
+    e2e = json.load(open(os.path.join(golden_dir, "e2e.json")))[name]
+    case = e2e["cases"][case_i]
+    net, sd = _build(golden_dir, name, e2e["weights_seed"])
+    x = synthetic_image(1, case["H"], case["W"], seed=case["image_seed"])
+    ora = Ora(sd)
+    # tables: bit-identical to the oracle's (hence to the reference's, test_oracle_pins)
+    assert np.array_equal(net.gaussian_conditional.quantized_cdf.cpu().numpy(), ora.gc_cdf)
+    assert np.array_equal(net.entropy_bottleneck.quantized_cdf.cpu().numpy(), ora.eb_cdf)
+
+    dbg, odbg = {}, {}
+    enc = net.compress(x.cuda(), debug=dbg)
+    oenc = ora.compress(x, debug=odbg)
+    assert oenc["strings"][0][0].hex() == case["y_string_hex"]          # oracle still pinned to the reference
+    assert list(enc["shape"]) == case["z_shape"]
+    # y: analysis transform through 12 tensor-core Swin blocks
+    y, oy = dbg["y"].cpu(), odbg["y"]
+    assert (y - oy).abs().max().item() <= 2e-2 * oy.abs().max().item()
+    sym, osym = dbg["symbols"].reshape(-1), odbg["symbols"].reshape(-1)
+    idx, oidx = dbg["indexes"].reshape(-1), odbg["indexes"].reshape(-1)
+    flips = float((sym != osym).float().mean())
+    idx_flips = float((idx != oidx).float().mean())
+    assert int((sym - osym).abs().max()) <= 1 or flips < 0.02           # flips are +-1 near ties
+    assert flips < 0.05 and idx_flips < 0.05, (flips, idx_flips)
+    ny, no = len(enc["strings"][0][0]), len(oenc["strings"][0][0])
+    assert abs(ny - no) <= 0.02 * no + 16
+    # bitstream is bit-exact GIVEN identical symbols: push the oracle's symbols through our coder
+    from stf_b200 import ans
+    tab = net.gaussian_conditional.rans_table()
+    assert ans.encode_array(tab, osym.numpy(), oidx.numpy()).hex() == case["y_string_hex"]
+    # ... and our own symbols through the oracle coder give our own string
+    from oracle import entropy as OE
+    assert OE.rans_encode(sym.numpy(), idx.numpy(), ora.gc_cdf, ora.gc_len, ora.gc_off) == enc["strings"][0][0]
+
+    # decode: exact self-consistency + closeness to the oracle's reconstruction
+    dec = net.decompress(enc["strings"], enc["shape"])
+    fwd = net(x.cuda())
+    assert dec["x_hat"].shape == (1, 3, case["H"], case["W"])
+    assert (dec["x_hat"] - fwd["x_hat"].clamp(0, 1)).abs().max().item() < 1e-4
+    odec = ora.decompress(oenc["strings"], oenc["shape"])
+    assert psnr(dec["x_hat"].cpu(), odec["x_hat"]) > 30.0
+    # our decoder on the REFERENCE's recorded strings (cross-implementation decode)
+    ref_strings = [[bytes.fromhex(case["y_string_hex"])], [bytes.fromhex(h) for h in case["z_strings_hex"]]]
+    xdec = net.decompress(ref_strings, case["z_shape"])
+    assert psnr(xdec["x_hat"].cpu(), odec["x_hat"]) > 20.0
+    # likelihoods: rate estimate agrees with the reference's recorded one
+    bpp_y = float(-torch.log2(fwd["likelihoods"]["y"]).sum() / (case["H"] * case["W"]))
+    bpp_z = float(-torch.log2(fwd["likelihoods"]["z"]).sum() / (case["H"] * case["W"]))
+    assert abs(bpp_y - case["bpp_y_est"]) <= 0.02 * case["bpp_y_est"]
+    assert abs(bpp_z - case["bpp_z_est"]) <= 0.02 * case["bpp_z_est"] + 1e-3
+
+
+def test_batched_compress_matches_per_image(golden_dir):
+    """Batch sharding contract: image b of a batched call yields the same strings
+    as a batch-1 call on that image, and a batched decompress reproduces each batch-1 reconstruction."""
+    net, _ = _build(golden_dir, "stf")
+    x = torch.cat([synthetic_image(1, 64, 96, seed=s) for s in (1, 2, 3)]).cuda()
+    enc = net.compress(x)
+    assert len(enc["strings"][0]) == 3 and len(enc["strings"][1]) == 3
+    dec = net.decompress(enc["strings"], enc["shape"])
+    same = 0
+    for b in range(3):
+        e1 = net.compress(x[b:b + 1])
+        same += int(e1["strings"][0][0] == enc["strings"][0][b] and e1["strings"][1][0] == enc["strings"][1][b])
+        d1 = net.decompress(e1["strings"], e1["shape"])
+        assert psnr(d1["x_hat"], dec["x_hat"][b:b + 1]) > 35.0
+    # cuDNN may pick batch-dependent algorithms for the conv stacks (outside our kernels); our own
+    # kernels are batch-invariant.  Report rather than require bit-identity of all three.
+    print(f"batched == per-image strings for {same}/3 images")
+    full = net(x)
+    assert (dec["x_hat"] - full["x_hat"].clamp(0, 1)).abs().max().item() < 1e-4
+
+
+def test_model_error_paths(golden_dir):
+    from stf_b200.models import SymmetricalTransFormer
+    net = SymmetricalTransFormer().cuda().eval()
+    x = synthetic_image(1, 64, 64).cuda()
+    with pytest.raises(ValueError):
+        net.compress(x)                                   # update() not called: "Uninitialized CDFs"
+    net.train()
+    with pytest.raises(NotImplementedError):
+        with torch.enable_grad():
+            net(x)
+    sd = net.state_dict()
+    net2 = SymmetricalTransFormer.from_state_dict(sd)     # load_state_dict with empty tables round-trips
+    assert set(net2.state_dict()) == set(sd)

@@ -1,0 +1,177 @@
+"""GPU parity: the entropy-model kernels (called through the C ABI via stf_b200.ops / entropy_models)
+against the CPU oracle and the golden vectors recorded from the reference.
+Integer outputs (indexes, symbols) are bit-exact; fp32 outputs are checked with
+|d| <= 1e-3 * |ref| + tiny absolute floor (BASELINE.json north_star tolerance), and in practice match
+to a few ulp."""
+import json
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import entropy as OE
+
+pytestmark = pytest.mark.gpu
+
+RTOL = 1e-3   # north-star fp32 tolerance
+
+
+@pytest.fixture(scope="module")
+def ent(golden_dir):
+    return np.load(os.path.join(golden_dir, "entropy_ops.npz"))
+
+
+@pytest.fixture(scope="module")
+def kat(golden_dir):
+    return json.load(open(os.path.join(golden_dir, "kat.json")))
+
+
+def cu(a):
+    return torch.as_tensor(a).cuda()
+
+
+def test_build_indexes_kat_and_golden(ent, kat):
+    from stf_b200 import ops
+    table = OE.scale_table()
+    s = torch.tensor([float(v) for v in kat["build_indexes_in"]])
+    assert ops.build_indexes(s.cuda(), table).cpu().tolist() == kat["build_indexes_out"]
+    idx = ops.build_indexes(cu(ent["bi_scales"]), table)
+    assert np.array_equal(idx.cpu().numpy(), ent["bi_indexes"])
+
+
+@pytest.mark.parametrize("n", [1, 3, 4, 1023, 49152, 131072, 360448, 1 << 22])
+def test_build_indexes_vs_oracle_sizes(n):
+    """Natural slice sizes of the BASELINE configs, ragged sizes (scalar tail path) and a large one."""
+    from stf_b200 import ops
+    g = torch.Generator().manual_seed(n)
+    table = OE.scale_table()
+    s = torch.exp(torch.rand(n, generator=g) * (np.log(400) - np.log(0.01)) + np.log(0.01))
+    k = min(n, 64)
+    s[:k] = table[:k]                                       # exact table hits (<= comparison edge)
+    if n > 200:
+        s[64:128] = torch.nextafter(table, torch.tensor(float("inf")))
+        s[128:192] = torch.nextafter(table, torch.tensor(0.0))
+        s[192:196] = torch.tensor([float("nan"), float("inf"), -float("inf"), 0.0])
+    ref = OE.build_indexes(s)
+    out = ops.build_indexes(s.cuda(), table)
+    assert out.dtype == torch.int32 and torch.equal(out.cpu(), ref)
+
+
+def test_build_indexes_non_monotone_table():
+    from stf_b200 import ops
+    table = torch.tensor([0.5, 0.2, 0.9, 0.3, 2.0])        # reference semantics = linear count
+    s = torch.rand(5000) * 3
+    ref = OE.build_indexes(s, table, scale_bound=0.11)
+    assert torch.equal(ops.build_indexes(s.cuda(), table, 0.11).cpu(), ref)
+
+
+def test_quantize_kats(ent, kat):
+    from stf_b200.entropy_models import GaussianConditional
+    gc = GaussianConditional(None).cuda()
+    assert gc.quantize(cu(kat["quantize_in"]).float(), "symbols").cpu().tolist() == kat["quantize_out"]
+    y, mu = cu(ent["gc_y"]), cu(ent["gc_mu"])
+    q = gc.quantize(y, "symbols", mu)
+    assert q.dtype == torch.int32 and np.array_equal(q.cpu().numpy(), ent["gc_symbols"])
+    assert np.array_equal(gc.dequantize(q, mu).cpu().numpy(), ent["gc_dequant"])
+    assert np.array_equal(gc.quantize(y, "dequantize", mu).cpu().numpy(), ent["gc_out"])
+    with pytest.raises(ValueError):
+        gc.quantize(y, "bogus")
+
+
+def test_gaussian_conditional_forward_golden(ent, kat):
+    from stf_b200.entropy_models import GaussianConditional
+    gc = GaussianConditional(None).cuda().eval()
+    f = kat["gc_forward"]
+    out, lik = gc(cu(f["y"]).float(), cu(f["scale"]).float(), cu(f["mu"]).float())
+    assert out.cpu().tolist() == f["out"]
+    assert np.allclose(lik.cpu().numpy(), np.array(f["lik"], dtype=np.float32), rtol=RTOL, atol=1e-12)
+    out, lik = gc(cu(ent["gc_y"]), cu(ent["gc_scale"]), cu(ent["gc_mu"]))
+    assert np.array_equal(out.cpu().numpy(), ent["gc_out"])
+    ref = ent["gc_lik"]
+    err = np.abs(lik.cpu().numpy() - ref)
+    assert np.all(err <= RTOL * ref + 1e-9)
+    assert np.median(err / ref) < 1e-6          # in practice: ulp-level agreement
+
+
+@pytest.mark.parametrize("shape", [(1, 32, 32, 48), (16, 32, 16, 16), (2, 32, 5, 7), (1, 32, 88, 128)])
+def test_compress_step_and_likelihood_slices(shape):
+    """Slice addressing inside a larger latent + the fused compress step, vs the oracle."""
+    from stf_b200 import ops
+    B, Cs, h, w = shape
+    M = 3 * Cs
+    g = torch.Generator().manual_seed(h * w)
+    y = 6 * torch.randn(B, M, h, w, generator=g)
+    mu = 2 * torch.randn(B, Cs, h, w, generator=g)
+    sc = torch.exp(torch.rand(B, Cs, h, w, generator=g) * 9 - 4.5)
+    y[:, Cs:2 * Cs].view(-1)[:16] = (mu.view(-1)[:16] + torch.arange(-8, 8) + 0.5)   # ties
+    table = OE.scale_table()
+    total = M * h * w
+    sym = torch.full((B, total), -7, dtype=torch.int32).cuda()
+    idx = torch.full((B, total), -7, dtype=torch.int32).cuda()
+    off = Cs * h * w
+    yh = ops.gaussian_compress_step(y.cuda(), Cs, sc.cuda(), mu.cuda(), table, sym, idx, off)
+    ys = y[:, Cs:2 * Cs]
+    q = OE.quantize(ys, "symbols", mu)
+    assert torch.equal(sym[:, off:2 * off].cpu().reshape(B, Cs, h, w), q)
+    assert torch.equal(idx[:, off:2 * off].cpu().reshape(B, Cs, h, w), OE.build_indexes(sc))
+    assert torch.equal(yh.cpu(), OE.dequantize(q, mu))
+    assert int((sym[:, :off] != -7).sum()) == 0 and int((sym[:, 2 * off:] != -7).sum()) == 0   # no stray writes
+    # decode side: dequantize from the strided symbol buffer
+    assert torch.equal(ops.dequantize(sym, off, mu.cuda()).cpu(), OE.dequantize(q, mu))
+    # likelihood + ste_round value
+    yhat, lik = ops.gaussian_likelihood(y.cuda(), Cs, sc.cuda(), mu.cuda(), ste_round=True)
+    o_out, o_lik = OE.gaussian_conditional_eval(ys, sc, mu)
+    assert torch.equal(yhat.cpu(), OE.ste_round_value(ys - mu) + mu)
+    err = (lik.cpu() - o_lik).abs()
+    assert bool((err <= RTOL * o_lik + 1e-9).all())
+    yq, _ = ops.gaussian_likelihood(y.cuda(), Cs, sc.cuda(), mu.cuda(), ste_round=False)
+    assert torch.equal(yq.cpu(), o_out)
+
+
+def test_empty_inputs():
+    from stf_b200 import ops
+    table = OE.scale_table()
+    e = torch.empty(0, device="cuda")
+    assert ops.build_indexes(e, table).numel() == 0
+    assert ops.quantize_symbols(e).numel() == 0
+    with pytest.raises(RuntimeError):
+        ops.build_indexes(torch.ones(4), table)              # CPU tensor: no fallback
+
+
+def _eb(seed, golden=True):
+    from stf_b200.entropy_models import EntropyBottleneck
+    from stf_b200.synth import synthetic_state_dict
+    eb = EntropyBottleneck(192)
+    spec = {"entropy_bottleneck." + k: (tuple(v.shape), v.dtype) for k, v in eb.state_dict().items()}
+    sd = synthetic_state_dict(spec, seed)
+    eb.load_state_dict({k[len("entropy_bottleneck."):]: v for k, v in sd.items()}, strict=False)
+    return eb.cuda().eval()
+
+
+def test_entropy_bottleneck_golden(ent):
+    eb = _eb(int(ent["eb_seed"]))
+    assert eb.update(force=True)
+    assert np.array_equal(eb.quantized_cdf.cpu().numpy(), ent["eb_cdf"])
+    z = cu(ent["eb_z"])
+    out, lik = eb(z)
+    assert np.allclose(out.cpu().numpy(), ent["eb_out"], rtol=1e-6, atol=1e-6)
+    ref = ent["eb_lik"]
+    assert np.all(np.abs(lik.cpu().numpy() - ref) <= RTOL * ref + 1e-9)
+    strings = eb.compress(z)
+    assert [s.hex() for s in strings] == [str(s) for s in ent["eb_strings_hex"]]      # bit-exact bitstream
+    assert np.array_equal(eb.decompress(strings, z.shape[-2:]).cpu().numpy(), ent["eb_zhat"])
+    with pytest.raises(ValueError):
+        _eb(3).compress(z)                                                             # update() not run
+
+
+@pytest.mark.parametrize("shape", [(16, 192, 4, 4), (1, 192, 8, 12), (1, 192, 22, 32)])
+def test_entropy_bottleneck_vs_oracle(shape):
+    eb = _eb(5)
+    p = {k: v.detach().cpu() for k, v in eb.state_dict().items() if k in OE.eb_param_names()}
+    g = torch.Generator().manual_seed(shape[2])
+    z = 5 * torch.randn(*shape, generator=g)
+    out, lik = eb(z.cuda())
+    o_out, o_lik = OE.eb_forward_eval(p, z)
+    assert torch.allclose(out.cpu(), o_out, rtol=1e-6, atol=1e-6)
+    assert bool(((lik.cpu() - o_lik).abs() <= RTOL * o_lik + 1e-9).all())
