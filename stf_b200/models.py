@@ -142,9 +142,12 @@ class _SliceCodec(CompressionModel):
     def _needed_as_support(self, i):
         return self.max_support_slices < 0 or i < self.max_support_slices
 
-    @torch.no_grad()
     def forward(self, x):
         self._require_inference()
+        with torch.no_grad():
+            return self._forward_eval(x)
+
+    def _forward_eval(self, x):
         y = self._analysis(x)
         hw = y.shape[2:]
         z = self.h_a(y)
@@ -171,7 +174,6 @@ class _SliceCodec(CompressionModel):
 
     @torch.no_grad()
     def compress(self, x, debug=None):
-        self._require_inference()
         gc = self.gaussian_conditional
         y_table = gc.rans_table()
         y = self._analysis(x)
@@ -210,7 +212,6 @@ class _SliceCodec(CompressionModel):
 
     @torch.no_grad()
     def decompress(self, strings, shape):
-        self._require_inference()
         assert isinstance(strings, list) and len(strings) == 2
         gc = self.gaussian_conditional
         y_table = gc.rans_table()

@@ -8,9 +8,24 @@ import math
 import numpy as np
 import torch
 
-from . import _C
+from . import _C, profiler
 
 _f32p = ctypes.POINTER(ctypes.c_float)
+
+
+def _launch(kernel, nbytes, fn, *args):
+    """Call one C-ABI entry point; raise on a non-zero status.  `kernel` / `nbytes` name the CUDA kernel
+    and its algorithmic bytes for profiler.capture()."""
+    cap = profiler.ACTIVE
+    if cap is None:
+        rc = fn(*args)
+    else:
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        rc = fn(*args)
+        e1.record()
+        cap.add(kernel, nbytes, e0, e1)
+    _C.check(rc, fn.__name__)
 
 
 def _dev(t, name, dtype=torch.float32):
@@ -39,10 +54,11 @@ def build_indexes(scales, table, scale_bound=0.11):
     """GaussianConditional.build_indexes (reference entropy_models.py:661-666) -> int32."""
     s = _dev(scales.contiguous() if scales.is_cuda else scales, "scales")
     out = torch.empty(s.shape, dtype=torch.int32, device=s.device)
+    if s.numel() == 0:
+        return out
     arr, p = _host_table(table)
-    rc = _C.lib().stf_build_indexes(s.data_ptr(), out.data_ptr(), s.numel(), p, arr.size, float(scale_bound),
-                                    _C.stream())
-    _C.check(rc, "stf_build_indexes")
+    _launch("compress_step_kernel(build_indexes)", 8 * s.numel(), _C.lib().stf_build_indexes, s.data_ptr(),
+            out.data_ptr(), s.numel(), p, arr.size, float(scale_bound), _C.stream())
     return out
 
 
@@ -53,8 +69,10 @@ def quantize_symbols(x, means=None):
     if means is not None:
         m = _dev(means.expand_as(x).contiguous(), "means")
     out = torch.empty(x.shape, dtype=torch.int32, device=x.device)
-    _C.check(_C.lib().stf_quantize_symbols(x.data_ptr(), _C.ptr(m), out.data_ptr(), x.numel(), _C.stream()),
-             "stf_quantize_symbols")
+    if x.numel() == 0:
+        return out
+    _launch("quantize_symbols_kernel", (8 if m is None else 12) * x.numel(), _C.lib().stf_quantize_symbols,
+            x.data_ptr(), _C.ptr(m), out.data_ptr(), x.numel(), _C.stream())
     return out
 
 
@@ -65,8 +83,10 @@ def quantize_dequantize(x, means=None):
     if means is not None:
         m = _dev(means.expand_as(x).contiguous(), "means")
     out = torch.empty_like(x)
-    _C.check(_C.lib().stf_quantize_dequantize(x.data_ptr(), _C.ptr(m), out.data_ptr(), x.numel(), _C.stream()),
-             "stf_quantize_dequantize")
+    if x.numel() == 0:
+        return out
+    _launch("quantize_dequantize_kernel", (8 if m is None else 12) * x.numel(), _C.lib().stf_quantize_dequantize,
+            x.data_ptr(), _C.ptr(m), out.data_ptr(), x.numel(), _C.stream())
     return out
 
 
@@ -96,11 +116,10 @@ def gaussian_compress_step(y, channel_offset, scales, means, table, symbols_out,
         raise ValueError("symbol buffer too small")
     y_hat = torch.empty_like(scales) if want_y_hat else None
     arr, p = _host_table(table)
-    rc = _C.lib().stf_gaussian_compress_step(
-        yp, ystride, scales.data_ptr(), means.data_ptr(), symbols_out.data_ptr() + 4 * out_offset,
-        indexes_out.data_ptr() + 4 * out_offset, total, _C.ptr(y_hat), B, Cs, plane, p, arr.size,
-        float(scale_bound), _C.stream())
-    _C.check(rc, "stf_gaussian_compress_step")
+    _launch("compress_step_kernel", (24 if want_y_hat else 20) * B * Cs * plane, _C.lib().stf_gaussian_compress_step,
+            yp, ystride, scales.data_ptr(), means.data_ptr(), symbols_out.data_ptr() + 4 * out_offset,
+            indexes_out.data_ptr() + 4 * out_offset, total, _C.ptr(y_hat), B, Cs, plane, p, arr.size,
+            float(scale_bound), _C.stream())
     return y_hat
 
 
@@ -112,9 +131,8 @@ def dequantize(symbols, sym_offset, means):
     B, Cs = means.shape[0], means.shape[1]
     plane = means[0, 0].numel()
     out = torch.empty_like(means)
-    rc = _C.lib().stf_dequantize(symbols.data_ptr() + 4 * sym_offset, symbols.shape[1], means.data_ptr(),
-                                 out.data_ptr(), B, Cs, plane, _C.stream())
-    _C.check(rc, "stf_dequantize")
+    _launch("dequantize_kernel", 12 * B * Cs * plane, _C.lib().stf_dequantize, symbols.data_ptr() + 4 * sym_offset,
+            symbols.shape[1], means.data_ptr(), out.data_ptr(), B, Cs, plane, _C.stream())
     return out
 
 
@@ -129,10 +147,9 @@ def gaussian_likelihood(y, channel_offset, scales, means, scale_bound=0.11, lik_
     yp, ystride, plane, B = _slice_geom(y, channel_offset, Cs)
     lik = torch.empty_like(scales)
     y_hat = torch.empty_like(scales) if want_y_hat else None
-    rc = _C.lib().stf_gaussian_likelihood(yp, ystride, scales.data_ptr(), _C.ptr(means), _C.ptr(y_hat),
-                                          lik.data_ptr(), B, Cs, plane, float(scale_bound), float(lik_bound),
-                                          int(bool(ste_round)), _C.stream())
-    _C.check(rc, "stf_gaussian_likelihood")
+    _launch("gaussian_likelihood_kernel", (20 if want_y_hat else 16) * B * Cs * plane,
+            _C.lib().stf_gaussian_likelihood, yp, ystride, scales.data_ptr(), _C.ptr(means), _C.ptr(y_hat),
+            lik.data_ptr(), B, Cs, plane, float(scale_bound), float(lik_bound), int(bool(ste_round)), _C.stream())
     return y_hat, lik
 
 
@@ -146,9 +163,10 @@ def entropy_bottleneck(z, params, lik_bound=1e-9, want_z_hat=True, want_lik=True
     z_hat = torch.empty_like(z) if want_z_hat else None
     lik = torch.empty_like(z) if want_lik else None
     sym = torch.empty(z.shape, dtype=torch.int32, device=z.device) if want_symbols else None
-    rc = _C.lib().stf_entropy_bottleneck(z.data_ptr(), params.data_ptr(), _C.ptr(z_hat), _C.ptr(lik), _C.ptr(sym),
-                                         B, C, plane, float(lik_bound), int(bool(ste_round)), _C.stream())
-    _C.check(rc, "stf_entropy_bottleneck")
+    nout = int(want_z_hat) + int(want_lik) + int(want_symbols)
+    _launch("entropy_bottleneck_kernel", 4 * (1 + nout) * z.numel(), _C.lib().stf_entropy_bottleneck, z.data_ptr(),
+            params.data_ptr(), _C.ptr(z_hat), _C.ptr(lik), _C.ptr(sym), B, C, plane, float(lik_bound),
+            int(bool(ste_round)), _C.stream())
     return z_hat, lik, sym
 
 
@@ -161,8 +179,8 @@ class PackedLinear:
         w = _dev(weight.detach().contiguous(), "weight")
         self.N, self.K = w.shape
         self.packed = torch.empty_like(w)
-        _C.check(_C.lib().stf_pack_linear_weight(w.data_ptr(), self.packed.data_ptr(), self.N, self.K, _C.stream()),
-                 "stf_pack_linear_weight")
+        _launch("pack_weight_kernel", 8 * w.numel(), _C.lib().stf_pack_linear_weight, w.data_ptr(),
+                self.packed.data_ptr(), self.N, self.K, _C.stream())
         self.bias = None if bias is None else _dev(bias.detach().contiguous(), "bias")
 
 
@@ -197,7 +215,9 @@ def linear(x, lin, *, M=None, rows=_C.ROWS_DENSE, ln=None, epilogue=_C.EPI_STORE
     a.q_cols, a.q_scale = int(q_cols), float(q_scale)
     if geom is not None:
         a.batch, a.H, a.W, a.window, a.shift = (int(v) for v in geom)
-    _C.check(_C.lib().stf_linear(ctypes.byref(a), _C.stream()), "stf_linear")
+    # algorithmic bytes: activations in + weights + outputs (+ residual read)
+    nbytes = 4 * (a.M * a.K + a.N * a.K + a.M * a.N * (2 if residual is not None else 1))
+    _launch("linear_tf32_kernel", nbytes, _C.lib().stf_linear, ctypes.byref(a), _C.stream())
     return out
 
 
@@ -210,9 +230,9 @@ def window_attention_core(qkv, bias_table, num_windows, C, heads, ws, shift, Hp=
     if mask is not None:
         mask = _dev(mask.contiguous(), "mask")
         mw = mask.shape[0]
-    rc = _C.lib().stf_window_attention(qkv.data_ptr(), out.data_ptr(), bias_table.data_ptr(), _C.ptr(mask), mw,
-                                       int(num_windows), C, heads, ws, shift, Hp, Wp, _C.stream())
-    _C.check(rc, "stf_window_attention")
+    _launch("window_attention_kernel", 4 * qkv.shape[0] * 4 * C, _C.lib().stf_window_attention, qkv.data_ptr(),
+            out.data_ptr(), bias_table.data_ptr(), _C.ptr(mask), mw, int(num_windows), C, heads, ws, shift, Hp, Wp,
+            _C.stream())
     return out
 
 

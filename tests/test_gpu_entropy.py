@@ -104,7 +104,7 @@ def test_compress_step_and_likelihood_slices(shape):
     y = 6 * torch.randn(B, M, h, w, generator=g)
     mu = 2 * torch.randn(B, Cs, h, w, generator=g)
     sc = torch.exp(torch.rand(B, Cs, h, w, generator=g) * 9 - 4.5)
-    y[:, Cs:2 * Cs].view(-1)[:16] = (mu.view(-1)[:16] + torch.arange(-8, 8) + 0.5)   # ties
+    y[0, Cs:2 * Cs].view(-1)[:16] = (mu[0].view(-1)[:16] + torch.arange(-8, 8) + 0.5)   # ties
     table = OE.scale_table()
     total = M * h * w
     sym = torch.full((B, total), -7, dtype=torch.int32).cuda()

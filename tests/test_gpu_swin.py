@@ -158,7 +158,8 @@ def test_index_math_exact(H, W, shift):
     win = OS.to_windows(h, ws).reshape(-1, C)
     ref_qkv = (rna_tf32(win).double() @ sd["attn.qkv.weight"].double().t() + sd["attn.qkv.bias"].double()).float()
     ref_qkv[:, :C] *= blk.attn.scale
-    assert (qkv.cpu() - ref_qkv).abs().max().item() < 5e-5
+    # (a 1-ulp LayerNorm difference can move an operand across a TF32 rounding boundary: 2^-11 relative)
+    assert (qkv.cpu() - ref_qkv).abs().max().item() < 5e-4
     # attention core is fp32 end to end: compare against the oracle's softmax on OUR qkv
     o = ops.window_attention_core(qkv, blk.attn.relative_position_bias_table, B * (Hp // ws) * (Wp // ws), C, nh, ws,
                                   shift, Hp, Wp)
