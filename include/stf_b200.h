@@ -111,18 +111,25 @@ int stf_entropy_bottleneck(const float *z, const float *params, float *z_hat, fl
 /* ------------------------------------------------------------------------------------------
  * Window-attention path (tensor-core bound).
  *
- * One tcgen05 / TMEM GEMM kernel  Y = epilogue( prologue(X) . W^T )  with TF32 operands and fp32
- * accumulation covers qkv, proj, fc1, fc2, PatchMerging and PatchSplit; the prologue does the
- * LayerNorm and the window-partition / cyclic-shift / 2x2-merge gathers as index math, the
- * epilogue does bias, q-scaling, exact-erf GELU, residual add and the window-reverse /
- * un-shift / pixel-shuffle scatters.  A second kernel does the per-window softmax(QK^T+B+mask)V.
+ * One persistent tcgen05 / TMEM GEMM kernel  Y = epilogue( LN?(gather(X)) . W^T )  with TF32 operands
+ * and fp32 accumulation covers qkv, proj, fc1, fc2, PatchMerging and PatchSplit; the producer warps do
+ * the window-partition / cyclic-shift / 2x2-merge gathers as index math on cp.async source addresses,
+ * the LayerNorm is folded through the GEMM (row statistics gathered on the fly), and the epilogue does
+ * bias, q-scaling, exact-erf GELU, residual add and the window-reverse / un-shift / pixel-shuffle scatters.  A second kernel does the per-window softmax(QK^T+B+mask)V.
  * ------------------------------------------------------------------------------------------ */
 
-/* Re-pack a torch Linear weight W[N][K] (row-major fp32) into the tile image the GEMM kernel
- * streams with 1-D bulk TMA copies: [N / n_tile][K / 4][n_tile][4] floats, rounded to TF32
- * (round-to-nearest, ties away).  n_tile = stf_linear_n_tile(N).  `packed` holds N*K floats. */
+/* Pack a torch Linear (weight W[N][K] row-major fp32, optional bias[N]) -- and, when the layer is
+ * preceded by a LayerNorm over its K inputs, that LayerNorm's gamma[K] / beta[K] -- into the image
+ * the GEMM kernel streams with 1-D bulk TMA copies.  `packed` (device) receives
+ * stf_packed_linear_floats(N, K) = N*K + 3*N floats:
+ *   [N / n_tile][K / 4][n_tile][4]   gamma o W rounded to TF32 (round-to-nearest), n_tile = stf_linear_n_tile(N)
+ *   s[N] = sum_k tf32(gamma_k W_nk)    t[N] = sum_k beta_k W_nk + bias_n    b[N] = bias_n
+ * so that LN(x).W^T + bias = rstd * (x.(gamma o W)^T - mean * s) + t is evaluated in the GEMM epilogue.
+ * All four source pointers are device pointers; bias and (ln_gamma, ln_beta) may be NULL. */
 int stf_linear_n_tile(int N);
-int stf_pack_linear_weight(const float *weight, float *packed, int N, int K, void *stream);
+int64_t stf_packed_linear_floats(int N, int K);
+int stf_pack_linear(const float *weight, const float *bias, const float *ln_gamma, const float *ln_beta,
+                    float *packed, int N, int K, void *stream);
 
 /* Row gather applied to X before the GEMM (what each of the 128 rows of an M-tile reads). */
 enum {
@@ -152,14 +159,12 @@ typedef struct {
   int K;            /* input features (for MERGE: 4 * C) */
   const float *x;   /* input activations (token-major, row stride = ldx floats) */
   int ldx;
-  const float *w_packed; /* from stf_pack_linear_weight */
-  const float *bias;     /* N floats or NULL */
+  const float *w_packed; /* from stf_pack_linear (weights, bias and LayerNorm affine folded in) */
   float *y;         /* output */
   int ldy;
   /* prologue */
   int rows;               /* STF_ROWS_* */
-  const float *ln_gamma;  /* K floats or NULL = no LayerNorm */
-  const float *ln_beta;
+  int has_ln;             /* 1: LayerNorm over the K gathered inputs (packed with ln_gamma / ln_beta) */
   float ln_eps;
   /* epilogue */
   int epilogue;           /* STF_EPI_* */

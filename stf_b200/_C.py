@@ -29,9 +29,9 @@ class LinearArgs(ctypes.Structure):
     _fields_ = [
         ("M", c_int), ("N", c_int), ("K", c_int),
         ("x", c_vp), ("ldx", c_int),
-        ("w_packed", c_vp), ("bias", c_vp),
+        ("w_packed", c_vp),
         ("y", c_vp), ("ldy", c_int),
-        ("rows", c_int), ("ln_gamma", c_vp), ("ln_beta", c_vp), ("ln_eps", c_f32),
+        ("rows", c_int), ("has_ln", c_int), ("ln_eps", c_f32),
         ("epilogue", c_int), ("residual", c_vp), ("q_cols", c_int), ("q_scale", c_f32),
         ("batch", c_int), ("H", c_int), ("W", c_int), ("window", c_int), ("shift", c_int),
     ]
@@ -50,7 +50,8 @@ SIGNATURES = {
     "stf_gaussian_likelihood": (c_int, [c_vp, c_i64, c_vp, c_vp, c_vp, c_vp, c_int, c_int, c_i64, c_f32, c_f32, c_int, c_vp]),
     "stf_entropy_bottleneck": (c_int, [c_vp, c_vp, c_vp, c_vp, c_vp, c_int, c_int, c_i64, c_f32, c_int, c_vp]),
     "stf_linear_n_tile": (c_int, [c_int]),
-    "stf_pack_linear_weight": (c_int, [c_vp, c_vp, c_int, c_int, c_vp]),
+    "stf_packed_linear_floats": (c_i64, [c_int, c_int]),
+    "stf_pack_linear": (c_int, [c_vp, c_vp, c_vp, c_vp, c_vp, c_int, c_int, c_vp]),
     "stf_linear": (c_int, [ctypes.POINTER(LinearArgs), c_vp]),
     "stf_window_attention": (c_int, [c_vp, c_vp, c_vp, c_vp, c_int, c_i64, c_int, c_int, c_int, c_int, c_int, c_int, c_vp]),
     "stf_rans_table_create": (c_vp, [_i32p, c_int, c_int, _i32p, _i32p]),

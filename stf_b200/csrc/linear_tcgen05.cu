@@ -1,4 +1,4 @@
-// Fused linear layer on 5th-gen tensor cores:  Y = epilogue( prologue(X) . W^T ),  TF32 x TF32 -> FP32.
+// Fused linear layer on 5th-gen tensor cores:  Y = epilogue( LayerNorm?(gather(X)) . W^T ),  TF32 x TF32 -> FP32.
 //
 // Replaces (reference compressai/models/stf.py):
 //   norm1 + F.pad + torch.roll + window_partition + qkv Linear + q*scale     :155-175, 97-100
@@ -8,18 +8,30 @@
 //   PatchMerging (2x2 gather, LayerNorm(4C), Linear 4C->2C)                    :209-235
 //   PatchSplit (LayerNorm, Linear C->2C, PixelShuffle(2) in token layout)      :251-260
 //
-// CTA = one 128-row M tile x one n_tile-column N tile.  6 warps, warp-specialised:
-//   warps 0-3  A producers: gather rows (index math), LayerNorm in fp32, round to TF32, store into
-//              the UMMA canonical K-major layout in shared memory; afterwards the same warps run
-//              the epilogue (TMEM lane i <-> tile row i, so every thread owns one output row).
-//   warp  4    TMEM allocator + the single thread that issues tcgen05.mma / tcgen05.commit.
-//   warp  5    one thread streaming pre-packed weight tiles with 1-D bulk TMA copies.
-// kStages-deep mbarrier ring (full: 4 producer warps + TMA tx bytes; empty: tcgen05.commit).
+// Persistent, warp-specialised kernel: one CTA per SM loops over (128-row M tile, n_tile-column N tile)
+// work items; 14 warps:
+//   warps 0-3   A producers.  cp.async (LDGSTS) 16-byte copies straight from the gathered rows (window
+//               partition / cyclic shift / 2x2 merge are index math on the source address; pad rows are
+//               zero-filled) into the UMMA K-major operand layout, kInflight k-blocks in flight per thread
+//               with no register staging.  When a k-block has landed the thread reads its own 4 chunks
+//               back, rounds them to TF32 (round-to-nearest) in place and accumulates the LayerNorm
+//               statistics of its rows on the fly.
+//   warps 4-11  epilogue, two warps per TMEM lane quadrant: tcgen05.ld -> registers -> math -> padded
+//               shared-memory staging -> fully coalesced 16-byte global stores (window_reverse / un-shift /
+//               pixel-shuffle are index math on the destination address).
+//   warp 12     the single thread issuing tcgen05.mma (kind::tf32) + tcgen05.commit.
+//   warp 13     one thread streaming pre-packed weight tiles with 1-D bulk TMA copies.
+// Three mbarrier pipelines: A ring (8 stages), B ring (4 stages), TMEM accumulator (double buffered: the
+// epilogue of tile i overlaps the loads and MMAs of tile i+1).
+//
+// LayerNorm is folded through the GEMM so that the producers never wait on a statistics pass:
+//   LN(x) . W^T = rstd * ( x . (gamma o W)^T  -  mean * colsum(gamma o W) ) + (beta . W^T + bias)
+// The packed weight image carries gamma o W (TF32) plus three N-vectors: s = colsum, t = beta.W^T + bias, b = bias.
 //
 // Shared-memory operand layout (no swizzle): element (row r, col k) of a stage lives at byte
 //   (k / 4) * rows * 16 + r * 16 + (k % 4) * 4        rows = 128 for A, n_tile for B
 // i.e. [K/4][rows][4 floats]: 8 consecutive rows x 16 B form one 128-byte UMMA core matrix,
-// SBO = 128 B between 8-row groups, LBO = rows*16 B between the K chunks.
+// SBO = 128 B between 8-row groups, LBO = rows*16 B between the K chunks (verified on B200).
 #include <math.h>
 
 #include "common.cuh"
@@ -31,27 +43,64 @@ namespace {
 using namespace sm100;
 
 constexpr int kTileM = 128;
-constexpr int kBlockK = 16;  // floats per pipeline stage (2 MMAs of K=8); every K here is a multiple of 16
-constexpr int kStages = 5;
-constexpr int kThreads = 192;
+constexpr int kBlockK = 16;           // floats per pipeline stage (2 MMAs of K=8); every K here is a multiple of 16
 constexpr int kChunks = kBlockK / 4;  // 16-byte K chunks per stage
-constexpr int kMaxNTile = 192;
+constexpr int kStagesA = 8;
+constexpr int kInflight = 6;          // cp.async groups in flight per producer thread (< kStagesA)
+constexpr int kStagesB = 4;
+constexpr int kProducerWarps = 4;
+constexpr int kEpiWarps = 8;
+constexpr int kMmaWarp = kProducerWarps + kEpiWarps;
+constexpr int kLoadWarp = kMmaWarp + 1;
+constexpr int kThreads = (kLoadWarp + 1) * 32;  // 448
+constexpr int kMaxNTile = 256;
+constexpr int kMaxSlab = 64;
+constexpr int kStagePad = 4;  // floats of padding per staging row: (slab + 4) % 32 in {4, 20} -> conflict-free v4 stores
+constexpr uint32_t kAStageBytes = kChunks * kTileM * 16;  // 8 KB
 
 struct LinearParams {
   stf_linear_args a;
-  int n_tile;
+  const float *aux;  // s[N], t[N], b[N] behind the weight image
+  int n_tile, n_tiles, m_tiles, total_tiles;
   int k_blocks;
-  int tmem_cols;
+  int slab;        // epilogue column slab (16/32/48/64), divides n_tile
+  int tmem_cols;   // 2 accumulators
+  int acc_stride;  // TMEM columns between the two accumulators
   uint32_t idesc;
-  // window geometry
-  int Hp, Wp, nWw, nW;  // padded size, windows per row, windows per image
+  int has_ln;
+  int Hp, Wp, nWw, nW;  // WINDOW geometry: padded size, windows per row, windows per image
 };
 
-struct RowSrc {  // where one A-tile row comes from
-  const float *p;  // base pointer of the row (part 0 for MERGE); nullptr = all-zero row
-  int merge_flags; // MERGE: bit0 = row 2i+1 valid, bit1 = col 2j+1 valid
-};
+// ---------------------------------------------------------------------------- cp.async helpers
+__device__ __forceinline__ void cp_async16(uint32_t smem_dst, const void *gsrc, uint32_t src_bytes) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(smem_dst), "l"(gsrc), "r"(src_bytes) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() {
+  asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_dyn(int n) {  // n in [0, kInflight)
+  switch (n) {
+    case 0: cp_async_wait<0>(); break;
+    case 1: cp_async_wait<1>(); break;
+    case 2: cp_async_wait<2>(); break;
+    case 3: cp_async_wait<3>(); break;
+    case 4: cp_async_wait<4>(); break;
+    case 5: cp_async_wait<5>(); break;
+    default: cp_async_wait<kInflight>(); break;
+  }
+}
+__device__ __forceinline__ float4 lds128(uint32_t addr) {
+  float4 v;
+  asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
+  return v;
+}
+__device__ __forceinline__ void sts128(uint32_t addr, float4 v) {
+  asm volatile("st.shared.v4.f32 [%0], {%1,%2,%3,%4};" ::"r"(addr), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+}
 
+// ---------------------------------------------------------------------------- row index math
 __device__ __forceinline__ int window_row_to_token(const LinearParams &P, int g, bool *valid) {
   const stf_linear_args &a = P.a;
   const int ws = a.window, N = ws * ws;
@@ -66,6 +115,11 @@ __device__ __forceinline__ int window_row_to_token(const LinearParams &P, int g,
   *valid = (h < a.H) && (w < a.W);
   return (b * a.H + h) * a.W + w;
 }
+
+struct RowSrc {     // where one A-tile row comes from
+  const float *p;   // base pointer of the row (part 0 for MERGE); nullptr = all-zero row
+  int merge_flags;  // MERGE: bit0 = row 2i+1 valid, bit1 = col 2j+1 valid
+};
 
 __device__ __forceinline__ RowSrc row_source(const LinearParams &P, int row) {
   const stf_linear_args &a = P.a;
@@ -88,256 +142,441 @@ __device__ __forceinline__ RowSrc row_source(const LinearParams &P, int row) {
   return r;
 }
 
-// float4 of row `r` at K-offset k (k % 4 == 0); zeros where the reference pads.
-__device__ __forceinline__ float4 load_chunk(const LinearParams &P, const RowSrc &r, int k) {
-  const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
-  if (!r.p) return z;
-  if (P.a.rows != STF_ROWS_MERGE) return __ldg(reinterpret_cast<const float4 *>(r.p + k));
+// source address of the 16-byte chunk at K offset k of row r (nullptr = zero-fill)
+__device__ __forceinline__ const float *chunk_source(const LinearParams &P, const RowSrc &r, int k) {
+  if (!r.p) return nullptr;
+  if (P.a.rows != STF_ROWS_MERGE) return r.p + k;
   const int C = P.a.K >> 2;
-  int part = k / C, c = k - part * C;  // concat order x0,x1,x2,x3 = (0,0),(1,0),(0,1),(1,1)
+  int part = k / C, c = k - part * C;  // concat order x0,x1,x2,x3 = (0,0),(1,0),(0,1),(1,1)  (stf.py:225-229)
   int di = part & 1, dj = part >> 1;
-  if ((di && !(r.merge_flags & 1)) || (dj && !(r.merge_flags & 2))) return z;
-  return __ldg(reinterpret_cast<const float4 *>(r.p + ((int64_t)di * P.a.W + dj) * P.a.ldx + c));
+  if ((di && !(r.merge_flags & 1)) || (dj && !(r.merge_flags & 2))) return nullptr;
+  return r.p + ((int64_t)di * P.a.W + dj) * P.a.ldx + c;
 }
 
-__device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752440f)); }
+// Exact-erf GELU (nn.GELU default, stf.py:35-36): 0.5 x (1 + erf(x / sqrt 2)).  erf through the
+// Abramowitz-Stegun 7.1.26 rational-exponential form (|abs error| <= 1.5e-7, i.e. fp32 round-off level for
+// the O(1) activations here), branch-free: one MUFU.RCP, one MUFU.EX2 and 8 FMAs instead of erff's ~25
+// instructions with a divergent branch -- the GELU epilogue is instruction-issue bound otherwise.
+__device__ __forceinline__ float gelu_erf(float x) {
+  const float ax = fabsf(x) * 0.70710678118654752440f;
+  const float t = __frcp_rn(fmaf(0.3275911f, ax, 1.0f));
+  float p = fmaf(t, 1.061405429f, -1.453152027f);
+  p = fmaf(t, p, 1.421413741f);
+  p = fmaf(t, p, -0.284496736f);
+  p = fmaf(t, p, 0.254829592f);
+  const float e = __expf(-ax * ax);
+  const float erf_abs = fmaf(-p * t, e, 1.0f);
+  return 0.5f * x * (1.0f + copysignf(erf_abs, x));
+}
 
-__global__ void __launch_bounds__(kThreads)
+
+// Epilogue phase 2 for one staged slab of 32 rows x F4ROW float4: lane handles elements lane + 32*j.
+// All residual loads of a group of 4 are issued before the first use (memory-level parallelism), every
+// global access is a full 16-byte segment and consecutive lanes touch consecutive addresses of a row.
+template <int F4ROW>
+__device__ __forceinline__ void store_slab(uint32_t stg_u32, int srow, const uint64_t *rdst, const uint64_t *rres,
+                                           int n0, int lane) {
+  constexpr int G = 4;
+#pragma unroll
+  for (int j0 = 0; j0 < F4ROW; j0 += G) {
+    float *dp[G];
+    float4 rv[G];
+    int col[G], row[G];
+#pragma unroll
+    for (int j = 0; j < G; ++j) {
+      const int i = lane + 32 * (j0 + j);
+      row[j] = i / F4ROW;
+      col[j] = (i - row[j] * F4ROW) * 4;
+      dp[j] = reinterpret_cast<float *>(rdst[row[j]]);
+      const float *rp = reinterpret_cast<const float *>(rres[row[j]]);
+      rv[j] = (dp[j] && rp) ? ldg_stream(reinterpret_cast<const float4 *>(rp + n0 + col[j])) : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+#pragma unroll
+    for (int j = 0; j < G; ++j) {
+      if (!dp[j]) continue;
+      float4 v = lds128(stg_u32 + (uint32_t)((row[j] * srow + col[j]) * 4));
+      v.x += rv[j].x, v.y += rv[j].y, v.z += rv[j].z, v.w += rv[j].w;
+      *reinterpret_cast<float4 *>(dp[j] + n0 + col[j]) = v;
+    }
+  }
+}
+
+// PatchSplit: features 4c..4c+3 of token (h, w) -> channel c of tokens (2h+i, 2w+j), f = 4c + 2i + j (stf.py:256-259)
+__device__ __forceinline__ void store_slab_pixel_shuffle(const stf_linear_args &a, uint32_t stg_u32, int srow, int f4row,
+                                                         const uint64_t *rdst, int n0, int lane) {
+  const int total = 32 * f4row;
+  const int64_t down = (int64_t)(2 * a.W) * a.ldy;
+  for (int i = lane; i < total; i += 32) {
+    const int r = i / f4row, c4 = i - r * f4row;
+    float *d = reinterpret_cast<float *>(rdst[r]);
+    if (!d) continue;
+    const float4 v = lds128(stg_u32 + (uint32_t)((r * srow + c4 * 4) * 4));
+    const int cch = (n0 + c4 * 4) >> 2;
+    d[cch] = v.x;
+    d[a.ldy + cch] = v.y;
+    d[down + cch] = v.z;
+    d[down + a.ldy + cch] = v.w;
+  }
+}
+
+// ---------------------------------------------------------------------------- shared-memory map
+struct SmemMap {
+  uint64_t *fullA, *emptyA, *fullB, *emptyB, *accFull, *accEmpty;
+  uint32_t *tmem_slot;
+  float2 *stats;        // [kStatSlots][128] (mean, rstd) per tile in flight
+  uint64_t *row_dst;    // [kEpiWarps][32] destination row pointers (0 = dropped row)
+  uint64_t *row_res;    // [kEpiWarps][32] residual row pointers
+  uint8_t *a_ring, *b_ring, *stage;
+};
+constexpr int kStatSlots = 4;  // LayerNorm statistics of the last 4 tiles (producers run ahead of the epilogue)
+constexpr size_t kSmemHeader = 512 + kStatSlots * 128 * 8 + 2 * kEpiWarps * 32 * 8;  // barriers + stats + row pointers
+
+__device__ __forceinline__ SmemMap carve(uint8_t *smem, int n_tile) {
+  SmemMap m;
+  uint64_t *bars = reinterpret_cast<uint64_t *>(smem);
+  m.fullA = bars;
+  m.emptyA = m.fullA + kStagesA;
+  m.fullB = m.emptyA + kStagesA;
+  m.emptyB = m.fullB + kStagesB;
+  m.accFull = m.emptyB + kStagesB;
+  m.accEmpty = m.accFull + 2;
+  m.tmem_slot = reinterpret_cast<uint32_t *>(m.accEmpty + 2);
+  m.stats = reinterpret_cast<float2 *>(smem + 512);
+  m.row_dst = reinterpret_cast<uint64_t *>(smem + 512 + kStatSlots * 128 * 8);
+  m.row_res = m.row_dst + kEpiWarps * 32;
+  m.a_ring = smem + kSmemHeader;
+  m.b_ring = m.a_ring + kStagesA * kAStageBytes;
+  m.stage = m.b_ring + (size_t)kStagesB * kChunks * n_tile * 16;
+  return m;
+}
+
+size_t linear_smem_bytes(int n_tile, int slab) {
+  return kSmemHeader + (size_t)kStagesA * kAStageBytes + (size_t)kStagesB * kChunks * n_tile * 16 +
+         (size_t)kEpiWarps * 32 * (slab + kStagePad) * 4;
+}
+
+// ---------------------------------------------------------------------------- the kernel
+__global__ void __launch_bounds__(kThreads, 1)
 linear_tf32_kernel(const __grid_constant__ LinearParams P) {
   extern __shared__ __align__(128) uint8_t smem[];
   const stf_linear_args &a = P.a;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int m0 = blockIdx.x * kTileM;
-  const int nt = blockIdx.y;
   const int NT = P.n_tile;
-
-  // ---- shared memory carve-up
-  uint64_t *full_bar = reinterpret_cast<uint64_t *>(smem);
-  uint64_t *empty_bar = full_bar + kStages;
-  uint64_t *accum_bar = empty_bar + kStages;
-  uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(accum_bar + 1);
-  const uint32_t a_stage_bytes = kChunks * kTileM * 16;
-  const uint32_t b_stage_bytes = kChunks * NT * 16;
-  uint8_t *a_smem = smem + 128;
-  uint8_t *b_smem = a_smem + kStages * a_stage_bytes;
+  const SmemMap S = carve(smem, NT);
+  const uint32_t b_stage_bytes = (uint32_t)(kChunks * NT * 16);
 
   if (threadIdx.x == 0) {
-    for (int s = 0; s < kStages; ++s) {
-      mbar_init(&full_bar[s], 4 + 1);  // 4 producer warps + the weight loader's expect_tx arrive
-      mbar_init(&empty_bar[s], 1);     // one tcgen05.commit
+    for (int s = 0; s < kStagesA; ++s) {
+      mbar_init(&S.fullA[s], kProducerWarps);  // one elected lane per producer warp
+      mbar_init(&S.emptyA[s], 1);              // one tcgen05.commit
     }
-    mbar_init(accum_bar, 1);
+    for (int s = 0; s < kStagesB; ++s) {
+      mbar_init(&S.fullB[s], 1);  // the loader's arrive.expect_tx (+ TMA transaction bytes)
+      mbar_init(&S.emptyB[s], 1);
+    }
+    for (int b = 0; b < 2; ++b) {
+      mbar_init(&S.accFull[b], 1);
+      mbar_init(&S.accEmpty[b], kEpiWarps);
+    }
     mbar_fence_init();
   }
-  if (warp == 4) tmem_alloc(tmem_slot, (uint32_t)P.tmem_cols);
+  if (warp == kMmaWarp) tmem_alloc(S.tmem_slot, (uint32_t)P.tmem_cols);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
-  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t tmem_base = *S.tmem_slot;
 
-  if (warp < 4) {
+  const int first_tile = blockIdx.x, tile_step = gridDim.x;
+
+  if (warp < kProducerWarps) {
     // =========================== A producers ===========================
     // lane -> (row sub-index lane&7, K chunk lane>>3); 4 row groups of 8 per warp.
     const int sub = lane & 7, chunk = lane >> 3;
-    RowSrc src[4];
-    float mean[4], rstd[4];
-#pragma unroll
-    for (int i = 0; i < 4; ++i) src[i] = row_source(P, m0 + warp * 32 + i * 8 + sub);
+    const uint32_t a_base = smem_u32(S.a_ring) + (uint32_t)(chunk * (kTileM * 16) + (warp * 32 + sub) * 16);
+    const float inv_k = 1.0f / (float)a.K;
 
-    const bool has_ln = a.ln_gamma != nullptr;
-    if (has_ln) {
-      // two-pass LayerNorm statistics; the 4 lanes sharing a row combine with shuffles
-      const float inv_k = 1.0f / (float)a.K;
+    // issue cursor
+    int i_tile = first_tile, i_kb = 0;
+    RowSrc src[4];
+    // finalize cursor (kInflight k-blocks behind)
+    int f_tile = first_tile, f_kb = 0, f_it = 0;
+    float shift0[4] = {0.f, 0.f, 0.f, 0.f}, sum[4] = {0.f, 0.f, 0.f, 0.f}, sq[4] = {0.f, 0.f, 0.f, 0.f};
+    uint32_t g = 0, issued = 0, finalized = 0;
+
+    auto finalize = [&](int pending_allowed) {
+      cp_async_wait_dyn(pending_allowed);
+      const uint32_t stage = finalized % kStagesA;
+      const uint32_t addr = a_base + stage * kAStageBytes;
 #pragma unroll
       for (int i = 0; i < 4; ++i) {
-        float s = 0.f;
-        for (int k = chunk * 4; k < a.K; k += 16) {
-          float4 v = load_chunk(P, src[i], k);
-          s += (v.x + v.y) + (v.z + v.w);
+        float4 v = lds128(addr + i * 128);
+        if (P.has_ln) {
+          if (f_kb == 0) {  // shift by the row's first element: keeps the one-pass variance well conditioned
+            shift0[i] = __shfl_sync(0xffffffffu, v.x, sub);
+            sum[i] = 0.f, sq[i] = 0.f;
+          }
+          float dx = v.x - shift0[i], dy = v.y - shift0[i], dz = v.z - shift0[i], dw = v.w - shift0[i];
+          sum[i] += (dx + dy) + (dz + dw);
+          sq[i] += (dx * dx + dy * dy) + (dz * dz + dw * dw);
         }
-        s += __shfl_xor_sync(0xffffffffu, s, 8);
-        s += __shfl_xor_sync(0xffffffffu, s, 16);
-        const float mu = s * inv_k;
-        float q = 0.f;
-        for (int k = chunk * 4; k < a.K; k += 16) {
-          float4 v = load_chunk(P, src[i], k);
-          float dx = v.x - mu, dy = v.y - mu, dz = v.z - mu, dw = v.w - mu;
-          q += (dx * dx + dy * dy) + (dz * dz + dw * dw);
-        }
-        q += __shfl_xor_sync(0xffffffffu, q, 8);
-        q += __shfl_xor_sync(0xffffffffu, q, 16);
-        mean[i] = mu;
-        rstd[i] = rsqrtf(q * inv_k + a.ln_eps);
+        sts128(addr + i * 128, make_float4(to_tf32(v.x), to_tf32(v.y), to_tf32(v.z), to_tf32(v.w)));
       }
-    }
-    // WINDOW pad rows are zero AFTER the LayerNorm (stf.py:155-162); MERGE pads before it.
-    for (int kb = 0; kb < P.k_blocks; ++kb) {
-      const int s = kb % kStages;
-      const uint32_t it = (uint32_t)(kb / kStages);
-      mbar_wait(&empty_bar[s], (it & 1u) ^ 1u);
-      const int k = kb * kBlockK + chunk * 4;
-      float4 v[4];
-#pragma unroll
-      for (int i = 0; i < 4; ++i) v[i] = load_chunk(P, src[i], k);
-      if (has_ln) {
-        const float4 g = __ldg(reinterpret_cast<const float4 *>(a.ln_gamma + k));
-        const float4 bt = __ldg(reinterpret_cast<const float4 *>(a.ln_beta + k));
+      if (P.has_ln && f_kb == P.k_blocks - 1) {  // row statistics for the epilogue of this tile
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
-          if (src[i].p) {
-            v[i].x = (v[i].x - mean[i]) * rstd[i] * g.x + bt.x;
-            v[i].y = (v[i].y - mean[i]) * rstd[i] * g.y + bt.y;
-            v[i].z = (v[i].z - mean[i]) * rstd[i] * g.z + bt.z;
-            v[i].w = (v[i].w - mean[i]) * rstd[i] * g.w + bt.w;
+          float s1 = sum[i], s2 = sq[i];
+          s1 += __shfl_xor_sync(0xffffffffu, s1, 8);
+          s1 += __shfl_xor_sync(0xffffffffu, s1, 16);
+          s2 += __shfl_xor_sync(0xffffffffu, s2, 8);
+          s2 += __shfl_xor_sync(0xffffffffu, s2, 16);
+          if (chunk == 0) {
+            float md = s1 * inv_k;
+            float var = fmaxf(s2 * inv_k - md * md, 0.f);
+            S.stats[(f_it % kStatSlots) * 128 + warp * 32 + i * 8 + sub] = make_float2(shift0[i] + md, rsqrtf(var + a.ln_eps));
           }
         }
       }
-      uint8_t *stage = a_smem + s * a_stage_bytes + chunk * (kTileM * 16);
-#pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        float4 t = make_float4(to_tf32(v[i].x), to_tf32(v[i].y), to_tf32(v[i].z), to_tf32(v[i].w));
-        *reinterpret_cast<float4 *>(stage + (warp * 32 + i * 8 + sub) * 16) = t;
-      }
       fence_proxy_async_smem();
       __syncwarp();
-      if (lane == 0) mbar_arrive(&full_bar[s]);
-    }
+      if (lane == 0) mbar_arrive(&S.fullA[stage]);
+      ++finalized;
+      if (++f_kb == P.k_blocks) {
+        f_kb = 0;
+        f_tile += tile_step;
+        ++f_it;
+      }
+    };
 
+    for (; i_tile < P.total_tiles; i_tile += tile_step) {
+      const int m0 = (i_tile / P.n_tiles) * kTileM;
+#pragma unroll
+      for (int i = 0; i < 4; ++i) src[i] = row_source(P, m0 + warp * 32 + i * 8 + sub);
+      for (i_kb = 0; i_kb < P.k_blocks; ++i_kb, ++g) {
+        const uint32_t stage = g % kStagesA;
+        mbar_wait(&S.emptyA[stage], ((g / kStagesA) & 1u) ^ 1u);
+        const int k = i_kb * kBlockK + chunk * 4;
+        const uint32_t dst = a_base + stage * kAStageBytes;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const float *p = chunk_source(P, src[i], k);
+          cp_async16(dst + i * 128, p ? (const void *)p : (const void *)a.x, p ? 16u : 0u);
+        }
+        cp_async_commit();
+        ++issued;
+        if (issued - finalized > (uint32_t)kInflight) finalize(kInflight);
+      }
+    }
+    while (finalized < issued) finalize((int)(issued - finalized) - 1);
+    (void)f_tile;
+  } else if (warp < kMmaWarp) {
     // =========================== epilogue ===========================
-    mbar_wait(accum_bar, 0);
-    tc_fence_after();
-    const int row = m0 + warp * 32 + lane;  // TMEM lane == tile row
-    float *dst = nullptr;
-    const float *res = nullptr;
-    int out_tok00 = 0;  // PIXEL_SHUFFLE: output token (2h, 2w)
-    if (row < a.M) {
-      if (a.epilogue == STF_EPI_WINDOW_RESIDUAL) {
-        bool valid;
-        int tok = window_row_to_token(P, row, &valid);
-        if (valid) {
-          dst = a.y + (int64_t)tok * a.ldy;
-          res = a.residual + (int64_t)tok * a.ldy;
+    const int ew = warp - kProducerWarps;  // 0..7
+    const int quad = warp & 3;             // TMEM lane quadrant this warp may read
+    const int half = ew >> 2;              // which alternate slabs this warp handles
+    const int slab = P.slab, n_slabs = NT / slab;
+    const int f4row = slab >> 2;           // float4 per staged row
+    const int srow = slab + kStagePad;     // staging row stride in floats
+    float *stg = reinterpret_cast<float *>(S.stage) + (size_t)ew * 32 * srow;
+    const uint32_t stg_u32 = smem_u32(stg);
+    uint64_t *rdst = S.row_dst + ew * 32, *rres = S.row_res + ew * 32;
+    const float *aux_s = P.aux, *aux_t = P.aux + a.N, *aux_b = P.aux + 2 * a.N;
+    int it = 0;
+    for (int tile = first_tile; tile < P.total_tiles; tile += tile_step, ++it) {
+      const int buf = it & 1;
+      const int mt = tile / P.n_tiles, nt = tile - mt * P.n_tiles;
+      const int row = mt * kTileM + quad * 32 + lane;  // TMEM lane == tile row
+      // destination / residual row pointers of this thread's row
+      float *dst = nullptr;
+      const float *res = nullptr;
+      bool pad_row = false;
+      if (row < a.M) {
+        if (a.epilogue == STF_EPI_WINDOW_RESIDUAL) {
+          bool valid;
+          int tok = window_row_to_token(P, row, &valid);
+          if (valid) {
+            dst = a.y + (int64_t)tok * a.ldy;
+            res = a.residual + (int64_t)tok * a.ldy;
+          }
+        } else if (a.epilogue == STF_EPI_PIXEL_SHUFFLE) {
+          int b = row / (a.H * a.W);
+          int rem = row - b * (a.H * a.W);
+          int h = rem / a.W, w = rem - h * a.W;
+          dst = a.y + (int64_t)((b * 2 * a.H + 2 * h) * (2 * a.W) + 2 * w) * a.ldy;  // token (2h, 2w)
+        } else {
+          dst = a.y + (int64_t)row * a.ldy;
+          if (a.epilogue == STF_EPI_RESIDUAL) res = a.residual + (int64_t)row * a.ldy;
         }
-      } else if (a.epilogue == STF_EPI_PIXEL_SHUFFLE) {
-        int b = row / (a.H * a.W);
-        int rem = row - b * (a.H * a.W);
-        int h = rem / a.W, w = rem - h * a.W;
-        out_tok00 = (b * 2 * a.H + 2 * h) * (2 * a.W) + 2 * w;
-        dst = a.y;
-      } else {
-        dst = a.y + (int64_t)row * a.ldy;
-        if (a.epilogue == STF_EPI_RESIDUAL) res = a.residual + (int64_t)row * a.ldy;
+        if (a.rows == STF_ROWS_WINDOW && P.has_ln) {  // pad tokens are zero AFTER norm1 (stf.py:155-162)
+          bool valid;
+          (void)window_row_to_token(P, row, &valid);
+          pad_row = !valid;
+        }
+      }
+      __syncwarp();  // previous tile's phase 2 has finished reading the row pointers
+      rdst[lane] = (uint64_t)dst;
+      rres[lane] = (uint64_t)res;
+
+      mbar_wait(&S.accFull[buf], (uint32_t)(it >> 1) & 1u);
+      tc_fence_after();
+      float mean = 0.f, rstd = 1.f;
+      if (P.has_ln) {
+        float2 st = S.stats[(it % kStatSlots) * 128 + quad * 32 + lane];
+        mean = st.x, rstd = st.y;
+      }
+      const uint32_t t_acc = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(buf * P.acc_stride);
+      for (int s = half; s < n_slabs; s += 2) {
+        const int c0 = s * slab;       // column inside the tile
+        const int n0 = nt * NT + c0;   // global output feature
+        // ---- phase 1: thread = row.  TMEM -> registers -> math -> staging
+        for (int c = 0; c < slab; c += 16) {
+          float acc[16];
+          tmem_ld16(t_acc + (uint32_t)(c0 + c), acc);
+          const int n = n0 + c;
+#pragma unroll
+          for (int j = 0; j < 16; j += 4) {
+            const float4 sv = __ldg(reinterpret_cast<const float4 *>(aux_s + n + j));
+            const float4 tv = __ldg(reinterpret_cast<const float4 *>((pad_row ? aux_b : aux_t) + n + j));
+            if (pad_row) {
+              acc[j] = tv.x, acc[j + 1] = tv.y, acc[j + 2] = tv.z, acc[j + 3] = tv.w;
+            } else {
+              acc[j] = fmaf(rstd, acc[j] - mean * sv.x, tv.x);
+              acc[j + 1] = fmaf(rstd, acc[j + 1] - mean * sv.y, tv.y);
+              acc[j + 2] = fmaf(rstd, acc[j + 2] - mean * sv.z, tv.z);
+              acc[j + 3] = fmaf(rstd, acc[j + 3] - mean * sv.w, tv.w);
+            }
+          }
+          if (a.epilogue == STF_EPI_QKV) {
+            if (n < a.q_cols) {  // q_cols is a multiple of 16
+#pragma unroll
+              for (int j = 0; j < 16; ++j) acc[j] *= a.q_scale;
+            }
+          } else if (a.epilogue == STF_EPI_GELU) {
+#pragma unroll
+            for (int j = 0; j < 16; ++j) acc[j] = gelu_erf(acc[j]);
+          }
+          const uint32_t sa = stg_u32 + (uint32_t)((lane * srow + c) * 4);
+#pragma unroll
+          for (int j = 0; j < 16; j += 4) sts128(sa + j * 4, make_float4(acc[j], acc[j + 1], acc[j + 2], acc[j + 3]));
+        }
+        if (s + 2 >= n_slabs) {  // last TMEM read of this warp for this tile: release the accumulator early
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&S.accEmpty[buf]);
+        }
+        __syncwarp();
+        // ---- phase 2: lanes sweep the 32 staged rows with contiguous 16-byte accesses
+        if (a.epilogue == STF_EPI_PIXEL_SHUFFLE) {
+          store_slab_pixel_shuffle(a, stg_u32, srow, f4row, rdst, n0, lane);
+        } else {
+          switch (f4row) {
+            case 4: store_slab<4>(stg_u32, srow, rdst, rres, n0, lane); break;
+            case 8: store_slab<8>(stg_u32, srow, rdst, rres, n0, lane); break;
+            case 12: store_slab<12>(stg_u32, srow, rdst, rres, n0, lane); break;
+            default: store_slab<16>(stg_u32, srow, rdst, rres, n0, lane); break;
+          }
+        }
+        __syncwarp();  // staging is reused by the next slab
+      }
+      if (half >= n_slabs) {  // this warp had no slab in this tile: still has to release the accumulator
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&S.accEmpty[buf]);
       }
     }
-    const uint32_t lane_base = tmem_base + ((uint32_t)(warp * 32) << 16);
-    for (int c0 = 0; c0 < NT; c0 += 16) {
-      float acc[16];
-      tmem_ld16(lane_base + (uint32_t)c0, acc);  // warp-collective: executed by all lanes
-      if (!dst) continue;
-      const int n0 = nt * NT + c0;
-      if (a.bias) {
-#pragma unroll
-        for (int j = 0; j < 16; j += 4) {
-          float4 bv = __ldg(reinterpret_cast<const float4 *>(a.bias + n0 + j));
-          acc[j] += bv.x, acc[j + 1] += bv.y, acc[j + 2] += bv.z, acc[j + 3] += bv.w;
-        }
-      }
-      if (a.epilogue == STF_EPI_QKV) {
-        if (n0 < a.q_cols) {  // q_cols is a multiple of 16 (head_dim % 8 == 0, C % 16 == 0)
-#pragma unroll
-          for (int j = 0; j < 16; ++j) acc[j] *= a.q_scale;
-        }
-      } else if (a.epilogue == STF_EPI_GELU) {
-#pragma unroll
-        for (int j = 0; j < 16; ++j) acc[j] = gelu_erf(acc[j]);
-      } else if (res) {
-#pragma unroll
-        for (int j = 0; j < 16; j += 4) {
-          float4 rv = __ldg(reinterpret_cast<const float4 *>(res + n0 + j));
-          acc[j] = rv.x + acc[j], acc[j + 1] = rv.y + acc[j + 1], acc[j + 2] = rv.z + acc[j + 2],
-          acc[j + 3] = rv.w + acc[j + 3];
-        }
-      }
-      if (a.epilogue == STF_EPI_PIXEL_SHUFFLE) {
-        // feature f = 4*c + 2*i + j -> token (2h+i, 2w+j), channel c
-        const int cbase = n0 >> 2;
-#pragma unroll
-        for (int ij = 0; ij < 4; ++ij) {
-          int tok = out_tok00 + (ij >> 1) * (2 * a.W) + (ij & 1);
-          float4 o = make_float4(acc[ij], acc[4 + ij], acc[8 + ij], acc[12 + ij]);
-          *reinterpret_cast<float4 *>(dst + (int64_t)tok * a.ldy + cbase) = o;
-        }
-      } else {
-#pragma unroll
-        for (int j = 0; j < 16; j += 4)
-          *reinterpret_cast<float4 *>(dst + n0 + j) = make_float4(acc[j], acc[j + 1], acc[j + 2], acc[j + 3]);
-      }
-    }
-    tc_fence_before();
-  } else if (warp == 4) {
+  } else if (warp == kMmaWarp) {
     // =========================== MMA issuer ===========================
     if (lane == 0) {
-      // K-major, no swizzle: LBO = distance between the two 16-byte K chunks of one MMA,
-      // SBO = distance between consecutive 8-row core matrices (verified on B200 at bring-up).
       const uint32_t a_lbo = (uint32_t)(kTileM * 16), a_sbo = 128u;
       const uint32_t b_lbo = (uint32_t)(NT * 16), b_sbo = 128u;
-      for (int kb = 0; kb < P.k_blocks; ++kb) {
-        const int s = kb % kStages;
-        const uint32_t it = (uint32_t)(kb / kStages);
-        mbar_wait(&full_bar[s], it & 1u);
+      uint32_t g = 0;
+      int it = 0;
+      for (int tile = first_tile; tile < P.total_tiles; tile += tile_step, ++it) {
+        const int buf = it & 1;
+        mbar_wait(&S.accEmpty[buf], ((uint32_t)(it >> 1) & 1u) ^ 1u);
         tc_fence_after();
-        const uint32_t a_addr = smem_u32(a_smem + s * a_stage_bytes);
-        const uint32_t b_addr = smem_u32(b_smem + s * b_stage_bytes);
+        const uint32_t d_tmem = tmem_base + (uint32_t)(buf * P.acc_stride);
+        for (int kb = 0; kb < P.k_blocks; ++kb, ++g) {
+          const uint32_t sa = g % kStagesA, sb = g % kStagesB;
+          mbar_wait(&S.fullA[sa], (g / kStagesA) & 1u);
+          mbar_wait(&S.fullB[sb], (g / kStagesB) & 1u);
+          tc_fence_after();
+          const uint32_t a_addr = smem_u32(S.a_ring) + sa * kAStageBytes;
+          const uint32_t b_addr = smem_u32(S.b_ring) + sb * b_stage_bytes;
 #pragma unroll
-        for (int ks = 0; ks < kBlockK / 8; ++ks) {  // one MMA consumes K = 8 tf32 = 2 chunks
-          uint64_t da = umma_smem_desc(a_addr + ks * 2 * (kTileM * 16), a_lbo, a_sbo);
-          uint64_t db = umma_smem_desc(b_addr + ks * 2 * (NT * 16), b_lbo, b_sbo);
-          umma_tf32(tmem_base, da, db, P.idesc, (kb | ks) ? 1u : 0u);
+          for (int ks = 0; ks < kBlockK / 8; ++ks) {  // one MMA consumes K = 8 tf32 = 2 chunks
+            uint64_t da = umma_smem_desc(a_addr + ks * 2 * (kTileM * 16), a_lbo, a_sbo);
+            uint64_t db = umma_smem_desc(b_addr + ks * 2 * (NT * 16), b_lbo, b_sbo);
+            umma_tf32(d_tmem, da, db, P.idesc, (kb | ks) ? 1u : 0u);
+          }
+          umma_commit(&S.emptyA[sa]);  // frees both ring slots once these MMAs have read them
+          umma_commit(&S.emptyB[sb]);
         }
-        umma_commit(&empty_bar[s]);  // frees the stage once these MMAs have read it
+        umma_commit(&S.accFull[buf]);  // accumulator complete -> epilogue
       }
-      umma_commit(accum_bar);  // accumulator complete -> epilogue
     }
     __syncwarp();
   } else {
     // =========================== weight loader (bulk TMA) ===========================
     if (lane == 0) {
-      const float *wt = a.w_packed + (size_t)nt * (size_t)(a.K >> 2) * NT * 4;
-      for (int kb = 0; kb < P.k_blocks; ++kb) {
-        const int s = kb % kStages;
-        const uint32_t it = (uint32_t)(kb / kStages);
-        mbar_wait(&empty_bar[s], (it & 1u) ^ 1u);
-        mbar_arrive_expect_tx(&full_bar[s], b_stage_bytes);
-        bulk_copy_g2s(b_smem + s * b_stage_bytes, wt + (size_t)kb * kChunks * NT * 4, b_stage_bytes, &full_bar[s]);
+      uint32_t g = 0;
+      for (int tile = first_tile; tile < P.total_tiles; tile += tile_step) {
+        const int nt = tile % P.n_tiles;
+        const float *wt = a.w_packed + (size_t)nt * (size_t)(a.K >> 2) * NT * 4;
+        for (int kb = 0; kb < P.k_blocks; ++kb, ++g) {
+          const uint32_t sb = g % kStagesB;
+          mbar_wait(&S.emptyB[sb], ((g / kStagesB) & 1u) ^ 1u);
+          mbar_arrive_expect_tx(&S.fullB[sb], b_stage_bytes);
+          bulk_copy_g2s(S.b_ring + sb * b_stage_bytes, wt + (size_t)kb * kChunks * NT * 4, b_stage_bytes, &S.fullB[sb]);
+        }
       }
     }
     __syncwarp();
   }
 
+  tc_fence_before();
   __syncthreads();
-  if (warp == 4) {
+  if (warp == kMmaWarp) {
     tc_fence_after();
     tmem_dealloc(tmem_base, (uint32_t)P.tmem_cols);
   }
 }
 
-__global__ void __launch_bounds__(256)
-pack_weight_kernel(const float *__restrict__ w, float *__restrict__ packed, int N, int K, int NT) {
-  // one thread per output float4: packed[nt][kc][n_in][0..3] = tf32(W[nt*NT + n_in][4*kc .. 4*kc+3])
-  const int64_t total = (int64_t)N * (K >> 2);
-  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
-    int n_in = (int)(i % NT);
-    int64_t r = i / NT;
-    int kc = (int)(r % (K >> 2));
-    int t = (int)(r / (K >> 2));
-    float4 v = __ldg(reinterpret_cast<const float4 *>(w + (int64_t)(t * NT + n_in) * K + kc * 4));
-    reinterpret_cast<float4 *>(packed)[i] =
-        make_float4(to_tf32(v.x), to_tf32(v.y), to_tf32(v.z), to_tf32(v.w));
+// One block per output feature n: scale by gamma, round to TF32, scatter into the tile image, reduce the
+// two LayerNorm-folding sums.
+__global__ void __launch_bounds__(128)
+pack_weight_kernel(const float *__restrict__ w, const float *__restrict__ bias, const float *__restrict__ gamma,
+                   const float *__restrict__ beta, float *__restrict__ packed, int N, int K, int NT) {
+  const int n = blockIdx.x;
+  const int t = n / NT, n_in = n - t * NT;
+  float *tile = packed + (size_t)t * (size_t)(K >> 2) * NT * 4;
+  float s = 0.f, tb = 0.f;
+  for (int k = threadIdx.x; k < K; k += blockDim.x) {
+    const float wv = w[(size_t)n * K + k];
+    const float wg = to_tf32(gamma ? wv * gamma[k] : wv);
+    tile[((size_t)(k >> 2) * NT + n_in) * 4 + (k & 3)] = wg;
+    s += wg;
+    if (beta) tb = fmaf(beta[k], wv, tb);
+  }
+  __shared__ float red[2][4];
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    s += __shfl_xor_sync(0xffffffffu, s, o);
+    tb += __shfl_xor_sync(0xffffffffu, tb, o);
+  }
+  if ((threadIdx.x & 31) == 0) red[0][threadIdx.x >> 5] = s, red[1][threadIdx.x >> 5] = tb;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float *aux = packed + (size_t)N * K;
+    const float bv = bias ? bias[n] : 0.f;
+    aux[n] = gamma ? (red[0][0] + red[0][1]) + (red[0][2] + red[0][3]) : 0.f;  // s: only used when LN is folded
+    aux[N + n] = ((red[1][0] + red[1][1]) + (red[1][2] + red[1][3])) + bv;       // t = beta.W^T + bias
+    aux[2 * N + n] = bv;                                                         // b = bias (pad rows)
   }
 }
 
-size_t linear_smem_bytes(int n_tile) {
-  return 128 + (size_t)kStages * (kChunks * kTileM * 16 + kChunks * n_tile * 16);
+int pick_slab(int n_tile) {
+  for (int s = kMaxSlab; s >= 16; s -= 16)
+    if (n_tile % s == 0) return s;
+  return 16;
 }
 
 int launch_linear(const stf_linear_args *args, void *stream) {
@@ -347,10 +586,7 @@ int launch_linear(const stf_linear_args *args, void *stream) {
   if (a.M == 0) return STF_OK;
   if (a.K % kBlockK != 0 || a.N % 16 != 0) return STF_E_SHAPE;
   if (a.ldx % 4 != 0 || a.ldy % 4 != 0) return STF_E_SHAPE;
-  if (!aligned16(a.x) || !aligned16(a.w_packed) || !aligned16(a.y) || !aligned16(a.bias) ||
-      !aligned16(a.residual) || !aligned16(a.ln_gamma) || !aligned16(a.ln_beta))
-    return STF_E_ALIGN;
-  if ((a.ln_gamma == nullptr) != (a.ln_beta == nullptr)) return STF_E_ARG;
+  if (!aligned16(a.x) || !aligned16(a.w_packed) || !aligned16(a.y) || !aligned16(a.residual)) return STF_E_ALIGN;
   if ((a.epilogue == STF_EPI_RESIDUAL || a.epilogue == STF_EPI_WINDOW_RESIDUAL) && !a.residual) return STF_E_ARG;
   if (a.epilogue < STF_EPI_STORE || a.epilogue > STF_EPI_PIXEL_SHUFFLE) return STF_E_ARG;
   if (a.rows < STF_ROWS_DENSE || a.rows > STF_ROWS_MERGE) return STF_E_ARG;
@@ -358,12 +594,23 @@ int launch_linear(const stf_linear_args *args, void *stream) {
 
   LinearParams P;
   P.a = a;
+  P.aux = a.w_packed + (size_t)a.N * a.K;
   P.n_tile = stf_linear_n_tile(a.N);
   if (P.n_tile <= 0) return STF_E_SHAPE;
+  P.n_tiles = a.N / P.n_tile;
+  P.m_tiles = (a.M + kTileM - 1) / kTileM;
+  const int64_t total = (int64_t)P.m_tiles * P.n_tiles;
+  if (total > 0x7fffffff) return STF_E_SHAPE;
+  P.total_tiles = (int)total;
   P.k_blocks = a.K / kBlockK;
+  P.slab = pick_slab(P.n_tile);
   P.tmem_cols = 32;
-  while (P.tmem_cols < P.n_tile) P.tmem_cols <<= 1;
+  while (P.tmem_cols < 2 * P.n_tile) P.tmem_cols <<= 1;
+  P.acc_stride = P.tmem_cols / 2;
   P.idesc = umma_idesc_tf32(kTileM, P.n_tile);
+  P.has_ln = a.has_ln ? 1 : 0;
+  // the statistics hand-over (kStatSlots tiles deep) relies on a tile spanning at least 3 ring stages
+  if (P.has_ln && P.k_blocks < 3) return STF_E_SHAPE;
   P.Hp = P.Wp = P.nWw = P.nW = 0;
   const bool windowed = a.rows == STF_ROWS_WINDOW || a.epilogue == STF_EPI_WINDOW_RESIDUAL;
   if (windowed) {
@@ -375,22 +622,22 @@ int launch_linear(const stf_linear_args *args, void *stream) {
     if ((int64_t)a.M != (int64_t)a.batch * P.Hp * P.Wp) return STF_E_SHAPE;
   }
   if (a.rows == STF_ROWS_MERGE) {
-    if (a.batch <= 0 || a.H <= 0 || a.W <= 0 || a.K % 4 != 0 || (a.K / 4) % 4 != 0) return STF_E_SHAPE;
+    if (a.batch <= 0 || a.H <= 0 || a.W <= 0 || a.K % 4 != 0 || (a.K / 4) % kBlockK != 0) return STF_E_SHAPE;
     if ((int64_t)a.M != (int64_t)a.batch * ((a.H + 1) / 2) * ((a.W + 1) / 2)) return STF_E_SHAPE;
   }
   if (a.epilogue == STF_EPI_PIXEL_SHUFFLE) {
     if (a.batch <= 0 || a.H <= 0 || a.W <= 0 || (int64_t)a.M != (int64_t)a.batch * a.H * a.W) return STF_E_SHAPE;
-    if (a.N % 16 != 0 || a.ldy < a.N / 4) return STF_E_SHAPE;
+    if (a.ldy < a.N / 4) return STF_E_SHAPE;
   }
-  const size_t smem = linear_smem_bytes(P.n_tile);
+  const size_t smem = linear_smem_bytes(P.n_tile, P.slab);
   static std::atomic<int> attr_set{0};
   if (!attr_set.load(std::memory_order_acquire)) {
     cudaError_t e = cudaFuncSetAttribute(linear_tf32_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         (int)linear_smem_bytes(kMaxNTile));
+                                         (int)linear_smem_bytes(kMaxNTile, kMaxSlab));
     if (e != cudaSuccess) return (int)e;
     attr_set.store(1, std::memory_order_release);
   }
-  dim3 grid((a.M + kTileM - 1) / kTileM, a.N / P.n_tile);
+  const int grid = P.total_tiles < kNumSMs ? P.total_tiles : kNumSMs;
   linear_tf32_kernel<<<grid, kThreads, smem, (cudaStream_t)stream>>>(P);
   return check_launch();
 }
@@ -407,16 +654,20 @@ extern "C" int stf_linear_n_tile(int N) {
   return STF_E_SHAPE;
 }
 
-extern "C" int stf_pack_linear_weight(const float *weight, float *packed, int N, int K, void *stream) {
+extern "C" int64_t stf_packed_linear_floats(int N, int K) {
+  if (N <= 0 || K <= 0) return STF_E_ARG;
+  return (int64_t)N * K + 3 * (int64_t)N;
+}
+
+extern "C" int stf_pack_linear(const float *weight, const float *bias, const float *ln_gamma, const float *ln_beta,
+                               float *packed, int N, int K, void *stream) {
   if (!weight || !packed || N <= 0 || K <= 0) return STF_E_ARG;
+  if ((ln_gamma == nullptr) != (ln_beta == nullptr)) return STF_E_ARG;
   if (K % kBlockK != 0) return STF_E_SHAPE;
   int nt = stf_linear_n_tile(N);
   if (nt <= 0) return STF_E_SHAPE;
-  if (!aligned16(weight) || !aligned16(packed)) return STF_E_ALIGN;
-  int64_t total = (int64_t)N * (K / 4);
-  int blocks = (int)((total + 255) / 256);
-  if (blocks > kNumSMs * 8) blocks = kNumSMs * 8;
-  pack_weight_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(weight, packed, N, K, nt);
+  if (!aligned16(packed)) return STF_E_ALIGN;
+  pack_weight_kernel<<<N, 128, 0, (cudaStream_t)stream>>>(weight, bias, ln_gamma, ln_beta, packed, N, K, nt);
   return check_launch();
 }
 

@@ -36,11 +36,14 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t *bar, uint32_t parity) {
   return ok != 0;
 }
 // Bounded wait: a protocol bug traps (launch error) instead of hanging the GPU box.
+// (try_wait suspends the warp in hardware for a bounded time, so the loop is not a hot spin; the
+// wall-clock check runs once every 1024 failed probes to keep the loop body at two instructions.)
 __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
   if (mbar_try_wait(bar, parity)) return;
   const long long t0 = clock64();
-  while (!mbar_try_wait(bar, parity)) {
-    if (clock64() - t0 > 4000000000LL) __trap();
+  for (uint32_t spins = 1;; ++spins) {
+    if (mbar_try_wait(bar, parity)) return;
+    if ((spins & 1023u) == 0 && clock64() - t0 > 8000000000LL) __trap();
   }
 }
 

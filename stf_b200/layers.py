@@ -45,10 +45,14 @@ class _PackCache:
     def __init__(self):
         self._key, self._val = None, None
 
-    def get(self, weight, bias=None):
-        key = (weight.data_ptr(), weight._version, None if bias is None else (bias.data_ptr(), bias._version))
+    def get(self, weight, bias=None, norm=None):
+        """norm: the nn.LayerNorm applied to the Linear's input (folded into the packed image) or None."""
+        key = tuple((t.data_ptr(), t._version) for t in
+                    (weight, bias, None if norm is None else norm.weight, None if norm is None else norm.bias)
+                    if t is not None)
         if key != self._key:
-            self._val = ops.PackedLinear(weight, bias)
+            ln = None if norm is None else (norm.weight, norm.bias, norm.eps)
+            self._val = ops.PackedLinear(weight, bias, ln)
             self._key = key
         return self._val
 
@@ -81,11 +85,12 @@ class Mlp(nn.Module):
         self.drop = nn.Dropout(drop)
         self._p1, self._p2 = _PackCache(), _PackCache()
 
-    def forward(self, x, ln=None, residual=None):
+    def forward(self, x, norm=None, residual=None):
+        """norm: optional nn.LayerNorm fused in front of fc1; residual: optional tensor added to the output."""
         _require_eval(self)
         shape = x.shape
         x2 = x.reshape(-1, shape[-1])
-        h = ops.linear(x2, self._p1.get(self.fc1.weight, self.fc1.bias), ln=ln, epilogue=_C.EPI_GELU)
+        h = ops.linear(x2, self._p1.get(self.fc1.weight, self.fc1.bias, norm), epilogue=_C.EPI_GELU)
         if residual is None:
             y = ops.linear(h, self._p2.get(self.fc2.weight, self.fc2.bias))
         else:
@@ -121,8 +126,8 @@ class WindowAttention(nn.Module):
         self.softmax = nn.Softmax(dim=-1)
         self._pq, self._pp = _PackCache(), _PackCache()
 
-    def packed_qkv(self):
-        return self._pq.get(self.qkv.weight, self.qkv.bias)
+    def packed_qkv(self, norm=None):
+        return self._pq.get(self.qkv.weight, self.qkv.bias, norm)
 
     def packed_proj(self):
         return self._pp.get(self.proj.weight, self.proj.bias)
@@ -172,15 +177,13 @@ class SwinTransformerBlock(nn.Module):
         Hp, Wp = ops.ceil_to(H, ws), ops.ceil_to(W, ws)
         geom = (B, H, W, ws, shift)
         x2 = x.reshape(B * L, C)
-        n1 = (self.norm1.weight, self.norm1.bias, self.norm1.eps)
-        qkv = ops.linear(x2, self.attn.packed_qkv(), M=B * Hp * Wp, rows=_C.ROWS_WINDOW, ln=n1,
+        qkv = ops.linear(x2, self.attn.packed_qkv(self.norm1), M=B * Hp * Wp, rows=_C.ROWS_WINDOW,
                          epilogue=_C.EPI_QKV, q_cols=C, q_scale=self.attn.scale, geom=geom)
         o = ops.window_attention_core(qkv, self.attn.relative_position_bias_table, B * (Hp // ws) * (Wp // ws), C,
                                       self.num_heads, ws, shift, Hp, Wp)
         x1 = ops.linear(o, self.attn.packed_proj(), epilogue=_C.EPI_WINDOW_RESIDUAL, residual=x2, geom=geom,
                         out_rows=B * L)
-        n2 = (self.norm2.weight, self.norm2.bias, self.norm2.eps)
-        y = self.mlp(x1, ln=n2, residual=x1)
+        y = self.mlp(x1, norm=self.norm2, residual=x1)
         return y.reshape(B, L, C)
 
 
@@ -199,8 +202,8 @@ class PatchMerging(nn.Module):
         B, L, C = x.shape
         assert L == H * W, "input feature has wrong size"
         H2, W2 = (H + 1) // 2, (W + 1) // 2
-        y = ops.linear(x.reshape(B * L, C), self._p.get(self.reduction.weight), M=B * H2 * W2, rows=_C.ROWS_MERGE,
-                       ln=(self.norm.weight, self.norm.bias, self.norm.eps), geom=(B, H, W, 0, 0))
+        y = ops.linear(x.reshape(B * L, C), self._p.get(self.reduction.weight, None, self.norm), M=B * H2 * W2,
+                       rows=_C.ROWS_MERGE, geom=(B, H, W, 0, 0))
         return y.reshape(B, H2 * W2, 2 * C)
 
 
@@ -219,9 +222,8 @@ class PatchSplit(nn.Module):
         _require_eval(self)
         B, L, C = x.shape
         assert L == H * W, "input feature has wrong size"
-        y = ops.linear(x.reshape(B * L, C), self._p.get(self.reduction.weight), epilogue=_C.EPI_PIXEL_SHUFFLE,
-                       ln=(self.norm.weight, self.norm.bias, self.norm.eps), geom=(B, H, W, 0, 0),
-                       out_rows=4 * B * L, out_cols=C // 2)
+        y = ops.linear(x.reshape(B * L, C), self._p.get(self.reduction.weight, None, self.norm),
+                       epilogue=_C.EPI_PIXEL_SHUFFLE, geom=(B, H, W, 0, 0), out_rows=4 * B * L, out_cols=C // 2)
         return y.reshape(B, 4 * L, C // 2)
 
 

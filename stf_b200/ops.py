@@ -173,22 +173,33 @@ def entropy_bottleneck(z, params, lik_bound=1e-9, want_z_hat=True, want_lik=True
 # ------------------------------------------------------------------------------------ tensor-core linear
 
 class PackedLinear:
-    """A torch Linear weight (N, K) re-packed for the tcgen05 kernel (+ optional bias)."""
+    """A torch Linear (weight (N, K), optional bias) -- and the LayerNorm in front of it, if any -- packed for
+    the tcgen05 kernel (stf_pack_linear: TF32 tile image + the three LayerNorm-folding vectors)."""
 
-    def __init__(self, weight, bias=None):
+    def __init__(self, weight, bias=None, ln=None):
         w = _dev(weight.detach().contiguous(), "weight")
         self.N, self.K = w.shape
-        self.packed = torch.empty_like(w)
-        _launch("pack_weight_kernel", 8 * w.numel(), _C.lib().stf_pack_linear_weight, w.data_ptr(),
-                self.packed.data_ptr(), self.N, self.K, _C.stream())
-        self.bias = None if bias is None else _dev(bias.detach().contiguous(), "bias")
+        b = None if bias is None else _dev(bias.detach().contiguous(), "bias")
+        g = be = None
+        self.ln_eps = 0.0
+        if ln is not None:
+            g, be = _dev(ln[0].detach().contiguous(), "ln.weight"), _dev(ln[1].detach().contiguous(), "ln.bias")
+            self.ln_eps = float(ln[2])
+            if g.numel() != self.K or be.numel() != self.K:
+                raise ValueError("LayerNorm width does not match the Linear's input features")
+        self.has_ln = ln is not None
+        n = int(_C.lib().stf_packed_linear_floats(self.N, self.K))
+        self.packed = torch.empty(n, dtype=torch.float32, device=w.device)
+        _launch("pack_weight_kernel", 8 * w.numel(), _C.lib().stf_pack_linear, w.data_ptr(), _C.ptr(b), _C.ptr(g),
+                _C.ptr(be), self.packed.data_ptr(), self.N, self.K, _C.stream())
 
 
-def linear(x, lin, *, M=None, rows=_C.ROWS_DENSE, ln=None, epilogue=_C.EPI_STORE, residual=None, q_cols=0,
-           q_scale=1.0, geom=None, out=None, out_rows=None, out_cols=None):
-    """Y = epilogue(prologue(X) . W^T)   (stf_linear in include/stf_b200.h).
+def linear(x, lin, *, M=None, rows=_C.ROWS_DENSE, epilogue=_C.EPI_STORE, residual=None, q_cols=0, q_scale=1.0,
+           geom=None, out=None, out_rows=None, out_cols=None):
+    """Y = epilogue(LN?(gather(X)) . W^T)   (stf_linear in include/stf_b200.h).
 
-    x: (rows_in, ldx) fp32; ln: (gamma, beta, eps) or None; geom: (batch, H, W, window, shift)."""
+    x: (rows_in, ldx) fp32; lin: PackedLinear (carries bias and the optional LayerNorm);
+    geom: (batch, H, W, window, shift) for the WINDOW / MERGE / PIXEL_SHUFFLE index math."""
     x = _dev(x, "x")
     x2 = x.reshape(-1, x.shape[-1])
     if x2.shape[1] * (4 if rows == _C.ROWS_MERGE else 1) != lin.K:
@@ -197,17 +208,14 @@ def linear(x, lin, *, M=None, rows=_C.ROWS_DENSE, ln=None, epilogue=_C.EPI_STORE
     a.M = x2.shape[0] if M is None else int(M)
     a.N, a.K = lin.N, lin.K
     a.x, a.ldx = x2.data_ptr(), x2.shape[1]
-    a.w_packed, a.bias = lin.packed.data_ptr(), _C.ptr(lin.bias)
+    a.w_packed = lin.packed.data_ptr()
     if out is None:
         out = torch.empty((a.M if out_rows is None else out_rows, lin.N if out_cols is None else out_cols),
                           dtype=torch.float32, device=x.device)
     out = _dev(out, "out")
     a.y, a.ldy = out.data_ptr(), out.shape[-1]
     a.rows = rows
-    if ln is not None:
-        g, b, eps = ln
-        g, b = _dev(g.detach(), "ln.weight"), _dev(b.detach(), "ln.bias")
-        a.ln_gamma, a.ln_beta, a.ln_eps = g.data_ptr(), b.data_ptr(), float(eps)
+    a.has_ln, a.ln_eps = int(lin.has_ln), lin.ln_eps
     a.epilogue = epilogue
     if residual is not None:
         residual = _dev(residual, "residual")

@@ -71,7 +71,12 @@ def test_linear_epilogues_and_layernorm():
     lin = ops.PackedLinear(w, b)
     xn = torch.nn.functional.layer_norm(x, (K,), gam, bet, 1e-5)
     ref = torch.nn.functional.gelu(xn @ w.t() + b)
-    _check(ops.linear(x, lin, ln=(gam, bet, 1e-5), epilogue=_C.EPI_GELU), ref.cpu(), "ln+gelu")
+    _check(ops.linear(x, ops.PackedLinear(w, b, (gam, bet, 1e-5)), epilogue=_C.EPI_GELU), ref.cpu(), "ln+gelu")
+    # LayerNorm folding must survive rows with a large common offset (mean >> std)
+    xo = x + 30.0
+    ref_o = torch.nn.functional.layer_norm(xo, (K,), gam, bet, 1e-5) @ w.t() + b
+    out_o = ops.linear(xo, ops.PackedLinear(w, b, (gam, bet, 1e-5)))
+    assert (out_o - ref_o).abs().max().item() <= 0.05 * ref_o.abs().max().item()
     res = torch.randn(M, N, generator=g).cuda()
     _check(ops.linear(x, lin, epilogue=_C.EPI_RESIDUAL, residual=res), (res + x @ w.t() + b).cpu(), "residual")
     q = ops.linear(x, lin, epilogue=_C.EPI_QKV, q_cols=128, q_scale=0.25)
@@ -147,8 +152,7 @@ def test_index_math_exact(H, W, shift):
     # stage 1+2+3 by hand so that intermediate activations can be compared before TF32 rounding compounds
     x2 = x.cuda().reshape(B * H * W, C)
     geom = (B, H, W, ws, shift)
-    n1 = (blk.norm1.weight, blk.norm1.bias, blk.norm1.eps)
-    qkv = ops.linear(x2, blk.attn.packed_qkv(), M=B * Hp * Wp, rows=_C.ROWS_WINDOW, ln=n1, epilogue=_C.EPI_QKV,
+    qkv = ops.linear(x2, blk.attn.packed_qkv(blk.norm1), M=B * Hp * Wp, rows=_C.ROWS_WINDOW, epilogue=_C.EPI_QKV,
                      q_cols=C, q_scale=blk.attn.scale, geom=geom)
     # oracle for the same stage
     h = OS.layer_norm(sd, "norm1.", x).reshape(B, H, W, C)
@@ -156,10 +160,11 @@ def test_index_math_exact(H, W, shift):
     if shift:
         h = torch.roll(h, (-shift, -shift), (1, 2))
     win = OS.to_windows(h, ws).reshape(-1, C)
-    ref_qkv = (rna_tf32(win).double() @ sd["attn.qkv.weight"].double().t() + sd["attn.qkv.bias"].double()).float()
+    ref_qkv = (win.double() @ sd["attn.qkv.weight"].double().t() + sd["attn.qkv.bias"].double()).float()
     ref_qkv[:, :C] *= blk.attn.scale
-    # (a 1-ulp LayerNorm difference can move an operand across a TF32 rounding boundary: 2^-11 relative)
-    assert (qkv.cpu() - ref_qkv).abs().max().item() < 5e-4
+    # LayerNorm is folded through the GEMM (raw x is the TF32 operand), so this stage is compared at TF32
+    # tolerance; a wrong window / shift / pad mapping would show up as an O(1) error
+    assert (qkv.cpu() - ref_qkv).abs().max().item() < TF32_TOL * ref_qkv.abs().max().item()
     # attention core is fp32 end to end: compare against the oracle's softmax on OUR qkv
     o = ops.window_attention_core(qkv, blk.attn.relative_position_bias_table, B * (Hp // ws) * (Wp // ws), C, nh, ws,
                                   shift, Hp, Wp)

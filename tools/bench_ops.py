@@ -44,9 +44,9 @@ def main():
         T = B * H * W
         x = torch.randn(T, C, device=dev)
         g, b = torch.ones(C, device=dev), torch.zeros(C, device=dev)
-        Wqkv = ops.PackedLinear(torch.randn(3 * C, C, device=dev) * C ** -0.5, torch.zeros(3 * C, device=dev))
+        Wqkv = ops.PackedLinear(torch.randn(3 * C, C, device=dev) * C ** -0.5, torch.zeros(3 * C, device=dev), (g, b, 1e-5))
         Wproj = ops.PackedLinear(torch.randn(C, C, device=dev) * C ** -0.5, torch.zeros(C, device=dev))
-        Wfc1 = ops.PackedLinear(torch.randn(4 * C, C, device=dev) * C ** -0.5, torch.zeros(4 * C, device=dev))
+        Wfc1 = ops.PackedLinear(torch.randn(4 * C, C, device=dev) * C ** -0.5, torch.zeros(4 * C, device=dev), (g, b, 1e-5))
         Wfc2 = ops.PackedLinear(torch.randn(C, 4 * C, device=dev) * (4 * C) ** -0.5, torch.zeros(C, device=dev))
         table = torch.randn(49, nh, device=dev)
         geom = (B, H, W, 4, 2)
@@ -56,13 +56,13 @@ def main():
         h = torch.empty(T, 4 * C, device=dev)
         x2 = torch.empty(T, C, device=dev)
         cases = {
-            "linear qkv (LN, window, shift)": (lambda: ops.linear(x, Wqkv, rows=_C.ROWS_WINDOW, ln=(g, b, 1e-5), epilogue=_C.EPI_QKV, q_cols=C, q_scale=0.25, geom=geom, out=qkv),
+            "linear qkv (LN, window, shift)": (lambda: ops.linear(x, Wqkv, rows=_C.ROWS_WINDOW, epilogue=_C.EPI_QKV, q_cols=C, q_scale=0.25, geom=geom, out=qkv),
                                                4 * T * (C + 3 * C), 2 * T * C * 3 * C),
             "attention core (shift)": (lambda: ops.window_attention_core(qkv, table, T // 16, C, nh, 4, 2, H, W),
                                        4 * T * 4 * C, 4 * T * 16 * C),
             "linear proj (+window residual)": (lambda: ops.linear(o, Wproj, epilogue=_C.EPI_WINDOW_RESIDUAL, residual=x, geom=geom, out=x1),
                                                4 * T * 3 * C, 2 * T * C * C),
-            "linear fc1 (LN, GELU)": (lambda: ops.linear(x1, Wfc1, ln=(g, b, 1e-5), epilogue=_C.EPI_GELU, out=h),
+            "linear fc1 (LN, GELU)": (lambda: ops.linear(x1, Wfc1, epilogue=_C.EPI_GELU, out=h),
                                       4 * T * 5 * C, 2 * T * C * 4 * C),
             "linear fc2 (+residual)": (lambda: ops.linear(h, Wfc2, epilogue=_C.EPI_RESIDUAL, residual=x1, out=x2),
                                        4 * T * 6 * C, 2 * T * C * 4 * C),
