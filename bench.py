@@ -174,13 +174,14 @@ def run_ours(args, rank, world, local_rank):
         dec = net.decompress(enc["strings"], enc["shape"])
         return enc, dec["x_hat"]
 
+    out_host = torch.empty((B, 3, H, W), dtype=torch.float32, pin_memory=True)   # caller-owned, reused every step
+
     def step_e2e(x_host):
-        x_dev = x_host.to(dev, non_blocking=True)
+        x_dev = x_host.to(dev, non_blocking=True)       # H2D of this step's images (pinned source)
         enc, x_hat = step_device(x_dev)
-        out = torch.empty(x_hat.shape, dtype=x_hat.dtype, pin_memory=True)
-        out.copy_(x_hat, non_blocking=True)
+        out_host.copy_(x_hat, non_blocking=True)         # D2H of the reconstructions
         torch.cuda.current_stream().synchronize()
-        return enc, out
+        return enc, out_host
 
     def timed(fn, inputs):
         for i in range(args.warmup):
@@ -219,9 +220,12 @@ def run_ours(args, rank, world, local_rank):
     if rank == 0:
         from stf_b200 import profiler
         peak, peak_src = load_peaks()
+        net.cuda_graphs = False          # eager launches so that every kernel can be bracketed by events
+        step_device(dev_imgs[-1])
         with profiler.capture() as prof:
             step_device(dev_imgs[-1])
         torch.cuda.synchronize()
+        net.cuda_graphs = True
         fam = prof.summary()
         if fam:
             top = max(fam.values(), key=lambda f: f["ms"])

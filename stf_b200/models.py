@@ -28,12 +28,38 @@ import torch
 import torch.nn as nn
 import torch.nn.functional as F
 
-from . import ans, ops
+import os
+
+from . import _C, ans, graphs, ops
 from .entropy_models import EntropyBottleneck, GaussianConditional, LowerBound
 from .layers import (BasicLayer, PatchEmbed, PatchMerging, PatchSplit, Win_noShift_Attention, conv3x3,
                      subpel_conv3x3)
 
 SCALES_MIN, SCALES_MAX, SCALES_LEVELS = 0.11, 256, 64   # stf.py:16-18
+
+_GRAPHS_DEFAULT = os.environ.get("STF_B200_CUDA_GRAPHS", "1") != "0"
+_EB_MEDIAN = _C.STF_EB_MEDIAN_SLOT
+PHASE_TIMES = None   # set to a dict to collect a synchronised wall-clock breakdown (tools/phase_breakdown.py)
+
+
+class _phase:
+    """`with _phase("name"):` -- no-op unless PHASE_TIMES is a dict (then: device sync on both sides)."""
+
+    def __init__(self, name):
+        self.name = name
+
+    def __enter__(self):
+        if PHASE_TIMES is not None:
+            import time
+            torch.cuda.synchronize()
+            self.t0 = time.perf_counter()
+
+    def __exit__(self, *exc):
+        if PHASE_TIMES is not None:
+            import time
+            torch.cuda.synchronize()
+            PHASE_TIMES[self.name] = PHASE_TIMES.get(self.name, 0.0) + (time.perf_counter() - self.t0) * 1e3
+        return False
 
 
 def get_scale_table(min=SCALES_MIN, max=SCALES_MAX, levels=SCALES_LEVELS):
@@ -127,6 +153,21 @@ class _SliceCodec(CompressionModel):
             raise NotImplementedError("stf_b200 implements the inference path: call .eval() / torch.no_grad(). "
                                       "The training step (config 5) needs backward kernels that are not built yet.")
 
+    # ------------------------------------------------------------------ slice-loop building blocks
+    # Inside the loop every tensor that feeds a convolution is channels_last (cuDNN's tensor-core kernels
+    # are NHWC: no per-conv layout transposes); the 32-channel tensors our kernels read / write are NCHW
+    # (the reference's coding order), converted by tiny copies.
+    _CL = torch.channels_last
+
+    def _prepare_inference(self):
+        """One-time: conv weights to channels_last (values unchanged, strides only)."""
+        if self.__dict__.get("_prepared"):
+            return
+        for m in self.modules():
+            if isinstance(m, (nn.Conv2d, nn.ConvTranspose2d)) and m.weight.dim() == 4:
+                m.weight.data = m.weight.data.contiguous(memory_format=self._CL)
+        self.__dict__["_prepared"] = True
+
     def _slice_params(self, i, latent_means, latent_scales, y_hat_slices, hw):
         support = y_hat_slices if self.max_support_slices < 0 else y_hat_slices[: self.max_support_slices]
         mean_support = torch.cat([latent_means] + support, dim=1)
@@ -136,11 +177,16 @@ class _SliceCodec(CompressionModel):
         return mean_support, mu, scale
 
     def _lrp(self, i, mean_support, y_hat_slice):
+        y_hat_slice = y_hat_slice.contiguous(memory_format=self._CL)
         lrp = self.lrp_transforms[i](torch.cat([mean_support, y_hat_slice], dim=1))
         return y_hat_slice + 0.5 * torch.tanh(lrp)
 
     def _needed_as_support(self, i):
         return self.max_support_slices < 0 or i < self.max_support_slices
+
+    def _hyper_synthesis(self, z_hat):
+        z_hat = z_hat.contiguous(memory_format=self._CL)
+        return self.h_scale_s(z_hat), self.h_mean_s(z_hat)
 
     def forward(self, x):
         self._require_inference()
@@ -148,14 +194,14 @@ class _SliceCodec(CompressionModel):
             return self._forward_eval(x)
 
     def _forward_eval(self, x):
+        self._prepare_inference()
         y = self._analysis(x)
         hw = y.shape[2:]
-        z = self.h_a(y)
+        z = self.h_a(y.contiguous(memory_format=self._CL)).contiguous()
         eb = self.entropy_bottleneck
-        z_hat, z_likelihoods, _ = ops.entropy_bottleneck(z.contiguous(), eb.packed_params(),
-                                                         lik_bound=eb._likelihood_bound, ste_round=True)
-        latent_scales = self.h_scale_s(z_hat)
-        latent_means = self.h_mean_s(z_hat)
+        z_hat, z_likelihoods, _ = ops.entropy_bottleneck(z, eb.packed_params(), lik_bound=eb._likelihood_bound,
+                                                         ste_round=True)
+        latent_scales, latent_means = self._hyper_synthesis(z_hat)
         gc = self.gaussian_conditional
         Cs = self.slice_channels
         y_hat_slices, y_likelihood = [], []
@@ -172,80 +218,199 @@ class _SliceCodec(CompressionModel):
             out["y"] = y if self.is_teacher else None
         return out
 
-    @torch.no_grad()
-    def compress(self, x, debug=None):
-        gc = self.gaussian_conditional
-        y_table = gc.rans_table()
-        y = self._analysis(x)
+    # ------------------------------------------------------------------ encoder
+    def _encode_gpu(self, x, keep=None):
+        """All device work of compress(): x -> (y symbols, y indexes, z symbols), each (B, n) / (B, C, h, w) int32.
+        No host synchronisation inside: capturable as one CUDA graph."""
+        gc, eb = self.gaussian_conditional, self.entropy_bottleneck
+        with _phase("enc.analysis"):
+            y = self._analysis(x)
         B, M, h, w = y.shape
-        z = self.h_a(y)
-        # EntropyBottleneck.compress + decompress (stf.py:688-689): decompress(z_strings) is
-        # dequantize(symbols, medians), which the same kernel emits -- no need to decode our own stream
-        eb = self.entropy_bottleneck
-        z_hat, _, z_sym = ops.entropy_bottleneck(z.contiguous(), eb.packed_params(), want_lik=False, want_symbols=True)
-        z_strings = eb.encode_symbols(z_sym)
-        latent_scales = self.h_scale_s(z_hat)
-        latent_means = self.h_mean_s(z_hat)
+        with _phase("enc.hyper"):
+            z = self.h_a(y.contiguous(memory_format=self._CL)).contiguous()
+            # EntropyBottleneck.compress + decompress (stf.py:688-689): decompress(z_strings) is
+            # dequantize(symbols, medians), which the same kernel emits -- no need to decode our own stream
+            z_hat, _, z_sym = ops.entropy_bottleneck(z, eb.packed_params(), want_lik=False, want_symbols=True)
+            latent_scales, latent_means = self._hyper_synthesis(z_hat)
         Cs, plane = self.slice_channels, h * w
-        total = M * plane
-        sym = torch.empty((B, total), dtype=torch.int32, device=y.device)
-        idx = torch.empty((B, total), dtype=torch.int32, device=y.device)
+        sym = torch.empty((B, M * plane), dtype=torch.int32, device=y.device)
+        idx = torch.empty((B, M * plane), dtype=torch.int32, device=y.device)
         table = gc.host_scale_table()
         y_hat_slices = []
-        for i in range(self.num_slices):
-            mean_support, mu, scale = self._slice_params(i, latent_means, latent_scales, y_hat_slices, (h, w))
-            need = self._needed_as_support(i) or debug is not None
-            y_hat_i = ops.gaussian_compress_step(y, i * Cs, scale, mu, table, sym, idx, i * Cs * plane,
-                                                 scale_bound=gc.scale_bound_value(), want_y_hat=need)
-            if need:   # later slices are never read again in compress(): their LRP stacks are dead work
-                y_hat_slices.append(self._lrp(i, mean_support, y_hat_i))
-        sym_h = torch.empty(sym.shape, dtype=torch.int32, pin_memory=True)
-        idx_h = torch.empty(idx.shape, dtype=torch.int32, pin_memory=True)
-        sym_h.copy_(sym, non_blocking=True)
-        idx_h.copy_(idx, non_blocking=True)
-        torch.cuda.current_stream().synchronize()
+        with _phase("enc.slices"):
+            for i in range(self.num_slices):
+                mean_support, mu, scale = self._slice_params(i, latent_means, latent_scales, y_hat_slices, (h, w))
+                need = self._needed_as_support(i) or keep is not None
+                y_hat_i = ops.gaussian_compress_step(y, i * Cs, scale, mu, table, sym, idx, i * Cs * plane,
+                                                     scale_bound=gc.scale_bound_value(), want_y_hat=need)
+                if need:   # later slices are never read again in compress(): their LRP stacks are dead work
+                    y_hat_slices.append(self._lrp(i, mean_support, y_hat_i))
+        if keep is not None:
+            keep.update(y=y, z=z, y_hat=torch.cat(y_hat_slices, 1).contiguous())
+        return sym, idx, z_sym
+
+    def _graphs_enabled(self):
+        return self.__dict__.get("cuda_graphs", _GRAPHS_DEFAULT) and PHASE_TIMES is None
+
+    @torch.no_grad()
+    def compress(self, x, debug=None):
+        gc, eb = self.gaussian_conditional, self.entropy_bottleneck
+        y_table, z_table = gc.rans_table(), eb.rans_table()
+        self._prepare_inference()
+        x = x.contiguous()
+        if debug is None and self._graphs_enabled():
+            plans = self.__dict__.setdefault("_enc_plans", {})
+            key = tuple(x.shape)
+            if key not in plans:
+                if len(plans) >= 4:
+                    plans.clear()
+                plans[key] = graphs.Segment(lambda t: self._encode_gpu(t), [x])
+            sym, idx, z_sym = plans[key](x)
+        else:
+            sym, idx, z_sym = self._encode_gpu(x, keep=debug)
+        B, total = sym.shape
+        with _phase("enc.d2h"):
+            sym_h, idx_h = self._host_buffers("y", B, total)
+            zsym_h, _ = self._host_buffers("z", B, z_sym[0].numel())
+            sym_h.copy_(sym, non_blocking=True)
+            idx_h.copy_(idx, non_blocking=True)
+            zsym_h.copy_(z_sym.reshape(B, -1), non_blocking=True)
+            torch.cuda.current_stream().synchronize()
         if debug is not None:
-            debug.update(y=y, z=z, symbols=sym_h.clone(), indexes=idx_h.clone(), y_hat=torch.cat(y_hat_slices, 1))
-        s_np, i_np = sym_h.numpy(), idx_h.numpy()
-        y_strings = ans.encode_batch(y_table, [s_np[b] for b in range(B)], [i_np[b] for b in range(B)])
-        return {"strings": [y_strings, z_strings], "shape": z.size()[-2:]}
+            debug.update(symbols=sym_h.clone(), indexes=idx_h.clone(), z_symbols=zsym_h.clone())
+        with _phase("enc.rans"):
+            s_np, i_np, z_np = sym_h.numpy(), idx_h.numpy(), zsym_h.numpy()
+            z_idx = eb._build_indexes(z_sym.size()).reshape(B, -1).numpy()
+            # y and z streams of all images in one thread-parallel call (2B independent streams)
+            y_strings = ans.encode_batch(y_table, [s_np[b] for b in range(B)], [i_np[b] for b in range(B)])
+            z_strings = ans.encode_batch(z_table, [z_np[b] for b in range(B)], [z_idx[b] for b in range(B)])
+        return {"strings": [y_strings, z_strings], "shape": z_sym.size()[-2:]}
+
+    def _host_buffers(self, tag, B, n):
+        """Pinned int32 staging buffer pair, cached per (tag, shape): cudaHostAlloc is slow."""
+        cache = self.__dict__.setdefault("_pinned", {})
+        key = (tag, B, n)
+        if key not in cache:
+            for k in [k for k in cache if k[0] == tag]:
+                del cache[k]
+            cache[key] = (torch.empty((B, n), dtype=torch.int32, pin_memory=True),
+                          torch.empty((B, n), dtype=torch.int32, pin_memory=True))
+        return cache[key]
+
+    # ------------------------------------------------------------------ decoder
+    # The decoder alternates device segments and host rANS decodes (12 hand-offs, stf.py:757-779):
+    #   seg 0        : z symbols -> z_hat -> hyper synthesis -> slice-0 parameters -> indexes 0
+    #   seg i (1..S-1): symbols i-1 -> y_hat i-1 (+LRP) -> slice-i parameters -> indexes i
+    #   seg S        : symbols S-1 -> y_hat S-1 (+LRP) -> synthesis transform -> x_hat
+    def _dec_first(self, st, z_sym):
+        eb = self.entropy_bottleneck
+        med = eb.packed_params()[:, _EB_MEDIAN]
+        B, C = z_sym.shape[0], z_sym.shape[1]
+        medians = med.reshape(1, C, 1).expand(B, C, z_sym[0, 0].numel()).contiguous()
+        z_hat = ops.dequantize(z_sym.reshape(B, -1), 0, medians).reshape(z_sym.shape)
+        st["scales"], st["means"] = self._hyper_synthesis(z_hat)
+        st["y_hat"] = []
+        return self._dec_params(st, 0)
+
+    def _dec_params(self, st, i):
+        gc = self.gaussian_conditional
+        # per-slice entries keep every segment idempotent on `st` (graph warm-up runs a segment several times)
+        st["mean_support", i], st["mu", i], scale = self._slice_params(i, st["means"], st["scales"], st["y_hat"][:i],
+                                                                       st["hw"])
+        return ops.build_indexes(scale, gc.host_scale_table(), gc.scale_bound_value())
+
+    def _dec_slice(self, st, i, sym_prev):
+        """Finish slice i-1.  Idempotent on `st` (graph warm-up runs it more than once)."""
+        y_hat = ops.dequantize(sym_prev, 0, st["mu", i - 1])
+        st["y_hat"] = st["y_hat"][: i - 1] + [self._lrp(i - 1, st["mean_support", i - 1], y_hat)]
+
+    def _dec_mid(self, st, i, sym_prev):
+        self._dec_slice(st, i, sym_prev)
+        return self._dec_params(st, i)
+
+    def _dec_last(self, st, sym_prev):
+        self._dec_slice(st, self.num_slices, sym_prev)
+        y_hat = torch.cat(st["y_hat"], dim=1)
+        return self._synthesis(y_hat).clamp_(0, 1)
+
+    def _decode_plan(self, B, C, zh, zw, device):
+        """13 CUDA-graph segments on one shared memory pool, captured once per (B, z shape)."""
+        plans = self.__dict__.setdefault("_dec_plans", {})
+        key = (B, zh, zw)
+        if key in plans:
+            return plans[key]
+        if len(plans) >= 4:
+            plans.clear()
+        h, w = zh * 4, zw * 4
+        n = self.slice_channels * h * w
+        st = {"hw": (h, w)}
+        z0 = torch.zeros((B, C, zh, zw), dtype=torch.int32, device=device)
+        s0 = torch.zeros((B, n), dtype=torch.int32, device=device)
+        segs = [graphs.Segment(lambda t: self._dec_first(st, t), [z0])]
+        pool = segs[0].pool()
+        for i in range(1, self.num_slices):
+            segs.append(graphs.Segment(lambda t, i=i: self._dec_mid(st, i, t), [s0], pool=pool))
+        segs.append(graphs.Segment(lambda t: self._dec_last(st, t), [s0], pool=pool))
+        plans[key] = (segs, st)
+        return plans[key]
 
     @torch.no_grad()
     def decompress(self, strings, shape):
         assert isinstance(strings, list) and len(strings) == 2
-        gc = self.gaussian_conditional
-        y_table = gc.rans_table()
-        z_hat = self.entropy_bottleneck.decompress(strings[1], shape)
-        B = z_hat.shape[0]
+        gc, eb = self.gaussian_conditional, self.entropy_bottleneck
+        y_table, z_table = gc.rans_table(), eb.rans_table()
+        self._prepare_inference()
+        B = len(strings[1])
         if len(strings[0]) != B:
             raise ValueError(f"{len(strings[0])} y-strings for {B} z-strings (one y-string per image expected)")
-        latent_scales = self.h_scale_s(z_hat)
-        latent_means = self.h_mean_s(z_hat)
-        h, w = z_hat.shape[2] * 4, z_hat.shape[3] * 4
-        Cs, plane = self.slice_channels, h * w
-        n = Cs * plane
-        decoders = []
-        for s in strings[0]:
-            d = ans.RansDecoder()
-            d.set_stream(s)
-            decoders.append(d)
-        idx_h = torch.empty((B, n), dtype=torch.int32, pin_memory=True)
-        sym_h = torch.empty((B, n), dtype=torch.int32, pin_memory=True)
-        idx_np, sym_np = idx_h.numpy(), sym_h.numpy()
-        table = gc.host_scale_table()
+        device = eb._quantized_cdf.device
+        C = eb._quantized_cdf.size(0)
+        zh, zw = int(shape[0]), int(shape[1])
+        h, w = zh * 4, zw * 4
+        n = self.slice_channels * h * w
         stream = torch.cuda.current_stream()
-        y_hat_slices = []
-        for i in range(self.num_slices):
-            mean_support, mu, scale = self._slice_params(i, latent_means, latent_scales, y_hat_slices, (h, w))
-            idx = ops.build_indexes(scale, table, gc.scale_bound_value())
-            idx_h.copy_(idx.reshape(B, n), non_blocking=True)
-            stream.synchronize()
-            ans.decode_batch(decoders, y_table, [idx_np[b] for b in range(B)], outs=[sym_np[b] for b in range(B)])
-            sym = sym_h.to(z_hat.device, non_blocking=True)
-            y_hat_i = ops.dequantize(sym, 0, mu)
-            y_hat_slices.append(self._lrp(i, mean_support, y_hat_i))
-        y_hat = torch.cat(y_hat_slices, dim=1)
-        return {"x_hat": self._synthesis(y_hat).clamp_(0, 1)}
+        use_graphs = self._graphs_enabled()
+        if use_graphs:
+            segs, st = self._decode_plan(B, C, zh, zw, device)
+        else:
+            st = {"hw": (h, w)}
+        with _phase("dec.hyper"):
+            zsym_h, _ = self._host_buffers("z", B, C * zh * zw)
+            z_np = zsym_h.numpy()
+            z_idx = eb._build_indexes((B, C, zh, zw)).reshape(B, -1).numpy()
+            ans.decode_batch(_decoders(strings[1]), z_table, [z_idx[b] for b in range(B)], outs=[z_np[b] for b in range(B)])
+            if use_graphs:
+                idx = segs[0](zsym_h.reshape(B, C, zh, zw))
+            else:
+                idx = self._dec_first(st, zsym_h.to(device, non_blocking=True).reshape(B, C, zh, zw))
+        decoders = _decoders(strings[0])
+        sym_h, idx_h = self._host_buffers("y", B, n)
+        idx_np, sym_np = idx_h.numpy(), sym_h.numpy()
+        for i in range(1, self.num_slices + 1):
+            with _phase("dec.slices.gpu"):
+                idx_h.copy_(idx.reshape(B, n), non_blocking=True)
+                stream.synchronize()
+            with _phase("dec.slices.rans"):
+                ans.decode_batch(decoders, y_table, [idx_np[b] for b in range(B)], outs=[sym_np[b] for b in range(B)])
+            last = i == self.num_slices
+            with _phase("dec.synthesis" if last else "dec.slices.gpu"):
+                if use_graphs:
+                    out = segs[i](sym_h)          # pinned host buffer -> the segment's static input
+                else:
+                    sym = sym_h.to(device, non_blocking=True)
+                    out = self._dec_last(st, sym) if last else self._dec_mid(st, i, sym)
+                if not last:
+                    idx = out
+        return {"x_hat": out.clone() if use_graphs else out}
+
+
+def _decoders(strings):
+    out = []
+    for s in strings:
+        d = ans.RansDecoder()
+        d.set_stream(s)
+        out.append(d)
+    return out
 
 
 class SymmetricalTransFormer(_SliceCodec):

@@ -244,8 +244,18 @@ def window_attention_core(qkv, bias_table, num_windows, C, heads, ws, shift, Hp=
     return out
 
 
+_replayed = 0
+
+
+def count_replayed_launches(n):
+    """Kernels of this library re-issued by a CUDA-graph replay (the C-side counter only sees captures)."""
+    global _replayed
+    _replayed += int(n)
+
+
 def launch_count():
-    return int(_C.lib().stf_launch_count())
+    """stf_b200 kernels launched by this process: direct C-ABI launches + launches replayed inside CUDA graphs."""
+    return int(_C.lib().stf_launch_count()) + _replayed
 
 
 def ceil_to(v, m):
