@@ -9,19 +9,20 @@
 //   PatchSplit (LayerNorm, Linear C->2C, PixelShuffle(2) in token layout)      :251-260
 //
 // Persistent, warp-specialised kernel: one CTA per SM loops over (128-row M tile, n_tile-column N tile)
-// work items; 14 warps:
-//   warps 0-3   A producers.  cp.async (LDGSTS) 16-byte copies straight from the gathered rows (window
+// work items; 26 warps:
+//   warps 0-3   A issue.  cp.async (LDGSTS) 16-byte copies straight from the gathered rows (window
 //               partition / cyclic shift / 2x2 merge are index math on the source address; pad rows are
-//               zero-filled) into the UMMA K-major operand layout, kInflight k-blocks in flight per thread
-//               with no register staging.  When a k-block has landed the thread reads its own 4 chunks
-//               back, rounds them to TF32 (round-to-nearest) in place and accumulates the LayerNorm
-//               statistics of its rows on the fly.
-//   warps 4-11  epilogue, two warps per TMEM lane quadrant: tcgen05.ld -> registers -> math -> padded
-//               shared-memory staging -> fully coalesced 16-byte global stores (window_reverse / un-shift /
-//               pixel-shuffle are index math on the destination address).
-//   warp 12     the single thread issuing tcgen05.mma (kind::tf32) + tcgen05.commit.
-//   warp 13     one thread streaming pre-packed weight tiles with 1-D bulk TMA copies.
-// Three mbarrier pipelines: A ring (8 stages), B ring (4 stages), TMEM accumulator (double buffered: the
+//               zero-filled) into the UMMA K-major operand layout; completion is handed to a per-stage
+//               landing mbarrier (cp.async.mbarrier.arrive.noinc), so the whole ring stays in flight with no
+//               register staging and no thread ever waits on (or fences behind) its own outstanding loads.
+//   warps 4-7   A finalize.  When a k-block has landed: round it to TF32 (round-to-nearest) in place,
+//               accumulate the LayerNorm statistics of the rows on the fly, fence.proxy.async, publish.
+//   warps 8-23  epilogue, four warps per TMEM lane quadrant, one column slab each: tcgen05.ld -> registers ->
+//               math (+ residual) -> the thread's staging row in shared memory -> ONE bulk (TMA) store of that row
+//               segment to its destination (window_reverse / un-shift are index math on the destination address).
+//   warp 24     the single thread issuing tcgen05.mma (kind::tf32) + tcgen05.commit.
+//   warp 25     one thread streaming pre-packed weight tiles with 1-D bulk TMA copies.
+// Four mbarrier pipelines: A landing + A ring (up to 16 stages), B ring (3-4 stages), TMEM accumulator (double buffered: the
 // epilogue of tile i overlaps the loads and MMAs of tile i+1).
 //
 // LayerNorm is folded through the GEMM so that the producers never wait on a statistics pass:
@@ -33,6 +34,7 @@
 // i.e. [K/4][rows][4 floats]: 8 consecutive rows x 16 B form one 128-byte UMMA core matrix,
 // SBO = 128 B between 8-row groups, LBO = rows*16 B between the K chunks (verified on B200).
 #include <math.h>
+#include <stdlib.h>
 
 #include "common.cuh"
 #include "sm100.cuh"
@@ -45,16 +47,18 @@ using namespace sm100;
 constexpr int kTileM = 128;
 constexpr int kBlockK = 16;           // floats per pipeline stage (2 MMAs of K=8); every K here is a multiple of 16
 constexpr int kChunks = kBlockK / 4;  // 16-byte K chunks per stage
-constexpr int kStagesA = 8;
-constexpr int kInflight = 6;          // cp.async groups in flight per producer thread (< kStagesA)
-constexpr int kStagesB = 4;
-constexpr int kProducerWarps = 4;
-constexpr int kEpiWarps = 8;
-constexpr int kMmaWarp = kProducerWarps + kEpiWarps;
+constexpr int kMaxStagesA = 16;       // A ring depth is chosen per launch from the shared memory left over (>= 4);
+                                      // stages - 1 k-blocks (8 KB each) are in flight per CTA: HBM latency x bandwidth / SM
+constexpr int kStagesB = 4;           // (3 when n_tile > 192: shared-memory budget)
+constexpr int kProducerWarps = 4;       // cp.async issue warps
+constexpr int kFinalizeWarps = 4;       // TF32 rounding + LayerNorm statistics + proxy fence (same row/chunk mapping)
+constexpr int kEpiWarps = 16;         // four per TMEM lane quadrant, one column slab each at a time
+constexpr int kFirstEpiWarp = kProducerWarps + kFinalizeWarps;  // 8: keeps (warp & 3) == TMEM lane quadrant
+constexpr int kMmaWarp = kFirstEpiWarp + kEpiWarps;
 constexpr int kLoadWarp = kMmaWarp + 1;
-constexpr int kThreads = (kLoadWarp + 1) * 32;  // 448
+constexpr int kThreads = (kLoadWarp + 1) * 32;  // 832
 constexpr int kMaxNTile = 256;
-constexpr int kMaxSlab = 64;
+constexpr int kMaxSlab = 48;
 constexpr int kStagePad = 4;  // floats of padding per staging row: (slab + 4) % 32 in {4, 20} -> conflict-free v4 stores
 constexpr uint32_t kAStageBytes = kChunks * kTileM * 16;  // 8 KB
 
@@ -68,6 +72,7 @@ struct LinearParams {
   int acc_stride;  // TMEM columns between the two accumulators
   uint32_t idesc;
   int has_ln;
+  int stages_a, stages_b;
   int Hp, Wp, nWw, nW;  // WINDOW geometry: padded size, windows per row, windows per image
 };
 
@@ -75,12 +80,17 @@ struct LinearParams {
 __device__ __forceinline__ void cp_async16(uint32_t smem_dst, const void *gsrc, uint32_t src_bytes) {
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(smem_dst), "l"(gsrc), "r"(src_bytes) : "memory");
 }
+// mbarrier arrive triggered when all cp.async copies issued so far by this thread have landed (the barrier's
+// expected count already includes it: .noinc)
+__device__ __forceinline__ void cp_async_arrive_noinc(uint64_t *bar) {
+  asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 template <int N>
 __device__ __forceinline__ void cp_async_wait() {
   asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
 }
-__device__ __forceinline__ void cp_async_wait_dyn(int n) {  // n in [0, kInflight)
+__device__ __forceinline__ void cp_async_wait_dyn(int n) {  // n in [0, kMaxStagesA)
   switch (n) {
     case 0: cp_async_wait<0>(); break;
     case 1: cp_async_wait<1>(); break;
@@ -88,8 +98,29 @@ __device__ __forceinline__ void cp_async_wait_dyn(int n) {  // n in [0, kInfligh
     case 3: cp_async_wait<3>(); break;
     case 4: cp_async_wait<4>(); break;
     case 5: cp_async_wait<5>(); break;
-    default: cp_async_wait<kInflight>(); break;
+    case 6: cp_async_wait<6>(); break;
+    case 7: cp_async_wait<7>(); break;
+    case 8: cp_async_wait<8>(); break;
+    case 9: cp_async_wait<9>(); break;
+    case 10: cp_async_wait<10>(); break;
+    case 11: cp_async_wait<11>(); break;
+    case 12: cp_async_wait<12>(); break;
+    case 13: cp_async_wait<13>(); break;
+    case 14: cp_async_wait<14>(); break;
+    default: cp_async_wait<15>(); break;
   }
+}
+__device__ __forceinline__ void bulk_store_s2g(void *gdst, uint32_t smem_src, uint32_t bytes) {
+  asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gdst), "r"(smem_src), "r"(bytes)
+               : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait0() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+// fp32 -> TF32 round-to-nearest (ties away from zero in magnitude) on the bit pattern: two integer ops.
+// Identical to cvt.rna.tf32.f32 for finite inputs below the overflow threshold (activations are O(1)).
+__device__ __forceinline__ float round_tf32(float x) {
+  return __uint_as_float((__float_as_uint(x) + 0x1000u) & 0xFFFFE000u);
 }
 __device__ __forceinline__ float4 lds128(uint32_t addr) {
   float4 v;
@@ -171,37 +202,6 @@ __device__ __forceinline__ float gelu_erf(float x) {
 }
 
 
-// Epilogue phase 2 for one staged slab of 32 rows x F4ROW float4: lane handles elements lane + 32*j.
-// All residual loads of a group of 4 are issued before the first use (memory-level parallelism), every
-// global access is a full 16-byte segment and consecutive lanes touch consecutive addresses of a row.
-template <int F4ROW>
-__device__ __forceinline__ void store_slab(uint32_t stg_u32, int srow, const uint64_t *rdst, const uint64_t *rres,
-                                           int n0, int lane) {
-  constexpr int G = 4;
-#pragma unroll
-  for (int j0 = 0; j0 < F4ROW; j0 += G) {
-    float *dp[G];
-    float4 rv[G];
-    int col[G], row[G];
-#pragma unroll
-    for (int j = 0; j < G; ++j) {
-      const int i = lane + 32 * (j0 + j);
-      row[j] = i / F4ROW;
-      col[j] = (i - row[j] * F4ROW) * 4;
-      dp[j] = reinterpret_cast<float *>(rdst[row[j]]);
-      const float *rp = reinterpret_cast<const float *>(rres[row[j]]);
-      rv[j] = (dp[j] && rp) ? ldg_stream(reinterpret_cast<const float4 *>(rp + n0 + col[j])) : make_float4(0.f, 0.f, 0.f, 0.f);
-    }
-#pragma unroll
-    for (int j = 0; j < G; ++j) {
-      if (!dp[j]) continue;
-      float4 v = lds128(stg_u32 + (uint32_t)((row[j] * srow + col[j]) * 4));
-      v.x += rv[j].x, v.y += rv[j].y, v.z += rv[j].z, v.w += rv[j].w;
-      *reinterpret_cast<float4 *>(dp[j] + n0 + col[j]) = v;
-    }
-  }
-}
-
 // PatchSplit: features 4c..4c+3 of token (h, w) -> channel c of tokens (2h+i, 2w+j), f = 4c + 2i + j (stf.py:256-259)
 __device__ __forceinline__ void store_slab_pixel_shuffle(const stf_linear_args &a, uint32_t stg_u32, int srow, int f4row,
                                                          const uint64_t *rdst, int n0, int lane) {
@@ -222,22 +222,25 @@ __device__ __forceinline__ void store_slab_pixel_shuffle(const stf_linear_args &
 
 // ---------------------------------------------------------------------------- shared-memory map
 struct SmemMap {
-  uint64_t *fullA, *emptyA, *fullB, *emptyB, *accFull, *accEmpty;
+  uint64_t *fullA, *emptyA, *landA, *fullB, *emptyB, *accFull, *accEmpty;
   uint32_t *tmem_slot;
   float2 *stats;        // [kStatSlots][128] (mean, rstd) per tile in flight
   uint64_t *row_dst;    // [kEpiWarps][32] destination row pointers (0 = dropped row)
   uint64_t *row_res;    // [kEpiWarps][32] residual row pointers
   uint8_t *a_ring, *b_ring, *stage;
 };
-constexpr int kStatSlots = 4;  // LayerNorm statistics of the last 4 tiles (producers run ahead of the epilogue)
+// LayerNorm statistics slots.  The producers lead the MMA by at most kMaxStagesA k-blocks = ceil(16 / 3) = 6 tiles
+// (a LayerNorm'ed tile has >= 3 k-blocks) and the MMA leads the epilogue's statistics read by < 2 tiles.
+constexpr int kStatSlots = 8;
 constexpr size_t kSmemHeader = 512 + kStatSlots * 128 * 8 + 2 * kEpiWarps * 32 * 8;  // barriers + stats + row pointers
 
-__device__ __forceinline__ SmemMap carve(uint8_t *smem, int n_tile) {
+__device__ __forceinline__ SmemMap carve(uint8_t *smem, int n_tile, int stages_a, int stages_b) {
   SmemMap m;
   uint64_t *bars = reinterpret_cast<uint64_t *>(smem);
   m.fullA = bars;
-  m.emptyA = m.fullA + kStagesA;
-  m.fullB = m.emptyA + kStagesA;
+  m.emptyA = m.fullA + kMaxStagesA;
+  m.landA = m.emptyA + kMaxStagesA;
+  m.fullB = m.landA + kMaxStagesA;
   m.emptyB = m.fullB + kStagesB;
   m.accFull = m.emptyB + kStagesB;
   m.accEmpty = m.accFull + 2;
@@ -246,13 +249,13 @@ __device__ __forceinline__ SmemMap carve(uint8_t *smem, int n_tile) {
   m.row_dst = reinterpret_cast<uint64_t *>(smem + 512 + kStatSlots * 128 * 8);
   m.row_res = m.row_dst + kEpiWarps * 32;
   m.a_ring = smem + kSmemHeader;
-  m.b_ring = m.a_ring + kStagesA * kAStageBytes;
-  m.stage = m.b_ring + (size_t)kStagesB * kChunks * n_tile * 16;
+  m.b_ring = m.a_ring + stages_a * kAStageBytes;
+  m.stage = m.b_ring + (size_t)stages_b * kChunks * n_tile * 16;
   return m;
 }
 
-size_t linear_smem_bytes(int n_tile, int slab) {
-  return kSmemHeader + (size_t)kStagesA * kAStageBytes + (size_t)kStagesB * kChunks * n_tile * 16 +
+size_t linear_smem_bytes(int n_tile, int slab, int stages_a, int stages_b) {
+  return kSmemHeader + (size_t)stages_a * kAStageBytes + (size_t)stages_b * kChunks * n_tile * 16 +
          (size_t)kEpiWarps * 32 * (slab + kStagePad) * 4;
 }
 
@@ -263,15 +266,17 @@ linear_tf32_kernel(const __grid_constant__ LinearParams P) {
   const stf_linear_args &a = P.a;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int NT = P.n_tile;
-  const SmemMap S = carve(smem, NT);
+  const SmemMap S = carve(smem, NT, P.stages_a, P.stages_b);
+  const uint32_t SA = (uint32_t)P.stages_a, SB = (uint32_t)P.stages_b;
   const uint32_t b_stage_bytes = (uint32_t)(kChunks * NT * 16);
 
   if (threadIdx.x == 0) {
-    for (int s = 0; s < kStagesA; ++s) {
-      mbar_init(&S.fullA[s], kProducerWarps);  // one elected lane per producer warp
+    for (int s = 0; s < P.stages_a; ++s) {
+      mbar_init(&S.fullA[s], kFinalizeWarps);       // one elected lane per finalize warp
+      mbar_init(&S.landA[s], kProducerWarps * 32);  // cp.async.mbarrier.arrive.noinc of every issuing thread
       mbar_init(&S.emptyA[s], 1);              // one tcgen05.commit
     }
-    for (int s = 0; s < kStagesB; ++s) {
+    for (int s = 0; s < P.stages_b; ++s) {
       mbar_init(&S.fullB[s], 1);  // the loader's arrive.expect_tx (+ TMA transaction bytes)
       mbar_init(&S.emptyB[s], 1);
     }
@@ -290,90 +295,98 @@ linear_tf32_kernel(const __grid_constant__ LinearParams P) {
   const int first_tile = blockIdx.x, tile_step = gridDim.x;
 
   if (warp < kProducerWarps) {
-    // =========================== A producers ===========================
-    // lane -> (row sub-index lane&7, K chunk lane>>3); 4 row groups of 8 per warp.
+    // =========================== A producers: issue ===========================
+    // lane -> (row sub-index lane&7, K chunk lane>>3); 4 row groups of 8 per warp.  The thread only ever
+    // issues cp.async copies and hands their completion to the stage's landing barrier: it never waits on
+    // its own loads, so the whole ring (up to 16 x 8 KB) stays in flight.
     const int sub = lane & 7, chunk = lane >> 3;
     const uint32_t a_base = smem_u32(S.a_ring) + (uint32_t)(chunk * (kTileM * 16) + (warp * 32 + sub) * 16);
-    const float inv_k = 1.0f / (float)a.K;
-
-    // issue cursor
-    int i_tile = first_tile, i_kb = 0;
-    RowSrc src[4];
-    // finalize cursor (kInflight k-blocks behind)
-    int f_tile = first_tile, f_kb = 0, f_it = 0;
-    float shift0[4] = {0.f, 0.f, 0.f, 0.f}, sum[4] = {0.f, 0.f, 0.f, 0.f}, sq[4] = {0.f, 0.f, 0.f, 0.f};
-    uint32_t g = 0, issued = 0, finalized = 0;
-
-    auto finalize = [&](int pending_allowed) {
-      cp_async_wait_dyn(pending_allowed);
-      const uint32_t stage = finalized % kStagesA;
-      const uint32_t addr = a_base + stage * kAStageBytes;
+    uint32_t i_stage = 0, i_phase = 1;  // waiting on parity 1 of a fresh barrier returns immediately
+    const bool merge = a.rows == STF_ROWS_MERGE;
+    for (int i_tile = first_tile; i_tile < P.total_tiles; i_tile += tile_step) {
+      const int m0 = (i_tile / P.n_tiles) * kTileM;
+      RowSrc src[4];
+      const float *base[4];
+      uint32_t nbytes[4];
 #pragma unroll
       for (int i = 0; i < 4; ++i) {
-        float4 v = lds128(addr + i * 128);
-        if (P.has_ln) {
-          if (f_kb == 0) {  // shift by the row's first element: keeps the one-pass variance well conditioned
-            shift0[i] = __shfl_sync(0xffffffffu, v.x, sub);
-            sum[i] = 0.f, sq[i] = 0.f;
-          }
-          float dx = v.x - shift0[i], dy = v.y - shift0[i], dz = v.z - shift0[i], dw = v.w - shift0[i];
-          sum[i] += (dx + dy) + (dz + dw);
-          sq[i] += (dx * dx + dy * dy) + (dz * dz + dw * dw);
-        }
-        sts128(addr + i * 128, make_float4(to_tf32(v.x), to_tf32(v.y), to_tf32(v.z), to_tf32(v.w)));
+        src[i] = row_source(P, m0 + warp * 32 + i * 8 + sub);
+        base[i] = src[i].p ? src[i].p + chunk * 4 : a.x;  // (zero-filled rows still need a valid address)
+        nbytes[i] = src[i].p ? 16u : 0u;
       }
-      if (P.has_ln && f_kb == P.k_blocks - 1) {  // row statistics for the epilogue of this tile
+      for (int i_kb = 0; i_kb < P.k_blocks; ++i_kb) {
+        mbar_wait(&S.emptyA[i_stage], i_phase);
+        const uint32_t dst = a_base + i_stage * kAStageBytes;
+        if (!merge) {
 #pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          float s1 = sum[i], s2 = sq[i];
-          s1 += __shfl_xor_sync(0xffffffffu, s1, 8);
-          s1 += __shfl_xor_sync(0xffffffffu, s1, 16);
-          s2 += __shfl_xor_sync(0xffffffffu, s2, 8);
-          s2 += __shfl_xor_sync(0xffffffffu, s2, 16);
-          if (chunk == 0) {
-            float md = s1 * inv_k;
-            float var = fmaxf(s2 * inv_k - md * md, 0.f);
-            S.stats[(f_it % kStatSlots) * 128 + warp * 32 + i * 8 + sub] = make_float2(shift0[i] + md, rsqrtf(var + a.ln_eps));
+          for (int i = 0; i < 4; ++i) cp_async16(dst + i * 128, base[i] + i_kb * kBlockK, nbytes[i]);
+        } else {
+          const int k = i_kb * kBlockK + chunk * 4;
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const float *p = chunk_source(P, src[i], k);
+            cp_async16(dst + i * 128, p ? (const void *)p : (const void *)a.x, p ? 16u : 0u);
           }
         }
-      }
-      fence_proxy_async_smem();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&S.fullA[stage]);
-      ++finalized;
-      if (++f_kb == P.k_blocks) {
-        f_kb = 0;
-        f_tile += tile_step;
-        ++f_it;
-      }
-    };
-
-    for (; i_tile < P.total_tiles; i_tile += tile_step) {
-      const int m0 = (i_tile / P.n_tiles) * kTileM;
-#pragma unroll
-      for (int i = 0; i < 4; ++i) src[i] = row_source(P, m0 + warp * 32 + i * 8 + sub);
-      for (i_kb = 0; i_kb < P.k_blocks; ++i_kb, ++g) {
-        const uint32_t stage = g % kStagesA;
-        mbar_wait(&S.emptyA[stage], ((g / kStagesA) & 1u) ^ 1u);
-        const int k = i_kb * kBlockK + chunk * 4;
-        const uint32_t dst = a_base + stage * kAStageBytes;
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          const float *p = chunk_source(P, src[i], k);
-          cp_async16(dst + i * 128, p ? (const void *)p : (const void *)a.x, p ? 16u : 0u);
-        }
-        cp_async_commit();
-        ++issued;
-        if (issued - finalized > (uint32_t)kInflight) finalize(kInflight);
+        cp_async_arrive_noinc(&S.landA[i_stage]);  // arrives once this thread's copies above have landed
+        if (++i_stage == SA) i_stage = 0, i_phase ^= 1u;
       }
     }
-    while (finalized < issued) finalize((int)(issued - finalized) - 1);
-    (void)f_tile;
+  } else if (warp < kFirstEpiWarp) {
+    // =========================== A producers: finalize ===========================
+    // Once a k-block has landed: round it to TF32 in place (the tensor core would truncate), accumulate the
+    // LayerNorm statistics of the rows, make the generic-proxy writes visible to the async proxy, publish.
+    const int fw = warp - kProducerWarps;
+    const int sub = lane & 7, chunk = lane >> 3;
+    const uint32_t a_base = smem_u32(S.a_ring) + (uint32_t)(chunk * (kTileM * 16) + (fw * 32 + sub) * 16);
+    const float inv_k = 1.0f / (float)a.K;
+    uint32_t f_stage = 0, f_phase = 0;
+    float shift0[4] = {0.f, 0.f, 0.f, 0.f}, sum[4] = {0.f, 0.f, 0.f, 0.f}, sq[4] = {0.f, 0.f, 0.f, 0.f};
+    int f_it = 0;
+    for (int tile = first_tile; tile < P.total_tiles; tile += tile_step, ++f_it) {
+      for (int f_kb = 0; f_kb < P.k_blocks; ++f_kb) {
+        mbar_wait(&S.landA[f_stage], f_phase);
+        const uint32_t addr = a_base + f_stage * kAStageBytes;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          float4 v = lds128(addr + i * 128);
+          if (P.has_ln) {
+            if (f_kb == 0) {  // shift by the row's first element: keeps the one-pass variance well conditioned
+              shift0[i] = __shfl_sync(0xffffffffu, v.x, sub);
+              sum[i] = 0.f, sq[i] = 0.f;
+            }
+            float dx = v.x - shift0[i], dy = v.y - shift0[i], dz = v.z - shift0[i], dw = v.w - shift0[i];
+            sum[i] += (dx + dy) + (dz + dw);
+            sq[i] += (dx * dx + dy * dy) + (dz * dz + dw * dw);
+          }
+          sts128(addr + i * 128, make_float4(round_tf32(v.x), round_tf32(v.y), round_tf32(v.z), round_tf32(v.w)));
+        }
+        if (P.has_ln && f_kb == P.k_blocks - 1) {  // row statistics for the epilogue of this tile
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            float s1 = sum[i], s2 = sq[i];
+            s1 += __shfl_xor_sync(0xffffffffu, s1, 8);
+            s1 += __shfl_xor_sync(0xffffffffu, s1, 16);
+            s2 += __shfl_xor_sync(0xffffffffu, s2, 8);
+            s2 += __shfl_xor_sync(0xffffffffu, s2, 16);
+            if (chunk == 0) {
+              float md = s1 * inv_k;
+              float var = fmaxf(s2 * inv_k - md * md, 0.f);
+              S.stats[(f_it % kStatSlots) * 128 + fw * 32 + i * 8 + sub] = make_float2(shift0[i] + md, rsqrtf(var + a.ln_eps));
+            }
+          }
+        }
+        fence_proxy_async_smem();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&S.fullA[f_stage]);
+        if (++f_stage == SA) f_stage = 0, f_phase ^= 1u;
+      }
+    }
   } else if (warp < kMmaWarp) {
     // =========================== epilogue ===========================
-    const int ew = warp - kProducerWarps;  // 0..7
+    const int ew = warp - kFirstEpiWarp;  // 0..15
     const int quad = warp & 3;             // TMEM lane quadrant this warp may read
-    const int half = ew >> 2;              // which alternate slabs this warp handles
+    const int half = ew >> 2;              // 0..3: this warp handles slabs half, half+4, ...
     const int slab = P.slab, n_slabs = NT / slab;
     const int f4row = slab >> 2;           // float4 per staged row
     const int srow = slab + kStagePad;     // staging row stride in floats
@@ -425,14 +438,21 @@ linear_tf32_kernel(const __grid_constant__ LinearParams P) {
         mean = st.x, rstd = st.y;
       }
       const uint32_t t_acc = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(buf * P.acc_stride);
-      for (int s = half; s < n_slabs; s += 2) {
+      for (int s = half; s < n_slabs; s += 4) {
         const int c0 = s * slab;       // column inside the tile
         const int n0 = nt * NT + c0;   // global output feature
+        const bool row_store = a.epilogue != STF_EPI_PIXEL_SHUFFLE;
+        if (row_store) bulk_wait_read0();  // this thread's previous bulk store has finished reading its staging row
         // ---- phase 1: thread = row.  TMEM -> registers -> math -> staging
         for (int c = 0; c < slab; c += 16) {
+          const int n = n0 + c;
+          float4 rv[4];
+          if (row_store && res) {  // issued before the TMEM load so that its latency overlaps
+#pragma unroll
+            for (int j = 0; j < 4; ++j) rv[j] = __ldg(reinterpret_cast<const float4 *>(res + n + 4 * j));
+          }
           float acc[16];
           tmem_ld16(t_acc + (uint32_t)(c0 + c), acc);
-          const int n = n0 + c;
 #pragma unroll
           for (int j = 0; j < 16; j += 4) {
             const float4 sv = __ldg(reinterpret_cast<const float4 *>(aux_s + n + j));
@@ -455,27 +475,29 @@ linear_tf32_kernel(const __grid_constant__ LinearParams P) {
 #pragma unroll
             for (int j = 0; j < 16; ++j) acc[j] = gelu_erf(acc[j]);
           }
+          if (row_store && res) {
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+              acc[4 * j] += rv[j].x, acc[4 * j + 1] += rv[j].y, acc[4 * j + 2] += rv[j].z, acc[4 * j + 3] += rv[j].w;
+          }
           const uint32_t sa = stg_u32 + (uint32_t)((lane * srow + c) * 4);
 #pragma unroll
           for (int j = 0; j < 16; j += 4) sts128(sa + j * 4, make_float4(acc[j], acc[j + 1], acc[j + 2], acc[j + 3]));
         }
-        if (s + 2 >= n_slabs) {  // last TMEM read of this warp for this tile: release the accumulator early
+        if (s + 4 >= n_slabs) {  // last TMEM read of this warp for this tile: release the accumulator early
           tc_fence_before();
           __syncwarp();
           if (lane == 0) mbar_arrive(&S.accEmpty[buf]);
         }
-        __syncwarp();
-        // ---- phase 2: lanes sweep the 32 staged rows with contiguous 16-byte accesses
-        if (a.epilogue == STF_EPI_PIXEL_SHUFFLE) {
-          store_slab_pixel_shuffle(a, stg_u32, srow, f4row, rdst, n0, lane);
-        } else {
-          switch (f4row) {
-            case 4: store_slab<4>(stg_u32, srow, rdst, rres, n0, lane); break;
-            case 8: store_slab<8>(stg_u32, srow, rdst, rres, n0, lane); break;
-            case 12: store_slab<12>(stg_u32, srow, rdst, rres, n0, lane); break;
-            default: store_slab<16>(stg_u32, srow, rdst, rres, n0, lane); break;
-          }
+        if (row_store) {  // one bulk (TMA) copy per row: staging row -> its destination row segment
+          fence_proxy_async_smem();
+          if (dst) bulk_store_s2g(dst + n0, stg_u32 + (uint32_t)(lane * srow * 4), (uint32_t)(slab * 4));
+          bulk_commit();
         }
+        if (row_store) continue;
+        __syncwarp();
+        // ---- PatchSplit only: lanes sweep the 32 staged rows and scatter (pixel shuffle)
+        store_slab_pixel_shuffle(a, stg_u32, srow, f4row, rdst, n0, lane);
         __syncwarp();  // staging is reused by the next slab
       }
       if (half >= n_slabs) {  // this warp had no slab in this tile: still has to release the accumulator
@@ -483,22 +505,22 @@ linear_tf32_kernel(const __grid_constant__ LinearParams P) {
         if (lane == 0) mbar_arrive(&S.accEmpty[buf]);
       }
     }
+    bulk_wait0();  // all bulk stores of this thread have been written
   } else if (warp == kMmaWarp) {
     // =========================== MMA issuer ===========================
     if (lane == 0) {
       const uint32_t a_lbo = (uint32_t)(kTileM * 16), a_sbo = 128u;
       const uint32_t b_lbo = (uint32_t)(NT * 16), b_sbo = 128u;
-      uint32_t g = 0;
+      uint32_t sa = 0, pa = 0, sb = 0, pb = 0;  // ring stage / phase of the A and B pipelines
       int it = 0;
       for (int tile = first_tile; tile < P.total_tiles; tile += tile_step, ++it) {
         const int buf = it & 1;
         mbar_wait(&S.accEmpty[buf], ((uint32_t)(it >> 1) & 1u) ^ 1u);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + (uint32_t)(buf * P.acc_stride);
-        for (int kb = 0; kb < P.k_blocks; ++kb, ++g) {
-          const uint32_t sa = g % kStagesA, sb = g % kStagesB;
-          mbar_wait(&S.fullA[sa], (g / kStagesA) & 1u);
-          mbar_wait(&S.fullB[sb], (g / kStagesB) & 1u);
+        for (int kb = 0; kb < P.k_blocks; ++kb) {
+          mbar_wait(&S.fullA[sa], pa);
+          mbar_wait(&S.fullB[sb], pb);
           tc_fence_after();
           const uint32_t a_addr = smem_u32(S.a_ring) + sa * kAStageBytes;
           const uint32_t b_addr = smem_u32(S.b_ring) + sb * b_stage_bytes;
@@ -510,6 +532,8 @@ linear_tf32_kernel(const __grid_constant__ LinearParams P) {
           }
           umma_commit(&S.emptyA[sa]);  // frees both ring slots once these MMAs have read them
           umma_commit(&S.emptyB[sb]);
+          if (++sa == SA) sa = 0, pa ^= 1u;
+          if (++sb == SB) sb = 0, pb ^= 1u;
         }
         umma_commit(&S.accFull[buf]);  // accumulator complete -> epilogue
       }
@@ -518,15 +542,15 @@ linear_tf32_kernel(const __grid_constant__ LinearParams P) {
   } else {
     // =========================== weight loader (bulk TMA) ===========================
     if (lane == 0) {
-      uint32_t g = 0;
+      uint32_t sb = 0, pb = 1;
       for (int tile = first_tile; tile < P.total_tiles; tile += tile_step) {
         const int nt = tile % P.n_tiles;
         const float *wt = a.w_packed + (size_t)nt * (size_t)(a.K >> 2) * NT * 4;
-        for (int kb = 0; kb < P.k_blocks; ++kb, ++g) {
-          const uint32_t sb = g % kStagesB;
-          mbar_wait(&S.emptyB[sb], ((g / kStagesB) & 1u) ^ 1u);
+        for (int kb = 0; kb < P.k_blocks; ++kb) {
+          mbar_wait(&S.emptyB[sb], pb);
           mbar_arrive_expect_tx(&S.fullB[sb], b_stage_bytes);
           bulk_copy_g2s(S.b_ring + sb * b_stage_bytes, wt + (size_t)kb * kChunks * NT * 4, b_stage_bytes, &S.fullB[sb]);
+          if (++sb == SB) sb = 0, pb ^= 1u;
         }
       }
     }
@@ -574,10 +598,17 @@ pack_weight_kernel(const float *__restrict__ w, const float *__restrict__ bias, 
   }
 }
 
+// Column slab handled by one epilogue warp at a time: minimise the columns on the critical path
+// (ceil(n_slabs / 4) * slab with four warps per lane quadrant), prefer wider slabs on ties.
 int pick_slab(int n_tile) {
-  for (int s = kMaxSlab; s >= 16; s -= 16)
-    if (n_tile % s == 0) return s;
-  return 16;
+  const int max_slab = n_tile > 192 ? 32 : kMaxSlab;  // shared-memory budget
+  int best = 16, best_cost = 1 << 30;
+  for (int s = 16; s <= max_slab; s += 16) {
+    if (n_tile % s) continue;
+    const int cost = ((n_tile / s + 3) / 4) * s;
+    if (cost <= best_cost) best = s, best_cost = cost;
+  }
+  return best;
 }
 
 int launch_linear(const stf_linear_args *args, void *stream) {
@@ -610,7 +641,15 @@ int launch_linear(const stf_linear_args *args, void *stream) {
   P.acc_stride = P.tmem_cols / 2;
   P.idesc = umma_idesc_tf32(kTileM, P.n_tile);
   P.has_ln = a.has_ln ? 1 : 0;
-  // the statistics hand-over (kStatSlots tiles deep) relies on a tile spanning at least 3 ring stages
+  P.stages_b = P.n_tile > 192 ? 3 : kStagesB;
+  {  // all the shared memory the B ring and the epilogue staging leave over goes to the A ring
+    const size_t fixed = linear_smem_bytes(P.n_tile, P.slab, 0, P.stages_b);
+    const size_t budget = 227 * 1024;
+    if (fixed + 4 * kAStageBytes > budget) return STF_E_SHAPE;
+    int sa = (int)((budget - fixed) / kAStageBytes);
+    P.stages_a = sa > kMaxStagesA ? kMaxStagesA : sa;
+  }
+  // the statistics hand-over (kStatSlots tiles deep) relies on a tile spanning at least 3 k-blocks
   if (P.has_ln && P.k_blocks < 3) return STF_E_SHAPE;
   P.Hp = P.Wp = P.nWw = P.nW = 0;
   const bool windowed = a.rows == STF_ROWS_WINDOW || a.epilogue == STF_EPI_WINDOW_RESIDUAL;
@@ -630,11 +669,12 @@ int launch_linear(const stf_linear_args *args, void *stream) {
     if (a.batch <= 0 || a.H <= 0 || a.W <= 0 || (int64_t)a.M != (int64_t)a.batch * a.H * a.W) return STF_E_SHAPE;
     if (a.ldy < a.N / 4) return STF_E_SHAPE;
   }
-  const size_t smem = linear_smem_bytes(P.n_tile, P.slab);
+  const size_t smem = linear_smem_bytes(P.n_tile, P.slab, P.stages_a, P.stages_b);
+  if (smem > 227 * 1024) return STF_E_SHAPE;
   static std::atomic<int> attr_set{0};
   if (!attr_set.load(std::memory_order_acquire)) {
     cudaError_t e = cudaFuncSetAttribute(linear_tf32_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         (int)linear_smem_bytes(kMaxNTile, kMaxSlab));
+                                         227 * 1024);
     if (e != cudaSuccess) return (int)e;
     attr_set.store(1, std::memory_order_release);
   }
