@@ -24,26 +24,45 @@ __device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t *bar, uint32_t by
   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes)
                : "memory");
 }
+// One probe with a hardware suspend-time hint (ns): the warp sleeps inside the instruction instead of spinning.
 __device__ __forceinline__ bool mbar_try_wait(uint64_t *bar, uint32_t parity) {
   uint32_t ok;
   asm volatile(
       "{\n\t.reg .pred p;\n\t"
-      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
       "selp.u32 %0, 1, 0, p;\n\t}"
       : "=r"(ok)
-      : "r"(smem_u32(bar)), "r"(parity)
+      : "r"(smem_u32(bar)), "r"(parity), "r"(200000u)
       : "memory");
   return ok != 0;
 }
-// Bounded wait: a protocol bug traps (launch error) instead of hanging the GPU box.
-// (try_wait suspends the warp in hardware for a bounded time, so the loop is not a hot spin; the
-// wall-clock check runs once every 1024 failed probes to keep the loop body at two instructions.)
+// Wait for the phase with the given parity.  The inner loop is three instructions (probe, branch, count), so
+// waiting warps leave the issue slots to the working ones; every 4096 failed probes the wall clock is checked
+// and a protocol bug traps (launch error) instead of hanging the GPU box.
 __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
-  if (mbar_try_wait(bar, parity)) return;
-  const long long t0 = clock64();
-  for (uint32_t spins = 1;; ++spins) {
-    if (mbar_try_wait(bar, parity)) return;
-    if ((spins & 1023u) == 0 && clock64() - t0 > 8000000000LL) __trap();
+  const uint32_t addr = smem_u32(bar);
+  long long t0 = 0;
+  for (;;) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t.reg .u32 n;\n\t"
+        "mov.u32 n, 4096;\n\t"
+        "W_%=:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
+        "@p bra D_%=;\n\t"
+        "sub.u32 n, n, 1;\n\t"
+        "setp.ne.u32 p, n, 0;\n\t"
+        "@p bra W_%=;\n\t"
+        "setp.eq.u32 p, n, 1;\n\t"   // n == 0 here: p = false
+        "D_%=:\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(addr), "r"(parity), "r"(200000u)
+        : "memory");
+    if (ok) return;
+    const long long now = clock64();
+    if (t0 == 0) t0 = now;
+    else if (now - t0 > 20000000000LL) __trap();
   }
 }
 

@@ -18,6 +18,7 @@
 #include <math.h>
 
 #include "common.cuh"
+#include "sm100.cuh"
 
 namespace stf {
 namespace {
@@ -113,6 +114,150 @@ window_attention_kernel(const float *__restrict__ qkv, float *__restrict__ out,
   for (int j = 0; j < D; j += 4) *reinterpret_cast<float4 *>(dst + j) = make_float4(o[j], o[j + 1], o[j + 2], o[j + 3]);
 }
 
+
+// ---------------------------------------------------------------------------------------------
+// 16-token windows (every STF stage, WACNN's d=40 block): shared-memory tiled variant.
+// A CTA owns `wpc` consecutive windows.  Their qkv rows are one contiguous block of wpc*16*3C floats,
+// fetched with a single bulk TMA copy; every thread (window, head, query row) then works out of shared
+// memory (keys / values are broadcast reads), writes its output over its own q slot, and the rows leave
+// with one bulk TMA store each.  HBM sees exactly one coalesced read of qkv and one write of the output.
+// ---------------------------------------------------------------------------------------------
+template <int D>
+__global__ void __launch_bounds__(384)
+window_attention16_kernel(const float *__restrict__ qkv, float *__restrict__ out,
+                          const float *__restrict__ bias_table, const float *__restrict__ mask, int mask_windows,
+                          int64_t num_windows, int C, int heads, int shift, int Hp, int Wp, int wpc) {
+  constexpr int WS = 4, N = 16;
+  extern __shared__ __align__(128) float tile[];  // [wpc][16][3C]
+  __shared__ __align__(8) uint64_t bar;
+  const int ld = 3 * C;
+  const int64_t win0 = (int64_t)blockIdx.x * wpc;
+  const int nwin = (int)((num_windows - win0) < wpc ? (num_windows - win0) : wpc);
+  const uint32_t bytes = (uint32_t)(nwin * N * ld * 4);
+  if (threadIdx.x == 0) {
+    sm100::mbar_init(&bar, 1);
+    sm100::mbar_fence_init();
+    sm100::mbar_arrive_expect_tx(&bar, bytes);
+    sm100::bulk_copy_g2s(tile, qkv + win0 * N * (int64_t)ld, bytes, &bar);
+  }
+  __syncthreads();  // barrier initialised before anyone waits on it
+  sm100::mbar_wait(&bar, 0);
+
+  const int n = threadIdx.x % N;
+  const int pair = threadIdx.x / N;  // (local window, head)
+  const int wl = pair / heads, head = pair - wl * heads;
+  const bool active = wl < nwin;
+  if (active) {
+    const int64_t win = win0 + wl;
+    float *base = tile + (size_t)wl * N * ld + head * D;
+    float q[D];
+#pragma unroll
+    for (int j = 0; j < D; j += 4) {
+      float4 v = *reinterpret_cast<const float4 *>(base + n * ld + j);
+      q[j] = v.x, q[j + 1] = v.y, q[j + 2] = v.z, q[j + 3] = v.w;
+    }
+    const int hn = n / WS, wn = n % WS;
+    int my_label = 0, wy = 0, wx = 0;
+    if (shift > 0) {
+      const int nWw = Wp / WS, nW = (Hp / WS) * nWw;
+      const int wi = (int)(win % nW);
+      wy = wi / nWw, wx = wi - wy * nWw;
+      const int hs = wy * WS + hn, wsft = wx * WS + wn;
+      my_label = 3 * (hs < Hp - WS ? 0 : (hs < Hp - shift ? 1 : 2)) + (wsft < Wp - WS ? 0 : (wsft < Wp - shift ? 1 : 2));
+    }
+    float s[N];
+    float smax = -INFINITY;
+    const float *kbase = base + C;
+#pragma unroll
+    for (int m = 0; m < N; ++m) {
+      float acc = 0.f;
+#pragma unroll
+      for (int j = 0; j < D; j += 4) {
+        const float4 kv = *reinterpret_cast<const float4 *>(kbase + m * ld + j);
+        acc = fmaf(q[j], kv.x, acc);
+        acc = fmaf(q[j + 1], kv.y, acc);
+        acc = fmaf(q[j + 2], kv.z, acc);
+        acc = fmaf(q[j + 3], kv.w, acc);
+      }
+      const int hm = m / WS, wm = m % WS;
+      const int rel = (hn - hm + WS - 1) * (2 * WS - 1) + (wn - wm + WS - 1);
+      acc += __ldg(bias_table + rel * heads + head);
+      if (shift > 0) {
+        const int hs = wy * WS + hm, wsft = wx * WS + wm;
+        const int lab = 3 * (hs < Hp - WS ? 0 : (hs < Hp - shift ? 1 : 2)) + (wsft < Wp - WS ? 0 : (wsft < Wp - shift ? 1 : 2));
+        if (lab != my_label) acc += kMaskValue;
+      }
+      if (mask) acc += __ldg(mask + ((int64_t)(win % mask_windows) * N + n) * N + m);
+      s[m] = acc;
+      smax = fmaxf(smax, acc);
+    }
+    float denom = 0.f;
+#pragma unroll
+    for (int m = 0; m < N; ++m) {
+      s[m] = expf(s[m] - smax);
+      denom += s[m];
+    }
+    const float inv = 1.0f / denom;
+    float o[D];
+#pragma unroll
+    for (int j = 0; j < D; ++j) o[j] = 0.f;
+    const float *vbase = base + 2 * C;
+#pragma unroll
+    for (int m = 0; m < N; ++m) {
+      const float p = s[m] * inv;
+#pragma unroll
+      for (int j = 0; j < D; j += 4) {
+        const float4 vv = *reinterpret_cast<const float4 *>(vbase + m * ld + j);
+        o[j] = fmaf(p, vv.x, o[j]);
+        o[j + 1] = fmaf(p, vv.y, o[j + 1]);
+        o[j + 2] = fmaf(p, vv.z, o[j + 2]);
+        o[j + 3] = fmaf(p, vv.w, o[j + 3]);
+      }
+    }
+    // the q slot (row n, this head's columns) is read by this thread only: reuse it for the output
+#pragma unroll
+    for (int j = 0; j < D; j += 4)
+      *reinterpret_cast<float4 *>(base + n * ld + j) = make_float4(o[j], o[j + 1], o[j + 2], o[j + 3]);
+  }
+  sm100::fence_proxy_async_smem();
+  __syncthreads();
+  // one bulk store per token row: first C floats of the staged row -> out row
+  if ((int)threadIdx.x < nwin * N) {
+    const int r = threadIdx.x;
+    const uint32_t src = sm100::smem_u32(tile + (size_t)r * ld);
+    float *dst = out + (win0 * N + r) * (int64_t)C;
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst), "r"(src), "r"((uint32_t)(C * 4))
+                 : "memory");
+    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+    asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+  }
+}
+
+template <int D>
+int launch16(const float *qkv, float *out, const float *bias_table, const float *mask, int mask_windows,
+             int64_t num_windows, int C, int heads, int shift, int Hp, int Wp, cudaStream_t st) {
+  const int per_window = heads * 16;                 // threads per window
+  const size_t win_bytes = (size_t)16 * 3 * C * 4;   // qkv tile of one window
+  int wpc = 384 / per_window;
+  const int by_smem = (int)((72 * 1024) / win_bytes);  // ~3 CTAs per SM
+  if (wpc > by_smem) wpc = by_smem;
+  if (wpc < 1) wpc = 1;
+  if (per_window > 384 || win_bytes > 200 * 1024) return STF_E_SHAPE;
+  const size_t smem = (size_t)wpc * win_bytes;
+  static std::atomic<int> attr_set{0};
+  if (!attr_set.load(std::memory_order_acquire)) {
+    cudaError_t e = cudaFuncSetAttribute(window_attention16_kernel<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    if (e != cudaSuccess) return (int)e;
+    attr_set.store(1, std::memory_order_release);
+  }
+  const int64_t blocks = (num_windows + wpc - 1) / wpc;
+  if (blocks > 0x7fffffffLL) return STF_E_SHAPE;
+  const int threads = (wpc * per_window + 31) / 32 * 32;
+  window_attention16_kernel<D><<<(unsigned)blocks, threads, smem, st>>>(qkv, out, bias_table, mask, mask_windows,
+                                                                      num_windows, C, heads, shift, Hp, Wp, wpc);
+  return check_launch();
+}
+
 template <int WS, int D>
 int launch(const float *qkv, float *out, const float *bias_table, const float *mask, int mask_windows,
            int64_t num_windows, int C, int heads, int shift, int Hp, int Wp, cudaStream_t st) {
@@ -142,10 +287,13 @@ extern "C" int stf_window_attention(const float *qkv, float *out, const float *b
   cudaStream_t st = (cudaStream_t)stream;
 #define CASE(WS_, D_) \
   if (ws == WS_ && d == D_) return launch<WS_, D_>(qkv, out, bias_table, mask, mask_windows, num_windows, C, heads, shift, Hp, Wp, st)
-  CASE(4, 16);
-  CASE(4, 24);
-  CASE(4, 32);
-  CASE(4, 40);
+#define CASE16(D_) \
+  if (ws == 4 && d == D_) return launch16<D_>(qkv, out, bias_table, mask, mask_windows, num_windows, C, heads, shift, Hp, Wp, st)
+  CASE16(16);
+  CASE16(24);
+  CASE16(32);
+  CASE16(40);
+#undef CASE16
   CASE(8, 16);
   CASE(8, 24);
   CASE(8, 32);

@@ -1,0 +1,85 @@
+"""CPU, world_size 2 on gloo: the N>1 host path -- contiguous batch sharding, per-rank host rANS coding,
+gather of the byte strings, max-over-ranks timing -- reproduces the single-process result byte for byte."""
+import os
+import socket
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from stf_b200.sharding import shard_range
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    return port
+
+
+def _images(n):
+    """Synthetic (symbols, indexes) per image, deterministic."""
+    from oracle import entropy as OE
+    table = OE.scale_table().numpy()
+    out = []
+    for i in range(n):
+        rng = np.random.default_rng(100 + i)
+        m = 3000 + 517 * i
+        ix = rng.integers(0, 64, size=m).astype(np.int32)
+        out.append((np.rint(rng.standard_normal(m) * table[ix] * 1.5).astype(np.int32), ix))
+    return out
+
+
+def _worker(rank, world, port, n_images, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from oracle import entropy as OE
+        from stf_b200 import ans
+        from stf_b200.sharding import gather_strings, max_over_ranks
+        cdf, lens, offs = OE.gaussian_tables()
+        tab = ans.RansTable(cdf, lens, offs)
+        lo, hi = shard_range(n_images, rank, world)
+        mine = _images(n_images)[lo:hi]
+        local = ans.encode_batch(tab, [s for s, _ in mine], [i for _, i in mine], threads=2)
+        everything = gather_strings(local)
+        slowest = max_over_ranks(10.0 + rank)
+        if rank == 0:
+            q.put((everything, slowest))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("n_images", [4, 5])
+def test_two_rank_sharding_matches_single_process(n_images):
+    from oracle import entropy as OE
+    from stf_b200 import ans
+    cdf, lens, offs = OE.gaussian_tables()
+    tab = ans.RansTable(cdf, lens, offs)
+    single = [ans.encode_array(tab, s, i) for s, i in _images(n_images)]
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, n_images, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    gathered, slowest = q.get(timeout=120)
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    assert gathered == single                     # per-image strings identical to the 1-process run, in image order
+    assert slowest == 11.0
+
+
+def test_shard_range_partitions_exactly():
+    for n in (0, 1, 7, 8, 64):
+        for w in (1, 2, 3, 8):
+            spans = [shard_range(n, r, w) for r in range(w)]
+            assert spans[0][0] == 0 and spans[-1][1] == n
+            assert all(a[1] == b[0] for a, b in zip(spans, spans[1:]))
+            assert max(b - a for a, b in spans) - min(b - a for a, b in spans) <= 1
+    with pytest.raises(ValueError):
+        shard_range(4, 2, 2)
