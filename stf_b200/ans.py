@@ -42,12 +42,13 @@ class RansTable:
                                           sizes.ctypes.data_as(_C._i32p), offs.ctypes.data_as(_C._i32p))
         if not self._h:
             raise ValueError("malformed CDF table (rows must start at 0, end at 65536 and increase strictly)")
+        self._destroy = L.stf_rans_table_destroy      # bound now: module globals may be gone at interpreter exit
         self.rows = cdf.shape[0]
 
     def __del__(self):
         h, self._h = getattr(self, "_h", None), None
         if h:
-            _C.lib().stf_rans_table_destroy(h)
+            self._destroy(h)
 
 
 def _table(cdfs, sizes, offsets):
@@ -117,6 +118,7 @@ class BufferedRansEncoder:
 class RansDecoder:
     def __init__(self):
         self._h = None
+        self._destroy = _C.lib().stf_rans_decoder_destroy   # bound now: module globals may be gone at interpreter exit
 
     def __del__(self):
         self._close()
@@ -124,7 +126,7 @@ class RansDecoder:
     def _close(self):
         h, self._h = getattr(self, "_h", None), None
         if h:
-            _C.lib().stf_rans_decoder_destroy(h)
+            self._destroy(h)
 
     def set_stream(self, encoded: bytes):
         self._close()

@@ -62,6 +62,30 @@ constexpr int kMaxSlab = 48;
 constexpr int kStagePad = 4;  // floats of padding per staging row: (slab + 4) % 32 in {4, 20} -> conflict-free v4 stores
 constexpr uint32_t kAStageBytes = kChunks * kTileM * 16;  // 8 KB
 
+// Division by a launch-invariant positive integer (n < 2^31): one multiply-high and a shift instead of the
+// ~25-instruction emulated divide.  The row <-> token index math runs per row per tile in two warp roles.
+struct FastDiv {
+  uint32_t mul, shr;
+  int d;
+  __host__ void init(int divisor) {
+    d = divisor > 0 ? divisor : 1;
+    if (d == 1) {
+      mul = 0, shr = 0;
+      return;
+    }
+    uint32_t lg = 0;
+    while ((1u << lg) < (uint32_t)d) ++lg;  // ceil(log2 d)
+    const uint32_t p = 31 + lg;
+    mul = (uint32_t)((((uint64_t)1 << p) + (uint64_t)d - 1) / (uint64_t)d);
+    shr = p - 32;
+  }
+  __device__ __forceinline__ int div(int n) const { return d == 1 ? n : (int)(__umulhi((uint32_t)n, mul) >> shr); }
+  __device__ __forceinline__ void divmod(int n, int &q, int &r) const {
+    q = div(n);
+    r = n - q * d;
+  }
+};
+
 struct LinearParams {
   stf_linear_args a;
   const float *aux;  // s[N], t[N], b[N] behind the weight image
@@ -73,8 +97,23 @@ struct LinearParams {
   uint32_t idesc;
   int has_ln;
   int stages_a, stages_b;
+  int epi_mode;    // 0: staged slab -> coalesced 16-byte stores by the whole warp; 1: one bulk (TMA) store per row
+  int debug_skip;  // bring-up / profiling only (env STF_B200_DEBUG_SKIP): 1 = no A loads, 2 = no B loads, 4 = no stores
+  int fin_group;  // k-blocks published per proxy fence by the finalize warps (divides k_blocks, < stages_a)
   int Hp, Wp, nWw, nW;  // WINDOW geometry: padded size, windows per row, windows per image
+  int has_pad;          // WINDOW: Hp != H or Wp != W (pad tokens exist)
+  FastDiv d_img, d_win, d_nWw, d_ws;  // rows per image (nW*N), tokens per window (N), windows per row, window size
+  FastDiv d_hw, d_w;                  // MERGE: (H2*W2, W2); PIXEL_SHUFFLE: (H*W, W)
 };
+
+// ---------------------------------------------------------------------------- in-kernel tracing (profiling builds)
+// STF_B200_DEBUG_SKIP & 8: CTA 0 records clock64() at the key hand-offs of its first kTraceTiles tiles.
+constexpr int kTraceTiles = 24, kTraceEvents = 16;
+__device__ long long g_trace[kTraceEvents][kTraceTiles];
+#define TRACE(ev, it)                                                                              \
+  do {                                                                                             \
+    if ((P.debug_skip & 8) && blockIdx.x == 0 && lane == 0 && (it) < kTraceTiles) g_trace[ev][it] = clock64(); \
+  } while (0)
 
 // ---------------------------------------------------------------------------- cp.async helpers
 __device__ __forceinline__ void cp_async16(uint32_t smem_dst, const void *gsrc, uint32_t src_bytes) {
@@ -134,13 +173,13 @@ __device__ __forceinline__ void sts128(uint32_t addr, float4 v) {
 // ---------------------------------------------------------------------------- row index math
 __device__ __forceinline__ int window_row_to_token(const LinearParams &P, int g, bool *valid) {
   const stf_linear_args &a = P.a;
-  const int ws = a.window, N = ws * ws;
-  int b = g / (P.nW * N);
-  int rem = g - b * (P.nW * N);
-  int wi = rem / N, n = rem - wi * N;
-  int wy = wi / P.nWw, wx = wi - wy * P.nWw;
-  int hs = wy * ws + n / ws, wsft = wx * ws + n % ws;  // coordinates in the shifted frame
-  int h = hs + a.shift, w = wsft + a.shift;            // torch.roll(x, -shift): shifted[h'] = x[(h'+s) mod Hp]
+  const int ws = a.window;
+  int b, rem, wi, n, wy, wx, nh, nw;
+  P.d_img.divmod(g, b, rem);
+  P.d_win.divmod(rem, wi, n);
+  P.d_nWw.divmod(wi, wy, wx);
+  P.d_ws.divmod(n, nh, nw);
+  int h = wy * ws + nh + a.shift, w = wx * ws + nw + a.shift;  // torch.roll(x, -shift): shifted[h'] = x[(h'+s) mod Hp]
   if (h >= P.Hp) h -= P.Hp;
   if (w >= P.Wp) w -= P.Wp;
   *valid = (h < a.H) && (w < a.W);
@@ -163,10 +202,9 @@ __device__ __forceinline__ RowSrc row_source(const LinearParams &P, int row) {
     int tok = window_row_to_token(P, row, &valid);
     if (valid) r.p = a.x + (int64_t)tok * a.ldx;
   } else {  // MERGE: output token (b, i, j) over ceil(H/2) x ceil(W/2)
-    int H2 = (a.H + 1) >> 1, W2 = (a.W + 1) >> 1;
-    int b = row / (H2 * W2);
-    int rem = row - b * (H2 * W2);
-    int i = rem / W2, j = rem - i * W2;
+    int b, rem, i, j;
+    P.d_hw.divmod(row, b, rem);
+    P.d_w.divmod(rem, i, j);
     r.p = a.x + ((int64_t)(b * a.H + 2 * i) * a.W + 2 * j) * a.ldx;
     r.merge_flags = ((2 * i + 1 < a.H) ? 1 : 0) | ((2 * j + 1 < a.W) ? 2 : 0);
   }
@@ -202,6 +240,37 @@ __device__ __forceinline__ float gelu_erf(float x) {
 }
 
 
+
+// Epilogue phase 2 (coalesced mode) for one staged slab of 32 rows x F4ROW float4: lane handles elements
+// lane + 32*j; every global access is a full 16-byte segment and consecutive lanes touch consecutive
+// addresses of a row (window_reverse / un-shift / crop live in the per-row destination pointers).
+template <int F4ROW>
+__device__ __forceinline__ void store_slab(uint32_t stg_u32, int srow, const uint64_t *rdst, float *dense0, int ldy,
+                                           int rows_valid, int n0, int lane) {
+  // RPI rows x F4ROW float4 per warp instruction (24 of 32 lanes for 48-column slabs): the lane's column and
+  // row offset are fixed, so an iteration is an add, two loads and a store -- no per-element index math.
+  constexpr int RPI = 32 / F4ROW;
+  if (lane >= RPI * F4ROW) return;
+  const int r0 = lane / F4ROW, col = (lane - r0 * F4ROW) * 4;
+  uint32_t sa = stg_u32 + (uint32_t)((r0 * srow + col) * 4);
+  if (dense0) {  // destination rows are consecutive: no pointer table
+    float *dp = dense0 + (int64_t)r0 * ldy + n0 + col;
+#pragma unroll 4
+    for (int row = r0; row < 32; row += RPI) {
+      if (row < rows_valid) *reinterpret_cast<float4 *>(dp) = lds128(sa);
+      dp += (int64_t)RPI * ldy;
+      sa += (uint32_t)(RPI * srow * 4);
+    }
+  } else {
+#pragma unroll 4
+    for (int row = r0; row < 32; row += RPI) {
+      float *dp = reinterpret_cast<float *>(rdst[row]);
+      if (dp) *reinterpret_cast<float4 *>(dp + n0 + col) = lds128(sa);
+      sa += (uint32_t)(RPI * srow * 4);
+    }
+  }
+}
+
 // PatchSplit: features 4c..4c+3 of token (h, w) -> channel c of tokens (2h+i, 2w+j), f = 4c + 2i + j (stf.py:256-259)
 __device__ __forceinline__ void store_slab_pixel_shuffle(const stf_linear_args &a, uint32_t stg_u32, int srow, int f4row,
                                                          const uint64_t *rdst, int n0, int lane) {
@@ -228,13 +297,15 @@ struct SmemMap {
   uint64_t *row_dst;    // [kEpiWarps][32] destination row pointers (0 = dropped row)
   uint64_t *row_res;    // [kEpiWarps][32] residual row pointers
   uint8_t *a_ring, *b_ring, *stage;
+  float *aux;           // [3][N]: s, t, b vectors of the packed weight (shared memory is maxed out, so L1 is ~0:
+                        // reading them from global in the epilogue costs an L2 round trip per 4 columns)
 };
 // LayerNorm statistics slots.  The producers lead the MMA by at most kMaxStagesA k-blocks = ceil(16 / 3) = 6 tiles
 // (a LayerNorm'ed tile has >= 3 k-blocks) and the MMA leads the epilogue's statistics read by < 2 tiles.
 constexpr int kStatSlots = 8;
 constexpr size_t kSmemHeader = 512 + kStatSlots * 128 * 8 + 2 * kEpiWarps * 32 * 8;  // barriers + stats + row pointers
 
-__device__ __forceinline__ SmemMap carve(uint8_t *smem, int n_tile, int stages_a, int stages_b) {
+__device__ __forceinline__ SmemMap carve(uint8_t *smem, int n_tile, int stages_a, int stages_b, int slab) {
   SmemMap m;
   uint64_t *bars = reinterpret_cast<uint64_t *>(smem);
   m.fullA = bars;
@@ -251,11 +322,12 @@ __device__ __forceinline__ SmemMap carve(uint8_t *smem, int n_tile, int stages_a
   m.a_ring = smem + kSmemHeader;
   m.b_ring = m.a_ring + stages_a * kAStageBytes;
   m.stage = m.b_ring + (size_t)stages_b * kChunks * n_tile * 16;
+  m.aux = reinterpret_cast<float *>(m.stage + (size_t)kEpiWarps * 32 * (slab + kStagePad) * 4);
   return m;
 }
 
-size_t linear_smem_bytes(int n_tile, int slab, int stages_a, int stages_b) {
-  return kSmemHeader + (size_t)stages_a * kAStageBytes + (size_t)stages_b * kChunks * n_tile * 16 +
+size_t linear_smem_bytes(int n_tile, int slab, int stages_a, int stages_b, int N) {
+  return (size_t)3 * N * 4 + kSmemHeader + (size_t)stages_a * kAStageBytes + (size_t)stages_b * kChunks * n_tile * 16 +
          (size_t)kEpiWarps * 32 * (slab + kStagePad) * 4;
 }
 
@@ -266,7 +338,8 @@ linear_tf32_kernel(const __grid_constant__ LinearParams P) {
   const stf_linear_args &a = P.a;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int NT = P.n_tile;
-  const SmemMap S = carve(smem, NT, P.stages_a, P.stages_b);
+  const SmemMap S = carve(smem, NT, P.stages_a, P.stages_b, P.slab);
+  for (int i = threadIdx.x; i < 3 * a.N; i += kThreads) S.aux[i] = __ldg(P.aux + i);  // visible after the __syncthreads below
   const uint32_t SA = (uint32_t)P.stages_a, SB = (uint32_t)P.stages_b;
   const uint32_t b_stage_bytes = (uint32_t)(kChunks * NT * 16);
 
@@ -303,8 +376,10 @@ linear_tf32_kernel(const __grid_constant__ LinearParams P) {
     const uint32_t a_base = smem_u32(S.a_ring) + (uint32_t)(chunk * (kTileM * 16) + (warp * 32 + sub) * 16);
     uint32_t i_stage = 0, i_phase = 1;  // waiting on parity 1 of a fresh barrier returns immediately
     const bool merge = a.rows == STF_ROWS_MERGE;
-    for (int i_tile = first_tile; i_tile < P.total_tiles; i_tile += tile_step) {
+    int tr_it = 0;
+    for (int i_tile = first_tile; i_tile < P.total_tiles; i_tile += tile_step, ++tr_it) {
       const int m0 = (i_tile / P.n_tiles) * kTileM;
+      if (warp == 0) TRACE(0, tr_it);
       RowSrc src[4];
       const float *base[4];
       uint32_t nbytes[4];
@@ -317,7 +392,8 @@ linear_tf32_kernel(const __grid_constant__ LinearParams P) {
       for (int i_kb = 0; i_kb < P.k_blocks; ++i_kb) {
         mbar_wait(&S.emptyA[i_stage], i_phase);
         const uint32_t dst = a_base + i_stage * kAStageBytes;
-        if (!merge) {
+        if (P.debug_skip & 1) {
+        } else if (!merge) {
 #pragma unroll
           for (int i = 0; i < 4; ++i) cp_async16(dst + i * 128, base[i] + i_kb * kBlockK, nbytes[i]);
         } else {
@@ -331,6 +407,7 @@ linear_tf32_kernel(const __grid_constant__ LinearParams P) {
         cp_async_arrive_noinc(&S.landA[i_stage]);  // arrives once this thread's copies above have landed
         if (++i_stage == SA) i_stage = 0, i_phase ^= 1u;
       }
+      if (warp == 0) TRACE(1, tr_it);
     }
   } else if (warp < kFirstEpiWarp) {
     // =========================== A producers: finalize ===========================
@@ -341,11 +418,13 @@ linear_tf32_kernel(const __grid_constant__ LinearParams P) {
     const uint32_t a_base = smem_u32(S.a_ring) + (uint32_t)(chunk * (kTileM * 16) + (fw * 32 + sub) * 16);
     const float inv_k = 1.0f / (float)a.K;
     uint32_t f_stage = 0, f_phase = 0;
+    int in_group = 0;
     float shift0[4] = {0.f, 0.f, 0.f, 0.f}, sum[4] = {0.f, 0.f, 0.f, 0.f}, sq[4] = {0.f, 0.f, 0.f, 0.f};
     int f_it = 0;
     for (int tile = first_tile; tile < P.total_tiles; tile += tile_step, ++f_it) {
       for (int f_kb = 0; f_kb < P.k_blocks; ++f_kb) {
         mbar_wait(&S.landA[f_stage], f_phase);
+        if (fw == 0 && f_kb == 0) TRACE(2, f_it);
         const uint32_t addr = a_base + f_stage * kAStageBytes;
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
@@ -376,11 +455,24 @@ linear_tf32_kernel(const __grid_constant__ LinearParams P) {
             }
           }
         }
-        fence_proxy_async_smem();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&S.fullA[f_stage]);
+        // One proxy fence publishes a group of `fin_group` k-blocks (it divides k_blocks): the fence is the
+        // expensive, latency-bound step of this role and K-deep GEMMs (fc2: up to 96 k-blocks) are paced by it.
+        if (++in_group == P.fin_group) {
+          fence_proxy_async_smem();
+          __syncwarp();
+          if (lane == 0) {
+            uint32_t st = f_stage + 1 - (uint32_t)in_group;  // first stage of the group (may wrap)
+            if ((int)st < 0) st += SA;
+            for (int q = 0; q < in_group; ++q) {
+              mbar_arrive(&S.fullA[st]);
+              if (++st == SA) st = 0;
+            }
+          }
+          in_group = 0;
+        }
         if (++f_stage == SA) f_stage = 0, f_phase ^= 1u;
       }
+      if (fw == 0) TRACE(3, f_it);
     }
   } else if (warp < kMmaWarp) {
     // =========================== epilogue ===========================
@@ -392,8 +484,8 @@ linear_tf32_kernel(const __grid_constant__ LinearParams P) {
     const int srow = slab + kStagePad;     // staging row stride in floats
     float *stg = reinterpret_cast<float *>(S.stage) + (size_t)ew * 32 * srow;
     const uint32_t stg_u32 = smem_u32(stg);
-    uint64_t *rdst = S.row_dst + ew * 32, *rres = S.row_res + ew * 32;
-    const float *aux_s = P.aux, *aux_t = P.aux + a.N, *aux_b = P.aux + 2 * a.N;
+    uint64_t *rdst = S.row_dst + ew * 32;
+    const float *aux_s = S.aux, *aux_t = S.aux + a.N, *aux_b = S.aux + 2 * a.N;
     int it = 0;
     for (int tile = first_tile; tile < P.total_tiles; tile += tile_step, ++it) {
       const int buf = it & 1;
@@ -412,25 +504,33 @@ linear_tf32_kernel(const __grid_constant__ LinearParams P) {
             res = a.residual + (int64_t)tok * a.ldy;
           }
         } else if (a.epilogue == STF_EPI_PIXEL_SHUFFLE) {
-          int b = row / (a.H * a.W);
-          int rem = row - b * (a.H * a.W);
-          int h = rem / a.W, w = rem - h * a.W;
+          int b, rem, h, w;
+          P.d_hw.divmod(row, b, rem);
+          P.d_w.divmod(rem, h, w);
           dst = a.y + (int64_t)((b * 2 * a.H + 2 * h) * (2 * a.W) + 2 * w) * a.ldy;  // token (2h, 2w)
         } else {
           dst = a.y + (int64_t)row * a.ldy;
           if (a.epilogue == STF_EPI_RESIDUAL) res = a.residual + (int64_t)row * a.ldy;
         }
-        if (a.rows == STF_ROWS_WINDOW && P.has_ln) {  // pad tokens are zero AFTER norm1 (stf.py:155-162)
+        if (a.rows == STF_ROWS_WINDOW && P.has_ln && P.has_pad) {  // pad tokens are zero AFTER norm1 (stf.py:155-162)
           bool valid;
           (void)window_row_to_token(P, row, &valid);
           pad_row = !valid;
         }
       }
-      __syncwarp();  // previous tile's phase 2 has finished reading the row pointers
-      rdst[lane] = (uint64_t)dst;
-      rres[lane] = (uint64_t)res;
+      // dense destinations (STORE / QKV / GELU / RESIDUAL): rows of this warp are consecutive in y
+      const bool dense = a.epilogue != STF_EPI_WINDOW_RESIDUAL && a.epilogue != STF_EPI_PIXEL_SHUFFLE;
+      const int row_base = mt * kTileM + quad * 32;
+      float *dense0 = dense ? a.y + (int64_t)row_base * a.ldy : nullptr;
+      const int rows_valid = a.M - row_base;
+      if (!dense) {
+        __syncwarp();  // previous tile's phase 2 has finished reading the row pointers
+        rdst[lane] = (uint64_t)dst;
+      }
 
+      if (ew == 0) TRACE(10, it);
       mbar_wait(&S.accFull[buf], (uint32_t)(it >> 1) & 1u);
+      if (ew == 0) TRACE(7, it);
       tc_fence_after();
       float mean = 0.f, rstd = 1.f;
       if (P.has_ln) {
@@ -441,13 +541,13 @@ linear_tf32_kernel(const __grid_constant__ LinearParams P) {
       for (int s = half; s < n_slabs; s += 4) {
         const int c0 = s * slab;       // column inside the tile
         const int n0 = nt * NT + c0;   // global output feature
-        const bool row_store = a.epilogue != STF_EPI_PIXEL_SHUFFLE;
+        const bool row_store = P.epi_mode == 1 && a.epilogue != STF_EPI_PIXEL_SHUFFLE;
         if (row_store) bulk_wait_read0();  // this thread's previous bulk store has finished reading its staging row
         // ---- phase 1: thread = row.  TMEM -> registers -> math -> staging
         for (int c = 0; c < slab; c += 16) {
           const int n = n0 + c;
           float4 rv[4];
-          if (row_store && res) {  // issued before the TMEM load so that its latency overlaps
+          if (res) {  // issued before the TMEM load so that its latency overlaps
 #pragma unroll
             for (int j = 0; j < 4; ++j) rv[j] = __ldg(reinterpret_cast<const float4 *>(res + n + 4 * j));
           }
@@ -455,8 +555,8 @@ linear_tf32_kernel(const __grid_constant__ LinearParams P) {
           tmem_ld16(t_acc + (uint32_t)(c0 + c), acc);
 #pragma unroll
           for (int j = 0; j < 16; j += 4) {
-            const float4 sv = __ldg(reinterpret_cast<const float4 *>(aux_s + n + j));
-            const float4 tv = __ldg(reinterpret_cast<const float4 *>((pad_row ? aux_b : aux_t) + n + j));
+            const float4 sv = *reinterpret_cast<const float4 *>(aux_s + n + j);
+            const float4 tv = *reinterpret_cast<const float4 *>((pad_row ? aux_b : aux_t) + n + j);
             if (pad_row) {
               acc[j] = tv.x, acc[j + 1] = tv.y, acc[j + 2] = tv.z, acc[j + 3] = tv.w;
             } else {
@@ -475,7 +575,7 @@ linear_tf32_kernel(const __grid_constant__ LinearParams P) {
 #pragma unroll
             for (int j = 0; j < 16; ++j) acc[j] = gelu_erf(acc[j]);
           }
-          if (row_store && res) {
+          if (res) {
 #pragma unroll
             for (int j = 0; j < 4; ++j)
               acc[4 * j] += rv[j].x, acc[4 * j + 1] += rv[j].y, acc[4 * j + 2] += rv[j].z, acc[4 * j + 3] += rv[j].w;
@@ -484,6 +584,7 @@ linear_tf32_kernel(const __grid_constant__ LinearParams P) {
 #pragma unroll
           for (int j = 0; j < 16; j += 4) sts128(sa + j * 4, make_float4(acc[j], acc[j + 1], acc[j + 2], acc[j + 3]));
         }
+        if (ew == 0) TRACE(8, it);
         if (s + 4 >= n_slabs) {  // last TMEM read of this warp for this tile: release the accumulator early
           tc_fence_before();
           __syncwarp();
@@ -491,21 +592,31 @@ linear_tf32_kernel(const __grid_constant__ LinearParams P) {
         }
         if (row_store) {  // one bulk (TMA) copy per row: staging row -> its destination row segment
           fence_proxy_async_smem();
-          if (dst) bulk_store_s2g(dst + n0, stg_u32 + (uint32_t)(lane * srow * 4), (uint32_t)(slab * 4));
+          if (dst && !(P.debug_skip & 4)) bulk_store_s2g(dst + n0, stg_u32 + (uint32_t)(lane * srow * 4), (uint32_t)(slab * 4));
           bulk_commit();
+          if (ew == 0) TRACE(9, it);
         }
         if (row_store) continue;
         __syncwarp();
-        // ---- PatchSplit only: lanes sweep the 32 staged rows and scatter (pixel shuffle)
-        store_slab_pixel_shuffle(a, stg_u32, srow, f4row, rdst, n0, lane);
+        // ---- phase 2: lanes sweep the 32 staged rows with contiguous 16-byte accesses
+        if (a.epilogue == STF_EPI_PIXEL_SHUFFLE) {
+          store_slab_pixel_shuffle(a, stg_u32, srow, f4row, rdst, n0, lane);
+        } else if (!(P.debug_skip & 4)) {
+          switch (f4row) {
+            case 4: store_slab<4>(stg_u32, srow, rdst, dense0, a.ldy, rows_valid, n0, lane); break;
+            case 8: store_slab<8>(stg_u32, srow, rdst, dense0, a.ldy, rows_valid, n0, lane); break;
+            default: store_slab<12>(stg_u32, srow, rdst, dense0, a.ldy, rows_valid, n0, lane); break;
+          }
+        }
         __syncwarp();  // staging is reused by the next slab
+        if (ew == 0) TRACE(9, it);
       }
       if (half >= n_slabs) {  // this warp had no slab in this tile: still has to release the accumulator
         __syncwarp();
         if (lane == 0) mbar_arrive(&S.accEmpty[buf]);
       }
     }
-    bulk_wait0();  // all bulk stores of this thread have been written
+    if (P.epi_mode == 1) bulk_wait0();  // all bulk stores of this thread have been written
   } else if (warp == kMmaWarp) {
     // =========================== MMA issuer ===========================
     if (lane == 0) {
@@ -516,11 +627,13 @@ linear_tf32_kernel(const __grid_constant__ LinearParams P) {
       for (int tile = first_tile; tile < P.total_tiles; tile += tile_step, ++it) {
         const int buf = it & 1;
         mbar_wait(&S.accEmpty[buf], ((uint32_t)(it >> 1) & 1u) ^ 1u);
+        TRACE(4, it);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + (uint32_t)(buf * P.acc_stride);
         for (int kb = 0; kb < P.k_blocks; ++kb) {
           mbar_wait(&S.fullA[sa], pa);
           mbar_wait(&S.fullB[sb], pb);
+          if (kb == 0) TRACE(5, it);
           tc_fence_after();
           const uint32_t a_addr = smem_u32(S.a_ring) + sa * kAStageBytes;
           const uint32_t b_addr = smem_u32(S.b_ring) + sb * b_stage_bytes;
@@ -536,6 +649,7 @@ linear_tf32_kernel(const __grid_constant__ LinearParams P) {
           if (++sb == SB) sb = 0, pb ^= 1u;
         }
         umma_commit(&S.accFull[buf]);  // accumulator complete -> epilogue
+        TRACE(6, it);
       }
     }
     __syncwarp();
@@ -548,8 +662,12 @@ linear_tf32_kernel(const __grid_constant__ LinearParams P) {
         const float *wt = a.w_packed + (size_t)nt * (size_t)(a.K >> 2) * NT * 4;
         for (int kb = 0; kb < P.k_blocks; ++kb) {
           mbar_wait(&S.emptyB[sb], pb);
-          mbar_arrive_expect_tx(&S.fullB[sb], b_stage_bytes);
-          bulk_copy_g2s(S.b_ring + sb * b_stage_bytes, wt + (size_t)kb * kChunks * NT * 4, b_stage_bytes, &S.fullB[sb]);
+          if (P.debug_skip & 2) {
+            mbar_arrive(&S.fullB[sb]);
+          } else {
+            mbar_arrive_expect_tx(&S.fullB[sb], b_stage_bytes);
+            bulk_copy_g2s(S.b_ring + sb * b_stage_bytes, wt + (size_t)kb * kChunks * NT * 4, b_stage_bytes, &S.fullB[sb]);
+          }
           if (++sb == SB) sb = 0, pb ^= 1u;
         }
       }
@@ -623,6 +741,7 @@ int launch_linear(const stf_linear_args *args, void *stream) {
   if (a.epilogue < STF_EPI_STORE || a.epilogue > STF_EPI_PIXEL_SHUFFLE) return STF_E_ARG;
   if (a.rows < STF_ROWS_DENSE || a.rows > STF_ROWS_MERGE) return STF_E_ARG;
   if (a.epilogue == STF_EPI_QKV && (a.q_cols % 16 != 0)) return STF_E_SHAPE;
+  if (a.rows == STF_ROWS_MERGE && a.epilogue == STF_EPI_PIXEL_SHUFFLE) return STF_E_SHAPE;  // share the H*W divisors
 
   LinearParams P;
   P.a = a;
@@ -642,8 +761,19 @@ int launch_linear(const stf_linear_args *args, void *stream) {
   P.idesc = umma_idesc_tf32(kTileM, P.n_tile);
   P.has_ln = a.has_ln ? 1 : 0;
   P.stages_b = P.n_tile > 192 ? 3 : kStagesB;
+  static const int debug_skip_env = [] {
+    const char *e = getenv("STF_B200_DEBUG_SKIP");
+    return e ? atoi(e) : 0;
+  }();
+  P.debug_skip = debug_skip_env;
+  static const int epi_mode_env = [] {
+    const char *e = getenv("STF_B200_EPILOGUE");
+    return e ? atoi(e) : 0;
+  }();
+  P.epi_mode = epi_mode_env;
+  P.fin_group = (P.k_blocks % 4 == 0) ? 4 : (P.k_blocks % 3 == 0) ? 3 : (P.k_blocks % 2 == 0) ? 2 : 1;
   {  // all the shared memory the B ring and the epilogue staging leave over goes to the A ring
-    const size_t fixed = linear_smem_bytes(P.n_tile, P.slab, 0, P.stages_b);
+    const size_t fixed = linear_smem_bytes(P.n_tile, P.slab, 0, P.stages_b, a.N);
     const size_t budget = 227 * 1024;
     if (fixed + 4 * kAStageBytes > budget) return STF_E_SHAPE;
     int sa = (int)((budget - fixed) / kAStageBytes);
@@ -652,6 +782,8 @@ int launch_linear(const stf_linear_args *args, void *stream) {
   // the statistics hand-over (kStatSlots tiles deep) relies on a tile spanning at least 3 k-blocks
   if (P.has_ln && P.k_blocks < 3) return STF_E_SHAPE;
   P.Hp = P.Wp = P.nWw = P.nW = 0;
+  P.has_pad = 0;
+  P.d_img.init(1), P.d_win.init(1), P.d_nWw.init(1), P.d_ws.init(1), P.d_hw.init(1), P.d_w.init(1);
   const bool windowed = a.rows == STF_ROWS_WINDOW || a.epilogue == STF_EPI_WINDOW_RESIDUAL;
   if (windowed) {
     if (a.window <= 0 || a.batch <= 0 || a.H <= 0 || a.W <= 0 || a.shift < 0 || a.shift >= a.window) return STF_E_SHAPE;
@@ -660,16 +792,20 @@ int launch_linear(const stf_linear_args *args, void *stream) {
     P.nWw = P.Wp / a.window;
     P.nW = (P.Hp / a.window) * P.nWw;
     if ((int64_t)a.M != (int64_t)a.batch * P.Hp * P.Wp) return STF_E_SHAPE;
+    P.has_pad = (P.Hp != a.H || P.Wp != a.W) ? 1 : 0;
+    P.d_img.init(P.nW * a.window * a.window), P.d_win.init(a.window * a.window), P.d_nWw.init(P.nWw), P.d_ws.init(a.window);
   }
   if (a.rows == STF_ROWS_MERGE) {
     if (a.batch <= 0 || a.H <= 0 || a.W <= 0 || a.K % 4 != 0 || (a.K / 4) % kBlockK != 0) return STF_E_SHAPE;
     if ((int64_t)a.M != (int64_t)a.batch * ((a.H + 1) / 2) * ((a.W + 1) / 2)) return STF_E_SHAPE;
+    P.d_hw.init(((a.H + 1) / 2) * ((a.W + 1) / 2)), P.d_w.init((a.W + 1) / 2);
   }
   if (a.epilogue == STF_EPI_PIXEL_SHUFFLE) {
     if (a.batch <= 0 || a.H <= 0 || a.W <= 0 || (int64_t)a.M != (int64_t)a.batch * a.H * a.W) return STF_E_SHAPE;
     if (a.ldy < a.N / 4) return STF_E_SHAPE;
+    P.d_hw.init(a.H * a.W), P.d_w.init(a.W);
   }
-  const size_t smem = linear_smem_bytes(P.n_tile, P.slab, P.stages_a, P.stages_b);
+  const size_t smem = linear_smem_bytes(P.n_tile, P.slab, P.stages_a, P.stages_b, a.N);
   if (smem > 227 * 1024) return STF_E_SHAPE;
   static std::atomic<int> attr_set{0};
   if (!attr_set.load(std::memory_order_acquire)) {
@@ -713,3 +849,14 @@ extern "C" int stf_pack_linear(const float *weight, const float *bias, const flo
 }
 
 extern "C" int stf_linear(const stf_linear_args *args, void *stream) { return launch_linear(args, stream); }
+
+// Profiling aid (not in the public header): copy the in-kernel trace of the last traced launch to the host.
+extern "C" int stf_debug_read_trace(long long *out, int max_entries) {
+  long long tmp[kTraceEvents * kTraceTiles];
+  cudaError_t e = cudaMemcpyFromSymbol(tmp, g_trace, sizeof(tmp));
+  if (e != cudaSuccess) return (int)e;
+  int n = kTraceEvents * kTraceTiles;
+  if (n > max_entries) n = max_entries;
+  for (int i = 0; i < n; ++i) out[i] = tmp[i];
+  return kTraceTiles;
+}

@@ -17,6 +17,9 @@
 #include <string.h>
 
 #include <cmath>
+#include <condition_variable>
+#include <functional>
+#include <mutex>
 #include <new>
 #include <thread>
 #include <vector>
@@ -177,20 +180,99 @@ int decode_run(stf_rans_decoder *d, const stf_rans_table *t, const int32_t *inde
   return STF_OK;
 }
 
+// Persistent worker pool: decode_batch is called once per slice (12-13 times per image batch), so
+// spawning std::threads per call (~25 us each) would cost more than the decoding itself.
+// The pool is the only process-wide state of the library; it is created on first use, its workers
+// sleep on a condition variable between calls, and concurrent callers are serialised.
+class Pool {
+ public:
+  static Pool &get() {
+    static Pool p;
+    return p;
+  }
+  template <class F>
+  void run(int count, int threads, F f) {
+    if (count <= 0) return;
+    if (threads > count) threads = count;
+    if (threads <= 1) {
+      for (int i = 0; i < count; ++i) f(i);
+      return;
+    }
+    std::lock_guard<std::mutex> caller(run_mutex_);
+    ensure_workers(threads - 1);
+    std::function<void(int)> fn = f;
+    {
+      std::lock_guard<std::mutex> lk(m_);
+      fn_ = &fn;
+      next_ = 0;
+      count_ = count;
+      pending_ = count;
+      helpers_ = threads - 1;
+      ++generation_;
+    }
+    cv_work_.notify_all();
+    drain();  // the calling thread works too
+    std::unique_lock<std::mutex> lk(m_);
+    cv_done_.wait(lk, [&] { return pending_ == 0 && busy_ == 0; });
+    fn_ = nullptr;
+  }
+
+ private:
+  Pool() = default;
+  ~Pool() {
+    {
+      std::lock_guard<std::mutex> lk(m_);
+      stop_ = true;
+    }
+    cv_work_.notify_all();
+    for (auto &t : workers_) t.join();
+  }
+  void ensure_workers(int n) {
+    while ((int)workers_.size() < n) {
+      const int id = (int)workers_.size();
+      workers_.emplace_back([this, id] { worker(id); });
+    }
+  }
+  void drain() {
+    for (;;) {
+      int i;
+      {
+        std::lock_guard<std::mutex> lk(m_);
+        if (next_ >= count_) return;
+        i = next_++;
+      }
+      (*fn_)(i);
+      std::lock_guard<std::mutex> lk(m_);
+      if (--pending_ == 0) cv_done_.notify_all();
+    }
+  }
+  void worker(int id) {
+    uint64_t seen = 0;
+    for (;;) {
+      {
+        std::unique_lock<std::mutex> lk(m_);
+        cv_work_.wait(lk, [&] { return stop_ || (generation_ != seen && id < helpers_ && next_ < count_); });
+        if (stop_) return;
+        seen = generation_;
+        ++busy_;
+      }
+      drain();
+      std::lock_guard<std::mutex> lk(m_);
+      if (--busy_ == 0 && pending_ == 0) cv_done_.notify_all();
+    }
+  }
+  std::mutex run_mutex_, m_;
+  std::condition_variable cv_work_, cv_done_;
+  std::vector<std::thread> workers_;
+  const std::function<void(int)> *fn_ = nullptr;
+  int next_ = 0, count_ = 0, pending_ = 0, helpers_ = 0, busy_ = 0;
+  uint64_t generation_ = 0;
+  bool stop_ = false;
+};
+
 template <class F>
 void parallel_for(int count, int threads, F f) {
-  if (threads > count) threads = count;
-  if (threads <= 1) {
-    for (int i = 0; i < count; ++i) f(i);
-    return;
-  }
-  std::vector<std::thread> pool;
-  pool.reserve(threads);
-  for (int tid = 0; tid < threads; ++tid)
-    pool.emplace_back([=] {
-      for (int i = tid; i < count; i += threads) f(i);
-    });
-  for (auto &th : pool) th.join();
+  Pool::get().run(count, threads, f);
 }
 
 }  // namespace

@@ -39,6 +39,10 @@ SCALES_MIN, SCALES_MAX, SCALES_LEVELS = 0.11, 256, 64   # stf.py:16-18
 
 _GRAPHS_DEFAULT = os.environ.get("STF_B200_CUDA_GRAPHS", "1") != "0"
 _EB_MEDIAN = _C.STF_EB_MEDIAN_SLOT
+# Batches of at least this many images are coded as two pipelined halves (host rANS of one half overlaps the
+# device work of the other).  Below it the per-slice device segments are launch-latency bound (~80 dependent
+# small kernels), so halving the batch does not halve their time and the split costs more than it hides.
+_PIPELINE_MIN_BATCH = int(os.environ.get("STF_B200_PIPELINE_MIN_BATCH", "1000000"))
 PHASE_TIMES = None   # set to a dict to collect a synchronised wall-clock breakdown (tools/phase_breakdown.py)
 
 
@@ -252,39 +256,59 @@ class _SliceCodec(CompressionModel):
     def _graphs_enabled(self):
         return self.__dict__.get("cuda_graphs", _GRAPHS_DEFAULT) and PHASE_TIMES is None
 
+    @staticmethod
+    def _parts(B, pipelined):
+        """Image ranges coded as independent sub-batches.  Two parts let the host rANS work of one part overlap
+        the device work of the other (the device runs part B while the host codes part A, and vice versa)."""
+        if not pipelined or B < _PIPELINE_MIN_BATCH:
+            return [(0, B)]
+        k = (B + 1) // 2
+        return [(0, k), (k, B)]
+
     @torch.no_grad()
     def compress(self, x, debug=None):
         gc, eb = self.gaussian_conditional, self.entropy_bottleneck
         y_table, z_table = gc.rans_table(), eb.rans_table()
         self._prepare_inference()
         x = x.contiguous()
-        if debug is None and self._graphs_enabled():
-            plans = self.__dict__.setdefault("_enc_plans", {})
-            key = tuple(x.shape)
-            if key not in plans:
-                if len(plans) >= 4:
-                    plans.clear()
-                plans[key] = graphs.Segment(lambda t: self._encode_gpu(t), [x])
-            sym, idx, z_sym = plans[key](x)
-        else:
-            sym, idx, z_sym = self._encode_gpu(x, keep=debug)
-        B, total = sym.shape
-        with _phase("enc.d2h"):
-            sym_h, idx_h = self._host_buffers("y", B, total)
-            zsym_h, _ = self._host_buffers("z", B, z_sym[0].numel())
-            sym_h.copy_(sym, non_blocking=True)
-            idx_h.copy_(idx, non_blocking=True)
-            zsym_h.copy_(z_sym.reshape(B, -1), non_blocking=True)
-            torch.cuda.current_stream().synchronize()
-        if debug is not None:
-            debug.update(symbols=sym_h.clone(), indexes=idx_h.clone(), z_symbols=zsym_h.clone())
-        with _phase("enc.rans"):
-            s_np, i_np, z_np = sym_h.numpy(), idx_h.numpy(), zsym_h.numpy()
-            z_idx = eb._build_indexes(z_sym.size()).reshape(B, -1).numpy()
-            # y and z streams of all images in one thread-parallel call (2B independent streams)
-            y_strings = ans.encode_batch(y_table, [s_np[b] for b in range(B)], [i_np[b] for b in range(B)])
-            z_strings = ans.encode_batch(z_table, [z_np[b] for b in range(B)], [z_idx[b] for b in range(B)])
-        return {"strings": [y_strings, z_strings], "shape": z_sym.size()[-2:]}
+        use_graphs = debug is None and self._graphs_enabled()
+        parts = self._parts(x.shape[0], use_graphs)
+        stream = torch.cuda.current_stream()
+        pending = []
+        for slot, (lo, hi) in enumerate(parts):
+            xp = x[lo:hi]
+            if use_graphs:
+                plans = self.__dict__.setdefault("_enc_plans", {})
+                key = tuple(xp.shape)
+                if key not in plans:
+                    if len(plans) >= 4:
+                        plans.clear()
+                    plans[key] = graphs.Segment(lambda t: self._encode_gpu(t), [xp])
+                sym, idx, z_sym = plans[key](xp)
+            else:
+                sym, idx, z_sym = self._encode_gpu(xp, keep=debug)
+            Bp, total = sym.shape
+            with _phase("enc.d2h"):
+                sym_h, idx_h = self._host_buffers(("y", slot), Bp, total)
+                zsym_h, _ = self._host_buffers(("z", slot), Bp, z_sym[0].numel())
+                sym_h.copy_(sym, non_blocking=True)      # stream-ordered before the next part's replay
+                idx_h.copy_(idx, non_blocking=True)      # overwrites the plan's static outputs
+                zsym_h.copy_(z_sym.reshape(Bp, -1), non_blocking=True)
+                ev = torch.cuda.Event()
+                ev.record(stream)
+            pending.append((ev, Bp, sym_h, idx_h, zsym_h, tuple(z_sym.shape)))
+        y_strings, z_strings = [], []
+        for ev, Bp, sym_h, idx_h, zsym_h, zshape in pending:
+            with _phase("enc.d2h"):
+                ev.synchronize()
+            if debug is not None:
+                debug.update(symbols=sym_h.clone(), indexes=idx_h.clone(), z_symbols=zsym_h.clone())
+            with _phase("enc.rans"):
+                s_np, i_np, z_np = sym_h.numpy(), idx_h.numpy(), zsym_h.numpy()
+                z_idx = eb._build_indexes(zshape).reshape(Bp, -1).numpy()
+                y_strings += ans.encode_batch(y_table, [s_np[b] for b in range(Bp)], [i_np[b] for b in range(Bp)])
+                z_strings += ans.encode_batch(z_table, [z_np[b] for b in range(Bp)], [z_idx[b] for b in range(Bp)])
+        return {"strings": [y_strings, z_strings], "shape": torch.Size(zshape[-2:])}
 
     def _host_buffers(self, tag, B, n):
         """Pinned int32 staging buffer pair, cached per (tag, shape): cudaHostAlloc is slow."""
@@ -333,13 +357,13 @@ class _SliceCodec(CompressionModel):
         y_hat = torch.cat(st["y_hat"], dim=1)
         return self._synthesis(y_hat).clamp_(0, 1)
 
-    def _decode_plan(self, B, C, zh, zw, device):
-        """13 CUDA-graph segments on one shared memory pool, captured once per (B, z shape)."""
+    def _decode_plan(self, slot, B, C, zh, zw, device):
+        """13 CUDA-graph segments on one shared memory pool, captured once per (slot, B, z shape)."""
         plans = self.__dict__.setdefault("_dec_plans", {})
-        key = (B, zh, zw)
+        key = (slot, B, zh, zw)
         if key in plans:
             return plans[key]
-        if len(plans) >= 4:
+        if len(plans) >= 6:
             plans.clear()
         h, w = zh * 4, zw * 4
         n = self.slice_channels * h * w
@@ -368,40 +392,58 @@ class _SliceCodec(CompressionModel):
         zh, zw = int(shape[0]), int(shape[1])
         h, w = zh * 4, zw * 4
         n = self.slice_channels * h * w
+        S = self.num_slices
         stream = torch.cuda.current_stream()
         use_graphs = self._graphs_enabled()
-        if use_graphs:
-            segs, st = self._decode_plan(B, C, zh, zw, device)
-        else:
-            st = {"hw": (h, w)}
-        with _phase("dec.hyper"):
-            zsym_h, _ = self._host_buffers("z", B, C * zh * zw)
-            z_np = zsym_h.numpy()
-            z_idx = eb._build_indexes((B, C, zh, zw)).reshape(B, -1).numpy()
-            ans.decode_batch(_decoders(strings[1]), z_table, [z_idx[b] for b in range(B)], outs=[z_np[b] for b in range(B)])
-            if use_graphs:
-                idx = segs[0](zsym_h.reshape(B, C, zh, zw))
-            else:
-                idx = self._dec_first(st, zsym_h.to(device, non_blocking=True).reshape(B, C, zh, zw))
-        decoders = _decoders(strings[0])
-        sym_h, idx_h = self._host_buffers("y", B, n)
-        idx_np, sym_np = idx_h.numpy(), sym_h.numpy()
-        for i in range(1, self.num_slices + 1):
-            with _phase("dec.slices.gpu"):
-                idx_h.copy_(idx.reshape(B, n), non_blocking=True)
-                stream.synchronize()
-            with _phase("dec.slices.rans"):
-                ans.decode_batch(decoders, y_table, [idx_np[b] for b in range(B)], outs=[sym_np[b] for b in range(B)])
-            last = i == self.num_slices
-            with _phase("dec.synthesis" if last else "dec.slices.gpu"):
+
+        class Part:
+            pass
+
+        parts = []
+        for slot, (lo, hi) in enumerate(self._parts(B, use_graphs)):
+            p = Part()
+            p.B = hi - lo
+            p.segs, p.st = self._decode_plan(slot, p.B, C, zh, zw, device) if use_graphs else (None, {"hw": (h, w)})
+            p.decoders = _decoders(strings[0][lo:hi])
+            p.sym_h, p.idx_h = self._host_buffers(("y", slot), p.B, n)
+            p.zsym_h, _ = self._host_buffers(("z", slot), p.B, C * zh * zw)
+            p.ev = torch.cuda.Event()
+            with _phase("dec.hyper"):
+                z_np = p.zsym_h.numpy()
+                z_idx = eb._build_indexes((p.B, C, zh, zw)).reshape(p.B, -1).numpy()
+                ans.decode_batch(_decoders(strings[1][lo:hi]), z_table, [z_idx[b] for b in range(p.B)],
+                                 outs=[z_np[b] for b in range(p.B)])
                 if use_graphs:
-                    out = segs[i](sym_h)          # pinned host buffer -> the segment's static input
+                    idx = p.segs[0](p.zsym_h.reshape(p.B, C, zh, zw))
                 else:
-                    sym = sym_h.to(device, non_blocking=True)
-                    out = self._dec_last(st, sym) if last else self._dec_mid(st, i, sym)
-                if not last:
-                    idx = out
-        return {"x_hat": out.clone() if use_graphs else out}
+                    idx = self._dec_first(p.st, p.zsym_h.to(device, non_blocking=True).reshape(p.B, C, zh, zw))
+                p.idx_h.copy_(idx.reshape(p.B, n), non_blocking=True)
+                p.ev.record(stream)
+            parts.append(p)
+        # slice loop: while the host decodes slice i-1 of one part, the device runs the other part's segment
+        outs = [None] * len(parts)
+        for i in range(1, S + 1):
+            last = i == S
+            for k, p in enumerate(parts):
+                with _phase("dec.slices.gpu"):
+                    p.ev.synchronize()
+                with _phase("dec.slices.rans"):
+                    idx_np, sym_np = p.idx_h.numpy(), p.sym_h.numpy()
+                    ans.decode_batch(p.decoders, y_table, [idx_np[b] for b in range(p.B)],
+                                     outs=[sym_np[b] for b in range(p.B)])
+                with _phase("dec.synthesis" if last else "dec.slices.gpu"):
+                    if use_graphs:
+                        out = p.segs[i](p.sym_h)          # pinned host buffer -> the segment's static input
+                    else:
+                        sym = p.sym_h.to(device, non_blocking=True)
+                        out = self._dec_last(p.st, sym) if last else self._dec_mid(p.st, i, sym)
+                    if last:
+                        outs[k] = out
+                    else:
+                        p.idx_h.copy_(out.reshape(p.B, n), non_blocking=True)
+                        p.ev.record(stream)
+        x_hat = torch.cat(outs, dim=0) if (len(outs) > 1 or use_graphs) else outs[0]
+        return {"x_hat": x_hat}
 
 
 def _decoders(strings):
