@@ -144,7 +144,7 @@ enum {
 enum {
   STF_EPI_STORE = 0,        /* Y[r, n] = acc (+bias)                                              */
   STF_EPI_QKV = 1,          /* (+bias), columns < q_cols scaled by q_scale (stf.py:97-100)        */
-  STF_EPI_GELU = 2,         /* exact-erf GELU(acc + bias) (stf.py:35-36)                          */
+  STF_EPI_GELU = 2,         /* exact-erf GELU(acc + bias) (stf.py:35-36), stored rounded to TF32  */
   STF_EPI_RESIDUAL = 3,     /* Y[r] = residual[r] + acc + bias  (stf.py:197)                      */
   STF_EPI_WINDOW_RESIDUAL = 4, /* row g -> token t via window_reverse + un-shift, pad rows dropped:*/
                             /* Y[t] = residual[t] + acc + bias (stf.py:181-196)                   */
@@ -165,6 +165,8 @@ typedef struct {
   /* prologue */
   int rows;               /* STF_ROWS_* */
   int has_ln;             /* 1: LayerNorm over the K gathered inputs (packed with ln_gamma / ln_beta) */
+  int x_is_tf32;          /* 1: caller guarantees X holds TF32-exact values (low 13 mantissa bits zero), e.g. the */
+                          /*    output of STF_EPI_GELU or stf_window_attention: the in-kernel rounding pass is skipped */
   float ln_eps;
   /* epilogue */
   int epilogue;           /* STF_EPI_* */

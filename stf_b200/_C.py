@@ -31,7 +31,7 @@ class LinearArgs(ctypes.Structure):
         ("x", c_vp), ("ldx", c_int),
         ("w_packed", c_vp),
         ("y", c_vp), ("ldy", c_int),
-        ("rows", c_int), ("has_ln", c_int), ("ln_eps", c_f32),
+        ("rows", c_int), ("has_ln", c_int), ("x_is_tf32", c_int), ("ln_eps", c_f32),
         ("epilogue", c_int), ("residual", c_vp), ("q_cols", c_int), ("q_scale", c_f32),
         ("batch", c_int), ("H", c_int), ("W", c_int), ("window", c_int), ("shift", c_int),
     ]

@@ -96,6 +96,7 @@ struct LinearParams {
   int acc_stride;  // TMEM columns between the two accumulators
   uint32_t idesc;
   int has_ln;
+  int lite;        // A operand needs no finalize pass (no LayerNorm, X already TF32-exact): one thread fences + publishes
   int stages_a, stages_b;
   int epi_mode;    // 0: staged slab -> coalesced 16-byte stores by the whole warp; 1: one bulk (TMA) store per row
   int debug_skip;  // bring-up / profiling only (env STF_B200_DEBUG_SKIP): 1 = no A loads, 2 = no B loads, 4 = no stores
@@ -345,7 +346,7 @@ linear_tf32_kernel(const __grid_constant__ LinearParams P) {
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < P.stages_a; ++s) {
-      mbar_init(&S.fullA[s], kFinalizeWarps);       // one elected lane per finalize warp
+      mbar_init(&S.fullA[s], P.lite ? 1 : kFinalizeWarps);  // one elected lane per (active) finalize warp
       mbar_init(&S.landA[s], kProducerWarps * 32);  // cp.async.mbarrier.arrive.noinc of every issuing thread
       mbar_init(&S.emptyA[s], 1);              // one tcgen05.commit
     }
@@ -414,6 +415,20 @@ linear_tf32_kernel(const __grid_constant__ LinearParams P) {
     // Once a k-block has landed: round it to TF32 in place (the tensor core would truncate), accumulate the
     // LayerNorm statistics of the rows, make the generic-proxy writes visible to the async proxy, publish.
     const int fw = warp - kProducerWarps;
+    if (P.lite) {
+      // The producer of X already rounded it to TF32 (GELU / attention epilogues do) and there is no LayerNorm:
+      // nothing to rewrite.  One thread turns "landed" into "visible to the tensor core" (proxy fence) and publishes.
+      if (fw == 0 && lane == 0) {
+        uint32_t st = 0, ph = 0;
+        const long long total_kb = (long long)((P.total_tiles - first_tile + tile_step - 1) / tile_step) * P.k_blocks;
+        for (long long g = 0; g < total_kb; ++g) {
+          mbar_wait(&S.landA[st], ph);
+          fence_proxy_async_smem();
+          mbar_arrive(&S.fullA[st]);
+          if (++st == SA) st = 0, ph ^= 1u;
+        }
+      }
+    } else {
     const int sub = lane & 7, chunk = lane >> 3;
     const uint32_t a_base = smem_u32(S.a_ring) + (uint32_t)(chunk * (kTileM * 16) + (fw * 32 + sub) * 16);
     const float inv_k = 1.0f / (float)a.K;
@@ -474,6 +489,7 @@ linear_tf32_kernel(const __grid_constant__ LinearParams P) {
       }
       if (fw == 0) TRACE(3, f_it);
     }
+    }  // !lite
   } else if (warp < kMmaWarp) {
     // =========================== epilogue ===========================
     const int ew = warp - kFirstEpiWarp;  // 0..15
@@ -573,7 +589,7 @@ linear_tf32_kernel(const __grid_constant__ LinearParams P) {
             }
           } else if (a.epilogue == STF_EPI_GELU) {
 #pragma unroll
-            for (int j = 0; j < 16; ++j) acc[j] = gelu_erf(acc[j]);
+            for (int j = 0; j < 16; ++j) acc[j] = round_tf32(gelu_erf(acc[j]));  // fc2 (the only consumer) reads it as TF32
           }
           if (res) {
 #pragma unroll
@@ -718,7 +734,9 @@ pack_weight_kernel(const float *__restrict__ w, const float *__restrict__ bias, 
 
 // Column slab handled by one epilogue warp at a time: minimise the columns on the critical path
 // (ceil(n_slabs / 4) * slab with four warps per lane quadrant), prefer wider slabs on ties.
-int pick_slab(int n_tile) {
+int pick_slab(int n_tile, int k_blocks) {
+  // K-deep tiles reach the epilogue rarely: give the shared memory to the A ring instead of the staging
+  if (k_blocks >= 12) return 16;
   const int max_slab = n_tile > 192 ? 32 : kMaxSlab;  // shared-memory budget
   int best = 16, best_cost = 1 << 30;
   for (int s = 16; s <= max_slab; s += 16) {
@@ -754,12 +772,13 @@ int launch_linear(const stf_linear_args *args, void *stream) {
   if (total > 0x7fffffff) return STF_E_SHAPE;
   P.total_tiles = (int)total;
   P.k_blocks = a.K / kBlockK;
-  P.slab = pick_slab(P.n_tile);
+  P.slab = pick_slab(P.n_tile, P.k_blocks);
   P.tmem_cols = 32;
   while (P.tmem_cols < 2 * P.n_tile) P.tmem_cols <<= 1;
   P.acc_stride = P.tmem_cols / 2;
   P.idesc = umma_idesc_tf32(kTileM, P.n_tile);
   P.has_ln = a.has_ln ? 1 : 0;
+  P.lite = (!a.has_ln && a.x_is_tf32) ? 1 : 0;
   P.stages_b = P.n_tile > 192 ? 3 : kStagesB;
   static const int debug_skip_env = [] {
     const char *e = getenv("STF_B200_DEBUG_SKIP");

@@ -26,6 +26,12 @@ namespace {
 constexpr int kThreads = 128;
 constexpr float kMaskValue = -100.0f;  // stf.py:334
 
+// The output feeds the proj GEMM only, which reads TF32: store it already rounded (round-to-nearest on the bit
+// pattern) so that stf_linear can take its x_is_tf32 fast path.
+__device__ __forceinline__ float round_tf32(float x) {
+  return __uint_as_float((__float_as_uint(x) + 0x1000u) & 0xFFFFE000u);
+}
+
 template <int WS, int D>
 __global__ void __launch_bounds__(kThreads)
 window_attention_kernel(const float *__restrict__ qkv, float *__restrict__ out,
@@ -111,7 +117,9 @@ window_attention_kernel(const float *__restrict__ qkv, float *__restrict__ out,
   }
   float *dst = out + (win * N + n) * (int64_t)C + head * D;
 #pragma unroll
-  for (int j = 0; j < D; j += 4) *reinterpret_cast<float4 *>(dst + j) = make_float4(o[j], o[j + 1], o[j + 2], o[j + 3]);
+  for (int j = 0; j < D; j += 4)
+    *reinterpret_cast<float4 *>(dst + j) =
+        make_float4(round_tf32(o[j]), round_tf32(o[j + 1]), round_tf32(o[j + 2]), round_tf32(o[j + 3]));
 }
 
 
@@ -217,7 +225,8 @@ window_attention16_kernel(const float *__restrict__ qkv, float *__restrict__ out
     // the q slot (row n, this head's columns) is read by this thread only: reuse it for the output
 #pragma unroll
     for (int j = 0; j < D; j += 4)
-      *reinterpret_cast<float4 *>(base + n * ld + j) = make_float4(o[j], o[j + 1], o[j + 2], o[j + 3]);
+      *reinterpret_cast<float4 *>(base + n * ld + j) =
+          make_float4(round_tf32(o[j]), round_tf32(o[j + 1]), round_tf32(o[j + 2]), round_tf32(o[j + 3]));
   }
   sm100::fence_proxy_async_smem();
   __syncthreads();

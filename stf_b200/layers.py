@@ -91,11 +91,12 @@ class Mlp(nn.Module):
         shape = x.shape
         x2 = x.reshape(-1, shape[-1])
         h = ops.linear(x2, self._p1.get(self.fc1.weight, self.fc1.bias, norm), epilogue=_C.EPI_GELU)
+        # h comes out of the GELU epilogue already rounded to TF32: fc2 skips its rounding pass
         if residual is None:
-            y = ops.linear(h, self._p2.get(self.fc2.weight, self.fc2.bias))
+            y = ops.linear(h, self._p2.get(self.fc2.weight, self.fc2.bias), x_is_tf32=True)
         else:
             y = ops.linear(h, self._p2.get(self.fc2.weight, self.fc2.bias), epilogue=_C.EPI_RESIDUAL,
-                           residual=residual.reshape(-1, residual.shape[-1]))
+                           residual=residual.reshape(-1, residual.shape[-1]), x_is_tf32=True)
         return y.reshape(*shape[:-1], y.shape[-1])
 
 
@@ -140,7 +141,7 @@ class WindowAttention(nn.Module):
         qkv = ops.linear(x.reshape(-1, C), self.packed_qkv(), epilogue=_C.EPI_QKV, q_cols=C, q_scale=self.scale)
         o = ops.window_attention_core(qkv, self.relative_position_bias_table, B_, C, self.num_heads, ws, 0,
                                       mask=mask)
-        y = ops.linear(o, self.packed_proj())
+        y = ops.linear(o, self.packed_proj(), x_is_tf32=True)   # the attention kernel stores TF32-rounded outputs
         return y.reshape(B_, N, C)
 
 
@@ -182,7 +183,7 @@ class SwinTransformerBlock(nn.Module):
         o = ops.window_attention_core(qkv, self.attn.relative_position_bias_table, B * (Hp // ws) * (Wp // ws), C,
                                       self.num_heads, ws, shift, Hp, Wp)
         x1 = ops.linear(o, self.attn.packed_proj(), epilogue=_C.EPI_WINDOW_RESIDUAL, residual=x2, geom=geom,
-                        out_rows=B * L)
+                        out_rows=B * L, x_is_tf32=True)
         y = self.mlp(x1, norm=self.norm2, residual=x1)
         return y.reshape(B, L, C)
 
@@ -316,7 +317,7 @@ class WinBasedAttention(nn.Module):
                          q_scale=self.attn.scale, geom=geom)
         o = ops.window_attention_core(qkv, self.attn.relative_position_bias_table, B * (H // ws) * (W // ws), C,
                                       self.num_heads, ws, shift, H, W)
-        y = ops.linear(o, self.attn.packed_proj(), epilogue=_C.EPI_WINDOW_RESIDUAL, residual=t, geom=geom)
+        y = ops.linear(o, self.attn.packed_proj(), epilogue=_C.EPI_WINDOW_RESIDUAL, residual=t, geom=geom, x_is_tf32=True)
         return y.reshape(B, H, W, C).permute(0, 3, 1, 2).contiguous()
 
 

@@ -195,7 +195,7 @@ class PackedLinear:
 
 
 def linear(x, lin, *, M=None, rows=_C.ROWS_DENSE, epilogue=_C.EPI_STORE, residual=None, q_cols=0, q_scale=1.0,
-           geom=None, out=None, out_rows=None, out_cols=None):
+           geom=None, out=None, out_rows=None, out_cols=None, x_is_tf32=False):
     """Y = epilogue(LN?(gather(X)) . W^T)   (stf_linear in include/stf_b200.h).
 
     x: (rows_in, ldx) fp32; lin: PackedLinear (carries bias and the optional LayerNorm);
@@ -216,6 +216,7 @@ def linear(x, lin, *, M=None, rows=_C.ROWS_DENSE, epilogue=_C.EPI_STORE, residua
     a.y, a.ldy = out.data_ptr(), out.shape[-1]
     a.rows = rows
     a.has_ln, a.ln_eps = int(lin.has_ln), lin.ln_eps
+    a.x_is_tf32 = int(bool(x_is_tf32))
     a.epilogue = epilogue
     if residual is not None:
         residual = _dev(residual, "residual")

@@ -1,0 +1,84 @@
+"""GPU: the BASELINE.json configurations at their FULL sizes, checked through size-independent properties
+(the CPU oracle needs minutes per image at these sizes):
+  * encode -> decode round trip reproduces the encoder-side reconstruction (forward) exactly up to clamp;
+  * our bitstreams decode, with the CPU oracle's rANS decoder and our own indexes, to our own symbols (bit-exact);
+  * a batched call equals per-image calls in structure; likelihoods are valid probabilities; rate bookkeeping is sane.
+"""
+import json
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import entropy as OE
+from stf_b200.synth import synthetic_image, synthetic_state_dict
+
+pytestmark = pytest.mark.gpu
+
+
+def _net(golden_dir, name):
+    from stf_b200.models import models
+    spec = {k: (tuple(s), getattr(torch, d.split(".")[-1])) for k, (s, d) in
+            json.load(open(os.path.join(golden_dir, f"{name}_spec.json"))).items()}
+    net = models[name]()
+    torch.nn.Module.load_state_dict(net, synthetic_state_dict(spec, 0), strict=False)
+    net = net.cuda().eval()
+    net.update(force=True)
+    return net
+
+
+def test_config2_stf_forward_batch16_256(golden_dir):
+    """BASELINE config 2: STF forward + GaussianConditional likelihoods, batch 16 of 256x256."""
+    net = _net(golden_dir, "stf")
+    x = synthetic_image(16, 256, 256, seed=2).cuda()
+    out = net(x)
+    assert out["x_hat"].shape == (16, 3, 256, 256)
+    ly, lz = out["likelihoods"]["y"], out["likelihoods"]["z"]
+    assert ly.shape == (16, 384, 16, 16) and lz.shape == (16, 192, 4, 4)
+    for lik in (ly, lz):
+        assert torch.isfinite(lik).all() and float(lik.min()) >= 0.999e-9 and float(lik.max()) <= 1.0 + 1e-6
+    # batch invariance of our kernels: image 3 alone gives the same likelihoods as inside the batch
+    # (cuDNN may pick other algorithms per batch size, hence a tolerance instead of equality)
+    one = net(x[3:4])
+    rel = (one["likelihoods"]["y"] - ly[3:4]).abs() / ly[3:4]
+    assert float((rel < 2e-2).float().mean()) > 0.99      # the rest: symbols that flipped across a rounding tie (F6)
+    bpp = float((-torch.log2(ly).sum() - torch.log2(lz).sum()) / (16 * 256 * 256))
+    assert 1.0 < bpp < 40.0
+
+
+@pytest.mark.parametrize("batch", [1, 4])
+def test_config3_stf_kodak_size_roundtrip(golden_dir, batch):
+    """BASELINE config 3: STF compress / decompress at 768x512."""
+    net = _net(golden_dir, "stf")
+    x = synthetic_image(batch, 512, 768, seed=7).cuda()
+    enc = net.compress(x)
+    assert len(enc["strings"][0]) == batch and len(enc["strings"][1]) == batch and tuple(enc["shape"]) == (8, 12)
+    dec = net.decompress(enc["strings"], enc["shape"])["x_hat"]
+    fwd = net(x)["x_hat"].clamp(0, 1)
+    assert dec.shape == (batch, 3, 512, 768)
+    assert float((dec - fwd).abs().max()) < 1e-4                      # decoder rebuilt the encoder's state exactly
+    # bit-exact entropy coding at full size: oracle C decoder + our indexes -> our symbols
+    dbg = {}
+    enc2 = net.compress(x[:1], debug=dbg)
+    assert enc2["strings"][0][0] == enc["strings"][0][0]              # graph path == eager path, batched == single
+    cdf, lens, offs = OE.gaussian_tables()
+    sym, idx = dbg["symbols"][0].numpy(), dbg["indexes"][0].numpy()
+    assert sym.size == 384 * 32 * 48
+    assert np.array_equal(OE.rans_decode(enc2["strings"][0][0], idx, cdf, lens, offs), sym)
+    assert OE.rans_encode(sym, idx, cdf, lens, offs) == enc2["strings"][0][0]
+    n_bytes = sum(len(s) for grp in enc["strings"] for s in grp)
+    assert 0.5 < 8 * n_bytes / (batch * 512 * 768) < 40.0
+
+
+def test_config4_wacnn_clic_size_roundtrip(golden_dir):
+    """BASELINE config 4: WACNN at 2048x1408 (64-token windows with head_dim 24, 16-token with head_dim 40)."""
+    net = _net(golden_dir, "cnn")
+    x = synthetic_image(1, 1408, 2048, seed=9).cuda()
+    enc = net.compress(x)
+    assert tuple(enc["shape"]) == (22, 32)
+    dec = net.decompress(enc["strings"], enc["shape"])["x_hat"]
+    fwd = net(x)["x_hat"].clamp(0, 1)
+    assert dec.shape == (1, 3, 1408, 2048)
+    assert float((dec - fwd).abs().max()) < 1e-4
+    assert torch.isfinite(dec).all()

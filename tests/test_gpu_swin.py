@@ -177,7 +177,9 @@ def test_index_math_exact(H, W, shift):
         nW = mask.shape[0]
         attn = (attn.reshape(B, nW, nh, ws * ws, ws * ws) + mask[None, :, None]).reshape(-1, nh, ws * ws, ws * ws)
     ref_o = (torch.softmax(attn, -1) @ v).transpose(1, 2).reshape(-1, C)
-    assert (o.cpu() - ref_o).abs().max().item() < 2e-5
+    # (the kernel stores o rounded to TF32 for the proj GEMM: half a TF32 ulp = 2^-11 relative on top of fp32 round-off)
+    assert ((o.cpu() - ref_o).abs() <= 5e-4 * ref_o.abs() + 2e-5).all()
+    assert torch.equal(o.cpu(), rna_tf32(o.cpu()))          # ... and is TF32-exact, as stf_linear's x_is_tf32 path assumes
     # full block vs oracle (TF32 tolerance)
     y = blk(x.cuda(), None)
     mask = OS.shift_mask(Hp, Wp, ws, ws // 2)

@@ -60,11 +60,11 @@ def main():
                                                4 * T * (C + 3 * C), 2 * T * C * 3 * C),
             "attention core (shift)": (lambda: ops.window_attention_core(qkv, table, T // 16, C, nh, 4, 2, H, W),
                                        4 * T * 4 * C, 4 * T * 16 * C),
-            "linear proj (+window residual)": (lambda: ops.linear(o, Wproj, epilogue=_C.EPI_WINDOW_RESIDUAL, residual=x, geom=geom, out=x1),
+            "linear proj (+window residual)": (lambda: ops.linear(o, Wproj, epilogue=_C.EPI_WINDOW_RESIDUAL, residual=x, geom=geom, out=x1, x_is_tf32=True),
                                                4 * T * 3 * C, 2 * T * C * C),
             "linear fc1 (LN, GELU)": (lambda: ops.linear(x1, Wfc1, epilogue=_C.EPI_GELU, out=h),
                                       4 * T * 5 * C, 2 * T * C * 4 * C),
-            "linear fc2 (+residual)": (lambda: ops.linear(h, Wfc2, epilogue=_C.EPI_RESIDUAL, residual=x1, out=x2),
+            "linear fc2 (+residual)": (lambda: ops.linear(h, Wfc2, epilogue=_C.EPI_RESIDUAL, residual=x1, out=x2, x_is_tf32=True),
                                        4 * T * 6 * C, 2 * T * C * 4 * C),
         }
         for name, (fn, nbytes, flops) in cases.items():
