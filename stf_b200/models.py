@@ -40,9 +40,9 @@ SCALES_MIN, SCALES_MAX, SCALES_LEVELS = 0.11, 256, 64   # stf.py:16-18
 _GRAPHS_DEFAULT = os.environ.get("STF_B200_CUDA_GRAPHS", "1") != "0"
 _EB_MEDIAN = _C.STF_EB_MEDIAN_SLOT
 # Batches of at least this many images are coded as two pipelined halves (host rANS of one half overlaps the
-# device work of the other).  Below it the per-slice device segments are launch-latency bound (~80 dependent
-# small kernels), so halving the batch does not halve their time and the split costs more than it hides.
-_PIPELINE_MIN_BATCH = int(os.environ.get("STF_B200_PIPELINE_MIN_BATCH", "1000000"))
+# device work of the other; measured +4 % at batch 16, +8 % at batch 32).  Below it the per-slice device segments
+# are latency bound (~80 dependent small kernels), so halving the batch does not halve their time.
+_PIPELINE_MIN_BATCH = int(os.environ.get("STF_B200_PIPELINE_MIN_BATCH", "16"))
 PHASE_TIMES = None   # set to a dict to collect a synchronised wall-clock breakdown (tools/phase_breakdown.py)
 
 
@@ -173,12 +173,27 @@ class _SliceCodec(CompressionModel):
         self.__dict__["_prepared"] = True
 
     def _slice_params(self, i, latent_means, latent_scales, y_hat_slices, hw):
+        """mu and scale of slice i.  The two five-layer conv stacks are independent (stf.py:615-621): the scale
+        stack runs on a side stream, forked and joined with events (captured as parallel branches of the CUDA graph)."""
         support = y_hat_slices if self.max_support_slices < 0 else y_hat_slices[: self.max_support_slices]
+        main = torch.cuda.current_stream()
+        side = self._side_stream(main.device)
+        side.wait_stream(main)
+        with torch.cuda.stream(side):
+            scale_support = torch.cat([latent_scales] + support, dim=1)
+            scale = self.cc_scale_transforms[i](scale_support)[:, :, : hw[0], : hw[1]].contiguous()
         mean_support = torch.cat([latent_means] + support, dim=1)
         mu = self.cc_mean_transforms[i](mean_support)[:, :, : hw[0], : hw[1]].contiguous()
-        scale_support = torch.cat([latent_scales] + support, dim=1)
-        scale = self.cc_scale_transforms[i](scale_support)[:, :, : hw[0], : hw[1]].contiguous()
+        main.wait_stream(side)
+        scale.record_stream(main)
         return mean_support, mu, scale
+
+    def _side_stream(self, device):
+        streams = self.__dict__.setdefault("_side_streams", {})
+        key = str(device)
+        if key not in streams:
+            streams[key] = torch.cuda.Stream(device=device)
+        return streams[key]
 
     def _lrp(self, i, mean_support, y_hat_slice):
         y_hat_slice = y_hat_slice.contiguous(memory_format=self._CL)
