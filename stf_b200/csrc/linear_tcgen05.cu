@@ -9,15 +9,15 @@
 //   PatchSplit (LayerNorm, Linear C->2C, PixelShuffle(2) in token layout)      :251-260
 //
 // Persistent, warp-specialised kernel: one CTA per SM loops over (128-row M tile, n_tile-column N tile)
-// work items; 26 warps:
+// work items; 27 warps:
 //   warps 0-3   A issue.  cp.async (LDGSTS) 16-byte copies straight from the gathered rows (window
 //               partition / cyclic shift / 2x2 merge are index math on the source address; pad rows are
 //               zero-filled) into the UMMA K-major operand layout; completion is handed to a per-stage
 //               landing mbarrier (cp.async.mbarrier.arrive.noinc), so the whole ring stays in flight with no
 //               register staging and no thread ever waits on (or fences behind) its own outstanding loads.
-//   warps 4-7   A finalize.  When a k-block has landed: round it to TF32 (round-to-nearest) in place,
+//   warps 4-11  A finalize (16 rows each).  When a k-block has landed: round it to TF32 (round-to-nearest) in place,
 //               accumulate the LayerNorm statistics of the rows on the fly, fence.proxy.async, publish.
-//   warps 8-23  epilogue, four warps per TMEM lane quadrant, one column slab each: tcgen05.ld -> registers ->
+//   warps 12-23 epilogue, three warps per TMEM lane quadrant, one column slab each: tcgen05.ld -> registers ->
 //               math (+ residual) -> the thread's staging row in shared memory -> ONE bulk (TMA) store of that row
 //               segment to its destination (window_reverse / un-shift are index math on the destination address).
 //   warp 24     the single thread issuing tcgen05.mma (kind::tf32) + tcgen05.commit.
@@ -51,14 +51,16 @@ constexpr int kMaxStagesA = 16;       // A ring depth is chosen per launch from 
                                       // stages - 1 k-blocks (8 KB each) are in flight per CTA: HBM latency x bandwidth / SM
 constexpr int kStagesB = 4;           // (3 when n_tile > 192: shared-memory budget)
 constexpr int kProducerWarps = 4;       // cp.async issue warps
-constexpr int kFinalizeWarps = 4;       // TF32 rounding + LayerNorm statistics + proxy fence (same row/chunk mapping)
-constexpr int kEpiWarps = 16;         // four per TMEM lane quadrant, one column slab each at a time
-constexpr int kFirstEpiWarp = kProducerWarps + kFinalizeWarps;  // 8: keeps (warp & 3) == TMEM lane quadrant
+constexpr int kFinalizeWarps = 8;       // TF32 rounding + LayerNorm statistics + proxy fence, 16 rows per warp
+constexpr int kEpiWarps = 12;         // three per TMEM lane quadrant, one column slab each at a time
+constexpr int kEpiPerQuad = kEpiWarps / 4;
+constexpr int kFirstEpiWarp = kProducerWarps + kFinalizeWarps;  // 12: keeps (warp & 3) == TMEM lane quadrant
 constexpr int kMmaWarp = kFirstEpiWarp + kEpiWarps;
 constexpr int kLoadWarp = kMmaWarp + 1;
-constexpr int kThreads = (kLoadWarp + 1) * 32;  // 832
+constexpr int kFwdWarp = kLoadWarp + 1;  // forwards "weight stage landed" onto the A-side full barrier
+constexpr int kThreads = (kFwdWarp + 1) * 32;  // 864
 constexpr int kMaxNTile = 256;
-constexpr int kMaxSlab = 48;
+constexpr int kMaxSlab = 64;
 constexpr int kStagePad = 4;  // floats of padding per staging row: (slab + 4) % 32 in {4, 20} -> conflict-free v4 stores
 constexpr uint32_t kAStageBytes = kChunks * kTileM * 16;  // 8 KB
 
@@ -346,7 +348,7 @@ linear_tf32_kernel(const __grid_constant__ LinearParams P) {
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < P.stages_a; ++s) {
-      mbar_init(&S.fullA[s], P.lite ? 1 : kFinalizeWarps);  // one elected lane per (active) finalize warp
+      mbar_init(&S.fullA[s], (P.lite ? 1 : kFinalizeWarps) + 1);  // finalize publishers + the weight forwarder
       mbar_init(&S.landA[s], kProducerWarps * 32);  // cp.async.mbarrier.arrive.noinc of every issuing thread
       mbar_init(&S.emptyA[s], 1);              // one tcgen05.commit
     }
@@ -430,11 +432,11 @@ linear_tf32_kernel(const __grid_constant__ LinearParams P) {
       }
     } else {
     const int sub = lane & 7, chunk = lane >> 3;
-    const uint32_t a_base = smem_u32(S.a_ring) + (uint32_t)(chunk * (kTileM * 16) + (fw * 32 + sub) * 16);
+    const uint32_t a_base = smem_u32(S.a_ring) + (uint32_t)(chunk * (kTileM * 16) + (fw * 16 + sub) * 16);
     const float inv_k = 1.0f / (float)a.K;
     uint32_t f_stage = 0, f_phase = 0;
     int in_group = 0;
-    float shift0[4] = {0.f, 0.f, 0.f, 0.f}, sum[4] = {0.f, 0.f, 0.f, 0.f}, sq[4] = {0.f, 0.f, 0.f, 0.f};
+    float shift0[2] = {0.f, 0.f}, sum[2] = {0.f, 0.f}, sq[2] = {0.f, 0.f};
     int f_it = 0;
     for (int tile = first_tile; tile < P.total_tiles; tile += tile_step, ++f_it) {
       for (int f_kb = 0; f_kb < P.k_blocks; ++f_kb) {
@@ -442,7 +444,7 @@ linear_tf32_kernel(const __grid_constant__ LinearParams P) {
         if (fw == 0 && f_kb == 0) TRACE(2, f_it);
         const uint32_t addr = a_base + f_stage * kAStageBytes;
 #pragma unroll
-        for (int i = 0; i < 4; ++i) {
+        for (int i = 0; i < 2; ++i) {
           float4 v = lds128(addr + i * 128);
           if (P.has_ln) {
             if (f_kb == 0) {  // shift by the row's first element: keeps the one-pass variance well conditioned
@@ -457,7 +459,7 @@ linear_tf32_kernel(const __grid_constant__ LinearParams P) {
         }
         if (P.has_ln && f_kb == P.k_blocks - 1) {  // row statistics for the epilogue of this tile
 #pragma unroll
-          for (int i = 0; i < 4; ++i) {
+          for (int i = 0; i < 2; ++i) {
             float s1 = sum[i], s2 = sq[i];
             s1 += __shfl_xor_sync(0xffffffffu, s1, 8);
             s1 += __shfl_xor_sync(0xffffffffu, s1, 16);
@@ -466,7 +468,7 @@ linear_tf32_kernel(const __grid_constant__ LinearParams P) {
             if (chunk == 0) {
               float md = s1 * inv_k;
               float var = fmaxf(s2 * inv_k - md * md, 0.f);
-              S.stats[(f_it % kStatSlots) * 128 + fw * 32 + i * 8 + sub] = make_float2(shift0[i] + md, rsqrtf(var + a.ln_eps));
+              S.stats[(f_it % kStatSlots) * 128 + fw * 16 + i * 8 + sub] = make_float2(shift0[i] + md, rsqrtf(var + a.ln_eps));
             }
           }
         }
@@ -494,7 +496,7 @@ linear_tf32_kernel(const __grid_constant__ LinearParams P) {
     // =========================== epilogue ===========================
     const int ew = warp - kFirstEpiWarp;  // 0..15
     const int quad = warp & 3;             // TMEM lane quadrant this warp may read
-    const int half = ew >> 2;              // 0..3: this warp handles slabs half, half+4, ...
+    const int half = ew >> 2;              // 0..2: this warp handles slabs half, half+3, ...
     const int slab = P.slab, n_slabs = NT / slab;
     const int f4row = slab >> 2;           // float4 per staged row
     const int srow = slab + kStagePad;     // staging row stride in floats
@@ -545,7 +547,7 @@ linear_tf32_kernel(const __grid_constant__ LinearParams P) {
       }
 
       if (ew == 0) TRACE(10, it);
-      mbar_wait(&S.accFull[buf], (uint32_t)(it >> 1) & 1u);
+      mbar_wait_relaxed(&S.accFull[buf], (uint32_t)(it >> 1) & 1u);
       if (ew == 0) TRACE(7, it);
       tc_fence_after();
       float mean = 0.f, rstd = 1.f;
@@ -554,7 +556,7 @@ linear_tf32_kernel(const __grid_constant__ LinearParams P) {
         mean = st.x, rstd = st.y;
       }
       const uint32_t t_acc = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(buf * P.acc_stride);
-      for (int s = half; s < n_slabs; s += 4) {
+      for (int s = half; s < n_slabs; s += kEpiPerQuad) {
         const int c0 = s * slab;       // column inside the tile
         const int n0 = nt * NT + c0;   // global output feature
         const bool row_store = P.epi_mode == 1 && a.epilogue != STF_EPI_PIXEL_SHUFFLE;
@@ -601,7 +603,7 @@ linear_tf32_kernel(const __grid_constant__ LinearParams P) {
           for (int j = 0; j < 16; j += 4) sts128(sa + j * 4, make_float4(acc[j], acc[j + 1], acc[j + 2], acc[j + 3]));
         }
         if (ew == 0) TRACE(8, it);
-        if (s + 4 >= n_slabs) {  // last TMEM read of this warp for this tile: release the accumulator early
+        if (s + kEpiPerQuad >= n_slabs) {  // last TMEM read of this warp for this tile: release the accumulator early
           tc_fence_before();
           __syncwarp();
           if (lane == 0) mbar_arrive(&S.accEmpty[buf]);
@@ -621,7 +623,8 @@ linear_tf32_kernel(const __grid_constant__ LinearParams P) {
           switch (f4row) {
             case 4: store_slab<4>(stg_u32, srow, rdst, dense0, a.ldy, rows_valid, n0, lane); break;
             case 8: store_slab<8>(stg_u32, srow, rdst, dense0, a.ldy, rows_valid, n0, lane); break;
-            default: store_slab<12>(stg_u32, srow, rdst, dense0, a.ldy, rows_valid, n0, lane); break;
+            case 12: store_slab<12>(stg_u32, srow, rdst, dense0, a.ldy, rows_valid, n0, lane); break;
+            default: store_slab<16>(stg_u32, srow, rdst, dense0, a.ldy, rows_valid, n0, lane); break;
           }
         }
         __syncwarp();  // staging is reused by the next slab
@@ -635,10 +638,21 @@ linear_tf32_kernel(const __grid_constant__ LinearParams P) {
     if (P.epi_mode == 1) bulk_wait0();  // all bulk stores of this thread have been written
   } else if (warp == kMmaWarp) {
     // =========================== MMA issuer ===========================
-    if (lane == 0) {
+    // The whole warp runs the loop with warp-uniform values (so descriptors and barrier addresses live in
+    // uniform registers and need no per-instruction R2UR moves); one lane issues the tcgen05 instructions.
+    {
+      const bool leader = elect_one();
+      // The issuing thread is the serial resource of a K-deep tile (measured ~200 cycles per mbarrier probe,
+      // ~100 per MMA issue, ~65 per commit): it waits on ONE barrier per k-block (the A-side publisher has
+      // already waited for the weight stage), builds descriptors with one add each and commits once
+      // (the weight loader reuses a B stage when the MMA that read it has released the matching A stage).
       const uint32_t a_lbo = (uint32_t)(kTileM * 16), a_sbo = 128u;
       const uint32_t b_lbo = (uint32_t)(NT * 16), b_sbo = 128u;
-      uint32_t sa = 0, pa = 0, sb = 0, pb = 0;  // ring stage / phase of the A and B pipelines
+      const uint64_t da0 = umma_smem_desc(smem_u32(S.a_ring), a_lbo, a_sbo);
+      const uint64_t db0 = umma_smem_desc(smem_u32(S.b_ring), b_lbo, b_sbo);
+      const uint32_t a_stage16 = kAStageBytes >> 4, b_stage16 = b_stage_bytes >> 4;  // descriptor address units
+      const uint32_t a_ks16 = (2u * kTileM * 16u) >> 4, b_ks16 = (2u * (uint32_t)NT * 16u) >> 4;
+      uint32_t sa = 0, pa = 0, sb = 0;  // ring stage / phase of the A pipeline, stage of the B ring
       int it = 0;
       for (int tile = first_tile; tile < P.total_tiles; tile += tile_step, ++it) {
         const int buf = it & 1;
@@ -647,45 +661,75 @@ linear_tf32_kernel(const __grid_constant__ LinearParams P) {
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + (uint32_t)(buf * P.acc_stride);
         for (int kb = 0; kb < P.k_blocks; ++kb) {
-          mbar_wait(&S.fullA[sa], pa);
-          mbar_wait(&S.fullB[sb], pb);
+          if (kb == 1) TRACE(11, it);
+          mbar_wait(&S.fullA[sa], pa);   // A stage published AND (forwarder) its weight stage landed
           if (kb == 0) TRACE(5, it);
+          if (kb == 1) TRACE(13, it);
           tc_fence_after();
-          const uint32_t a_addr = smem_u32(S.a_ring) + sa * kAStageBytes;
-          const uint32_t b_addr = smem_u32(S.b_ring) + sb * b_stage_bytes;
+          const uint64_t da = da0 + (uint64_t)(sa * a_stage16);   // start-address field (14 bits) cannot carry out:
+          const uint64_t db = db0 + (uint64_t)(sb * b_stage16);   // shared memory is < 256 KB
 #pragma unroll
-          for (int ks = 0; ks < kBlockK / 8; ++ks) {  // one MMA consumes K = 8 tf32 = 2 chunks
-            uint64_t da = umma_smem_desc(a_addr + ks * 2 * (kTileM * 16), a_lbo, a_sbo);
-            uint64_t db = umma_smem_desc(b_addr + ks * 2 * (NT * 16), b_lbo, b_sbo);
-            umma_tf32(d_tmem, da, db, P.idesc, (kb | ks) ? 1u : 0u);
-          }
-          umma_commit(&S.emptyA[sa]);  // frees both ring slots once these MMAs have read them
-          umma_commit(&S.emptyB[sb]);
+          for (int ks = 0; ks < kBlockK / 8; ++ks)  // one MMA consumes K = 8 tf32 = 2 chunks
+            if (leader) umma_tf32(d_tmem, da + (uint64_t)(ks * a_ks16), db + (uint64_t)(ks * b_ks16), P.idesc, (kb | ks) ? 1u : 0u);
+          if (kb == 1) TRACE(14, it);
+          if (leader) umma_commit(&S.emptyA[sa]);  // frees the A stage and (for the loader) the B stage of this k-block
+          if (kb == 1) TRACE(15, it);
           if (++sa == SA) sa = 0, pa ^= 1u;
-          if (++sb == SB) sb = 0, pb ^= 1u;
+          if (++sb == SB) sb = 0;
         }
-        umma_commit(&S.accFull[buf]);  // accumulator complete -> epilogue
+        if (leader) umma_commit(&S.accFull[buf]);  // accumulator complete -> epilogue
+        __syncwarp();
         TRACE(6, it);
       }
     }
     __syncwarp();
-  } else {
+  } else if (warp == kLoadWarp) {
     // =========================== weight loader (bulk TMA) ===========================
-    if (lane == 0) {
-      uint32_t sb = 0, pb = 1;
+    {  // whole warp, warp-uniform values; one elected lane issues (see the MMA warp)
+      const bool leader = elect_one();
+      // B stage g % SB is free again when the MMAs of k-block g - SB have completed, which is exactly what
+      // emptyA[(g - SB) % SA] (phase ((g - SB) / SA) & 1) reports: no separate "empty" barrier for the weights.
+      uint32_t sb = 0;
+      uint32_t wa = 0, wpa = 0;   // A stage / phase of k-block g - SB
+      long long g = 0;
       for (int tile = first_tile; tile < P.total_tiles; tile += tile_step) {
         const int nt = tile % P.n_tiles;
         const float *wt = a.w_packed + (size_t)nt * (size_t)(a.K >> 2) * NT * 4;
-        for (int kb = 0; kb < P.k_blocks; ++kb) {
-          mbar_wait(&S.emptyB[sb], pb);
-          if (P.debug_skip & 2) {
-            mbar_arrive(&S.fullB[sb]);
-          } else {
-            mbar_arrive_expect_tx(&S.fullB[sb], b_stage_bytes);
-            bulk_copy_g2s(S.b_ring + sb * b_stage_bytes, wt + (size_t)kb * kChunks * NT * 4, b_stage_bytes, &S.fullB[sb]);
+        for (int kb = 0; kb < P.k_blocks; ++kb, ++g) {
+          if (g >= (long long)SB) {
+            mbar_wait(&S.emptyA[wa], wpa);
+            if (++wa == SA) wa = 0, wpa ^= 1u;
           }
-          if (++sb == SB) sb = 0, pb ^= 1u;
+          if (leader) {
+            if (P.debug_skip & 2) {
+              mbar_arrive(&S.fullB[sb]);
+            } else {
+              mbar_arrive_expect_tx(&S.fullB[sb], b_stage_bytes);
+              bulk_copy_g2s(S.b_ring + sb * b_stage_bytes, wt + (size_t)kb * kChunks * NT * 4, b_stage_bytes, &S.fullB[sb]);
+            }
+          }
+          __syncwarp();
+          if (++sb == SB) sb = 0;
         }
+      }
+    }
+    __syncwarp();
+  }
+
+  else {
+    // =========================== weight forwarder ===========================
+    // Waits (in order) for each weight stage to land and adds one arrival to that k-block's A-side full
+    // barrier, so the MMA thread -- the serial resource of a K-deep tile -- probes a single barrier per k-block.
+    // (B stage g lands only after MMA(g - SB) completed, i.e. after fullA's previous phase completed: the
+    // arrival can never be counted into the wrong phase.)
+    if (lane == 0) {
+      uint32_t sa = 0, sb = 0, pb = 0;
+      const long long total_kb = (long long)((P.total_tiles - first_tile + tile_step - 1) / tile_step) * P.k_blocks;
+      for (long long g = 0; g < total_kb; ++g) {
+        mbar_wait(&S.fullB[sb], pb);
+        mbar_arrive(&S.fullA[sa]);
+        if (++sa == SA) sa = 0;
+        if (++sb == SB) sb = 0, pb ^= 1u;
       }
     }
     __syncwarp();
@@ -733,7 +777,7 @@ pack_weight_kernel(const float *__restrict__ w, const float *__restrict__ bias, 
 }
 
 // Column slab handled by one epilogue warp at a time: minimise the columns on the critical path
-// (ceil(n_slabs / 4) * slab with four warps per lane quadrant), prefer wider slabs on ties.
+// (ceil(n_slabs / 3) * slab with three warps per lane quadrant), prefer wider slabs on ties.
 int pick_slab(int n_tile, int k_blocks) {
   // K-deep tiles reach the epilogue rarely: give the shared memory to the A ring instead of the staging
   if (k_blocks >= 12) return 16;
@@ -741,7 +785,7 @@ int pick_slab(int n_tile, int k_blocks) {
   int best = 16, best_cost = 1 << 30;
   for (int s = 16; s <= max_slab; s += 16) {
     if (n_tile % s) continue;
-    const int cost = ((n_tile / s + 3) / 4) * s;
+    const int cost = ((n_tile / s + kEpiPerQuad - 1) / kEpiPerQuad) * s;
     if (cost <= best_cost) best = s, best_cost = cost;
   }
   return best;

@@ -10,6 +10,18 @@ namespace sm100 {
 
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
+// One lane of a converged warp (elect.sync): ptxas keeps warp-uniform operands of the guarded single-thread
+// instructions (tcgen05.mma / commit / bulk copies) in uniform registers instead of moving them per lane.
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n\t.reg .pred P;\n\t"
+      "elect.sync _|P, 0xffffffff;\n\t"
+      "selp.u32 %0, 1, 0, P;\n\t}"
+      : "=r"(pred));
+  return pred != 0;
+}
+
 // ---------------------------------------------------------------- mbarrier
 __device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
@@ -63,6 +75,18 @@ __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
     const long long now = clock64();
     if (t0 == 0) t0 = now;
     else if (now - t0 > 20000000000LL) __trap();
+  }
+}
+
+// Same, for roles that usually wait long (the epilogue warps wait a whole K loop for their accumulator): back off
+// with nanosleep between probes so that the waiting warps do not compete for issue slots with the working ones.
+__device__ __forceinline__ void mbar_wait_relaxed(uint64_t *bar, uint32_t parity) {
+  if (mbar_try_wait(bar, parity)) return;
+  const long long t0 = clock64();
+  for (uint32_t spins = 1;; ++spins) {
+    __nanosleep(128);
+    if (mbar_try_wait(bar, parity)) return;
+    if ((spins & 4095u) == 0 && clock64() - t0 > 20000000000LL) __trap();
   }
 }
 

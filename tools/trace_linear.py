@@ -12,7 +12,7 @@ import torch  # noqa: E402
 from stf_b200 import _C, ops  # noqa: E402
 
 NAMES = ["issue:tile_start", "issue:all_kb_issued", "fin:first_landed", "fin:tile_published", "mma:accEmpty_ok",
-         "mma:first_full_ok", "mma:last_commit", "epi:accFull_ok", "epi:phase1_done", "epi:stores_done", "epi:ptrs_ready"]
+         "mma:first_full_ok", "mma:last_commit", "epi:accFull_ok", "epi:phase1_done", "epi:stores_done", "epi:ptrs_ready", "mma:kb1_begin", "mma:kb1_fullA_ok", "mma:kb1_fullB_ok", "mma:kb1_mma_issued", "mma:kb1_committed"]
 
 
 def main():
