@@ -49,7 +49,8 @@ constexpr int kBlockK = 16;           // floats per pipeline stage (2 MMAs of K=
 constexpr int kChunks = kBlockK / 4;  // 16-byte K chunks per stage
 constexpr int kMaxStagesA = 16;       // A ring depth is chosen per launch from the shared memory left over (>= 4);
                                       // stages - 1 k-blocks (8 KB each) are in flight per CTA: HBM latency x bandwidth / SM
-constexpr int kStagesB = 4;           // (3 when n_tile > 192: shared-memory budget)
+constexpr int kStagesB = 4;           // default B ring depth (3 when n_tile > 192, more for K-deep tiles)
+constexpr int kMaxStagesB = 8;
 constexpr int kProducerWarps = 4;       // cp.async issue warps
 constexpr int kFinalizeWarps = 8;       // TF32 rounding + LayerNorm statistics + proxy fence, 16 rows per warp
 constexpr int kEpiWarps = 12;         // three per TMEM lane quadrant, one column slab each at a time
@@ -113,6 +114,11 @@ struct LinearParams {
 // STF_B200_DEBUG_SKIP & 8: CTA 0 records clock64() at the key hand-offs of its first kTraceTiles tiles.
 constexpr int kTraceTiles = 24, kTraceEvents = 16;
 __device__ long long g_trace[kTraceEvents][kTraceTiles];
+__device__ long long g_ktrace[8][32];   // per-k-block events of CTA 0's third tile (STF_B200_DEBUG_SKIP & 8)
+#define KTRACE(ev, tile_it, kb)                                                                             \
+  do {                                                                                                      \
+    if ((P.debug_skip & 8) && blockIdx.x == 0 && (tile_it) == 2 && (kb) < 32) g_ktrace[ev][kb] = clock64(); \
+  } while (0)
 #define TRACE(ev, it)                                                                              \
   do {                                                                                             \
     if ((P.debug_skip & 8) && blockIdx.x == 0 && lane == 0 && (it) < kTraceTiles) g_trace[ev][it] = clock64(); \
@@ -294,7 +300,7 @@ __device__ __forceinline__ void store_slab_pixel_shuffle(const stf_linear_args &
 
 // ---------------------------------------------------------------------------- shared-memory map
 struct SmemMap {
-  uint64_t *fullA, *emptyA, *landA, *fullB, *emptyB, *accFull, *accEmpty;
+  uint64_t *fullA, *emptyA, *landA, *fullB, *accFull, *accEmpty;
   uint32_t *tmem_slot;
   float2 *stats;        // [kStatSlots][128] (mean, rstd) per tile in flight
   uint64_t *row_dst;    // [kEpiWarps][32] destination row pointers (0 = dropped row)
@@ -315,8 +321,7 @@ __device__ __forceinline__ SmemMap carve(uint8_t *smem, int n_tile, int stages_a
   m.emptyA = m.fullA + kMaxStagesA;
   m.landA = m.emptyA + kMaxStagesA;
   m.fullB = m.landA + kMaxStagesA;
-  m.emptyB = m.fullB + kStagesB;
-  m.accFull = m.emptyB + kStagesB;
+  m.accFull = m.fullB + kMaxStagesB;
   m.accEmpty = m.accFull + 2;
   m.tmem_slot = reinterpret_cast<uint32_t *>(m.accEmpty + 2);
   m.stats = reinterpret_cast<float2 *>(smem + 512);
@@ -354,7 +359,6 @@ linear_tf32_kernel(const __grid_constant__ LinearParams P) {
     }
     for (int s = 0; s < P.stages_b; ++s) {
       mbar_init(&S.fullB[s], 1);  // the loader's arrive.expect_tx (+ TMA transaction bytes)
-      mbar_init(&S.emptyB[s], 1);
     }
     for (int b = 0; b < 2; ++b) {
       mbar_init(&S.accFull[b], 1);
@@ -408,6 +412,7 @@ linear_tf32_kernel(const __grid_constant__ LinearParams P) {
           }
         }
         cp_async_arrive_noinc(&S.landA[i_stage]);  // arrives once this thread's copies above have landed
+        if (warp == 0 && lane == 0) KTRACE(0, tr_it, i_kb);
         if (++i_stage == SA) i_stage = 0, i_phase ^= 1u;
       }
       if (warp == 0) TRACE(1, tr_it);
@@ -420,14 +425,19 @@ linear_tf32_kernel(const __grid_constant__ LinearParams P) {
     if (P.lite) {
       // The producer of X already rounded it to TF32 (GELU / attention epilogues do) and there is no LayerNorm:
       // nothing to rewrite.  One thread turns "landed" into "visible to the tensor core" (proxy fence) and publishes.
-      if (fw == 0 && lane == 0) {
-        uint32_t st = 0, ph = 0;
+      // Each landed k-block needs a wait + proxy fence + arrive (~800 cycles of latency in one thread): the eight
+      // finalize warps take the k-blocks round-robin, one lane each, so eight of them are in flight.
+      if (lane == 0) {
         const long long total_kb = (long long)((P.total_tiles - first_tile + tile_step - 1) / tile_step) * P.k_blocks;
-        for (long long g = 0; g < total_kb; ++g) {
+        uint32_t st = (uint32_t)fw % SA, ph = ((uint32_t)fw / SA) & 1u;
+        for (long long g = fw; g < total_kb; g += kFinalizeWarps) {
           mbar_wait(&S.landA[st], ph);
+          KTRACE(1, (int)(g / P.k_blocks), (int)(g % P.k_blocks));
           fence_proxy_async_smem();
           mbar_arrive(&S.fullA[st]);
-          if (++st == SA) st = 0, ph ^= 1u;
+          KTRACE(2, (int)(g / P.k_blocks), (int)(g % P.k_blocks));
+          st += kFinalizeWarps;
+          while (st >= SA) st -= SA, ph ^= 1u;
         }
       }
     } else {
@@ -665,6 +675,7 @@ linear_tf32_kernel(const __grid_constant__ LinearParams P) {
           mbar_wait(&S.fullA[sa], pa);   // A stage published AND (forwarder) its weight stage landed
           if (kb == 0) TRACE(5, it);
           if (kb == 1) TRACE(13, it);
+          if (lane == 0) KTRACE(3, it, kb);
           tc_fence_after();
           const uint64_t da = da0 + (uint64_t)(sa * a_stage16);   // start-address field (14 bits) cannot carry out:
           const uint64_t db = db0 + (uint64_t)(sb * b_stage16);   // shared memory is < 256 KB
@@ -674,6 +685,11 @@ linear_tf32_kernel(const __grid_constant__ LinearParams P) {
           if (kb == 1) TRACE(14, it);
           if (leader) umma_commit(&S.emptyA[sa]);  // frees the A stage and (for the loader) the B stage of this k-block
           if (kb == 1) TRACE(15, it);
+          if (lane == 0) KTRACE(4, it, kb);
+          if ((P.debug_skip & 16) && it == 2) {  // experiment: expose the MMA completion latency
+            mbar_wait(&S.emptyA[sa], pa);
+            if (lane == 0) KTRACE(7, it, kb);
+          }
           if (++sa == SA) sa = 0, pa ^= 1u;
           if (++sb == SB) sb = 0;
         }
@@ -700,6 +716,7 @@ linear_tf32_kernel(const __grid_constant__ LinearParams P) {
             mbar_wait(&S.emptyA[wa], wpa);
             if (++wa == SA) wa = 0, wpa ^= 1u;
           }
+          if (lane == 0) KTRACE(6, (int)(g / P.k_blocks), kb);
           if (leader) {
             if (P.debug_skip & 2) {
               mbar_arrive(&S.fullB[sb]);
@@ -728,6 +745,7 @@ linear_tf32_kernel(const __grid_constant__ LinearParams P) {
       for (long long g = 0; g < total_kb; ++g) {
         mbar_wait(&S.fullB[sb], pb);
         mbar_arrive(&S.fullA[sa]);
+        KTRACE(5, (int)(g / P.k_blocks), (int)(g % P.k_blocks));
         if (++sa == SA) sa = 0;
         if (++sb == SB) sb = 0, pb ^= 1u;
       }
@@ -823,7 +841,8 @@ int launch_linear(const stf_linear_args *args, void *stream) {
   P.idesc = umma_idesc_tf32(kTileM, P.n_tile);
   P.has_ln = a.has_ln ? 1 : 0;
   P.lite = (!a.has_ln && a.x_is_tf32) ? 1 : 0;
-  P.stages_b = P.n_tile > 192 ? 3 : kStagesB;
+  // weight stages: a 1-D TMA load takes ~1300 cycles from L2; K-deep tiles need more of them in flight
+  P.stages_b = P.n_tile > 192 ? (P.k_blocks >= 12 ? 4 : 3) : (P.k_blocks >= 12 ? 6 : kStagesB);
   static const int debug_skip_env = [] {
     const char *e = getenv("STF_B200_DEBUG_SKIP");
     return e ? atoi(e) : 0;
@@ -914,6 +933,10 @@ extern "C" int stf_pack_linear(const float *weight, const float *bias, const flo
 extern "C" int stf_linear(const stf_linear_args *args, void *stream) { return launch_linear(args, stream); }
 
 // Profiling aid (not in the public header): copy the in-kernel trace of the last traced launch to the host.
+extern "C" int stf_debug_read_ktrace(long long *out) {
+  cudaError_t e = cudaMemcpyFromSymbol(out, g_ktrace, sizeof(long long) * 8 * 32);
+  return e == cudaSuccess ? 0 : (int)e;
+}
 extern "C" int stf_debug_read_trace(long long *out, int max_entries) {
   long long tmp[kTraceEvents * kTraceTiles];
   cudaError_t e = cudaMemcpyFromSymbol(tmp, g_trace, sizeof(tmp));

@@ -36,15 +36,15 @@ __device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t *bar, uint32_t by
   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes)
                : "memory");
 }
-// One probe with a hardware suspend-time hint (ns): the warp sleeps inside the instruction instead of spinning.
+// One probe (the hardware suspends the warp for a bounded, implementation-defined time if the phase is pending).
 __device__ __forceinline__ bool mbar_try_wait(uint64_t *bar, uint32_t parity) {
   uint32_t ok;
   asm volatile(
       "{\n\t.reg .pred p;\n\t"
-      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
       "selp.u32 %0, 1, 0, p;\n\t}"
       : "=r"(ok)
-      : "r"(smem_u32(bar)), "r"(parity), "r"(200000u)
+      : "r"(smem_u32(bar)), "r"(parity)
       : "memory");
   return ok != 0;
 }
@@ -60,7 +60,7 @@ __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
         "{\n\t.reg .pred p;\n\t.reg .u32 n;\n\t"
         "mov.u32 n, 4096;\n\t"
         "W_%=:\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
         "@p bra D_%=;\n\t"
         "sub.u32 n, n, 1;\n\t"
         "setp.ne.u32 p, n, 0;\n\t"
@@ -69,7 +69,7 @@ __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
         "D_%=:\n\t"
         "selp.u32 %0, 1, 0, p;\n\t}"
         : "=r"(ok)
-        : "r"(addr), "r"(parity), "r"(200000u)
+        : "r"(addr), "r"(parity)
         : "memory");
     if (ok) return;
     const long long now = clock64();

@@ -48,6 +48,14 @@ def main():
     print(f"stage {st} op {op}: cycles relative to the first tile's start (CTA 0), tiles 0..{n_t - 1}")
     for e, name in enumerate(NAMES):
         print(f"{name:22s}", " ".join(f"{(v - t0):7d}" for v in t[e][:12]))
+    kb = (ctypes.c_longlong * (8 * 32))()
+    L.stf_debug_read_ktrace.argtypes = [ctypes.POINTER(ctypes.c_longlong)]
+    L.stf_debug_read_ktrace(kb)
+    kn = ["issue:copies_issued", "pub:landed_ok", "pub:arrived", "mma:full_ok", "mma:committed", "fwd:B_arrived", "load:B_issue", "mma:completed(exp)"]
+    k0 = min(v for v in kb[:32] if v > 0) if any(v > 0 for v in kb[:32]) else 0
+    print("per-k-block events of the third tile (cycles from its first issue):")
+    for e, name in enumerate(kn):
+        print(f"{name:22s}", " ".join(f"{(kb[e * 32 + i] - k0):6d}" for i in range(14)))
     per_tile = (t[8][n_t - 1] - t[8][4]) / (n_t - 1 - 4)
     print(f"steady-state cycles per tile (store_issued deltas): {per_tile:.0f}")
 
