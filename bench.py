@@ -39,6 +39,20 @@ def load_peaks():
     return 6650.0, "fallback (B200_PROFILING.md)"
 
 
+def measured_traffic(kernel, batch):
+    """DRAM bytes per launch of `kernel` (dram__bytes_read.sum + dram__bytes_write.sum) from the committed ncu
+    capture of one step (profiles/r1_traffic_linear_step.json, batch 8), scaled linearly to this batch."""
+    p = os.path.join(ROOT, "profiles", "r1_traffic_linear_step.json")
+    if not os.path.exists(p):
+        return None, None
+    d = json.load(open(p))
+    if kernel not in d:
+        return None, None
+    k = d[kernel]
+    per_launch = (k["dram_read_bytes"] + k["dram_write_bytes"]) / k["launches"] * batch / k["batch"]
+    return per_launch, f"ncu capture at batch {k['batch']} scaled x{batch / k['batch']:g} (profiles/r1_traffic_linear_step.json)"
+
+
 class ClockSampler:
     """nvidia-smi clocks / throttle reasons DURING the timed region."""
     Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
@@ -230,8 +244,10 @@ def run_ours(args, rank, world, local_rank):
         if fam:
             top = max(fam.values(), key=lambda f: f["ms"])
             achieved = top["bytes"] / (top["ms"] * 1e-3) / 1e9
+            traffic, traffic_src = measured_traffic(top["name"], B)
             roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                        "traffic": None, "kernel": top["name"], "launches_per_step": top["launches"],
+                        "traffic": traffic, "traffic_source": traffic_src, "kernel": top["name"],
+                        "launches_per_step": top["launches"],
                         "avg_launch_us": top["ms"] * 1e3 / top["launches"],
                         "algorithmic_bytes_per_launch": top["bytes"] / top["launches"], "peak_source": peak_src,
                         "step_share": {k: round(v["ms"], 3) for k, v in fam.items()},

@@ -192,3 +192,34 @@ def test_training_mode_raises_instead_of_falling_back():
     blk.H, blk.W = 4, 4
     with pytest.raises(NotImplementedError):
         blk(torch.randn(1, 16, 48, device="cuda", requires_grad=True), None)
+
+
+def test_linear_tf32_fast_path_matches_rounding_path():
+    """x_is_tf32: inputs that are TF32-exact skip the in-kernel rounding pass -- same result either way."""
+    from stf_b200 import _C, ops
+    g = torch.Generator().manual_seed(5)
+    M, K, N = 1000, 768, 192
+    x = rna_tf32(torch.randn(M, K, generator=g)).cuda()
+    w = (torch.randn(N, K, generator=g) / K ** 0.5).cuda()
+    b = torch.randn(N, generator=g).cuda()
+    res = torch.randn(M, N, generator=g).cuda()
+    lin = ops.PackedLinear(w, b)
+    slow = ops.linear(x, lin, epilogue=_C.EPI_RESIDUAL, residual=res)
+    fast = ops.linear(x, lin, epilogue=_C.EPI_RESIDUAL, residual=res, x_is_tf32=True)
+    assert torch.equal(slow, fast)
+    h = ops.linear(x, ops.PackedLinear(w, b), epilogue=_C.EPI_GELU)
+    assert torch.equal(h, rna_tf32(h))                     # the GELU epilogue stores TF32-exact values
+
+
+def test_linear_argument_errors():
+    from stf_b200 import _C, ops
+    x = torch.randn(64, 48, device="cuda")
+    lin = ops.PackedLinear(torch.randn(48, 48, device="cuda"))
+    with pytest.raises(ValueError):     # residual epilogue without residual
+        ops.linear(x, lin, epilogue=_C.EPI_RESIDUAL)
+    with pytest.raises(ValueError):     # window geometry that does not match M
+        ops.linear(x, lin, rows=_C.ROWS_WINDOW, geom=(1, 4, 4, 4, 0))
+    with pytest.raises(ValueError):     # N not a multiple of 16
+        ops.PackedLinear(torch.randn(40, 48, device="cuda"))
+    with pytest.raises(ValueError):     # LayerNorm width mismatch
+        ops.PackedLinear(torch.randn(48, 48, device="cuda"), None, (torch.ones(32, device="cuda"), torch.zeros(32, device="cuda"), 1e-5))
