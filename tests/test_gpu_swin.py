@@ -223,3 +223,38 @@ def test_linear_argument_errors():
         ops.PackedLinear(torch.randn(40, 48, device="cuda"))
     with pytest.raises(ValueError):     # LayerNorm width mismatch
         ops.PackedLinear(torch.randn(48, 48, device="cuda"), None, (torch.ones(32, device="cuda"), torch.zeros(32, device="cuda"), 1e-5))
+
+
+@pytest.mark.parametrize("M,N,K", [(1, 48, 48), (130, 144, 48), (257, 48, 192), (511, 384, 96)])
+def test_linear_and_attention_write_only_their_outputs(M, N, K):
+    """Guard bands (compute-sanitizer is not available on the GPU pool): ragged M, outputs placed inside a larger
+    sentinel-filled buffer; nothing outside [0, M) x [0, N) may change."""
+    from stf_b200 import ops
+    g = torch.Generator().manual_seed(M)
+    x = torch.randn(M, K, generator=g).cuda()
+    lin = ops.PackedLinear((torch.randn(N, K, generator=g) / K ** 0.5).cuda(), torch.randn(N, generator=g).cuda())
+    guard = 300
+    big = torch.full((guard + M + guard, N), 7.25, device="cuda")
+    out = big[guard:guard + M]
+    ops.linear(x, lin, out=out)
+    torch.cuda.synchronize()
+    assert bool((big[:guard] == 7.25).all()) and bool((big[guard + M:] == 7.25).all())
+    assert torch.isfinite(out).all()
+
+
+def test_attention_guard_bands():
+    from stf_b200 import ops
+    C, heads, ws = 48, 3, 4
+    for windows in (1, 7, 9):                    # not a multiple of the windows-per-CTA group
+        rows = windows * ws * ws
+        qkv = torch.randn(rows, 3 * C, device="cuda")
+        table = torch.randn(49, heads, device="cuda")
+        o = ops.window_attention_core(qkv, table, windows, C, heads, ws, 0)
+        ref_rows = o.shape[0]
+        assert ref_rows == rows and torch.isfinite(o).all()
+        # same call with the rows embedded in a larger qkv buffer must give the same result (no out-of-range reads
+        # influence the output)
+        big = torch.full((rows + 64, 3 * C), float("nan"), device="cuda")
+        big[:rows] = qkv
+        o2 = ops.window_attention_core(big[:rows], table, windows, C, heads, ws, 0)
+        assert torch.equal(o, o2)
