@@ -261,9 +261,10 @@ def run_ours(args, rank, world, local_rank):
         print(json.dumps({
             "metric": METRIC, "value": value, "unit": "Mpixel/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms_dev / args.steps, "higher_is_better": True, "scaling": "weak",
-            "vs_baseline": None, "dtype": "tf32", "data": "synthetic",
+            "vs_baseline": None, "dtype": "f32 (3xTF32 split on tcgen05, fp32 accumulate)" if ops.precision() == "fp32" else "tf32",
+            "data": "synthetic",
             "config": {"workload": f"STF compress+decompress, batch {B} x 768x512 RGB per GPU per step (BASELINE config 3)",
-                       "batch_per_gpu": B, "image": [H, W], "weights": "synthetic (stf_b200/synth.py seed 0)",
+                       "batch_per_gpu": B, "image": [H, W], "gemm_precision": ops.precision(), "weights": "synthetic (stf_b200/synth.py seed 0)",
                        "l2": "inputs differ every step; per-step activations >> 126 MB L2",
                        "bpp": nbytes * 8 / (B * H * W * args.steps)},
             "e2e": {"value": e2e, "unit": "Mpixel/s", "h2d_bytes_per_step": B * 3 * H * W * 4,
@@ -282,6 +283,8 @@ def main():
     ap.add_argument("--batch", type=int, default=32, help="images per GPU per step")
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--precision", default=None, choices=["fp32", "tf32"],
+                    help="GEMM arithmetic: fp32 = 3xTF32 split (default, parity with the reference's fp32 matmuls), tf32 = single pass")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -295,6 +298,8 @@ def main():
                "--master-addr", "127.0.0.1", "--master-port", os.environ.get("MASTER_PORT", "29517"), __file__] + sys.argv[1:]
         os.execv(sys.executable, cmd)
     args.warmup = max(args.warmup, 3)
+    if args.precision:
+        os.environ["STF_B200_PRECISION"] = args.precision
     run_ours(args, rank, world, local_rank)
 
 

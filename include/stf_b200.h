@@ -126,10 +126,19 @@ int stf_entropy_bottleneck(const float *z, const float *params, float *z_hat, fl
  *   s[N] = sum_k tf32(gamma_k W_nk)    t[N] = sum_k beta_k W_nk + bias_n    b[N] = bias_n
  * so that LN(x).W^T + bias = rstd * (x.(gamma o W)^T - mean * s) + t is evaluated in the GEMM epilogue.
  * All four source pointers are device pointers; bias and (ln_gamma, ln_beta) may be NULL. */
+/* Arithmetic of the tensor-core GEMMs.  The reference's matmuls are true fp32 (torch's allow_tf32 is off for
+ * matmul), so STF_PREC_FP32 is the parity mode: every operand is split into two TF32 halves x = hi + lo
+ * (lo = tf32(x - hi), |x - hi - lo| <= 2^-22 |x|) and the tensor core accumulates hi.hi + lo.hi + hi.lo in
+ * fp32 ("3xTF32"); the dropped lo.lo term is below fp32 round-off.  STF_PREC_TF32 is the single-pass mode. */
+enum {
+  STF_PREC_TF32 = 0, /* operands rounded to TF32 (10-bit mantissa), one MMA per k-step: ~1e-3 relative per GEMM */
+  STF_PREC_FP32 = 1  /* 3xTF32 split: fp32-grade results (~1e-6 relative), three MMAs per k-step            */
+};
 int stf_linear_n_tile(int N);
-int64_t stf_packed_linear_floats(int N, int K);
+/* Packed size in floats: (1 + precision) * N*K + 3*N  (STF_PREC_FP32 stores a hi and a lo image per k-block). */
+int64_t stf_packed_linear_floats(int N, int K, int precision);
 int stf_pack_linear(const float *weight, const float *bias, const float *ln_gamma, const float *ln_beta,
-                    float *packed, int N, int K, void *stream);
+                    float *packed, int N, int K, int precision, void *stream);
 
 /* Row gather applied to X before the GEMM (what each of the 128 rows of an M-tile reads). */
 enum {
@@ -177,6 +186,7 @@ typedef struct {
   int batch, H, W;
   int window;             /* window size ws (WINDOW) */
   int shift;              /* cyclic shift (0 or ws/2) */
+  int precision;          /* STF_PREC_*; must match the precision w_packed was packed with */
 } stf_linear_args;
 
 /* Fused linear layer on tcgen05 tensor cores.  Replaces, depending on the arguments:
@@ -193,10 +203,12 @@ int stf_linear(const stf_linear_args *args, void *stream);
  * computed analytically from the window position when shift > 0: windows are numbered
  * image-major then row-major over the (Hp/ws, Wp/ws) grid.  Independently, `mask` may point to an
  * explicit additive (mask_windows, N, N) fp32 tensor applied as mask[window % mask_windows]
- * (the WindowAttention.forward(x, mask) signature, stf.py:108-110); NULL = none. */
+ * (the WindowAttention.forward(x, mask) signature, stf.py:108-110); NULL = none.
+ * tf32_out != 0: the output is stored rounded to TF32 (for a STF_PREC_TF32 proj GEMM called with
+ * x_is_tf32); 0: full fp32 output. */
 int stf_window_attention(const float *qkv, float *out, const float *bias_table, const float *mask,
                          int mask_windows, int64_t num_windows, int C, int heads, int ws, int shift,
-                         int Hp, int Wp, void *stream);
+                         int Hp, int Wp, int tf32_out, void *stream);
 
 /* ------------------------------------------------------------------------------------------
  * Host-side rANS codec (CPU; replaces compressai.ans, cpp_exts/rans/rans_interface.cpp:99-350,

@@ -19,6 +19,7 @@ STF_EB_PARAMS = 60
 STF_EB_MEDIAN_SLOT = 58
 ROWS_DENSE, ROWS_WINDOW, ROWS_MERGE = 0, 1, 2
 EPI_STORE, EPI_QKV, EPI_GELU, EPI_RESIDUAL, EPI_WINDOW_RESIDUAL, EPI_PIXEL_SHUFFLE = range(6)
+PREC_TF32, PREC_FP32 = 0, 1
 
 _ERRORS = {-1: "invalid argument", -2: "unsupported shape", -3: "pointer not 16-byte aligned",
            -4: "invalid table", -5: "output buffer too small", -6: "corrupt bitstream"}
@@ -33,7 +34,7 @@ class LinearArgs(ctypes.Structure):
         ("y", c_vp), ("ldy", c_int),
         ("rows", c_int), ("has_ln", c_int), ("x_is_tf32", c_int), ("ln_eps", c_f32),
         ("epilogue", c_int), ("residual", c_vp), ("q_cols", c_int), ("q_scale", c_f32),
-        ("batch", c_int), ("H", c_int), ("W", c_int), ("window", c_int), ("shift", c_int),
+        ("batch", c_int), ("H", c_int), ("W", c_int), ("window", c_int), ("shift", c_int), ("precision", c_int),
     ]
 
 
@@ -50,10 +51,10 @@ SIGNATURES = {
     "stf_gaussian_likelihood": (c_int, [c_vp, c_i64, c_vp, c_vp, c_vp, c_vp, c_int, c_int, c_i64, c_f32, c_f32, c_int, c_vp]),
     "stf_entropy_bottleneck": (c_int, [c_vp, c_vp, c_vp, c_vp, c_vp, c_int, c_int, c_i64, c_f32, c_int, c_vp]),
     "stf_linear_n_tile": (c_int, [c_int]),
-    "stf_packed_linear_floats": (c_i64, [c_int, c_int]),
-    "stf_pack_linear": (c_int, [c_vp, c_vp, c_vp, c_vp, c_vp, c_int, c_int, c_vp]),
+    "stf_packed_linear_floats": (c_i64, [c_int, c_int, c_int]),
+    "stf_pack_linear": (c_int, [c_vp, c_vp, c_vp, c_vp, c_vp, c_int, c_int, c_int, c_vp]),
     "stf_linear": (c_int, [ctypes.POINTER(LinearArgs), c_vp]),
-    "stf_window_attention": (c_int, [c_vp, c_vp, c_vp, c_vp, c_int, c_i64, c_int, c_int, c_int, c_int, c_int, c_int, c_vp]),
+    "stf_window_attention": (c_int, [c_vp, c_vp, c_vp, c_vp, c_int, c_i64, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_vp]),
     "stf_rans_table_create": (c_vp, [_i32p, c_int, c_int, _i32p, _i32p]),
     "stf_rans_table_destroy": (None, [c_vp]),
     "stf_rans_encode_bound": (c_i64, [c_i64]),

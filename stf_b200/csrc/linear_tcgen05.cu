@@ -99,6 +99,7 @@ struct LinearParams {
   int acc_stride;  // TMEM columns between the two accumulators
   uint32_t idesc;
   int has_ln;
+  int precise;     // 3xTF32: operands split into hi + lo TF32 halves, D = Ahi.Bhi + Alo.Bhi + Ahi.Blo (fp32-grade)
   int lite;        // A operand needs no finalize pass (no LayerNorm, X already TF32-exact): one thread fences + publishes
   int stages_a, stages_b;
   int epi_mode;    // 0: staged slab -> coalesced 16-byte stores by the whole warp; 1: one bulk (TMA) store per row
@@ -314,7 +315,7 @@ struct SmemMap {
 constexpr int kStatSlots = 8;
 constexpr size_t kSmemHeader = 512 + kStatSlots * 128 * 8 + 2 * kEpiWarps * 32 * 8;  // barriers + stats + row pointers
 
-__device__ __forceinline__ SmemMap carve(uint8_t *smem, int n_tile, int stages_a, int stages_b, int slab) {
+__device__ __forceinline__ SmemMap carve(uint8_t *smem, int n_tile, int stages_a, int stages_b, int slab, int planes) {
   SmemMap m;
   uint64_t *bars = reinterpret_cast<uint64_t *>(smem);
   m.fullA = bars;
@@ -328,14 +329,15 @@ __device__ __forceinline__ SmemMap carve(uint8_t *smem, int n_tile, int stages_a
   m.row_dst = reinterpret_cast<uint64_t *>(smem + 512 + kStatSlots * 128 * 8);
   m.row_res = m.row_dst + kEpiWarps * 32;
   m.a_ring = smem + kSmemHeader;
-  m.b_ring = m.a_ring + stages_a * kAStageBytes;
-  m.stage = m.b_ring + (size_t)stages_b * kChunks * n_tile * 16;
+  m.b_ring = m.a_ring + (size_t)stages_a * planes * kAStageBytes;
+  m.stage = m.b_ring + (size_t)stages_b * planes * kChunks * n_tile * 16;
   m.aux = reinterpret_cast<float *>(m.stage + (size_t)kEpiWarps * 32 * (slab + kStagePad) * 4);
   return m;
 }
 
-size_t linear_smem_bytes(int n_tile, int slab, int stages_a, int stages_b, int N) {
-  return (size_t)3 * N * 4 + kSmemHeader + (size_t)stages_a * kAStageBytes + (size_t)stages_b * kChunks * n_tile * 16 +
+size_t linear_smem_bytes(int n_tile, int slab, int stages_a, int stages_b, int N, int planes) {
+  return (size_t)3 * N * 4 + kSmemHeader + (size_t)stages_a * planes * kAStageBytes +
+         (size_t)stages_b * planes * kChunks * n_tile * 16 +
          (size_t)kEpiWarps * 32 * (slab + kStagePad) * 4;
 }
 
@@ -346,10 +348,13 @@ linear_tf32_kernel(const __grid_constant__ LinearParams P) {
   const stf_linear_args &a = P.a;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int NT = P.n_tile;
-  const SmemMap S = carve(smem, NT, P.stages_a, P.stages_b, P.slab);
+  const int planes = P.precise ? 2 : 1;  // hi (+ lo) operand images per stage
+  const SmemMap S = carve(smem, NT, P.stages_a, P.stages_b, P.slab, planes);
+  const uint32_t a_stage_bytes = (uint32_t)planes * kAStageBytes;
   for (int i = threadIdx.x; i < 3 * a.N; i += kThreads) S.aux[i] = __ldg(P.aux + i);  // visible after the __syncthreads below
   const uint32_t SA = (uint32_t)P.stages_a, SB = (uint32_t)P.stages_b;
-  const uint32_t b_stage_bytes = (uint32_t)(kChunks * NT * 16);
+  const uint32_t b_plane_bytes = (uint32_t)(kChunks * NT * 16);
+  const uint32_t b_stage_bytes = (uint32_t)planes * b_plane_bytes;
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < P.stages_a; ++s) {
@@ -398,7 +403,7 @@ linear_tf32_kernel(const __grid_constant__ LinearParams P) {
       }
       for (int i_kb = 0; i_kb < P.k_blocks; ++i_kb) {
         mbar_wait(&S.emptyA[i_stage], i_phase);
-        const uint32_t dst = a_base + i_stage * kAStageBytes;
+        const uint32_t dst = a_base + i_stage * a_stage_bytes;
         if (P.debug_skip & 1) {
         } else if (!merge) {
 #pragma unroll
@@ -452,7 +457,7 @@ linear_tf32_kernel(const __grid_constant__ LinearParams P) {
       for (int f_kb = 0; f_kb < P.k_blocks; ++f_kb) {
         mbar_wait(&S.landA[f_stage], f_phase);
         if (fw == 0 && f_kb == 0) TRACE(2, f_it);
-        const uint32_t addr = a_base + f_stage * kAStageBytes;
+        const uint32_t addr = a_base + f_stage * a_stage_bytes;
 #pragma unroll
         for (int i = 0; i < 2; ++i) {
           float4 v = lds128(addr + i * 128);
@@ -465,7 +470,11 @@ linear_tf32_kernel(const __grid_constant__ LinearParams P) {
             sum[i] += (dx + dy) + (dz + dw);
             sq[i] += (dx * dx + dy * dy) + (dz * dz + dw * dw);
           }
-          sts128(addr + i * 128, make_float4(round_tf32(v.x), round_tf32(v.y), round_tf32(v.z), round_tf32(v.w)));
+          const float4 hi = make_float4(round_tf32(v.x), round_tf32(v.y), round_tf32(v.z), round_tf32(v.w));
+          sts128(addr + i * 128, hi);
+          if (P.precise)  // residual of the TF32 rounding, itself TF32: x = hi + lo to ~2^-22 relative
+            sts128(addr + kAStageBytes + i * 128, make_float4(round_tf32(v.x - hi.x), round_tf32(v.y - hi.y),
+                                                            round_tf32(v.z - hi.z), round_tf32(v.w - hi.w)));
         }
         if (P.has_ln && f_kb == P.k_blocks - 1) {  // row statistics for the epilogue of this tile
 #pragma unroll
@@ -601,7 +610,10 @@ linear_tf32_kernel(const __grid_constant__ LinearParams P) {
             }
           } else if (a.epilogue == STF_EPI_GELU) {
 #pragma unroll
-            for (int j = 0; j < 16; ++j) acc[j] = round_tf32(gelu_erf(acc[j]));  // fc2 (the only consumer) reads it as TF32
+            for (int j = 0; j < 16; ++j) {
+              const float ge = gelu_erf(acc[j]);
+              acc[j] = P.precise ? ge : round_tf32(ge);  // TF32 mode: fc2 (the only consumer) reads it as TF32
+            }
           }
           if (res) {
 #pragma unroll
@@ -660,7 +672,8 @@ linear_tf32_kernel(const __grid_constant__ LinearParams P) {
       const uint32_t b_lbo = (uint32_t)(NT * 16), b_sbo = 128u;
       const uint64_t da0 = umma_smem_desc(smem_u32(S.a_ring), a_lbo, a_sbo);
       const uint64_t db0 = umma_smem_desc(smem_u32(S.b_ring), b_lbo, b_sbo);
-      const uint32_t a_stage16 = kAStageBytes >> 4, b_stage16 = b_stage_bytes >> 4;  // descriptor address units
+      const uint32_t a_stage16 = a_stage_bytes >> 4, b_stage16 = b_stage_bytes >> 4;  // descriptor address units
+      const uint32_t a_lo16 = kAStageBytes >> 4, b_lo16 = b_plane_bytes >> 4;         // hi -> lo plane of a stage
       const uint32_t a_ks16 = (2u * kTileM * 16u) >> 4, b_ks16 = (2u * (uint32_t)NT * 16u) >> 4;
       uint32_t sa = 0, pa = 0, sb = 0;  // ring stage / phase of the A pipeline, stage of the B ring
       int it = 0;
@@ -681,7 +694,14 @@ linear_tf32_kernel(const __grid_constant__ LinearParams P) {
           const uint64_t db = db0 + (uint64_t)(sb * b_stage16);   // shared memory is < 256 KB
 #pragma unroll
           for (int ks = 0; ks < kBlockK / 8; ++ks)  // one MMA consumes K = 8 tf32 = 2 chunks
-            if (leader) umma_tf32(d_tmem, da + (uint64_t)(ks * a_ks16), db + (uint64_t)(ks * b_ks16), P.idesc, (kb | ks) ? 1u : 0u);
+            if (leader) {
+              const uint64_t dak = da + (uint64_t)(ks * a_ks16), dbk = db + (uint64_t)(ks * b_ks16);
+              umma_tf32(d_tmem, dak, dbk, P.idesc, (kb | ks) ? 1u : 0u);
+              if (P.precise) {  // 3xTF32 error compensation (the lo.lo term is below fp32 round-off)
+                umma_tf32(d_tmem, dak + a_lo16, dbk, P.idesc, 1u);
+                umma_tf32(d_tmem, dak, dbk + b_lo16, P.idesc, 1u);
+              }
+            }
           if (kb == 1) TRACE(14, it);
           if (leader) umma_commit(&S.emptyA[sa]);  // frees the A stage and (for the loader) the B stage of this k-block
           if (kb == 1) TRACE(15, it);
@@ -710,7 +730,7 @@ linear_tf32_kernel(const __grid_constant__ LinearParams P) {
       long long g = 0;
       for (int tile = first_tile; tile < P.total_tiles; tile += tile_step) {
         const int nt = tile % P.n_tiles;
-        const float *wt = a.w_packed + (size_t)nt * (size_t)(a.K >> 2) * NT * 4;
+        const float *wt = a.w_packed + (size_t)nt * (size_t)(a.K >> 2) * NT * 4 * planes;
         for (int kb = 0; kb < P.k_blocks; ++kb, ++g) {
           if (g >= (long long)SB) {
             mbar_wait(&S.emptyA[wa], wpa);
@@ -722,7 +742,7 @@ linear_tf32_kernel(const __grid_constant__ LinearParams P) {
               mbar_arrive(&S.fullB[sb]);
             } else {
               mbar_arrive_expect_tx(&S.fullB[sb], b_stage_bytes);
-              bulk_copy_g2s(S.b_ring + sb * b_stage_bytes, wt + (size_t)kb * kChunks * NT * 4, b_stage_bytes, &S.fullB[sb]);
+              bulk_copy_g2s(S.b_ring + sb * b_stage_bytes, wt + (size_t)kb * kChunks * NT * 4 * planes, b_stage_bytes, &S.fullB[sb]);
             }
           }
           __syncwarp();
@@ -765,16 +785,25 @@ linear_tf32_kernel(const __grid_constant__ LinearParams P) {
 // two LayerNorm-folding sums.
 __global__ void __launch_bounds__(128)
 pack_weight_kernel(const float *__restrict__ w, const float *__restrict__ bias, const float *__restrict__ gamma,
-                   const float *__restrict__ beta, float *__restrict__ packed, int N, int K, int NT) {
+                   const float *__restrict__ beta, float *__restrict__ packed, int N, int K, int NT, int planes) {
   const int n = blockIdx.x;
   const int t = n / NT, n_in = n - t * NT;
-  float *tile = packed + (size_t)t * (size_t)(K >> 2) * NT * 4;
+  float *tile = packed + (size_t)t * (size_t)(K >> 2) * NT * 4 * planes;
+  const size_t plane = (size_t)kChunks * NT * 4;  // floats of one k-block image; a k-block stores hi then lo
   float s = 0.f, tb = 0.f;
   for (int k = threadIdx.x; k < K; k += blockDim.x) {
     const float wv = w[(size_t)n * K + k];
-    const float wg = to_tf32(gamma ? wv * gamma[k] : wv);
-    tile[((size_t)(k >> 2) * NT + n_in) * 4 + (k & 3)] = wg;
-    s += wg;
+    const float wf = gamma ? wv * gamma[k] : wv;
+    const float wg = to_tf32(wf);
+    const size_t at = (size_t)(k / kBlockK) * plane * planes + ((size_t)((k % kBlockK) >> 2) * NT + n_in) * 4 + (k & 3);
+    tile[at] = wg;
+    if (planes == 2) {
+      const float lo = to_tf32(wf - wg);
+      tile[at + plane] = lo;
+      s += wg + lo;
+    } else {
+      s += wg;
+    }
     if (beta) tb = fmaf(beta[k], wv, tb);
   }
   __shared__ float red[2][4];
@@ -786,7 +815,7 @@ pack_weight_kernel(const float *__restrict__ w, const float *__restrict__ bias, 
   if ((threadIdx.x & 31) == 0) red[0][threadIdx.x >> 5] = s, red[1][threadIdx.x >> 5] = tb;
   __syncthreads();
   if (threadIdx.x == 0) {
-    float *aux = packed + (size_t)N * K;
+    float *aux = packed + (size_t)N * K * planes;
     const float bv = bias ? bias[n] : 0.f;
     aux[n] = gamma ? (red[0][0] + red[0][1]) + (red[0][2] + red[0][3]) : 0.f;  // s: only used when LN is folded
     aux[N + n] = ((red[1][0] + red[1][1]) + (red[1][2] + red[1][3])) + bv;       // t = beta.W^T + bias
@@ -825,7 +854,10 @@ int launch_linear(const stf_linear_args *args, void *stream) {
 
   LinearParams P;
   P.a = a;
-  P.aux = a.w_packed + (size_t)a.N * a.K;
+  if (a.precision != STF_PREC_TF32 && a.precision != STF_PREC_FP32) return STF_E_ARG;
+  P.precise = a.precision == STF_PREC_FP32 ? 1 : 0;
+  const int planes = P.precise ? 2 : 1;
+  P.aux = a.w_packed + (size_t)a.N * a.K * (P.precise ? 2 : 1);
   P.n_tile = stf_linear_n_tile(a.N);
   if (P.n_tile <= 0) return STF_E_SHAPE;
   P.n_tiles = a.N / P.n_tile;
@@ -835,14 +867,16 @@ int launch_linear(const stf_linear_args *args, void *stream) {
   P.total_tiles = (int)total;
   P.k_blocks = a.K / kBlockK;
   P.slab = pick_slab(P.n_tile, P.k_blocks);
+  if (P.precise && P.n_tile > 128) P.slab = 16;  // two operand planes per stage: the rings need the shared memory
   P.tmem_cols = 32;
   while (P.tmem_cols < 2 * P.n_tile) P.tmem_cols <<= 1;
   P.acc_stride = P.tmem_cols / 2;
   P.idesc = umma_idesc_tf32(kTileM, P.n_tile);
   P.has_ln = a.has_ln ? 1 : 0;
-  P.lite = (!a.has_ln && a.x_is_tf32) ? 1 : 0;
+  P.lite = (!a.has_ln && a.x_is_tf32 && !P.precise) ? 1 : 0;
   // weight stages: a 1-D TMA load takes ~1300 cycles from L2; K-deep tiles need more of them in flight
   P.stages_b = P.n_tile > 192 ? (P.k_blocks >= 12 ? 4 : 3) : (P.k_blocks >= 12 ? 6 : kStagesB);
+  if (P.precise) P.stages_b = P.n_tile > 192 ? 2 : P.n_tile > 128 ? 3 : 4;  // stages are twice as large (hi + lo)
   static const int debug_skip_env = [] {
     const char *e = getenv("STF_B200_DEBUG_SKIP");
     return e ? atoi(e) : 0;
@@ -855,10 +889,10 @@ int launch_linear(const stf_linear_args *args, void *stream) {
   P.epi_mode = epi_mode_env;
   P.fin_group = (P.k_blocks % 4 == 0) ? 4 : (P.k_blocks % 3 == 0) ? 3 : (P.k_blocks % 2 == 0) ? 2 : 1;
   {  // all the shared memory the B ring and the epilogue staging leave over goes to the A ring
-    const size_t fixed = linear_smem_bytes(P.n_tile, P.slab, 0, P.stages_b, a.N);
+    const size_t fixed = linear_smem_bytes(P.n_tile, P.slab, 0, P.stages_b, a.N, planes);
     const size_t budget = 227 * 1024;
-    if (fixed + 4 * kAStageBytes > budget) return STF_E_SHAPE;
-    int sa = (int)((budget - fixed) / kAStageBytes);
+    if (fixed + 4 * planes * kAStageBytes > budget) return STF_E_SHAPE;
+    int sa = (int)((budget - fixed) / (planes * kAStageBytes));
     P.stages_a = sa > kMaxStagesA ? kMaxStagesA : sa;
   }
   // the statistics hand-over (kStatSlots tiles deep) relies on a tile spanning at least 3 k-blocks
@@ -887,7 +921,7 @@ int launch_linear(const stf_linear_args *args, void *stream) {
     if (a.ldy < a.N / 4) return STF_E_SHAPE;
     P.d_hw.init(a.H * a.W), P.d_w.init(a.W);
   }
-  const size_t smem = linear_smem_bytes(P.n_tile, P.slab, P.stages_a, P.stages_b, a.N);
+  const size_t smem = linear_smem_bytes(P.n_tile, P.slab, P.stages_a, P.stages_b, a.N, planes);
   if (smem > 227 * 1024) return STF_E_SHAPE;
   static std::atomic<int> attr_set{0};
   if (!attr_set.load(std::memory_order_acquire)) {
@@ -913,20 +947,21 @@ extern "C" int stf_linear_n_tile(int N) {
   return STF_E_SHAPE;
 }
 
-extern "C" int64_t stf_packed_linear_floats(int N, int K) {
-  if (N <= 0 || K <= 0) return STF_E_ARG;
-  return (int64_t)N * K + 3 * (int64_t)N;
+extern "C" int64_t stf_packed_linear_floats(int N, int K, int precision) {
+  if (N <= 0 || K <= 0 || (precision != STF_PREC_TF32 && precision != STF_PREC_FP32)) return STF_E_ARG;
+  return (int64_t)N * K * (precision == STF_PREC_FP32 ? 2 : 1) + 3 * (int64_t)N;
 }
 
 extern "C" int stf_pack_linear(const float *weight, const float *bias, const float *ln_gamma, const float *ln_beta,
-                               float *packed, int N, int K, void *stream) {
+                               float *packed, int N, int K, int precision, void *stream) {
   if (!weight || !packed || N <= 0 || K <= 0) return STF_E_ARG;
+  if (precision != STF_PREC_TF32 && precision != STF_PREC_FP32) return STF_E_ARG;
   if ((ln_gamma == nullptr) != (ln_beta == nullptr)) return STF_E_ARG;
   if (K % kBlockK != 0) return STF_E_SHAPE;
   int nt = stf_linear_n_tile(N);
   if (nt <= 0) return STF_E_SHAPE;
   if (!aligned16(packed)) return STF_E_ALIGN;
-  pack_weight_kernel<<<N, 128, 0, (cudaStream_t)stream>>>(weight, bias, ln_gamma, ln_beta, packed, N, K, nt);
+  pack_weight_kernel<<<N, 128, 0, (cudaStream_t)stream>>>(weight, bias, ln_gamma, ln_beta, packed, N, K, nt, precision == STF_PREC_FP32 ? 2 : 1);
   return check_launch();
 }
 

@@ -36,7 +36,7 @@ template <int WS, int D>
 __global__ void __launch_bounds__(kThreads)
 window_attention_kernel(const float *__restrict__ qkv, float *__restrict__ out,
                         const float *__restrict__ bias_table, const float *__restrict__ mask, int mask_windows,
-                        int64_t num_pairs, int C, int heads, int shift, int Hp, int Wp) {
+                        int64_t num_pairs, int C, int heads, int shift, int Hp, int Wp, int tf32_out) {
   constexpr int N = WS * WS;
   constexpr int PAIRS = kThreads / N;
   const int n = threadIdx.x % N;
@@ -119,7 +119,8 @@ window_attention_kernel(const float *__restrict__ qkv, float *__restrict__ out,
 #pragma unroll
   for (int j = 0; j < D; j += 4)
     *reinterpret_cast<float4 *>(dst + j) =
-        make_float4(round_tf32(o[j]), round_tf32(o[j + 1]), round_tf32(o[j + 2]), round_tf32(o[j + 3]));
+        tf32_out ? make_float4(round_tf32(o[j]), round_tf32(o[j + 1]), round_tf32(o[j + 2]), round_tf32(o[j + 3]))
+                     : make_float4(o[j], o[j + 1], o[j + 2], o[j + 3]);
 }
 
 
@@ -134,7 +135,7 @@ template <int D>
 __global__ void __launch_bounds__(384)
 window_attention16_kernel(const float *__restrict__ qkv, float *__restrict__ out,
                           const float *__restrict__ bias_table, const float *__restrict__ mask, int mask_windows,
-                          int64_t num_windows, int C, int heads, int shift, int Hp, int Wp, int wpc) {
+                          int64_t num_windows, int C, int heads, int shift, int Hp, int Wp, int wpc, int tf32_out) {
   constexpr int WS = 4, N = 16;
   extern __shared__ __align__(128) float tile[];  // [wpc][16][3C]
   __shared__ __align__(8) uint64_t bar;
@@ -226,7 +227,8 @@ window_attention16_kernel(const float *__restrict__ qkv, float *__restrict__ out
 #pragma unroll
     for (int j = 0; j < D; j += 4)
       *reinterpret_cast<float4 *>(base + n * ld + j) =
-          make_float4(round_tf32(o[j]), round_tf32(o[j + 1]), round_tf32(o[j + 2]), round_tf32(o[j + 3]));
+          tf32_out ? make_float4(round_tf32(o[j]), round_tf32(o[j + 1]), round_tf32(o[j + 2]), round_tf32(o[j + 3]))
+                     : make_float4(o[j], o[j + 1], o[j + 2], o[j + 3]);
   }
   sm100::fence_proxy_async_smem();
   __syncthreads();
@@ -244,7 +246,7 @@ window_attention16_kernel(const float *__restrict__ qkv, float *__restrict__ out
 
 template <int D>
 int launch16(const float *qkv, float *out, const float *bias_table, const float *mask, int mask_windows,
-             int64_t num_windows, int C, int heads, int shift, int Hp, int Wp, cudaStream_t st) {
+             int64_t num_windows, int C, int heads, int shift, int Hp, int Wp, int tf32_out, cudaStream_t st) {
   const int per_window = heads * 16;                 // threads per window
   const size_t win_bytes = (size_t)16 * 3 * C * 4;   // qkv tile of one window
   int wpc = 384 / per_window;
@@ -263,18 +265,18 @@ int launch16(const float *qkv, float *out, const float *bias_table, const float 
   if (blocks > 0x7fffffffLL) return STF_E_SHAPE;
   const int threads = (wpc * per_window + 31) / 32 * 32;
   window_attention16_kernel<D><<<(unsigned)blocks, threads, smem, st>>>(qkv, out, bias_table, mask, mask_windows,
-                                                                      num_windows, C, heads, shift, Hp, Wp, wpc);
+                                                                      num_windows, C, heads, shift, Hp, Wp, wpc, tf32_out);
   return check_launch();
 }
 
 template <int WS, int D>
 int launch(const float *qkv, float *out, const float *bias_table, const float *mask, int mask_windows,
-           int64_t num_windows, int C, int heads, int shift, int Hp, int Wp, cudaStream_t st) {
+           int64_t num_windows, int C, int heads, int shift, int Hp, int Wp, int tf32_out, cudaStream_t st) {
   constexpr int PAIRS = kThreads / (WS * WS);
   const int64_t pairs = num_windows * heads;
   const int64_t blocks = (pairs + PAIRS - 1) / PAIRS;
   if (blocks > 0x7fffffffLL) return STF_E_SHAPE;
-  window_attention_kernel<WS, D><<<(unsigned)blocks, kThreads, 0, st>>>(qkv, out, bias_table, mask, mask_windows, pairs, C, heads, shift, Hp, Wp);
+  window_attention_kernel<WS, D><<<(unsigned)blocks, kThreads, 0, st>>>(qkv, out, bias_table, mask, mask_windows, pairs, C, heads, shift, Hp, Wp, tf32_out);
   return check_launch();
 }
 
@@ -285,7 +287,7 @@ using namespace stf;
 
 extern "C" int stf_window_attention(const float *qkv, float *out, const float *bias_table, const float *mask,
                                     int mask_windows, int64_t num_windows, int C, int heads, int ws, int shift,
-                                    int Hp, int Wp, void *stream) {
+                                    int Hp, int Wp, int tf32_out, void *stream) {
   if (!qkv || !out || !bias_table || num_windows < 0 || C <= 0 || heads <= 0) return STF_E_ARG;
   if (num_windows == 0) return STF_OK;
   if (C % heads != 0 || shift < 0 || shift >= ws) return STF_E_SHAPE;
@@ -295,9 +297,9 @@ extern "C" int stf_window_attention(const float *qkv, float *out, const float *b
   const int d = C / heads;
   cudaStream_t st = (cudaStream_t)stream;
 #define CASE(WS_, D_) \
-  if (ws == WS_ && d == D_) return launch<WS_, D_>(qkv, out, bias_table, mask, mask_windows, num_windows, C, heads, shift, Hp, Wp, st)
+  if (ws == WS_ && d == D_) return launch<WS_, D_>(qkv, out, bias_table, mask, mask_windows, num_windows, C, heads, shift, Hp, Wp, tf32_out, st)
 #define CASE16(D_) \
-  if (ws == 4 && d == D_) return launch16<D_>(qkv, out, bias_table, mask, mask_windows, num_windows, C, heads, shift, Hp, Wp, st)
+  if (ws == 4 && d == D_) return launch16<D_>(qkv, out, bias_table, mask, mask_windows, num_windows, C, heads, shift, Hp, Wp, tf32_out, st)
   CASE16(16);
   CASE16(24);
   CASE16(32);

@@ -49,7 +49,7 @@ class _PackCache:
         """norm: the nn.LayerNorm applied to the Linear's input (folded into the packed image) or None."""
         key = tuple((t.data_ptr(), t._version) for t in
                     (weight, bias, None if norm is None else norm.weight, None if norm is None else norm.bias)
-                    if t is not None)
+                    if t is not None) + (ops.precision_code(),)
         if key != self._key:
             ln = None if norm is None else (norm.weight, norm.bias, norm.eps)
             self._val = ops.PackedLinear(weight, bias, ln)

@@ -4,6 +4,7 @@ non-zero status.  No CPU / eager fallback: CPU tensors are rejected.
 """
 import ctypes
 import math
+import os
 
 import numpy as np
 import torch
@@ -172,11 +173,35 @@ def entropy_bottleneck(z, params, lik_bound=1e-9, want_z_hat=True, want_lik=True
 
 # ------------------------------------------------------------------------------------ tensor-core linear
 
+# Arithmetic of the tensor-core GEMMs (include/stf_b200.h STF_PREC_*).  "fp32" (default) is the parity mode: the
+# reference's matmuls are true fp32, so operands are split hi + lo and multiplied as 3xTF32 (fp32-grade results).
+# "tf32" is the single-pass fast mode (~1e-3 relative per GEMM).  Select with STF_B200_PRECISION or set_precision().
+_PRECISIONS = {"fp32": _C.PREC_FP32, "tf32": _C.PREC_TF32}
+_precision = _PRECISIONS[os.environ.get("STF_B200_PRECISION", "fp32").lower()]
+
+
+def set_precision(name):
+    """'fp32' (3xTF32, parity with the reference's fp32 matmuls) or 'tf32' (single pass).  Returns the old name."""
+    global _precision
+    old = precision()
+    _precision = _PRECISIONS[name.lower()]
+    return old
+
+
+def precision():
+    return "fp32" if _precision == _C.PREC_FP32 else "tf32"
+
+
+def precision_code():
+    return _precision
+
+
 class PackedLinear:
     """A torch Linear (weight (N, K), optional bias) -- and the LayerNorm in front of it, if any -- packed for
-    the tcgen05 kernel (stf_pack_linear: TF32 tile image + the three LayerNorm-folding vectors)."""
+    the tcgen05 kernel (stf_pack_linear: TF32 tile image(s) + the three LayerNorm-folding vectors)."""
 
-    def __init__(self, weight, bias=None, ln=None):
+    def __init__(self, weight, bias=None, ln=None, prec=None):
+        self.precision = _precision if prec is None else int(prec)
         w = _dev(weight.detach().contiguous(), "weight")
         self.N, self.K = w.shape
         b = None if bias is None else _dev(bias.detach().contiguous(), "bias")
@@ -188,10 +213,10 @@ class PackedLinear:
             if g.numel() != self.K or be.numel() != self.K:
                 raise ValueError("LayerNorm width does not match the Linear's input features")
         self.has_ln = ln is not None
-        n = int(_C.lib().stf_packed_linear_floats(self.N, self.K))
+        n = int(_C.lib().stf_packed_linear_floats(self.N, self.K, self.precision))
         self.packed = torch.empty(n, dtype=torch.float32, device=w.device)
         _launch("pack_weight_kernel", 8 * w.numel(), _C.lib().stf_pack_linear, w.data_ptr(), _C.ptr(b), _C.ptr(g),
-                _C.ptr(be), self.packed.data_ptr(), self.N, self.K, _C.stream())
+                _C.ptr(be), self.packed.data_ptr(), self.N, self.K, self.precision, _C.stream())
 
 
 def linear(x, lin, *, M=None, rows=_C.ROWS_DENSE, epilogue=_C.EPI_STORE, residual=None, q_cols=0, q_scale=1.0,
@@ -216,7 +241,8 @@ def linear(x, lin, *, M=None, rows=_C.ROWS_DENSE, epilogue=_C.EPI_STORE, residua
     a.y, a.ldy = out.data_ptr(), out.shape[-1]
     a.rows = rows
     a.has_ln, a.ln_eps = int(lin.has_ln), lin.ln_eps
-    a.x_is_tf32 = int(bool(x_is_tf32))
+    a.x_is_tf32 = int(bool(x_is_tf32)) if lin.precision == _C.PREC_TF32 else 0
+    a.precision = lin.precision
     a.epilogue = epilogue
     if residual is not None:
         residual = _dev(residual, "residual")
@@ -230,8 +256,11 @@ def linear(x, lin, *, M=None, rows=_C.ROWS_DENSE, epilogue=_C.EPI_STORE, residua
     return out
 
 
-def window_attention_core(qkv, bias_table, num_windows, C, heads, ws, shift, Hp=0, Wp=0, mask=None):
-    """softmax(q k^T + B + mask) v per (window, head); qkv (num_windows*ws*ws, 3C), q pre-scaled."""
+def window_attention_core(qkv, bias_table, num_windows, C, heads, ws, shift, Hp=0, Wp=0, mask=None, tf32_out=None):
+    """softmax(q k^T + B + mask) v per (window, head); qkv (num_windows*ws*ws, 3C), q pre-scaled.
+    tf32_out (default: the TF32 precision mode is active): store the output rounded to TF32 for the proj GEMM."""
+    if tf32_out is None:
+        tf32_out = _precision == _C.PREC_TF32
     qkv = _dev(qkv, "qkv")
     bias_table = _dev(bias_table.detach(), "relative_position_bias_table")
     out = torch.empty((qkv.shape[0], C), dtype=torch.float32, device=qkv.device)
@@ -241,7 +270,7 @@ def window_attention_core(qkv, bias_table, num_windows, C, heads, ws, shift, Hp=
         mw = mask.shape[0]
     _launch("window_attention_kernel", 4 * qkv.shape[0] * 4 * C, _C.lib().stf_window_attention, qkv.data_ptr(),
             out.data_ptr(), bias_table.data_ptr(), _C.ptr(mask), mw, int(num_windows), C, heads, ws, shift, Hp, Wp,
-            _C.stream())
+            int(bool(tf32_out)), _C.stream())
     return out
 
 

@@ -105,6 +105,46 @@ def test_codec_vs_oracle_and_golden(golden_dir, name, Ora, case_i):
     assert abs(bpp_z - case["bpp_z_est"]) <= 0.02 * case["bpp_z_est"] + 1e-3
 
 
+def test_codec_fp32_strict_parity(golden_dir):
+    """The parity mode proper: 3xTF32 GEMMs (fp32-grade) and cuDNN's TF32 convolutions switched off, so that every
+    operator computes in fp32 like the CPU oracle.  What is left is summation order: y agrees to ~1e-5 and only
+    symbols whose pre-round value sits within that of a tie can flip."""
+    from stf_b200 import ops
+    e2e = json.load(open(os.path.join(golden_dir, "e2e.json")))["stf"]
+    case = e2e["cases"][0]
+    old_prec, old_tf32 = ops.set_precision("fp32"), torch.backends.cudnn.allow_tf32
+    torch.backends.cudnn.allow_tf32 = False
+    try:
+        net, sd = _build(golden_dir, "stf", e2e["weights_seed"])
+        net.cuda_graphs = False
+        x = synthetic_image(1, case["H"], case["W"], seed=case["image_seed"])
+        ora = OC.StfOracle(sd)
+        dbg, odbg = {}, {}
+        enc = net.compress(x.cuda(), debug=dbg)
+        oenc = ora.compress(x, debug=odbg)
+        y, oy = dbg["y"].cpu(), odbg["y"]
+        y_err = (y - oy).abs().max().item() / oy.abs().max().item()
+        sym, osym = dbg["symbols"].reshape(-1), odbg["symbols"].reshape(-1)
+        idx, oidx = dbg["indexes"].reshape(-1), odbg["indexes"].reshape(-1)
+        flips, idx_flips = float((sym != osym).float().mean()), float((idx != oidx).float().mean())
+        fwd = net(x.cuda())
+        ofwd = ora.forward(x)
+        xh, oxh = fwd["x_hat"].cpu(), ofwd["x_hat"]
+        ly, oly = fwd["likelihoods"]["y"].cpu(), ofwd["likelihoods"]["y"]
+        print(f"fp32 strict: y rel err {y_err:.2e}, symbol flips {flips:.2e}, index flips {idx_flips:.2e}, "
+              f"x_hat max err {(xh - oxh).abs().max().item():.2e}, "
+              f"y strings equal: {enc['strings'][0][0] == oenc['strings'][0][0]}")
+        assert y_err <= 1e-4
+        assert flips <= 1e-3 and idx_flips <= 1e-3
+        # likelihoods within 1e-3 relative (+ the 1e-9 floor) wherever the symbol did not flip (SURVEY F6)
+        bad = ((ly - oly).abs() > 1e-3 * oly + 1e-9).float().mean().item()
+        assert bad <= 5e-3, bad
+        assert psnr(xh, oxh) > 45.0
+    finally:
+        ops.set_precision(old_prec)
+        torch.backends.cudnn.allow_tf32 = old_tf32
+
+
 def test_batched_compress_matches_per_image(golden_dir):
     """Batch sharding contract: image b of a batched call yields the same strings
     as a batch-1 call on that image, and a batched decompress reproduces each batch-1 reconstruction."""

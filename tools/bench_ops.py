@@ -72,12 +72,55 @@ def main():
                 continue
             ms = timeit(fn, args.iters, flush)
             rows.append((st, C, T, name, ms, nbytes / ms / 1e6, flops / ms / 1e9))
+    print(f"GEMM precision: {ops.precision()}")
     print(f"{'stage':>5} {'C':>4} {'tokens':>8}  {'op':34} {'ms':>8} {'GB/s':>8} {'TFLOP/s':>8}")
     tot = 0
     for st, C, T, name, ms, gbs, tf in rows:
         tot += ms
         print(f"{st:5d} {C:4d} {T:8d}  {name:34} {ms:8.3f} {gbs:8.0f} {tf:8.1f}")
     print(f"sum of medians: {tot:.3f} ms for one Swin block per stage at batch {B}")
+    if not args.only or "entropy" in args.only:
+        entropy(args, flush)
+
+
+def entropy(args, flush):
+    """Entropy kernels at the roofline size of SURVEY.md 8d (2^26 elements: 256 MB per fp32 tensor >> 126 MB L2)
+    and at a natural slice size (batch 32 x 32 channels x 32 x 48)."""
+    import json
+    import math
+    peak = 6453.4
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        peak = float(json.load(open(p))["hbm_gbs"])
+    table = torch.exp(torch.linspace(math.log(0.11), math.log(256.0), 64))    # get_scale_table() (stf.py:21-31)
+    dev = "cuda"
+    print(f"{'elements':>10}  {'entropy kernel':44} {'ms':>8} {'GB/s':>8} {'of HBM peak':>11}")
+    for B, Cs, h, w in ((2048, 32, 32, 32), (32, 32, 32, 48)):
+        n = B * Cs * h * w
+        g = torch.Generator(device=dev).manual_seed(0)
+        scales = torch.exp(torch.empty(B, Cs, h, w, device=dev).uniform_(math.log(0.01), math.log(400.0), generator=g))
+        means = 2 * torch.randn(B, Cs, h, w, device=dev, generator=g)
+        y = means + scales * torch.randn(B, Cs, h, w, device=dev, generator=g)
+        sym = torch.empty(B, Cs * h * w, dtype=torch.int32, device=dev)
+        idx = torch.empty_like(sym)
+        C_eb = 192
+        z = 3 * torch.randn(max(B * Cs // C_eb, 1), C_eb, h, w, device=dev, generator=g)
+        from stf_b200.entropy_models import EntropyBottleneck
+        eb = EntropyBottleneck(C_eb).to(dev)
+        params = eb.packed_params()
+        cases = [
+            ("gaussian_likelihood (y_hat + lik, 20 B/el)", lambda: ops.gaussian_likelihood(y, 0, scales, means, ste_round=True), 20 * n),
+            ("gaussian_likelihood (lik only, 16 B/el)", lambda: ops.gaussian_likelihood(y, 0, scales, means, want_y_hat=False), 16 * n),
+            ("compress_step (idx + sym + y_hat, 24 B/el)", lambda: ops.gaussian_compress_step(y, 0, scales, means, table, sym, idx, 0), 24 * n),
+            ("build_indexes (8 B/el)", lambda: ops.build_indexes(scales, table), 8 * n),
+            ("dequantize (12 B/el)", lambda: ops.dequantize(sym, 0, means), 12 * n),
+            ("quantize symbols (12 B/el)", lambda: ops.quantize_symbols(y, means), 12 * n),
+        ]
+        if params is not None:
+            cases.append(("entropy_bottleneck (z_hat + lik, 12 B/el)", lambda: ops.entropy_bottleneck(z, params), 12 * z.numel()))
+        for name, fn, nbytes in cases:
+            ms = timeit(fn, args.iters, flush)
+            print(f"{n:10d}  {name:44} {ms:8.3f} {nbytes / ms / 1e6:8.0f} {nbytes / ms / 1e6 / peak:11.2f}")
 
 
 if __name__ == "__main__":
