@@ -29,6 +29,11 @@ struct ScaleTable {
   float v[64];
   int levels;
   int monotone;  // 1: non-decreasing -> binary search is exact; 0: reference's linear count
+  // Bucket LUT over the float bit pattern (monotone tables whose thresholds are at most two per bucket, e.g. the
+  // reference's geometric 64-level table): key = (bits(sigma) >> 20) - key_min indexes `lut`, which holds the number
+  // of thresholds below the bucket; at most two exact comparisons finish the count.  keys == 0: not usable.
+  int key_min, keys;
+  uint8_t lut[128];
 };
 
 // 16-byte streaming accesses: inputs are read once, outputs written once (no reuse in L1).

@@ -8,6 +8,8 @@
 //   stf_gaussian_likelihood      GaussianConditional.forward (eval)  entropy_models.py:645-659
 //   stf_entropy_bottleneck       EntropyBottleneck.forward (eval)    entropy_models.py:446-489
 #include <math.h>
+#include <stdlib.h>
+#include <string.h>
 
 #include "common.cuh"
 
@@ -44,6 +46,20 @@ __device__ __forceinline__ int scale_index(float sigma, const float *__restrict_
   }
 }
 
+// Same count through the bucket LUT (see ScaleTable): one conflict-free shared-memory byte lookup (the 128-entry LUT is
+// 32 words = one per bank) + two exact comparisons against the thresholds of that bucket.  `tp` = thresholds
+// t[0..levels-2] padded with +inf.  Bit-exact with the search above for every float input (tests/test_gpu_entropy.py).
+__device__ __forceinline__ int scale_index_lut(float sigma, const float *__restrict__ tp, const uint8_t *__restrict__ lut,
+                                               int key_min, int keys, int levels) {
+  // The bit pattern as a SIGNED integer orders like the float for sigma > 0; negative floats (sign bit) land below
+  // key_min and clamp to bucket 0.  NaNs of either sign are caught by the final select.
+  int key = (__float_as_int(sigma) >> 20) - key_min;
+  key = min(max(key, 0), keys - 1);
+  const int base = lut[key];   // byte load: the 128-entry LUT spans 32 words = one per bank, conflict-free
+  const int idx = base + (tp[base] < sigma ? 1 : 0) + (tp[base + 1] < sigma ? 1 : 0);
+  return sigma != sigma ? levels - 1 : idx;
+}
+
 __device__ __forceinline__ int round_to_symbol(float v) { return __float2int_rn(v); }  // half-to-even
 
 struct SliceGeom {
@@ -55,15 +71,25 @@ struct SliceGeom {
 // ---------------------------------------------------------------------------------------------
 // compress step: (y, mu, scale) -> (symbols, indexes, y_hat)
 // ---------------------------------------------------------------------------------------------
-template <bool kVec, bool kMonotone>
+template <bool kVec, int kMode>  // kMode: 0 = linear count, 1 = binary search, 2 = bucket LUT
 __global__ void __launch_bounds__(kThreads)
 compress_step_kernel(const float *__restrict__ y, const float *__restrict__ scales,
                      const float *__restrict__ means, int32_t *__restrict__ symbols,
                      int32_t *__restrict__ indexes, float *__restrict__ y_hat, SliceGeom g,
                      float scale_bound, const __grid_constant__ ScaleTable table) {
-  __shared__ float t[64];
-  if (threadIdx.x < 64) t[threadIdx.x] = table.v[threadIdx.x < table.levels ? threadIdx.x : table.levels - 1];
+  __shared__ float t[68];
+  __shared__ __align__(16) uint8_t lut[128];
+  if (kMode == 2) {  // thresholds t[0..levels-2] padded with +inf, LUT bytes packed four per word
+    if (threadIdx.x < 68) t[threadIdx.x] = (int)threadIdx.x < table.levels - 1 ? table.v[threadIdx.x] : __int_as_float(0x7f800000);
+    if (threadIdx.x >= 128) lut[threadIdx.x - 128] = table.lut[threadIdx.x - 128];
+  } else if (threadIdx.x < 64) {
+    t[threadIdx.x] = table.v[threadIdx.x < table.levels ? threadIdx.x : table.levels - 1];
+  }
   __syncthreads();
+  auto index_of = [&](float sigma) -> int {
+    if (kMode == 2) return scale_index_lut(sigma, t, lut, table.key_min, table.keys, table.levels);
+    return scale_index<kMode == 1>(sigma, t, table.levels);
+  };
   const int b = blockIdx.y;
   const float *yb = y ? y + (int64_t)b * g.y_batch_stride : nullptr;
   const float *sb = scales ? scales + (int64_t)b * g.inner : nullptr;
@@ -104,10 +130,10 @@ compress_step_kernel(const float *__restrict__ y, const float *__restrict__ scal
         }
         if (sb && idxb) {
           int4 ix;
-          ix.x = scale_index<kMonotone>(lower_bound_f(ss[u].x, scale_bound), t, table.levels);
-          ix.y = scale_index<kMonotone>(lower_bound_f(ss[u].y, scale_bound), t, table.levels);
-          ix.z = scale_index<kMonotone>(lower_bound_f(ss[u].z, scale_bound), t, table.levels);
-          ix.w = scale_index<kMonotone>(lower_bound_f(ss[u].w, scale_bound), t, table.levels);
+          ix.x = index_of(lower_bound_f(ss[u].x, scale_bound));
+          ix.y = index_of(lower_bound_f(ss[u].y, scale_bound));
+          ix.z = index_of(lower_bound_f(ss[u].z, scale_bound));
+          ix.w = index_of(lower_bound_f(ss[u].w, scale_bound));
           stg_stream(reinterpret_cast<int4 *>(idxb) + v, ix);
         }
       }
@@ -121,7 +147,7 @@ compress_step_kernel(const float *__restrict__ y, const float *__restrict__ scal
         if (symb) symb[i] = q;
         if (yhb) yhb[i] = (float)q + m;
       }
-      if (sb && idxb) idxb[i] = scale_index<kMonotone>(lower_bound_f(sb[i], scale_bound), t, table.levels);
+      if (sb && idxb) idxb[i] = index_of(lower_bound_f(sb[i], scale_bound));
     }
   }
 }
@@ -155,6 +181,28 @@ dequantize_kernel(const int32_t *__restrict__ symbols, const float *__restrict__
 // ---------------------------------------------------------------------------------------------
 // Gaussian likelihood (eval) fused with ste_round
 // ---------------------------------------------------------------------------------------------
+// erfc with relative accuracy (needed in the tails: the likelihood is a difference of two of them, floored at
+// 1e-9): erfc(z) = t exp(-z^2 + P(t)), t = 1/(1 + z/2), z >= 0 -- the Chebyshev fit of Numerical Recipes' erfcc
+// (fractional error < 1.2e-7 everywhere; measured here in fp32: < 2e-6 for z <= 4.5, 4e-6 to z = 6.5).
+// 1 MUFU.RCP + 1 MUFU.EX2 + 13 FMA-pipe instructions instead of erfcf's ~45 with a division: the kernel was
+// instruction-issue bound at 0.54-0.64 of the HBM roofline with erfcf.  Tolerance bar: 1e-3 |ref| + 1e-9.
+__device__ __forceinline__ float erfc_fast(float x) {
+  const float z = fabsf(x);
+  float t;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(t) : "f"(fmaf(0.5f, z, 1.0f)));
+  float p = fmaf(t, 0.17087277f, -0.82215223f);
+  p = fmaf(t, p, 1.48851587f);
+  p = fmaf(t, p, -1.13520398f);
+  p = fmaf(t, p, 0.27886807f);
+  p = fmaf(t, p, -0.18628806f);
+  p = fmaf(t, p, 0.09678418f);
+  p = fmaf(t, p, 0.37409196f);
+  p = fmaf(t, p, 1.00002368f);
+  p = fmaf(t, p, -1.26551223f);
+  const float r = t * exp2f(fmaf(-z, z, p) * 1.4426950408889634f);
+  return x >= 0.f ? r : 2.0f - r;   // (NaN compares false and is carried by r)
+}
+
 template <bool kSte>
 __device__ __forceinline__ float gauss_lik(float y, float mu, float scale, float scale_bound,
                                            float lik_bound, float *y_hat_out) {
@@ -166,8 +214,9 @@ __device__ __forceinline__ float gauss_lik(float y, float mu, float scale, float
   *y_hat_out = kSte ? ((r - t) + t) + mu : yh;
   float v = fabsf(yh - mu);
   float s = lower_bound_f(scale, scale_bound);
-  float upper = 0.5f * erfcf(kNegInvSqrt2 * ((0.5f - v) / s));
-  float lower = 0.5f * erfcf(kNegInvSqrt2 * ((-0.5f - v) / s));
+  const float inv_s = 1.0f / s;   // one IEEE reciprocal for both arguments (the reference divides twice: <= 1.5 ulp apart)
+  float upper = 0.5f * erfc_fast(kNegInvSqrt2 * ((0.5f - v) * inv_s));
+  float lower = 0.5f * erfc_fast(kNegInvSqrt2 * ((-0.5f - v) * inv_s));
   return lower_bound_f(upper - lower, lik_bound);
 }
 
@@ -297,6 +346,32 @@ int fill_table(ScaleTable *t, const float *table_host, int levels) {
   for (int i = 0; i < 64; ++i) t->v[i] = table_host[i < levels ? i : levels - 1];
   for (int i = 1; i < levels; ++i)
     if (!(table_host[i] >= table_host[i - 1])) t->monotone = 0;
+  // bucket LUT (see ScaleTable): thresholds are t[0 .. levels-2]
+  t->key_min = 0, t->keys = 0;
+  for (uint8_t &b : t->lut) b = 0;
+  const int nthr = levels - 1;
+  auto bits_of = [](float f) { uint32_t u; memcpy(&u, &f, 4); return u; };
+  auto float_of = [](uint32_t u) { float f; memcpy(&f, &u, 4); return f; };
+  if (t->monotone && nthr >= 1 && table_host[0] > 0.f && table_host[nthr - 1] < 3.0e38f) {
+    const int kmin = (int)(bits_of(table_host[0]) >> 20), kmax = (int)(bits_of(table_host[nthr - 1]) >> 20) + 1;
+    const int keys = kmax - kmin + 1;
+    if (keys <= 128) {
+      bool ok = true;
+      for (int k = 0; k < keys && ok; ++k) {
+        const float lo = float_of((uint32_t)(kmin + k) << 20), hi = float_of((uint32_t)(kmin + k + 1) << 20);
+        int below = 0, inside = 0;  // bucket 0 also takes everything below its lower edge, the last everything above
+        for (int i = 0; i < nthr; ++i) {
+          const bool is_below = k > 0 && table_host[i] < lo;
+          const bool is_above = k < keys - 1 && !(table_host[i] < hi);
+          below += is_below ? 1 : 0;
+          inside += (!is_below && !is_above) ? 1 : 0;
+        }
+        ok = inside <= 2;
+        t->lut[k] = (uint8_t)below;
+      }
+      if (ok) t->key_min = kmin, t->keys = keys;
+    }
+  }
   return STF_OK;
 }
 
@@ -339,6 +414,7 @@ extern "C" int stf_gaussian_compress_step(const float *y, int64_t y_batch_stride
   } else {
     t.levels = 1;
     t.monotone = 1;
+    t.key_min = t.keys = 0;
     for (float &v : t.v) v = 0.f;
   }
   SliceGeom g{(int64_t)channels * plane, y_batch_stride, out_batch_stride};
@@ -348,10 +424,12 @@ extern "C" int stf_gaussian_compress_step(const float *y, int64_t y_batch_stride
   cudaStream_t st = (cudaStream_t)stream;
 #define LAUNCH(V, M) \
   compress_step_kernel<V, M><<<grid, kThreads, 0, st>>>(y, scales, means, symbols, indexes, y_hat, g, scale_bound, t)
+  static const bool no_lut = getenv("STF_B200_NO_INDEX_LUT") != nullptr;  // (test hook: exercise the binary search)
+  const int mode = !t.monotone ? 0 : (t.keys > 0 && !no_lut) ? 2 : 1;
   if (vec) {
-    if (t.monotone) LAUNCH(true, true); else LAUNCH(true, false);
+    if (mode == 2) LAUNCH(true, 2); else if (mode == 1) LAUNCH(true, 1); else LAUNCH(true, 0);
   } else {
-    if (t.monotone) LAUNCH(false, true); else LAUNCH(false, false);
+    if (mode == 2) LAUNCH(false, 2); else if (mode == 1) LAUNCH(false, 1); else LAUNCH(false, 0);
   }
 #undef LAUNCH
   return check_launch();

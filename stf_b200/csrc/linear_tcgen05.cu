@@ -103,6 +103,7 @@ struct LinearParams {
   int lite;        // A operand needs no finalize pass (no LayerNorm, X already TF32-exact): one thread fences + publishes
   int stages_a, stages_b;
   int epi_mode;    // 0: staged slab -> coalesced 16-byte stores by the whole warp; 1: one bulk (TMA) store per row
+  uint32_t backoff_ns;  // nanosleep between mbarrier probes of the producer-side roles (0 = tight spin)
   int debug_skip;  // bring-up / profiling only (env STF_B200_DEBUG_SKIP): 1 = no A loads, 2 = no B loads, 4 = no stores
   int fin_group;  // k-blocks published per proxy fence by the finalize warps (divides k_blocks, < stages_a)
   int Hp, Wp, nWw, nW;  // WINDOW geometry: padded size, windows per row, windows per image
@@ -118,11 +119,11 @@ __device__ long long g_trace[kTraceEvents][kTraceTiles];
 __device__ long long g_ktrace[8][32];   // per-k-block events of CTA 0's third tile (STF_B200_DEBUG_SKIP & 8)
 #define KTRACE(ev, tile_it, kb)                                                                             \
   do {                                                                                                      \
-    if ((P.debug_skip & 8) && blockIdx.x == 0 && (tile_it) == 2 && (kb) < 32) g_ktrace[ev][kb] = clock64(); \
+    if (kDbg && (P.debug_skip & 8) && blockIdx.x == 0 && (tile_it) == 2 && (kb) < 32) g_ktrace[ev][kb] = clock64(); \
   } while (0)
 #define TRACE(ev, it)                                                                              \
   do {                                                                                             \
-    if ((P.debug_skip & 8) && blockIdx.x == 0 && lane == 0 && (it) < kTraceTiles) g_trace[ev][it] = clock64(); \
+    if (kDbg && (P.debug_skip & 8) && blockIdx.x == 0 && lane == 0 && (it) < kTraceTiles) g_trace[ev][it] = clock64(); \
   } while (0)
 
 // ---------------------------------------------------------------------------- cp.async helpers
@@ -201,13 +202,13 @@ struct RowSrc {     // where one A-tile row comes from
   int merge_flags;  // MERGE: bit0 = row 2i+1 valid, bit1 = col 2j+1 valid
 };
 
-__device__ __forceinline__ RowSrc row_source(const LinearParams &P, int row) {
+__device__ __forceinline__ RowSrc row_source(const LinearParams &P, int rows_mode, int row) {
   const stf_linear_args &a = P.a;
   RowSrc r{nullptr, 0};
   if (row >= a.M) return r;
-  if (a.rows == STF_ROWS_DENSE) {
+  if (rows_mode == STF_ROWS_DENSE) {
     r.p = a.x + (int64_t)row * a.ldx;
-  } else if (a.rows == STF_ROWS_WINDOW) {
+  } else if (rows_mode == STF_ROWS_WINDOW) {
     bool valid;
     int tok = window_row_to_token(P, row, &valid);
     if (valid) r.p = a.x + (int64_t)tok * a.ldx;
@@ -222,9 +223,9 @@ __device__ __forceinline__ RowSrc row_source(const LinearParams &P, int row) {
 }
 
 // source address of the 16-byte chunk at K offset k of row r (nullptr = zero-fill)
-__device__ __forceinline__ const float *chunk_source(const LinearParams &P, const RowSrc &r, int k) {
+__device__ __forceinline__ const float *chunk_source(const LinearParams &P, int rows_mode, const RowSrc &r, int k) {
   if (!r.p) return nullptr;
-  if (P.a.rows != STF_ROWS_MERGE) return r.p + k;
+  if (rows_mode != STF_ROWS_MERGE) return r.p + k;
   const int C = P.a.K >> 2;
   int part = k / C, c = k - part * C;  // concat order x0,x1,x2,x3 = (0,0),(1,0),(0,1),(1,1)  (stf.py:225-229)
   int di = part & 1, dj = part >> 1;
@@ -342,13 +343,25 @@ size_t linear_smem_bytes(int n_tile, int slab, int stages_a, int stages_b, int N
 }
 
 // ---------------------------------------------------------------------------- the kernel
+// Template arguments >= 0 fix the epilogue / row-gather / LayerNorm / precision mode at compile time (-1 = read it
+// from the parameters).  ncu on the all-runtime kernel: 26 KB of instructions executed per tile against a 32 KB
+// instruction cache, 13 % instruction-cache misses and the GPC instruction-fetch path at 75 % of its peak -- every role
+// ran at ~15 cycles per instruction.  The specialised instances drop the untaken paths, the tracing hooks (kDbg) and the
+// bring-up switches from the instruction stream.
+template <int kEpi, int kRows, int kLn, int kPrec, int kDbg>
 __global__ void __launch_bounds__(kThreads, 1)
 linear_tf32_kernel(const __grid_constant__ LinearParams P) {
   extern __shared__ __align__(128) uint8_t smem[];
   const stf_linear_args &a = P.a;
+  const int epi = kEpi >= 0 ? kEpi : a.epilogue;
+  const int rows_mode = kRows >= 0 ? kRows : a.rows;
+  const int has_ln = kLn >= 0 ? kLn : P.has_ln;
+  const int precise = kPrec >= 0 ? kPrec : P.precise;
+  const int dbg = kDbg ? P.debug_skip : 0;
+  const int epi_mode = kDbg ? P.epi_mode : 0;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int NT = P.n_tile;
-  const int planes = P.precise ? 2 : 1;  // hi (+ lo) operand images per stage
+  const int planes = precise ? 2 : 1;  // hi (+ lo) operand images per stage
   const SmemMap S = carve(smem, NT, P.stages_a, P.stages_b, P.slab, planes);
   const uint32_t a_stage_bytes = (uint32_t)planes * kAStageBytes;
   for (int i = threadIdx.x; i < 3 * a.N; i += kThreads) S.aux[i] = __ldg(P.aux + i);  // visible after the __syncthreads below
@@ -387,7 +400,7 @@ linear_tf32_kernel(const __grid_constant__ LinearParams P) {
     const int sub = lane & 7, chunk = lane >> 3;
     const uint32_t a_base = smem_u32(S.a_ring) + (uint32_t)(chunk * (kTileM * 16) + (warp * 32 + sub) * 16);
     uint32_t i_stage = 0, i_phase = 1;  // waiting on parity 1 of a fresh barrier returns immediately
-    const bool merge = a.rows == STF_ROWS_MERGE;
+    const bool merge = rows_mode == STF_ROWS_MERGE;
     int tr_it = 0;
     for (int i_tile = first_tile; i_tile < P.total_tiles; i_tile += tile_step, ++tr_it) {
       const int m0 = (i_tile / P.n_tiles) * kTileM;
@@ -397,14 +410,14 @@ linear_tf32_kernel(const __grid_constant__ LinearParams P) {
       uint32_t nbytes[4];
 #pragma unroll
       for (int i = 0; i < 4; ++i) {
-        src[i] = row_source(P, m0 + warp * 32 + i * 8 + sub);
+        src[i] = row_source(P, rows_mode, m0 + warp * 32 + i * 8 + sub);
         base[i] = src[i].p ? src[i].p + chunk * 4 : a.x;  // (zero-filled rows still need a valid address)
         nbytes[i] = src[i].p ? 16u : 0u;
       }
       for (int i_kb = 0; i_kb < P.k_blocks; ++i_kb) {
-        mbar_wait(&S.emptyA[i_stage], i_phase);
+        if (P.backoff_ns) mbar_wait_backoff(&S.emptyA[i_stage], i_phase, P.backoff_ns); else mbar_wait(&S.emptyA[i_stage], i_phase);
         const uint32_t dst = a_base + i_stage * a_stage_bytes;
-        if (P.debug_skip & 1) {
+        if (dbg & 1) {
         } else if (!merge) {
 #pragma unroll
           for (int i = 0; i < 4; ++i) cp_async16(dst + i * 128, base[i] + i_kb * kBlockK, nbytes[i]);
@@ -412,7 +425,7 @@ linear_tf32_kernel(const __grid_constant__ LinearParams P) {
           const int k = i_kb * kBlockK + chunk * 4;
 #pragma unroll
           for (int i = 0; i < 4; ++i) {
-            const float *p = chunk_source(P, src[i], k);
+            const float *p = chunk_source(P, rows_mode, src[i], k);
             cp_async16(dst + i * 128, p ? (const void *)p : (const void *)a.x, p ? 16u : 0u);
           }
         }
@@ -436,7 +449,7 @@ linear_tf32_kernel(const __grid_constant__ LinearParams P) {
         const long long total_kb = (long long)((P.total_tiles - first_tile + tile_step - 1) / tile_step) * P.k_blocks;
         uint32_t st = (uint32_t)fw % SA, ph = ((uint32_t)fw / SA) & 1u;
         for (long long g = fw; g < total_kb; g += kFinalizeWarps) {
-          mbar_wait(&S.landA[st], ph);
+          if (P.backoff_ns) mbar_wait_backoff(&S.landA[st], ph, P.backoff_ns); else mbar_wait(&S.landA[st], ph);
           KTRACE(1, (int)(g / P.k_blocks), (int)(g % P.k_blocks));
           fence_proxy_async_smem();
           mbar_arrive(&S.fullA[st]);
@@ -455,13 +468,13 @@ linear_tf32_kernel(const __grid_constant__ LinearParams P) {
     int f_it = 0;
     for (int tile = first_tile; tile < P.total_tiles; tile += tile_step, ++f_it) {
       for (int f_kb = 0; f_kb < P.k_blocks; ++f_kb) {
-        mbar_wait(&S.landA[f_stage], f_phase);
+        if (P.backoff_ns) mbar_wait_backoff(&S.landA[f_stage], f_phase, P.backoff_ns); else mbar_wait(&S.landA[f_stage], f_phase);
         if (fw == 0 && f_kb == 0) TRACE(2, f_it);
         const uint32_t addr = a_base + f_stage * a_stage_bytes;
 #pragma unroll
         for (int i = 0; i < 2; ++i) {
           float4 v = lds128(addr + i * 128);
-          if (P.has_ln) {
+          if (has_ln) {
             if (f_kb == 0) {  // shift by the row's first element: keeps the one-pass variance well conditioned
               shift0[i] = __shfl_sync(0xffffffffu, v.x, sub);
               sum[i] = 0.f, sq[i] = 0.f;
@@ -472,11 +485,11 @@ linear_tf32_kernel(const __grid_constant__ LinearParams P) {
           }
           const float4 hi = make_float4(round_tf32(v.x), round_tf32(v.y), round_tf32(v.z), round_tf32(v.w));
           sts128(addr + i * 128, hi);
-          if (P.precise)  // residual of the TF32 rounding, itself TF32: x = hi + lo to ~2^-22 relative
+          if (precise)  // residual of the TF32 rounding, itself TF32: x = hi + lo to ~2^-22 relative
             sts128(addr + kAStageBytes + i * 128, make_float4(round_tf32(v.x - hi.x), round_tf32(v.y - hi.y),
                                                             round_tf32(v.z - hi.z), round_tf32(v.w - hi.w)));
         }
-        if (P.has_ln && f_kb == P.k_blocks - 1) {  // row statistics for the epilogue of this tile
+        if (has_ln && f_kb == P.k_blocks - 1) {  // row statistics for the epilogue of this tile
 #pragma unroll
           for (int i = 0; i < 2; ++i) {
             float s1 = sum[i], s2 = sq[i];
@@ -533,30 +546,30 @@ linear_tf32_kernel(const __grid_constant__ LinearParams P) {
       const float *res = nullptr;
       bool pad_row = false;
       if (row < a.M) {
-        if (a.epilogue == STF_EPI_WINDOW_RESIDUAL) {
+        if (epi == STF_EPI_WINDOW_RESIDUAL) {
           bool valid;
           int tok = window_row_to_token(P, row, &valid);
           if (valid) {
             dst = a.y + (int64_t)tok * a.ldy;
             res = a.residual + (int64_t)tok * a.ldy;
           }
-        } else if (a.epilogue == STF_EPI_PIXEL_SHUFFLE) {
+        } else if (epi == STF_EPI_PIXEL_SHUFFLE) {
           int b, rem, h, w;
           P.d_hw.divmod(row, b, rem);
           P.d_w.divmod(rem, h, w);
           dst = a.y + (int64_t)((b * 2 * a.H + 2 * h) * (2 * a.W) + 2 * w) * a.ldy;  // token (2h, 2w)
         } else {
           dst = a.y + (int64_t)row * a.ldy;
-          if (a.epilogue == STF_EPI_RESIDUAL) res = a.residual + (int64_t)row * a.ldy;
+          if (epi == STF_EPI_RESIDUAL) res = a.residual + (int64_t)row * a.ldy;
         }
-        if (a.rows == STF_ROWS_WINDOW && P.has_ln && P.has_pad) {  // pad tokens are zero AFTER norm1 (stf.py:155-162)
+        if (rows_mode == STF_ROWS_WINDOW && has_ln && P.has_pad) {  // pad tokens are zero AFTER norm1 (stf.py:155-162)
           bool valid;
           (void)window_row_to_token(P, row, &valid);
           pad_row = !valid;
         }
       }
       // dense destinations (STORE / QKV / GELU / RESIDUAL): rows of this warp are consecutive in y
-      const bool dense = a.epilogue != STF_EPI_WINDOW_RESIDUAL && a.epilogue != STF_EPI_PIXEL_SHUFFLE;
+      const bool dense = epi != STF_EPI_WINDOW_RESIDUAL && epi != STF_EPI_PIXEL_SHUFFLE;
       const int row_base = mt * kTileM + quad * 32;
       float *dense0 = dense ? a.y + (int64_t)row_base * a.ldy : nullptr;
       const int rows_valid = a.M - row_base;
@@ -570,7 +583,7 @@ linear_tf32_kernel(const __grid_constant__ LinearParams P) {
       if (ew == 0) TRACE(7, it);
       tc_fence_after();
       float mean = 0.f, rstd = 1.f;
-      if (P.has_ln) {
+      if (has_ln) {
         float2 st = S.stats[(it % kStatSlots) * 128 + quad * 32 + lane];
         mean = st.x, rstd = st.y;
       }
@@ -578,7 +591,7 @@ linear_tf32_kernel(const __grid_constant__ LinearParams P) {
       for (int s = half; s < n_slabs; s += kEpiPerQuad) {
         const int c0 = s * slab;       // column inside the tile
         const int n0 = nt * NT + c0;   // global output feature
-        const bool row_store = P.epi_mode == 1 && a.epilogue != STF_EPI_PIXEL_SHUFFLE;
+        const bool row_store = epi_mode == 1 && epi != STF_EPI_PIXEL_SHUFFLE;
         if (row_store) bulk_wait_read0();  // this thread's previous bulk store has finished reading its staging row
         // ---- phase 1: thread = row.  TMEM -> registers -> math -> staging
         for (int c = 0; c < slab; c += 16) {
@@ -603,16 +616,16 @@ linear_tf32_kernel(const __grid_constant__ LinearParams P) {
               acc[j + 3] = fmaf(rstd, acc[j + 3] - mean * sv.w, tv.w);
             }
           }
-          if (a.epilogue == STF_EPI_QKV) {
+          if (epi == STF_EPI_QKV) {
             if (n < a.q_cols) {  // q_cols is a multiple of 16
 #pragma unroll
               for (int j = 0; j < 16; ++j) acc[j] *= a.q_scale;
             }
-          } else if (a.epilogue == STF_EPI_GELU) {
+          } else if (epi == STF_EPI_GELU) {
 #pragma unroll
             for (int j = 0; j < 16; ++j) {
               const float ge = gelu_erf(acc[j]);
-              acc[j] = P.precise ? ge : round_tf32(ge);  // TF32 mode: fc2 (the only consumer) reads it as TF32
+              acc[j] = precise ? ge : round_tf32(ge);  // TF32 mode: fc2 (the only consumer) reads it as TF32
             }
           }
           if (res) {
@@ -632,16 +645,16 @@ linear_tf32_kernel(const __grid_constant__ LinearParams P) {
         }
         if (row_store) {  // one bulk (TMA) copy per row: staging row -> its destination row segment
           fence_proxy_async_smem();
-          if (dst && !(P.debug_skip & 4)) bulk_store_s2g(dst + n0, stg_u32 + (uint32_t)(lane * srow * 4), (uint32_t)(slab * 4));
+          if (dst && !(dbg & 4)) bulk_store_s2g(dst + n0, stg_u32 + (uint32_t)(lane * srow * 4), (uint32_t)(slab * 4));
           bulk_commit();
           if (ew == 0) TRACE(9, it);
         }
         if (row_store) continue;
         __syncwarp();
         // ---- phase 2: lanes sweep the 32 staged rows with contiguous 16-byte accesses
-        if (a.epilogue == STF_EPI_PIXEL_SHUFFLE) {
+        if (epi == STF_EPI_PIXEL_SHUFFLE) {
           store_slab_pixel_shuffle(a, stg_u32, srow, f4row, rdst, n0, lane);
-        } else if (!(P.debug_skip & 4)) {
+        } else if (!(dbg & 4)) {
           switch (f4row) {
             case 4: store_slab<4>(stg_u32, srow, rdst, dense0, a.ldy, rows_valid, n0, lane); break;
             case 8: store_slab<8>(stg_u32, srow, rdst, dense0, a.ldy, rows_valid, n0, lane); break;
@@ -657,7 +670,7 @@ linear_tf32_kernel(const __grid_constant__ LinearParams P) {
         if (lane == 0) mbar_arrive(&S.accEmpty[buf]);
       }
     }
-    if (P.epi_mode == 1) bulk_wait0();  // all bulk stores of this thread have been written
+    if (epi_mode == 1) bulk_wait0();  // all bulk stores of this thread have been written
   } else if (warp == kMmaWarp) {
     // =========================== MMA issuer ===========================
     // The whole warp runs the loop with warp-uniform values (so descriptors and barrier addresses live in
@@ -697,7 +710,7 @@ linear_tf32_kernel(const __grid_constant__ LinearParams P) {
             if (leader) {
               const uint64_t dak = da + (uint64_t)(ks * a_ks16), dbk = db + (uint64_t)(ks * b_ks16);
               umma_tf32(d_tmem, dak, dbk, P.idesc, (kb | ks) ? 1u : 0u);
-              if (P.precise) {  // 3xTF32 error compensation (the lo.lo term is below fp32 round-off)
+              if (precise) {  // 3xTF32 error compensation (the lo.lo term is below fp32 round-off)
                 umma_tf32(d_tmem, dak + a_lo16, dbk, P.idesc, 1u);
                 umma_tf32(d_tmem, dak, dbk + b_lo16, P.idesc, 1u);
               }
@@ -706,7 +719,7 @@ linear_tf32_kernel(const __grid_constant__ LinearParams P) {
           if (leader) umma_commit(&S.emptyA[sa]);  // frees the A stage and (for the loader) the B stage of this k-block
           if (kb == 1) TRACE(15, it);
           if (lane == 0) KTRACE(4, it, kb);
-          if ((P.debug_skip & 16) && it == 2) {  // experiment: expose the MMA completion latency
+          if ((dbg & 16) && it == 2) {  // experiment: expose the MMA completion latency
             mbar_wait(&S.emptyA[sa], pa);
             if (lane == 0) KTRACE(7, it, kb);
           }
@@ -733,12 +746,12 @@ linear_tf32_kernel(const __grid_constant__ LinearParams P) {
         const float *wt = a.w_packed + (size_t)nt * (size_t)(a.K >> 2) * NT * 4 * planes;
         for (int kb = 0; kb < P.k_blocks; ++kb, ++g) {
           if (g >= (long long)SB) {
-            mbar_wait(&S.emptyA[wa], wpa);
+            if (P.backoff_ns) mbar_wait_backoff(&S.emptyA[wa], wpa, P.backoff_ns); else mbar_wait(&S.emptyA[wa], wpa);
             if (++wa == SA) wa = 0, wpa ^= 1u;
           }
           if (lane == 0) KTRACE(6, (int)(g / P.k_blocks), kb);
           if (leader) {
-            if (P.debug_skip & 2) {
+            if (dbg & 2) {
               mbar_arrive(&S.fullB[sb]);
             } else {
               mbar_arrive_expect_tx(&S.fullB[sb], b_stage_bytes);
@@ -763,7 +776,7 @@ linear_tf32_kernel(const __grid_constant__ LinearParams P) {
       uint32_t sa = 0, sb = 0, pb = 0;
       const long long total_kb = (long long)((P.total_tiles - first_tile + tile_step - 1) / tile_step) * P.k_blocks;
       for (long long g = 0; g < total_kb; ++g) {
-        mbar_wait(&S.fullB[sb], pb);
+        if (P.backoff_ns) mbar_wait_backoff(&S.fullB[sb], pb, P.backoff_ns); else mbar_wait(&S.fullB[sb], pb);
         mbar_arrive(&S.fullA[sa]);
         KTRACE(5, (int)(g / P.k_blocks), (int)(g % P.k_blocks));
         if (++sa == SA) sa = 0;
@@ -887,6 +900,11 @@ int launch_linear(const stf_linear_args *args, void *stream) {
     return e ? atoi(e) : 0;
   }();
   P.epi_mode = epi_mode_env;
+  static const int backoff_env = [] {
+    const char *e = getenv("STF_B200_BACKOFF_NS");
+    return e ? atoi(e) : 64;
+  }();
+  P.backoff_ns = (uint32_t)backoff_env;
   P.fin_group = (P.k_blocks % 4 == 0) ? 4 : (P.k_blocks % 3 == 0) ? 3 : (P.k_blocks % 2 == 0) ? 2 : 1;
   {  // all the shared memory the B ring and the epilogue staging leave over goes to the A ring
     const size_t fixed = linear_smem_bytes(P.n_tile, P.slab, 0, P.stages_b, a.N, planes);
@@ -923,15 +941,30 @@ int launch_linear(const stf_linear_args *args, void *stream) {
   }
   const size_t smem = linear_smem_bytes(P.n_tile, P.slab, P.stages_a, P.stages_b, a.N, planes);
   if (smem > 227 * 1024) return STF_E_SHAPE;
-  static std::atomic<int> attr_set{0};
-  if (!attr_set.load(std::memory_order_acquire)) {
-    cudaError_t e = cudaFuncSetAttribute(linear_tf32_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         227 * 1024);
+  // Specialised instances for the combinations the model mirrors use; anything else (and every bring-up / tracing
+  // run) takes the all-runtime instance.
+  using KernelFn = void (*)(const LinearParams);
+  KernelFn fn = linear_tf32_kernel<-1, -1, -1, -1, 1>;
+  const bool plain = debug_skip_env == 0 && epi_mode_env == 0;
+#define STF_LINEAR_CASE(E, R, L)                                                                \
+  if (plain && a.epilogue == (E) && a.rows == (R) && P.has_ln == (L))                            \
+    fn = P.precise ? (KernelFn)linear_tf32_kernel<E, R, L, 1, 0> : (KernelFn)linear_tf32_kernel<E, R, L, 0, 0>;
+  STF_LINEAR_CASE(STF_EPI_QKV, STF_ROWS_WINDOW, 1)              // STF block: norm1 + shift + partition + qkv
+  STF_LINEAR_CASE(STF_EPI_QKV, STF_ROWS_WINDOW, 0)              // WACNN attention: partition + qkv
+  STF_LINEAR_CASE(STF_EPI_QKV, STF_ROWS_DENSE, 0)               // WindowAttention.forward on ready-made windows
+  STF_LINEAR_CASE(STF_EPI_WINDOW_RESIDUAL, STF_ROWS_DENSE, 0)   // proj + reverse + un-shift + shortcut
+  STF_LINEAR_CASE(STF_EPI_STORE, STF_ROWS_DENSE, 0)             // plain proj / fc2
+  STF_LINEAR_CASE(STF_EPI_GELU, STF_ROWS_DENSE, 1)              // norm2 + fc1 + GELU
+  STF_LINEAR_CASE(STF_EPI_RESIDUAL, STF_ROWS_DENSE, 0)          // fc2 + residual
+  STF_LINEAR_CASE(STF_EPI_STORE, STF_ROWS_MERGE, 1)             // PatchMerging
+  STF_LINEAR_CASE(STF_EPI_PIXEL_SHUFFLE, STF_ROWS_DENSE, 1)     // PatchSplit
+#undef STF_LINEAR_CASE
+  {
+    cudaError_t e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);  // idempotent, cheap
     if (e != cudaSuccess) return (int)e;
-    attr_set.store(1, std::memory_order_release);
   }
   const int grid = P.total_tiles < kNumSMs ? P.total_tiles : kNumSMs;
-  linear_tf32_kernel<<<grid, kThreads, smem, (cudaStream_t)stream>>>(P);
+  fn<<<grid, kThreads, smem, (cudaStream_t)stream>>>(P);
   return check_launch();
 }
 

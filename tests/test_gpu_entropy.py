@@ -204,3 +204,30 @@ def test_gaussian_conditional_compress_decompress_api():
         gc.decompress(strings[:2], idx, mu.cuda())
     with pytest.raises(ValueError):
         gc.decompress("notalist", idx)
+
+
+def test_build_indexes_lut_equals_count_on_random_bit_patterns():
+    """The bucket-LUT index (csrc/entropy_kernels.cu scale_index_lut) against the definition
+    idx = #{i < 63 : table[i] < max(scale, bound)} (NaN -> 63) on uniformly random float BIT PATTERNS
+    (negatives, denormals, infinities, NaNs, every exponent) plus every table value and its +-1-ulp neighbours."""
+    from stf_b200 import ops
+    table = OE.scale_table()
+    g = torch.Generator().manual_seed(7)
+    bits = torch.randint(-2 ** 31, 2 ** 31 - 1, (1 << 20,), generator=g, dtype=torch.int64).to(torch.int32)
+    t = torch.as_tensor(table, dtype=torch.float32)
+    ti = t.view(torch.int32)
+    near = torch.cat([ti - 1, ti, ti + 1, ti - 2, ti + 2])
+    s = torch.cat([bits, near]).view(torch.float32)
+    sig = torch.where(s < 0.11, torch.full_like(s, 0.11), s)          # torch.max(x, bound) with NaN propagation
+    sig = torch.where(torch.isnan(s), s, sig)
+    ref = (t[:-1][None, :] < sig[:, None]).sum(1).to(torch.int32)
+    ref = torch.where(torch.isnan(sig), torch.full_like(ref, 63), ref)
+    got = ops.build_indexes(s.cuda(), table).cpu()
+    assert torch.equal(got, ref)
+    # a table whose thresholds crowd one bucket falls back to the binary search: same definition
+    crowded = torch.cat([torch.linspace(0.11, 0.1101, 40), torch.linspace(0.2, 256.0, 24)]).float()
+    sig2 = torch.where(s < 0.11, torch.full_like(s, 0.11), s)
+    sig2 = torch.where(torch.isnan(s), s, sig2)
+    ref2 = (crowded[:-1][None, :] < sig2[:, None]).sum(1).to(torch.int32)
+    ref2 = torch.where(torch.isnan(sig2), torch.full_like(ref2, 63), ref2)
+    assert torch.equal(ops.build_indexes(s.cuda(), crowded.numpy()).cpu(), ref2)
