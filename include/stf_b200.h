@@ -211,6 +211,44 @@ int stf_window_attention(const float *qkv, float *out, const float *bias_table, 
                          int Hp, int Wp, int tf32_out, void *stream);
 
 /* ------------------------------------------------------------------------------------------
+ * Training step (BASELINE config 5): backward kernels.  The backward GEMMs dX = dY . W are stf_linear calls
+ * on the packed transposed weight; weight gradients dW = dY^T . X are plain library GEMMs on the caller's side.
+ * Row / window reductions are two-stage and atomic-free: every CTA writes its partial sums to its own slot of
+ * `partials`, the caller adds the slots in a fixed order (deterministic gradients).
+ * ------------------------------------------------------------------------------------------ */
+
+/* Backward of stf_window_attention for 4x4 windows (autograd of stf.py:100-118):
+ *   dqkv (num_windows*16, 3C): [dq * q_scale | dk | dv]   (q in `qkv` is the pre-scaled q the forward consumed;
+ *   dq is returned already multiplied by q_scale = d(q_scaled)/d(q), so dqkv is the gradient of the qkv Linear output)
+ *   dbias_partials: (stf_attention_bwd_ctas(...), (2*ws-1)^2, heads) partial sums of d relative_position_bias_table.
+ * stf_attention_bwd_ctas returns the number of partial slots (CTAs) for a problem size. */
+int stf_attention_bwd_ctas(int64_t num_windows, int C, int heads, int *windows_per_cta_out);
+int stf_window_attention_bwd(const float *qkv, const float *dout, const float *bias_table, float *dqkv,
+                             float *dbias_partials, int64_t num_windows, int C, int heads, int ws, int shift,
+                             int Hp, int Wp, float q_scale, void *stream);
+
+/* LayerNorm backward over rows of C <= 768 features (autograd of nn.LayerNorm, stf.py:155,197):
+ *   g = dL/d(LN output) (M, C);  dx = LN'(g) + res (res = gradient of the residual path or NULL);
+ *   xn (optional) = LN(x) recomputed (the wgrad operand of the Linear behind the norm);
+ *   partials: (stf_layernorm_bwd_ctas(M), 2, C) partial sums of (dgamma, dbeta). */
+int stf_layernorm_bwd_ctas(int64_t M);
+int stf_layernorm_bwd(const float *x, const float *g, const float *gamma, const float *beta, const float *res,
+                      float *dx, float *xn, float *partials, int64_t M, int C, float eps, void *stream);
+
+/* Exact-erf GELU backward: dpre = dh * (Phi(pre) + pre * phi(pre)); n % 4 == 0. */
+int stf_gelu_bwd(const float *pre, const float *dh, float *dpre, int64_t n, void *stream);
+
+/* GaussianConditional.forward in training mode (entropy_models.py:131-135, 645-659): the likelihood of
+ * y + noise (noise = U(-1/2, 1/2) supplied by the caller, NULL = 0) under N(means, max(scales, bound)),
+ * floored at lik_bound; and its backward with the LowerBound gradient rule (ops/bound_ops.py:21-27: the
+ * gradient passes where x >= bound or grad < 0).  dmean may be NULL. */
+int stf_gaussian_likelihood_train(const float *y, const float *scales, const float *means, const float *noise,
+                                  float *likelihood, int64_t n, float scale_bound, float lik_bound, void *stream);
+int stf_gaussian_likelihood_train_bwd(const float *y, const float *scales, const float *means, const float *noise,
+                                      const float *dlik, float *dy, float *dscale, float *dmean, int64_t n,
+                                      float scale_bound, float lik_bound, void *stream);
+
+/* ------------------------------------------------------------------------------------------
  * Host-side rANS codec (CPU; replaces compressai.ans, cpp_exts/rans/rans_interface.cpp:99-350,
  * bit-exact streams, no Python lists, LUT symbol search, thread-parallel over streams).
  * ------------------------------------------------------------------------------------------ */

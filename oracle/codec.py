@@ -43,6 +43,18 @@ def _hyper_synthesis(sd, pfx, x):
     return _conv(sd, pfx + "8", x)
 
 
+def train_noise(seed, B, M, h, w, Cz, hz, wz, num_slices=12):
+    """The reference's quantisation-noise stream under torch.manual_seed(seed) in train() mode: entropy_models.py:131-135
+    draws torch.empty_like(inputs).uniform_(-1/2, 1/2) first for z in the (C, 1, B*h*w) layout of :455-461, then for each
+    y slice (B, M/num_slices, h, w) in order (stf.py:613-623).  Returned in model layout: {"z": (B,Cz,hz,wz), "y": (B,M,h,w)}."""
+    state = torch.random.get_rng_state()
+    torch.manual_seed(seed)
+    nz = torch.empty(Cz, 1, B * hz * wz).uniform_(-0.5, 0.5)
+    ny = [torch.empty(B, M // num_slices, h, w).uniform_(-0.5, 0.5) for _ in range(num_slices)]
+    torch.random.set_rng_state(state)
+    return {"z": nz.reshape(Cz, B, hz, wz).permute(1, 0, 2, 3).contiguous(), "y": torch.cat(ny, dim=1)}
+
+
 def _eb_params(sd, pfx="entropy_bottleneck."):
     return {k: sd[pfx + k] for k in E.eb_param_names()}
 
@@ -130,6 +142,28 @@ class _SliceCodec:
         y_hat = torch.cat(y_hat_slices, dim=1)
         return {"x_hat": self.synthesis(y_hat), "likelihoods": {"y": torch.cat(liks, dim=1), "z": z_lik},
                 "y": y, "y_hat": y_hat}
+
+    def forward_train(self, x, noise):
+        """stf.py:584-648 with self.training == True and drop_path_rate = 0: "noise" quantisation for both
+        likelihoods (injected tensors noise["y"], noise["z"] stand for U(-1/2, 1/2)), ste_round for
+        z_hat / y_hat.  Differentiable: call with requires_grad tensors in self.sd for the gradient oracle."""
+        y = self.analysis(x)
+        hw = y.shape[2:]
+        z = self._h_a(y)
+        _, z_lik = E.eb_forward_train(self.eb, z, noise["z"])
+        med = E.eb_medians(self.eb).reshape(1, -1, 1, 1)
+        z_hat = E.ste_round(z - med) + med
+        scales = _hyper_synthesis(self.sd, "h_scale_s.", z_hat)
+        means = _hyper_synthesis(self.sd, "h_mean_s.", z_hat)
+        y_hat_slices, liks = [], []
+        for i, y_i in enumerate(y.chunk(self.num_slices, 1)):
+            mean_sup, mu, sc = self._slice_params(i, means, scales, y_hat_slices, hw)
+            _, lik = E.gaussian_conditional_train(y_i, sc, mu, noise["y"].chunk(self.num_slices, 1)[i])
+            liks.append(lik)
+            y_hat_i = E.ste_round(y_i - mu) + mu
+            y_hat_slices.append(self._lrp(i, mean_sup, y_hat_i))
+        y_hat = torch.cat(y_hat_slices, dim=1)
+        return {"x_hat": self.synthesis(y_hat), "likelihoods": {"y": torch.cat(liks, dim=1), "z": z_lik}}
 
     @torch.no_grad()
     def compress(self, x, debug=None):

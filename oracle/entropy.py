@@ -138,6 +138,55 @@ def gaussian_likelihood(values, scales, means=None, scale_bound=0.11):
     return upper - lower
 
 
+class LowerBoundFn(torch.autograd.Function):
+    """ops/bound_ops.py:21-65 -- forward max(x, bound); backward passes the gradient where x >= bound or grad < 0."""
+
+    @staticmethod
+    def forward(ctx, x, bound):
+        ctx.save_for_backward(x, bound)
+        return torch.max(x, bound)
+
+    @staticmethod
+    def backward(ctx, grad_output):
+        x, bound = ctx.saved_tensors
+        pass_through = (x >= bound) | (grad_output < 0)
+        return pass_through.type(grad_output.dtype) * grad_output, None
+
+
+def lower_bound_train(x, bound):
+    return LowerBoundFn.apply(x, torch.tensor([float(bound)], dtype=x.dtype))
+
+
+def ste_round(x):
+    """ops/ops.py:20-34 -- round(x) - x.detach() + x (identity gradient)."""
+    return torch.round(x) - x.detach() + x
+
+
+def gaussian_conditional_train(x, scales, means, noise, scale_bound=0.11):
+    """GaussianConditional.forward with training=True, entropy_models.py:645-659 + :131-135 ("noise" ignores the
+    means) + :626-643, with the injected noise tensor standing for U(-1/2, 1/2).  Differentiable."""
+    out = x + noise
+    v = torch.abs(out - means if means is not None else out)
+    s = lower_bound_train(scales, scale_bound)
+    lik = std_normal_cdf((0.5 - v) / s) - std_normal_cdf((-0.5 - v) / s)
+    return out, lower_bound_train(lik, LIKELIHOOD_FLOOR)
+
+
+def eb_forward_train(p, z, noise):
+    """EntropyBottleneck.forward with training=True, entropy_models.py:446-489 (noise quantisation, :131-135;
+    the sign of :428-429 is detached).  Differentiable w.r.t. z and the parameters."""
+    perm = list(range(z.ndim))
+    perm[0], perm[1] = 1, 0
+    zc = z.permute(*perm).contiguous()
+    shape = zc.shape
+    out = zc.reshape(shape[0], 1, -1) + noise.permute(*perm).contiguous().reshape(shape[0], 1, -1)
+    lo = eb_logits_cumulative(p, out - 0.5)
+    hi = eb_logits_cumulative(p, out + 0.5)
+    sgn = -torch.sign(lo + hi).detach()
+    lik = lower_bound_train(torch.abs(torch.sigmoid(sgn * hi) - torch.sigmoid(sgn * lo)), LIKELIHOOD_FLOOR)
+    return out.reshape(shape).permute(*perm).contiguous(), lik.reshape(shape).permute(*perm).contiguous()
+
+
 def gaussian_conditional_eval(x, scales, means=None):
     """GaussianConditional.forward with training=False, entropy_models.py:645-659.
     Returns (outputs, likelihood)."""

@@ -55,6 +55,13 @@ SIGNATURES = {
     "stf_pack_linear": (c_int, [c_vp, c_vp, c_vp, c_vp, c_vp, c_int, c_int, c_int, c_vp]),
     "stf_linear": (c_int, [ctypes.POINTER(LinearArgs), c_vp]),
     "stf_window_attention": (c_int, [c_vp, c_vp, c_vp, c_vp, c_int, c_i64, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_vp]),
+    "stf_attention_bwd_ctas": (c_int, [c_i64, c_int, c_int, ctypes.POINTER(c_int)]),
+    "stf_window_attention_bwd": (c_int, [c_vp, c_vp, c_vp, c_vp, c_vp, c_i64, c_int, c_int, c_int, c_int, c_int, c_int, c_f32, c_vp]),
+    "stf_layernorm_bwd_ctas": (c_int, [c_i64]),
+    "stf_layernorm_bwd": (c_int, [c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_i64, c_int, c_f32, c_vp]),
+    "stf_gelu_bwd": (c_int, [c_vp, c_vp, c_vp, c_i64, c_vp]),
+    "stf_gaussian_likelihood_train": (c_int, [c_vp, c_vp, c_vp, c_vp, c_vp, c_i64, c_f32, c_f32, c_vp]),
+    "stf_gaussian_likelihood_train_bwd": (c_int, [c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_i64, c_f32, c_f32, c_vp]),
     "stf_rans_table_create": (c_vp, [_i32p, c_int, c_int, _i32p, _i32p]),
     "stf_rans_table_destroy": (None, [c_vp]),
     "stf_rans_encode_bound": (c_i64, [c_i64]),

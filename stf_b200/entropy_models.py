@@ -44,7 +44,8 @@ class LowerBound(nn.Module):
 
     def forward(self, x):
         if x.requires_grad and torch.is_grad_enabled():
-            raise NotImplementedError("stf_b200: LowerBound's custom gradient (bound_ops.py:25-27) is not built yet")
+            from .autograd import LowerBoundFunction
+            return LowerBoundFunction.apply(x, self.bound)
         return torch.max(x, self.bound)
 
 
@@ -278,16 +279,36 @@ class EntropyBottleneck(EntropyModel):
         logits = self._logits_cumulative(self.quantiles, stop_gradient=True)
         return torch.abs(logits - self.target).sum()
 
-    def forward(self, x, training=None):
+    def forward(self, x, training=None, noise=None):
         if training is None:
             training = self.training
-        if training and torch.is_grad_enabled():
-            raise NotImplementedError("stf_b200: EntropyBottleneck training forward (noise + autograd) is not built yet")
         if x.dim() < 2 or x.shape[1] != self.channels:
             raise ValueError(f"expected (B, {self.channels}, ...) input, got {tuple(x.shape)}")
+        if training and torch.is_grad_enabled():
+            return self._forward_train(x, noise)
         z_hat, lik, _ = ops.entropy_bottleneck(x.contiguous(), self.packed_params(),
                                                lik_bound=self._likelihood_bound if self.use_likelihood_bound else 0.0)
         return z_hat, lik
+
+    def _forward_train(self, x, noise=None):
+        """Training forward (entropy_models.py:446-489 with "noise" quantisation), differentiable w.r.t. x and the 58
+        parameters per channel.  z is 18 k - 50 k elements: latency-bound either way, so this path is the reference's own
+        op sequence on torch's autograd (the eval kernel has no backward); the LowerBound keeps its custom gradient."""
+        perm = [1, 0] + list(range(2, x.dim()))
+        v = x.permute(*perm).contiguous()
+        shape = v.size()
+        v = v.reshape(v.size(0), 1, -1)
+        n = torch.empty_like(v).uniform_(-0.5, 0.5) if noise is None else \
+            noise.permute(*perm).contiguous().reshape(v.shape)
+        out = v + n
+        lower = self._logits_cumulative(out - 0.5, stop_gradient=False)
+        upper = self._logits_cumulative(out + 0.5, stop_gradient=False)
+        sign = -torch.sign(lower + upper).detach()
+        lik = torch.abs(torch.sigmoid(sign * upper) - torch.sigmoid(sign * lower))
+        if self.use_likelihood_bound:
+            lik = self.likelihood_lower_bound(lik)
+        inv = [1, 0] + list(range(2, x.dim()))
+        return out.reshape(shape).permute(*inv).contiguous(), lik.reshape(shape).permute(*inv).contiguous()
 
     @staticmethod
     def _build_indexes(size):
@@ -386,11 +407,16 @@ class GaussianConditional(EntropyModel):
             self._table_host = (key, self.scale_table.detach().float().cpu().numpy().copy())
         return self._table_host[1]
 
-    def forward(self, inputs, scales, means=None, training=None):
+    def forward(self, inputs, scales, means=None, training=None, noise=None):
         if training is None:
             training = self.training
         if training and torch.is_grad_enabled():
-            raise NotImplementedError("stf_b200: GaussianConditional training forward (noise + autograd) is not built yet")
+            from .autograd import GaussianLikelihoodTrain
+            n = torch.empty_like(inputs).uniform_(-0.5, 0.5) if noise is None else noise
+            lik = GaussianLikelihoodTrain.apply(inputs, scales.expand_as(inputs), None if means is None else
+                                                means.expand_as(inputs), n, self.scale_bound_value(),
+                                                self._likelihood_bound if self.use_likelihood_bound else 0.0)
+            return inputs + n, lik
         x = inputs.contiguous()
         x4 = x.reshape(x.shape[0], x.shape[1] if x.dim() > 1 else 1, -1)
         s = scales.expand_as(inputs).contiguous().reshape(x4.shape)

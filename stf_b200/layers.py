@@ -35,8 +35,12 @@ def to_2tuple(x):
 def _require_eval(mod):
     if mod.training and torch.is_grad_enabled():
         raise NotImplementedError(
-            f"{type(mod).__name__}: stf_b200 implements the inference path (call .eval() or use torch.no_grad()); "
-            "training-mode kernels (backward) are not built yet")
+            f"{type(mod).__name__}: the stand-alone module has no backward; the training path runs through "
+            "SwinTransformerBlock / BasicLayer (stf_b200/autograd.py)")
+
+
+def _grad_mode(mod):
+    return mod.training and torch.is_grad_enabled()
 
 
 class _PackCache:
@@ -55,6 +59,14 @@ class _PackCache:
             self._val = ops.PackedLinear(weight, bias, ln)
             self._key = key
         return self._val
+
+    def get_t(self, weight):
+        """Packed W^T (no bias, no LayerNorm): stf_linear on it computes dY . W, the input gradient of the Linear."""
+        key = (weight.data_ptr(), weight._version, ops.precision_code())
+        if key != getattr(self, "_key_t", None):
+            self._val_t = ops.PackedLinear(weight.detach().t().contiguous())
+            self._key_t = key
+        return self._val_t
 
 
 def window_partition(x, window_size):
@@ -170,7 +182,6 @@ class SwinTransformerBlock(nn.Module):
     def forward(self, x, mask_matrix=None):
         """x: (B, H*W, C).  `mask_matrix` is accepted for signature parity and ignored: the
         shifted-window mask is computed analytically inside the attention kernel."""
-        _require_eval(self)
         B, L, C = x.shape
         H, W = self.H, self.W
         assert L == H * W, "input feature has wrong size"
@@ -178,6 +189,8 @@ class SwinTransformerBlock(nn.Module):
         Hp, Wp = ops.ceil_to(H, ws), ops.ceil_to(W, ws)
         geom = (B, H, W, ws, shift)
         x2 = x.reshape(B * L, C)
+        if _grad_mode(self):
+            return self._forward_train(x2, geom).reshape(B, L, C)
         qkv = ops.linear(x2, self.attn.packed_qkv(self.norm1), M=B * Hp * Wp, rows=_C.ROWS_WINDOW,
                          epilogue=_C.EPI_QKV, q_cols=C, q_scale=self.attn.scale, geom=geom)
         o = ops.window_attention_core(qkv, self.attn.relative_position_bias_table, B * (Hp // ws) * (Wp // ws), C,
@@ -186,6 +199,28 @@ class SwinTransformerBlock(nn.Module):
                         out_rows=B * L, x_is_tf32=True)
         y = self.mlp(x1, norm=self.norm2, residual=x1)
         return y.reshape(B, L, C)
+
+
+def _swin_train(self, x2, geom):
+    """Training step of one block (stf.py:149-199): same fused forward kernels, backward in stf_b200/autograd.py;
+    DropPath (timm 0.4.12, per-sample) rescales each branch's update."""
+    from . import autograd as AG
+    B = geom[0]
+    a, m = self.attn, self.mlp
+    x1 = AG.AttentionBranch.apply(x2, self.norm1.weight, self.norm1.bias, a.qkv.weight, a.qkv.bias,
+                                  a.relative_position_bias_table, a.proj.weight, a.proj.bias, self, geom)
+    s = AG.drop_path_scale(x2.reshape(B, -1, 1), self.drop_path_rate, True)
+    if s is not None:
+        x1 = (x2.reshape(B, -1, x2.shape[-1]) + (x1 - x2).reshape(B, -1, x2.shape[-1]) * s).reshape(x2.shape)
+    y = AG.MlpBranch.apply(x1, self.norm2.weight, self.norm2.bias, m.fc1.weight, m.fc1.bias, m.fc2.weight, m.fc2.bias,
+                           self)
+    s = AG.drop_path_scale(x2.reshape(B, -1, 1), self.drop_path_rate, True)
+    if s is not None:
+        y = (x1.reshape(B, -1, x2.shape[-1]) + (y - x1).reshape(B, -1, x2.shape[-1]) * s).reshape(x2.shape)
+    return y
+
+
+SwinTransformerBlock._forward_train = _swin_train
 
 
 class PatchMerging(nn.Module):
@@ -199,9 +234,15 @@ class PatchMerging(nn.Module):
         self._p = _PackCache()
 
     def forward(self, x, H, W):
-        _require_eval(self)
         B, L, C = x.shape
         assert L == H * W, "input feature has wrong size"
+        if _grad_mode(self):
+            # training: three of these per forward (0.7 % of the FLOPs) -- differentiable torch ops, stf.py:218-235
+            x = x.view(B, H, W, C)
+            if (H % 2 == 1) or (W % 2 == 1):
+                x = F.pad(x, (0, 0, 0, W % 2, 0, H % 2))
+            x = torch.cat([x[:, 0::2, 0::2, :], x[:, 1::2, 0::2, :], x[:, 0::2, 1::2, :], x[:, 1::2, 1::2, :]], -1)
+            return self.reduction(self.norm(x.view(B, -1, 4 * C)))
         H2, W2 = (H + 1) // 2, (W + 1) // 2
         y = ops.linear(x.reshape(B * L, C), self._p.get(self.reduction.weight, None, self.norm), M=B * H2 * W2,
                        rows=_C.ROWS_MERGE, geom=(B, H, W, 0, 0))
@@ -220,9 +261,13 @@ class PatchSplit(nn.Module):
         self._p = _PackCache()
 
     def forward(self, x, H, W):
-        _require_eval(self)
         B, L, C = x.shape
         assert L == H * W, "input feature has wrong size"
+        if _grad_mode(self):
+            # training: differentiable torch ops, stf.py:251-260
+            y = self.reduction(self.norm(x))
+            y = self.shuffle(y.permute(0, 2, 1).contiguous().view(B, 2 * C, H, W))
+            return y.permute(0, 2, 3, 1).contiguous().view(B, 4 * L, -1)
         y = ops.linear(x.reshape(B * L, C), self._p.get(self.reduction.weight, None, self.norm),
                        epilogue=_C.EPI_PIXEL_SHUFFLE, geom=(B, H, W, 0, 0), out_rows=4 * B * L, out_cols=C // 2)
         return y.reshape(B, 4 * L, C // 2)

@@ -154,8 +154,8 @@ class _SliceCodec(CompressionModel):
 
     def _require_inference(self):
         if self.training and torch.is_grad_enabled():
-            raise NotImplementedError("stf_b200 implements the inference path: call .eval() / torch.no_grad(). "
-                                      "The training step (config 5) needs backward kernels that are not built yet.")
+            raise NotImplementedError("compress() / decompress() are inference entry points: call .eval() or wrap "
+                                      "them in torch.no_grad()")
 
     # ------------------------------------------------------------------ slice-loop building blocks
     # Inside the loop every tensor that feeds a convolution is channels_last (cuDNN's tensor-core kernels
@@ -207,10 +207,47 @@ class _SliceCodec(CompressionModel):
         z_hat = z_hat.contiguous(memory_format=self._CL)
         return self.h_scale_s(z_hat), self.h_mean_s(z_hat)
 
-    def forward(self, x):
-        self._require_inference()
+    def forward(self, x, noise=None):
+        """eval / no_grad: the fused inference path.  train() with grad enabled: the training forward of
+        stf.py:584-648 / cnn.py:141-189 ("noise" quantisation for the likelihoods, ste_round for y_hat / z_hat) with
+        backward through stf_b200/autograd.py.  `noise` (optional dict {"y": (B,M,h,w), "z": (B,192,h',w')} of
+        U(-1/2, 1/2) tensors) injects the quantisation noise for parity runs."""
+        if self.training and torch.is_grad_enabled():
+            return self._forward_train(x, noise)
         with torch.no_grad():
             return self._forward_eval(x)
+
+    def _forward_train(self, x, noise=None):
+        from . import autograd as AG
+        y = self._analysis(x)
+        hw = y.shape[2:]
+        z = self.h_a(y)
+        eb, gc = self.entropy_bottleneck, self.gaussian_conditional
+        _, z_likelihoods = eb(z, noise=None if noise is None else noise.get("z"))
+        z_offset = eb._get_medians().reshape(1, -1, 1, 1)
+        z_hat = AG.ste_round(z - z_offset) + z_offset
+        latent_scales, latent_means = self.h_scale_s(z_hat), self.h_mean_s(z_hat)
+        Cs = self.slice_channels
+        y_hat_slices, y_likelihood = [], []
+        for i, y_slice in enumerate(y.chunk(self.num_slices, 1)):
+            support = y_hat_slices if self.max_support_slices < 0 else y_hat_slices[: self.max_support_slices]
+            mean_support = torch.cat([latent_means] + support, dim=1)
+            mu = self.cc_mean_transforms[i](mean_support)[:, :, : hw[0], : hw[1]]
+            scale = self.cc_scale_transforms[i](torch.cat([latent_scales] + support, dim=1))[:, :, : hw[0], : hw[1]]
+            n_i = (torch.empty_like(y_slice).uniform_(-0.5, 0.5) if noise is None
+                   else noise["y"][:, i * Cs:(i + 1) * Cs])
+            lik = AG.GaussianLikelihoodTrain.apply(y_slice, scale, mu, n_i, gc.scale_bound_value(),
+                                                   gc._likelihood_bound if gc.use_likelihood_bound else 0.0)
+            y_likelihood.append(lik)
+            y_hat_slice = AG.ste_round(y_slice - mu) + mu
+            lrp = self.lrp_transforms[i](torch.cat([mean_support, y_hat_slice], dim=1))
+            y_hat_slices.append(y_hat_slice + 0.5 * torch.tanh(lrp))
+        y_hat = torch.cat(y_hat_slices, dim=1)
+        out = {"x_hat": self._synthesis(y_hat),
+               "likelihoods": {"y": torch.cat(y_likelihood, dim=1), "z": z_likelihoods}}
+        if hasattr(self, "is_teacher"):
+            out["y"] = y if self.is_teacher else None
+        return out
 
     def _forward_eval(self, x):
         self._prepare_inference()

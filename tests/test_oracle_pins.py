@@ -187,3 +187,31 @@ def test_oracle_vs_live_reference_random_ops():
     mask = OS.shift_mask(12, 8, 4, 2)
     with torch.no_grad():
         assert torch.allclose(blk(x, mask), OS.swin_block(sd, "", x, 12, 8, 6, 4, 2, mask), rtol=2e-5, atol=2e-5)
+
+
+def test_training_restatement_matches_recorded_reference(golden_dir):
+    """oracle forward_train (+ torch autograd) reproduces the loss and every gradient norm the live reference produced in
+    train() mode (tests/golden/train_kat.json, recorded by oracle/gen_golden_train.py)."""
+    import math
+    from oracle import codec as OC
+    from stf_b200.synth import synthetic_image
+    kat = json.load(open(os.path.join(golden_dir, "train_kat.json")))
+    spec = {k: (tuple(s), getattr(torch, d.split(".")[-1])) for k, (s, d) in
+            json.load(open(os.path.join(golden_dir, "stf_spec.json"))).items()}
+    sd = synthetic_state_dict(spec, kat["weights_seed"])
+    ora = OC.StfOracle(sd)
+    for k, v in ora.sd.items():
+        if k in kat["grad_norm"]:
+            v.requires_grad_(True)
+    im = kat["image"]
+    x = synthetic_image(im["B"], im["H"], im["W"], seed=im["seed"])
+    noise = OC.train_noise(kat["noise_seed"], im["B"], 384, im["H"] // 16, im["W"] // 16, 192, im["H"] // 64, im["W"] // 64)
+    out = ora.forward_train(x, noise)
+    n_px = im["B"] * im["H"] * im["W"]
+    bpp = sum(torch.log(l).sum() / (-math.log(2) * n_px) for l in out["likelihoods"].values())
+    loss = kat["lmbda"] * 255 ** 2 * torch.nn.functional.mse_loss(out["x_hat"], x) + bpp
+    loss.backward()
+    assert abs(float(loss.detach()) - kat["loss"]) <= 1e-5 * abs(kat["loss"])
+    for n, ref in kat["grad_norm"].items():
+        got = float(ora.sd[n].grad.norm())
+        assert abs(got - ref) <= 1e-4 * ref + 1e-9, (n, got, ref)
