@@ -152,11 +152,6 @@ class _SliceCodec(CompressionModel):
         net.load_state_dict(state_dict)
         return net
 
-    def _require_inference(self):
-        if self.training and torch.is_grad_enabled():
-            raise NotImplementedError("compress() / decompress() are inference entry points: call .eval() or wrap "
-                                      "them in torch.no_grad()")
-
     # ------------------------------------------------------------------ slice-loop building blocks
     # Inside the loop every tensor that feeds a convolution is channels_last (cuDNN's tensor-core kernels
     # are NHWC: no per-conv layout transposes); the 32-channel tensors our kernels read / write are NCHW

@@ -173,9 +173,9 @@ def test_model_error_paths(golden_dir):
     with pytest.raises(ValueError):
         net.compress(x)                                   # update() not called: "Uninitialized CDFs"
     net.train()
-    with pytest.raises(NotImplementedError):
-        with torch.enable_grad():
-            net(x)
+    with torch.enable_grad():
+        out = net(x)                                      # train() forward is the differentiable training path
+    assert out["x_hat"].requires_grad and out["likelihoods"]["y"].requires_grad
     sd = net.state_dict()
     net2 = SymmetricalTransFormer.from_state_dict(sd)     # load_state_dict with empty tables round-trips
     assert set(net2.state_dict()) == set(sd)

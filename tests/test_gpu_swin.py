@@ -209,12 +209,17 @@ def test_index_math_exact(H, W, shift):
     _check(y, OS.swin_block(sd, "", x, H, W, nh, ws, shift, mask), "block vs oracle")
 
 
-def test_training_mode_raises_instead_of_falling_back():
+def test_training_mode_limits_raise_instead_of_falling_back():
+    """The training path covers window-aligned feature maps (every training shape of the reference); the zero-pad
+    path and the stand-alone WindowAttention module have no backward and say so."""
     from stf_b200 import layers as L
     blk = L.SwinTransformerBlock(48, 3, 4, 0).cuda().train()
-    blk.H, blk.W = 4, 4
+    blk.H, blk.W = 6, 6
     with pytest.raises(NotImplementedError):
-        blk(torch.randn(1, 16, 48, device="cuda", requires_grad=True), None)
+        blk(torch.randn(1, 36, 48, device="cuda", requires_grad=True), None)
+    wa = L.WindowAttention(48, (4, 4), 3).cuda().train()
+    with pytest.raises(NotImplementedError):
+        wa(torch.randn(2, 16, 48, device="cuda", requires_grad=True))
 
 
 def test_linear_tf32_fast_path_matches_rounding_path():

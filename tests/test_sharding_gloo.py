@@ -83,3 +83,64 @@ def test_shard_range_partitions_exactly():
             assert max(b - a for a, b in spans) - min(b - a for a, b in spans) <= 1
     with pytest.raises(ValueError):
         shard_range(4, 2, 2)
+
+
+def _train_worker(rank, world, port, q):
+    """Data-parallel training step on gloo: each rank has its own half batch; after GradientAllReduce every rank must hold
+    the gradient of the full-batch mean loss, and the optimizer steps must keep the replicas identical."""
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from stf_b200.training import GradientAllReduce
+        torch.manual_seed(0)                                   # identical replicas
+        net = torch.nn.Sequential(torch.nn.Linear(12, 32), torch.nn.GELU(), torch.nn.Linear(32, 3))
+        unused = torch.nn.Parameter(torch.ones(5))             # a parameter that never receives a gradient
+        params = list(net.parameters()) + [unused]
+        g = torch.Generator().manual_seed(1)
+        x, y = torch.randn(8, 12, generator=g), torch.randn(8, 3, generator=g)
+        opt = torch.optim.Adam(net.parameters(), lr=1e-2)
+        red = GradientAllReduce(params, bucket_mb=0.0005)      # ~130 floats per bucket: several buckets
+        assert len(red.buckets) >= 2
+        lo, hi = rank * 4, rank * 4 + 4
+        for _ in range(2):
+            opt.zero_grad()
+            torch.nn.functional.mse_loss(net(x[lo:hi]), y[lo:hi]).backward()
+            nbytes = red()
+            opt.step()
+        # (numpy, not tensors: tensors travel through the queue as shared-memory handles that die with the worker)
+        grads = [p.grad.numpy().copy() for p in net.parameters()]
+        q.put((rank, nbytes, [p.detach().numpy().copy() for p in net.parameters()], grads, unused.grad.numpy().copy()))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_two_rank_gradient_allreduce_equals_full_batch():
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_train_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    got = sorted((q.get(timeout=120) for _ in range(2)), key=lambda t: t[0])
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    # single-process reference: full batch of 8, mean loss == mean of the two half-batch mean losses
+    torch.manual_seed(0)
+    net = torch.nn.Sequential(torch.nn.Linear(12, 32), torch.nn.GELU(), torch.nn.Linear(32, 3))
+    g = torch.Generator().manual_seed(1)
+    x, y = torch.randn(8, 12, generator=g), torch.randn(8, 3, generator=g)
+    opt = torch.optim.Adam(net.parameters(), lr=1e-2)
+    for _ in range(2):
+        opt.zero_grad()
+        torch.nn.functional.mse_loss(net(x), y).backward()
+        opt.step()
+    n_param_bytes = 4 * (sum(p.numel() for p in net.parameters()) + 5)
+    for rank, nbytes, params, grads, unused_grad in got:
+        assert nbytes == n_param_bytes
+        for p, ref in zip(params, net.parameters()):
+            assert np.allclose(p, ref.detach().numpy(), rtol=1e-5, atol=1e-6)
+        for gr, ref in zip(grads, net.parameters()):
+            assert np.allclose(gr, ref.grad.numpy(), rtol=1e-4, atol=1e-6)
+        assert np.array_equal(unused_grad, np.zeros(5, dtype=np.float32))
+    assert all(np.array_equal(a, b) for a, b in zip(got[0][2], got[1][2]))     # replicas stay bit-identical
