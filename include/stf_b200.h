@@ -211,6 +211,19 @@ int stf_window_attention(const float *qkv, float *out, const float *bias_table, 
                          int Hp, int Wp, int tf32_out, void *stream);
 
 /* ------------------------------------------------------------------------------------------
+ * Element-wise glue around the cuDNN convolution stacks (the callers either side of the hot path).
+ * ------------------------------------------------------------------------------------------ */
+
+/* x <- act(x + bias[c]) in place on an NHWC (channels_last) fp32 tensor of n elements, c = element index % channels;
+ * act 0 = none, 1 = exact-erf GELU.  Replaces the strided broadcast bias add + GELU launches after every convolution of
+ * the hyperprior / cc_mean / cc_scale / lrp stacks (stf.py:472-548).  channels % 4 == 0. */
+int stf_bias_act(float *x, const float *bias, int channels, int64_t n, int act, void *stream);
+
+/* y = LayerNorm(x) over the C <= 768 channels of M token-major rows (PatchEmbed.norm, stf.py:375-379). */
+int stf_layernorm_fwd(const float *x, const float *gamma, const float *beta, float *y, int64_t M, int C, float eps,
+                      void *stream);
+
+/* ------------------------------------------------------------------------------------------
  * Training step (BASELINE config 5): backward kernels.  The backward GEMMs dX = dY . W are stf_linear calls
  * on the packed transposed weight; weight gradients dW = dY^T . X are plain library GEMMs on the caller's side.
  * Row / window reductions are two-stage and atomic-free: every CTA writes its partial sums to its own slot of

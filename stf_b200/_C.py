@@ -55,6 +55,8 @@ SIGNATURES = {
     "stf_pack_linear": (c_int, [c_vp, c_vp, c_vp, c_vp, c_vp, c_int, c_int, c_int, c_vp]),
     "stf_linear": (c_int, [ctypes.POINTER(LinearArgs), c_vp]),
     "stf_window_attention": (c_int, [c_vp, c_vp, c_vp, c_vp, c_int, c_i64, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_vp]),
+    "stf_bias_act": (c_int, [c_vp, c_vp, c_int, c_i64, c_int, c_vp]),
+    "stf_layernorm_fwd": (c_int, [c_vp, c_vp, c_vp, c_vp, c_i64, c_int, c_f32, c_vp]),
     "stf_attention_bwd_ctas": (c_int, [c_i64, c_int, c_int, ctypes.POINTER(c_int)]),
     "stf_window_attention_bwd": (c_int, [c_vp, c_vp, c_vp, c_vp, c_vp, c_i64, c_int, c_int, c_int, c_int, c_int, c_int, c_f32, c_vp]),
     "stf_layernorm_bwd_ctas": (c_int, [c_i64]),

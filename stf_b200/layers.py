@@ -318,6 +318,27 @@ class PatchEmbed(nn.Module):
         self.proj = nn.Conv2d(in_chans, embed_dim, kernel_size=self.patch_size, stride=self.patch_size)
         self.norm = norm_layer(embed_dim) if norm_layer is not None else None
 
+    def tokens(self, x):
+        """Inference path: the same computation returning token-major (B, Wh*Ww, C) directly.  The NHWC output of the
+        convolution IS the token layout, so the reference's NCHW round trip (two full-tensor copies) disappears; the bias
+        add and the LayerNorm are one vectorised kernel each (torch launches its LayerNorm with one CTA per 48-float row)."""
+        _, _, H, W = x.shape
+        ph, pw = self.patch_size
+        if W % pw != 0:
+            x = F.pad(x, (0, pw - W % pw))
+        if H % ph != 0:
+            x = F.pad(x, (0, 0, 0, ph - H % ph))
+        p = self.proj
+        x = F.conv2d(x.contiguous(memory_format=torch.channels_last), p.weight, None, p.stride, p.padding)
+        x = x.contiguous(memory_format=torch.channels_last)
+        if p.bias is not None:
+            ops.bias_act_(x, p.bias, gelu=False)
+        B, C, Wh, Ww = x.shape
+        t = x.permute(0, 2, 3, 1).reshape(B * Wh * Ww, C)          # a view: channels_last memory is token-major
+        if self.norm is not None:
+            t = ops.layernorm(t, self.norm.weight, self.norm.bias, self.norm.eps)
+        return t.reshape(B, Wh * Ww, C), Wh, Ww
+
     def forward(self, x):
         _, _, H, W = x.shape
         ph, pw = self.patch_size

@@ -120,6 +120,40 @@ def _stack5(c_in):
                          conv(128, 64, stride=1, kernel_size=3), nn.GELU(), conv(64, 32, stride=1, kernel_size=3))
 
 
+def _run_stack(seq, x):
+    """Inference path of a conv stack (nn.Sequential of Conv2d / GELU / subpel Sequential(Conv2d, PixelShuffle)): the
+    convolution is a cuDNN call WITHOUT bias on channels_last data, bias add + exact GELU are one in-place vectorised
+    kernel (ops.bias_act_) instead of torch's strided broadcast add + separate GELU launch (values identical: one fp32 add,
+    torch's GELU formula).  Module tree and checkpoint keys are untouched."""
+    mods = list(seq)
+    i = 0
+    while i < len(mods):
+        m = mods[i]
+        shuffle = None
+        if isinstance(m, nn.Sequential) and len(m) == 2 and isinstance(m[0], nn.Conv2d) and isinstance(m[1], nn.PixelShuffle):
+            conv, shuffle = m[0], m[1]
+        elif isinstance(m, nn.Conv2d):
+            conv = m
+        else:
+            x = m(x)
+            i += 1
+            continue
+        gelu = i + 1 < len(mods) and isinstance(mods[i + 1], nn.GELU)
+        y = F.conv2d(x, conv.weight, None, conv.stride, conv.padding, conv.dilation, conv.groups)
+        if conv.bias is not None and y.shape[1] % 4 == 0:
+            if not y.is_contiguous(memory_format=torch.channels_last):
+                y = y.contiguous(memory_format=torch.channels_last)
+            ops.bias_act_(y, conv.bias, gelu)
+        else:
+            if conv.bias is not None:
+                y = y + conv.bias.reshape(1, -1, 1, 1)
+            if gelu:
+                y = F.gelu(y)
+        x = shuffle(y) if shuffle is not None else y
+        i += 2 if gelu else 1
+    return x
+
+
 class _SliceCodec(CompressionModel):
     """Hyperprior + channel-conditional slice loop shared by STF and WACNN
     (stf.py:600-636, 687-735, 737-779 == cnn.py:144-183, 223-267, 289-327)."""
@@ -176,9 +210,9 @@ class _SliceCodec(CompressionModel):
         side.wait_stream(main)
         with torch.cuda.stream(side):
             scale_support = torch.cat([latent_scales] + support, dim=1)
-            scale = self.cc_scale_transforms[i](scale_support)[:, :, : hw[0], : hw[1]].contiguous()
+            scale = _run_stack(self.cc_scale_transforms[i], scale_support)[:, :, : hw[0], : hw[1]].contiguous()
         mean_support = torch.cat([latent_means] + support, dim=1)
-        mu = self.cc_mean_transforms[i](mean_support)[:, :, : hw[0], : hw[1]].contiguous()
+        mu = _run_stack(self.cc_mean_transforms[i], mean_support)[:, :, : hw[0], : hw[1]].contiguous()
         main.wait_stream(side)
         scale.record_stream(main)
         return mean_support, mu, scale
@@ -192,7 +226,7 @@ class _SliceCodec(CompressionModel):
 
     def _lrp(self, i, mean_support, y_hat_slice):
         y_hat_slice = y_hat_slice.contiguous(memory_format=self._CL)
-        lrp = self.lrp_transforms[i](torch.cat([mean_support, y_hat_slice], dim=1))
+        lrp = _run_stack(self.lrp_transforms[i], torch.cat([mean_support, y_hat_slice], dim=1))
         return y_hat_slice + 0.5 * torch.tanh(lrp)
 
     def _needed_as_support(self, i):
@@ -200,7 +234,7 @@ class _SliceCodec(CompressionModel):
 
     def _hyper_synthesis(self, z_hat):
         z_hat = z_hat.contiguous(memory_format=self._CL)
-        return self.h_scale_s(z_hat), self.h_mean_s(z_hat)
+        return _run_stack(self.h_scale_s, z_hat), _run_stack(self.h_mean_s, z_hat)
 
     def forward(self, x, noise=None):
         """eval / no_grad: the fused inference path.  train() with grad enabled: the training forward of
@@ -248,7 +282,7 @@ class _SliceCodec(CompressionModel):
         self._prepare_inference()
         y = self._analysis(x)
         hw = y.shape[2:]
-        z = self.h_a(y.contiguous(memory_format=self._CL)).contiguous()
+        z = _run_stack(self.h_a, y.contiguous(memory_format=self._CL)).contiguous()
         eb = self.entropy_bottleneck
         z_hat, z_likelihoods, _ = ops.entropy_bottleneck(z, eb.packed_params(), lik_bound=eb._likelihood_bound,
                                                          ste_round=True)
@@ -278,7 +312,7 @@ class _SliceCodec(CompressionModel):
             y = self._analysis(x)
         B, M, h, w = y.shape
         with _phase("enc.hyper"):
-            z = self.h_a(y.contiguous(memory_format=self._CL)).contiguous()
+            z = _run_stack(self.h_a, y.contiguous(memory_format=self._CL)).contiguous()
             # EntropyBottleneck.compress + decompress (stf.py:688-689): decompress(z_strings) is
             # dequantize(symbols, medians), which the same kernel emits -- no need to decode our own stream
             z_hat, _, z_sym = ops.entropy_bottleneck(z, eb.packed_params(), want_lik=False, want_symbols=True)
@@ -589,9 +623,12 @@ class SymmetricalTransFormer(_SliceCodec):
                 nn.init.constant_(m.weight, 1.0)
 
     def _analysis(self, x):
-        t = self.patch_embed(x)
-        Wh, Ww = t.shape[2], t.shape[3]
-        t = t.flatten(2).transpose(1, 2).contiguous()
+        if torch.is_grad_enabled() and self.training:
+            t = self.patch_embed(x)
+            Wh, Ww = t.shape[2], t.shape[3]
+            t = t.flatten(2).transpose(1, 2).contiguous()
+        else:
+            t, Wh, Ww = self.patch_embed.tokens(x)
         for layer in self.layers:
             t, Wh, Ww = layer(t, Wh, Ww)
         C = self.embed_dim * 8
@@ -602,7 +639,19 @@ class SymmetricalTransFormer(_SliceCodec):
         t = y_hat.permute(0, 2, 3, 1).contiguous().reshape(B, Wh * Ww, C)
         for layer in self.syn_layers:
             t, Wh, Ww = layer(t, Wh, Ww)
-        return self.end_conv(t.reshape(B, Wh, Ww, self.embed_dim).permute(0, 3, 1, 2).contiguous())
+        if torch.is_grad_enabled() and self.training:
+            return self.end_conv(t.reshape(B, Wh, Ww, self.embed_dim).permute(0, 3, 1, 2).contiguous())
+        # inference: stay in NHWC end to end (stf.py:466-469 makes three full-size layout copies around the pixel shuffle).
+        # The token-major tensor IS the channels_last image; the pixel shuffle is one NHWC copy; x_hat leaves as NCHW.
+        E = self.embed_dim
+        c0, c2 = self.end_conv[0], self.end_conv[2]
+        v = t.reshape(B, Wh, Ww, E).permute(0, 3, 1, 2)                                  # view, channels_last strides
+        u = F.conv2d(v, c0.weight, None, c0.stride, c0.padding).contiguous(memory_format=self._CL)
+        ops.bias_act_(u, c0.bias, gelu=False)
+        r = c0.out_channels // E                                                          # = patch_size ** 2
+        k = int(round(r ** 0.5))
+        s = u.permute(0, 2, 3, 1).reshape(B, Wh, Ww, E, k, k).permute(0, 1, 4, 2, 5, 3).reshape(B, Wh * k, Ww * k, E)
+        return c2(s.permute(0, 3, 1, 2)).contiguous()
 
 
 class _NonNegativeParametrizer(nn.Module):

@@ -274,6 +274,26 @@ def window_attention_core(qkv, bias_table, num_windows, C, heads, ws, shift, Hp=
     return out
 
 
+def bias_act_(x, bias, gelu):
+    """x <- act(x + bias[c]) in place; x: (B, C, H, W) in channels_last memory format (dense NHWC)."""
+    if not x.is_cuda or x.dtype != torch.float32 or x.dim() != 4 or not x.is_contiguous(memory_format=torch.channels_last):
+        raise ValueError("stf_b200.bias_act_: expected a CUDA fp32 (B, C, H, W) tensor in channels_last format")
+    bias = _dev(bias.detach(), "bias")
+    _launch("bias_act_kernel", 8 * x.numel(), _C.lib().stf_bias_act, x.data_ptr(), bias.data_ptr(), x.shape[1], x.numel(),
+            1 if gelu else 0, _C.stream())
+    return x
+
+
+def layernorm(x, weight, bias, eps):
+    """Token-major LayerNorm: x (M, C) contiguous -> (M, C)."""
+    x = _dev(x, "x")
+    out = torch.empty_like(x)
+    _launch("layernorm_fwd_kernel", 8 * x.numel(), _C.lib().stf_layernorm_fwd, x.data_ptr(),
+            _dev(weight.detach(), "weight").data_ptr(), _dev(bias.detach(), "bias").data_ptr(), out.data_ptr(), x.shape[0],
+            x.shape[1], float(eps), _C.stream())
+    return out
+
+
 _replayed = 0
 
 

@@ -82,3 +82,40 @@ def test_config4_wacnn_clic_size_roundtrip(golden_dir):
     assert dec.shape == (1, 3, 1408, 2048)
     assert float((dec - fwd).abs().max()) < 1e-4
     assert torch.isfinite(dec).all()
+
+
+def test_config5_training_step_full_size_batch_linearity(golden_dir):
+    """BASELINE config 5 at its full size (16 x 256x256, lambda 0.0035).  Size-independent property: the loss is a mean
+    over images, so the gradient of the full batch equals the mean of the gradients of its two halves (same injected
+    noise, drop_path 0) -- which is also what the data-parallel all-reduce relies on."""
+    from stf_b200.models import SymmetricalTransFormer
+    from stf_b200.training import RateDistortionLoss
+    spec = {k: (tuple(s), getattr(torch, d.split(".")[-1])) for k, (s, d) in
+            json.load(open(os.path.join(golden_dir, "stf_spec.json"))).items()}
+    net = SymmetricalTransFormer(drop_path_rate=0.0)
+    torch.nn.Module.load_state_dict(net, synthetic_state_dict(spec, 0), strict=False)
+    net = net.cuda().train()
+    crit = RateDistortionLoss(0.0035)
+    x = synthetic_image(16, 256, 256, seed=4).cuda()
+    g = torch.Generator().manual_seed(9)
+    noise = {"y": (torch.rand(16, 384, 16, 16, generator=g) - 0.5).cuda(), "z": (torch.rand(16, 192, 4, 4, generator=g) - 0.5).cuda()}
+
+    def grads(lo, hi):
+        net.zero_grad(set_to_none=True)
+        out = crit(net(x[lo:hi], noise={k: v[lo:hi] for k, v in noise.items()}), x[lo:hi])
+        out["loss"].backward()
+        return float(out["loss"].detach()), {n: p.grad.detach().clone() for n, p in net.named_parameters() if p.grad is not None}
+
+    l_full, g_full = grads(0, 16)
+    l_a, g_a = grads(0, 8)
+    l_b, g_b = grads(8, 16)
+    assert abs(l_full - 0.5 * (l_a + l_b)) <= 1e-4 * abs(l_full)
+    assert len(g_full) >= 700 and all(torch.isfinite(v).all() for v in g_full.values())
+    worst = 0.0
+    for n, gf in g_full.items():
+        ref = 0.5 * (g_a[n] + g_b[n])
+        scale = float(ref.abs().max())
+        if scale < 1e-12:
+            continue
+        worst = max(worst, float((gf - ref).abs().max()) / scale)
+    assert worst <= 2e-2, worst      # (cuDNN TF32 convolutions may pick per-batch-size algorithms; our kernels are batch-invariant)

@@ -231,3 +231,25 @@ def test_build_indexes_lut_equals_count_on_random_bit_patterns():
     ref2 = (crowded[:-1][None, :] < sig2[:, None]).sum(1).to(torch.int32)
     ref2 = torch.where(torch.isnan(sig2), torch.full_like(ref2, 63), ref2)
     assert torch.equal(ops.build_indexes(s.cuda(), crowded.numpy()).cpu(), ref2)
+
+
+def test_conv_glue_kernels_bias_gelu_and_layernorm():
+    """stf_bias_act == torch's `conv_out + bias` followed by nn.GELU() on channels_last data (same fp32 add, same GELU
+    formula: bit-identical or 1 ulp), stf_layernorm_fwd == F.layer_norm to fp32 round-off."""
+    from stf_b200 import ops
+    g = torch.Generator().manual_seed(2)
+    for (B, C, H, W) in ((3, 224, 8, 12), (2, 32, 5, 7), (1, 48, 16, 24)):
+        x = (3 * torch.randn(B, C, H, W, generator=g)).cuda().contiguous(memory_format=torch.channels_last)
+        b = torch.randn(C, generator=g).cuda()
+        ref = torch.nn.functional.gelu(x + b.reshape(1, -1, 1, 1))
+        got = ops.bias_act_(x.clone(memory_format=torch.channels_last), b, gelu=True)
+        assert float((got - ref).abs().max()) <= 2e-7 * float(ref.abs().max())
+        got2 = ops.bias_act_(x.clone(memory_format=torch.channels_last), b, gelu=False)
+        assert torch.equal(got2, x + b.reshape(1, -1, 1, 1))
+    with pytest.raises(ValueError):
+        ops.bias_act_(torch.randn(2, 8, 4, 4, device="cuda"), torch.zeros(8, device="cuda"), True)   # NCHW-contiguous input
+    for (M, C) in ((1000, 48), (77, 384), (5, 768)):
+        x = (2 * torch.randn(M, C, generator=g) + 1).cuda()
+        w, b = (1 + 0.1 * torch.randn(C, generator=g)).cuda(), (0.1 * torch.randn(C, generator=g)).cuda()
+        ref = torch.nn.functional.layer_norm(x, (C,), w, b, 1e-5)
+        assert float((ops.layernorm(x, w, b, 1e-5) - ref).abs().max()) <= 2e-6 * float(ref.abs().max())
