@@ -134,7 +134,8 @@ enum {
   STF_PREC_TF32 = 0, /* operands rounded to TF32 (10-bit mantissa), one MMA per k-step: ~1e-3 relative per GEMM */
   STF_PREC_FP32 = 1  /* 3xTF32 split: fp32-grade results (~1e-6 relative), three MMAs per k-step            */
 };
-int stf_linear_n_tile(int N);
+int stf_linear_n_tile(int N);                       /* STF_PREC_TF32 */
+int stf_linear_n_tile_prec(int N, int precision);   /* n_tile of the packed image for either precision */
 /* Packed size in floats: (1 + precision) * N*K + 3*N  (STF_PREC_FP32 stores a hi and a lo image per k-block). */
 int64_t stf_packed_linear_floats(int N, int K, int precision);
 int stf_pack_linear(const float *weight, const float *bias, const float *ln_gamma, const float *ln_beta,

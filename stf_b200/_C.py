@@ -51,6 +51,7 @@ SIGNATURES = {
     "stf_gaussian_likelihood": (c_int, [c_vp, c_i64, c_vp, c_vp, c_vp, c_vp, c_int, c_int, c_i64, c_f32, c_f32, c_int, c_vp]),
     "stf_entropy_bottleneck": (c_int, [c_vp, c_vp, c_vp, c_vp, c_vp, c_int, c_int, c_i64, c_f32, c_int, c_vp]),
     "stf_linear_n_tile": (c_int, [c_int]),
+    "stf_linear_n_tile_prec": (c_int, [c_int, c_int]),
     "stf_packed_linear_floats": (c_i64, [c_int, c_int, c_int]),
     "stf_pack_linear": (c_int, [c_vp, c_vp, c_vp, c_vp, c_vp, c_int, c_int, c_int, c_vp]),
     "stf_linear": (c_int, [ctypes.POINTER(LinearArgs), c_vp]),

@@ -31,18 +31,20 @@ bias_act_kernel(float *__restrict__ x, const float *__restrict__ bias, int c4, i
 constexpr int kLnWarps = 8;
 constexpr int kLnMaxPerLane = 24;
 
+// PER = elements per lane (compile time: the row loops are fully unrolled with no dead iterations)
+template <int PER>
 __global__ void __launch_bounds__(kLnWarps * 32)
 layernorm_fwd_kernel(const float *__restrict__ x, const float *__restrict__ gamma, const float *__restrict__ beta,
                      float *__restrict__ y, int64_t M, int C, float eps) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int per = (C + 31) / 32;
+  constexpr int per = PER;
   const float inv_c = 1.0f / (float)C;
   for (int64_t row = (int64_t)blockIdx.x * kLnWarps + warp; row < M; row += (int64_t)gridDim.x * kLnWarps) {
     const float *xr = x + row * C;
-    float v[kLnMaxPerLane];
+    float v[PER];
     float s = 0.f;
 #pragma unroll
-    for (int i = 0; i < kLnMaxPerLane; ++i) {
+    for (int i = 0; i < PER; ++i) {
       const int c = lane + 32 * i;
       v[i] = (i < per && c < C) ? xr[c] : 0.f;
       s += v[i];
@@ -52,7 +54,7 @@ layernorm_fwd_kernel(const float *__restrict__ x, const float *__restrict__ gamm
     const float mean = s * inv_c;
     float q = 0.f;
 #pragma unroll
-    for (int i = 0; i < kLnMaxPerLane; ++i) {
+    for (int i = 0; i < PER; ++i) {
       const int c = lane + 32 * i;
       const float d = (i < per && c < C) ? v[i] - mean : 0.f;
       q = fmaf(d, d, q);
@@ -61,7 +63,7 @@ layernorm_fwd_kernel(const float *__restrict__ x, const float *__restrict__ gamm
     for (int o = 16; o > 0; o >>= 1) q += __shfl_xor_sync(0xffffffffu, q, o);
     const float rstd = rsqrtf(q * inv_c + eps);
 #pragma unroll
-    for (int i = 0; i < kLnMaxPerLane; ++i) {
+    for (int i = 0; i < PER; ++i) {
       const int c = lane + 32 * i;
       if (i < per && c < C) y[row * C + c] = fmaf((v[i] - mean) * rstd, __ldg(gamma + c), __ldg(beta + c));
     }
@@ -94,7 +96,14 @@ extern "C" int stf_layernorm_fwd(const float *x, const float *gamma, const float
   if (C > 32 * kLnMaxPerLane) return STF_E_SHAPE;
   if (M == 0) return STF_OK;
   int64_t blocks = (M + kLnWarps - 1) / kLnWarps;
-  if (blocks > (int64_t)kNumSMs * 8) blocks = (int64_t)kNumSMs * 8;
-  layernorm_fwd_kernel<<<(unsigned)blocks, kLnWarps * 32, 0, (cudaStream_t)stream>>>(x, gamma, beta, y, M, C, eps);
+  if (blocks > (int64_t)kNumSMs * 16) blocks = (int64_t)kNumSMs * 16;
+  const int per = (C + 31) / 32;
+#define STF_LN(P) layernorm_fwd_kernel<P><<<(unsigned)blocks, kLnWarps * 32, 0, (cudaStream_t)stream>>>(x, gamma, beta, y, M, C, eps)
+  if (per <= 2) STF_LN(2);
+  else if (per <= 3) STF_LN(3);
+  else if (per <= 6) STF_LN(6);
+  else if (per <= 12) STF_LN(12);
+  else STF_LN(24);
+#undef STF_LN
   return check_launch();
 }

@@ -89,6 +89,18 @@ struct FastDiv {
   }
 };
 
+// Column tile: the largest divisor of N (multiple of 16) up to 256, in both precision modes.  (Measured: capping the
+// 3xTF32 mode at 192 columns to fit four weight stages instead of two made the K-deep GEMMs 10-35 % slower -- they are
+// bound by the weight stream out of L2, 18 B/clk/SM with every CTA re-reading the whole weight per 128-row tile, not by
+// its latency; the fix is sharing weight tiles across a CTA pair / cluster, not more stages.)
+static int n_tile_for(int N, int precision) {
+  (void)precision;
+  if (N <= 0 || N % 16 != 0) return STF_E_SHAPE;
+  for (int nt = kMaxNTile; nt >= 16; nt -= 16)
+    if (N % nt == 0) return nt;
+  return STF_E_SHAPE;
+}
+
 struct LinearParams {
   stf_linear_args a;
   const float *aux;  // s[N], t[N], b[N] behind the weight image
@@ -539,7 +551,7 @@ linear_tf32_kernel(const __grid_constant__ LinearParams P) {
     int it = 0;
     for (int tile = first_tile; tile < P.total_tiles; tile += tile_step, ++it) {
       const int buf = it & 1;
-      const int mt = tile / P.n_tiles, nt = tile - mt * P.n_tiles;
+      const int mt = P.n_tiles == 1 ? tile : tile / P.n_tiles, nt = tile - mt * P.n_tiles;
       const int row = mt * kTileM + quad * 32 + lane;  // TMEM lane == tile row
       // destination / residual row pointers of this thread's row
       float *dst = nullptr;
@@ -594,6 +606,7 @@ linear_tf32_kernel(const __grid_constant__ LinearParams P) {
         const bool row_store = epi_mode == 1 && epi != STF_EPI_PIXEL_SHUFFLE;
         if (row_store) bulk_wait_read0();  // this thread's previous bulk store has finished reading its staging row
         // ---- phase 1: thread = row.  TMEM -> registers -> math -> staging
+        // (prefetching the next chunk's TMEM load while this one is processed was measured: no gain)
         for (int c = 0; c < slab; c += 16) {
           const int n = n0 + c;
           float4 rv[4];
@@ -871,7 +884,7 @@ int launch_linear(const stf_linear_args *args, void *stream) {
   P.precise = a.precision == STF_PREC_FP32 ? 1 : 0;
   const int planes = P.precise ? 2 : 1;
   P.aux = a.w_packed + (size_t)a.N * a.K * (P.precise ? 2 : 1);
-  P.n_tile = stf_linear_n_tile(a.N);
+  P.n_tile = n_tile_for(a.N, a.precision);
   if (P.n_tile <= 0) return STF_E_SHAPE;
   P.n_tiles = a.N / P.n_tile;
   P.m_tiles = (a.M + kTileM - 1) / kTileM;
@@ -949,6 +962,13 @@ int launch_linear(const stf_linear_args *args, void *stream) {
 #define STF_LINEAR_CASE(E, R, L)                                                                \
   if (plain && a.epilogue == (E) && a.rows == (R) && P.has_ln == (L))                            \
     fn = P.precise ? (KernelFn)linear_tf32_kernel<E, R, L, 1, 0> : (KernelFn)linear_tf32_kernel<E, R, L, 0, 0>;
+#define STF_LINEAR_TRACED(E, R, L)                                                              \
+  if (debug_skip_env == 8 && epi_mode_env == 0 && a.epilogue == (E) && a.rows == (R) && P.has_ln == (L)) \
+    fn = P.precise ? (KernelFn)linear_tf32_kernel<E, R, L, 1, 1> : (KernelFn)linear_tf32_kernel<E, R, L, 0, 1>;
+  STF_LINEAR_TRACED(STF_EPI_QKV, STF_ROWS_WINDOW, 1)            // (tools/trace_linear.py: specialised + clock64 hooks)
+  STF_LINEAR_TRACED(STF_EPI_GELU, STF_ROWS_DENSE, 1)
+  STF_LINEAR_TRACED(STF_EPI_RESIDUAL, STF_ROWS_DENSE, 0)
+#undef STF_LINEAR_TRACED
   STF_LINEAR_CASE(STF_EPI_QKV, STF_ROWS_WINDOW, 1)              // STF block: norm1 + shift + partition + qkv
   STF_LINEAR_CASE(STF_EPI_QKV, STF_ROWS_WINDOW, 0)              // WACNN attention: partition + qkv
   STF_LINEAR_CASE(STF_EPI_QKV, STF_ROWS_DENSE, 0)               // WindowAttention.forward on ready-made windows
@@ -973,11 +993,10 @@ int launch_linear(const stf_linear_args *args, void *stream) {
 
 using namespace stf;
 
-extern "C" int stf_linear_n_tile(int N) {
-  if (N <= 0 || N % 16 != 0) return STF_E_SHAPE;
-  for (int nt = kMaxNTile; nt >= 16; nt -= 16)
-    if (N % nt == 0) return nt;
-  return STF_E_SHAPE;
+extern "C" int stf_linear_n_tile(int N) { return n_tile_for(N, STF_PREC_TF32); }
+extern "C" int stf_linear_n_tile_prec(int N, int precision) {
+  if (precision != STF_PREC_TF32 && precision != STF_PREC_FP32) return STF_E_ARG;
+  return n_tile_for(N, precision);
 }
 
 extern "C" int64_t stf_packed_linear_floats(int N, int K, int precision) {
@@ -991,7 +1010,7 @@ extern "C" int stf_pack_linear(const float *weight, const float *bias, const flo
   if (precision != STF_PREC_TF32 && precision != STF_PREC_FP32) return STF_E_ARG;
   if ((ln_gamma == nullptr) != (ln_beta == nullptr)) return STF_E_ARG;
   if (K % kBlockK != 0) return STF_E_SHAPE;
-  int nt = stf_linear_n_tile(N);
+  int nt = n_tile_for(N, precision);
   if (nt <= 0) return STF_E_SHAPE;
   if (!aligned16(packed)) return STF_E_ALIGN;
   pack_weight_kernel<<<N, 128, 0, (cudaStream_t)stream>>>(weight, bias, ln_gamma, ln_beta, packed, N, K, nt, precision == STF_PREC_FP32 ? 2 : 1);

@@ -1,4 +1,4 @@
 set -x
-timeout 1500 python -m pytest tests -x -q -m gpu -s > gpurun_out/t35.log 2>&1; echo "pytest rc=$?" >> gpurun_out/t35.log
-timeout 900 python bench.py --no-cpu-baseline > gpurun_out/bench35.json 2> gpurun_out/bench35.err
-tail -3 gpurun_out/t35.log; grep -E "fp32 strict|symbol flips" gpurun_out/t35.log; head -c 300 gpurun_out/bench35.json
+timeout 900 python -m pytest tests/test_gpu_swin.py -x -q -m gpu > gpurun_out/t39.log 2>&1; echo "pytest rc=$?" >> gpurun_out/t39.log
+STF_B200_PRECISION=fp32 timeout 300 python tools/bench_ops.py --only linear > gpurun_out/ops39_fp32.log 2>&1
+tail -2 gpurun_out/t39.log; tail -18 gpurun_out/ops39_fp32.log
