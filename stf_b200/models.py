@@ -43,6 +43,7 @@ _EB_MEDIAN = _C.STF_EB_MEDIAN_SLOT
 # device work of the other; measured +4 % at batch 16, +8 % at batch 32).  Below it the per-slice device segments
 # are latency bound (~80 dependent small kernels), so halving the batch does not halve their time.
 _PIPELINE_MIN_BATCH = int(os.environ.get("STF_B200_PIPELINE_MIN_BATCH", "16"))
+_PIPELINE_PARTS = int(os.environ.get("STF_B200_PIPELINE_PARTS", "2"))
 PHASE_TIMES = None   # set to a dict to collect a synchronised wall-clock breakdown (tools/phase_breakdown.py)
 
 
@@ -343,8 +344,9 @@ class _SliceCodec(CompressionModel):
         the device work of the other (the device runs part B while the host codes part A, and vice versa)."""
         if not pipelined or B < _PIPELINE_MIN_BATCH:
             return [(0, B)]
-        k = (B + 1) // 2
-        return [(0, k), (k, B)]
+        n = max(2, min(_PIPELINE_PARTS, B // 8 if B >= 16 else 2))
+        bounds = [round(i * B / n) for i in range(n + 1)]
+        return [(lo, hi) for lo, hi in zip(bounds, bounds[1:]) if hi > lo]
 
     @torch.no_grad()
     def compress(self, x, debug=None):

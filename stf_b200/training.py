@@ -7,8 +7,8 @@
 Data parallelism: one process per GPU, every rank steps on its own images; the only
 collective is the gradient all-reduce (mean) -- 99.86 M fp32 = 399 MB per step for STF.  `GradientAllReduce` does what
 DDP's reducer does for this model: gradients are packed into a few flat fp32 buckets, each bucket is all-reduced with
-NCCL (NVLS / NVLink) asynchronously in reverse registration order, and unpacked -- launched after backward here (the
-backward of this model ends with the largest conv stacks, so there is little left to overlap with).
+NCCL (NVLS / NVLink) asynchronously in reverse registration order -- from post-accumulate hooks inside backward, so the
+transfers overlap the remaining backward work -- and unpacked before the optimizer step.
 """
 import math
 
@@ -47,9 +47,14 @@ def configure_optimizers(net, learning_rate=1e-4, aux_learning_rate=1e-3):
 
 
 class GradientAllReduce:
-    """Bucketed gradient averaging over the data-parallel group (the one collective of the training step)."""
+    """Bucketed gradient averaging over the data-parallel group (the one collective of the training step).
 
-    def __init__(self, params, bucket_mb=100.0, group=None):
+    `attach()` registers post-accumulate hooks: as soon as the last gradient of a bucket has been produced by backward,
+    the bucket is packed and its all-reduce is launched asynchronously, so the transfers of the early buckets (the
+    synthesis transform and the conv stacks, whose gradients come first) run under the rest of the backward pass.
+    `__call__()` after backward launches whatever has not been launched, waits, and writes the averages back."""
+
+    def __init__(self, params, bucket_mb=50.0, group=None):
         self.params = [p for p in params if p.requires_grad]
         self.group = group
         self.buckets, cur, size = [], [], 0
@@ -63,34 +68,63 @@ class GradientAllReduce:
         if cur:
             self.buckets.append(cur)
         self._flat = None
+        self._bucket_of = {id(p): k for k, b in enumerate(self.buckets) for p in b}
+        self._pending = [len(b) for b in self.buckets]
+        self._works = [None] * len(self.buckets)
+        self._hooks = []
 
     def world(self):
         return dist.get_world_size(self.group) if dist.is_available() and dist.is_initialized() else 1
 
-    def __call__(self):
-        """Average .grad over the ranks in place.  Returns the number of bytes all-reduced."""
-        w = self.world()
-        if w == 1:
-            return 0
+    def attach(self):
+        """Overlap mode: launch each bucket's all-reduce from inside backward."""
+        if self._hooks or self.world() == 1:
+            return self
+        for p in self.params:
+            self._hooks.append(p.register_post_accumulate_grad_hook(self._on_grad))
+        return self
+
+    def arm(self):
+        """Call right before the backward pass whose gradients are to be averaged (other backward passes, e.g. the
+        aux loss, leave the counters alone)."""
+        self._pending = [len(b) for b in self.buckets]
+        self._works = [None] * len(self.buckets)
+        self._armed = True
+
+    def _on_grad(self, p):
+        if not getattr(self, "_armed", False):
+            return
+        k = self._bucket_of[id(p)]
+        self._pending[k] -= 1
+        if self._pending[k] == 0:
+            self._launch(k)
+
+    def _launch(self, k):
         if self._flat is None:
             dev = self.params[0].device
             self._flat = [torch.empty(sum(p.numel() for p in b), dtype=torch.float32, device=dev) for b in self.buckets]
-        works, nbytes = [], 0
-        for flat, bucket in zip(self._flat, self.buckets):
-            off = 0
-            for p in bucket:
-                n = p.numel()
-                if p.grad is None:
-                    flat[off:off + n].zero_()
-                else:
-                    flat[off:off + n].copy_(p.grad.reshape(-1))
-                off += n
-            flat.div_(w)
-            works.append(dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=self.group, async_op=True))
-            nbytes += flat.numel() * 4
-        for work, flat, bucket in zip(works, self._flat, self.buckets):
-            work.wait()
-            off = 0
+        flat, off = self._flat[k], 0
+        for p in self.buckets[k]:
+            n = p.numel()
+            if p.grad is None:
+                flat[off:off + n].zero_()
+            else:
+                flat[off:off + n].copy_(p.grad.reshape(-1))
+            off += n
+        flat.div_(self.world())
+        self._works[k] = dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=self.group, async_op=True)
+
+    def __call__(self):
+        """Average .grad over the ranks in place.  Returns the number of bytes all-reduced."""
+        if self.world() == 1:
+            return 0
+        nbytes = 0
+        for k in range(len(self.buckets)):
+            if self._works[k] is None:              # parameters without a gradient this step, or no hooks attached
+                self._launch(k)
+        for k, bucket in enumerate(self.buckets):
+            self._works[k].wait()
+            flat, off = self._flat[k], 0
             for p in bucket:
                 n = p.numel()
                 if p.grad is None:
@@ -98,6 +132,9 @@ class GradientAllReduce:
                 else:
                     p.grad.copy_(flat[off:off + n].reshape(p.shape))
                 off += n
+            nbytes += flat.numel() * 4
+        self._armed = False
+        self._works = [None] * len(self.buckets)
         return nbytes
 
 
@@ -106,6 +143,8 @@ def train_step(net, x, criterion, optimizer, aux_optimizer, reducer=None, clip_m
     optimizer.zero_grad(set_to_none=True)
     aux_optimizer.zero_grad(set_to_none=True)
     out = criterion(net(x) if noise is None else net(x, noise=noise), x)
+    if reducer is not None:
+        reducer.arm()
     out["loss"].backward()
     if reducer is not None:
         reducer()

@@ -100,12 +100,15 @@ def _train_worker(rank, world, port, q):
         x, y = torch.randn(8, 12, generator=g), torch.randn(8, 3, generator=g)
         opt = torch.optim.Adam(net.parameters(), lr=1e-2)
         red = GradientAllReduce(params, bucket_mb=0.0005)      # ~130 floats per bucket: several buckets
+        red.attach()                                           # overlap mode: buckets launched from backward hooks
         assert len(red.buckets) >= 2
         lo, hi = rank * 4, rank * 4 + 4
         for _ in range(2):
             opt.zero_grad()
+            red.arm()
             torch.nn.functional.mse_loss(net(x[lo:hi]), y[lo:hi]).backward()
             nbytes = red()
+            (net[0].weight.sum() * 0.0).backward()              # an unrelated backward (cf. the aux loss) must not disturb it
             opt.step()
         # (numpy, not tensors: tensors travel through the queue as shared-memory handles that die with the worker)
         grads = [p.grad.numpy().copy() for p in net.parameters()]

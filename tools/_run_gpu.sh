@@ -1,4 +1,4 @@
 set -x
-timeout 900 python -m pytest tests/test_gpu_swin.py -x -q -m gpu > gpurun_out/t39.log 2>&1; echo "pytest rc=$?" >> gpurun_out/t39.log
-STF_B200_PRECISION=fp32 timeout 300 python tools/bench_ops.py --only linear > gpurun_out/ops39_fp32.log 2>&1
-tail -2 gpurun_out/t39.log; tail -18 gpurun_out/ops39_fp32.log
+timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29541 bench.py --gpus 2 --steps 5 --warmup 3 > gpurun_out/bench42_n2.json 2> gpurun_out/bench42_n2.err
+timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29542 tools/bench_train.py --gpus 2 > gpurun_out/train42_n2.json 2> gpurun_out/train42_n2.err
+tail -c 300 gpurun_out/bench42_n2.err; head -c 300 gpurun_out/bench42_n2.json; echo; cat gpurun_out/train42_n2.json; tail -c 500 gpurun_out/train42_n2.err

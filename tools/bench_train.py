@@ -65,6 +65,7 @@ def main():
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
+        os.environ.setdefault("NCCL_DEBUG", "WARN")
         dist.init_process_group("nccl", device_id=dev)
     torch.manual_seed(0)                                   # identical replicas on every rank
     net = SymmetricalTransFormer()                          # constructor defaults: drop_path_rate 0.2 live in train()
@@ -72,7 +73,7 @@ def main():
     net = net.to(dev).train()
     opt, aux = configure_optimizers(net, 1e-4, 1e-3)
     crit = RateDistortionLoss(0.0035)
-    red = GradientAllReduce(net.parameters()) if world > 1 else None
+    red = GradientAllReduce(net.parameters()).attach() if world > 1 else None
     n = args.warmup + args.steps
     imgs = [synthetic_image(args.batch, 256, 256, seed=1000 * rank + i).to(dev) for i in range(n)]
     torch.manual_seed(100 + rank)                           # per-rank noise / stochastic-depth streams
@@ -105,7 +106,7 @@ def main():
                 "dtype": "f32 (3xTF32 GEMMs)" if ops.precision() == "fp32" else "tf32", "data": "synthetic",
                 "config": {"workload": f"STF train step, batch {args.batch} x 256x256 per GPU, lambda 0.0035, Adam 1e-4 + aux Adam 1e-3, clip 1.0",
                            "parameters": n_params, "allreduce_bytes_per_step": 4 * n_params if world > 1 else 0,
-                           "collective": "NCCL all-reduce (mean) of all gradients, 100 MB buckets" if world > 1 else "none"},
+                           "collective": "NCCL all-reduce (mean) of all gradients, 50 MB buckets launched from backward hooks" if world > 1 else "none"},
                 "loss": float(out["loss"].detach()), "gpu_launches": ops.launch_count() - l0,
                 "peak_memory_gb": torch.cuda.max_memory_allocated() / 2 ** 30}
         if world == 1 and not args.no_cpu_baseline:
