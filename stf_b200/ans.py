@@ -69,7 +69,14 @@ def encode_array(table: RansTable, symbols, indexes) -> bytes:
 
 
 def default_threads():
-    return max(1, min(32, (os.cpu_count() or 1)))
+    """Host threads of this process for the per-image rANS streams: the cores this process may run on, shared evenly
+    between the ranks of the node (torchrun's LOCAL_WORLD_SIZE) so that N processes do not oversubscribe the host."""
+    try:
+        cores = len(os.sched_getaffinity(0))
+    except (AttributeError, OSError):
+        cores = os.cpu_count() or 1
+    ranks = max(1, int(os.environ.get("LOCAL_WORLD_SIZE", "1") or 1))
+    return max(1, min(32, cores // ranks))
 
 
 def encode_batch(table: RansTable, symbols, indexes, threads=None):

@@ -102,32 +102,63 @@ inline void put_nibble(uint64_t &x, uint32_t *&w, uint32_t val) {
   x = (x << kNibbleBits) | val;
 }
 
+// One symbol of one stream (returns false on an out-of-range index).
+inline bool encode_step(const stf_rans_table *t, int32_t sym, int32_t row, uint64_t &x, uint32_t *&w) {
+  if (row < 0 || row >= t->rows) return false;
+  const int32_t escape = t->sizes[row] - 2;
+  int32_t v = sym - t->offsets[row];
+  if (v >= 0 && v < escape) {
+    put_symbol(x, w, t->enc[t->base[row] + v]);
+    return true;
+  }
+  // escape: staged order is [escape symbol][count nibbles][value nibbles]; emit it reversed
+  uint32_t raw = v < 0 ? (uint32_t)(-2 * v - 1) : (uint32_t)(2 * (v - escape));
+  int32_t nn = 0;
+  while ((raw >> (nn * kNibbleBits)) != 0) ++nn;
+  for (int32_t j = nn - 1; j >= 0; --j) put_nibble(x, w, (raw >> (j * kNibbleBits)) & kNibbleMax);
+  int32_t full = nn / kNibbleMax, rest = nn % kNibbleMax;  // count = 15,15,...,rest
+  put_nibble(x, w, (uint32_t)rest);
+  for (int32_t j = 0; j < full; ++j) put_nibble(x, w, kNibbleMax);
+  put_symbol(x, w, t->enc[t->base[row] + escape]);
+  return true;
+}
+
+inline int64_t encode_finish(uint64_t x, uint32_t *w, uint32_t *buf_end) {
+  *--w = (uint32_t)(x >> 32);  // Rans64EncFlush: low word first in memory
+  *--w = (uint32_t)x;
+  return (int64_t)(buf_end - w) * 4;
+}
+
 int64_t encode_into(const stf_rans_table *t, const int32_t *symbols, const int32_t *indexes, int64_t n,
                     uint32_t *buf_end) {
   uint32_t *w = buf_end;
   uint64_t x = kLow;
-  for (int64_t i = n - 1; i >= 0; --i) {
-    const int32_t row = indexes[i];
-    if (row < 0 || row >= t->rows) return STF_E_ARG;
-    const int32_t escape = t->sizes[row] - 2;
-    int32_t v = symbols[i] - t->offsets[row];
-    if (v >= 0 && v < escape) {
-      put_symbol(x, w, t->enc[t->base[row] + v]);
-      continue;
-    }
-    // escape: staged order is [escape symbol][count nibbles][value nibbles]; emit it reversed
-    uint32_t raw = v < 0 ? (uint32_t)(-2 * v - 1) : (uint32_t)(2 * (v - escape));
-    int32_t nn = 0;
-    while ((raw >> (nn * kNibbleBits)) != 0) ++nn;
-    for (int32_t j = nn - 1; j >= 0; --j) put_nibble(x, w, (raw >> (j * kNibbleBits)) & kNibbleMax);
-    int32_t full = nn / kNibbleMax, rest = nn % kNibbleMax;  // count = 15,15,...,rest
-    put_nibble(x, w, (uint32_t)rest);
-    for (int32_t j = 0; j < full; ++j) put_nibble(x, w, kNibbleMax);
-    put_symbol(x, w, t->enc[t->base[row] + escape]);
+  for (int64_t i = n - 1; i >= 0; --i)
+    if (!encode_step(t, symbols[i], indexes[i], x, w)) return STF_E_ARG;
+  return encode_finish(x, w, buf_end);
+}
+
+// Two independent streams in lockstep: a stream is one serial dependency chain (state -> multiply-high -> state,
+// ~15 cycles per symbol), so a thread that owns two images interleaves them and the core overlaps the two chains.
+// Same bytes as two encode_into calls.
+void encode_into2(const stf_rans_table *t, const int32_t *const sym[2], const int32_t *const idx[2], const int64_t n[2],
+                  uint32_t *const buf_end[2], int64_t nb[2]) {
+  uint32_t *w0 = buf_end[0], *w1 = buf_end[1];
+  uint64_t x0 = kLow, x1 = kLow;
+  int64_t i0 = n[0] - 1, i1 = n[1] - 1;
+  bool ok = true;
+  for (; ok && i0 >= 0 && i1 >= 0; --i0, --i1) {
+    ok = encode_step(t, sym[0][i0], idx[0][i0], x0, w0);
+    ok = encode_step(t, sym[1][i1], idx[1][i1], x1, w1) && ok;
   }
-  *--w = (uint32_t)(x >> 32);  // Rans64EncFlush: low word first in memory
-  *--w = (uint32_t)x;
-  return (int64_t)(buf_end - w) * 4;
+  for (; ok && i0 >= 0; --i0) ok = encode_step(t, sym[0][i0], idx[0][i0], x0, w0);
+  for (; ok && i1 >= 0; --i1) ok = encode_step(t, sym[1][i1], idx[1][i1], x1, w1);
+  if (!ok) {
+    nb[0] = nb[1] = STF_E_ARG;
+    return;
+  }
+  nb[0] = encode_finish(x0, w0, buf_end[0]);
+  nb[1] = encode_finish(x1, w1, buf_end[1]);
 }
 
 inline bool refill(stf_rans_decoder *d, uint64_t &x) {
@@ -144,40 +175,67 @@ inline bool get_nibble(stf_rans_decoder *d, uint64_t &x, int32_t *val) {
   return refill(d, x);
 }
 
+// One symbol of one stream.
+inline int decode_step(stf_rans_decoder *d, const stf_rans_table *t, int32_t row, uint64_t &x, int32_t *out) {
+  if (row < 0 || row >= t->rows) return STF_E_ARG;
+  const uint32_t *cdf = t->cdf.data() + t->cbase[row];
+  const int32_t escape = t->sizes[row] - 2;
+  const uint32_t cum = (uint32_t)x & (kProbScale - 1);
+  uint32_t s = t->lut[(size_t)row * (1 << kLutBits) + (cum >> (kProbBits - kLutBits))];
+  while (cdf[s + 1] <= cum) ++s;
+  const uint32_t start = cdf[s], freq = cdf[s + 1] - start;
+  x = freq * (x >> kProbBits) + cum - start;  // Rans64DecAdvance, rans64.h:126-142
+  if (!refill(d, x)) return STF_E_STREAM;
+  int32_t v = (int32_t)s;
+  if (v == escape) {  // rans_interface.cpp:320-343
+    int32_t nib, nn;
+    if (!get_nibble(d, x, &nib)) return STF_E_STREAM;
+    nn = nib;
+    while (nib == kNibbleMax) {
+      if (!get_nibble(d, x, &nib)) return STF_E_STREAM;
+      nn += nib;
+    }
+    int32_t raw = 0;
+    for (int32_t j = 0; j < nn; ++j) {
+      if (!get_nibble(d, x, &nib)) return STF_E_STREAM;
+      if (j < 8) raw |= nib << (j * kNibbleBits);
+    }
+    v = raw >> 1;
+    v = (raw & 1) ? -v - 1 : v + escape;
+  }
+  *out = v + t->offsets[row];
+  return STF_OK;
+}
+
 int decode_run(stf_rans_decoder *d, const stf_rans_table *t, const int32_t *indexes, int64_t n, int32_t *out) {
   uint64_t x = d->x;
   for (int64_t i = 0; i < n; ++i) {
-    const int32_t row = indexes[i];
-    if (row < 0 || row >= t->rows) return STF_E_ARG;
-    const uint32_t *cdf = t->cdf.data() + t->cbase[row];
-    const int32_t escape = t->sizes[row] - 2;
-    const uint32_t cum = (uint32_t)x & (kProbScale - 1);
-    uint32_t s = t->lut[(size_t)row * (1 << kLutBits) + (cum >> (kProbBits - kLutBits))];
-    while (cdf[s + 1] <= cum) ++s;
-    const uint32_t start = cdf[s], freq = cdf[s + 1] - start;
-    x = freq * (x >> kProbBits) + cum - start;  // Rans64DecAdvance, rans64.h:126-142
-    if (!refill(d, x)) return STF_E_STREAM;
-    int32_t v = (int32_t)s;
-    if (v == escape) {  // rans_interface.cpp:320-343
-      int32_t nib, nn;
-      if (!get_nibble(d, x, &nib)) return STF_E_STREAM;
-      nn = nib;
-      while (nib == kNibbleMax) {
-        if (!get_nibble(d, x, &nib)) return STF_E_STREAM;
-        nn += nib;
-      }
-      int32_t raw = 0;
-      for (int32_t j = 0; j < nn; ++j) {
-        if (!get_nibble(d, x, &nib)) return STF_E_STREAM;
-        if (j < 8) raw |= nib << (j * kNibbleBits);
-      }
-      v = raw >> 1;
-      v = (raw & 1) ? -v - 1 : v + escape;
-    }
-    out[i] = v + t->offsets[row];
+    const int rc = decode_step(d, t, indexes[i], x, out + i);
+    if (rc) return rc;
   }
   d->x = x;
   return STF_OK;
+}
+
+// Two decoders in lockstep (see encode_into2).
+void decode_run2(stf_rans_decoder *const d[2], const stf_rans_table *t, const int32_t *const idx[2], const int64_t n[2],
+                 int32_t *const out[2], int rc[2]) {
+  uint64_t x0 = d[0]->x, x1 = d[1]->x;
+  const int64_t m = n[0] < n[1] ? n[0] : n[1];
+  rc[0] = rc[1] = STF_OK;
+  int64_t i = 0;
+  for (; i < m; ++i) {
+    const int r0 = decode_step(d[0], t, idx[0][i], x0, out[0] + i);
+    const int r1 = decode_step(d[1], t, idx[1][i], x1, out[1] + i);
+    if (r0 | r1) {
+      rc[0] = r0, rc[1] = r1;
+      return;
+    }
+  }
+  for (int64_t j = i; j < n[0] && !rc[0]; ++j) rc[0] = decode_step(d[0], t, idx[0][j], x0, out[0] + j);
+  for (int64_t j = i; j < n[1] && !rc[1]; ++j) rc[1] = decode_step(d[1], t, idx[1][j], x1, out[1] + j);
+  if (!rc[0]) d[0]->x = x0;
+  if (!rc[1]) d[1]->x = x1;
 }
 
 // Persistent worker pool: decode_batch is called once per slice (12-13 times per image batch), so
@@ -342,8 +400,33 @@ extern "C" int stf_rans_encode_batch(const stf_rans_table *t, int count, const i
                                      const int32_t *const *indexes, const int64_t *n, uint8_t *const *out,
                                      const int64_t *out_cap, int64_t *out_lens, int threads) {
   if (!t || count < 0 || !symbols || !indexes || !n || !out || !out_cap || !out_lens) return STF_E_ARG;
-  parallel_for(count, threads,
-               [&](int i) { out_lens[i] = stf_rans_encode(t, symbols[i], indexes[i], n[i], out[i], out_cap[i]); });
+  bool pairable = count > threads && threads >= 1;
+  for (int i = 0; pairable && i < count; ++i)
+    pairable = n[i] >= 0 && symbols[i] && indexes[i] && out[i] && out_cap[i] >= stf_rans_encode_bound(n[i]) &&
+               ((uintptr_t)out[i] & 3u) == 0;
+  if (!pairable) {
+    parallel_for(count, threads,
+                 [&](int i) { out_lens[i] = stf_rans_encode(t, symbols[i], indexes[i], n[i], out[i], out_cap[i]); });
+  } else {  // more images than threads: every task codes two images in lockstep, straight into the callers' buffers
+    parallel_for((count + 1) / 2, threads, [&](int j) {
+      const int a = 2 * j, b = 2 * j + 1;
+      if (b >= count) {
+        out_lens[a] = stf_rans_encode(t, symbols[a], indexes[a], n[a], out[a], out_cap[a]);
+        return;
+      }
+      const int32_t *const sy[2] = {symbols[a], symbols[b]}, *const ix[2] = {indexes[a], indexes[b]};
+      const int64_t nn[2] = {n[a], n[b]};
+      uint32_t *const end[2] = {reinterpret_cast<uint32_t *>(out[a]) + out_cap[a] / 4,
+                                reinterpret_cast<uint32_t *>(out[b]) + out_cap[b] / 4};
+      int64_t nb[2];
+      encode_into2(t, sy, ix, nn, end, nb);
+      for (int k = 0; k < 2; ++k) {
+        const int i = k ? b : a;
+        if (nb[k] > 0) memmove(out[i], reinterpret_cast<uint8_t *>(end[k]) - nb[k], (size_t)nb[k]);
+        out_lens[i] = nb[k];
+      }
+    });
+  }
   for (int i = 0; i < count; ++i)
     if (out_lens[i] < 0) return (int)out_lens[i];
   return STF_OK;
@@ -375,7 +458,26 @@ extern "C" int stf_rans_decode_batch(stf_rans_decoder *const *d, const stf_rans_
                                      int32_t *const *symbols_out, int threads) {
   if (!d || !t || count < 0 || !indexes || !n || !symbols_out) return STF_E_ARG;
   std::vector<int> rc((size_t)count, 0);
-  parallel_for(count, threads, [&](int i) { rc[i] = stf_rans_decode(d[i], t, indexes[i], n[i], symbols_out[i]); });
+  bool pairable = count > threads && threads >= 1;
+  for (int i = 0; pairable && i < count; ++i) pairable = d[i] && n[i] >= 0 && indexes[i] && symbols_out[i];
+  if (!pairable) {
+    parallel_for(count, threads, [&](int i) { rc[i] = stf_rans_decode(d[i], t, indexes[i], n[i], symbols_out[i]); });
+  } else {
+    parallel_for((count + 1) / 2, threads, [&](int j) {
+      const int a = 2 * j, b = 2 * j + 1;
+      if (b >= count) {
+        rc[a] = stf_rans_decode(d[a], t, indexes[a], n[a], symbols_out[a]);
+        return;
+      }
+      stf_rans_decoder *const dd[2] = {d[a], d[b]};
+      const int32_t *const ix[2] = {indexes[a], indexes[b]};
+      const int64_t nn[2] = {n[a], n[b]};
+      int32_t *const oo[2] = {symbols_out[a], symbols_out[b]};
+      int r2[2];
+      decode_run2(dd, t, ix, nn, oo, r2);
+      rc[a] = r2[0], rc[b] = r2[1];
+    });
+  }
   for (int i = 0; i < count; ++i)
     if (rc[i]) return rc[i];
   return STF_OK;

@@ -118,6 +118,22 @@ def test_rans_batch_threads_identical(tables):
         decs.append(d)
     outs = ans.decode_batch(decs, tab, idxs, threads=3)
     assert all(np.array_equal(o, s) for o, s in zip(outs, syms))
+    # more streams than threads: tasks code two streams in lockstep (odd count, unequal lengths, escape-heavy tails)
+    for s in syms:
+        s[-50:] *= 40                                   # far outside the modelled range -> bypass nibbles
+    single = [ans.encode_array(tab, s, i) for s, i in zip(syms[:5], idxs[:5])]
+    for threads in (1, 2):
+        assert ans.encode_batch(tab, syms[:5], idxs[:5], threads=threads) == single
+        decs = []
+        for b in single:
+            d = ans.RansDecoder()
+            d.set_stream(b)
+            decs.append(d)
+        outs = ans.decode_batch(decs, tab, idxs[:5], threads=threads)
+        assert all(np.array_equal(o, s) for o, s in zip(outs, syms[:5]))
+        # a second run of the same decoders continues where the first stopped: nothing left -> stream error
+        with pytest.raises(ValueError):
+            ans.decode_batch(decs, tab, [np.zeros(100000, np.int32) + 63] * 5, threads=threads)
 
 
 def test_rans_error_paths(tables):
