@@ -249,6 +249,11 @@ int stf_layernorm_bwd_ctas(int64_t M);
 int stf_layernorm_bwd(const float *x, const float *g, const float *gamma, const float *beta, const float *res,
                       float *dx, float *xn, float *partials, int64_t M, int C, float eps, void *stream);
 
+/* Column sums of a row-major (M, C) fp32 matrix (the bias gradients db = sum_rows dY): partials is
+ * (stf_colsum_ctas(M), C); C % 4 == 0, C <= 1024. */
+int stf_colsum_ctas(int64_t M);
+int stf_colsum(const float *a, float *partials, int64_t M, int C, void *stream);
+
 /* Exact-erf GELU backward: dpre = dh * (Phi(pre) + pre * phi(pre)); n % 4 == 0. */
 int stf_gelu_bwd(const float *pre, const float *dh, float *dpre, int64_t n, void *stream);
 

@@ -62,6 +62,8 @@ SIGNATURES = {
     "stf_window_attention_bwd": (c_int, [c_vp, c_vp, c_vp, c_vp, c_vp, c_i64, c_int, c_int, c_int, c_int, c_int, c_int, c_f32, c_vp]),
     "stf_layernorm_bwd_ctas": (c_int, [c_i64]),
     "stf_layernorm_bwd": (c_int, [c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_i64, c_int, c_f32, c_vp]),
+    "stf_colsum_ctas": (c_int, [c_i64]),
+    "stf_colsum": (c_int, [c_vp, c_vp, c_i64, c_int, c_vp]),
     "stf_gelu_bwd": (c_int, [c_vp, c_vp, c_vp, c_i64, c_vp]),
     "stf_gaussian_likelihood_train": (c_int, [c_vp, c_vp, c_vp, c_vp, c_vp, c_i64, c_f32, c_f32, c_vp]),
     "stf_gaussian_likelihood_train_bwd": (c_int, [c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_i64, c_f32, c_f32, c_vp]),

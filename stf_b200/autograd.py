@@ -9,21 +9,15 @@ Backward:
   * LayerNorm (+ residual)   stf_layernorm_bwd          (also re-emits LN(x), the wgrad operand)
   * GELU                     stf_gelu_bwd on the pre-activation, which is RECOMPUTED by one more fc1 GEMM
                              (the forward keeps only GELU(h): 4C floats per token instead of 8C)
-  * dW = dY^T . X, db        plain library GEMMs / column sums (torch -> cuBLAS, fp32), as SURVEY section 7 allows
+  * dW = dY^T . X            plain library GEMM (torch -> cuBLAS; TF32 tensor cores by default, see _wgrad_precision)
+  * db = column sums         stf_colsum (two-stage, deterministic)
   * Gaussian likelihood      stf_gaussian_likelihood_train{,_bwd} with the LowerBound gradient rule
 Reductions are two-stage and atomic-free (deterministic gradients).  Windows must tile the feature map (true for
 every training shape of the reference: 256x256 patches); the zero-pad path is inference-only.
 """
-import ctypes
-
 import torch
 
 from . import _C, ops
-
-
-def _transposed_pack(cache, weight):
-    """PackedLinear of W^T (so that stf_linear computes dY . W), cached per parameter version."""
-    return cache.get_t(weight)
 
 
 def window_row_index(B, H, W, ws, shift, device):
@@ -49,6 +43,40 @@ def layernorm_bwd(x, g, gamma, beta, eps, res=None, want_xn=True):
                 part.data_ptr(), M, C, float(eps), _C.stream())
     s = part.sum(0)
     return dx, xn, s[0], s[1]
+
+
+def colsum(a):
+    """Column sums of a contiguous (M, C) matrix (bias gradients), deterministic two-stage reduction."""
+    M, C = a.shape
+    L = _C.lib()
+    if C % 4 or C > 1024:
+        return a.sum(0)
+    ctas = int(L.stf_colsum_ctas(M))
+    part = torch.empty((ctas, C), dtype=torch.float32, device=a.device)
+    ops._launch("colsum_kernel", 4 * M * C, L.stf_colsum, a.data_ptr(), part.data_ptr(), M, C, _C.stream())
+    return part.sum(0)
+
+
+class _wgrad_precision:
+    """dW = dY^T . X is a plain library GEMM (cuBLAS).  By default it may use TF32 tensor cores: the products are summed
+    over 10^4 .. 10^5 token rows, so the 2^-11 operand rounding averages out (measured gradient error vs the fp32
+    reference: < 1e-3 of the tensor's max); STF_B200_WGRAD_FP32=1 keeps cuBLAS in fp32 (SIMT SGEMM, ~8x slower)."""
+    import os as _os
+    _fp32 = _os.environ.get("STF_B200_WGRAD_FP32", "0") == "1"
+
+    def __enter__(self):
+        self.old = torch.backends.cuda.matmul.allow_tf32
+        if not self._fp32:
+            torch.backends.cuda.matmul.allow_tf32 = True
+
+    def __exit__(self, *exc):
+        torch.backends.cuda.matmul.allow_tf32 = self.old
+        return False
+
+
+def wgrad(dy, x):
+    with _wgrad_precision():
+        return dy.t().mm(x)
 
 
 def gelu_bwd(pre, dh):
@@ -103,8 +131,8 @@ class AttentionBranch(torch.autograd.Function):
         # proj: y_w = o . Wp^T + b, scattered to tokens
         d_o = ops.linear(dx1, attn._pp.get_t(wproj), M=B * H * W, rows=_C.ROWS_WINDOW, geom=geom)
         dy_w = dx1.index_select(0, idx)
-        dwproj = dy_w.t().mm(o)
-        dbproj = dx1.sum(0)
+        dwproj = wgrad(dy_w, o)
+        dbproj = colsum(dx1)
         # attention core
         dqkv, dtable = attention_bwd(qkv, d_o, table, B * (H // ws) * (W // ws), C, attn.num_heads, ws, shift, H, W,
                                      attn.scale)
@@ -113,8 +141,8 @@ class AttentionBranch(torch.autograd.Function):
         g = ops.linear(dqkv, attn._pq.get_t(wqkv), epilogue=_C.EPI_WINDOW_RESIDUAL, residual=zeros, geom=geom,
                        out_rows=B * H * W)
         dx, xn, dg1, db1 = layernorm_bwd(x, g, g1, b1, blk.norm1.eps, res=dx1)
-        dwqkv = dqkv.t().mm(xn.index_select(0, idx))
-        dbqkv = dqkv.sum(0)
+        dwqkv = wgrad(dqkv, xn.index_select(0, idx))
+        dbqkv = colsum(dqkv)
         return dx, dg1, db1, dwqkv, dbqkv, dtable, dwproj, dbproj, None, None
 
 
@@ -137,14 +165,14 @@ class MlpBranch(torch.autograd.Function):
         mlp = blk.mlp
         dy = dy.contiguous()
         dh = ops.linear(dy, mlp._p2.get_t(w2))
-        dw2 = dy.t().mm(h)
-        db2 = dy.sum(0)
+        dw2 = wgrad(dy, h)
+        db2 = colsum(dy)
         pre = ops.linear(x, mlp._p1.get(w1, bb1, blk.norm2))          # recompute the fc1 pre-activation
         dpre = gelu_bwd(pre, dh)
         g = ops.linear(dpre, mlp._p1.get_t(w1))
         dx, xn, dg2, dbeta2 = layernorm_bwd(x, g, g2, b2, blk.norm2.eps, res=dy)
-        dw1 = dpre.t().mm(xn)
-        db1 = dpre.sum(0)
+        dw1 = wgrad(dpre, xn)
+        db1 = colsum(dpre)
         return dx, dg2, dbeta2, dw1, db1, dw2, db2, None
 
 

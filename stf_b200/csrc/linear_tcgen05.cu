@@ -978,6 +978,8 @@ int launch_linear(const stf_linear_args *args, void *stream) {
   STF_LINEAR_CASE(STF_EPI_RESIDUAL, STF_ROWS_DENSE, 0)          // fc2 + residual
   STF_LINEAR_CASE(STF_EPI_STORE, STF_ROWS_MERGE, 1)             // PatchMerging
   STF_LINEAR_CASE(STF_EPI_PIXEL_SHUFFLE, STF_ROWS_DENSE, 1)     // PatchSplit
+  STF_LINEAR_CASE(STF_EPI_STORE, STF_ROWS_WINDOW, 0)            // backward: proj input gradient (gathers dx1 by window)
+  STF_LINEAR_CASE(STF_EPI_STORE, STF_ROWS_DENSE, 1)             // backward: recomputed fc1 pre-activation (norm2 + fc1)
 #undef STF_LINEAR_CASE
   {
     cudaError_t e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);  // idempotent, cheap

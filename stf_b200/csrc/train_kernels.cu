@@ -203,13 +203,16 @@ int launch_attn_bwd(const float *qkv, const float *dout, const float *bias_table
 constexpr int kLnWarps = 8;
 constexpr int kLnMaxPerLane = 24;  // C <= 768
 
+// PER = elements per lane (compile time: the row loops are fully unrolled with no dead iterations)
+template <int PER>
 __global__ void __launch_bounds__(kLnWarps * 32)
 layernorm_bwd_kernel(const float *__restrict__ x, const float *__restrict__ g, const float *__restrict__ gamma,
                      const float *__restrict__ beta, const float *__restrict__ res, float *__restrict__ dx,
                      float *__restrict__ xn, float *__restrict__ part, int64_t M, int C, float eps) {
   extern __shared__ float red[];  // [kLnWarps][2][C]
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int per = (C + 31) / 32;
+  constexpr int per = PER;
+  constexpr int kLnMaxPerLane = PER;   // (shadows the global bound inside this instance)
   float gam[kLnMaxPerLane], bet[kLnMaxPerLane], dgam[kLnMaxPerLane], dbet[kLnMaxPerLane];
 #pragma unroll
   for (int i = 0; i < kLnMaxPerLane; ++i) {
@@ -352,6 +355,35 @@ gaussian_train_bwd_kernel(const float *__restrict__ y, const float *__restrict__
   }
 }
 
+// Column sums of a row-major (M, C) matrix (bias gradients), two-stage and atomic-free: CTA b sums its row range into
+// part[b][C].  Threads form (256 / C4) row lanes x C4 float4 columns; consecutive threads read consecutive 16-byte
+// segments of a row.
+__global__ void __launch_bounds__(256)
+colsum_kernel(const float *__restrict__ a, float *__restrict__ part, int64_t M, int C) {
+  extern __shared__ float4 acc_s[];  // [row lanes][C4]
+  const int c4 = C >> 2;
+  const int lanes = 256 / c4;
+  const int col = threadIdx.x % c4, rl = threadIdx.x / c4;
+  const int64_t rows_per_cta = (M + gridDim.x - 1) / gridDim.x;
+  const int64_t r0 = (int64_t)blockIdx.x * rows_per_cta, r1 = r0 + rows_per_cta < M ? r0 + rows_per_cta : M;
+  float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (rl < lanes)
+    for (int64_t r = r0 + rl; r < r1; r += lanes) {
+      const float4 v = ldg_stream(reinterpret_cast<const float4 *>(a + r * C) + col);
+      acc.x += v.x, acc.y += v.y, acc.z += v.z, acc.w += v.w;
+    }
+  if (rl < lanes) acc_s[rl * c4 + col] = acc;
+  __syncthreads();
+  for (int i = threadIdx.x; i < c4; i += blockDim.x) {
+    float4 t = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int l = 0; l < lanes; ++l) {
+      const float4 v = acc_s[l * c4 + i];
+      t.x += v.x, t.y += v.y, t.z += v.z, t.w += v.w;
+    }
+    reinterpret_cast<float4 *>(part + (int64_t)blockIdx.x * C)[i] = t;
+  }
+}
+
 inline unsigned ew_grid(int64_t n, int per_block) {
   int64_t b = (n + per_block - 1) / per_block;
   const int64_t cap = (int64_t)kNumSMs * 16;
@@ -412,8 +444,34 @@ extern "C" int stf_layernorm_bwd(const float *x, const float *g, const float *ga
   if (C > 32 * kLnMaxPerLane) return STF_E_SHAPE;
   if (M == 0) return STF_OK;
   const int ctas = stf_layernorm_bwd_ctas(M);
-  layernorm_bwd_kernel<<<ctas, kLnWarps * 32, (size_t)kLnWarps * 2 * C * 4, (cudaStream_t)stream>>>(
-      x, g, gamma, beta, res, dx, xn, partials, M, C, eps);
+  const int per = (C + 31) / 32;
+#define STF_LNB(P)                                                                                          \
+  layernorm_bwd_kernel<P><<<ctas, kLnWarps * 32, (size_t)kLnWarps * 2 * C * 4, (cudaStream_t)stream>>>( \
+      x, g, gamma, beta, res, dx, xn, partials, M, C, eps)
+  if (per <= 2) STF_LNB(2);
+  else if (per <= 3) STF_LNB(3);
+  else if (per <= 6) STF_LNB(6);
+  else if (per <= 12) STF_LNB(12);
+  else STF_LNB(24);
+#undef STF_LNB
+  return check_launch();
+}
+
+extern "C" int stf_colsum_ctas(int64_t M) {
+  if (M < 0) return STF_E_ARG;
+  int64_t b = (M + 255) / 256;
+  if (b > kNumSMs * 4) b = kNumSMs * 4;
+  return (int)(b < 1 ? 1 : b);
+}
+
+extern "C" int stf_colsum(const float *a, float *partials, int64_t M, int C, void *stream) {
+  if (!a || !partials || M < 0 || C <= 0) return STF_E_ARG;
+  if (C % 4 != 0 || C > 1024 * 4) return STF_E_SHAPE;
+  if (!aligned16(a) || !aligned16(partials)) return STF_E_ALIGN;
+  const int ctas = stf_colsum_ctas(M);
+  const int c4 = C / 4;
+  if (c4 > 256) return STF_E_SHAPE;
+  colsum_kernel<<<ctas, 256, (size_t)(256 / c4) * c4 * 16, (cudaStream_t)stream>>>(a, partials, M, C);
   return check_launch();
 }
 

@@ -44,6 +44,7 @@ _EB_MEDIAN = _C.STF_EB_MEDIAN_SLOT
 # are latency bound (~80 dependent small kernels), so halving the batch does not halve their time.
 _PIPELINE_MIN_BATCH = int(os.environ.get("STF_B200_PIPELINE_MIN_BATCH", "16"))
 _PIPELINE_PARTS = int(os.environ.get("STF_B200_PIPELINE_PARTS", "2"))
+_DEC_PARTS = int(os.environ.get("STF_B200_DEC_PARTS", "0")) or None     # decompress(): sub-batches (default: same as compress)
 PHASE_TIMES = None   # set to a dict to collect a synchronised wall-clock breakdown (tools/phase_breakdown.py)
 
 
@@ -249,7 +250,8 @@ class _SliceCodec(CompressionModel):
 
     def _forward_train(self, x, noise=None):
         from . import autograd as AG
-        y = self._analysis(x)
+        self._prepare_inference()          # conv weights in channels_last (values unchanged): cuDNN runs NHWC fwd and bwd
+        y = self._analysis(x).contiguous(memory_format=self._CL)
         hw = y.shape[2:]
         z = self.h_a(y)
         eb, gc = self.entropy_bottleneck, self.gaussian_conditional
@@ -339,12 +341,12 @@ class _SliceCodec(CompressionModel):
         return self.__dict__.get("cuda_graphs", _GRAPHS_DEFAULT) and PHASE_TIMES is None
 
     @staticmethod
-    def _parts(B, pipelined):
+    def _parts(B, pipelined, n_parts=None):
         """Image ranges coded as independent sub-batches.  Two parts let the host rANS work of one part overlap
         the device work of the other (the device runs part B while the host codes part A, and vice versa)."""
         if not pipelined or B < _PIPELINE_MIN_BATCH:
             return [(0, B)]
-        n = max(2, min(_PIPELINE_PARTS, B // 8 if B >= 16 else 2))
+        n = max(2, min(n_parts or _PIPELINE_PARTS, B // 8 if B >= 16 else 2))
         bounds = [round(i * B / n) for i in range(n + 1)]
         return [(lo, hi) for lo, hi in zip(bounds, bounds[1:]) if hi > lo]
 
@@ -483,7 +485,7 @@ class _SliceCodec(CompressionModel):
             pass
 
         parts = []
-        for slot, (lo, hi) in enumerate(self._parts(B, use_graphs)):
+        for slot, (lo, hi) in enumerate(self._parts(B, use_graphs, _DEC_PARTS)):
             p = Part()
             p.B = hi - lo
             p.segs, p.st = self._decode_plan(slot, p.B, C, zh, zw, device) if use_graphs else (None, {"hw": (h, w)})

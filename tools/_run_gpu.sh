@@ -1,4 +1,3 @@
-timeout 300 python tools/split_times.py --batch 32
-STF_B200_PIPELINE_MIN_BATCH=1000 timeout 300 python tools/split_times.py --batch 32
-timeout 300 python tools/split_times.py --batch 16
-nproc; lscpu | grep -E "Model name|^CPU\(s\)|Thread"
+timeout 900 python -m pytest tests/test_gpu_train.py tests/test_gpu_configs.py -x -q -m gpu -s > gpurun_out/t47.log 2>&1; echo "pytest rc=$?" >> gpurun_out/t47.log
+timeout 600 python tools/bench_train.py > gpurun_out/train47_n1.json 2> gpurun_out/train47_n1.err
+tail -3 gpurun_out/t47.log; grep -E "training step|linearity" gpurun_out/t47.log; cat gpurun_out/train47_n1.json | head -c 300
