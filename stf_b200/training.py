@@ -139,7 +139,9 @@ class GradientAllReduce:
 
 
 def train_step(net, x, criterion, optimizer, aux_optimizer, reducer=None, clip_max_norm=1.0, noise=None):
-    """One step of train.py:135-150.  Returns the criterion dict (+ "aux_loss")."""
+    """One step of train.py:135-150.  Returns the criterion dict (+ "aux_loss").  `net` may be the bare model (with an
+    optional GradientAllReduce `reducer`) or the model wrapped in torch DistributedDataParallel, as in train.py:363 (the
+    custom autograd functions produce ordinary .grad tensors, so DDP's bucketed, overlapped all-reduce applies)."""
     optimizer.zero_grad(set_to_none=True)
     aux_optimizer.zero_grad(set_to_none=True)
     out = criterion(net(x) if noise is None else net(x, noise=noise), x)
@@ -151,7 +153,7 @@ def train_step(net, x, criterion, optimizer, aux_optimizer, reducer=None, clip_m
     if clip_max_norm > 0:
         torch.nn.utils.clip_grad_norm_(net.parameters(), clip_max_norm)
     optimizer.step()
-    aux = net.aux_loss()
+    aux = (net.module if hasattr(net, "module") else net).aux_loss()
     aux.backward()
     # (the aux loss depends on the replicated parameters only: its gradient is identical on every rank, no collective)
     aux_optimizer.step()

@@ -51,6 +51,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--batch", type=int, default=16)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--reducer", default="buckets", choices=["ddp", "buckets"],
+                    help="N > 1: torch DistributedDataParallel (train.py:363) or stf_b200.training.GradientAllReduce")
     args = ap.parse_args()
     import torch
     import torch.distributed as dist
@@ -73,7 +75,13 @@ def main():
     net = net.to(dev).train()
     opt, aux = configure_optimizers(net, 1e-4, 1e-3)
     crit = RateDistortionLoss(0.0035)
-    red = GradientAllReduce(net.parameters()).attach() if world > 1 else None
+    red, model = None, net
+    if world > 1 and args.reducer == "buckets":
+        red = GradientAllReduce(net.parameters()).attach()
+    elif world > 1:
+        net._prepare_inference()     # conv weights to channels_last BEFORE DDP fixes its bucket-view strides
+        model = torch.nn.parallel.DistributedDataParallel(net, device_ids=[local], bucket_cap_mb=50,
+                                                          gradient_as_bucket_view=True)
     n = args.warmup + args.steps
     imgs = [synthetic_image(args.batch, 256, 256, seed=1000 * rank + i).to(dev) for i in range(n)]
     torch.manual_seed(100 + rank)                           # per-rank noise / stochastic-depth streams
@@ -84,13 +92,13 @@ def main():
         torch.cuda.synchronize()
 
     for i in range(args.warmup):
-        out = train_step(net, imgs[i], crit, opt, aux, red)
+        out = train_step(model, imgs[i], crit, opt, aux, red)
     barrier()
     l0 = ops.launch_count()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     for i in range(args.warmup, n):
-        out = train_step(net, imgs[i], crit, opt, aux, red)
+        out = train_step(model, imgs[i], crit, opt, aux, red)
     e1.record()
     barrier()
     ms = e0.elapsed_time(e1)
@@ -106,7 +114,9 @@ def main():
                 "dtype": "f32 (3xTF32 GEMMs)" if ops.precision() == "fp32" else "tf32", "data": "synthetic",
                 "config": {"workload": f"STF train step, batch {args.batch} x 256x256 per GPU, lambda 0.0035, Adam 1e-4 + aux Adam 1e-3, clip 1.0",
                            "parameters": n_params, "allreduce_bytes_per_step": 4 * n_params if world > 1 else 0,
-                           "collective": "NCCL all-reduce (mean) of all gradients, 50 MB buckets launched from backward hooks" if world > 1 else "none"},
+                           "collective": ("NCCL all-reduce (mean) of all gradients, 50 MB buckets, " +
+                                          ("torch DDP reducer (overlapped with backward)" if args.reducer == "ddp" else
+                                           "GradientAllReduce hooks")) if world > 1 else "none"},
                 "loss": float(out["loss"].detach()), "gpu_launches": ops.launch_count() - l0,
                 "peak_memory_gb": torch.cuda.max_memory_allocated() / 2 ** 30}
         if world == 1 and not args.no_cpu_baseline:
