@@ -297,6 +297,8 @@ int stf_rans_encode_batch(const stf_rans_table *t, int count, const int32_t *con
 /* RansDecoder (rans_interface.cpp:277-350): set_stream + repeated decode_stream calls. */
 typedef struct stf_rans_decoder stf_rans_decoder;
 stf_rans_decoder *stf_rans_decoder_create(const uint8_t *stream, int64_t nbytes);
+/* Zero-copy variant: `stream` must stay alive and unchanged until stf_rans_decoder_destroy. */
+stf_rans_decoder *stf_rans_decoder_create_view(const uint8_t *stream, int64_t nbytes);
 void stf_rans_decoder_destroy(stf_rans_decoder *d);
 int stf_rans_decode(stf_rans_decoder *d, const stf_rans_table *t, const int32_t *indexes,
                     int64_t n, int32_t *symbols_out);

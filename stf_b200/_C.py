@@ -74,6 +74,7 @@ SIGNATURES = {
     "stf_rans_encode_batch": (c_int, [c_vp, c_int, ctypes.POINTER(c_vp), ctypes.POINTER(c_vp), ctypes.POINTER(c_i64),
                                       ctypes.POINTER(c_vp), ctypes.POINTER(c_i64), ctypes.POINTER(c_i64), c_int]),
     "stf_rans_decoder_create": (c_vp, [c_vp, c_i64]),
+    "stf_rans_decoder_create_view": (c_vp, [c_vp, c_i64]),
     "stf_rans_decoder_destroy": (None, [c_vp]),
     "stf_rans_decode": (c_int, [c_vp, c_vp, c_vp, c_i64, c_vp]),
     "stf_rans_decode_batch": (c_int, [ctypes.POINTER(c_vp), c_vp, c_int, ctypes.POINTER(c_vp), ctypes.POINTER(c_i64),

@@ -137,8 +137,9 @@ class RansDecoder:
 
     def set_stream(self, encoded: bytes):
         self._close()
-        buf = np.frombuffer(bytes(encoded), dtype=np.uint8)
-        self._h = _C.lib().stf_rans_decoder_create(buf.ctypes.data, buf.size)
+        buf = np.frombuffer(encoded if isinstance(encoded, bytes) else bytes(encoded), dtype=np.uint8)
+        self._buf = buf                      # zero-copy: the decoder reads the caller's bytes object in place
+        self._h = _C.lib().stf_rans_decoder_create_view(buf.ctypes.data, buf.size)
         if not self._h:
             raise ValueError("invalid rANS stream (need a multiple of 4 bytes, at least 8)")
 

@@ -445,6 +445,20 @@ extern "C" stf_rans_decoder *stf_rans_decoder_create(const uint8_t *stream, int6
   return d;
 }
 
+// Same, without copying the stream: the caller keeps `stream` alive and unchanged for the decoder's lifetime
+// (a batch of 32 Kodak-size y-strings is 19 MB of memcpy otherwise).  Unaligned buffers fall back to the copy.
+extern "C" stf_rans_decoder *stf_rans_decoder_create_view(const uint8_t *stream, int64_t nbytes) {
+  if (!stream || nbytes < 8 || (nbytes & 3)) return nullptr;
+  if ((uintptr_t)stream & 3u) return stf_rans_decoder_create(stream, nbytes);
+  stf_rans_decoder *d = new (std::nothrow) stf_rans_decoder;
+  if (!d) return nullptr;
+  d->w = reinterpret_cast<const uint32_t *>(stream);
+  d->end = d->w + nbytes / 4;
+  d->x = (uint64_t)d->w[0] | ((uint64_t)d->w[1] << 32);
+  d->w += 2;
+  return d;
+}
+
 extern "C" void stf_rans_decoder_destroy(stf_rans_decoder *d) { delete d; }
 
 extern "C" int stf_rans_decode(stf_rans_decoder *d, const stf_rans_table *t, const int32_t *indexes, int64_t n,

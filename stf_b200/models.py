@@ -390,10 +390,19 @@ class _SliceCodec(CompressionModel):
                 debug.update(symbols=sym_h.clone(), indexes=idx_h.clone(), z_symbols=zsym_h.clone())
             with _phase("enc.rans"):
                 s_np, i_np, z_np = sym_h.numpy(), idx_h.numpy(), zsym_h.numpy()
-                z_idx = eb._build_indexes(zshape).reshape(Bp, -1).numpy()
+                z_idx = self._z_indexes(tuple(zshape))
                 y_strings += ans.encode_batch(y_table, [s_np[b] for b in range(Bp)], [i_np[b] for b in range(Bp)])
                 z_strings += ans.encode_batch(z_table, [z_np[b] for b in range(Bp)], [z_idx[b] for b in range(Bp)])
         return {"strings": [y_strings, z_strings], "shape": torch.Size(zshape[-2:])}
+
+    def _z_indexes(self, zshape):
+        """EntropyBottleneck._build_indexes(size) as a cached (B, C*h*w) int32 numpy array (channel ids; entropy_models.py:517-522)."""
+        cache = self.__dict__.setdefault("_z_idx_cache", {})
+        if zshape not in cache:
+            if len(cache) >= 8:
+                cache.clear()
+            cache[zshape] = self.entropy_bottleneck._build_indexes(zshape).reshape(zshape[0], -1).numpy().copy()
+        return cache[zshape]
 
     def _host_buffers(self, tag, B, n):
         """Pinned int32 staging buffer pair, cached per (tag, shape): cudaHostAlloc is slow."""
@@ -495,7 +504,7 @@ class _SliceCodec(CompressionModel):
             p.ev = torch.cuda.Event()
             with _phase("dec.hyper"):
                 z_np = p.zsym_h.numpy()
-                z_idx = eb._build_indexes((p.B, C, zh, zw)).reshape(p.B, -1).numpy()
+                z_idx = self._z_indexes((p.B, C, zh, zw))
                 ans.decode_batch(_decoders(strings[1][lo:hi]), z_table, [z_idx[b] for b in range(p.B)],
                                  outs=[z_np[b] for b in range(p.B)])
                 if use_graphs:
