@@ -244,6 +244,145 @@ window_attention16_kernel(const float *__restrict__ qkv, float *__restrict__ out
   }
 }
 
+// ---------------------------------------------------------------------------------------------
+// 64-token windows (WACNN's first attention block: 8x8 windows, 8 heads of 24 channels): one CTA per window.
+// The window's 64 qkv rows are one contiguous block (64 * 3C floats = 147 KB at C = 192) fetched with a single bulk
+// TMA copy; thread = (head, query row) works out of shared memory with an ONLINE softmax over chunks of 8 keys
+// (running maximum / denominator, accumulator rescaled once per chunk) so that no 64-entry score array lives in
+// registers; outputs overwrite the thread's own q slot and leave with one bulk store per token row.
+// (The global-memory variant above ran at 7 % of the HBM roofline on the 2048x1408 WACNN configuration.)
+// ---------------------------------------------------------------------------------------------
+template <int D>
+__global__ void __launch_bounds__(512)
+window_attention64_kernel(const float *__restrict__ qkv, float *__restrict__ out,
+                          const float *__restrict__ bias_table, const float *__restrict__ mask, int mask_windows,
+                          int64_t num_windows, int C, int heads, int shift, int Hp, int Wp, int tf32_out) {
+  constexpr int WS = 8, N = 64, R = 2 * WS - 1;
+  extern __shared__ __align__(128) float tile[];  // [64][3C] then the bias table [R*R][heads]
+  __shared__ __align__(8) uint64_t bar;
+  const int ld = 3 * C;
+  const int64_t win = blockIdx.x;
+  float *tbl = tile + (size_t)N * ld;
+  const uint32_t bytes = (uint32_t)(N * ld * 4);
+  if (threadIdx.x == 0) {
+    sm100::mbar_init(&bar, 1);
+    sm100::mbar_fence_init();
+    sm100::mbar_arrive_expect_tx(&bar, bytes);
+    sm100::bulk_copy_g2s(tile, qkv + win * N * (int64_t)ld, bytes, &bar);
+  }
+  for (int i = threadIdx.x; i < R * R * heads; i += blockDim.x) tbl[i] = __ldg(bias_table + i);
+  __syncthreads();  // barrier initialised + bias table staged
+  sm100::mbar_wait(&bar, 0);
+
+  const int n = threadIdx.x % N;
+  const int head = threadIdx.x / N;
+  if (head < heads) {
+    float *base = tile + head * D;
+    float q[D], o[D];
+#pragma unroll
+    for (int j = 0; j < D; j += 4) {
+      const float4 v = *reinterpret_cast<const float4 *>(base + n * ld + j);
+      q[j] = v.x, q[j + 1] = v.y, q[j + 2] = v.z, q[j + 3] = v.w;
+    }
+#pragma unroll
+    for (int j = 0; j < D; ++j) o[j] = 0.f;
+    const int hn = n / WS, wn = n % WS;
+    int my_label = 0, wy = 0, wx = 0;
+    if (shift > 0) {
+      const int nWw = Wp / WS, nW = (Hp / WS) * nWw;
+      const int wi = (int)(win % nW);
+      wy = wi / nWw, wx = wi - wy * nWw;
+      const int hs = wy * WS + hn, wsft = wx * WS + wn;
+      my_label = 3 * (hs < Hp - WS ? 0 : (hs < Hp - shift ? 1 : 2)) + (wsft < Wp - WS ? 0 : (wsft < Wp - shift ? 1 : 2));
+    }
+    const float *kbase = base + C, *vbase = base + 2 * C;
+    float run_max = -INFINITY, denom = 0.f;
+    for (int m0 = 0; m0 < N; m0 += 8) {
+      float s[8];
+      float cmax = -INFINITY;
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        const int m = m0 + u;
+        float acc = 0.f;
+#pragma unroll
+        for (int j = 0; j < D; j += 4) {
+          const float4 kv = *reinterpret_cast<const float4 *>(kbase + m * ld + j);
+          acc = fmaf(q[j], kv.x, acc);
+          acc = fmaf(q[j + 1], kv.y, acc);
+          acc = fmaf(q[j + 2], kv.z, acc);
+          acc = fmaf(q[j + 3], kv.w, acc);
+        }
+        const int hm = m / WS, wm = m % WS;
+        acc += tbl[((hn - hm + WS - 1) * R + (wn - wm + WS - 1)) * heads + head];
+        if (shift > 0) {
+          const int hs = wy * WS + hm, wsft = wx * WS + wm;
+          const int lab = 3 * (hs < Hp - WS ? 0 : (hs < Hp - shift ? 1 : 2)) + (wsft < Wp - WS ? 0 : (wsft < Wp - shift ? 1 : 2));
+          if (lab != my_label) acc += kMaskValue;
+        }
+        if (mask) acc += __ldg(mask + ((int64_t)(win % mask_windows) * N + n) * N + m);
+        s[u] = acc;
+        cmax = fmaxf(cmax, acc);
+      }
+      const float new_max = fmaxf(run_max, cmax);
+      const float scale = expf(run_max - new_max);   // exp(-inf) = 0 on the first chunk
+      denom *= scale;
+#pragma unroll
+      for (int j = 0; j < D; ++j) o[j] *= scale;
+      run_max = new_max;
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        const float p = expf(s[u] - run_max);
+        denom += p;
+        const int m = m0 + u;
+#pragma unroll
+        for (int j = 0; j < D; j += 4) {
+          const float4 vv = *reinterpret_cast<const float4 *>(vbase + m * ld + j);
+          o[j] = fmaf(p, vv.x, o[j]);
+          o[j + 1] = fmaf(p, vv.y, o[j + 1]);
+          o[j + 2] = fmaf(p, vv.z, o[j + 2]);
+          o[j + 3] = fmaf(p, vv.w, o[j + 3]);
+        }
+      }
+    }
+    const float inv = 1.0f / denom;
+    // the q slot (row n, this head's columns) is read by this thread only: reuse it for the output
+#pragma unroll
+    for (int j = 0; j < D; j += 4) {
+      const float4 r = make_float4(o[j] * inv, o[j + 1] * inv, o[j + 2] * inv, o[j + 3] * inv);
+      *reinterpret_cast<float4 *>(base + n * ld + j) =
+          tf32_out ? make_float4(round_tf32(r.x), round_tf32(r.y), round_tf32(r.z), round_tf32(r.w)) : r;
+    }
+  }
+  sm100::fence_proxy_async_smem();
+  __syncthreads();
+  if ((int)threadIdx.x < N) {  // one bulk store per token row: first C floats of the staged row -> out row
+    const int r = threadIdx.x;
+    const uint32_t src = sm100::smem_u32(tile + (size_t)r * ld);
+    float *dst = out + (win * N + r) * (int64_t)C;
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst), "r"(src), "r"((uint32_t)(C * 4))
+                 : "memory");
+    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+    asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+  }
+}
+
+template <int D>
+int launch64(const float *qkv, float *out, const float *bias_table, const float *mask, int mask_windows,
+             int64_t num_windows, int C, int heads, int shift, int Hp, int Wp, int tf32_out, cudaStream_t st) {
+  const size_t smem = (size_t)64 * 3 * C * 4 + (size_t)15 * 15 * heads * 4;
+  if (heads * 64 > 512 || smem > 220 * 1024) return -100;   // not this variant: the caller falls back to the generic kernel
+  static std::atomic<int> attr_set{0};
+  if (!attr_set.load(std::memory_order_acquire)) {
+    cudaError_t e = cudaFuncSetAttribute(window_attention64_kernel<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
+    if (e != cudaSuccess) return (int)e;
+    attr_set.store(1, std::memory_order_release);
+  }
+  if (num_windows > 0x7fffffffLL) return STF_E_SHAPE;
+  window_attention64_kernel<D><<<(unsigned)num_windows, heads * 64, smem, st>>>(qkv, out, bias_table, mask, mask_windows,
+                                                                               num_windows, C, heads, shift, Hp, Wp, tf32_out);
+  return check_launch();
+}
+
 template <int D>
 int launch16(const float *qkv, float *out, const float *bias_table, const float *mask, int mask_windows,
              int64_t num_windows, int C, int heads, int shift, int Hp, int Wp, int tf32_out, cudaStream_t st) {
@@ -305,6 +444,16 @@ extern "C" int stf_window_attention(const float *qkv, float *out, const float *b
   CASE16(32);
   CASE16(40);
 #undef CASE16
+#define CASE64(D_)                                                                                               \
+  if (ws == 8 && d == D_) {                                                                                      \
+    const int rc = launch64<D_>(qkv, out, bias_table, mask, mask_windows, num_windows, C, heads, shift, Hp, Wp, tf32_out, st); \
+    if (rc != -100) return rc;                                                                                   \
+  }
+  CASE64(16);
+  CASE64(24);
+  CASE64(32);
+  CASE64(40);
+#undef CASE64
   CASE(8, 16);
   CASE(8, 24);
   CASE(8, 32);
