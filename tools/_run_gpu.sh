@@ -1,3 +1,3 @@
-timeout 1500 python -m pytest tests -x -q -m gpu > gpurun_out/t55.log 2>&1; echo "pytest rc=$?" >> gpurun_out/t55.log
-timeout 600 python tools/bench_forward.py > gpurun_out/fwd55.json 2> gpurun_out/fwd55.err
-tail -3 gpurun_out/t55.log; cat gpurun_out/fwd55.json | head -c 400; tail -c 300 gpurun_out/fwd55.err
+nproc; free -g | head -2 | tail -1
+timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 --master-port 29561 bench.py --gpus 8 --steps 3 --warmup 3 > gpurun_out/bench56_n8.json 2> gpurun_out/bench56_n8.err
+grep "^{" gpurun_out/bench56_n8.json | head -c 500; tail -c 400 gpurun_out/bench56_n8.err
