@@ -231,12 +231,13 @@ int stf_layernorm_fwd(const float *x, const float *gamma, const float *beta, flo
  * `partials`, the caller adds the slots in a fixed order (deterministic gradients).
  * ------------------------------------------------------------------------------------------ */
 
-/* Backward of stf_window_attention for 4x4 windows (autograd of stf.py:100-118):
+/* Backward of stf_window_attention for 4x4 and 8x8 windows (autograd of stf.py:100-118 / layers/win_attention.py:94-112):
  *   dqkv (num_windows*16, 3C): [dq * q_scale | dk | dv]   (q in `qkv` is the pre-scaled q the forward consumed;
  *   dq is returned already multiplied by q_scale = d(q_scaled)/d(q), so dqkv is the gradient of the qkv Linear output)
- *   dbias_partials: (stf_attention_bwd_ctas(...), (2*ws-1)^2, heads) partial sums of d relative_position_bias_table.
+ *   dbias_partials: (stf_attention_bwd_slots(...), (2*ws-1)^2, heads) partial sums of d relative_position_bias_table.
  * stf_attention_bwd_ctas returns the number of partial slots (CTAs) for a problem size. */
-int stf_attention_bwd_ctas(int64_t num_windows, int C, int heads, int *windows_per_cta_out);
+int stf_attention_bwd_ctas(int64_t num_windows, int C, int heads, int *windows_per_cta_out);   /* ws = 4 */
+int stf_attention_bwd_slots(int64_t num_windows, int C, int heads, int ws);   /* partial slots for ws = 4 or 8 */
 int stf_window_attention_bwd(const float *qkv, const float *dout, const float *bias_table, float *dqkv,
                              float *dbias_partials, int64_t num_windows, int C, int heads, int ws, int shift,
                              int Hp, int Wp, float q_scale, void *stream);

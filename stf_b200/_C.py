@@ -59,6 +59,7 @@ SIGNATURES = {
     "stf_bias_act": (c_int, [c_vp, c_vp, c_int, c_i64, c_int, c_vp]),
     "stf_layernorm_fwd": (c_int, [c_vp, c_vp, c_vp, c_vp, c_i64, c_int, c_f32, c_vp]),
     "stf_attention_bwd_ctas": (c_int, [c_i64, c_int, c_int, ctypes.POINTER(c_int)]),
+    "stf_attention_bwd_slots": (c_int, [c_i64, c_int, c_int, c_int]),
     "stf_window_attention_bwd": (c_int, [c_vp, c_vp, c_vp, c_vp, c_vp, c_i64, c_int, c_int, c_int, c_int, c_int, c_int, c_f32, c_vp]),
     "stf_layernorm_bwd_ctas": (c_int, [c_i64]),
     "stf_layernorm_bwd": (c_int, [c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_i64, c_int, c_f32, c_vp]),

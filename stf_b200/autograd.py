@@ -88,9 +88,9 @@ def gelu_bwd(pre, dh):
 
 def attention_bwd(qkv, d_o, table, num_windows, C, heads, ws, shift, Hp, Wp, q_scale):
     L = _C.lib()
-    ctas = int(L.stf_attention_bwd_ctas(num_windows, C, heads, None))
+    ctas = int(L.stf_attention_bwd_slots(num_windows, C, heads, ws))
     if ctas < 0:
-        _C.check(ctas, "stf_attention_bwd_ctas")
+        _C.check(ctas, "stf_attention_bwd_slots")
     dqkv = torch.empty_like(qkv)
     part = torch.empty((ctas, (2 * ws - 1) ** 2, heads), dtype=torch.float32, device=qkv.device)
     ops._launch("window_attention16_bwd_kernel", 4 * qkv.shape[0] * 7 * C, L.stf_window_attention_bwd, qkv.data_ptr(),
@@ -110,7 +110,8 @@ class AttentionBranch(torch.autograd.Function):
                                       f"({H}x{W} vs window {ws}); the zero-pad path is inference-only")
         C = x.shape[1]
         attn = blk.attn
-        qkv = ops.linear(x, attn.packed_qkv(blk.norm1), M=B * H * W, rows=_C.ROWS_WINDOW, epilogue=_C.EPI_QKV,
+        norm1 = getattr(blk, "norm1", None)           # WinBasedAttention (WACNN) has no LayerNorm in front of qkv
+        qkv = ops.linear(x, attn.packed_qkv(norm1), M=B * H * W, rows=_C.ROWS_WINDOW, epilogue=_C.EPI_QKV,
                          q_cols=C, q_scale=attn.scale, geom=geom)
         o = ops.window_attention_core(qkv, table, B * (H // ws) * (W // ws), C, attn.num_heads, ws, shift, H, W)
         x1 = ops.linear(o, attn.packed_proj(), epilogue=_C.EPI_WINDOW_RESIDUAL, residual=x, geom=geom,
@@ -136,6 +137,12 @@ class AttentionBranch(torch.autograd.Function):
         # attention core
         dqkv, dtable = attention_bwd(qkv, d_o, table, B * (H // ws) * (W // ws), C, attn.num_heads, ws, shift, H, W,
                                      attn.scale)
+        if g1 is None:
+            # no LayerNorm: the qkv input gradient lands in token order on top of the shortcut gradient directly
+            dx = ops.linear(dqkv, attn._pq.get_t(wqkv), epilogue=_C.EPI_WINDOW_RESIDUAL, residual=dx1, geom=geom,
+                            out_rows=B * H * W)
+            dwqkv = wgrad(dqkv, x.index_select(0, idx))
+            return dx, None, None, dwqkv, colsum(dqkv), dtable, dwproj, dbproj, None, None
         # qkv Linear (window-ordered rows -> token order) then LayerNorm 1, plus the shortcut gradient
         zeros = torch.zeros_like(x)
         g = ops.linear(dqkv, attn._pq.get_t(wqkv), epilogue=_C.EPI_WINDOW_RESIDUAL, residual=zeros, geom=geom,

@@ -177,6 +177,143 @@ window_attention16_bwd_kernel(const float *__restrict__ qkv, const float *__rest
   }
 }
 
+// ---------------------------------------------------------------------------------------------
+// Window attention backward for 8x8 windows (WACNN's first attention block: 64 tokens, 8 heads of 24 channels).
+// One CTA per (window, head), one thread per token.  Shared memory: the head's q / k / v / dO slices and the 64x64 P and
+// dS matrices.  Same formulas as the 16-token kernel; scores are staged in P between the softmax passes so that no
+// 64-entry array lives in registers.  d bias_table partial of the CTA goes to slot (window, rel, head).
+// ---------------------------------------------------------------------------------------------
+template <int D>
+__global__ void __launch_bounds__(64)
+window_attention64_bwd_kernel(const float *__restrict__ qkv, const float *__restrict__ dout,
+                              const float *__restrict__ bias_table, float *__restrict__ dqkv,
+                              float *__restrict__ dbias_part, int C, int heads, int shift, int Hp, int Wp, float q_scale) {
+  constexpr int WS = 8, N = 64, R = 2 * WS - 1, PS = N + 1;
+  extern __shared__ __align__(16) float sm[];
+  float *qs = sm, *ks = qs + N * D, *vs = ks + N * D, *gs = vs + N * D;  // [64][D] each
+  float *Pm = gs + N * D, *dS = Pm + N * PS;                              // [64][65] each
+  const int64_t win = blockIdx.x / heads;
+  const int head = blockIdx.x % heads;
+  const int ld = 3 * C;
+  const int n = threadIdx.x;
+  {
+    const float *row = qkv + (win * N + n) * (int64_t)ld + head * D;
+    const float *grow = dout + (win * N + n) * (int64_t)C + head * D;
+#pragma unroll
+    for (int j = 0; j < D; ++j) {
+      qs[n * D + j] = row[j];
+      ks[n * D + j] = row[C + j];
+      vs[n * D + j] = row[2 * C + j];
+      gs[n * D + j] = grow[j];
+    }
+  }
+  __syncthreads();
+  const int hn = n / WS, wn = n % WS;
+  int my_label = 0, wy = 0, wx = 0;
+  if (shift > 0) {
+    const int nWw = Wp / WS, nW = (Hp / WS) * nWw;
+    const int wi = (int)(win % nW);
+    wy = wi / nWw, wx = wi - wy * nWw;
+    const int hs = wy * WS + hn, wsft = wx * WS + wn;
+    my_label = 3 * (hs < Hp - WS ? 0 : (hs < Hp - shift ? 1 : 2)) + (wsft < Wp - WS ? 0 : (wsft < Wp - shift ? 1 : 2));
+  }
+  float q[D], go[D];
+#pragma unroll
+  for (int j = 0; j < D; ++j) q[j] = qs[n * D + j], go[j] = gs[n * D + j];
+  float *prow = Pm + n * PS, *drow = dS + n * PS;
+  float smax = -INFINITY;
+  for (int m = 0; m < N; ++m) {
+    float acc = 0.f, g = 0.f;
+#pragma unroll
+    for (int j = 0; j < D; ++j) {
+      acc = fmaf(q[j], ks[m * D + j], acc);
+      g = fmaf(go[j], vs[m * D + j], g);
+    }
+    const int hm = m / WS, wm = m % WS;
+    acc += __ldg(bias_table + ((hn - hm + WS - 1) * R + (wn - wm + WS - 1)) * heads + head);
+    if (shift > 0) {
+      const int hs = wy * WS + hm, wsft = wx * WS + wm;
+      const int lab = 3 * (hs < Hp - WS ? 0 : (hs < Hp - shift ? 1 : 2)) + (wsft < Wp - WS ? 0 : (wsft < Wp - shift ? 1 : 2));
+      if (lab != my_label) acc += kMaskValue;
+    }
+    prow[m] = acc;   // raw score
+    drow[m] = g;     // dP
+    smax = fmaxf(smax, acc);
+  }
+  float denom = 0.f;
+  for (int m = 0; m < N; ++m) {
+    const float e = expf(prow[m] - smax);
+    prow[m] = e;
+    denom += e;
+  }
+  const float inv = 1.0f / denom;
+  float dot = 0.f;
+  for (int m = 0; m < N; ++m) {
+    const float p = prow[m] * inv;
+    prow[m] = p;
+    dot = fmaf(p, drow[m], dot);
+  }
+  float dq[D];
+#pragma unroll
+  for (int j = 0; j < D; ++j) dq[j] = 0.f;
+  for (int m = 0; m < N; ++m) {
+    const float ds = prow[m] * (drow[m] - dot);
+    drow[m] = ds;
+#pragma unroll
+    for (int j = 0; j < D; ++j) dq[j] = fmaf(ds, ks[m * D + j], dq[j]);
+  }
+  float *dst = dqkv + (win * N + n) * (int64_t)ld + head * D;
+#pragma unroll
+  for (int j = 0; j < D; ++j) dst[j] = q_scale * dq[j];
+  __syncthreads();
+  {  // second phase: this thread is key / value token m = n
+    float dk[D], dv[D];
+#pragma unroll
+    for (int j = 0; j < D; ++j) dk[j] = 0.f, dv[j] = 0.f;
+    for (int r = 0; r < N; ++r) {
+      const float ds = dS[r * PS + n], p = Pm[r * PS + n];
+#pragma unroll
+      for (int j = 0; j < D; ++j) {
+        dk[j] = fmaf(ds, qs[r * D + j], dk[j]);
+        dv[j] = fmaf(p, gs[r * D + j], dv[j]);
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < D; ++j) dst[C + j] = dk[j], dst[2 * C + j] = dv[j];
+  }
+  for (int e = threadIdx.x; e < R * R; e += blockDim.x) {
+    const int dh = e / R - (WS - 1), dw = e % R - (WS - 1);
+    float acc = 0.f;
+    for (int hm = 0; hm < WS; ++hm) {
+      const int hq = hm + dh;
+      if (hq < 0 || hq >= WS) continue;
+      for (int wm = 0; wm < WS; ++wm) {
+        const int wq = wm + dw;
+        if (wq < 0 || wq >= WS) continue;
+        acc += dS[(hq * WS + wq) * PS + hm * WS + wm];
+      }
+    }
+    dbias_part[((int64_t)win * R * R + e) * heads + head] = acc;
+  }
+}
+
+template <int D>
+int launch_attn64_bwd(const float *qkv, const float *dout, const float *bias_table, float *dqkv, float *dbias_part,
+                      int64_t num_windows, int C, int heads, int shift, int Hp, int Wp, float q_scale, cudaStream_t st) {
+  const size_t smem = ((size_t)4 * 64 * D + (size_t)2 * 64 * 65) * 4;
+  static std::atomic<int> attr_set{0};
+  if (!attr_set.load(std::memory_order_acquire)) {
+    cudaError_t e = cudaFuncSetAttribute(window_attention64_bwd_kernel<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
+    if (e != cudaSuccess) return (int)e;
+    attr_set.store(1, std::memory_order_release);
+  }
+  const int64_t blocks = num_windows * heads;
+  if (blocks > 0x7fffffffLL) return STF_E_SHAPE;
+  window_attention64_bwd_kernel<D><<<(unsigned)blocks, 64, smem, st>>>(qkv, dout, bias_table, dqkv, dbias_part, C, heads,
+                                                                       shift, Hp, Wp, q_scale);
+  return check_launch();
+}
+
 template <int D>
 int launch_attn_bwd(const float *qkv, const float *dout, const float *bias_table, float *dqkv, float *dbias_part,
                     int64_t num_windows, int C, int heads, int shift, int Hp, int Wp, int wpc, float q_scale,
@@ -408,14 +545,29 @@ extern "C" int stf_attention_bwd_ctas(int64_t num_windows, int C, int heads, int
   return (int)((num_windows + wpc - 1) / wpc);
 }
 
+extern "C" int stf_attention_bwd_slots(int64_t num_windows, int C, int heads, int ws) {
+  if (ws == 8) return (num_windows < 0 || num_windows > 0x7fffffffLL) ? STF_E_ARG : (int)num_windows;
+  if (ws != 4) return STF_E_SHAPE;
+  return stf_attention_bwd_ctas(num_windows, C, heads, nullptr);
+}
+
 extern "C" int stf_window_attention_bwd(const float *qkv, const float *dout, const float *bias_table, float *dqkv,
                                         float *dbias_partials, int64_t num_windows, int C, int heads, int ws, int shift,
                                         int Hp, int Wp, float q_scale, void *stream) {
   if (!qkv || !dout || !bias_table || !dqkv || !dbias_partials || num_windows < 0 || C <= 0 || heads <= 0) return STF_E_ARG;
   if (num_windows == 0) return STF_OK;
-  if (ws != 4 || C % heads != 0 || shift < 0 || shift >= ws) return STF_E_SHAPE;
+  if ((ws != 4 && ws != 8) || C % heads != 0 || shift < 0 || shift >= ws) return STF_E_SHAPE;
   if (shift > 0 && (Hp <= 0 || Wp <= 0 || Hp % ws != 0 || Wp % ws != 0)) return STF_E_SHAPE;
   if (!aligned16(qkv) || !aligned16(dout) || !aligned16(dqkv)) return STF_E_ALIGN;
+  if (ws == 8) {
+    cudaStream_t st8 = (cudaStream_t)stream;
+    switch (C / heads) {
+      case 16: return launch_attn64_bwd<16>(qkv, dout, bias_table, dqkv, dbias_partials, num_windows, C, heads, shift, Hp, Wp, q_scale, st8);
+      case 24: return launch_attn64_bwd<24>(qkv, dout, bias_table, dqkv, dbias_partials, num_windows, C, heads, shift, Hp, Wp, q_scale, st8);
+      case 32: return launch_attn64_bwd<32>(qkv, dout, bias_table, dqkv, dbias_partials, num_windows, C, heads, shift, Hp, Wp, q_scale, st8);
+    }
+    return STF_E_SHAPE;
+  }
   int wpc = 0;
   const int ctas = stf_attention_bwd_ctas(num_windows, C, heads, &wpc);
   if (ctas < 0) return ctas;

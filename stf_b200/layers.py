@@ -370,12 +370,20 @@ class WinBasedAttention(nn.Module):
         self.drop_path = nn.Identity()
 
     def forward(self, x):
-        _require_eval(self)
         B, C, H, W = x.shape
         ws, shift = self.window_size, self.shift_size
         if H % ws or W % ws:
             raise RuntimeError(f"WinBasedAttention: {H}x{W} is not a multiple of window {ws} "
                                "(the reference's view() fails on this input too, win_attention.py:11)")
+        if _grad_mode(self):
+            # training: same fused forward kernels, backward in stf_b200/autograd.py (AttentionBranch without LayerNorm);
+            # the NCHW <-> token-major permutes stay on torch autograd
+            from . import autograd as AG
+            a = self.attn
+            t = x.permute(0, 2, 3, 1).contiguous().reshape(B * H * W, C)
+            y = AG.AttentionBranch.apply(t, None, None, a.qkv.weight, a.qkv.bias, a.relative_position_bias_table,
+                                         a.proj.weight, a.proj.bias, self, (B, H, W, ws, shift))
+            return y.reshape(B, H, W, C).permute(0, 3, 1, 2).contiguous()
         # NCHW -> token-major once; shift / partition / reverse / residual happen inside the kernels
         t = x.permute(0, 2, 3, 1).contiguous().reshape(B * H * W, C)
         geom = (B, H, W, ws, shift)

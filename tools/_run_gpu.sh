@@ -1,3 +1,2 @@
-nproc; free -g | head -2 | tail -1
-timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 --master-port 29561 bench.py --gpus 8 --steps 3 --warmup 3 > gpurun_out/bench56_n8.json 2> gpurun_out/bench56_n8.err
-grep "^{" gpurun_out/bench56_n8.json | head -c 500; tail -c 400 gpurun_out/bench56_n8.err
+timeout 900 python -m pytest tests/test_gpu_train.py -x -q -m gpu -s -k wacnn > gpurun_out/t58.log 2>&1; echo "pytest rc=$?" >> gpurun_out/t58.log
+tail -12 gpurun_out/t58.log
