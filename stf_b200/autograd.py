@@ -12,8 +12,8 @@ Backward:
   * dW = dY^T . X            plain library GEMM (torch -> cuBLAS; TF32 tensor cores by default, see _wgrad_precision)
   * db = column sums         stf_colsum (two-stage, deterministic)
   * Gaussian likelihood      stf_gaussian_likelihood_train{,_bwd} with the LowerBound gradient rule
-Reductions are two-stage and atomic-free (deterministic gradients).  Windows must tile the feature map (true for
-every training shape of the reference: 256x256 patches); the zero-pad path is inference-only.
+Reductions are two-stage and atomic-free (deterministic gradients).  Feature maps that are not a multiple of the window go
+through the same zero-pad index math as the forward kernels (pad tokens are zero after norm1 and take part as keys).
 """
 import torch
 
@@ -21,13 +21,22 @@ from . import _C, ops
 
 
 def window_row_index(B, H, W, ws, shift, device):
-    """Token index of every row of the window-ordered layout (roll(-shift) + window_partition, stf.py:167-171):
-    used to bring token-ordered tensors into window order for the weight-gradient GEMMs."""
-    idx = torch.arange(B * H * W, device=device, dtype=torch.int64).view(B, H, W)
+    """Token index of every row of the window-ordered layout (F.pad + roll(-shift) + window_partition, stf.py:158-171), -1
+    for the zero-pad tokens: used to bring token-ordered tensors into window order for the weight-gradient GEMMs."""
+    Hp, Wp = ops.ceil_to(H, ws), ops.ceil_to(W, ws)
+    idx = torch.full((B, Hp, Wp), -1, device=device, dtype=torch.int64)
+    idx[:, :H, :W] = torch.arange(B * H * W, device=device, dtype=torch.int64).view(B, H, W)
     if shift:
         idx = torch.roll(idx, shifts=(-shift, -shift), dims=(1, 2))
-    idx = idx.view(B, H // ws, ws, W // ws, ws).permute(0, 1, 3, 2, 4)
+    idx = idx.view(B, Hp // ws, ws, Wp // ws, ws).permute(0, 1, 3, 2, 4)
     return idx.reshape(-1)
+
+
+def gather_rows(t, idx):
+    """t[idx] with all-zero rows where idx < 0 (pad tokens are zero after norm1 and their outputs are cropped)."""
+    if bool((idx >= 0).all()):
+        return t.index_select(0, idx)
+    return t.index_select(0, idx.clamp_min(0)) * (idx >= 0).unsqueeze(1).to(t.dtype)
 
 
 def layernorm_bwd(x, g, gamma, beta, eps, res=None, want_xn=True):
@@ -105,15 +114,13 @@ class AttentionBranch(torch.autograd.Function):
     @staticmethod
     def forward(ctx, x, g1, b1, wqkv, bqkv, table, wproj, bproj, blk, geom):
         B, H, W, ws, shift = geom
-        if H % ws or W % ws:
-            raise NotImplementedError("stf_b200 training path: windows must tile the feature map "
-                                      f"({H}x{W} vs window {ws}); the zero-pad path is inference-only")
+        Hp, Wp = ops.ceil_to(H, ws), ops.ceil_to(W, ws)      # zero-pad to whole windows (stf.py:158-163)
         C = x.shape[1]
         attn = blk.attn
         norm1 = getattr(blk, "norm1", None)           # WinBasedAttention (WACNN) has no LayerNorm in front of qkv
-        qkv = ops.linear(x, attn.packed_qkv(norm1), M=B * H * W, rows=_C.ROWS_WINDOW, epilogue=_C.EPI_QKV,
+        qkv = ops.linear(x, attn.packed_qkv(norm1), M=B * Hp * Wp, rows=_C.ROWS_WINDOW, epilogue=_C.EPI_QKV,
                          q_cols=C, q_scale=attn.scale, geom=geom)
-        o = ops.window_attention_core(qkv, table, B * (H // ws) * (W // ws), C, attn.num_heads, ws, shift, H, W)
+        o = ops.window_attention_core(qkv, table, B * (Hp // ws) * (Wp // ws), C, attn.num_heads, ws, shift, Hp, Wp)
         x1 = ops.linear(o, attn.packed_proj(), epilogue=_C.EPI_WINDOW_RESIDUAL, residual=x, geom=geom,
                         out_rows=B * H * W, x_is_tf32=True)
         ctx.save_for_backward(x, g1, b1, wqkv, table, wproj, qkv, o)
@@ -125,30 +132,32 @@ class AttentionBranch(torch.autograd.Function):
         x, g1, b1, wqkv, table, wproj, qkv, o = ctx.saved_tensors
         blk, geom = ctx.blk, ctx.geom
         B, H, W, ws, shift = geom
+        Hp, Wp = ops.ceil_to(H, ws), ops.ceil_to(W, ws)
         attn = blk.attn
         C = x.shape[1]
         dx1 = dx1.contiguous()
         idx = window_row_index(B, H, W, ws, shift, x.device)
-        # proj: y_w = o . Wp^T + b, scattered to tokens
-        d_o = ops.linear(dx1, attn._pp.get_t(wproj), M=B * H * W, rows=_C.ROWS_WINDOW, geom=geom)
-        dy_w = dx1.index_select(0, idx)
+        # proj: y_w = o . Wp^T + b, scattered to tokens (pad rows cropped: their gradient is zero, which is what the
+        # WINDOW row gather feeds for them)
+        d_o = ops.linear(dx1, attn._pp.get_t(wproj), M=B * Hp * Wp, rows=_C.ROWS_WINDOW, geom=geom)
+        dy_w = gather_rows(dx1, idx)
         dwproj = wgrad(dy_w, o)
         dbproj = colsum(dx1)
         # attention core
-        dqkv, dtable = attention_bwd(qkv, d_o, table, B * (H // ws) * (W // ws), C, attn.num_heads, ws, shift, H, W,
+        dqkv, dtable = attention_bwd(qkv, d_o, table, B * (Hp // ws) * (Wp // ws), C, attn.num_heads, ws, shift, Hp, Wp,
                                      attn.scale)
         if g1 is None:
             # no LayerNorm: the qkv input gradient lands in token order on top of the shortcut gradient directly
             dx = ops.linear(dqkv, attn._pq.get_t(wqkv), epilogue=_C.EPI_WINDOW_RESIDUAL, residual=dx1, geom=geom,
                             out_rows=B * H * W)
-            dwqkv = wgrad(dqkv, x.index_select(0, idx))
+            dwqkv = wgrad(dqkv, gather_rows(x, idx))
             return dx, None, None, dwqkv, colsum(dqkv), dtable, dwproj, dbproj, None, None
         # qkv Linear (window-ordered rows -> token order) then LayerNorm 1, plus the shortcut gradient
         zeros = torch.zeros_like(x)
         g = ops.linear(dqkv, attn._pq.get_t(wqkv), epilogue=_C.EPI_WINDOW_RESIDUAL, residual=zeros, geom=geom,
                        out_rows=B * H * W)
         dx, xn, dg1, db1 = layernorm_bwd(x, g, g1, b1, blk.norm1.eps, res=dx1)
-        dwqkv = wgrad(dqkv, xn.index_select(0, idx))
+        dwqkv = wgrad(dqkv, gather_rows(xn, idx))
         dbqkv = colsum(dqkv)
         return dx, dg1, db1, dwqkv, dbqkv, dtable, dwproj, dbproj, None, None
 

@@ -210,13 +210,9 @@ def test_index_math_exact(H, W, shift):
 
 
 def test_training_mode_limits_raise_instead_of_falling_back():
-    """The training path covers window-aligned feature maps (every training shape of the reference); the zero-pad
-    path and the stand-alone WindowAttention module have no backward and say so."""
+    """The stand-alone WindowAttention module has no backward (the training path runs through SwinTransformerBlock /
+    WinBasedAttention) and says so instead of falling back."""
     from stf_b200 import layers as L
-    blk = L.SwinTransformerBlock(48, 3, 4, 0).cuda().train()
-    blk.H, blk.W = 6, 6
-    with pytest.raises(NotImplementedError):
-        blk(torch.randn(1, 36, 48, device="cuda", requires_grad=True), None)
     wa = L.WindowAttention(48, (4, 4), 3).cuda().train()
     with pytest.raises(NotImplementedError):
         wa(torch.randn(2, 16, 48, device="cuda", requires_grad=True))

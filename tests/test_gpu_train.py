@@ -26,7 +26,8 @@ def _close(got, ref, what, tol=TOL):
     assert err <= tol * scale + 1e-7, f"{what}: max err {err:.3e} vs scale {scale:.3e}"
 
 
-@pytest.mark.parametrize("C,nh,H,W,shift", [(48, 3, 8, 12, 0), (48, 3, 8, 12, 2), (96, 6, 8, 8, 2), (384, 24, 4, 4, 2)])
+@pytest.mark.parametrize("C,nh,H,W,shift", [(48, 3, 8, 12, 0), (48, 3, 8, 12, 2), (96, 6, 8, 8, 2), (384, 24, 4, 4, 2),
+                                            (48, 3, 6, 10, 2), (96, 6, 5, 7, 0)])     # the last two: zero-pad path
 def test_swin_block_gradients(C, nh, H, W, shift):
     from stf_b200 import layers as L
     B, ws = 2, 4
@@ -45,7 +46,7 @@ def test_swin_block_gradients(C, nh, H, W, shift):
     # oracle: torch autograd over the restated block
     osd = {k: v.clone().requires_grad_(v.is_floating_point()) for k, v in sd.items()}
     xo = x.clone().requires_grad_(True)
-    mask = OS.shift_mask(H, W, ws, ws // 2)
+    mask = OS.shift_mask(-(-H // ws) * ws, -(-W // ws) * ws, ws, ws // 2)
     yo = OS.swin_block(osd, "", xo, H, W, nh, ws, shift, mask)
     (yo * w).sum().backward()
     _close(y, yo, "forward")
