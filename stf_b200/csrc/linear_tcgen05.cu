@@ -115,6 +115,7 @@ struct LinearParams {
   int lite;        // A operand needs no finalize pass (no LayerNorm, X already TF32-exact): one thread fences + publishes
   int stages_a, stages_b;
   int epi_mode;    // 0: staged slab -> coalesced 16-byte stores by the whole warp; 1: one bulk (TMA) store per row
+  int pair;        // CTA pairs (cluster of 2) share every weight stage: each CTA fetches half and multicasts it to both
   uint32_t backoff_ns;  // nanosleep between mbarrier probes of the producer-side roles (0 = tight spin)
   int debug_skip;  // bring-up / profiling only (env STF_B200_DEBUG_SKIP): 1 = no A loads, 2 = no B loads, 4 = no stores
   int fin_group;  // k-blocks published per proxy fence by the finalize warps (divides k_blocks, < stages_a)
@@ -314,7 +315,7 @@ __device__ __forceinline__ void store_slab_pixel_shuffle(const stf_linear_args &
 
 // ---------------------------------------------------------------------------- shared-memory map
 struct SmemMap {
-  uint64_t *fullA, *emptyA, *landA, *fullB, *accFull, *accEmpty;
+  uint64_t *fullA, *emptyA, *landA, *fullB, *accFull, *accEmpty, *emptyB;
   uint32_t *tmem_slot;
   float2 *stats;        // [kStatSlots][128] (mean, rstd) per tile in flight
   uint64_t *row_dst;    // [kEpiWarps][32] destination row pointers (0 = dropped row)
@@ -326,7 +327,8 @@ struct SmemMap {
 // LayerNorm statistics slots.  The producers lead the MMA by at most kMaxStagesA k-blocks = ceil(16 / 3) = 6 tiles
 // (a LayerNorm'ed tile has >= 3 k-blocks) and the MMA leads the epilogue's statistics read by < 2 tiles.
 constexpr int kStatSlots = 8;
-constexpr size_t kSmemHeader = 512 + kStatSlots * 128 * 8 + 2 * kEpiWarps * 32 * 8;  // barriers + stats + row pointers
+constexpr size_t kBarBytes = 640;  // mbarriers + the TMEM slot
+constexpr size_t kSmemHeader = kBarBytes + kStatSlots * 128 * 8 + 2 * kEpiWarps * 32 * 8;  // barriers + stats + row pointers
 
 __device__ __forceinline__ SmemMap carve(uint8_t *smem, int n_tile, int stages_a, int stages_b, int slab, int planes) {
   SmemMap m;
@@ -337,9 +339,10 @@ __device__ __forceinline__ SmemMap carve(uint8_t *smem, int n_tile, int stages_a
   m.fullB = m.landA + kMaxStagesA;
   m.accFull = m.fullB + kMaxStagesB;
   m.accEmpty = m.accFull + 2;
-  m.tmem_slot = reinterpret_cast<uint32_t *>(m.accEmpty + 2);
-  m.stats = reinterpret_cast<float2 *>(smem + 512);
-  m.row_dst = reinterpret_cast<uint64_t *>(smem + 512 + kStatSlots * 128 * 8);
+  m.emptyB = m.accEmpty + 2;
+  m.tmem_slot = reinterpret_cast<uint32_t *>(m.emptyB + kMaxStagesB);
+  m.stats = reinterpret_cast<float2 *>(smem + kBarBytes);
+  m.row_dst = reinterpret_cast<uint64_t *>(smem + kBarBytes + kStatSlots * 128 * 8);
   m.row_res = m.row_dst + kEpiWarps * 32;
   m.a_ring = smem + kSmemHeader;
   m.b_ring = m.a_ring + (size_t)stages_a * planes * kAStageBytes;
@@ -388,7 +391,8 @@ linear_tf32_kernel(const __grid_constant__ LinearParams P) {
       mbar_init(&S.emptyA[s], 1);              // one tcgen05.commit
     }
     for (int s = 0; s < P.stages_b; ++s) {
-      mbar_init(&S.fullB[s], 1);  // the loader's arrive.expect_tx (+ TMA transaction bytes)
+      mbar_init(&S.fullB[s], 1);   // the loader's arrive.expect_tx (+ TMA transaction bytes)
+      mbar_init(&S.emptyB[s], 2);  // pair mode: one tcgen05.commit from each CTA of the pair
     }
     for (int b = 0; b < 2; ++b) {
       mbar_init(&S.accFull[b], 1);
@@ -400,9 +404,15 @@ linear_tf32_kernel(const __grid_constant__ LinearParams P) {
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
+  if (P.pair) cluster_sync();  // the peer's barriers exist before anything is multicast into this CTA
   const uint32_t tmem_base = *S.tmem_slot;
 
-  const int first_tile = blockIdx.x, tile_step = gridDim.x;
+  // Work items: (m-tile, n-tile) strided over the grid; in pair mode (super m-tile of 256 rows, n-tile) strided over the
+  // CTA pairs, CTA `rank` of a pair taking the 128-row half `rank` (a half past the last row is an all-zero dummy tile
+  // without stores), so that both CTAs consume the same weight stages in the same order.
+  const int rank = P.pair ? (int)cluster_ctarank() : 0;
+  const int first_tile = P.pair ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
+  const int tile_step = P.pair ? (int)(gridDim.x >> 1) : (int)gridDim.x;
 
   if (warp < kProducerWarps) {
     // =========================== A producers: issue ===========================
@@ -415,7 +425,7 @@ linear_tf32_kernel(const __grid_constant__ LinearParams P) {
     const bool merge = rows_mode == STF_ROWS_MERGE;
     int tr_it = 0;
     for (int i_tile = first_tile; i_tile < P.total_tiles; i_tile += tile_step, ++tr_it) {
-      const int m0 = (i_tile / P.n_tiles) * kTileM;
+      const int m0 = (P.pair ? 2 * (i_tile / P.n_tiles) + rank : i_tile / P.n_tiles) * kTileM;
       if (warp == 0) TRACE(0, tr_it);
       RowSrc src[4];
       const float *base[4];
@@ -551,7 +561,8 @@ linear_tf32_kernel(const __grid_constant__ LinearParams P) {
     int it = 0;
     for (int tile = first_tile; tile < P.total_tiles; tile += tile_step, ++it) {
       const int buf = it & 1;
-      const int mt = P.n_tiles == 1 ? tile : tile / P.n_tiles, nt = tile - mt * P.n_tiles;
+      const int smt = P.n_tiles == 1 ? tile : tile / P.n_tiles, nt = tile - smt * P.n_tiles;
+      const int mt = P.pair ? 2 * smt + rank : smt;
       const int row = mt * kTileM + quad * 32 + lane;  // TMEM lane == tile row
       // destination / residual row pointers of this thread's row
       float *dst = nullptr;
@@ -730,6 +741,7 @@ linear_tf32_kernel(const __grid_constant__ LinearParams P) {
             }
           if (kb == 1) TRACE(14, it);
           if (leader) umma_commit(&S.emptyA[sa]);  // frees the A stage and (for the loader) the B stage of this k-block
+          if (P.pair && leader) umma_commit_multicast(&S.emptyB[sb], (uint16_t)0x3);  // ... in both CTAs of the pair
           if (kb == 1) TRACE(15, it);
           if (lane == 0) KTRACE(4, it, kb);
           if ((dbg & 16) && it == 2) {  // experiment: expose the MMA completion latency
@@ -759,8 +771,12 @@ linear_tf32_kernel(const __grid_constant__ LinearParams P) {
         const float *wt = a.w_packed + (size_t)nt * (size_t)(a.K >> 2) * NT * 4 * planes;
         for (int kb = 0; kb < P.k_blocks; ++kb, ++g) {
           if (g >= (long long)SB) {
-            if (P.backoff_ns) mbar_wait_backoff(&S.emptyA[wa], wpa, P.backoff_ns); else mbar_wait(&S.emptyA[wa], wpa);
-            if (++wa == SA) wa = 0, wpa ^= 1u;
+            if (P.pair) {  // both CTAs' MMAs of k-block g - SB are done with this stage
+              mbar_wait(&S.emptyB[sb], (uint32_t)((g / SB) - 1) & 1u);
+            } else {
+              if (P.backoff_ns) mbar_wait_backoff(&S.emptyA[wa], wpa, P.backoff_ns); else mbar_wait(&S.emptyA[wa], wpa);
+              if (++wa == SA) wa = 0, wpa ^= 1u;
+            }
           }
           if (lane == 0) KTRACE(6, (int)(g / P.k_blocks), kb);
           if (leader) {
@@ -768,7 +784,14 @@ linear_tf32_kernel(const __grid_constant__ LinearParams P) {
               mbar_arrive(&S.fullB[sb]);
             } else {
               mbar_arrive_expect_tx(&S.fullB[sb], b_stage_bytes);
-              bulk_copy_g2s(S.b_ring + sb * b_stage_bytes, wt + (size_t)kb * kChunks * NT * 4 * planes, b_stage_bytes, &S.fullB[sb]);
+              const uint8_t *src = reinterpret_cast<const uint8_t *>(wt + (size_t)kb * kChunks * NT * 4 * planes);
+              if (P.pair) {  // this CTA fetches its half of the stage and delivers it to both CTAs
+                const uint32_t half = b_stage_bytes >> 1;
+                bulk_copy_g2s_multicast(S.b_ring + sb * b_stage_bytes + rank * half, src + rank * half, half, &S.fullB[sb],
+                                        (uint16_t)0x3);
+              } else {
+                bulk_copy_g2s(S.b_ring + sb * b_stage_bytes, src, b_stage_bytes, &S.fullB[sb]);
+              }
             }
           }
           __syncwarp();
@@ -801,6 +824,7 @@ linear_tf32_kernel(const __grid_constant__ LinearParams P) {
 
   tc_fence_before();
   __syncthreads();
+  if (P.pair) cluster_sync();  // the peer may still multicast into this CTA / arrive on its barriers until it is done too
   if (warp == kMmaWarp) {
     tc_fence_after();
     tmem_dealloc(tmem_base, (uint32_t)P.tmem_cols);
@@ -892,6 +916,17 @@ int launch_linear(const stf_linear_args *args, void *stream) {
   if (total > 0x7fffffff) return STF_E_SHAPE;
   P.total_tiles = (int)total;
   P.k_blocks = a.K / kBlockK;
+  // Pair mode (opt-in, STF_B200_PAIR=1) for K >= 192, where every CTA re-reads the whole weight from L2 per 128-row tile:
+  // clusters of two CTAs work on neighbouring 128-row tiles of the same column tile and each fetches half of every weight
+  // stage, multicast to both.  Correct (tests pass with it on) but measured neutral on B200 (0.101 vs 0.102 ms, 0.129 vs
+  // 0.131 ms on the stage-2 GEMMs): the L2 already merges concurrent requests for the same lines, and the bytes entering
+  // each SM do not change -- halving those takes cta_group::2 MMAs with the weight tile split across the pair.
+  static const int pair_env = [] {
+    const char *e = getenv("STF_B200_PAIR");
+    return e ? atoi(e) : 0;
+  }();
+  P.pair = (pair_env && P.k_blocks >= 12 && P.m_tiles >= 4) ? 1 : 0;
+  if (P.pair) P.total_tiles = ((P.m_tiles + 1) / 2) * P.n_tiles;
   P.slab = pick_slab(P.n_tile, P.k_blocks);
   if (P.precise && P.n_tile > 128) P.slab = 16;  // two operand planes per stage: the rings need the shared memory
   P.tmem_cols = 32;
@@ -985,7 +1020,23 @@ int launch_linear(const stf_linear_args *args, void *stream) {
     cudaError_t e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);  // idempotent, cheap
     if (e != cudaSuccess) return (int)e;
   }
-  const int grid = P.total_tiles < kNumSMs ? P.total_tiles : kNumSMs;
+  int grid = P.total_tiles < kNumSMs ? P.total_tiles : kNumSMs;
+  if (P.pair) {
+    const int pairs = P.total_tiles < kNumSMs / 2 ? P.total_tiles : kNumSMs / 2;   // total_tiles counts super tiles here
+    grid = 2 * pairs;
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)grid), cfg.blockDim = dim3(kThreads), cfg.dynamicSmemBytes = smem, cfg.stream = (cudaStream_t)stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2, attr[0].val.clusterDim.y = 1, attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr, cfg.numAttrs = 1;
+    cudaError_t e = cudaLaunchKernelEx(&cfg, fn, P);
+    if (e != cudaSuccess) {
+      (void)cudaGetLastError();
+      return (int)e;
+    }
+    return check_launch();
+  }
   fn<<<grid, kThreads, smem, (cudaStream_t)stream>>>(P);
   return check_launch();
 }
