@@ -16,6 +16,7 @@
 // (row label, column label) pairs of query and key differ; rel_idx(n,m) =
 // (hn-hm+ws-1)*(2ws-1) + (wn-wm+ws-1).
 #include <math.h>
+#include <stdlib.h>
 
 #include "common.cuh"
 #include "sm100.cuh"
@@ -389,7 +390,13 @@ int launch16(const float *qkv, float *out, const float *bias_table, const float 
   const int per_window = heads * 16;                 // threads per window
   const size_t win_bytes = (size_t)16 * 3 * C * 4;   // qkv tile of one window
   int wpc = 384 / per_window;
-  const int by_smem = (int)((72 * 1024) / win_bytes);  // ~3 CTAs per SM
+  static const int tile_kb = [] {
+    const char *e = getenv("STF_B200_ATTN_TILE_KB");
+    return e ? atoi(e) : 24;
+  }();
+  // 24 KB tiles (2-3 windows at C = 48): many small CTAs per SM overlap each other's load / compute / store phases better
+  // than three 72 KB ones (measured at stage 0: 2.78 -> 3.24 TB/s)
+  const int by_smem = (int)(((size_t)tile_kb * 1024) / win_bytes);
   if (wpc > by_smem) wpc = by_smem;
   if (wpc < 1) wpc = 1;
   if (per_window > 384 || win_bytes > 200 * 1024) return STF_E_SHAPE;

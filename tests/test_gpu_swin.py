@@ -283,3 +283,29 @@ def test_attention_guard_bands():
         big[:rows] = qkv
         o2 = ops.window_attention_core(big[:rows], table, windows, C, heads, ws, 0)
         assert torch.equal(o, o2)
+
+
+def test_pair_mode_clusters_match_single_cta(tmp_path):
+    """Opt-in CTA-pair mode (cluster of 2, TMA-multicast weight stages; STF_B200_PAIR=1 is read once per process, hence the
+    subprocess): same results as the default mode, including an odd number of 128-row tiles (dummy half tile)."""
+    import subprocess
+    import sys
+    code = (
+        "import torch, sys\n"
+        "sys.path.insert(0, %r)\n"
+        "from stf_b200 import _C, ops\n"
+        "g = torch.Generator().manual_seed(3)\n"
+        "for (M, N, K) in ((1000, 96, 384), (641, 576, 192), (4096, 1536, 384)):\n"
+        "    x = torch.randn(M, K, generator=g).cuda(); w = (torch.randn(N, K, generator=g) / K ** 0.5).cuda()\n"
+        "    b = torch.randn(N, generator=g).cuda(); r = torch.randn(M, N, generator=g).cuda()\n"
+        "    for prec in ('fp32', 'tf32'):\n"
+        "        ops.set_precision(prec)\n"
+        "        y = ops.linear(x, ops.PackedLinear(w, b), epilogue=_C.EPI_RESIDUAL, residual=r)\n"
+        "        ref = r.double() + x.double() @ w.double().t() + b.double()\n"
+        "        tol = 1e-5 if prec == 'fp32' else 4e-3\n"
+        "        err = float((y.double() - ref).abs().max() / ref.abs().max())\n"
+        "        assert err <= tol, (M, N, K, prec, err)\n"
+        "print('pair mode ok')\n" % os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    env = dict(os.environ, STF_B200_PAIR="1")
+    out = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0 and "pair mode ok" in out.stdout, out.stdout + out.stderr
