@@ -629,8 +629,12 @@ linear_tf32_kernel(const __grid_constant__ LinearParams P) {
           tmem_ld16(t_acc + (uint32_t)(c0 + c), acc);
 #pragma unroll
           for (int j = 0; j < 16; j += 4) {
-            const float4 sv = *reinterpret_cast<const float4 *>(aux_s + n + j);
             const float4 tv = *reinterpret_cast<const float4 *>((pad_row ? aux_b : aux_t) + n + j);
+            if (!has_ln) {  // no LayerNorm in front: the accumulator only takes the bias (t == bias)
+              acc[j] += tv.x, acc[j + 1] += tv.y, acc[j + 2] += tv.z, acc[j + 3] += tv.w;
+              continue;
+            }
+            const float4 sv = *reinterpret_cast<const float4 *>(aux_s + n + j);
             if (pad_row) {
               acc[j] = tv.x, acc[j + 1] = tv.y, acc[j + 2] = tv.z, acc[j + 3] = tv.w;
             } else {
@@ -722,6 +726,7 @@ linear_tf32_kernel(const __grid_constant__ LinearParams P) {
         const uint32_t d_tmem = tmem_base + (uint32_t)(buf * P.acc_stride);
         for (int kb = 0; kb < P.k_blocks; ++kb) {
           if (kb == 1) TRACE(11, it);
+          // (probing only the last stage of each published group of k-blocks instead of every stage was measured: no gain)
           mbar_wait(&S.fullA[sa], pa);   // A stage published AND (forwarder) its weight stage landed
           if (kb == 0) TRACE(5, it);
           if (kb == 1) TRACE(13, it);

@@ -1,2 +1,3 @@
-for kb in 72 48 36 24 18; do echo "tile_kb $kb"; STF_B200_ATTN_TILE_KB=$kb timeout 300 python tools/bench_ops.py --only attention 2>&1 | grep attention; done
-timeout 600 python -m pytest tests/test_gpu_swin.py -x -q -m gpu -k pair 2>&1 | tail -2
+timeout 600 python -m pytest tests/test_gpu_swin.py -x -q -m gpu > gpurun_out/t62.log 2>&1; echo "pytest rc=$?" >> gpurun_out/t62.log; tail -2 gpurun_out/t62.log
+STF_B200_PRECISION=fp32 timeout 300 python tools/bench_ops.py --only linear 2>&1 | tail -18
+STF_B200_PRECISION=tf32 timeout 300 python tools/bench_ops.py --only linear 2>&1 | tail -1
