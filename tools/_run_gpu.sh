@@ -1,3 +1,4 @@
-timeout 600 python -m pytest tests/test_gpu_swin.py -x -q -m gpu > gpurun_out/t62.log 2>&1; echo "pytest rc=$?" >> gpurun_out/t62.log; tail -2 gpurun_out/t62.log
-STF_B200_PRECISION=fp32 timeout 300 python tools/bench_ops.py --only linear 2>&1 | tail -18
+timeout 600 python -m pytest tests/test_gpu_swin.py -x -q -m gpu > gpurun_out/t64.log 2>&1; echo "pytest rc=$?" >> gpurun_out/t64.log; tail -2 gpurun_out/t64.log
+STF_B200_PRECISION=fp32 timeout 300 python tools/bench_ops.py --only linear 2>&1 | tail -17
 STF_B200_PRECISION=tf32 timeout 300 python tools/bench_ops.py --only linear 2>&1 | tail -1
+STF_B200_B_LDGSTS=0 STF_B200_PRECISION=fp32 timeout 300 python tools/bench_ops.py --only linear 2>&1 | tail -1
