@@ -1003,7 +1003,7 @@ int launch_linear(const stf_linear_args *args, void *stream) {
   if (plain && a.epilogue == (E) && a.rows == (R) && P.has_ln == (L))                            \
     fn = P.precise ? (KernelFn)linear_tf32_kernel<E, R, L, 1, 0> : (KernelFn)linear_tf32_kernel<E, R, L, 0, 0>;
 #define STF_LINEAR_TRACED(E, R, L)                                                              \
-  if (debug_skip_env == 8 && epi_mode_env == 0 && a.epilogue == (E) && a.rows == (R) && P.has_ln == (L)) \
+  if ((debug_skip_env & 8) && epi_mode_env == 0 && a.epilogue == (E) && a.rows == (R) && P.has_ln == (L)) \
     fn = P.precise ? (KernelFn)linear_tf32_kernel<E, R, L, 1, 1> : (KernelFn)linear_tf32_kernel<E, R, L, 0, 1>;
   STF_LINEAR_TRACED(STF_EPI_QKV, STF_ROWS_WINDOW, 1)            // (tools/trace_linear.py: specialised + clock64 hooks)
   STF_LINEAR_TRACED(STF_EPI_GELU, STF_ROWS_DENSE, 1)

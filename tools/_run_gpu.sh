@@ -1,4 +1,4 @@
-timeout 600 python -m pytest tests/test_gpu_swin.py -x -q -m gpu > gpurun_out/t64.log 2>&1; echo "pytest rc=$?" >> gpurun_out/t64.log; tail -2 gpurun_out/t64.log
-STF_B200_PRECISION=fp32 timeout 300 python tools/bench_ops.py --only linear 2>&1 | tail -17
-STF_B200_PRECISION=tf32 timeout 300 python tools/bench_ops.py --only linear 2>&1 | tail -1
-STF_B200_B_LDGSTS=0 STF_B200_PRECISION=fp32 timeout 300 python tools/bench_ops.py --only linear 2>&1 | tail -1
+for skip in 8 9 10 11 12 15; do
+  echo "== DEBUG_SKIP=$skip (1: no A loads, 2: no weight loads, 4: no stores; 8: traced specialised instance)"
+  STF_B200_DEBUG_SKIP=$skip STF_B200_PRECISION=fp32 timeout 300 python tools/bench_ops.py --only linear --stages 0,2 2>&1 | grep -E "qkv|fc1|fc2"
+done
