@@ -958,7 +958,13 @@ int launch_linear(const stf_linear_args *args, void *stream) {
     return e ? atoi(e) : 64;
   }();
   P.backoff_ns = (uint32_t)backoff_env;
-  P.fin_group = (P.k_blocks % 4 == 0) ? 4 : (P.k_blocks % 3 == 0) ? 3 : (P.k_blocks % 2 == 0) ? 2 : 1;
+  static const int fin_group_max = [] {
+    const char *e = getenv("STF_B200_FIN_GROUP");
+    return e ? atoi(e) : 4;
+  }();
+  P.fin_group = 1;
+  for (int g = 1; g <= fin_group_max; ++g)
+    if (P.k_blocks % g == 0) P.fin_group = g;
   {  // all the shared memory the B ring and the epilogue staging leave over goes to the A ring
     const size_t fixed = linear_smem_bytes(P.n_tile, P.slab, 0, P.stages_b, a.N, planes);
     const size_t budget = 227 * 1024;
@@ -966,6 +972,7 @@ int launch_linear(const stf_linear_args *args, void *stream) {
     int sa = (int)((budget - fixed) / (planes * kAStageBytes));
     P.stages_a = sa > kMaxStagesA ? kMaxStagesA : sa;
   }
+  while (P.fin_group > 1 && (P.fin_group > P.stages_a - 2 || P.k_blocks % P.fin_group != 0)) --P.fin_group;  // a group must fit the ring
   // the statistics hand-over (kStatSlots tiles deep) relies on a tile spanning at least 3 k-blocks
   if (P.has_ln && P.k_blocks < 3) return STF_E_SHAPE;
   P.Hp = P.Wp = P.nWw = P.nW = 0;

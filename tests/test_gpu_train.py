@@ -248,3 +248,27 @@ def test_wacnn_training_step_gradients(golden_dir):
     print(f"WACNN training step: loss {float(out['loss'].detach()):.4f} (oracle {float(oout['loss'].detach()):.4f}), "
           f"worst gradient-norm error {worst[1]:.2e} at {worst[0]}")
     assert worst[1] <= 5e-3       # (observed 2.8e-4; cuDNN TF32 convolutions dominate this model)
+
+
+def test_training_c_abi_argument_errors():
+    """New entry points reject bad shapes / alignment with STF_E_* codes (-> ValueError), nothing is launched."""
+    import ctypes
+    from stf_b200 import _C
+    L = _C.lib()
+    x = torch.randn(64, 48, device="cuda")
+    st = _C.stream()
+    assert L.stf_colsum(x.data_ptr(), x.data_ptr(), 64, 50, st) == -2                      # C % 4
+    assert L.stf_colsum(None, x.data_ptr(), 64, 48, st) == -1
+    assert L.stf_gelu_bwd(x.data_ptr(), x.data_ptr(), x.data_ptr(), 63, st) == -2           # n % 4
+    assert L.stf_gelu_bwd(x.data_ptr() + 4, x.data_ptr(), x.data_ptr(), 64, st) == -3       # alignment
+    assert L.stf_layernorm_bwd(x.data_ptr(), x.data_ptr(), x.data_ptr(), None, None, x.data_ptr(), None, x.data_ptr(),
+                               64, 1000, ctypes.c_float(1e-5), st) == -2                   # C > 768
+    assert L.stf_window_attention_bwd(x.data_ptr(), x.data_ptr(), x.data_ptr(), x.data_ptr(), x.data_ptr(), 4, 48, 3, 7, 0,
+                                      0, 0, ctypes.c_float(0.25), st) == -2                # window size 7
+    assert L.stf_attention_bwd_slots(4, 48, 3, 5) == -2
+    assert L.stf_bias_act(x.data_ptr(), x.data_ptr(), 6, 3072, 1, st) == -2                 # channels % 4
+    assert L.stf_bias_act(x.data_ptr(), x.data_ptr(), 48, 3072, 7, st) == -1                # unknown activation
+    assert L.stf_layernorm_fwd(x.data_ptr(), x.data_ptr(), x.data_ptr(), x.data_ptr(), 64, 2000, ctypes.c_float(1e-5), st) == -2
+    assert L.stf_gaussian_likelihood_train(None, x.data_ptr(), None, None, x.data_ptr(), 10, ctypes.c_float(0.11),
+                                           ctypes.c_float(1e-9), st) == -1
+    torch.cuda.synchronize()
