@@ -47,13 +47,19 @@ def build(force=False, verbose=False):
         return LIB
     nvcc = _nvcc()
     flags = [f for f in NVCC_FLAGS if not f.startswith("--use_fast_math")]
-    objs = []
-    for src in SOURCES:
+    def compile_one(src):
         obj = os.path.join(LIBDIR, os.path.splitext(src)[0] + ".o")
         cmd = [nvcc] + flags + (["-Xptxas", "-v"] if verbose else []) + ["-c", os.path.join(CSRC, src), "-o", obj]
         if src.endswith(".cpp"):
             cmd = [nvcc, "-O3", "-std=c++17", "-Xcompiler", "-fPIC,-O3", "-c", os.path.join(CSRC, src), "-o", obj]
         r = subprocess.run(cmd, capture_output=True, text=True)
+        return src, obj, r
+
+    from concurrent.futures import ThreadPoolExecutor
+    with ThreadPoolExecutor(max_workers=min(len(SOURCES), os.cpu_count() or 1)) as ex:   # translation units in parallel
+        results = list(ex.map(compile_one, SOURCES))
+    objs = []
+    for src, obj, r in results:
         if verbose or r.returncode:
             sys.stderr.write(r.stdout + r.stderr)
         if r.returncode:
