@@ -33,7 +33,7 @@ def main():
     else:
         h = torch.randn(T, 4 * C, device=dev)
         lin = ops.PackedLinear(torch.randn(C, 4 * C, device=dev) * (4 * C) ** -0.5, torch.zeros(C, device=dev))
-        fn = lambda: ops.linear(h, lin, epilogue=_C.EPI_RESIDUAL, residual=x)
+        fn = lambda: ops.linear(h, lin, epilogue=_C.EPI_RESIDUAL, residual=x, x_is_tf32=os.environ.get("TRACE_LITE", "0") == "1")
     fn()
     fn()
     torch.cuda.synchronize()
