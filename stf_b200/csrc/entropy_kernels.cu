@@ -71,7 +71,10 @@ struct SliceGeom {
 // ---------------------------------------------------------------------------------------------
 // compress step: (y, mu, scale) -> (symbols, indexes, y_hat)
 // ---------------------------------------------------------------------------------------------
-template <bool kVec, int kMode>  // kMode: 0 = linear count, 1 = binary search, 2 = bucket LUT
+// kIdxOnly: stf_build_indexes (scales -> indexes only): the y / means / symbols / y_hat paths compile out, which takes the
+// kernel from 125 to ~40 registers, i.e. from 2 to 8 resident CTAs per SM for its single input stream (ncu: 0.66 of the HBM peak
+// at 125 registers, latency-bound).
+template <bool kVec, int kMode, bool kIdxOnly>  // kMode: 0 = linear count, 1 = binary search, 2 = bucket LUT
 __global__ void __launch_bounds__(kThreads)
 compress_step_kernel(const float *__restrict__ y, const float *__restrict__ scales,
                      const float *__restrict__ means, int32_t *__restrict__ symbols,
@@ -91,12 +94,12 @@ compress_step_kernel(const float *__restrict__ y, const float *__restrict__ scal
     return scale_index<kMode == 1>(sigma, t, table.levels);
   };
   const int b = blockIdx.y;
-  const float *yb = y ? y + (int64_t)b * g.y_batch_stride : nullptr;
+  const float *yb = (!kIdxOnly && y) ? y + (int64_t)b * g.y_batch_stride : nullptr;
   const float *sb = scales ? scales + (int64_t)b * g.inner : nullptr;
-  const float *mb = means ? means + (int64_t)b * g.inner : nullptr;
-  int32_t *symb = symbols ? symbols + (int64_t)b * g.out_batch_stride : nullptr;
+  const float *mb = (!kIdxOnly && means) ? means + (int64_t)b * g.inner : nullptr;
+  int32_t *symb = (!kIdxOnly && symbols) ? symbols + (int64_t)b * g.out_batch_stride : nullptr;
   int32_t *idxb = indexes ? indexes + (int64_t)b * g.out_batch_stride : nullptr;
-  float *yhb = y_hat ? y_hat + (int64_t)b * g.inner : nullptr;
+  float *yhb = (!kIdxOnly && y_hat) ? y_hat + (int64_t)b * g.inner : nullptr;
 
   if (kVec) {
     const int64_t nvec = g.inner >> 2;
@@ -107,8 +110,10 @@ compress_step_kernel(const float *__restrict__ y, const float *__restrict__ scal
       for (int u = 0; u < kVecPerThread; ++u) {
         int64_t v = v0 + u * stride;
         if (v < nvec) {
-          if (yb) yy[u] = ldg_stream(reinterpret_cast<const float4 *>(yb) + v);
-          mm[u] = mb ? ldg_stream(reinterpret_cast<const float4 *>(mb) + v) : make_float4(0.f, 0.f, 0.f, 0.f);
+          if (!kIdxOnly) {
+            if (yb) yy[u] = ldg_stream(reinterpret_cast<const float4 *>(yb) + v);
+            mm[u] = mb ? ldg_stream(reinterpret_cast<const float4 *>(mb) + v) : make_float4(0.f, 0.f, 0.f, 0.f);
+          }
           if (sb) ss[u] = ldg_stream(reinterpret_cast<const float4 *>(sb) + v);
         }
       }
@@ -116,7 +121,7 @@ compress_step_kernel(const float *__restrict__ y, const float *__restrict__ scal
       for (int u = 0; u < kVecPerThread; ++u) {
         int64_t v = v0 + u * stride;
         if (v >= nvec) continue;
-        if (yb) {
+        if (!kIdxOnly && yb) {
           int4 q;
           q.x = round_to_symbol(yy[u].x - mm[u].x);
           q.y = round_to_symbol(yy[u].y - mm[u].y);
@@ -422,8 +427,14 @@ extern "C" int stf_gaussian_compress_step(const float *y, int64_t y_batch_stride
   bool vec = vec_ok(g.inner, y_batch_stride, out_batch_stride, y, scales, means, symbols, indexes, y_hat);
   dim3 grid(grid_x(vec ? g.inner / 4 : g.inner, kThreads * (vec ? kVecPerThread : 1), batch), batch);
   cudaStream_t st = (cudaStream_t)stream;
-#define LAUNCH(V, M) \
-  compress_step_kernel<V, M><<<grid, kThreads, 0, st>>>(y, scales, means, symbols, indexes, y_hat, g, scale_bound, t)
+  const bool idx_only = !y && !symbols && !y_hat;
+#define LAUNCH(V, M)                                                                                                    \
+  do {                                                                                                                  \
+    if (idx_only)                                                                                                       \
+      compress_step_kernel<V, M, true><<<grid, kThreads, 0, st>>>(y, scales, means, symbols, indexes, y_hat, g, scale_bound, t); \
+    else                                                                                                                \
+      compress_step_kernel<V, M, false><<<grid, kThreads, 0, st>>>(y, scales, means, symbols, indexes, y_hat, g, scale_bound, t); \
+  } while (0)
   static const bool no_lut = getenv("STF_B200_NO_INDEX_LUT") != nullptr;  // (test hook: exercise the binary search)
   const int mode = !t.monotone ? 0 : (t.keys > 0 && !no_lut) ? 2 : 1;
   if (vec) {
