@@ -21,7 +21,8 @@
 //               math (+ residual) -> the thread's staging row in shared memory -> ONE bulk (TMA) store of that row
 //               segment to its destination (window_reverse / un-shift are index math on the destination address).
 //   warp 24     the single thread issuing tcgen05.mma (kind::tf32) + tcgen05.commit.
-//   warp 25     one thread streaming pre-packed weight tiles with 1-D bulk TMA copies.
+//   warp 25     one thread streaming pre-packed weight tiles with 1-D bulk TMA copies whose completion is signalled on
+//               the A-side full barrier of the same k-block (warp 26 forwards it from a separate barrier in pair mode).
 // Four mbarrier pipelines: A landing + A ring (up to 16 stages), B ring (3-4 stages), TMEM accumulator (double buffered: the
 // epilogue of tile i overlaps the loads and MMAs of tile i+1).
 //
@@ -115,6 +116,7 @@ struct LinearParams {
   int lite;        // A operand needs no finalize pass (no LayerNorm, X already TF32-exact): one thread fences + publishes
   int stages_a, stages_b;
   int epi_mode;    // 0: staged slab -> coalesced 16-byte stores by the whole warp; 1: one bulk (TMA) store per row
+  int direct_b;    // the weight copy completes on the A-side full barrier of its k-block (no forwarder hop)
   int pair;        // CTA pairs (cluster of 2) share every weight stage: each CTA fetches half and multicasts it to both
   uint32_t backoff_ns;  // nanosleep between mbarrier probes of the producer-side roles (0 = tight spin)
   int debug_skip;  // bring-up / profiling only (env STF_B200_DEBUG_SKIP): 1 = no A loads, 2 = no B loads, 4 = no stores
@@ -770,6 +772,7 @@ linear_tf32_kernel(const __grid_constant__ LinearParams P) {
       // emptyA[(g - SB) % SA] (phase ((g - SB) / SA) & 1) reports: no separate "empty" barrier for the weights.
       uint32_t sb = 0;
       uint32_t wa = 0, wpa = 0;   // A stage / phase of k-block g - SB
+      uint32_t la = 0;            // A stage of k-block g (direct mode: the copy signals that stage's full barrier itself)
       long long g = 0;
       for (int tile = first_tile; tile < P.total_tiles; tile += tile_step) {
         const int nt = tile % P.n_tiles;
@@ -784,18 +787,20 @@ linear_tf32_kernel(const __grid_constant__ LinearParams P) {
             }
           }
           if (lane == 0) KTRACE(6, (int)(g / P.k_blocks), kb);
+          uint64_t *const bfull = P.direct_b ? &S.fullA[la] : &S.fullB[sb];
+          if (++la == SA) la = 0;
           if (leader) {
             if (dbg & 2) {
-              mbar_arrive(&S.fullB[sb]);
+              mbar_arrive(bfull);
             } else {
-              mbar_arrive_expect_tx(&S.fullB[sb], b_stage_bytes);
+              mbar_arrive_expect_tx(bfull, b_stage_bytes);
               const uint8_t *src = reinterpret_cast<const uint8_t *>(wt + (size_t)kb * kChunks * NT * 4 * planes);
               if (P.pair) {  // this CTA fetches its half of the stage and delivers it to both CTAs
                 const uint32_t half = b_stage_bytes >> 1;
                 bulk_copy_g2s_multicast(S.b_ring + sb * b_stage_bytes + rank * half, src + rank * half, half, &S.fullB[sb],
                                         (uint16_t)0x3);
               } else {
-                bulk_copy_g2s(S.b_ring + sb * b_stage_bytes, src, b_stage_bytes, &S.fullB[sb]);
+                bulk_copy_g2s(S.b_ring + sb * b_stage_bytes, src, b_stage_bytes, bfull);
               }
             }
           }
@@ -813,7 +818,7 @@ linear_tf32_kernel(const __grid_constant__ LinearParams P) {
     // barrier, so the MMA thread -- the serial resource of a K-deep tile -- probes a single barrier per k-block.
     // (B stage g lands only after MMA(g - SB) completed, i.e. after fullA's previous phase completed: the
     // arrival can never be counted into the wrong phase.)
-    if (lane == 0) {
+    if (lane == 0 && !P.direct_b) {
       uint32_t sa = 0, sb = 0, pb = 0;
       const long long total_kb = (long long)((P.total_tiles - first_tile + tile_step - 1) / tile_step) * P.k_blocks;
       for (long long g = 0; g < total_kb; ++g) {
@@ -973,6 +978,13 @@ int launch_linear(const stf_linear_args *args, void *stream) {
     P.stages_a = sa > kMaxStagesA ? kMaxStagesA : sa;
   }
   while (P.fin_group > 1 && (P.fin_group > P.stages_a - 2 || P.k_blocks % P.fin_group != 0)) --P.fin_group;  // a group must fit the ring
+  static const int direct_b_env = [] {
+    const char *e = getenv("STF_B200_DIRECT_B");
+    return e ? atoi(e) : 1;
+  }();
+  // (the weight ring must be shallower than the activation ring: the loader then never signals a full barrier that is
+  // still in the phase of the k-block SA steps earlier)
+  P.direct_b = (direct_b_env && !P.pair && P.stages_b < P.stages_a) ? 1 : 0;
   // the statistics hand-over (kStatSlots tiles deep) relies on a tile spanning at least 3 k-blocks
   if (P.has_ln && P.k_blocks < 3) return STF_E_SHAPE;
   P.Hp = P.Wp = P.nWw = P.nW = 0;
