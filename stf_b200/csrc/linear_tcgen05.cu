@@ -35,6 +35,7 @@
 // i.e. [K/4][rows][4 floats]: 8 consecutive rows x 16 B form one 128-byte UMMA core matrix,
 // SBO = 128 B between 8-row groups, LBO = rows*16 B between the K chunks (verified on B200).
 #include <math.h>
+#include <stdio.h>
 #include <stdlib.h>
 
 #include "common.cuh"
@@ -1013,6 +1014,14 @@ int launch_linear(const stf_linear_args *args, void *stream) {
   }
   const size_t smem = linear_smem_bytes(P.n_tile, P.slab, P.stages_a, P.stages_b, a.N, planes);
   if (smem > 227 * 1024) return STF_E_SHAPE;
+  static const int verbose_env = [] {
+    const char *e = getenv("STF_B200_VERBOSE");
+    return e ? atoi(e) : 0;
+  }();
+  if (verbose_env)
+    fprintf(stderr, "stf_linear M=%d N=%d K=%d epi=%d rows=%d ln=%d prec=%d: n_tile=%d tiles=%d k_blocks=%d stages_a=%d stages_b=%d slab=%d "
+            "fin_group=%d lite=%d direct_b=%d pair=%d smem=%zu\n", a.M, a.N, a.K, a.epilogue, a.rows, P.has_ln, P.precise, P.n_tile,
+            P.total_tiles, P.k_blocks, P.stages_a, P.stages_b, P.slab, P.fin_group, P.lite, P.direct_b, P.pair, smem);
   // Specialised instances for the combinations the model mirrors use; anything else (and every bring-up / tracing
   // run) takes the all-runtime instance.
   using KernelFn = void (*)(const LinearParams);
