@@ -20,7 +20,20 @@ import torch
 from . import _C, ops
 
 
+_ROW_INDEX_CACHE = {}
+
+
 def window_row_index(B, H, W, ws, shift, device):
+    """Cached per geometry (the same few shapes recur every step)."""
+    key = (B, H, W, ws, shift, str(device))
+    if key not in _ROW_INDEX_CACHE:
+        if len(_ROW_INDEX_CACHE) >= 64:
+            _ROW_INDEX_CACHE.clear()
+        _ROW_INDEX_CACHE[key] = _window_row_index(B, H, W, ws, shift, device)
+    return _ROW_INDEX_CACHE[key]
+
+
+def _window_row_index(B, H, W, ws, shift, device):
     """Token index of every row of the window-ordered layout (F.pad + roll(-shift) + window_partition, stf.py:158-171), -1
     for the zero-pad tokens: used to bring token-ordered tensors into window order for the weight-gradient GEMMs."""
     Hp, Wp = ops.ceil_to(H, ws), ops.ceil_to(W, ws)
@@ -32,9 +45,10 @@ def window_row_index(B, H, W, ws, shift, device):
     return idx.reshape(-1)
 
 
-def gather_rows(t, idx):
-    """t[idx] with all-zero rows where idx < 0 (pad tokens are zero after norm1 and their outputs are cropped)."""
-    if bool((idx >= 0).all()):
+def gather_rows(t, idx, has_pad):
+    """t[idx] with all-zero rows where idx < 0 (pad tokens are zero after norm1 and their outputs are cropped).  `has_pad`
+    comes from the geometry on the host: inspecting idx on the device would synchronise the launch queue in every backward."""
+    if not has_pad:
         return t.index_select(0, idx)
     return t.index_select(0, idx.clamp_min(0)) * (idx >= 0).unsqueeze(1).to(t.dtype)
 
@@ -140,7 +154,8 @@ class AttentionBranch(torch.autograd.Function):
         # proj: y_w = o . Wp^T + b, scattered to tokens (pad rows cropped: their gradient is zero, which is what the
         # WINDOW row gather feeds for them)
         d_o = ops.linear(dx1, attn._pp.get_t(wproj), M=B * Hp * Wp, rows=_C.ROWS_WINDOW, geom=geom)
-        dy_w = gather_rows(dx1, idx)
+        has_pad = (Hp != H) or (Wp != W)
+        dy_w = gather_rows(dx1, idx, has_pad)
         dwproj = wgrad(dy_w, o)
         dbproj = colsum(dx1)
         # attention core
@@ -150,14 +165,14 @@ class AttentionBranch(torch.autograd.Function):
             # no LayerNorm: the qkv input gradient lands in token order on top of the shortcut gradient directly
             dx = ops.linear(dqkv, attn._pq.get_t(wqkv), epilogue=_C.EPI_WINDOW_RESIDUAL, residual=dx1, geom=geom,
                             out_rows=B * H * W)
-            dwqkv = wgrad(dqkv, gather_rows(x, idx))
+            dwqkv = wgrad(dqkv, gather_rows(x, idx, has_pad))
             return dx, None, None, dwqkv, colsum(dqkv), dtable, dwproj, dbproj, None, None
         # qkv Linear (window-ordered rows -> token order) then LayerNorm 1, plus the shortcut gradient
         zeros = torch.zeros_like(x)
         g = ops.linear(dqkv, attn._pq.get_t(wqkv), epilogue=_C.EPI_WINDOW_RESIDUAL, residual=zeros, geom=geom,
                        out_rows=B * H * W)
         dx, xn, dg1, db1 = layernorm_bwd(x, g, g1, b1, blk.norm1.eps, res=dx1)
-        dwqkv = wgrad(dqkv, gather_rows(xn, idx))
+        dwqkv = wgrad(dqkv, gather_rows(xn, idx, has_pad))
         dbqkv = colsum(dqkv)
         return dx, dg1, db1, dwqkv, dbqkv, dtable, dwproj, dbproj, None, None
 
