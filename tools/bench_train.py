@@ -67,7 +67,8 @@ def main():
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
-        os.environ.setdefault("NCCL_DEBUG", "WARN")
+        if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
+            os.environ["NCCL_DEBUG"] = "WARN"
         dist.init_process_group("nccl", device_id=dev)
     torch.manual_seed(0)                                   # identical replicas on every rank
     net = SymmetricalTransFormer()                          # constructor defaults: drop_path_rate 0.2 live in train()
