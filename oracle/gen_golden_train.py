@@ -37,6 +37,56 @@ def rd_loss(out, x, lmbda=LMBDA):
     return lmbda * 255 ** 2 * mse + bpp, bpp, mse
 
 
+def record(name, net, Ora, x, latent, probes, out_file):
+    """Live reference in train() mode vs the oracle's restatement on the same noise stream -> golden file."""
+    spec = {k: (tuple(v.shape), v.dtype) for k, v in net.state_dict().items()}
+    sd = synthetic_state_dict(spec, 0)
+    torch.nn.Module.load_state_dict(net, sd, strict=False)
+    net.train()
+    torch.manual_seed(NOISE_SEED)
+    out = net(x)
+    loss, bpp, mse = rd_loss(out, x)
+    loss.backward()
+    ref_grads = {n: p.grad.detach().clone() for n, p in net.named_parameters() if p.grad is not None}
+    ora = Ora({k: v.clone() for k, v in net.state_dict().items()})
+    names = dict(net.named_parameters())
+    for k, v in ora.sd.items():
+        if v.is_floating_point() and k in names:
+            v.requires_grad_(True)
+    B, M, h, w, Cz, hz, wz, slices = latent
+    noise = OC.train_noise(NOISE_SEED, B, M, h, w, Cz, hz, wz, num_slices=slices)
+    o_loss, _, _ = rd_loss(ora.forward_train(x, noise), x)
+    o_loss.backward()
+    assert abs(float(o_loss.detach()) - float(loss.detach())) <= 1e-5 * abs(float(loss.detach())), (float(o_loss), float(loss))
+    worst = 0.0
+    for n, g in ref_grads.items():
+        og = ora.sd[n].grad
+        assert og is not None, n
+        err = float((og - g).abs().max()) / (float(g.abs().max()) + 1e-12)
+        worst = max(worst, err)
+        assert err <= 2e-3, (n, err)
+    print(f"{name}: oracle forward_train == live reference: loss {float(loss.detach())}, worst relative gradient error {worst}")
+    kat = {"noise_seed": NOISE_SEED, "lmbda": LMBDA, "image": {"B": x.shape[0], "H": x.shape[2], "W": x.shape[3], "seed": 7},
+           "weights_seed": 0, "latent": list(latent), "loss": float(loss.detach()), "bpp_loss": float(bpp.detach()),
+           "mse_loss": float(mse.detach()),
+           "grad_norm": {n: float(g.norm()) for n, g in ref_grads.items()},
+           "grad_absmax": {n: float(g.abs().max()) for n, g in ref_grads.items()},
+           "grad_probe": {n: ref_grads[n].reshape(-1)[:: max(1, ref_grads[n].numel() // 16)][:16].tolist() for n in probes}}
+    with open(os.path.join(GOLD, out_file), "w") as f:
+        json.dump(kat, f, indent=0)
+    print("wrote", os.path.join(GOLD, out_file), len(kat["grad_norm"]), "parameters")
+
+
+def main_wacnn():
+    import_reference()
+    from compressai.models.cnn import WACNN
+    torch.manual_seed(0)
+    x = synthetic_image(1, 64, 128, seed=7)
+    record("cnn", WACNN(), OC.WacnnOracle, x, (1, 320, 4, 8, 192, 1, 2, 10),
+           ("g_a.4.conv_b.0.attn.relative_position_bias_table", "g_a.8.conv_b.0.attn.qkv.weight", "g_s.0.conv_b.0.attn.proj.weight",
+            "entropy_bottleneck._matrix1", "cc_mean_transforms.2.0.weight"), "train_kat_cnn.json")
+
+
 def main():
     import_reference()
     from compressai.models.stf import SymmetricalTransFormer
@@ -85,4 +135,7 @@ def main():
 
 
 if __name__ == "__main__":
-    main()
+    if "--stf-only" not in sys.argv:
+        main_wacnn()
+    if "--cnn-only" not in sys.argv:
+        main()

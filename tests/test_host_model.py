@@ -70,3 +70,30 @@ def test_entropy_model_argument_errors():
         eb.decompress([b"12345678"], (2, 2))
     with pytest.raises(ValueError):
         eb.quantize(torch.zeros(2), "nope")
+
+
+def test_rate_distortion_loss_and_optimizer_split():
+    """train.py:39-59 (loss) and train.py:88-120 (the two Adam parameter sets) -- host logic, CPU only."""
+    import math
+    from stf_b200.models import SymmetricalTransFormer, WACNN
+    from stf_b200.training import RateDistortionLoss, configure_optimizers
+    g = torch.Generator().manual_seed(0)
+    x = torch.rand(2, 3, 16, 24, generator=g)
+    xh = torch.rand(2, 3, 16, 24, generator=g)
+    lik = {"y": torch.rand(2, 8, 1, 2, generator=g) * 0.9 + 0.05, "z": torch.rand(2, 4, 1, 1, generator=g) * 0.9 + 0.05}
+    out = RateDistortionLoss(0.0035)({"x_hat": xh, "likelihoods": lik}, x)
+    bpp = -(np.log2(lik["y"].double().numpy()).sum() + np.log2(lik["z"].double().numpy()).sum()) / (2 * 16 * 24)
+    mse = float(((xh.double() - x.double()) ** 2).mean())
+    assert abs(float(out["bpp_loss"]) - bpp) <= 1e-5 * bpp
+    assert abs(float(out["mse_loss"]) - mse) <= 1e-5 * mse
+    assert abs(float(out["loss"]) - (0.0035 * 255 ** 2 * mse + bpp)) <= 1e-5 * float(out["loss"])
+    assert math.isfinite(float(out["loss"]))
+    for Net in (SymmetricalTransFormer, WACNN):
+        net = Net()
+        opt, aux = configure_optimizers(net, 1e-4, 1e-3)
+        named = dict(net.named_parameters())
+        aux_ids = {id(p) for grp in aux.param_groups for p in grp["params"]}
+        main_ids = {id(p) for grp in opt.param_groups for p in grp["params"]}
+        assert aux_ids == {id(p) for n, p in named.items() if n.endswith(".quantiles")} and len(aux_ids) == 1
+        assert not aux_ids & main_ids and len(aux_ids) + len(main_ids) == len(named)
+        assert opt.param_groups[0]["lr"] == 1e-4 and aux.param_groups[0]["lr"] == 1e-3

@@ -215,3 +215,30 @@ def test_training_restatement_matches_recorded_reference(golden_dir):
     for n, ref in kat["grad_norm"].items():
         got = float(ora.sd[n].grad.norm())
         assert abs(got - ref) <= 1e-4 * ref + 1e-9, (n, got, ref)
+
+
+def test_wacnn_training_restatement_matches_recorded_reference(golden_dir):
+    """Same pin for WACNN (cnn.py) in train() mode: tests/golden/train_kat_cnn.json."""
+    import math
+    from oracle import codec as OC
+    from stf_b200.synth import synthetic_image
+    kat = json.load(open(os.path.join(golden_dir, "train_kat_cnn.json")))
+    spec = {k: (tuple(s), getattr(torch, d.split(".")[-1])) for k, (s, d) in
+            json.load(open(os.path.join(golden_dir, "cnn_spec.json"))).items()}
+    ora = OC.WacnnOracle(synthetic_state_dict(spec, kat["weights_seed"]))
+    for k, v in ora.sd.items():
+        if k in kat["grad_norm"]:
+            v.requires_grad_(True)
+    im = kat["image"]
+    x = synthetic_image(im["B"], im["H"], im["W"], seed=im["seed"])
+    B, M, h, w, Cz, hz, wz, slices = kat["latent"]
+    noise = OC.train_noise(kat["noise_seed"], B, M, h, w, Cz, hz, wz, num_slices=slices)
+    out = ora.forward_train(x, noise)
+    n_px = im["B"] * im["H"] * im["W"]
+    bpp = sum(torch.log(l).sum() / (-math.log(2) * n_px) for l in out["likelihoods"].values())
+    loss = kat["lmbda"] * 255 ** 2 * torch.nn.functional.mse_loss(out["x_hat"], x) + bpp
+    loss.backward()
+    assert abs(float(loss.detach()) - kat["loss"]) <= 1e-5 * abs(kat["loss"])
+    for n, ref in kat["grad_norm"].items():
+        got = float(ora.sd[n].grad.norm())
+        assert abs(got - ref) <= 1e-4 * ref + 1e-9, (n, got, ref)
