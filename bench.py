@@ -155,6 +155,23 @@ def run_reference(args, rank):
 
 # ----------------------------------------------------------------------------- product arm
 
+def init_nccl_quiet(dist, dev):
+    """NCCL process group + first collective with fd 1 pointed at stderr: whatever NCCL_DEBUG level the environment sets,
+    NCCL's banner ("NCCL version ...", printed on stdout at communicator creation) stays out of the one-JSON-line stdout."""
+    sys.stdout.flush()
+    saved = os.dup(1)
+    os.dup2(2, 1)
+    try:
+        dist.init_process_group("nccl", device_id=dev)
+        dist.barrier()
+        import torch
+        torch.cuda.synchronize()
+    finally:
+        sys.stdout.flush()
+        os.dup2(saved, 1)
+        os.close(saved)
+
+
 def run_ours(args, rank, world, local_rank):
     import torch
     import torch.distributed as dist
@@ -166,9 +183,7 @@ def run_ours(args, rank, world, local_rank):
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     if world > 1:
-        if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
-            os.environ["NCCL_DEBUG"] = "WARN"      # keep NCCL's version banner off stdout (one JSON line only)
-        dist.init_process_group("nccl", device_id=dev)
+        init_nccl_quiet(dist, dev)
 
     def barrier():
         if world > 1:

@@ -84,12 +84,10 @@ class _wgrad_precision:
     """dW = dY^T . X is a plain library GEMM (cuBLAS).  By default it may use TF32 tensor cores: the products are summed
     over 10^4 .. 10^5 token rows, so the 2^-11 operand rounding averages out (measured gradient error vs the fp32
     reference: < 1e-3 of the tensor's max); STF_B200_WGRAD_FP32=1 keeps cuBLAS in fp32 (SIMT SGEMM, ~8x slower)."""
-    import os as _os
-    _fp32 = _os.environ.get("STF_B200_WGRAD_FP32", "0") == "1"
-
     def __enter__(self):
+        import os
         self.old = torch.backends.cuda.matmul.allow_tf32
-        if not self._fp32:
+        if os.environ.get("STF_B200_WGRAD_FP32", "0") != "1":
             torch.backends.cuda.matmul.allow_tf32 = True
 
     def __exit__(self, *exc):

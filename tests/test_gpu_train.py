@@ -250,41 +250,52 @@ def test_wacnn_training_step_gradients(golden_dir):
     assert worst[1] <= 5e-3       # (observed 2.8e-4; cuDNN TF32 convolutions dominate this model)
 
 
-def test_wacnn_training_gradients_match_recorded_reference(golden_dir):
+@pytest.mark.parametrize("conv_tf32", [False, True])
+def test_wacnn_training_gradients_match_recorded_reference(golden_dir, conv_tf32, monkeypatch):
     """WACNN loss and every gradient norm against what the live reference produced in train() mode on the same weights,
-    image and noise stream (tests/golden/train_kat_cnn.json, oracle/gen_golden_train.py)."""
+    image and noise stream (tests/golden/train_kat_cnn.json, oracle/gen_golden_train.py).  With cuDNN's TF32 convolutions
+    off (and fp32 wgrad) every gradient norm is within 1e-3 (observed 8e-5, loss to 1e-7); with torch's default TF32
+    convolutions the bound is the usual 5e-3 on every parameter whose gradient is not vanishing."""
     from stf_b200.models import WACNN
     from stf_b200.training import RateDistortionLoss
     kat = json.load(open(os.path.join(golden_dir, "train_kat_cnn.json")))
     spec = {k: (tuple(s), getattr(torch, d.split(".")[-1])) for k, (s, d) in
             json.load(open(os.path.join(golden_dir, "cnn_spec.json"))).items()}
-    net = WACNN()
-    torch.nn.Module.load_state_dict(net, synthetic_state_dict(spec, kat["weights_seed"]), strict=False)
-    net = net.cuda().train()
-    im = kat["image"]
-    x = synthetic_image(im["B"], im["H"], im["W"], seed=im["seed"]).cuda()
-    B, M, h, w, Cz, hz, wz, slices = kat["latent"]
-    noise = OC.train_noise(kat["noise_seed"], B, M, h, w, Cz, hz, wz, num_slices=slices)
-    out = RateDistortionLoss(kat["lmbda"])(net(x, noise={k: v.cuda() for k, v in noise.items()}), x)
-    out["loss"].backward()
+    monkeypatch.setenv("STF_B200_WGRAD_FP32", "0" if conv_tf32 else "1")
+    saved = torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32
+    torch.backends.cudnn.allow_tf32 = torch.backends.cuda.matmul.allow_tf32 = conv_tf32
+    try:
+        net = WACNN()
+        torch.nn.Module.load_state_dict(net, synthetic_state_dict(spec, kat["weights_seed"]), strict=False)
+        net = net.cuda().train()
+        im = kat["image"]
+        x = synthetic_image(im["B"], im["H"], im["W"], seed=im["seed"]).cuda()
+        B, M, h, w, Cz, hz, wz, slices = kat["latent"]
+        noise = OC.train_noise(kat["noise_seed"], B, M, h, w, Cz, hz, wz, num_slices=slices)
+        out = RateDistortionLoss(kat["lmbda"])(net(x, noise={k: v.cuda() for k, v in noise.items()}), x)
+        out["loss"].backward()
+        torch.cuda.synchronize()
+    finally:
+        torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32 = saved
+    tol, floor = (5e-3, 1e-4) if conv_tf32 else (1e-3, 1e-9)
     for k in ("loss", "bpp_loss", "mse_loss"):
-        assert abs(float(out[k].detach()) - kat[k]) <= 2e-3 * abs(kat[k]), (k, float(out[k].detach()), kat[k])
+        assert abs(float(out[k].detach()) - kat[k]) <= (2e-3 if conv_tf32 else 1e-5) * abs(kat[k]), (k, float(out[k].detach()), kat[k])
     worst = ("", 0.0)
     for n, p in net.named_parameters():
         ref = kat["grad_norm"].get(n)
-        if ref is None or ref < 1e-9:
+        if ref is None or ref < floor:
             continue
         assert p.grad is not None, n
         err = abs(float(p.grad.norm()) - ref) / ref
         if err > worst[1]:
             worst = (n, err)
-    print(f"WACNN vs recorded reference: loss {float(out['loss'].detach()):.4f} ({kat['loss']:.4f}), worst gradient-norm "
-          f"error {worst[1]:.2e} at {worst[0]}")
-    assert worst[1] <= 5e-3
+    print(f"WACNN vs recorded reference (cuDNN TF32 {conv_tf32}): loss {float(out['loss'].detach()):.5f} ({kat['loss']:.5f}), "
+          f"worst gradient-norm error {worst[1]:.2e} at {worst[0]}")
+    assert worst[1] <= tol
     for n, probe in kat["grad_probe"].items():
         gp = dict(net.named_parameters())[n].grad.reshape(-1)
         got = gp[:: max(1, gp.numel() // 16)][:16].cpu()
-        assert float((got - torch.tensor(probe)).abs().max()) <= 5e-3 * kat["grad_absmax"][n] + 1e-9, n
+        assert float((got - torch.tensor(probe)).abs().max()) <= tol * kat["grad_absmax"][n] + 1e-9, n
 
 
 def test_training_c_abi_argument_errors():

@@ -67,9 +67,7 @@ def main():
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
-        if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
-            os.environ["NCCL_DEBUG"] = "WARN"
-        dist.init_process_group("nccl", device_id=dev)
+        bench.init_nccl_quiet(dist, dev)
     torch.manual_seed(0)                                   # identical replicas on every rank
     net = SymmetricalTransFormer()                          # constructor defaults: drop_path_rate 0.2 live in train()
     torch.nn.Module.load_state_dict(net, bench.synthetic_weights(), strict=False)
