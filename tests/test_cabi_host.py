@@ -33,6 +33,13 @@ def test_library_exports_every_declared_symbol():
     assert b"sm_100a" in _C.lib().stf_version()
 
 
+def test_every_entry_point_is_mapped_to_the_reference_in_integration_md():
+    """INTEGRATION.md names, for every exported function, the reference code it replaces."""
+    doc = open(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "INTEGRATION.md")).read()
+    missing = [n for n in header_functions() if n not in doc]
+    assert not missing, missing
+
+
 def test_library_contains_sm100a_tcgen05_code():
     """The shipped .so carries sm_100a SASS with tcgen05 (UTC*MMA) and bulk-TMA (UBLKCP) instructions."""
     import shutil
