@@ -201,6 +201,36 @@ def test_pipelined_halves_equal_single_part(golden_dir, monkeypatch):
     assert (dec2 - fwd).abs().max().item() < 2e-2                      # exact when the conv algorithms coincide
 
 
+def test_three_ragged_sub_batches_from_48_images(golden_dir):
+    """From 48 images compress / decompress run three pipelined sub-batches (50 images -> 17 + 16 + 17): every image's
+    own stream decodes to what a batch-1 compress / decompress of that image gives (up to cuDNN's per-batch algorithm
+    choice), and the decoder's reconstruction equals the forward pass."""
+    from stf_b200 import models as M
+    net, _ = _build(golden_dir, "stf")
+    assert [hi - lo for lo, hi in net._parts(50, True)] == [17, 16, 17]
+    assert [hi - lo for lo, hi in net._parts(64, True)] == [21, 22, 21] and len(net._parts(32, True)) == 2
+    x = torch.cat([synthetic_image(1, 64, 64, seed=100 + s) for s in range(50)]).cuda()
+    enc = net.compress(x)
+    assert [len(g) for g in enc["strings"]] == [50, 50]
+    dec = net.decompress(enc["strings"], enc["shape"])["x_hat"].clone()
+    # forward pass on the same partition (cuDNN may pick per-batch-size algorithms: a rare flipped symbol moves a patch
+    # of one image, a wrong image / slot mapping would move everything)
+    fwd = torch.cat([net(x[lo:hi])["x_hat"].clamp(0, 1) for lo, hi in net._parts(50, True)])
+    per_image = (dec - fwd).abs().flatten(1).max(dim=1).values
+    print(f"50 images in 3 sub-batches: decoder vs forward PSNR {psnr(dec, fwd):.1f} dB, per-image max diff median "
+          f"{per_image.median().item():.2e}, worst {per_image.max().item():.2e}")
+    assert psnr(dec, fwd) > 30.0 and per_image.median().item() < 2e-2
+    same = 0
+    for i in (0, 16, 17, 32, 33, 49):                                  # first / last image of every sub-batch
+        e1 = net.compress(x[i:i + 1])
+        same += e1["strings"][0][0] == enc["strings"][0][i] and e1["strings"][1][0] == enc["strings"][1][i]
+        d1 = net.decompress(e1["strings"], e1["shape"])["x_hat"]
+        assert psnr(d1, dec[i:i + 1]) > 30.0, i
+    print(f"batch-1 strings identical for {same} of 6 probed images")
+    enc2 = net.compress(x)                                             # graph replays of the three parts
+    assert enc2["strings"] == enc["strings"]
+
+
 def test_cuda_graph_path_equals_eager(golden_dir):
     net, _ = _build(golden_dir, "stf")
     x = synthetic_image(2, 64, 128, seed=11).cuda()
