@@ -11,9 +11,10 @@ One JSON line is printed by rank 0:
                byte strings -> decompress -> x_hat -> D2H, all inside the timed region
   roofline     dominant stf_b200 kernel (by device time over one instrumented step): algorithmic bytes
                per launch / CUDA-event time per launch vs the measured HBM peak
-  cpu_baseline the CPU oracle port of the reference's path timed on this box's host cores (N=1 only)
+  cpu_baseline the UNMODIFIED reference (the byte-for-byte copy `make -C oracle` leaves in the git-ignored oracle/_ref:
+               its Python model code + its own C++ rANS extension) timed on this box's host cores (N=1 only)
 `--impl reference` times that CPU implementation alone (rank 0 only), same metric/unit/config.
-Nothing here reads /root/reference.
+Nothing here reads /root/reference at run time on the GPU box.
 """
 import argparse
 import json
@@ -103,29 +104,50 @@ def synthetic_weights():
 
 # ----------------------------------------------------------------------------- CPU reference arm
 
-def cpu_reference_rate(steps, warmup, log=None):
-    """The CPU oracle port of the reference's STF compress/decompress (torch CPU ops in the
-    reference's order, all host threads; rANS = the reference's own C++ coder from oracle/_ref when
-    it was built, else the C restatement).  One 768x512 image per step."""
+def _reference_net(device="cpu"):
+    """The UNMODIFIED reference model (compressai.zoo.models['stf'] from oracle/_ref/compressai -- the byte-for-byte copy
+    `make -C oracle` leaves there -- or /root/reference in the build container) with the bench's synthetic weights."""
     import torch
-    from oracle import codec as OC
+    from oracle.ref_import import import_reference
+    import_reference()
+    from compressai.zoo import models as zoo
+    net = zoo["stf"]()
+    torch.nn.Module.load_state_dict(net, synthetic_weights(), strict=False)
+    net = net.to(device).eval()
+    net.update(force=True)
+    return net
+
+
+def cpu_reference_rate(steps, warmup, log=None):
+    """The reference's own CPU implementation of the path, timed on this box's host cores with all of them
+    (torch intra-op threads = os.cpu_count()): compress() + decompress() of one 768x512 image per step.
+    kind "reference": the unmodified reference Python + its own C++ rANS extension (oracle/_ref);
+    kind "port": the oracle restatement (only when the reference copy was not built)."""
+    import torch
     from stf_b200.synth import synthetic_image
-    rans = "oracle"
-    try:
-        from oracle.ref_import import load_ref_ans
-        load_ref_ans()
-        rans = "ref"
-    except Exception:
-        pass
     threads = os.cpu_count() or 1
     torch.set_num_threads(threads)
-    ora = OC.StfOracle(synthetic_weights(), rans=rans)
+    kind, what = "reference", "unmodified reference (compressai.models.stf.SymmetricalTransFormer.compress/decompress, its own C++ rANS)"
+    try:
+        net = _reference_net("cpu")
+
+        def run(x):
+            with torch.no_grad():
+                enc = net.compress(x)
+                net.decompress(enc["strings"], enc["shape"])
+    except Exception as e:   # the copy was not built: the oracle port stands in
+        from oracle import codec as OC
+        kind, what = "port", f"oracle port of stf.py on torch CPU ops (reference copy unavailable: {type(e).__name__})"
+        ora = OC.StfOracle(synthetic_weights())
+
+        def run(x):
+            enc = ora.compress(x)
+            ora.decompress(enc["strings"], enc["shape"])
     times = []
     for i in range(warmup + steps):
         x = synthetic_image(1, H, W, seed=100 + i)
         t0 = time.perf_counter()
-        enc = ora.compress(x)
-        ora.decompress(enc["strings"], enc["shape"])
+        run(x)
         dt = time.perf_counter() - t0
         if i >= warmup:
             times.append(dt)
@@ -133,10 +155,29 @@ def cpu_reference_rate(steps, warmup, log=None):
             log(f"cpu reference step {i}: {dt:.2f}s")
     total = sum(times)
     mpx = steps * H * W / total / 1e6
-    return mpx, total / steps * 1e3, {"value": mpx, "unit": "Mpixel/s", "cores": torch.get_num_threads(), "kind": "port",
-                                      "sample": f"{steps} x (1 image 768x512 compress+decompress) after {warmup} warm-up, "
-                                                f"oracle port of stf.py on torch CPU ops, rANS coder = "
-                                                f"{'reference C++ (oracle/_ref)' if rans == 'ref' else 'oracle C restatement'}"}
+    return mpx, total / steps * 1e3, {"value": mpx, "unit": "Mpixel/s", "cores": torch.get_num_threads(), "kind": kind,
+                                      "sample": f"{steps} x (1 image 768x512 compress+decompress) after {warmup} warm-up, {what}"}
+
+
+def gpu_eager_reference_rate(steps=3, warmup=1):
+    """Context number (eval_model/__main__.py:103-110): the unmodified reference moved .to("cuda"), eager,
+    batch 1, timed the way its own evaluator does (wall clock around compress and decompress, device synchronised)."""
+    import torch
+    from stf_b200.synth import synthetic_image
+    net = _reference_net("cuda")
+    times = []
+    for i in range(warmup + steps):
+        x = synthetic_image(1, H, W, seed=100 + i).cuda()
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        with torch.no_grad():
+            enc = net.compress(x)
+            net.decompress(enc["strings"], enc["shape"])
+        torch.cuda.synchronize()
+        if i >= warmup:
+            times.append(time.perf_counter() - t0)
+    return {"value": steps * H * W / sum(times) / 1e6, "unit": "Mpixel/s", "batch": 1,
+            "what": "unmodified reference, model.to('cuda'), eager, 1 image 768x512 per step (context only)"}
 
 
 def run_reference(args, rank):
@@ -147,7 +188,8 @@ def run_reference(args, rank):
         "impl": "reference", "metric": METRIC, "value": mpx, "unit": "Mpixel/s", "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic",
-        "config": {"workload": "STF compress+decompress, 1 image 768x512 per step on host CPU cores (bounded sample)"},
+        "config": {"workload": "STF compress+decompress, 1 image 768x512 per step on host CPU cores (bounded sample of the product arm's batch)",
+                   "image": [H, W], "implementation": base["kind"]},
         "cpu_baseline": base,
         "e2e": {"value": mpx, "unit": "Mpixel/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0}), flush=True)

@@ -18,9 +18,13 @@ import os
 import sys
 import types
 
-REF_ROOT = os.environ.get("STF_REFERENCE_ROOT", "/root/reference")
 _HERE = os.path.dirname(os.path.abspath(__file__))
 REF_SO_DIR = os.path.join(_HERE, "_ref")
+# /root/reference in the build container; on the GPU box the byte-for-byte copy that `make -C oracle` left in
+# oracle/_ref/compressai (a git-ignored build output, see oracle/Makefile)
+REF_ROOT = os.environ.get("STF_REFERENCE_ROOT", "/root/reference")
+if not os.path.isdir(os.path.join(REF_ROOT, "compressai")) and os.path.isdir(os.path.join(REF_SO_DIR, "compressai")):
+    REF_ROOT = REF_SO_DIR
 
 
 def reference_available() -> bool:

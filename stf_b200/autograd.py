@@ -80,24 +80,52 @@ def colsum(a):
     return part.sum(0)
 
 
-class _wgrad_precision:
-    """dW = dY^T . X is a plain library GEMM (cuBLAS).  By default it may use TF32 tensor cores: the products are summed
-    over 10^4 .. 10^5 token rows, so the 2^-11 operand rounding averages out (measured gradient error vs the fp32
-    reference: < 1e-3 of the tensor's max); STF_B200_WGRAD_FP32=1 keeps cuBLAS in fp32 (SIMT SGEMM, ~8x slower)."""
+def wgrad(dy, x):
+    """dW = dY^T . X, a plain library GEMM (cuBLAS through torch).  Its arithmetic follows the library's precision mode
+    (ops.precision()): "fp32" -> 3xTF32-grade via a manual hi/lo split of both operands on TF32 tensor cores (three GEMMs,
+    fp32 accumulate; the dropped lo.lo term is below fp32 round-off), "tf32" -> one TF32 GEMM.  Each product runs under
+    a scoped, lock-protected TF32 override that always restores the caller's setting (STF_B200_WGRAD_FP32=1: plain fp32
+    SIMT SGEMM instead, ~8x slower)."""
+    import os
+    if os.environ.get("STF_B200_WGRAD_FP32", "0") == "1":
+        with _tf32_matmul(False):
+            return dy.t().mm(x)
+    with _tf32_matmul(True):
+        if ops.precision() != "fp32":
+            return dy.t().mm(x)
+        a, b = dy.t(), x
+        a_hi, b_hi = _tf32_trunc(a), _tf32_trunc(b)
+        a_lo, b_lo = a - a_hi, b - b_hi          # exact in fp32; the GEMM reads its upper 11 bits: x = hi + lo to 2^-22
+        out = a_hi.mm(b_hi)
+        out.addmm_(a_lo, b_hi)
+        out.addmm_(a_hi, b_lo)
+        return out
+
+
+def _tf32_trunc(t):
+    """Keep the upper 19 bits (sign, exponent, 10 mantissa bits): the value a TF32 tensor core reads from an fp32 word."""
+    return (t.contiguous().view(torch.int32) & -8192).view(torch.float32)
+
+
+class _tf32_matmul:
+    """Scoped TF32 switch for torch.mm with a re-entrancy lock: autograd runs backward nodes of one device on one
+    worker thread, but user code may call matmuls from other threads; the lock keeps the flag flip + GEMM atomic with
+    respect to other wgrad calls and the old value is always restored."""
+    import threading
+    _lock = threading.RLock()
+
+    def __init__(self, on):
+        self.on = on
+
     def __enter__(self):
-        import os
+        self._lock.acquire()
         self.old = torch.backends.cuda.matmul.allow_tf32
-        if os.environ.get("STF_B200_WGRAD_FP32", "0") != "1":
-            torch.backends.cuda.matmul.allow_tf32 = True
+        torch.backends.cuda.matmul.allow_tf32 = self.on
 
     def __exit__(self, *exc):
         torch.backends.cuda.matmul.allow_tf32 = self.old
+        self._lock.release()
         return False
-
-
-def wgrad(dy, x):
-    with _wgrad_precision():
-        return dy.t().mm(x)
 
 
 def gelu_bwd(pre, dh):
@@ -137,6 +165,7 @@ class AttentionBranch(torch.autograd.Function):
                         out_rows=B * H * W, x_is_tf32=True)
         ctx.save_for_backward(x, g1, b1, wqkv, table, wproj, qkv, o)
         ctx.blk, ctx.geom = blk, geom
+        ctx.has_bqkv, ctx.has_bproj = bqkv is not None, bproj is not None
         return x1
 
     @staticmethod
@@ -164,15 +193,16 @@ class AttentionBranch(torch.autograd.Function):
             dx = ops.linear(dqkv, attn._pq.get_t(wqkv), epilogue=_C.EPI_WINDOW_RESIDUAL, residual=dx1, geom=geom,
                             out_rows=B * H * W)
             dwqkv = wgrad(dqkv, gather_rows(x, idx, has_pad))
-            return dx, None, None, dwqkv, colsum(dqkv), dtable, dwproj, dbproj, None, None
+            return (dx, None, None, dwqkv, colsum(dqkv) if ctx.has_bqkv else None, dtable, dwproj,
+                    dbproj if ctx.has_bproj else None, None, None)
         # qkv Linear (window-ordered rows -> token order) then LayerNorm 1, plus the shortcut gradient
         zeros = torch.zeros_like(x)
         g = ops.linear(dqkv, attn._pq.get_t(wqkv), epilogue=_C.EPI_WINDOW_RESIDUAL, residual=zeros, geom=geom,
                        out_rows=B * H * W)
         dx, xn, dg1, db1 = layernorm_bwd(x, g, g1, b1, blk.norm1.eps, res=dx1)
         dwqkv = wgrad(dqkv, gather_rows(xn, idx, has_pad))
-        dbqkv = colsum(dqkv)
-        return dx, dg1, db1, dwqkv, dbqkv, dtable, dwproj, dbproj, None, None
+        dbqkv = colsum(dqkv) if ctx.has_bqkv else None      # qkv_bias=False: the input was None (stf.py:66)
+        return dx, dg1, db1, dwqkv, dbqkv, dtable, dwproj, dbproj if ctx.has_bproj else None, None, None
 
 
 class MlpBranch(torch.autograd.Function):

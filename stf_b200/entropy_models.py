@@ -15,7 +15,9 @@ What runs where:
     buffers copied once from the device, one stream per image on its own host thread;
   * update() (CDF table construction, once per model) = host-side set-up in torch CPU fp32, in the
     reference's operation order so the tables are bit-identical, quantised by stf_pmf_to_quantized_cdf.
-Training-mode forward (additive noise + autograd) is not implemented in this round and raises.
+Training-mode forward (additive noise, ste_round, LowerBound gradient rule): GaussianConditional through
+stf_b200/autograd.py's fused likelihood kernels, EntropyBottleneck through torch autograd over the reference's op
+sequence (an 18 k-element tensor); see DESIGN.md section 4.5.
 """
 import math
 

@@ -16,8 +16,9 @@ kernel launches instead of ~40 --
   4. norm2 + fc1 + exact GELU                                           -> stf_linear (LN, GELU epilogue)
   5. fc2 + residual                                                     -> stf_linear (RESIDUAL epilogue)
 No mask tensor, no rolled / partitioned copies and no (B_, nH, N, N) score tensor are materialised.
-There is no eager fallback: CPU tensors raise, training-mode forward raises (backward kernels are
-not part of this round).
+There is no eager fallback: CPU tensors raise.  Training (train() + grad enabled) runs the same forward kernels
+inside the autograd Functions of stf_b200/autograd.py (hand-written backward kernels); only the
+stand-alone WindowAttention.forward(x, mask) module has no backward and says so.
 """
 import math
 

@@ -102,7 +102,55 @@ class CompressionModel(nn.Module):
     def aux_loss(self):
         return sum(m.loss() for m in self.modules() if isinstance(m, EntropyBottleneck))
 
+    # ------------------------------------------------------------------ CUDA-graph plan validity
+    # A captured plan bakes in raw pointers to (and, for the scale table, values of) buffers DERIVED from the
+    # parameters: packed weight images, the EntropyBottleneck's pre-activated parameter block, medians, the host scale
+    # table passed by value.  They are rebuilt -- and the old ones freed -- when a parameter changes (optimizer.step(),
+    # load_state_dict(), update(force=True), .to(), set_precision()).  Every plan cache is therefore tagged with a
+    # "weights epoch": storage pointer + in-place version counter of every parameter and buffer, plus the GEMM precision
+    # mode.  A mismatch drops all plans; the next call re-captures from the live weights.
+    def _weights_epoch(self):
+        ts = self.__dict__.get("_epoch_tensors")
+        if ts is None:   # the module tree walk is the slow part: cached until the next _drop_plans()
+            ts = self.__dict__["_epoch_tensors"] = list(self.parameters()) + list(self.buffers())
+        return hash((ops.precision_code(), tuple([t.data_ptr() for t in ts]), tuple([t._version for t in ts])))
+
+    def _plans(self, name):
+        """Plan cache `name` for the current weights epoch (all caches are dropped when the epoch changed)."""
+        d = self.__dict__
+        epoch = self._weights_epoch()
+        if d.get("_plan_epoch") != epoch:
+            self._drop_plans()
+            d["_plan_epoch"] = epoch
+        return d.setdefault(name, {})
+
+    @staticmethod
+    def _plan_slot(plans, key, cap):
+        """LRU bookkeeping for a plan cache: returns True when `key` is cached (and marks it most recently used),
+        else evicts the least recently used entries down to cap - 1 (mixed-size workloads keep their hot shapes
+        instead of re-capturing everything whenever a fifth shape shows up)."""
+        if key in plans:
+            plans[key] = plans.pop(key)
+            return True
+        while len(plans) >= cap:
+            plans.pop(next(iter(plans)))
+        return False
+
+    def _drop_plans(self):
+        for k in ("_fwd_plans", "_enc_plans", "_dec_plans", "_plan_epoch", "_epoch_tensors"):
+            self.__dict__.pop(k, None)
+
+    def train(self, mode=True):
+        if mode != self.training:
+            self._drop_plans()      # an optimizer step between two eval phases changes the weights in place
+        return super().train(mode)
+
+    def _apply(self, fn, *args, **kwargs):
+        self._drop_plans()          # .to() / .cuda() / .float(): new storages
+        return super()._apply(fn, *args, **kwargs)
+
     def update(self, force=False):
+        self._drop_plans()
         updated = False
         for m in self.children():
             if isinstance(m, EntropyBottleneck):
@@ -110,6 +158,7 @@ class CompressionModel(nn.Module):
         return updated
 
     def load_state_dict(self, state_dict, strict=True):
+        self._drop_plans()
         _resize_buffers(self.entropy_bottleneck, "entropy_bottleneck", ["_quantized_cdf", "_offset", "_cdf_length"],
                         state_dict)
         return super().load_state_dict(state_dict, strict=strict)
@@ -250,11 +299,9 @@ class _SliceCodec(CompressionModel):
                 return self._forward_eval(x)
             # one CUDA graph per input shape (~340 launches of ours + cuDNN, launch-bound when issued eagerly); the
             # returned tensors are clones: the graph's static outputs are overwritten by the next call
-            plans = self.__dict__.setdefault("_fwd_plans", {})
+            plans = self._plans("_fwd_plans")
             key = tuple(x.shape)
-            if key not in plans:
-                if len(plans) >= 4:
-                    plans.clear()
+            if not self._plan_slot(plans, key, 8):
                 self._prepare_inference()
 
                 def fn(t):
@@ -381,14 +428,12 @@ class _SliceCodec(CompressionModel):
         parts = self._parts(x.shape[0], use_graphs)
         stream = torch.cuda.current_stream()
         pending = []
+        plans = self._plans("_enc_plans") if use_graphs else None      # (validated against the weights epoch once per call)
         for slot, (lo, hi) in enumerate(parts):
             xp = x[lo:hi]
             if use_graphs:
-                plans = self.__dict__.setdefault("_enc_plans", {})
                 key = tuple(xp.shape)
-                if key not in plans:
-                    if len(plans) >= 4:
-                        plans.clear()
+                if not self._plan_slot(plans, key, 8):
                     plans[key] = graphs.Segment(lambda t: self._encode_gpu(t), [xp])
                 sym, idx, z_sym = plans[key](xp)
             else:
@@ -472,14 +517,11 @@ class _SliceCodec(CompressionModel):
         y_hat = torch.cat(st["y_hat"], dim=1)
         return self._synthesis(y_hat).clamp_(0, 1)
 
-    def _decode_plan(self, slot, B, C, zh, zw, device):
+    def _decode_plan(self, plans, slot, B, C, zh, zw, device):
         """13 CUDA-graph segments on one shared memory pool, captured once per (slot, B, z shape)."""
-        plans = self.__dict__.setdefault("_dec_plans", {})
         key = (slot, B, zh, zw)
-        if key in plans:
+        if self._plan_slot(plans, key, 12):
             return plans[key]
-        if len(plans) >= 6:
-            plans.clear()
         h, w = zh * 4, zw * 4
         n = self.slice_channels * h * w
         st = {"hw": (h, w)}
@@ -515,10 +557,11 @@ class _SliceCodec(CompressionModel):
             pass
 
         parts = []
+        plans = self._plans("_dec_plans") if use_graphs else None
         for slot, (lo, hi) in enumerate(self._parts(B, use_graphs, _DEC_PARTS)):
             p = Part()
             p.B = hi - lo
-            p.segs, p.st = self._decode_plan(slot, p.B, C, zh, zw, device) if use_graphs else (None, {"hw": (h, w)})
+            p.segs, p.st = self._decode_plan(plans, slot, p.B, C, zh, zw, device) if use_graphs else (None, {"hw": (h, w)})
             p.decoders = _decoders(strings[0][lo:hi])
             p.sym_h, p.idx_h = self._host_buffers(("y", slot), p.B, n)
             p.zsym_h, _ = self._host_buffers(("z", slot), p.B, C * zh * zw)
