@@ -66,6 +66,31 @@ int stf_gaussian_compress_step(const float *y, int64_t y_batch_stride, const flo
                                int64_t plane, const float *table_host, int levels,
                                float scale_bound, void *stream);
 
+/* The same slice steps on NHWC operands -- the layout of the convolution kernel below, so the slice loop runs without a
+ * single layout copy: mu / scale / y / y_hat are pixel-major (element (b, p, c) at [(b * plane + p) * ld + c]; a channel
+ * slice of a wider NHWC tensor is fine, e.g. y_hat goes straight into its 32-channel slot of the support buffer), while
+ * symbols / indexes / likelihoods are written in the reference's coding order (b, c, p) (stf.py:721-722).  Which step runs
+ * follows from the non-NULL pointers:
+ *   likelihood != NULL            forward  (entropy_models.py:645-659 + stf.py:623-626): y, scales, means -> likelihood, y_hat
+ *   else y != NULL                encode   (stf.py:717-722): -> symbols_out, indexes_out (if scales), y_hat (if non-NULL)
+ *   else symbols_in != NULL       decode   (stf.py:770-772): y_hat = float(symbols_in) + means; + indexes_out if scales
+ *   else                          indexes  (stf.py:767): scales -> indexes_out
+ * Arithmetic is the NCHW kernels': identical bits for identical inputs.  channels <= 32. */
+typedef struct {
+  const float *y; int y_ld;
+  const float *scales; int scales_ld;
+  const float *means; int means_ld;
+  const int32_t *symbols_in; int64_t symbols_in_batch_stride;
+  int32_t *symbols_out; int32_t *indexes_out; int64_t out_batch_stride;
+  float *y_hat; int y_hat_ld;
+  float *likelihood; int64_t likelihood_batch_stride;
+  int batch, channels; int64_t plane;
+  const float *table_host; int levels;   /* HOST scale table (needed when indexes_out != NULL) */
+  float scale_bound, lik_bound;
+  int ste_round;                         /* forward: y_hat = ((round(t) - t) + t) + mu (ops/ops.py:34) */
+} stf_slice_args;
+int stf_slice_step_nhwc(const stf_slice_args *args, void *stream);
+
 /* EntropyModel.quantize(x, "symbols", means) (entropy_models.py:126-150); means may be NULL. */
 int stf_quantize_symbols(const float *x, const float *means, int32_t *symbols, int64_t n,
                          void *stream);
@@ -212,6 +237,48 @@ int stf_window_attention(const float *qkv, float *out, const float *bias_table, 
                          int Hp, int Wp, int tf32_out, void *stream);
 
 /* ------------------------------------------------------------------------------------------
+ * Convolution stacks either side of the entropy kernels: the five-layer 3x3 cc_mean / cc_scale /
+ * lrp stacks of the slice loop (stf.py:510-548 called at :613-633, :706-729, :757-779; cnn.py:89-127), the hyperprior
+ * h_a / h_mean_s / h_scale_s incl. subpel_conv3x3 = conv + PixelShuffle(2) (stf.py:472-509, layers/layers.py:47-51) and the
+ * 5x5 end_conv (stf.py:466).  One implicit-GEMM tcgen05 kernel, NHWC, operands and results moved by tensor-map TMA:
+ *   Y[b,oy,ox,n] = act( sum_{ky,kx,c} X[b, oy*s+ky-p, ox*s+kx-p, c] * W[n,c,ky,kx] + bias[n] ),   p = ksize / 2
+ * X is the channel concatenation of n_src (<= 3) NHWC tensors (torch.cat([latent, y_hat_0, ...], 1) is never materialised);
+ * the zero padding, the tile halo and ragged edges are TMA out-of-bounds fill; stride 2 is the tensor map's element stride;
+ * pixel_shuffle = 2 stores conv channel 4c + 2i + j of pixel (y, x) at channel c of pixel (2y+i, 2x+j) (nn.PixelShuffle).
+ * Every output element is one fixed-order K loop (tap-major, source, channel) whatever the batch size or tiling: results are
+ * batch-invariant bit for bit, which is what lets a stream encoded in a batch be decoded alone (stf.py:767).
+ * ------------------------------------------------------------------------------------------ */
+typedef struct {
+  int batch, H, W;            /* input feature map: batch images of H x W pixels, NHWC */
+  int n_src;                  /* 1..3 channel-concatenated sources */
+  const float *src[3];        /* device pointers, 16-byte aligned */
+  int src_channels[3];        /* channels of each source (multiples of 4) */
+  int src_ld[3];              /* pixel stride of each source in floats (>= channels; a channel slice of a wider tensor is fine) */
+  int N;                      /* conv output channels (multiple of 16) */
+  int ksize;                  /* 1, 3 or 5; padding = ksize / 2 */
+  int stride;                 /* 1 or 2 */
+  const float *w_packed;      /* from stf_pack_conv (same n_src / channels / N / ksize / pixel_shuffle / precision) */
+  float *y;                   /* output NHWC: (batch, Ho, Wo, N), or (batch, 2Ho, 2Wo, N/4) with pixel_shuffle */
+  int ldy;                    /* output pixel stride in floats */
+  int act;                    /* 0: none, 1: exact-erf GELU (nn.GELU), 2: residual + 0.5 * tanh(.) -- the LRP tail */
+                              /* `y_hat_slice + 0.5 * torch.tanh(lrp)` (stf.py:631-633), no pixel shuffle */
+  const float *residual;      /* act 2: NHWC (batch, Ho, Wo, N) tensor, may alias y (updated in place) */
+  int res_ld;                 /* its pixel stride in floats */
+  int pixel_shuffle;          /* 0 or 2 */
+  int precision;              /* STF_PREC_TF32: one MMA per k-step on the raw fp32 activations (what cuDNN's default TF32 */
+                              /* convolutions do); STF_PREC_FP32: 3xTF32 split of both operands, fp32-grade */
+} stf_conv_args;
+/* Floats of the packed weight image: planes * N * Kp + N, Kp = ksize^2 * sum_s ceil32(src_channels[s]). */
+int64_t stf_packed_conv_floats(const stf_conv_args *args);
+/* Pack an nn.Conv2d weight (N, sum C_s, ksize, ksize) contiguous fp32 (+ bias[N] or NULL), device pointers, into the K-major
+ * [N][tap][source][channel padded to 32] image (TF32 hi plane, plus the lo plane for STF_PREC_FP32) followed by the bias,
+ * output channels permuted to sub-pixel-major order when pixel_shuffle = 2. */
+int stf_pack_conv(const stf_conv_args *args, const float *weight, const float *bias, float *packed, void *stream);
+int stf_conv2d(const stf_conv_args *args, void *stream);
+/* Output size of the convolution: Ho = (H + 2p - k) / s + 1 (before any pixel shuffle). */
+int stf_conv2d_out_hw(int H, int W, int ksize, int stride, int *Ho, int *Wo);
+
+/* ------------------------------------------------------------------------------------------
  * Element-wise glue around the cuDNN convolution stacks (the callers either side of the hot path).
  * ------------------------------------------------------------------------------------------ */
 
@@ -219,6 +286,14 @@ int stf_window_attention(const float *qkv, float *out, const float *bias_table, 
  * act 0 = none, 1 = exact-erf GELU.  Replaces the strided broadcast bias add + GELU launches after every convolution of
  * the hyperprior / cc_mean / cc_scale / lrp stacks (stf.py:472-548).  channels % 4 == 0. */
 int stf_bias_act(float *x, const float *bias, int channels, int64_t n, int act, void *stream);
+
+/* PatchEmbed (stf.py:350-381): Conv2d(in_chans -> embed_dim, kernel = stride = patch) on the NCHW image x (batch, in_chans,
+ * H, W), zero-padded to a multiple of the patch, + LayerNorm(embed_dim) when ln_gamma / ln_beta are non-NULL, written
+ * token-major: tokens (batch * ceil(H/patch) * ceil(W/patch), embed_dim).  weight: (embed_dim, in_chans, patch, patch)
+ * contiguous.  embed_dim in {48, 96}, in_chans * patch^2 <= 48.  Fixed summation order per token (batch-invariant). */
+int stf_patch_embed(const float *x, const float *weight, const float *bias, const float *ln_gamma, const float *ln_beta,
+                    float *tokens, int batch, int in_chans, int H, int W, int patch, int embed_dim, float ln_eps,
+                    void *stream);
 
 /* y = LayerNorm(x) over the C <= 768 channels of M token-major rows (PatchEmbed.norm, stf.py:375-379). */
 int stf_layernorm_fwd(const float *x, const float *gamma, const float *beta, float *y, int64_t M, int C, float eps,

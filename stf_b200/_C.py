@@ -38,6 +38,29 @@ class LinearArgs(ctypes.Structure):
     ]
 
 
+class ConvArgs(ctypes.Structure):
+    """struct stf_conv_args (include/stf_b200.h)."""
+    _fields_ = [
+        ("batch", c_int), ("H", c_int), ("W", c_int), ("n_src", c_int),
+        ("src", c_vp * 3), ("src_channels", c_int * 3), ("src_ld", c_int * 3),
+        ("N", c_int), ("ksize", c_int), ("stride", c_int),
+        ("w_packed", c_vp), ("y", c_vp), ("ldy", c_int), ("act", c_int), ("residual", c_vp), ("res_ld", c_int),
+        ("pixel_shuffle", c_int), ("precision", c_int),
+    ]
+
+
+class SliceArgs(ctypes.Structure):
+    """struct stf_slice_args (include/stf_b200.h)."""
+    _fields_ = [
+        ("y", c_vp), ("y_ld", c_int), ("scales", c_vp), ("scales_ld", c_int), ("means", c_vp), ("means_ld", c_int),
+        ("symbols_in", c_vp), ("symbols_in_batch_stride", c_i64),
+        ("symbols_out", c_vp), ("indexes_out", c_vp), ("out_batch_stride", c_i64),
+        ("y_hat", c_vp), ("y_hat_ld", c_int), ("likelihood", c_vp), ("likelihood_batch_stride", c_i64),
+        ("batch", c_int), ("channels", c_int), ("plane", c_i64),
+        ("table_host", _f32p), ("levels", c_int), ("scale_bound", c_f32), ("lik_bound", c_f32), ("ste_round", c_int),
+    ]
+
+
 # name -> (restype, argtypes); mirrors include/stf_b200.h one to one (tests check the export list)
 SIGNATURES = {
     "stf_version": (ctypes.c_char_p, []),
@@ -45,6 +68,7 @@ SIGNATURES = {
     "stf_build_indexes": (c_int, [c_vp, c_vp, c_i64, _f32p, c_int, c_f32, c_vp]),
     "stf_gaussian_compress_step": (c_int, [c_vp, c_i64, c_vp, c_vp, c_vp, c_vp, c_i64, c_vp, c_int, c_int, c_i64,
                                            _f32p, c_int, c_f32, c_vp]),
+    "stf_slice_step_nhwc": (c_int, [ctypes.POINTER(SliceArgs), c_vp]),
     "stf_quantize_symbols": (c_int, [c_vp, c_vp, c_vp, c_i64, c_vp]),
     "stf_quantize_dequantize": (c_int, [c_vp, c_vp, c_vp, c_i64, c_vp]),
     "stf_dequantize": (c_int, [c_vp, c_i64, c_vp, c_vp, c_int, c_int, c_i64, c_vp]),
@@ -56,6 +80,11 @@ SIGNATURES = {
     "stf_pack_linear": (c_int, [c_vp, c_vp, c_vp, c_vp, c_vp, c_int, c_int, c_int, c_vp]),
     "stf_linear": (c_int, [ctypes.POINTER(LinearArgs), c_vp]),
     "stf_window_attention": (c_int, [c_vp, c_vp, c_vp, c_vp, c_int, c_i64, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_vp]),
+    "stf_packed_conv_floats": (c_i64, [ctypes.POINTER(ConvArgs)]),
+    "stf_pack_conv": (c_int, [ctypes.POINTER(ConvArgs), c_vp, c_vp, c_vp, c_vp]),
+    "stf_conv2d": (c_int, [ctypes.POINTER(ConvArgs), c_vp]),
+    "stf_conv2d_out_hw": (c_int, [c_int, c_int, c_int, c_int, ctypes.POINTER(c_int), ctypes.POINTER(c_int)]),
+    "stf_patch_embed": (c_int, [c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_int, c_int, c_int, c_int, c_int, c_int, c_f32, c_vp]),
     "stf_bias_act": (c_int, [c_vp, c_vp, c_int, c_i64, c_int, c_vp]),
     "stf_layernorm_fwd": (c_int, [c_vp, c_vp, c_vp, c_vp, c_i64, c_int, c_f32, c_vp]),
     "stf_attention_bwd_ctas": (c_int, [c_i64, c_int, c_int, ctypes.POINTER(c_int)]),

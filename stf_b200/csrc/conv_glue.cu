@@ -70,10 +70,98 @@ layernorm_fwd_kernel(const float *__restrict__ x, const float *__restrict__ gamm
   }
 }
 
+// ---------------------------------------------------------------------------------------------
+// PatchEmbed (stf.py:350-381): Conv2d(in_chans -> E, kernel = stride = patch) + LayerNorm(E) on the NCHW image, emitted
+// token-major (B * Wh * Ww, E) = the NHWC layout every later kernel works in.  K = in_chans * patch^2 is 12 for STF: far
+// below a tensor-core tile, so this is an fp32 FFMA kernel, one thread per token, weights broadcast from shared memory, the
+// token's E outputs and its LayerNorm statistics in registers, output staged through shared memory for coalesced stores.
+// HBM-bound: 4 * (K + E) B per token.  Fixed summation order per token: batch-invariant.
+// ---------------------------------------------------------------------------------------------
+constexpr int kPeTokens = 64;     // tokens (= threads) per block, consecutive along the token row
+constexpr int kPeMaxE = 96, kPeMaxK = 48;
+
+template <int E>
+__global__ void __launch_bounds__(kPeTokens)
+patch_embed_kernel(const float *__restrict__ x, const float *__restrict__ w, const float *__restrict__ bias,
+                   const float *__restrict__ gamma, const float *__restrict__ beta, float *__restrict__ out, int B, int Cin,
+                   int H, int W, int P, int Wh, int Ww, float eps) {
+  __shared__ float ws[kPeMaxK * E];          // [k][e]: all threads read the same word (broadcast)
+  __shared__ float stage[kPeTokens * (E + 1)];
+  const int K = Cin * P * P;
+  for (int i = threadIdx.x; i < K * E; i += kPeTokens) {
+    const int k = i / E, e = i - k * E;
+    ws[i] = w[e * K + k];                    // conv weight (E, Cin, P, P) contiguous: k = (c * P + dy) * P + dx
+  }
+  __syncthreads();
+  const int64_t tokens = (int64_t)B * Wh * Ww;
+  const int64_t tok0 = (int64_t)blockIdx.x * kPeTokens;
+  const int64_t tok = tok0 + threadIdx.x;
+  if (tok < tokens) {
+    const int b = (int)(tok / ((int64_t)Wh * Ww));
+    const int rem = (int)(tok - (int64_t)b * Wh * Ww);
+    const int ty = rem / Ww, tx = rem - ty * Ww;
+    float acc[E];
+#pragma unroll
+    for (int e = 0; e < E; ++e) acc[e] = bias ? __ldg(bias + e) : 0.f;
+    for (int c = 0; c < Cin; ++c)
+      for (int dy = 0; dy < P; ++dy)
+        for (int dx = 0; dx < P; ++dx) {
+          const int yy = ty * P + dy, xx = tx * P + dx;   // zero padding to a multiple of the patch (stf.py:369-372)
+          const float v = (yy < H && xx < W) ? __ldg(x + (((int64_t)b * Cin + c) * H + yy) * W + xx) : 0.f;
+          const float *wk = ws + ((c * P + dy) * P + dx) * E;
+#pragma unroll
+          for (int e = 0; e < E; ++e) acc[e] = fmaf(v, wk[e], acc[e]);
+        }
+    if (gamma) {   // LayerNorm over the E channels (two-pass in registers)
+      float s = 0.f;
+#pragma unroll
+      for (int e = 0; e < E; ++e) s += acc[e];
+      const float mean = s * (1.0f / E);
+      float q = 0.f;
+#pragma unroll
+      for (int e = 0; e < E; ++e) {
+        const float d = acc[e] - mean;
+        q = fmaf(d, d, q);
+      }
+      const float rstd = rsqrtf(q * (1.0f / E) + eps);
+#pragma unroll
+      for (int e = 0; e < E; ++e) acc[e] = fmaf((acc[e] - mean) * rstd, __ldg(gamma + e), __ldg(beta + e));
+    }
+#pragma unroll
+    for (int e = 0; e < E; ++e) stage[threadIdx.x * (E + 1) + e] = acc[e];
+  }
+  __syncthreads();
+  const int64_t left = tokens - tok0;
+  const int n = (int)(left < kPeTokens ? left : kPeTokens) * E;
+  for (int i = threadIdx.x; i < n; i += kPeTokens) {
+    const int t = i / E, e = i - t * E;
+    out[tok0 * E + i] = stage[t * (E + 1) + e];
+  }
+}
+
 }  // namespace
 }  // namespace stf
 
 using namespace stf;
+
+extern "C" int stf_patch_embed(const float *x, const float *weight, const float *bias, const float *ln_gamma,
+                               const float *ln_beta, float *tokens, int batch, int in_chans, int H, int W, int patch,
+                               int embed_dim, float ln_eps, void *stream) {
+  if (!x || !weight || !tokens || batch < 0 || in_chans <= 0 || H <= 0 || W <= 0 || patch <= 0) return STF_E_ARG;
+  if ((ln_gamma == nullptr) != (ln_beta == nullptr)) return STF_E_ARG;
+  if (in_chans * patch * patch > kPeMaxK || (embed_dim != 48 && embed_dim != 96)) return STF_E_SHAPE;
+  const int Wh = (H + patch - 1) / patch, Ww = (W + patch - 1) / patch;
+  const int64_t tokens_n = (int64_t)batch * Wh * Ww;
+  if (tokens_n == 0) return STF_OK;
+  const unsigned blocks = (unsigned)((tokens_n + kPeTokens - 1) / kPeTokens);
+  if (embed_dim == 48)
+    patch_embed_kernel<48><<<blocks, kPeTokens, 0, (cudaStream_t)stream>>>(x, weight, bias, ln_gamma, ln_beta, tokens, batch,
+                                                                          in_chans, H, W, patch, Wh, Ww, ln_eps);
+  else
+    patch_embed_kernel<96><<<blocks, kPeTokens, 0, (cudaStream_t)stream>>>(x, weight, bias, ln_gamma, ln_beta, tokens, batch,
+                                                                          in_chans, H, W, patch, Wh, Ww, ln_eps);
+  return check_launch();
+}
 
 extern "C" int stf_bias_act(float *x, const float *bias, int channels, int64_t n, int act, void *stream) {
   if (!x || !bias || channels <= 0 || n < 0 || (act != 0 && act != 1)) return STF_E_ARG;

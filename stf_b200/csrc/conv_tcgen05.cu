@@ -1,0 +1,648 @@
+// Implicit-GEMM 2-D convolution on 5th-gen tensor cores, NHWC, TMA in / TMA out:
+//
+//   Y[b, oy, ox, n] = act( sum_{ky,kx,c} X[b, oy*s + ky - p, ox*s + kx - p, c] * W[n, c, ky, kx] + bias[n] )
+//
+// with X the channel concatenation of up to three NHWC tensors (the slice loop's torch.cat([latent, y_hat_0..]) never
+// materialises), p = k/2 zero padding, s in {1, 2}, and an optional PixelShuffle(2) folded into the store.
+//
+// Replaces (reference memory4963/STF): the five-layer cc_mean / cc_scale / lrp stacks of the slice loop
+// (compressai/models/stf.py:510-548, called at :613-633, :706-729, :757-779; cnn.py:89-127), the hyperprior h_a / h_mean_s /
+// h_scale_s (stf.py:472-509) incl. subpel_conv3x3 = conv + PixelShuffle (layers/layers.py:47-51) and the 5x5 end_conv
+// (stf.py:466); i.e. nn.Conv2d + bias + nn.GELU (+ torch.cat in front, + nn.PixelShuffle behind).
+//
+// Why our own kernel and not cuDNN: (1) the decoder must rebuild the encoder's indexes bit for bit (stf.py:767), so mu and
+// scale must not depend on how many images share a launch -- here every output element is one fixed-order K loop
+// (tap-major, then source, then channel; k-steps of 8) whatever the batch, tile shape or N tiling, so strings are
+// batch-invariant by construction; (2) the concat, the bias + GELU and the pixel shuffle cost nothing extra.
+//
+// GEMM view: M = output pixels (a 128-pixel tile is a TW x TH box of one image), N = output channels, K = taps x channels.
+//   A operand  k-block (tap, 32-channel block of one source): ONE 4-D tensor-map TMA load of the box
+//              [32 ch][TW*s][TH*s][1 image] at (c0, ox0*s + kx - p, oy0*s + ky - p, b) -- the halo, the zero padding and
+//              the ragged right/bottom edge are TMA out-of-bounds zero fill, stride 2 is the map's element stride --
+//              landing as 128 rows x 128 B in the SWIZZLE_128B K-major layout tcgen05.mma reads.
+//   B operand  pre-packed weights [N][taps * Cpad] (hi plane, and a lo plane for the 3xTF32 mode), 2-D tensor map, box [32][n_tile].
+//   D          fp32 accumulators in TMEM, double buffered (epilogue of tile i under the K loop of tile i+1).
+//   epilogue   tcgen05.ld -> + bias -> exact-erf GELU -> swizzled staging tile -> 4-D tensor-map TMA store (edge clipping and
+//              the pixel-shuffle scatter are the store map's geometry).
+// Warp roles (384 threads, one persistent CTA per SM): warp 0 TMA producer, warp 1 MMA issuer (+ TMEM alloc), warps 4-7 epilogue
+// (warp & 3 = TMEM lane quadrant), warps 8-11 hi/lo splitter (3xTF32 mode only: A stage -> truncated hi in place + lo plane).
+#include <cuda.h>  // CUtensorMap + enums only; cuTensorMapEncodeTiled is resolved at run time (no link-time libcuda dependency)
+#include <math.h>
+#include <stdio.h>
+#include <stdlib.h>
+
+#include <mutex>
+
+#include "common.cuh"
+#include "sm100.cuh"
+
+namespace stf {
+namespace {
+
+using namespace sm100;
+
+constexpr int kTileM = 128;
+constexpr int kBlockK = 32;                       // floats per k-block = one 128-byte swizzle row
+constexpr uint32_t kAStageBytes = kTileM * 128;   // 16 KB
+constexpr int kMaxStages = 8;
+constexpr int kThreads = 384;
+constexpr int kProducerWarp = 0, kMmaWarp = 1, kFirstEpiWarp = 4, kFirstSplitWarp = 8;
+constexpr int kMaxSrc = 3;
+constexpr uint32_t kStagingBytes = kTileM * 128;  // one 128 x 32-float output chunk (or 128 x 16 in 64-byte rows)
+
+struct ConvParams {
+  alignas(64) CUtensorMap a_map[kMaxSrc];
+  alignas(64) CUtensorMap b_map[2];   // hi, lo
+  alignas(64) CUtensorMap y_map[4];   // plain: [0]; pixel shuffle: one per (i, j) sub-pixel
+  const float *bias;                  // N floats in packed column order
+  const float *residual;              // act 2: NHWC tensor of the output's geometry (may alias the output), pixel stride res_ld
+  int res_ld, Ho, Wo;
+  int n_src;
+  int src_kb[kMaxSrc];                // 32-channel k-blocks per tap of each source
+  int kb_per_tap, k_blocks, ksize, pad, stride;
+  int N, n_tile, n_tiles;
+  int TW, TH, tiles_x, tiles_y, tiles_per_img, m_tiles, total_tiles;
+  int act;                            // 0 none, 1 exact-erf GELU, 2 residual + 0.5 * tanh(.)  (the LRP tail, stf.py:631-633)
+  int shuffle_cout;                   // 0: plain store; else channels after PixelShuffle(2) (N = 4 * shuffle_cout)
+  int cw;                             // store chunk width in channels: 32 (SWIZZLE_128B staging) or 16 (SWIZZLE_64B)
+  int stages;
+  uint32_t idesc;
+  int tmem_cols, acc_stride;
+  uint32_t stage_bytes, b_plane_bytes;  // per pipeline stage: A hi (+ A lo) + B hi (+ B lo)
+};
+
+// ---------------------------------------------------------------------------- PTX: tensor-map TMA
+__device__ __forceinline__ void tma_load_4d(uint32_t smem_dst, const CUtensorMap *map, uint64_t *bar, int c0, int c1, int c2,
+                                            int c3) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];" ::"r"(
+          smem_dst),
+      "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(uint32_t smem_dst, const CUtensorMap *map, uint64_t *bar, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(smem_dst),
+      "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void tma_store_4d(const CUtensorMap *map, uint32_t smem_src, int c0, int c1, int c2, int c3) {
+  asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.tile.bulk_group [%0, {%2, %3, %4, %5}], [%1];" ::"l"(map),
+               "r"(smem_src), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+               : "memory");
+}
+__device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap *map) {
+  asm volatile("prefetch.tensormap [%0];" ::"l"(map) : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_read1() { asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait0() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+__device__ __forceinline__ void named_bar_sync(int id, int threads) {
+  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(threads) : "memory");
+}
+
+// Shared-memory matrix descriptor, K-major operand in the SWIZZLE_128B layout (rows of 128 B, 8-row swizzle atoms of
+// 1024 B): start address >> 4 in [0,14), LBO (unused for swizzled K-major) = 1 in [16,30), SBO = 1024 B >> 4 in [32,46),
+// descriptor version 1 in [46,48), layout type 2 (SWIZZLE_128B) in [61,64).  Stage bases are 1024-byte aligned (base
+// offset field 0); a k-step of 8 tf32 inside the 128-byte row advances the start address by 32 B.
+__device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t smem_addr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr >> 4) & 0x3FFF);
+  d |= (uint64_t)1 << 16;
+  d |= (uint64_t)(1024 >> 4) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)2 << 61;
+  return d;
+}
+
+// 32 lanes x 32 consecutive 32-bit columns -> 32 registers per thread; the second half is skipped (warp-uniformly) when
+// `second` is 0.  Loads and tcgen05.wait::ld sit in ONE asm statement, so no use of the outputs can be scheduled above the wait.
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t second, uint32_t (&r)[32]) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %33, 0;\n\t"
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%32];\n\t"
+      "@p tcgen05.ld.sync.aligned.32x32b.x16.b32 {%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%34];\n\t"
+      "tcgen05.wait::ld.sync.aligned;\n\t}"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]),
+        "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]),
+        "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr), "r"(second), "r"(taddr + 16u)
+      : "memory");
+}
+
+__device__ __forceinline__ float4 lds128(uint32_t addr) {
+  float4 v;
+  asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
+  return v;
+}
+__device__ __forceinline__ void sts128(uint32_t addr, float4 v) {
+  asm volatile("st.shared.v4.f32 [%0], {%1,%2,%3,%4};" ::"r"(addr), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+}
+
+// Exact-erf GELU (nn.GELU default): same evaluation as the linear kernel's epilogue (Abramowitz-Stegun 7.1.26,
+// |abs error| <= 1.5e-7, branch-free).
+__device__ __forceinline__ float gelu_erf(float x) {
+  const float ax = fabsf(x) * 0.70710678118654752440f;
+  float t;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(t) : "f"(fmaf(0.3275911f, ax, 1.0f)));
+  float p = fmaf(t, 1.061405429f, -1.453152027f);
+  p = fmaf(t, p, 1.421413741f);
+  p = fmaf(t, p, -0.284496736f);
+  p = fmaf(t, p, 0.254829592f);
+  const float e = __expf(-ax * ax);
+  const float erf_abs = fmaf(-p * t, e, 1.0f);
+  return 0.5f * x * (1.0f + copysignf(erf_abs, x));
+}
+
+__device__ __forceinline__ float trunc_tf32(float x) { return __uint_as_float(__float_as_uint(x) & 0xFFFFE000u); }
+
+// ---------------------------------------------------------------------------- the kernel
+template <int kPrecise>
+__global__ void __launch_bounds__(kThreads, 1) conv_tf32_kernel(const __grid_constant__ ConvParams P) {
+  extern __shared__ uint8_t smem_raw[];
+  // operand stages need 1024-byte alignment (swizzle atoms); the launch asks for 1 KB of slack
+  const uint32_t raw_u32 = smem_u32(smem_raw);
+  uint8_t *smem = smem_raw + ((1024u - (raw_u32 & 1023u)) & 1023u);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t S = (uint32_t)P.stages;
+  const uint32_t a_lo_off = kAStageBytes;                                  // precise: A lo plane behind A hi
+  const uint32_t b_off = kPrecise ? 2 * kAStageBytes : kAStageBytes;       // B hi plane
+  const uint32_t b_lo_off = b_off + P.b_plane_bytes;
+  uint8_t *ring = smem;
+  uint8_t *staging = ring + (size_t)S * P.stage_bytes;                    // 2 x 16 KB, 1024-aligned (stage_bytes % 1024 == 0)
+  float *bias_s = reinterpret_cast<float *>(staging + 2 * kStagingBytes);
+  uint64_t *bars = reinterpret_cast<uint64_t *>(bias_s + ((P.N + 3) & ~3));
+  uint64_t *full = bars, *empty = full + kMaxStages, *split = empty + kMaxStages, *acc_full = split + kMaxStages,
+           *acc_empty = acc_full + 2;
+  uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(acc_empty + 2);
+
+  for (int i = threadIdx.x; i < P.N; i += kThreads) bias_s[i] = P.bias ? __ldg(P.bias + i) : 0.f;
+  if (threadIdx.x == 0) {
+    for (uint32_t s = 0; s < S; ++s) {
+      mbar_init(&full[s], 1);    // the producer's arrive.expect_tx (+ TMA transaction bytes)
+      mbar_init(&empty[s], 1);   // one tcgen05.commit
+      mbar_init(&split[s], 4);   // one arrival per splitter warp
+    }
+    for (int b = 0; b < 2; ++b) {
+      mbar_init(&acc_full[b], 1);
+      mbar_init(&acc_empty[b], 4);  // one arrival per epilogue warp
+    }
+    mbar_fence_init();
+    for (int s = 0; s < P.n_src; ++s) tma_prefetch_desc(&P.a_map[s]);
+    tma_prefetch_desc(&P.b_map[0]);
+    if (kPrecise) tma_prefetch_desc(&P.b_map[1]);
+    tma_prefetch_desc(&P.y_map[0]);
+  }
+  if (warp == kMmaWarp) tmem_alloc(tmem_slot, (uint32_t)P.tmem_cols);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == kProducerWarp) {
+    // =========================== TMA producer ===========================
+    if (lane == 0) {
+      uint32_t st = 0, ph = 1;  // waiting on parity 1 of a fresh barrier returns immediately
+      const uint32_t tx_bytes = kAStageBytes + (uint32_t)(kPrecise ? 2 : 1) * P.b_plane_bytes;
+      for (int tile = blockIdx.x; tile < P.total_tiles; tile += gridDim.x) {
+        const int mt = tile / P.n_tiles, nt = tile - mt * P.n_tiles;
+        const int b = mt / P.tiles_per_img, rem = mt - b * P.tiles_per_img;
+        const int ty = rem / P.tiles_x, tx = rem - ty * P.tiles_x;
+        const int x0 = tx * P.TW * P.stride - P.pad, y0 = ty * P.TH * P.stride - P.pad;
+        const int n0 = nt * P.n_tile;
+        int kb = 0;
+        for (int tap = 0; tap < P.ksize * P.ksize; ++tap) {
+          const int ky = tap / P.ksize, kx = tap - ky * P.ksize;
+          for (int s = 0; s < P.n_src; ++s) {
+            for (int cb = 0; cb < P.src_kb[s]; ++cb, ++kb) {
+              mbar_wait(&empty[st], ph);
+              const uint32_t base = smem_u32(ring) + st * P.stage_bytes;
+              mbar_arrive_expect_tx(&full[st], tx_bytes);
+              tma_load_4d(base, &P.a_map[s], &full[st], cb * kBlockK, x0 + kx, y0 + ky, b);
+              tma_load_2d(base + b_off, &P.b_map[0], &full[st], kb * kBlockK, n0);
+              if (kPrecise) tma_load_2d(base + b_lo_off, &P.b_map[1], &full[st], kb * kBlockK, n0);
+              if (++st == S) st = 0, ph ^= 1u;
+            }
+          }
+        }
+      }
+    }
+  } else if (warp == kMmaWarp) {
+    // =========================== MMA issuer ===========================
+    if (lane == 0) {
+      uint32_t st = 0, ph = 0;
+      int it = 0;
+      for (int tile = blockIdx.x; tile < P.total_tiles; tile += gridDim.x, ++it) {
+        const int buf = it & 1;
+        mbar_wait(&acc_empty[buf], (((uint32_t)it >> 1) & 1u) ^ 1u);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + (uint32_t)(buf * P.acc_stride);
+        for (int kb = 0; kb < P.k_blocks; ++kb) {
+          mbar_wait(kPrecise ? &split[st] : &full[st], ph);
+          tc_fence_after();
+          const uint32_t base = smem_u32(ring) + st * P.stage_bytes;
+          const uint64_t da = umma_desc_sw128(base), db = umma_desc_sw128(base + b_off);
+#pragma unroll
+          for (int ks = 0; ks < kBlockK / 8; ++ks) {  // one MMA consumes K = 8 tf32 = 32 B of every row
+            const uint64_t dak = da + (uint64_t)(ks * 2), dbk = db + (uint64_t)(ks * 2);
+            umma_tf32(d_tmem, dak, dbk, P.idesc, (kb | ks) ? 1u : 0u);
+            if (kPrecise) {  // 3xTF32: hi.hi + lo.hi + hi.lo (lo.lo is below fp32 round-off)
+              umma_tf32(d_tmem, dak + (uint64_t)(a_lo_off >> 4), dbk, P.idesc, 1u);
+              umma_tf32(d_tmem, dak, dbk + (uint64_t)(P.b_plane_bytes >> 4), P.idesc, 1u);
+            }
+          }
+          umma_commit(&empty[st]);  // frees the stage when the MMAs above have read it
+          if (++st == S) st = 0, ph ^= 1u;
+        }
+        umma_commit(&acc_full[buf]);
+      }
+    }
+  } else if (warp >= kFirstEpiWarp && warp < kFirstEpiWarp + 4) {
+    // =========================== epilogue ===========================
+    const int quad = warp & 3;
+    const int row = quad * 32 + lane;  // TMEM lane == tile row == pixel (row / TW, row % TW) of the tile box
+    const int et = threadIdx.x - kFirstEpiWarp * 32;  // 0..127
+    const int cw = P.cw;
+    const uint32_t row_bytes = (uint32_t)cw * 4u;
+    const uint32_t swz = cw == 32 ? (uint32_t)(row & 7) : (uint32_t)((row >> 1) & 3);
+    int it = 0;
+    uint32_t chunk_no = 0;  // running chunk counter -> staging buffer parity
+    for (int tile = blockIdx.x; tile < P.total_tiles; tile += gridDim.x, ++it) {
+      const int buf = it & 1;
+      const int mt = tile / P.n_tiles, nt = tile - mt * P.n_tiles;
+      const int b = mt / P.tiles_per_img, rem = mt - b * P.tiles_per_img;
+      const int ty = rem / P.tiles_x, tx = rem - ty * P.tiles_x;
+      const int ox0 = tx * P.TW, oy0 = ty * P.TH;
+      mbar_wait_relaxed(&acc_full[buf], ((uint32_t)it >> 1) & 1u);
+      tc_fence_after();
+      const uint32_t t_acc = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(buf * P.acc_stride);
+      const int n_chunks = (P.n_tile + cw - 1) / cw;
+      for (int c = 0; c < n_chunks; ++c, ++chunk_no) {
+        const int col0 = c * cw;            // column inside the tile
+        const int n0 = nt * P.n_tile + col0;  // packed output column
+        uint32_t r[32];
+        tmem_ld32(t_acc + (uint32_t)col0, (cw == 32 && col0 + 16 < P.n_tile) ? 1u : 0u, r);
+        if (c == n_chunks - 1) {  // last TMEM read of this tile: hand the accumulator back to the MMA warp
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&acc_empty[buf]);
+        }
+        const int valid = min(cw, P.n_tile - col0);  // 16 or 32 (n_tile % 16 == 0)
+        float v[32];
+        const float *res_row = nullptr;
+        if (P.act == 2) {  // y_hat_slice + 0.5 * tanh(lrp): the residual is the pixel's own 32 channels (read before the store)
+          const int oy = oy0 + row / P.TW, ox = ox0 + row % P.TW;
+          if (oy < P.Ho && ox < P.Wo) res_row = P.residual + ((int64_t)(b * P.Ho + oy) * P.Wo + ox) * P.res_ld + n0;
+        }
+#pragma unroll
+        for (int j = 0; j < 32; j += 4) {
+          float4 rv = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (res_row && j < valid && n0 + j < P.N) rv = *reinterpret_cast<const float4 *>(res_row + j);
+          const float rr[4] = {rv.x, rv.y, rv.z, rv.w};
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            float a = __uint_as_float(r[j + q]);
+            if (j + q < valid && n0 + j + q < P.N) {
+              a += bias_s[n0 + j + q];
+              if (P.act == 1) a = gelu_erf(a);
+              else if (P.act == 2) a = rr[q] + 0.5f * tanhf(a);
+            } else {
+              a = 0.f;
+            }
+            v[j + q] = a;
+          }
+        }
+        named_bar_sync(1, 128);  // the store that last read this staging buffer has finished reading (thread 0 waited)
+        const uint32_t stg = smem_u32(staging) + (chunk_no & 1u) * kStagingBytes + (uint32_t)row * row_bytes;
+        if (cw == 32) {
+#pragma unroll
+          for (int j = 0; j < 8; ++j)
+            sts128(stg + (((uint32_t)j ^ swz) << 4), make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]));
+        } else {
+#pragma unroll
+          for (int j = 0; j < 4; ++j)
+            sts128(stg + (((uint32_t)j ^ swz) << 4), make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]));
+        }
+        fence_proxy_async_smem();
+        named_bar_sync(2, 128);
+        if (et == 0) {
+          const uint32_t src = smem_u32(staging) + (chunk_no & 1u) * kStagingBytes;
+          if (n0 >= P.N) {
+            // chunk entirely past the last output channel (overhanging last column tile): nothing to store
+          } else if (P.shuffle_cout) {
+            const int g = n0 / P.shuffle_cout, c0 = n0 - g * P.shuffle_cout;  // sub-pixel (i, j) = (g >> 1, g & 1)
+            tma_store_4d(&P.y_map[g], src, c0, ox0, oy0, b);
+          } else {
+            tma_store_4d(&P.y_map[0], src, n0, ox0, oy0, b);
+          }
+          bulk_commit();
+          bulk_wait_read1();  // the previous chunk's store has finished reading the other staging buffer
+        }
+      }
+    }
+    if (et == 0) bulk_wait0();
+  } else if (kPrecise && warp >= kFirstSplitWarp) {
+    // =========================== hi / lo splitter (3xTF32) ===========================
+    // Element-wise on the landed A stage (layout-agnostic): hi = upper 19 bits written back in place, so the tensor core
+    // reads an exact TF32 value whatever its own rounding of fp32 words is; lo = x - hi (exact in fp32) into the lo plane,
+    // of which the tensor core reads the upper 11 significant bits: x = hi + lo to 2^-22 relative.
+    const int st_thread = threadIdx.x - kFirstSplitWarp * 32;  // 0..127
+    uint32_t st = 0, ph = 0;
+    for (int tile = blockIdx.x; tile < P.total_tiles; tile += gridDim.x) {
+      for (int kb = 0; kb < P.k_blocks; ++kb) {
+        mbar_wait(&full[st], ph);
+        const uint32_t base = smem_u32(ring) + st * P.stage_bytes + (uint32_t)st_thread * 16u;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const uint32_t a = base + (uint32_t)i * 2048u;
+          const float4 x = lds128(a);
+          const float4 hi = make_float4(trunc_tf32(x.x), trunc_tf32(x.y), trunc_tf32(x.z), trunc_tf32(x.w));
+          sts128(a, hi);
+          sts128(a + a_lo_off, make_float4(x.x - hi.x, x.y - hi.y, x.z - hi.z, x.w - hi.w));
+        }
+        fence_proxy_async_smem();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&split[st]);
+        if (++st == S) st = 0, ph ^= 1u;
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == kMmaWarp) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, (uint32_t)P.tmem_cols);
+  }
+}
+
+// ---------------------------------------------------------------------------- weight packing
+// out: [planes][N][Kp] + bias'[N];  Kp = taps * Cp, Cp = sum_s ceil32(C_s).  Column n' of the packed matrix is conv output
+// channel n: plain n' = n; pixel shuffle n' = g * Cout + c  <->  n = 4 c + g  (PixelShuffle(2): f = 4c + 2i + j, g = 2i + j).
+struct PackParams {
+  const float *w;      // (N, Ctot, k, k) contiguous
+  const float *bias;   // N or nullptr
+  float *out;
+  int N, Ctot, taps, Cp, Kp, n_src;
+  int src_c[kMaxSrc], src_cp[kMaxSrc];
+  int shuffle_cout, planes;
+};
+
+__global__ void pack_conv_kernel(const PackParams P) {
+  const int64_t total = (int64_t)P.N * P.Kp;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int np = (int)(i / P.Kp), kp = (int)(i - (int64_t)np * P.Kp);
+    const int n = P.shuffle_cout ? 4 * (np % P.shuffle_cout) + np / P.shuffle_cout : np;
+    const int tap = kp / P.Cp;
+    int q = kp - tap * P.Cp, c = -1, cbase = 0;
+    for (int s = 0; s < P.n_src; ++s) {
+      if (q < P.src_cp[s]) {
+        c = q < P.src_c[s] ? cbase + q : -1;
+        break;
+      }
+      q -= P.src_cp[s];
+      cbase += P.src_c[s];
+    }
+    const float v = c >= 0 ? P.w[((int64_t)n * P.Ctot + c) * P.taps + tap] : 0.f;
+    const float hi = to_tf32(v);
+    P.out[i] = hi;
+    if (P.planes == 2) P.out[total + i] = to_tf32(v - hi);
+  }
+  if (blockIdx.x == 0)
+    for (int np = threadIdx.x; np < P.N; np += blockDim.x) {
+      const int n = P.shuffle_cout ? 4 * (np % P.shuffle_cout) + np / P.shuffle_cout : np;
+      P.out[(int64_t)P.planes * total + np] = P.bias ? P.bias[n] : 0.f;
+    }
+}
+
+// ---------------------------------------------------------------------------- host side
+typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
+                                  const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    void *p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(p);
+    (void)cudaGetLastError();
+  });
+  return fn;
+}
+
+int ceil32(int c) { return (c + 31) & ~31; }
+
+struct Geometry {
+  int Ho, Wo, TW, TH, tiles_x, tiles_y;
+};
+
+Geometry geometry(int H, int W, int ksize, int stride) {
+  Geometry g;
+  const int pad = ksize / 2;
+  g.Ho = (H + 2 * pad - ksize) / stride + 1;
+  g.Wo = (W + 2 * pad - ksize) / stride + 1;
+  int best = 1 << 30;
+  g.TW = 16, g.TH = 8;
+  const int cand[3] = {16, 32, 8};  // preference order on ties
+  for (int i = 0; i < 3; ++i) {
+    const int tw = cand[i], th = kTileM / tw;
+    const int n = ((g.Wo + tw - 1) / tw) * ((g.Ho + th - 1) / th);
+    if (n < best) best = n, g.TW = tw, g.TH = th;
+  }
+  g.tiles_x = (g.Wo + g.TW - 1) / g.TW;
+  g.tiles_y = (g.Ho + g.TH - 1) / g.TH;
+  return g;
+}
+
+// Column tile.  One tile when N fits (<= 256 columns; 128 in the 3xTF32 mode, whose stages carry a lo plane of both
+// operands); several tiles are multiples of the 32-column store chunk (the last one may overhang N: TMA zero-fills the
+// weight rows past N and clips the store).  Which width: the one with the lowest estimated time -- waves x k-blocks x
+// max(operand bytes per k-block / the ~53 B/clk an SM pulls from L2 (measured), MMA cycles) -- so that a small batch
+// (12 pixel tiles for one 768x512 image) spreads over the SMs as narrow column tiles, while a large batch takes the widest
+// tile (least A re-reads).  The choice never changes a result bit: every output element is the same fixed-order K loop.
+int conv_n_tile(int N, int precise, int gran, int m_tiles, int k_blocks) {
+  const int cap = precise ? 128 : 256;
+  if (N <= 0 || N % 16) return STF_E_SHAPE;
+  if (gran < 32) gran = 32;
+  int best = -1;
+  double best_t = 0;
+  for (int nt = gran; nt <= cap + gran - 1; nt += gran) {
+    int w = nt;
+    if (w >= N) w = N;          // single tile: N itself (any multiple of 16)
+    if (w > cap) break;
+    const int n_tiles = (N + w - 1) / w;
+    const long long tiles = (long long)m_tiles * n_tiles;
+    const long long waves = (tiles + kNumSMs - 1) / kNumSMs;
+    const double bytes = (precise ? 2.0 : 1.0) * (16384.0 + 128.0 * w);
+    const double mma = (precise ? 3.0 : 1.0) * 2.0 * w;
+    const double per_kb = bytes / 53.0 > mma ? bytes / 53.0 : mma;
+    const double t = (double)waves * ((double)k_blocks * per_kb + 12.0 * w + 1500.0);
+    if (best < 0 || t < best_t * 0.999 || (t <= best_t * 1.001 && w > best)) best = w, best_t = t;
+    if (w == N) break;
+  }
+  return best > 0 ? best : STF_E_SHAPE;
+}
+
+int packed_geometry(const stf_conv_args *a, int *Cp, int *Kp) {
+  if (a->n_src < 1 || a->n_src > kMaxSrc) return STF_E_ARG;
+  int cp = 0;
+  for (int s = 0; s < a->n_src; ++s) {
+    if (a->src_channels[s] <= 0 || a->src_channels[s] % 4) return STF_E_SHAPE;
+    cp += ceil32(a->src_channels[s]);
+  }
+  *Cp = cp;
+  *Kp = cp * a->ksize * a->ksize;
+  return STF_OK;
+}
+
+}  // namespace
+
+extern "C" int64_t stf_packed_conv_floats(const stf_conv_args *a) {
+  int Cp, Kp;
+  if (!a || packed_geometry(a, &Cp, &Kp) != STF_OK) return STF_E_ARG;
+  return (int64_t)(a->precision == STF_PREC_FP32 ? 2 : 1) * a->N * Kp + a->N;
+}
+
+extern "C" int stf_pack_conv(const stf_conv_args *a, const float *weight, const float *bias, float *packed, void *stream) {
+  if (!a || !weight || !packed) return STF_E_ARG;
+  if (!aligned16(packed)) return STF_E_ALIGN;
+  PackParams P{};
+  int rc = packed_geometry(a, &P.Cp, &P.Kp);
+  if (rc != STF_OK) return rc;
+  if (a->pixel_shuffle != 0 && (a->pixel_shuffle != 2 || a->N % 4)) return STF_E_SHAPE;
+  P.w = weight, P.bias = bias, P.out = packed, P.N = a->N, P.taps = a->ksize * a->ksize, P.n_src = a->n_src;
+  P.Ctot = 0;
+  for (int s = 0; s < a->n_src; ++s) P.src_c[s] = a->src_channels[s], P.src_cp[s] = ceil32(a->src_channels[s]), P.Ctot += a->src_channels[s];
+  P.shuffle_cout = a->pixel_shuffle ? a->N / 4 : 0;
+  P.planes = a->precision == STF_PREC_FP32 ? 2 : 1;
+  const int64_t total = (int64_t)P.N * P.Kp;
+  const int blocks = (int)((total + 255) / 256 < 2048 ? (total + 255) / 256 : 2048);
+  pack_conv_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(P);
+  return check_launch();
+}
+
+extern "C" int stf_conv2d(const stf_conv_args *a, void *stream) {
+  if (!a || !a->w_packed || !a->y) return STF_E_ARG;
+  if (a->batch <= 0 || a->H <= 0 || a->W <= 0 || a->N <= 0) return STF_E_SHAPE;
+  if (a->ksize != 1 && a->ksize != 3 && a->ksize != 5) return STF_E_SHAPE;
+  if (a->stride != 1 && a->stride != 2) return STF_E_SHAPE;
+  if (a->pixel_shuffle != 0 && (a->pixel_shuffle != 2 || a->N % 4 || (a->N / 4) % 16)) return STF_E_SHAPE;
+  if (a->ldy % 4 || !aligned16(a->y) || !aligned16(a->w_packed)) return STF_E_ALIGN;
+  const int precise = a->precision == STF_PREC_FP32 ? 1 : 0;
+  ConvParams P{};
+  int Cp, Kp;
+  int rc = packed_geometry(a, &Cp, &Kp);
+  if (rc != STF_OK) return rc;
+  const int shuffle_cout = a->pixel_shuffle ? a->N / 4 : 0;
+  const int cw = (!shuffle_cout || shuffle_cout % 32 == 0) ? 32 : 16;
+  EncodeTiledFn enc = encode_fn();
+  if (!enc) return STF_E_ARG;
+  const Geometry g = geometry(a->H, a->W, a->ksize, a->stride);
+  const int s = a->stride;
+  const int n_tile = conv_n_tile(a->N, precise, cw, g.tiles_x * g.tiles_y * a->batch, (Cp / kBlockK) * a->ksize * a->ksize);
+  if (n_tile < 0) return n_tile;
+  if (shuffle_cout && n_tile % cw) return STF_E_SHAPE;
+
+  P.n_src = a->n_src;
+  P.kb_per_tap = 0;
+  for (int i = 0; i < a->n_src; ++i) {
+    if (!a->src[i] || !aligned16(a->src[i]) || a->src_ld[i] % 4 || a->src_ld[i] < a->src_channels[i]) return STF_E_ALIGN;
+    P.src_kb[i] = ceil32(a->src_channels[i]) / kBlockK;
+    P.kb_per_tap += P.src_kb[i];
+    const cuuint64_t gdim[4] = {(cuuint64_t)a->src_channels[i], (cuuint64_t)a->W, (cuuint64_t)a->H, (cuuint64_t)a->batch};
+    const cuuint64_t gstr[3] = {(cuuint64_t)a->src_ld[i] * 4, (cuuint64_t)a->W * a->src_ld[i] * 4,
+                                (cuuint64_t)a->H * a->W * a->src_ld[i] * 4};
+    const cuuint32_t box[4] = {(cuuint32_t)kBlockK, (cuuint32_t)(g.TW * s), (cuuint32_t)(g.TH * s), 1};
+    const cuuint32_t estr[4] = {1, (cuuint32_t)s, (cuuint32_t)s, 1};
+    if (enc(&P.a_map[i], CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<float *>(a->src[i]), gdim, gstr, box, estr,
+            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+      return STF_E_SHAPE;
+  }
+  P.ksize = a->ksize, P.pad = a->ksize / 2, P.stride = s;
+  P.k_blocks = P.kb_per_tap * a->ksize * a->ksize;
+  for (int p = 0; p < 1 + precise; ++p) {
+    const cuuint64_t gdim[2] = {(cuuint64_t)Kp, (cuuint64_t)a->N};
+    const cuuint64_t gstr[1] = {(cuuint64_t)Kp * 4};
+    const cuuint32_t box[2] = {(cuuint32_t)kBlockK, (cuuint32_t)n_tile};
+    const cuuint32_t estr[2] = {1, 1};
+    if (enc(&P.b_map[p], CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float *>(a->w_packed) + (size_t)p * a->N * Kp, gdim,
+            gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+      return STF_E_SHAPE;
+  }
+  P.bias = a->w_packed + (size_t)(1 + precise) * a->N * Kp;
+  P.shuffle_cout = shuffle_cout;
+  P.cw = cw;
+  const int n_maps = P.shuffle_cout ? 4 : 1;
+  for (int m = 0; m < n_maps; ++m) {
+    cuuint64_t gdim[4], gstr[3];
+    float *base = a->y;
+    if (P.shuffle_cout) {
+      const int i = m >> 1, j = m & 1;
+      const int64_t Wo2 = 2 * (int64_t)g.Wo, Ho2 = 2 * (int64_t)g.Ho;
+      base += ((int64_t)i * Wo2 + j) * a->ldy;
+      gdim[0] = (cuuint64_t)P.shuffle_cout, gdim[1] = (cuuint64_t)g.Wo, gdim[2] = (cuuint64_t)g.Ho, gdim[3] = (cuuint64_t)a->batch;
+      gstr[0] = (cuuint64_t)2 * a->ldy * 4, gstr[1] = (cuuint64_t)2 * Wo2 * a->ldy * 4, gstr[2] = (cuuint64_t)Ho2 * Wo2 * a->ldy * 4;
+    } else {
+      gdim[0] = (cuuint64_t)a->N, gdim[1] = (cuuint64_t)g.Wo, gdim[2] = (cuuint64_t)g.Ho, gdim[3] = (cuuint64_t)a->batch;
+      gstr[0] = (cuuint64_t)a->ldy * 4, gstr[1] = (cuuint64_t)g.Wo * a->ldy * 4, gstr[2] = (cuuint64_t)g.Ho * g.Wo * a->ldy * 4;
+    }
+    const cuuint32_t box[4] = {(cuuint32_t)P.cw, (cuuint32_t)g.TW, (cuuint32_t)g.TH, 1};
+    const cuuint32_t estr[4] = {1, 1, 1, 1};
+    if (enc(&P.y_map[m], CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, base, gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+            P.cw == 32 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_NONE,
+            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+      return STF_E_SHAPE;
+  }
+  P.N = a->N, P.n_tile = n_tile, P.n_tiles = (a->N + n_tile - 1) / n_tile;
+  P.TW = g.TW, P.TH = g.TH, P.tiles_x = g.tiles_x, P.tiles_y = g.tiles_y;
+  P.tiles_per_img = g.tiles_x * g.tiles_y;
+  P.m_tiles = P.tiles_per_img * a->batch;
+  P.total_tiles = P.m_tiles * P.n_tiles;
+  P.act = a->act;
+  if (a->act == 2) {
+    if (!a->residual || a->pixel_shuffle || a->res_ld % 4 || !aligned16(a->residual)) return STF_E_ARG;
+    P.residual = a->residual, P.res_ld = a->res_ld;
+  }
+  P.Ho = g.Ho, P.Wo = g.Wo;
+  P.idesc = umma_idesc_tf32(kTileM, n_tile);
+  P.acc_stride = n_tile;
+  int cols = 32;
+  while (cols < 2 * n_tile) cols <<= 1;
+  P.tmem_cols = cols;
+  P.b_plane_bytes = (uint32_t)n_tile * 128u;
+  P.stage_bytes = (uint32_t)(1 + precise) * (kAStageBytes + P.b_plane_bytes);
+  const size_t fixed = 1024 /*alignment slack*/ + 2 * kStagingBytes + (size_t)((a->N + 3) & ~3) * 4 + (3 * kMaxStages + 4) * 8 + 16;
+  const size_t cap = 227 * 1024;
+  int stages = (int)((cap - fixed) / P.stage_bytes);
+  if (stages > kMaxStages) stages = kMaxStages;
+  if (stages > P.k_blocks) stages = P.k_blocks < 2 ? 2 : P.k_blocks;
+  if (stages < 2) return STF_E_SHAPE;
+  P.stages = stages;
+  const size_t smem = fixed + (size_t)stages * P.stage_bytes;
+  const int grid = P.total_tiles < kNumSMs ? P.total_tiles : kNumSMs;
+  auto kern = precise ? conv_tf32_kernel<1> : conv_tf32_kernel<0>;
+  static std::once_flag attr_once[2];
+  std::call_once(attr_once[precise], [&] {
+    (void)cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cap);
+  });
+  kern<<<grid, kThreads, smem, (cudaStream_t)stream>>>(P);
+  return check_launch();
+}
+
+extern "C" int stf_conv2d_out_hw(int H, int W, int ksize, int stride, int *Ho, int *Wo) {
+  if (H <= 0 || W <= 0 || (ksize != 1 && ksize != 3 && ksize != 5) || (stride != 1 && stride != 2)) return STF_E_SHAPE;
+  const Geometry g = geometry(H, W, ksize, stride);
+  if (Ho) *Ho = g.Ho;
+  if (Wo) *Wo = g.Wo;
+  return STF_OK;
+}
+
+}  // namespace stf

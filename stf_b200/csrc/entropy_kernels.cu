@@ -274,6 +274,86 @@ gaussian_likelihood_kernel(const float *__restrict__ y, const float *__restrict_
 }
 
 // ---------------------------------------------------------------------------------------------
+// Slice step on NHWC operands (the conv kernel's layout): mu / scale / y / y_hat are read and written pixel-major
+// (element (b, p, c) at [(b * plane + p) * ld + c], a channel slice of a wider NHWC tensor is fine), while symbols, indexes
+// and likelihoods leave in the reference's coding order (b, c, p) (stf.py:721-722) -- a 32 x 32 transpose through shared
+// memory, so both sides are 128-byte coalesced.  Same arithmetic (device functions) as the NCHW kernels above: bit-identical
+// symbols / indexes / y_hat for identical inputs.  One block = 32 pixels x (<= 32) channels of one image.
+// ---------------------------------------------------------------------------------------------
+struct SliceNhwc {
+  const float *y;        int y_ld;     // slice of the latent (already offset to its first channel); nullptr in decode
+  const float *scales;   int s_ld;
+  const float *means;    int m_ld;
+  const int32_t *sym_in; int64_t sym_in_bstride;   // decode: symbols of this slice in coding order
+  int32_t *sym_out, *idx_out; int64_t out_bstride;
+  float *y_hat;          int yh_ld;
+  float *lik;            int64_t lik_bstride;      // forward: likelihoods in (b, c, p) order
+  int C, plane;
+  float scale_bound, lik_bound;
+  int ste_round;
+};
+
+template <int kMode>  // index search as in compress_step_kernel
+__global__ void __launch_bounds__(256)
+slice_step_nhwc_kernel(const SliceNhwc a, const __grid_constant__ ScaleTable table) {
+  __shared__ float t[68];
+  __shared__ __align__(16) uint8_t lut[128];
+  __shared__ int32_t tile_a[32][33];   // symbols (in or out)
+  __shared__ int32_t tile_b[32][33];   // indexes, or likelihood bits
+  if (kMode == 2) {
+    if (threadIdx.x < 68) t[threadIdx.x] = (int)threadIdx.x < table.levels - 1 ? table.v[threadIdx.x] : __int_as_float(0x7f800000);
+    if (threadIdx.x >= 128) lut[threadIdx.x - 128] = table.lut[threadIdx.x - 128];
+  } else if (threadIdx.x < 64) {
+    t[threadIdx.x] = table.v[threadIdx.x < table.levels ? threadIdx.x : table.levels - 1];
+  }
+  auto index_of = [&](float sigma) -> int {
+    if (kMode == 2) return scale_index_lut(sigma, t, lut, table.key_min, table.keys, table.levels);
+    return scale_index<kMode == 1>(sigma, t, table.levels);
+  };
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int b = blockIdx.y, p0 = blockIdx.x * 32;
+  if (a.sym_in) {  // coding order -> tile: warp = channel, lane = pixel
+    for (int c = warp; c < a.C; c += 8) {
+      const int p = p0 + lane;
+      if (p < a.plane) tile_a[c][lane] = a.sym_in[(int64_t)b * a.sym_in_bstride + (int64_t)c * a.plane + p];
+    }
+  }
+  __syncthreads();
+  for (int pp = warp; pp < 32; pp += 8) {  // warp = pixel, lane = channel: 128-byte rows of the NHWC tensors
+    const int p = p0 + pp, c = lane;
+    if (p >= a.plane || c >= a.C) continue;
+    const int64_t pix = (int64_t)b * a.plane + p;
+    const float m = a.means ? a.means[pix * a.m_ld + c] : 0.f;
+    const float sc = a.scales ? a.scales[pix * a.s_ld + c] : 0.f;
+    if (a.lik) {          // forward: likelihood + (ste-)rounded y_hat
+      float yh;
+      const float l = a.ste_round ? gauss_lik<true>(a.y[pix * a.y_ld + c], m, sc, a.scale_bound, a.lik_bound, &yh)
+                                  : gauss_lik<false>(a.y[pix * a.y_ld + c], m, sc, a.scale_bound, a.lik_bound, &yh);
+      tile_b[c][pp] = __float_as_int(l);
+      if (a.y_hat) a.y_hat[pix * a.yh_ld + c] = yh;
+      continue;
+    }
+    if (a.y) {            // encode: symbols + y_hat
+      const int q = round_to_symbol(a.y[pix * a.y_ld + c] - m);
+      tile_a[c][pp] = q;
+      if (a.y_hat) a.y_hat[pix * a.yh_ld + c] = (float)q + m;
+    } else if (a.sym_in) {  // decode: y_hat from the decoded symbols
+      a.y_hat[pix * a.yh_ld + c] = (float)tile_a[c][pp] + m;
+    }
+    if (a.scales && a.idx_out) tile_b[c][pp] = index_of(lower_bound_f(sc, a.scale_bound));
+  }
+  __syncthreads();
+  for (int c = warp; c < a.C; c += 8) {    // tile -> coding order
+    const int p = p0 + lane;
+    if (p >= a.plane) continue;
+    const int64_t o = (int64_t)c * a.plane + p;
+    if (a.lik) a.lik[(int64_t)b * a.lik_bstride + o] = __int_as_float(tile_b[c][lane]);
+    if (a.sym_out) a.sym_out[(int64_t)b * a.out_bstride + o] = tile_a[c][lane];
+    if (a.idx_out) a.idx_out[(int64_t)b * a.out_bstride + o] = tile_b[c][lane];
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
 // Entropy bottleneck (factorised prior), eval mode.  One block = one (batch, channel) plane tile;
 // the 58 pre-activated parameters (+ median) of the channel sit in shared memory.
 // ---------------------------------------------------------------------------------------------
@@ -443,6 +523,41 @@ extern "C" int stf_gaussian_compress_step(const float *y, int64_t y_batch_stride
     if (mode == 2) LAUNCH(false, 2); else if (mode == 1) LAUNCH(false, 1); else LAUNCH(false, 0);
   }
 #undef LAUNCH
+  return check_launch();
+}
+
+extern "C" int stf_slice_step_nhwc(const stf_slice_args *a, void *stream) {
+  if (!a || a->batch < 0 || a->channels <= 0 || a->channels > 32 || a->plane < 0) return STF_E_ARG;
+  const bool forward = a->likelihood != nullptr;
+  const bool encode = !forward && a->y != nullptr;
+  const bool decode_fin = !forward && !encode && a->symbols_in != nullptr;
+  if (forward && (!a->y || !a->scales)) return STF_E_ARG;
+  if (encode && !a->symbols_out && !a->y_hat) return STF_E_ARG;
+  if (decode_fin && !a->y_hat) return STF_E_ARG;
+  if (!forward && !encode && !decode_fin && !(a->scales && a->indexes_out)) return STF_E_ARG;
+  if (a->indexes_out && !a->scales) return STF_E_ARG;
+  ScaleTable t;
+  if (a->scales && a->indexes_out) {
+    int rc = fill_table(&t, a->table_host, a->levels);
+    if (rc) return rc;
+  } else {
+    t.levels = 1, t.monotone = 1, t.key_min = t.keys = 0;
+    for (float &v : t.v) v = 0.f;
+  }
+  if (a->batch == 0 || a->plane == 0) return STF_OK;
+  SliceNhwc k{};
+  k.y = a->y, k.y_ld = a->y_ld, k.scales = a->scales, k.s_ld = a->scales_ld, k.means = a->means, k.m_ld = a->means_ld;
+  k.sym_in = decode_fin ? a->symbols_in : nullptr, k.sym_in_bstride = a->symbols_in_batch_stride;
+  k.sym_out = encode ? a->symbols_out : nullptr, k.idx_out = forward ? nullptr : a->indexes_out, k.out_bstride = a->out_batch_stride;
+  k.y_hat = a->y_hat, k.yh_ld = a->y_hat_ld, k.lik = a->likelihood, k.lik_bstride = a->likelihood_batch_stride;
+  k.C = a->channels, k.plane = (int)a->plane, k.scale_bound = a->scale_bound, k.lik_bound = a->lik_bound, k.ste_round = a->ste_round;
+  dim3 grid((unsigned)((a->plane + 31) / 32), (unsigned)a->batch);
+  cudaStream_t st = (cudaStream_t)stream;
+  static const bool no_lut = getenv("STF_B200_NO_INDEX_LUT") != nullptr;
+  const int mode = !t.monotone ? 0 : (t.keys > 0 && !no_lut) ? 2 : 1;
+  if (mode == 2) slice_step_nhwc_kernel<2><<<grid, 256, 0, st>>>(k, t);
+  else if (mode == 1) slice_step_nhwc_kernel<1><<<grid, 256, 0, st>>>(k, t);
+  else slice_step_nhwc_kernel<0><<<grid, 256, 0, st>>>(k, t);
   return check_launch();
 }
 

@@ -286,7 +286,7 @@ class EntropyBottleneck(EntropyModel):
             training = self.training
         if x.dim() < 2 or x.shape[1] != self.channels:
             raise ValueError(f"expected (B, {self.channels}, ...) input, got {tuple(x.shape)}")
-        if training and torch.is_grad_enabled():
+        if training:      # noise quantisation is selected by `training` alone (entropy_models.py:131-135, 456)
             return self._forward_train(x, noise)
         z_hat, lik, _ = ops.entropy_bottleneck(x.contiguous(), self.packed_params(),
                                                lik_bound=self._likelihood_bound if self.use_likelihood_bound else 0.0)
@@ -412,7 +412,7 @@ class GaussianConditional(EntropyModel):
     def forward(self, inputs, scales, means=None, training=None, noise=None):
         if training is None:
             training = self.training
-        if training and torch.is_grad_enabled():
+        if training:
             from .autograd import GaussianLikelihoodTrain
             n = torch.empty_like(inputs).uniform_(-0.5, 0.5) if noise is None else noise
             lik = GaussianLikelihoodTrain.apply(inputs, scales.expand_as(inputs), None if means is None else

@@ -41,7 +41,10 @@ def _require_eval(mod):
 
 
 def _grad_mode(mod):
-    return mod.training and torch.is_grad_enabled()
+    """Training path (noise / DropPath / autograd Functions) is chosen on `training` alone, as in the reference
+    (stf.py:196-197 DropPath, entropy_models.py:131-135 noise); under torch.no_grad() the same Functions simply run
+    their forward.  eval() is the inference path: its kernels record no autograd graph."""
+    return mod.training
 
 
 class _PackCache:
@@ -308,8 +311,8 @@ class BasicLayer(nn.Module):
 
 
 class PatchEmbed(nn.Module):
-    """Conv2d(k=s=patch) + LayerNorm over channels (stf.py:350-381).  The 2x2 stride-2 convolution is a
-    cuDNN call (adjacent to the hot path)."""
+    """Conv2d(k=s=patch) + LayerNorm over channels (stf.py:350-381).  Inference: `tokens()` = one stf_patch_embed launch;
+    `forward()` (training) is the reference's op sequence on torch autograd."""
 
     def __init__(self, patch_size=4, in_chans=3, embed_dim=96, norm_layer=None):
         super().__init__()
@@ -320,25 +323,18 @@ class PatchEmbed(nn.Module):
         self.norm = norm_layer(embed_dim) if norm_layer is not None else None
 
     def tokens(self, x):
-        """Inference path: the same computation returning token-major (B, Wh*Ww, C) directly.  The NHWC output of the
-        convolution IS the token layout, so the reference's NCHW round trip (two full-tensor copies) disappears; the bias
-        add and the LayerNorm are one vectorised kernel each (torch launches its LayerNorm with one CTA per 48-float row)."""
-        _, _, H, W = x.shape
+        """Inference path: one kernel (stf_patch_embed) from the NCHW image to LayerNorm'ed token-major (B, Wh*Ww, C) -- the
+        layout every later kernel works in; the reference's NCHW round trip (two full-tensor copies), the separate bias add
+        and the LayerNorm launch disappear, and the result does not depend on the batch size (fixed summation order)."""
         ph, pw = self.patch_size
-        if W % pw != 0:
-            x = F.pad(x, (0, pw - W % pw))
-        if H % ph != 0:
-            x = F.pad(x, (0, 0, 0, ph - H % ph))
-        p = self.proj
-        x = F.conv2d(x.contiguous(memory_format=torch.channels_last), p.weight, None, p.stride, p.padding)
-        x = x.contiguous(memory_format=torch.channels_last)
-        if p.bias is not None:
-            ops.bias_act_(x, p.bias, gelu=False)
-        B, C, Wh, Ww = x.shape
-        t = x.permute(0, 2, 3, 1).reshape(B * Wh * Ww, C)          # a view: channels_last memory is token-major
-        if self.norm is not None:
-            t = ops.layernorm(t, self.norm.weight, self.norm.bias, self.norm.eps)
-        return t.reshape(B, Wh * Ww, C), Wh, Ww
+        E = self.embed_dim
+        if ph != pw or E not in (48, 96) or self.in_chans * ph * pw > 48:
+            raise ValueError(f"stf_patch_embed: unsupported PatchEmbed(patch={self.patch_size}, in={self.in_chans}, dim={E})")
+        B = x.shape[0]
+        n = self.norm
+        t, Wh, Ww = ops.patch_embed(x, self.proj.weight, self.proj.bias, None if n is None else n.weight,
+                                    None if n is None else n.bias, ph, 0.0 if n is None else n.eps)
+        return t.reshape(B, Wh * Ww, E), Wh, Ww
 
     def forward(self, x):
         _, _, H, W = x.shape

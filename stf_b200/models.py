@@ -13,13 +13,16 @@ load_state_dict / aux_loss signatures are the reference's.  What runs underneath
   * symbols and indexes of ALL slices are written by the kernels straight into one (B, M*h*w) int32
     device buffer in the reference's coding order and cross PCIe once, instead of 24 `.tolist()` syncs;
   * rANS runs on the host codec of the same library, one stream per image per host thread.
-Convolution stacks (hyperprior, cc_mean / cc_scale / lrp, PatchEmbed, end_conv, WACNN's g_a / g_s convs,
-GDN) are cuDNN calls through torch: adjacent to the hot path.
+  * the convolution stacks between the transforms (hyperprior h_a / h_mean_s / h_scale_s, cc_mean / cc_scale / lrp,
+    STF's PatchEmbed and end_conv[0]) -> stf_conv2d / stf_patch_embed: implicit-GEMM tcgen05 kernels on NHWC data moved
+    by tensor-map TMA, with the channel concat, bias + GELU, PixelShuffle and the LRP tail fused.
+Still cuDNN through torch: WACNN's g_a / g_s convolutions + GDN (8f rank 3) and the 3-channel end_conv[2] of STF
+(x_hat only).  For STF nothing upstream of a bitstream runs on cuDNN, so strings do not depend on the batch geometry.
 
 Batch semantics: the reference's compress() concatenates a whole batch into one y-string that its own
-decompress() cannot decode.  Here strings[0] holds ONE y-string PER IMAGE, each
-byte-identical to what the reference emits for that image alone; for batch 1 the return value has
-exactly the reference's structure.
+decompress() cannot decode.  Here strings[0] holds ONE y-string PER IMAGE, identical to what a
+batch-1 call on that image gives (asserted in tests/test_gpu_codec.py); for batch 1 the return value has exactly the
+reference's structure.
 """
 import math
 
@@ -171,38 +174,44 @@ def _stack5(c_in):
                          conv(128, 64, stride=1, kernel_size=3), nn.GELU(), conv(64, 32, stride=1, kernel_size=3))
 
 
-def _run_stack(seq, x):
-    """Inference path of a conv stack (nn.Sequential of Conv2d / GELU / subpel Sequential(Conv2d, PixelShuffle)): the
-    convolution is a cuDNN call WITHOUT bias on channels_last data, bias add + exact GELU are one in-place vectorised
-    kernel (ops.bias_act_) instead of torch's strided broadcast add + separate GELU launch (values identical: one fp32 add,
-    torch's GELU formula).  Module tree and checkpoint keys are untouched."""
-    mods = list(seq)
-    i = 0
+class _ConvPacks:
+    """Packed weight images of the convolutions that run on stf_conv2d, one per (conv module, source split, precision),
+    rebuilt when the module's weight / bias changed (storage pointer or in-place version counter)."""
+
+    def __init__(self):
+        self.cache = {}
+
+    def get(self, conv, src_channels, shuffle):
+        prec = ops.conv_precision_code()
+        key = (id(conv), tuple(src_channels), shuffle, prec)
+        w, b = conv.weight, conv.bias
+        ver = (w.data_ptr(), w._version, None if b is None else (b.data_ptr(), b._version))
+        hit = self.cache.get(key)
+        if hit is None or hit[0] != ver:
+            if conv.kernel_size[0] != conv.kernel_size[1] or conv.padding[0] != conv.kernel_size[0] // 2 or \
+                    conv.stride[0] != conv.stride[1] or conv.groups != 1 or conv.dilation[0] != 1:
+                raise ValueError(f"stf_conv2d: unsupported convolution {conv}")
+            hit = (ver, ops.PackedConv(w, b, src_channels, stride=conv.stride[0], pixel_shuffle=shuffle, prec=prec))
+            self.cache[key] = hit
+        return hit[1]
+
+
+def _stack_layers(seq):
+    """nn.Sequential of Conv2d / GELU / Sequential(Conv2d, PixelShuffle) -> [(conv, pixel_shuffle_factor, gelu_follows)]."""
+    mods, out, i = list(seq), [], 0
     while i < len(mods):
         m = mods[i]
-        shuffle = None
+        shuffle = 0
         if isinstance(m, nn.Sequential) and len(m) == 2 and isinstance(m[0], nn.Conv2d) and isinstance(m[1], nn.PixelShuffle):
-            conv, shuffle = m[0], m[1]
+            conv, shuffle = m[0], m[1].upscale_factor
         elif isinstance(m, nn.Conv2d):
             conv = m
         else:
-            x = m(x)
-            i += 1
-            continue
+            raise ValueError(f"unexpected module in a conv stack: {type(m).__name__}")
         gelu = i + 1 < len(mods) and isinstance(mods[i + 1], nn.GELU)
-        y = F.conv2d(x, conv.weight, None, conv.stride, conv.padding, conv.dilation, conv.groups)
-        if conv.bias is not None and y.shape[1] % 4 == 0:
-            if not y.is_contiguous(memory_format=torch.channels_last):
-                y = y.contiguous(memory_format=torch.channels_last)
-            ops.bias_act_(y, conv.bias, gelu)
-        else:
-            if conv.bias is not None:
-                y = y + conv.bias.reshape(1, -1, 1, 1)
-            if gelu:
-                y = F.gelu(y)
-        x = shuffle(y) if shuffle is not None else y
+        out.append((conv, shuffle, gelu))
         i += 2 if gelu else 1
-    return x
+    return out
 
 
 class _SliceCodec(CompressionModel):
@@ -217,6 +226,14 @@ class _SliceCodec(CompressionModel):
 
     def _synthesis(self, y_hat):
         raise NotImplementedError
+
+    def _analysis_nhwc(self, x):
+        """Inference: the latent as (B, h, w, M) NHWC."""
+        return self._analysis(x).permute(0, 2, 3, 1).contiguous()
+
+    def _synthesis_nhwc(self, y_hat):
+        """Inference: x_hat from the NHWC (B, h, w, M) y_hat buffer."""
+        return self._synthesis(y_hat.permute(0, 3, 1, 2))
 
     # shared ---------------------------------------------------------------------------------
     def update(self, scale_table=None, force=False):
@@ -238,35 +255,59 @@ class _SliceCodec(CompressionModel):
         return net
 
     # ------------------------------------------------------------------ slice-loop building blocks
-    # Inside the loop every tensor that feeds a convolution is channels_last (cuDNN's tensor-core kernels
-    # are NHWC: no per-conv layout transposes); the 32-channel tensors our kernels read / write are NCHW
-    # (the reference's coding order), converted by tiny copies.
+    # Everything between the analysis and the synthesis transform is NHWC (pixel-major) and runs on our own kernels:
+    # stf_conv2d for every convolution (the torch.cat in front of a stack is a multi-source gather, bias + GELU, the pixel
+    # shuffle and the LRP tail are its epilogues) and stf_slice_step_nhwc for the entropy steps.  All y_hat slices live in
+    # ONE (B, h, w, M) buffer: slice i's slot is channels [32i, 32i+32), the support of slice i is the channel prefix
+    # [0, 32 * min(i, max_support)) of the same buffer -- no concatenation, no layout copies, and after the last slice the
+    # buffer IS the synthesis transform's token-major input.  No cuDNN in here: per-image results do not depend on the
+    # batch they were computed in (stf.py:767 needs the decoder's indexes to equal the encoder's bit for bit).
     _CL = torch.channels_last
 
     def _prepare_inference(self):
-        """One-time: conv weights to channels_last (values unchanged, strides only)."""
+        """One-time: conv weights to channels_last (values unchanged, strides only) for the cuDNN convolutions that
+        remain (training path, WACNN g_a / g_s, the 3-channel image-side convolutions)."""
         if self.__dict__.get("_prepared"):
             return
         for m in self.modules():
             if isinstance(m, (nn.Conv2d, nn.ConvTranspose2d)) and m.weight.dim() == 4:
                 m.weight.data = m.weight.data.contiguous(memory_format=self._CL)
         self.__dict__["_prepared"] = True
+        self._drop_plans()
 
-    def _slice_params(self, i, latent_means, latent_scales, y_hat_slices, hw):
-        """mu and scale of slice i.  The two five-layer conv stacks are independent (stf.py:615-621): the scale
-        stack runs on a side stream, forked and joined with events (captured as parallel branches of the CUDA graph)."""
-        support = y_hat_slices if self.max_support_slices < 0 else y_hat_slices[: self.max_support_slices]
+    def _conv_stack(self, seq, srcs, out=None, last_act=None):
+        """Run a conv stack on NHWC sources through stf_conv2d.  srcs: list of (B, h, w, C_s) views = the channel concat
+        the reference builds with torch.cat; out: optional NHWC destination view of the last layer; last_act: "lrp" makes
+        the last layer compute out <- out + 0.5 * tanh(conv) in place (stf.py:631-633)."""
+        packs = self.__dict__.setdefault("_conv_packs", _ConvPacks())
+        layers = _stack_layers(seq)
+        x = list(srcs)
+        for li, (conv, shuffle, gelu) in enumerate(layers):
+            last = li == len(layers) - 1
+            pc = packs.get(conv, [t.shape[3] for t in x], shuffle)
+            act = True if gelu else (last_act if last else False)
+            x = [ops.conv2d(x, pc, act=act, out=out if last else None)]
+        return x[0]
+
+    def _support(self, y_hat, i):
+        """Channel prefix of the y_hat buffer that slice i is conditioned on (stf.py:608-611); None for slice 0."""
+        ns = i if self.max_support_slices < 0 else min(i, self.max_support_slices)
+        return y_hat[..., : self.slice_channels * ns] if ns else None
+
+    def _slice_params(self, i, latent_means, latent_scales, y_hat):
+        """mu and scale of slice i, NHWC (B, h, w, 32).  The two five-layer conv stacks are independent (stf.py:615-621):
+        the scale stack runs on a side stream, forked and joined with events (parallel branches of the CUDA graph)."""
+        sup = self._support(y_hat, i)
+        extra = [] if sup is None else [sup]
         main = torch.cuda.current_stream()
         side = self._side_stream(main.device)
         side.wait_stream(main)
         with torch.cuda.stream(side):
-            scale_support = torch.cat([latent_scales] + support, dim=1)
-            scale = _run_stack(self.cc_scale_transforms[i], scale_support)[:, :, : hw[0], : hw[1]].contiguous()
-        mean_support = torch.cat([latent_means] + support, dim=1)
-        mu = _run_stack(self.cc_mean_transforms[i], mean_support)[:, :, : hw[0], : hw[1]].contiguous()
+            scale = self._conv_stack(self.cc_scale_transforms[i], [latent_scales] + extra)
+        mu = self._conv_stack(self.cc_mean_transforms[i], [latent_means] + extra)
         main.wait_stream(side)
         scale.record_stream(main)
-        return mean_support, mu, scale
+        return mu, scale
 
     def _side_stream(self, device):
         streams = self.__dict__.setdefault("_side_streams", {})
@@ -275,25 +316,45 @@ class _SliceCodec(CompressionModel):
             streams[key] = torch.cuda.Stream(device=device)
         return streams[key]
 
-    def _lrp(self, i, mean_support, y_hat_slice):
-        y_hat_slice = y_hat_slice.contiguous(memory_format=self._CL)
-        lrp = _run_stack(self.lrp_transforms[i], torch.cat([mean_support, y_hat_slice], dim=1))
-        return y_hat_slice + 0.5 * torch.tanh(lrp)
+    def _lrp(self, i, latent_means, y_hat):
+        """y_hat slot i <- y_hat_i + 0.5 * tanh(lrp_i(cat([latent_means, support, y_hat_i])))  in place."""
+        Cs = self.slice_channels
+        slot = y_hat[..., Cs * i: Cs * (i + 1)]
+        ns = i if self.max_support_slices < 0 else min(i, self.max_support_slices)
+        if ns == i:      # the slot directly follows the support: one contiguous channel range
+            srcs = [latent_means, y_hat[..., : Cs * (i + 1)]]
+        else:
+            srcs = [latent_means, y_hat[..., : Cs * ns], slot]
+        self._conv_stack(self.lrp_transforms[i], srcs, out=slot, last_act="lrp")
 
     def _needed_as_support(self, i):
         return self.max_support_slices < 0 or i < self.max_support_slices
 
+    def _hyper_analysis(self, y):
+        """h_a on the NHWC latent -> z as (B, C, zh, zw) NCHW (18 k elements per image: the layout the bottleneck kernel and
+        the z coding order use)."""
+        return self._conv_stack(self.h_a, [y]).permute(0, 3, 1, 2).contiguous()
+
     def _hyper_synthesis(self, z_hat):
-        z_hat = z_hat.contiguous(memory_format=self._CL)
-        return _run_stack(self.h_scale_s, z_hat), _run_stack(self.h_mean_s, z_hat)
+        """z_hat (B, C, zh, zw) NCHW -> (latent_scales, latent_means), NHWC (B, h, w, M)."""
+        z = z_hat.permute(0, 2, 3, 1).contiguous()
+        return self._conv_stack(self.h_scale_s, [z]), self._conv_stack(self.h_mean_s, [z])
+
+    def _check_latent(self, latent, y_shape):
+        if tuple(latent.shape) != tuple(y_shape):
+            raise ValueError(f"hyper-synthesis output {tuple(latent.shape)} does not match the latent {tuple(y_shape)}: "
+                             "pad the image to a multiple of 64 (the reference's torch.cat fails the same way, stf.py:612)")
 
     def forward(self, x, noise=None):
         """eval / no_grad: the fused inference path.  train() with grad enabled: the training forward of
         stf.py:584-648 / cnn.py:141-189 ("noise" quantisation for the likelihoods, ste_round for y_hat / z_hat) with
         backward through stf_b200/autograd.py.  `noise` (optional dict {"y": (B,M,h,w), "z": (B,192,h',w')} of
         U(-1/2, 1/2) tensors) injects the quantisation noise for parity runs."""
-        if self.training and torch.is_grad_enabled():
+        if self.training:     # chosen on `training` alone, like the reference (noise + DropPath also under no_grad)
             return self._forward_train(x, noise)
+        if torch.is_grad_enabled() and x.requires_grad:
+            raise RuntimeError("eval-mode forward is the inference path (fused kernels, no autograd graph): call "
+                               ".train() for a differentiable forward, or detach the input")
         with torch.no_grad():
             if not (x.is_cuda and self._graphs_enabled()):
                 return self._forward_eval(x)
@@ -349,27 +410,27 @@ class _SliceCodec(CompressionModel):
 
     def _forward_eval(self, x):
         self._prepare_inference()
-        y = self._analysis(x)
-        hw = y.shape[2:]
-        z = _run_stack(self.h_a, y.contiguous(memory_format=self._CL)).contiguous()
+        y = self._analysis_nhwc(x)                                    # (B, h, w, M)
+        B, h, w, M = y.shape
+        z = self._hyper_analysis(y)
         eb = self.entropy_bottleneck
         z_hat, z_likelihoods, _ = ops.entropy_bottleneck(z, eb.packed_params(), lik_bound=eb._likelihood_bound,
                                                          ste_round=True)
         latent_scales, latent_means = self._hyper_synthesis(z_hat)
+        self._check_latent(latent_means, y.shape)
         gc = self.gaussian_conditional
         Cs = self.slice_channels
-        y_hat_slices, y_likelihood = [], []
+        y_hat = torch.empty_like(y)
+        y_lik = torch.empty((B, M, h, w), dtype=torch.float32, device=y.device)
         for i in range(self.num_slices):
-            mean_support, mu, scale = self._slice_params(i, latent_means, latent_scales, y_hat_slices, hw)
-            y_hat_i, lik = ops.gaussian_likelihood(y, i * Cs, scale, mu, scale_bound=gc.scale_bound_value(),
-                                                   lik_bound=gc._likelihood_bound, ste_round=True)
-            y_likelihood.append(lik)
-            y_hat_slices.append(self._lrp(i, mean_support, y_hat_i))
-        y_hat = torch.cat(y_hat_slices, dim=1)
-        out = {"x_hat": self._synthesis(y_hat),
-               "likelihoods": {"y": torch.cat(y_likelihood, dim=1), "z": z_likelihoods}}
+            mu, scale = self._slice_params(i, latent_means, latent_scales, y_hat)
+            ops.slice_step_nhwc(y=y[..., Cs * i: Cs * (i + 1)], scales=scale, means=mu, y_hat=y_hat[..., Cs * i: Cs * (i + 1)],
+                                likelihood=y_lik, lik_offset=Cs * i, scale_bound=gc.scale_bound_value(),
+                                lik_bound=gc._likelihood_bound, ste_round=True)
+            self._lrp(i, latent_means, y_hat)
+        out = {"x_hat": self._synthesis_nhwc(y_hat), "likelihoods": {"y": y_lik, "z": z_likelihoods}}
         if hasattr(self, "is_teacher"):
-            out["y"] = y if self.is_teacher else None
+            out["y"] = y.permute(0, 3, 1, 2).contiguous() if self.is_teacher else None
         return out
 
     # ------------------------------------------------------------------ encoder
@@ -378,29 +439,31 @@ class _SliceCodec(CompressionModel):
         No host synchronisation inside: capturable as one CUDA graph."""
         gc, eb = self.gaussian_conditional, self.entropy_bottleneck
         with _phase("enc.analysis"):
-            y = self._analysis(x)
-        B, M, h, w = y.shape
+            y = self._analysis_nhwc(x)
+        B, h, w, M = y.shape
         with _phase("enc.hyper"):
-            z = _run_stack(self.h_a, y.contiguous(memory_format=self._CL)).contiguous()
+            z = self._hyper_analysis(y)
             # EntropyBottleneck.compress + decompress (stf.py:688-689): decompress(z_strings) is
             # dequantize(symbols, medians), which the same kernel emits -- no need to decode our own stream
             z_hat, _, z_sym = ops.entropy_bottleneck(z, eb.packed_params(), want_lik=False, want_symbols=True)
             latent_scales, latent_means = self._hyper_synthesis(z_hat)
+            self._check_latent(latent_means, y.shape)
         Cs, plane = self.slice_channels, h * w
         sym = torch.empty((B, M * plane), dtype=torch.int32, device=y.device)
         idx = torch.empty((B, M * plane), dtype=torch.int32, device=y.device)
         table = gc.host_scale_table()
-        y_hat_slices = []
+        y_hat = torch.empty_like(y)
         with _phase("enc.slices"):
             for i in range(self.num_slices):
-                mean_support, mu, scale = self._slice_params(i, latent_means, latent_scales, y_hat_slices, (h, w))
+                mu, scale = self._slice_params(i, latent_means, latent_scales, y_hat)
                 need = self._needed_as_support(i) or keep is not None
-                y_hat_i = ops.gaussian_compress_step(y, i * Cs, scale, mu, table, sym, idx, i * Cs * plane,
-                                                     scale_bound=gc.scale_bound_value(), want_y_hat=need)
+                ops.slice_step_nhwc(y=y[..., Cs * i: Cs * (i + 1)], scales=scale, means=mu, symbols_out=sym, indexes_out=idx,
+                                    out_offset=i * Cs * plane, y_hat=y_hat[..., Cs * i: Cs * (i + 1)] if need else None,
+                                    table=table, scale_bound=gc.scale_bound_value())
                 if need:   # later slices are never read again in compress(): their LRP stacks are dead work
-                    y_hat_slices.append(self._lrp(i, mean_support, y_hat_i))
+                    self._lrp(i, latent_means, y_hat)
         if keep is not None:
-            keep.update(y=y, z=z, y_hat=torch.cat(y_hat_slices, 1).contiguous())
+            keep.update(y=y.permute(0, 3, 1, 2).contiguous(), z=z, y_hat=y_hat.permute(0, 3, 1, 2).contiguous())
         return sym, idx, z_sym
 
     def _graphs_enabled(self):
@@ -493,20 +556,25 @@ class _SliceCodec(CompressionModel):
         medians = med.reshape(1, C, 1).expand(B, C, z_sym[0, 0].numel()).contiguous()
         z_hat = ops.dequantize(z_sym.reshape(B, -1), 0, medians).reshape(z_sym.shape)
         st["scales"], st["means"] = self._hyper_synthesis(z_hat)
-        st["y_hat"] = []
+        st["y_hat"] = torch.empty_like(st["means"])
         return self._dec_params(st, 0)
 
     def _dec_params(self, st, i):
+        """Parameters of slice i -> its indexes (B, 32 * h * w) in coding order; mu is kept for the dequantize step."""
         gc = self.gaussian_conditional
         # per-slice entries keep every segment idempotent on `st` (graph warm-up runs a segment several times)
-        st["mean_support", i], st["mu", i], scale = self._slice_params(i, st["means"], st["scales"], st["y_hat"][:i],
-                                                                       st["hw"])
-        return ops.build_indexes(scale, gc.host_scale_table(), gc.scale_bound_value())
+        st["mu", i], scale = self._slice_params(i, st["means"], st["scales"], st["y_hat"])
+        B, h, w, Cs = scale.shape
+        idx = torch.empty((B, Cs * h * w), dtype=torch.int32, device=scale.device)
+        ops.slice_step_nhwc(scales=scale, indexes_out=idx, table=gc.host_scale_table(), scale_bound=gc.scale_bound_value())
+        return idx
 
     def _dec_slice(self, st, i, sym_prev):
-        """Finish slice i-1.  Idempotent on `st` (graph warm-up runs it more than once)."""
-        y_hat = ops.dequantize(sym_prev, 0, st["mu", i - 1])
-        st["y_hat"] = st["y_hat"][: i - 1] + [self._lrp(i - 1, st["mean_support", i - 1], y_hat)]
+        """Finish slice i-1: y_hat = symbols + mu into its slot, then the LRP update in place.  Idempotent on `st`: the slot
+        is rewritten from the symbols first (graph warm-up runs a segment more than once)."""
+        Cs = self.slice_channels
+        ops.slice_step_nhwc(symbols_in=sym_prev, means=st["mu", i - 1], y_hat=st["y_hat"][..., Cs * (i - 1): Cs * i])
+        self._lrp(i - 1, st["means"], st["y_hat"])
 
     def _dec_mid(self, st, i, sym_prev):
         self._dec_slice(st, i, sym_prev)
@@ -514,8 +582,7 @@ class _SliceCodec(CompressionModel):
 
     def _dec_last(self, st, sym_prev):
         self._dec_slice(st, self.num_slices, sym_prev)
-        y_hat = torch.cat(st["y_hat"], dim=1)
-        return self._synthesis(y_hat).clamp_(0, 1)
+        return self._synthesis_nhwc(st["y_hat"]).clamp_(0, 1)
 
     def _decode_plan(self, plans, slot, B, C, zh, zw, device):
         """13 CUDA-graph segments on one shared memory pool, captured once per (slot, B, z shape)."""
@@ -700,7 +767,7 @@ class SymmetricalTransFormer(_SliceCodec):
                 nn.init.constant_(m.weight, 1.0)
 
     def _analysis(self, x):
-        if torch.is_grad_enabled() and self.training:
+        if self.training:
             t = self.patch_embed(x)
             Wh, Ww = t.shape[2], t.shape[3]
             t = t.flatten(2).transpose(1, 2).contiguous()
@@ -711,24 +778,34 @@ class SymmetricalTransFormer(_SliceCodec):
         C = self.embed_dim * 8
         return t.reshape(-1, Wh, Ww, C).permute(0, 3, 1, 2).contiguous()
 
+    def _analysis_nhwc(self, x):
+        """Inference: the token-major output of the last Swin stage IS the NHWC latent (no layout copy)."""
+        t, Wh, Ww = self.patch_embed.tokens(x)
+        for layer in self.layers:
+            t, Wh, Ww = layer(t, Wh, Ww)
+        return t.reshape(-1, Wh, Ww, self.embed_dim * 8)
+
     def _synthesis(self, y_hat):
         B, C, Wh, Ww = y_hat.shape
         t = y_hat.permute(0, 2, 3, 1).contiguous().reshape(B, Wh * Ww, C)
         for layer in self.syn_layers:
             t, Wh, Ww = layer(t, Wh, Ww)
-        if torch.is_grad_enabled() and self.training:
-            return self.end_conv(t.reshape(B, Wh, Ww, self.embed_dim).permute(0, 3, 1, 2).contiguous())
-        # inference: stay in NHWC end to end (stf.py:466-469 makes three full-size layout copies around the pixel shuffle).
-        # The token-major tensor IS the channels_last image; the pixel shuffle is one NHWC copy; x_hat leaves as NCHW.
+        return self.end_conv(t.reshape(B, Wh, Ww, self.embed_dim).permute(0, 3, 1, 2).contiguous())
+
+    def _synthesis_nhwc(self, y_hat):
+        """Inference: NHWC end to end (stf.py:466-469 makes three full-size layout copies around the pixel shuffle).  The
+        y_hat buffer is the token-major input of the first synthesis stage; end_conv[0] + PixelShuffle is one stf_conv2d
+        launch on the token-major output of the last stage; the 3-channel end_conv[2] is a cuDNN call (x_hat only: nothing
+        downstream of the bitstream)."""
+        B, Wh, Ww, C = y_hat.shape
+        t = y_hat.reshape(B, Wh * Ww, C)
+        for layer in self.syn_layers:
+            t, Wh, Ww = layer(t, Wh, Ww)
         E = self.embed_dim
-        c0, c2 = self.end_conv[0], self.end_conv[2]
-        v = t.reshape(B, Wh, Ww, E).permute(0, 3, 1, 2)                                  # view, channels_last strides
-        u = F.conv2d(v, c0.weight, None, c0.stride, c0.padding).contiguous(memory_format=self._CL)
-        ops.bias_act_(u, c0.bias, gelu=False)
-        r = c0.out_channels // E                                                          # = patch_size ** 2
-        k = int(round(r ** 0.5))
-        s = u.permute(0, 2, 3, 1).reshape(B, Wh, Ww, E, k, k).permute(0, 1, 4, 2, 5, 3).reshape(B, Wh * k, Ww * k, E)
-        return c2(s.permute(0, 3, 1, 2)).contiguous()
+        c0, ps, c2 = self.end_conv[0], self.end_conv[1], self.end_conv[2]
+        packs = self.__dict__.setdefault("_conv_packs", _ConvPacks())
+        u = ops.conv2d([t.reshape(B, Wh, Ww, E)], packs.get(c0, [E], ps.upscale_factor))     # (B, 2Wh, 2Ww, E) NHWC
+        return c2(u.permute(0, 3, 1, 2)).contiguous()
 
 
 class _NonNegativeParametrizer(nn.Module):
@@ -805,6 +882,9 @@ class WACNN(_SliceCodec):
 
     def _synthesis(self, y_hat):
         return self.g_s(y_hat)
+
+    def _synthesis_nhwc(self, y_hat):
+        return self.g_s(y_hat.permute(0, 3, 1, 2).contiguous())      # (g_s starts with a token-major attention block)
 
 
 models = {"stf": SymmetricalTransFormer, "cnn": WACNN}   # compressai/zoo/__init__.py:20-27 (in-scope entries)

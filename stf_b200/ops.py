@@ -12,13 +12,30 @@ import torch
 from . import _C, profiler
 
 _f32p = ctypes.POINTER(ctypes.c_float)
+_SYNC_LAUNCH = os.environ.get("STF_B200_SYNC_LAUNCH", "0") == "1"
 
 
 def _launch(kernel, nbytes, fn, *args):
     """Call one C-ABI entry point; raise on a non-zero status.  `kernel` / `nbytes` name the CUDA kernel
     and its algorithmic bytes for profiler.capture()."""
     cap = profiler.ACTIVE
-    if cap is None:
+    if _SYNC_LAUNCH:     # bring-up: synchronise after every launch so that a device fault names its kernel and arguments
+        rc = fn(*args)
+        try:
+            torch.cuda.synchronize()
+        except Exception:
+            import sys
+            desc = []
+            for a in args:
+                obj = getattr(a, "_obj", None)     # ctypes.byref(struct)
+                if obj is not None and hasattr(obj, "_fields_"):
+                    desc.append({f[0]: (list(getattr(obj, f[0])) if hasattr(getattr(obj, f[0]), "__len__") else getattr(obj, f[0]))
+                                 for f in obj._fields_})
+                else:
+                    desc.append(a)
+            print(f"[stf_b200] device fault after {kernel} ({fn.__name__}): {desc}", file=sys.stderr, flush=True)
+            raise
+    elif cap is None:
         rc = fn(*args)
     else:
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -154,6 +171,70 @@ def gaussian_likelihood(y, channel_offset, scales, means, scale_bound=0.11, lik_
     return y_hat, lik
 
 
+def _nhwc(t, name, C=None):
+    """(B, h, w, C) fp32 CUDA view with unit channel stride and a uniform pixel stride -> (ptr, ld)."""
+    if t is None:
+        return None, 0
+    if not t.is_cuda or t.dtype != torch.float32:
+        raise RuntimeError(f"stf_b200: `{name}` must be a CUDA fp32 tensor (there is no CPU path)")
+    if t.dim() != 4:
+        raise ValueError(f"stf_b200: `{name}` must be a 4-D NHWC tensor, got {tuple(t.shape)}")
+    B, h, w, c = t.shape
+    # pixel stride from the first dimension that has one (strides of size-1 dimensions are arbitrary)
+    ld = t.stride(2) if w > 1 else (t.stride(1) if h > 1 else (t.stride(0) if B > 1 else c))
+    ok = (c == 1 or t.stride(3) == 1) and (w == 1 or t.stride(2) == ld) and (h == 1 or t.stride(1) == w * ld) and \
+        (B == 1 or t.stride(0) == h * w * ld) and ld >= c and (C is None or c == C)
+    if not ok:
+        raise ValueError(f"stf_b200: `{name}` must be an NHWC view with a uniform pixel stride, got {tuple(t.shape)} / {t.stride()}")
+    return t.data_ptr(), ld
+
+
+def slice_step_nhwc(*, y=None, scales=None, means=None, symbols_in=None, sym_in_offset=0, symbols_out=None,
+                    indexes_out=None, out_offset=0, y_hat=None, likelihood=None, lik_offset=0, table=None,
+                    scale_bound=0.11, lik_bound=1e-9, ste_round=False):
+    """One slice step on NHWC operands (stf_slice_step_nhwc in include/stf_b200.h).
+
+    y / scales / means / y_hat: (B, h, w, C<=32) NHWC views (channel slices of wider tensors are fine; y_hat is written).
+    symbols_in / symbols_out / indexes_out: (B, total) int32 buffers in coding order, the slice at element offset
+    sym_in_offset / out_offset of every row.  likelihood: (B, M, h, w) NCHW tensor, the slice at channel lik_offset.
+    The step (forward / encode / decode / indexes) follows from which arguments are given."""
+    ref = next(t for t in (y, scales, means, y_hat) if t is not None)
+    B, h, w, C = ref.shape
+    plane = h * w
+    a = _C.SliceArgs()
+    a.y, a.y_ld = _nhwc(y, "y", C)
+    a.scales, a.scales_ld = _nhwc(scales, "scales", C)
+    a.means, a.means_ld = _nhwc(means, "means", C)
+    a.y_hat, a.y_hat_ld = _nhwc(y_hat, "y_hat", C)
+    if symbols_in is not None:
+        symbols_in = _dev(symbols_in, "symbols_in", torch.int32)
+        a.symbols_in, a.symbols_in_batch_stride = symbols_in.data_ptr() + 4 * sym_in_offset, symbols_in.shape[1]
+    total = None
+    for name, buf in (("symbols_out", symbols_out), ("indexes_out", indexes_out)):
+        if buf is None:
+            continue
+        buf = _dev(buf, name, torch.int32)
+        if total is not None and buf.shape[1] != total:
+            raise ValueError("symbols_out and indexes_out must have the same row length")
+        total = buf.shape[1]
+        if out_offset + C * plane > total:
+            raise ValueError(f"{name} buffer too small")
+        setattr(a, name, buf.data_ptr() + 4 * out_offset)
+    a.out_batch_stride = total or 0
+    if likelihood is not None:
+        likelihood = _dev(likelihood, "likelihood")
+        a.likelihood = likelihood.data_ptr() + 4 * lik_offset * plane
+        a.likelihood_batch_stride = likelihood.shape[1] * plane
+    a.batch, a.channels, a.plane = B, C, plane
+    keep = None
+    if indexes_out is not None:
+        keep, a.table_host = _host_table(table)
+        a.levels = keep.size
+    a.scale_bound, a.lik_bound, a.ste_round = float(scale_bound), float(lik_bound), int(bool(ste_round))
+    streams = sum(t is not None for t in (y, scales, means, symbols_in, symbols_out, indexes_out, y_hat, likelihood))
+    _launch("slice_step_nhwc_kernel", 4 * streams * B * C * plane, _C.lib().stf_slice_step_nhwc, ctypes.byref(a), _C.stream())
+
+
 def entropy_bottleneck(z, params, lik_bound=1e-9, want_z_hat=True, want_lik=True, want_symbols=False,
                        ste_round=False):
     """EntropyBottleneck.forward (eval) without the permutes; params: (C, 60) packed (see header)."""
@@ -274,6 +355,100 @@ def window_attention_core(qkv, bias_table, num_windows, C, heads, ws, shift, Hp=
     return out
 
 
+# ------------------------------------------------------------------------------------ convolution stacks
+
+def conv_precision_code():
+    """Arithmetic of the conv kernel.  Default = the library's GEMM precision for the strict "fp32" parity runs only when
+    STF_B200_CONV_PRECISION=fp32 (or set_conv_precision("fp32")): otherwise single-pass TF32 on the raw fp32 activations,
+    which is what the reference's convolutions do on a GPU (torch's cudnn.allow_tf32 default)."""
+    return _conv_precision
+
+
+def set_conv_precision(name):
+    global _conv_precision
+    old = "fp32" if _conv_precision == _C.PREC_FP32 else "tf32"
+    _conv_precision = _PRECISIONS[name.lower()]
+    return old
+
+
+_conv_precision = _PRECISIONS[os.environ.get("STF_B200_CONV_PRECISION", "tf32").lower()]
+
+
+class PackedConv:
+    """An nn.Conv2d weight (N, sum C_s, k, k) + bias packed for stf_conv2d: K-major [N][tap][source][channel padded to 32]
+    TF32 image(s) + bias, output channels in sub-pixel-major order when a PixelShuffle(2) follows."""
+
+    def __init__(self, weight, bias, src_channels, stride=1, pixel_shuffle=0, prec=None):
+        self.precision = _conv_precision if prec is None else int(prec)
+        w = _dev(weight.detach().contiguous(), "weight")      # (N, C, k, k) in NCHW-contiguous order for the packer
+        self.N, ctot, self.ksize, k2 = w.shape
+        if k2 != self.ksize or sum(src_channels) != ctot:
+            raise ValueError("stf_conv2d: weight shape does not match the sources' channels")
+        self.src_channels = tuple(int(c) for c in src_channels)
+        self.stride, self.pixel_shuffle = int(stride), int(pixel_shuffle)
+        b = None if bias is None else _dev(bias.detach().contiguous(), "bias")
+        a = self.args()
+        n = int(_C.lib().stf_packed_conv_floats(ctypes.byref(a)))
+        if n < 0:
+            _C.check(n, "stf_packed_conv_floats")
+        self.packed = torch.empty(n, dtype=torch.float32, device=w.device)
+        _launch("pack_conv_kernel", 8 * w.numel(), _C.lib().stf_pack_conv, ctypes.byref(a), w.data_ptr(), _C.ptr(b),
+                self.packed.data_ptr(), _C.stream())
+
+    def args(self):
+        a = _C.ConvArgs()
+        a.n_src = len(self.src_channels)
+        for i, c in enumerate(self.src_channels):
+            a.src_channels[i] = c
+        a.N, a.ksize, a.stride = self.N, self.ksize, self.stride
+        a.pixel_shuffle, a.precision = self.pixel_shuffle, self.precision
+        return a
+
+
+def conv_out_hw(H, W, ksize, stride):
+    ho, wo = ctypes.c_int(), ctypes.c_int()
+    _C.check(_C.lib().stf_conv2d_out_hw(int(H), int(W), int(ksize), int(stride), ctypes.byref(ho), ctypes.byref(wo)),
+             "stf_conv2d_out_hw")
+    return ho.value, wo.value
+
+
+def conv2d(srcs, pc, act=False, out=None, residual=None):
+    """act(conv2d(cat(srcs, channel), W) + bias) on NHWC tensors (stf_conv2d in include/stf_b200.h).
+
+    srcs: list of (B, H, W, C_s) fp32 CUDA tensors whose last dimension is dense (a channel slice of a wider NHWC tensor
+    is fine: only the pixel stride must be uniform); pc: PackedConv; out: optional (B, Ho, Wo, N) / (B, 2Ho, 2Wo, N/4)
+    destination view (same stride rules).  act: False / True ("gelu") / "lrp" (out = residual + 0.5 * tanh(conv + bias), the
+    residual defaulting to `out` itself, updated in place: stf.py:631-633).  Returns the NHWC output."""
+    a = pc.args()
+    B, H, W = srcs[0].shape[:3]
+    if len(srcs) != a.n_src:
+        raise ValueError("stf_conv2d: number of sources does not match the packed weight")
+    for i, t in enumerate(srcs):
+        if not t.is_cuda or t.dtype != torch.float32:
+            raise RuntimeError("stf_conv2d: sources must be CUDA fp32 tensors (there is no CPU path)")
+        if t.dim() != 4 or tuple(t.shape[:3]) != (B, H, W) or t.shape[3] != pc.src_channels[i]:
+            raise ValueError(f"stf_conv2d: source {i} has shape {tuple(t.shape)}")
+        a.src[i], a.src_ld[i] = _nhwc(t, f"source {i}")
+    a.batch, a.H, a.W = B, H, W
+    Ho, Wo = conv_out_hw(H, W, pc.ksize, pc.stride)
+    r = 2 if pc.pixel_shuffle else 1
+    shape = (B, Ho * r, Wo * r, pc.N // (r * r))
+    if out is None:
+        out = torch.empty(shape, dtype=torch.float32, device=srcs[0].device)
+    elif tuple(out.shape) != shape:
+        raise ValueError(f"stf_conv2d: `out` must be an NHWC view of shape {shape}")
+    a.w_packed = pc.packed.data_ptr()
+    a.y, a.ldy = _nhwc(out, "out")
+    a.act = {False: 0, True: 1, None: 0, "gelu": 1, "lrp": 2}[act]
+    if a.act == 2:      # out <- residual + 0.5 * tanh(conv + bias); the residual defaults to the output's current content
+        res = out if residual is None else residual
+        a.residual, a.res_ld = _nhwc(res, "residual", shape[3])
+    ctot = sum(pc.src_channels)
+    nbytes = 4 * (B * H * W * ctot + pc.N * ctot * pc.ksize ** 2 + B * Ho * Wo * pc.N)
+    _launch("conv_tf32_kernel", nbytes, _C.lib().stf_conv2d, ctypes.byref(a), _C.stream())
+    return out
+
+
 def bias_act_(x, bias, gelu):
     """x <- act(x + bias[c]) in place; x: (B, C, H, W) in channels_last memory format (dense NHWC)."""
     if not x.is_cuda or x.dtype != torch.float32 or x.dim() != 4 or not x.is_contiguous(memory_format=torch.channels_last):
@@ -282,6 +457,22 @@ def bias_act_(x, bias, gelu):
     _launch("bias_act_kernel", 8 * x.numel(), _C.lib().stf_bias_act, x.data_ptr(), bias.data_ptr(), x.shape[1], x.numel(),
             1 if gelu else 0, _C.stream())
     return x
+
+
+def patch_embed(x, weight, bias, ln_weight, ln_bias, patch, eps):
+    """PatchEmbed (stf.py:350-381) on the NCHW image -> (tokens (B * Wh * Ww, E), Wh, Ww)."""
+    x = _dev(x.contiguous(), "x")
+    B, Cin, H, W = x.shape
+    w = _dev(weight.detach().contiguous(), "weight")
+    E = w.shape[0]
+    Wh, Ww = -(-H // patch), -(-W // patch)
+    out = torch.empty((B * Wh * Ww, E), dtype=torch.float32, device=x.device)
+    g = None if ln_weight is None else _dev(ln_weight.detach().contiguous(), "norm.weight")
+    be = None if ln_bias is None else _dev(ln_bias.detach().contiguous(), "norm.bias")
+    b = None if bias is None else _dev(bias.detach().contiguous(), "bias")
+    _launch("patch_embed_kernel", 4 * (x.numel() + out.numel()), _C.lib().stf_patch_embed, x.data_ptr(), w.data_ptr(),
+            _C.ptr(b), _C.ptr(g), _C.ptr(be), out.data_ptr(), B, Cin, H, W, int(patch), E, float(eps), _C.stream())
+    return out, Wh, Ww
 
 
 def layernorm(x, weight, bias, eps):
