@@ -236,6 +236,16 @@ int stf_window_attention(const float *qkv, float *out, const float *bias_table, 
                          int mask_windows, int64_t num_windows, int C, int heads, int ws, int shift,
                          int Hp, int Wp, int tf32_out, void *stream);
 
+/* The same attention core for 4x4 windows / head_dim 16 (every STF stage) on TOKEN-order operands, contractions on tensor
+ * cores: qkv (batch, H, W, 3C) as the dense qkv GEMM (stf_conv2d, ksize 1) leaves it, out (batch, H, W, C) as the proj GEMM
+ * reads it.  window_partition / torch.roll / F.pad / window_reverse / un-roll / crop (stf.py:155-196) are the kernel's
+ * address arithmetic on per-token bulk (TMA) copies; pad tokens (zero after norm1, stf.py:155-162) take the row pad_qkv[3C]
+ * (= qkv bias with the q third pre-scaled; may be NULL when H and W are multiples of 4) and their outputs are dropped.
+ * QK^T and PV run as mma.sync.m16n8k8 TF32 tiles, one warp per (window, head) -- 3xTF32 (hi / lo split) when precision is
+ * STF_PREC_FP32 --, bias + analytic mask are added on the accumulator fragments, softmax reduces rows with warp shuffles. */
+int stf_window_attention_tokens(const float *qkv, float *out, const float *bias_table, const float *pad_qkv, int batch,
+                                int H, int W, int C, int heads, int ws, int shift, int precision, void *stream);
+
 /* ------------------------------------------------------------------------------------------
  * Convolution stacks either side of the entropy kernels: the five-layer 3x3 cc_mean / cc_scale /
  * lrp stacks of the slice loop (stf.py:510-548 called at :613-633, :706-729, :757-779; cnn.py:89-127), the hyperprior
@@ -261,19 +271,28 @@ typedef struct {
   float *y;                   /* output NHWC: (batch, Ho, Wo, N), or (batch, 2Ho, 2Wo, N/4) with pixel_shuffle */
   int ldy;                    /* output pixel stride in floats */
   int act;                    /* 0: none, 1: exact-erf GELU (nn.GELU), 2: residual + 0.5 * tanh(.) -- the LRP tail */
-                              /* `y_hat_slice + 0.5 * torch.tanh(lrp)` (stf.py:631-633), no pixel shuffle */
-  const float *residual;      /* act 2: NHWC (batch, Ho, Wo, N) tensor, may alias y (updated in place) */
+                              /* `y_hat_slice + 0.5 * torch.tanh(lrp)` (stf.py:631-633), 3: residual + (.) -- the */
+                              /* shortcut add behind fc2 / proj (stf.py:196-197); 2 and 3 without pixel shuffle */
+  const float *residual;      /* act 2 / 3: NHWC (batch, Ho, Wo, N) tensor, may alias y (updated in place) */
   int res_ld;                 /* its pixel stride in floats */
   int pixel_shuffle;          /* 0 or 2 */
+  int has_ln;                 /* ksize 1, one source: a LayerNorm over the source's channels is folded through the GEMM */
+  float ln_eps;               /* (row statistics gathered in-kernel while the rows stream through shared memory) */
   int precision;              /* STF_PREC_TF32: one MMA per k-step on the raw fp32 activations (what cuDNN's default TF32 */
                               /* convolutions do); STF_PREC_FP32: 3xTF32 split of both operands, fp32-grade */
 } stf_conv_args;
-/* Floats of the packed weight image: planes * N * Kp + N, Kp = ksize^2 * sum_s ceil32(src_channels[s]). */
+/* Floats of the packed weight image: planes * N * Kp + 2 N, Kp = ksize^2 * sum_s ceil32(src_channels[s]). */
 int64_t stf_packed_conv_floats(const stf_conv_args *args);
 /* Pack an nn.Conv2d weight (N, sum C_s, ksize, ksize) contiguous fp32 (+ bias[N] or NULL), device pointers, into the K-major
- * [N][tap][source][channel padded to 32] image (TF32 hi plane, plus the lo plane for STF_PREC_FP32) followed by the bias,
- * output channels permuted to sub-pixel-major order when pixel_shuffle = 2. */
-int stf_pack_conv(const stf_conv_args *args, const float *weight, const float *bias, float *packed, void *stream);
+ * [N][tap][source][channel padded to 32] image (TF32 hi plane, plus the lo plane for STF_PREC_FP32) followed by two N-vectors
+ * t (= bias) and s (= 0), output channels permuted to sub-pixel-major order when pixel_shuffle = 2.
+ * The same entry packs an nn.Linear (ksize 1; a token-major (M, K) matrix is the NHWC image (1, 1, M, K)) together with the
+ * LayerNorm in front of it (args->has_ln, ln_gamma / ln_beta of K floats): the image holds gamma o W,
+ * s = sum_k (gamma o W)[n][k], t = beta . W^T + bias, and stf_conv2d evaluates
+ * LN(x) . W^T + bias = rstd * (x . (gamma o W)^T - mean * s) + t in its epilogue.  Output columns < scale_cols are multiplied
+ * by row_scale (the q third of a qkv Linear times d^-1/2, stf.py:99); pass 0 / 1.0f otherwise. */
+int stf_pack_conv(const stf_conv_args *args, const float *weight, const float *bias, const float *ln_gamma,
+                  const float *ln_beta, int scale_cols, float row_scale, float *packed, void *stream);
 int stf_conv2d(const stf_conv_args *args, void *stream);
 /* Output size of the convolution: Ho = (H + 2p - k) / s + 1 (before any pixel shuffle). */
 int stf_conv2d_out_hw(int H, int W, int ksize, int stride, int *Ho, int *Wo);

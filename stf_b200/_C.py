@@ -45,7 +45,7 @@ class ConvArgs(ctypes.Structure):
         ("src", c_vp * 3), ("src_channels", c_int * 3), ("src_ld", c_int * 3),
         ("N", c_int), ("ksize", c_int), ("stride", c_int),
         ("w_packed", c_vp), ("y", c_vp), ("ldy", c_int), ("act", c_int), ("residual", c_vp), ("res_ld", c_int),
-        ("pixel_shuffle", c_int), ("precision", c_int),
+        ("pixel_shuffle", c_int), ("has_ln", c_int), ("ln_eps", c_f32), ("precision", c_int),
     ]
 
 
@@ -80,8 +80,9 @@ SIGNATURES = {
     "stf_pack_linear": (c_int, [c_vp, c_vp, c_vp, c_vp, c_vp, c_int, c_int, c_int, c_vp]),
     "stf_linear": (c_int, [ctypes.POINTER(LinearArgs), c_vp]),
     "stf_window_attention": (c_int, [c_vp, c_vp, c_vp, c_vp, c_int, c_i64, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_vp]),
+    "stf_window_attention_tokens": (c_int, [c_vp, c_vp, c_vp, c_vp, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_vp]),
     "stf_packed_conv_floats": (c_i64, [ctypes.POINTER(ConvArgs)]),
-    "stf_pack_conv": (c_int, [ctypes.POINTER(ConvArgs), c_vp, c_vp, c_vp, c_vp]),
+    "stf_pack_conv": (c_int, [ctypes.POINTER(ConvArgs), c_vp, c_vp, c_vp, c_vp, c_int, c_f32, c_vp, c_vp]),
     "stf_conv2d": (c_int, [ctypes.POINTER(ConvArgs), c_vp]),
     "stf_conv2d_out_hw": (c_int, [c_int, c_int, c_int, c_int, ctypes.POINTER(c_int), ctypes.POINTER(c_int)]),
     "stf_patch_embed": (c_int, [c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_int, c_int, c_int, c_int, c_int, c_int, c_f32, c_vp]),

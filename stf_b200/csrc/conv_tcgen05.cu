@@ -24,8 +24,9 @@
 //   D          fp32 accumulators in TMEM, double buffered (epilogue of tile i under the K loop of tile i+1).
 //   epilogue   tcgen05.ld -> + bias -> exact-erf GELU -> swizzled staging tile -> 4-D tensor-map TMA store (edge clipping and
 //              the pixel-shuffle scatter are the store map's geometry).
-// Warp roles (384 threads, one persistent CTA per SM): warp 0 TMA producer, warp 1 MMA issuer (+ TMEM alloc), warps 4-7 epilogue
-// (warp & 3 = TMEM lane quadrant), warps 8-11 hi/lo splitter (3xTF32 mode only: A stage -> truncated hi in place + lo plane).
+// Warp roles (512 threads, one persistent CTA per SM): warp 0 TMA producer, warp 1 MMA issuer (+ TMEM alloc), warps 4-11 epilogue
+// (warp & 3 = TMEM lane quadrant, two warps per quadrant on alternating column chunks), warps 12-15 A pass (3xTF32: A stage ->
+// truncated hi in place + lo plane; LayerNorm: row statistics).
 #include <cuda.h>  // CUtensorMap + enums only; cuTensorMapEncodeTiled is resolved at run time (no link-time libcuda dependency)
 #include <math.h>
 #include <stdio.h>
@@ -45,10 +46,15 @@ constexpr int kTileM = 128;
 constexpr int kBlockK = 32;                       // floats per k-block = one 128-byte swizzle row
 constexpr uint32_t kAStageBytes = kTileM * 128;   // 16 KB
 constexpr int kMaxStages = 8;
-constexpr int kThreads = 384;
-constexpr int kProducerWarp = 0, kMmaWarp = 1, kFirstEpiWarp = 4, kFirstSplitWarp = 8;
+constexpr int kEpiWarps = 8;   // two per TMEM lane quadrant (alternating column chunks): one warp per scheduler cannot hide its
+                               // own ALU / LDS / MUFU latencies (measured: the GELU epilogue of a 192-column tile took 38 k cycles)
+constexpr int kThreads = 512;
+constexpr int kProducerWarp = 0, kMmaWarp = 1, kFirstEpiWarp = 4, kFirstSplitWarp = kFirstEpiWarp + kEpiWarps;
 constexpr int kMaxSrc = 3;
-constexpr uint32_t kStagingBytes = kTileM * 128;  // one 128 x 32-float output chunk (or 128 x 16 in 64-byte rows)
+constexpr uint32_t kSlabBytes = 32 * 128;         // one epilogue warp's 32 rows x 32 floats (or 32 x 16 in 64-byte rows)
+constexpr int kMaxSlabs = 4;                      // staging slabs per epilogue warp (2..4: bulk stores in flight per warp + 1)
+constexpr int kStatSlots = 12;                    // (mean, rstd) of the 128 rows of a tile, ring over the tiles in flight: the
+                                                  // A pass leads the epilogue by at most kMaxStages k-blocks + 2 tiles
 
 struct ConvParams {
   alignas(64) CUtensorMap a_map[kMaxSrc];
@@ -60,12 +66,19 @@ struct ConvParams {
   int n_src;
   int src_kb[kMaxSrc];                // 32-channel k-blocks per tap of each source
   int kb_per_tap, k_blocks, ksize, pad, stride;
-  int N, n_tile, n_tiles;
+  int N, n_tile, n_tiles, n_pad;      // n_pad = n_tiles * n_tile rounded up to 32: length of the shared-memory epilogue vectors
   int TW, TH, tiles_x, tiles_y, tiles_per_img, m_tiles, total_tiles;
-  int act;                            // 0 none, 1 exact-erf GELU, 2 residual + 0.5 * tanh(.)  (the LRP tail, stf.py:631-633)
+  int act;                            // 0 none, 1 exact-erf GELU, 2 residual + 0.5 * tanh(.)  (the LRP tail, stf.py:631-633),
+                                      // 3 residual + (.)  (fc2 / proj + shortcut, stf.py:196-197)
+  int ln_k;                           // has_ln: number of real input features (K before padding to 32)
+  int has_ln;                         // LayerNorm over the K inputs of every row folded through the GEMM (see pack)
+  float ln_eps;
+  const float *svec;                  // has_ln: s[N] = sum_k (gamma o W)[n][k]
   int shuffle_cout;                   // 0: plain store; else channels after PixelShuffle(2) (N = 4 * shuffle_cout)
   int cw;                             // store chunk width in channels: 32 (SWIZZLE_128B staging) or 16 (SWIZZLE_64B)
   int stages;
+  int slabs;                          // staging slabs per epilogue warp
+  int debug;                          // bring-up (env STF_B200_CONV_DEBUG): 1 no stores, 2 no staging writes, 4 no epilogue math, 8 no A loads
   uint32_t idesc;
   int tmem_cols, acc_stride;
   uint32_t stage_bytes, b_plane_bytes;  // per pipeline stage: A hi (+ A lo) + B hi (+ B lo)
@@ -95,7 +108,8 @@ __device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap *map) {
   asm volatile("prefetch.tensormap [%0];" ::"l"(map) : "memory");
 }
 __device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
-__device__ __forceinline__ void bulk_wait_read1() { asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory"); }
 __device__ __forceinline__ void bulk_wait0() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
 __device__ __forceinline__ void named_bar_sync(int id, int threads) {
   asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(threads) : "memory");
@@ -158,9 +172,36 @@ __device__ __forceinline__ float gelu_erf(float x) {
 
 __device__ __forceinline__ float trunc_tf32(float x) { return __uint_as_float(__float_as_uint(x) & 0xFFFFE000u); }
 
+// Epilogue math of one chunk (32 accumulator columns of one row), act fixed at compile time: the 32 element chains are
+// independent and branch-free, bias / LayerNorm vectors come as 128-bit broadcast loads.  Columns past the tile or past N carry
+// finite garbage: they land in staging columns the TMA store clips.
+template <int kLn, int kAct>
+__device__ __forceinline__ void epi_math(const uint32_t (&r)[32], float (&v)[32], const float *__restrict__ tv,
+                                         const float *__restrict__ sv, float mean, float rstd,
+                                         const float *__restrict__ res_row, int res_cols) {
+#pragma unroll
+  for (int j = 0; j < 32; j += 4) {
+    const float4 t4 = *reinterpret_cast<const float4 *>(tv + j);
+    float4 s4 = make_float4(0.f, 0.f, 0.f, 0.f), r4 = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (kLn) s4 = *reinterpret_cast<const float4 *>(sv + j);
+    if (kAct >= 2 && res_row && j < res_cols) r4 = *reinterpret_cast<const float4 *>(res_row + j);
+    const float tt[4] = {t4.x, t4.y, t4.z, t4.w}, ss[4] = {s4.x, s4.y, s4.z, s4.w}, rr[4] = {r4.x, r4.y, r4.z, r4.w};
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      float a = __uint_as_float(r[j + q]);
+      a = kLn ? fmaf(rstd, a - mean * ss[q], tt[q]) : a + tt[q];
+      if (kAct == 1) a = gelu_erf(a);
+      else if (kAct == 2) a = rr[q] + 0.5f * tanhf(a);
+      else if (kAct == 3) a = rr[q] + a;
+      v[j + q] = a;
+    }
+  }
+}
+
 // ---------------------------------------------------------------------------- the kernel
-template <int kPrecise>
+template <int kPrecise, int kLn>
 __global__ void __launch_bounds__(kThreads, 1) conv_tf32_kernel(const __grid_constant__ ConvParams P) {
+  constexpr bool kAPass = kPrecise || kLn;   // warps 8-11 touch every landed A stage (hi / lo split and / or row statistics)
   extern __shared__ uint8_t smem_raw[];
   // operand stages need 1024-byte alignment (swizzle atoms); the launch asks for 1 KB of slack
   const uint32_t raw_u32 = smem_u32(smem_raw);
@@ -171,14 +212,19 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tf32_kernel(const __grid_con
   const uint32_t b_off = kPrecise ? 2 * kAStageBytes : kAStageBytes;       // B hi plane
   const uint32_t b_lo_off = b_off + P.b_plane_bytes;
   uint8_t *ring = smem;
-  uint8_t *staging = ring + (size_t)S * P.stage_bytes;                    // 2 x 16 KB, 1024-aligned (stage_bytes % 1024 == 0)
-  float *bias_s = reinterpret_cast<float *>(staging + 2 * kStagingBytes);
-  uint64_t *bars = reinterpret_cast<uint64_t *>(bias_s + ((P.N + 3) & ~3));
+  uint8_t *staging = ring + (size_t)S * P.stage_bytes;   // [4 warps][slabs] x 4 KB, 1024-aligned (stage_bytes % 1024 == 0)
+  float *bias_s = reinterpret_cast<float *>(staging + (size_t)kEpiWarps * P.slabs * kSlabBytes);   // t[Npad] (bias, or beta.W^T + bias)
+  float *svec_s = bias_s + P.n_pad;                                         // s[Npad] (LayerNorm fold); Npad covers every chunk, zero past N
+  float2 *stats = reinterpret_cast<float2 *>(svec_s + (kLn ? P.n_pad : 0));   // [kStatSlots][128]
+  uint64_t *bars = reinterpret_cast<uint64_t *>(stats + (kLn ? kStatSlots * kTileM : 0));
   uint64_t *full = bars, *empty = full + kMaxStages, *split = empty + kMaxStages, *acc_full = split + kMaxStages,
            *acc_empty = acc_full + 2;
   uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(acc_empty + 2);
 
-  for (int i = threadIdx.x; i < P.N; i += kThreads) bias_s[i] = P.bias ? __ldg(P.bias + i) : 0.f;
+  for (int i = threadIdx.x; i < P.n_pad; i += kThreads) {
+    bias_s[i] = (P.bias && i < P.N) ? __ldg(P.bias + i) : 0.f;
+    if (kLn) svec_s[i] = i < P.N ? __ldg(P.svec + i) : 0.f;
+  }
   if (threadIdx.x == 0) {
     for (uint32_t s = 0; s < S; ++s) {
       mbar_init(&full[s], 1);    // the producer's arrive.expect_tx (+ TMA transaction bytes)
@@ -187,7 +233,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tf32_kernel(const __grid_con
     }
     for (int b = 0; b < 2; ++b) {
       mbar_init(&acc_full[b], 1);
-      mbar_init(&acc_empty[b], 4);  // one arrival per epilogue warp
+      mbar_init(&acc_empty[b], kEpiWarps);  // one arrival per epilogue warp
     }
     mbar_fence_init();
     for (int s = 0; s < P.n_src; ++s) tma_prefetch_desc(&P.a_map[s]);
@@ -220,7 +266,8 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tf32_kernel(const __grid_con
               mbar_wait(&empty[st], ph);
               const uint32_t base = smem_u32(ring) + st * P.stage_bytes;
               mbar_arrive_expect_tx(&full[st], tx_bytes);
-              tma_load_4d(base, &P.a_map[s], &full[st], cb * kBlockK, x0 + kx, y0 + ky, b);
+              if (P.debug & 8) asm volatile("mbarrier.complete_tx.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(&full[st])), "r"(kAStageBytes) : "memory");
+              else tma_load_4d(base, &P.a_map[s], &full[st], cb * kBlockK, x0 + kx, y0 + ky, b);
               tma_load_2d(base + b_off, &P.b_map[0], &full[st], kb * kBlockK, n0);
               if (kPrecise) tma_load_2d(base + b_lo_off, &P.b_map[1], &full[st], kb * kBlockK, n0);
               if (++st == S) st = 0, ph ^= 1u;
@@ -240,7 +287,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tf32_kernel(const __grid_con
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + (uint32_t)(buf * P.acc_stride);
         for (int kb = 0; kb < P.k_blocks; ++kb) {
-          mbar_wait(kPrecise ? &split[st] : &full[st], ph);
+          mbar_wait(kAPass ? &split[st] : &full[st], ph);   // (the A pass has waited for the stage's TMA bytes)
           tc_fence_after();
           const uint32_t base = smem_u32(ring) + st * P.stage_bytes;
           const uint64_t da = umma_desc_sw128(base), db = umma_desc_sw128(base + b_off);
@@ -259,64 +306,79 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tf32_kernel(const __grid_con
         umma_commit(&acc_full[buf]);
       }
     }
-  } else if (warp >= kFirstEpiWarp && warp < kFirstEpiWarp + 4) {
+  } else if (warp >= kFirstEpiWarp && warp < kFirstEpiWarp + kEpiWarps) {
     // =========================== epilogue ===========================
     const int quad = warp & 3;
     const int row = quad * 32 + lane;  // TMEM lane == tile row == pixel (row / TW, row % TW) of the tile box
-    const int et = threadIdx.x - kFirstEpiWarp * 32;  // 0..127
+    // Each epilogue warp stores its own 32 rows: a private ring of `slabs` staging slabs and its own bulk-store groups
+    // (lane 0), so `slabs - 1` TMA stores per warp stay in flight and no CTA-wide barrier sits in the chunk loop.  The
+    // warp's rows are the sub-box (min(TW, 32) x 32 / min(TW, 32)) of the tile at (row0 % TW, row0 / TW).
     const int cw = P.cw;
     const uint32_t row_bytes = (uint32_t)cw * 4u;
     const uint32_t swz = cw == 32 ? (uint32_t)(row & 7) : (uint32_t)((row >> 1) & 3);
+    const int ew = warp - kFirstEpiWarp, half = ew >> 2;   // the two warps of a quadrant take even / odd chunks
+    const uint32_t slab0 = smem_u32(staging) + (uint32_t)(ew * P.slabs) * kSlabBytes;
+    const int sub_x = (quad * 32) % P.TW, sub_y = (quad * 32) / P.TW;
     int it = 0;
-    uint32_t chunk_no = 0;  // running chunk counter -> staging buffer parity
+    uint32_t slab = 0;  // running slab index of this warp
     for (int tile = blockIdx.x; tile < P.total_tiles; tile += gridDim.x, ++it) {
       const int buf = it & 1;
       const int mt = tile / P.n_tiles, nt = tile - mt * P.n_tiles;
       const int b = mt / P.tiles_per_img, rem = mt - b * P.tiles_per_img;
       const int ty = rem / P.tiles_x, tx = rem - ty * P.tiles_x;
       const int ox0 = tx * P.TW, oy0 = ty * P.TH;
+      const float *res_pix = nullptr;
+      if (P.act >= 2) {  // y_hat_slice + 0.5 * tanh(lrp) / shortcut + (.): the residual is the pixel's own channels
+        const int oy = oy0 + row / P.TW, ox = ox0 + row % P.TW;
+        if (oy < P.Ho && ox < P.Wo) res_pix = P.residual + ((int64_t)(b * P.Ho + oy) * P.Wo + ox) * P.res_ld;
+      }
       mbar_wait_relaxed(&acc_full[buf], ((uint32_t)it >> 1) & 1u);
       tc_fence_after();
+      float mean = 0.f, rstd = 1.f;
+      if (kLn) {   // written by the A pass before it published the tile's last k-block
+        const float2 st2 = stats[(it % kStatSlots) * kTileM + row];
+        mean = st2.x, rstd = st2.y;
+      }
       const uint32_t t_acc = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(buf * P.acc_stride);
       const int n_chunks = (P.n_tile + cw - 1) / cw;
-      for (int c = 0; c < n_chunks; ++c, ++chunk_no) {
+      if (half >= n_chunks) {  // no chunk for this warp in this tile: it still has to release the accumulator
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&acc_empty[buf]);
+      }
+      for (int c = half; c < n_chunks; c += 2) {
         const int col0 = c * cw;            // column inside the tile
         const int n0 = nt * P.n_tile + col0;  // packed output column
         uint32_t r[32];
         tmem_ld32(t_acc + (uint32_t)col0, (cw == 32 && col0 + 16 < P.n_tile) ? 1u : 0u, r);
-        if (c == n_chunks - 1) {  // last TMEM read of this tile: hand the accumulator back to the MMA warp
+        if (c + 2 >= n_chunks) {  // last TMEM read of this warp for this tile: hand the accumulator back to the MMA warp
           tc_fence_before();
           __syncwarp();
           if (lane == 0) mbar_arrive(&acc_empty[buf]);
         }
-        const int valid = min(cw, P.n_tile - col0);  // 16 or 32 (n_tile % 16 == 0)
         float v[32];
-        const float *res_row = nullptr;
-        if (P.act == 2) {  // y_hat_slice + 0.5 * tanh(lrp): the residual is the pixel's own 32 channels (read before the store)
-          const int oy = oy0 + row / P.TW, ox = ox0 + row % P.TW;
-          if (oy < P.Ho && ox < P.Wo) res_row = P.residual + ((int64_t)(b * P.Ho + oy) * P.Wo + ox) * P.res_ld + n0;
-        }
+        const float *res_row = res_pix ? res_pix + n0 : nullptr;
+        const int res_cols = P.N - n0;      // residual columns that exist (guards the row end of the last chunk)
+        if (P.debug & 4) {
 #pragma unroll
-        for (int j = 0; j < 32; j += 4) {
-          float4 rv = make_float4(0.f, 0.f, 0.f, 0.f);
-          if (res_row && j < valid && n0 + j < P.N) rv = *reinterpret_cast<const float4 *>(res_row + j);
-          const float rr[4] = {rv.x, rv.y, rv.z, rv.w};
-#pragma unroll
-          for (int q = 0; q < 4; ++q) {
-            float a = __uint_as_float(r[j + q]);
-            if (j + q < valid && n0 + j + q < P.N) {
-              a += bias_s[n0 + j + q];
-              if (P.act == 1) a = gelu_erf(a);
-              else if (P.act == 2) a = rr[q] + 0.5f * tanhf(a);
-            } else {
-              a = 0.f;
-            }
-            v[j + q] = a;
+          for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
+        } else {
+          switch (P.act) {
+            case 1: epi_math<kLn, 1>(r, v, bias_s + n0, svec_s + n0, mean, rstd, nullptr, 0); break;
+            case 2: epi_math<kLn, 2>(r, v, bias_s + n0, svec_s + n0, mean, rstd, res_row, res_cols); break;
+            case 3: epi_math<kLn, 3>(r, v, bias_s + n0, svec_s + n0, mean, rstd, res_row, res_cols); break;
+            default: epi_math<kLn, 0>(r, v, bias_s + n0, svec_s + n0, mean, rstd, nullptr, 0); break;
           }
         }
-        named_bar_sync(1, 128);  // the store that last read this staging buffer has finished reading (thread 0 waited)
-        const uint32_t stg = smem_u32(staging) + (chunk_no & 1u) * kStagingBytes + (uint32_t)row * row_bytes;
-        if (cw == 32) {
+        if (lane == 0) {  // the store that last read this slab (`slabs` chunks of this warp ago) has finished reading it
+          if (P.slabs == 1) bulk_wait_read<0>(); else if (P.slabs == 2) bulk_wait_read<1>();
+          else if (P.slabs == 3) bulk_wait_read<2>(); else bulk_wait_read<3>();
+        }
+        __syncwarp();
+        const uint32_t src = slab0 + slab * kSlabBytes;
+        const uint32_t stg = src + (uint32_t)lane * row_bytes;
+        if (P.debug & 2) {
+          if (v[0] == 1.2345e-30f) sts128(stg, make_float4(v[1], v[2], v[3], v[4]));   // keep v alive
+        } else if (cw == 32) {
 #pragma unroll
           for (int j = 0; j < 8; ++j)
             sts128(stg + (((uint32_t)j ^ swz) << 4), make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]));
@@ -326,31 +388,36 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tf32_kernel(const __grid_con
             sts128(stg + (((uint32_t)j ^ swz) << 4), make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]));
         }
         fence_proxy_async_smem();
-        named_bar_sync(2, 128);
-        if (et == 0) {
-          const uint32_t src = smem_u32(staging) + (chunk_no & 1u) * kStagingBytes;
-          if (n0 >= P.N) {
+        __syncwarp();
+        if (lane == 0) {
+          if (n0 >= P.N || (P.debug & 1)) {
             // chunk entirely past the last output channel (overhanging last column tile): nothing to store
           } else if (P.shuffle_cout) {
             const int g = n0 / P.shuffle_cout, c0 = n0 - g * P.shuffle_cout;  // sub-pixel (i, j) = (g >> 1, g & 1)
-            tma_store_4d(&P.y_map[g], src, c0, ox0, oy0, b);
+            tma_store_4d(&P.y_map[g], src, c0, ox0 + sub_x, oy0 + sub_y, b);
           } else {
-            tma_store_4d(&P.y_map[0], src, n0, ox0, oy0, b);
+            tma_store_4d(&P.y_map[0], src, n0, ox0 + sub_x, oy0 + sub_y, b);
           }
-          bulk_commit();
-          bulk_wait_read1();  // the previous chunk's store has finished reading the other staging buffer
+          bulk_commit();   // (an empty group when nothing was stored: keeps the slab <-> group bookkeeping uniform)
         }
+        if (++slab == (uint32_t)P.slabs) slab = 0;
       }
     }
-    if (et == 0) bulk_wait0();
-  } else if (kPrecise && warp >= kFirstSplitWarp) {
-    // =========================== hi / lo splitter (3xTF32) ===========================
-    // Element-wise on the landed A stage (layout-agnostic): hi = upper 19 bits written back in place, so the tensor core
-    // reads an exact TF32 value whatever its own rounding of fp32 words is; lo = x - hi (exact in fp32) into the lo plane,
-    // of which the tensor core reads the upper 11 significant bits: x = hi + lo to 2^-22 relative.
+    if (lane == 0) bulk_wait0();
+  } else if (kAPass && warp >= kFirstSplitWarp) {
+    // =========================== A pass: hi / lo split (3xTF32) and LayerNorm row statistics ===========================
+    // Element-wise on the landed A stage.  3xTF32: the raw fp32 stage IS the hi operand (the tensor core reads the upper 19
+    // bits of each word: hi = trunc_tf32(x), checked on B200 against an explicit rewrite); lo = x - hi (exact in fp32) goes
+    // into the lo plane, of which the tensor core again reads the upper 11 significant bits: x = hi + lo to 2^-22 relative.  LayerNorm: shifted one-pass
+    // sum / sum of squares of every row while it streams through (thread t owns the 16-byte position t % 8 of rows
+    // t / 8 + 16 i; the swizzle only permutes chunks inside a row), reduced over the row's 8 lanes after the last k-block.
     const int st_thread = threadIdx.x - kFirstSplitWarp * 32;  // 0..127
+    const int grp_lane0 = lane & ~7;                           // first lane of this thread's 8-lane row group
+    const int first_pos = (st_thread >> 3) & 7;                // swizzled position of the row's logical chunk 0 (row & 7)
     uint32_t st = 0, ph = 0;
-    for (int tile = blockIdx.x; tile < P.total_tiles; tile += gridDim.x) {
+    int it = 0;
+    float shift0[8], sum[8], sq[8];
+    for (int tile = blockIdx.x; tile < P.total_tiles; tile += gridDim.x, ++it) {
       for (int kb = 0; kb < P.k_blocks; ++kb) {
         mbar_wait(&full[st], ph);
         const uint32_t base = smem_u32(ring) + st * P.stage_bytes + (uint32_t)st_thread * 16u;
@@ -358,11 +425,45 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tf32_kernel(const __grid_con
         for (int i = 0; i < 8; ++i) {
           const uint32_t a = base + (uint32_t)i * 2048u;
           const float4 x = lds128(a);
-          const float4 hi = make_float4(trunc_tf32(x.x), trunc_tf32(x.y), trunc_tf32(x.z), trunc_tf32(x.w));
-          sts128(a, hi);
-          sts128(a + a_lo_off, make_float4(x.x - hi.x, x.y - hi.y, x.z - hi.z, x.w - hi.w));
+          if (kLn) {
+            if (kb == 0) {  // shift by the row's first element: keeps the one-pass variance well conditioned
+              shift0[i] = __shfl_sync(0xffffffffu, x.x, grp_lane0 + first_pos);
+              sum[i] = 0.f, sq[i] = 0.f;
+            }
+            const float dx = x.x - shift0[i], dy = x.y - shift0[i], dz = x.z - shift0[i], dw = x.w - shift0[i];
+            sum[i] += (dx + dy) + (dz + dw);
+            sq[i] += (dx * dx + dy * dy) + (dz * dz + dw * dw);
+          }
+          if (kPrecise) {
+            const float4 hi = make_float4(trunc_tf32(x.x), trunc_tf32(x.y), trunc_tf32(x.z), trunc_tf32(x.w));
+            if (P.debug & 16) sts128(a, hi);   // (bring-up: rewrite hi explicitly.  Measured on B200: results are identical either
+                                              // way -- tcgen05.mma kind::tf32 reads the upper 19 bits of an fp32 word, i.e. truncates)
+            sts128(a + a_lo_off, make_float4(x.x - hi.x, x.y - hi.y, x.z - hi.z, x.w - hi.w));
+          }
         }
-        fence_proxy_async_smem();
+        if (kLn && kb == P.k_blocks - 1) {
+          // Channels past K in the last k-block are TMA zero fill: each contributed (0 - shift)^n to the sums; remove them.
+          const float inv_k = 1.0f / (float)P.ln_k;
+          const float pad = (float)(P.k_blocks * kBlockK - P.ln_k);
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            float s1 = sum[i], s2 = sq[i];
+            s1 += __shfl_xor_sync(0xffffffffu, s1, 1);
+            s2 += __shfl_xor_sync(0xffffffffu, s2, 1);
+            s1 += __shfl_xor_sync(0xffffffffu, s1, 2);
+            s2 += __shfl_xor_sync(0xffffffffu, s2, 2);
+            s1 += __shfl_xor_sync(0xffffffffu, s1, 4);
+            s2 += __shfl_xor_sync(0xffffffffu, s2, 4);
+            s1 += pad * shift0[i];
+            s2 -= pad * shift0[i] * shift0[i];
+            if ((lane & 7) == 0) {
+              const float md = s1 * inv_k;
+              const float var = fmaxf(s2 * inv_k - md * md, 0.f);
+              stats[(it % kStatSlots) * kTileM + (st_thread >> 3) + 16 * i] = make_float2(shift0[i] + md, rsqrtf(var + P.ln_eps));
+            }
+          }
+        }
+        if (kPrecise) fence_proxy_async_smem();
         __syncwarp();
         if (lane == 0) mbar_arrive(&split[st]);
         if (++st == S) st = 0, ph ^= 1u;
@@ -379,16 +480,33 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tf32_kernel(const __grid_con
 }
 
 // ---------------------------------------------------------------------------- weight packing
-// out: [planes][N][Kp] + bias'[N];  Kp = taps * Cp, Cp = sum_s ceil32(C_s).  Column n' of the packed matrix is conv output
+// out: [planes][N][Kp]  t[N]  s[N];  Kp = taps * Cp, Cp = sum_s ceil32(C_s).  Column n' of the packed matrix is output
 // channel n: plain n' = n; pixel shuffle n' = g * Cout + c  <->  n = 4 c + g  (PixelShuffle(2): f = 4c + 2i + j, g = 2i + j).
+// With a LayerNorm in front (Linear layers, ksize 1): the image holds gamma o W, and
+//   LN(x) . W^T + bias = rstd * ( x . (gamma o W)^T - mean * s ) + t,   s = sum_k (gamma o W)[n][k],  t = beta . W^T + bias
+// so the GEMM runs on the raw rows and the epilogue applies the row statistics.  Rows n' < scale_cols (the q third of a qkv
+// Linear) are multiplied by row_scale (q * d^-1/2, stf.py:99; exact for d = 16) in W, s and t alike.
 struct PackParams {
   const float *w;      // (N, Ctot, k, k) contiguous
   const float *bias;   // N or nullptr
+  const float *gamma, *beta;   // Ctot each, or nullptr
   float *out;
   int N, Ctot, taps, Cp, Kp, n_src;
   int src_c[kMaxSrc], src_cp[kMaxSrc];
   int shuffle_cout, planes;
+  int scale_cols;
+  float row_scale;
 };
+
+__device__ __forceinline__ int pack_src_channel(const PackParams &P, int q) {
+  int cbase = 0;
+  for (int s = 0; s < P.n_src; ++s) {
+    if (q < P.src_cp[s]) return q < P.src_c[s] ? cbase + q : -1;
+    q -= P.src_cp[s];
+    cbase += P.src_c[s];
+  }
+  return -1;
+}
 
 __global__ void pack_conv_kernel(const PackParams P) {
   const int64_t total = (int64_t)P.N * P.Kp;
@@ -396,25 +514,42 @@ __global__ void pack_conv_kernel(const PackParams P) {
     const int np = (int)(i / P.Kp), kp = (int)(i - (int64_t)np * P.Kp);
     const int n = P.shuffle_cout ? 4 * (np % P.shuffle_cout) + np / P.shuffle_cout : np;
     const int tap = kp / P.Cp;
-    int q = kp - tap * P.Cp, c = -1, cbase = 0;
-    for (int s = 0; s < P.n_src; ++s) {
-      if (q < P.src_cp[s]) {
-        c = q < P.src_c[s] ? cbase + q : -1;
-        break;
-      }
-      q -= P.src_cp[s];
-      cbase += P.src_c[s];
-    }
-    const float v = c >= 0 ? P.w[((int64_t)n * P.Ctot + c) * P.taps + tap] : 0.f;
+    const int c = pack_src_channel(P, kp - tap * P.Cp);
+    float v = c >= 0 ? P.w[((int64_t)n * P.Ctot + c) * P.taps + tap] : 0.f;
+    if (c >= 0 && P.gamma) v *= P.gamma[c];
+    if (np < P.scale_cols) v *= P.row_scale;
     const float hi = to_tf32(v);
     P.out[i] = hi;
     if (P.planes == 2) P.out[total + i] = to_tf32(v - hi);
   }
-  if (blockIdx.x == 0)
-    for (int np = threadIdx.x; np < P.N; np += blockDim.x) {
-      const int n = P.shuffle_cout ? 4 * (np % P.shuffle_cout) + np / P.shuffle_cout : np;
-      P.out[(int64_t)P.planes * total + np] = P.bias ? P.bias[n] : 0.f;
+}
+
+// t[n'] and s[n'] (one block per output column, fixed-order tree reduction: deterministic); runs after pack_conv_kernel.
+__global__ void __launch_bounds__(128) pack_vectors_kernel(const PackParams P) {
+  __shared__ float red_s[128], red_t[128];
+  const int np = blockIdx.x;
+  const int n = P.shuffle_cout ? 4 * (np % P.shuffle_cout) + np / P.shuffle_cout : np;
+  const int64_t total = (int64_t)P.N * P.Kp;
+  float ps = 0.f, pt = 0.f;
+  if (P.gamma) {
+    for (int kp = threadIdx.x; kp < P.Kp; kp += 128) {
+      ps += P.out[(int64_t)np * P.Kp + kp];
+      if (P.planes == 2) ps += P.out[total + (int64_t)np * P.Kp + kp];
     }
+    for (int c = threadIdx.x; c < P.Ctot; c += 128) pt += P.beta[c] * P.w[((int64_t)n * P.Ctot + c) * P.taps];   // (taps == 1)
+  }
+  red_s[threadIdx.x] = ps, red_t[threadIdx.x] = pt;
+  __syncthreads();
+  for (int o = 64; o > 0; o >>= 1) {
+    if ((int)threadIdx.x < o) red_s[threadIdx.x] += red_s[threadIdx.x + o], red_t[threadIdx.x] += red_t[threadIdx.x + o];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) {
+    float t = red_t[0] + (P.bias ? P.bias[n] : 0.f);
+    if (np < P.scale_cols) t *= P.row_scale;
+    P.out[(int64_t)P.planes * total + np] = t;
+    P.out[(int64_t)P.planes * total + P.N + np] = red_s[0];
+  }
 }
 
 // ---------------------------------------------------------------------------- host side
@@ -447,6 +582,11 @@ Geometry geometry(int H, int W, int ksize, int stride) {
   const int pad = ksize / 2;
   g.Ho = (H + 2 * pad - ksize) / stride + 1;
   g.Wo = (W + 2 * pad - ksize) / stride + 1;
+  if (g.Ho == 1 && g.Wo > 16) {  // token-major rows (a Linear layer = 1x1 "convolution" over an H = 1 image): 128 x 1 tiles
+    g.TW = kTileM, g.TH = 1;
+    g.tiles_x = (g.Wo + kTileM - 1) / kTileM, g.tiles_y = 1;
+    return g;
+  }
   int best = 1 << 30;
   g.TW = 16, g.TH = 8;
   const int cand[3] = {16, 32, 8};  // preference order on ties
@@ -467,21 +607,34 @@ Geometry geometry(int H, int W, int ksize, int stride) {
 // (12 pixel tiles for one 768x512 image) spreads over the SMs as narrow column tiles, while a large batch takes the widest
 // tile (least A re-reads).  The choice never changes a result bit: every output element is the same fixed-order K loop.
 int conv_n_tile(int N, int precise, int gran, int m_tiles, int k_blocks) {
-  const int cap = precise ? 128 : 256;
   if (N <= 0 || N % 16) return STF_E_SHAPE;
   if (gran < 32) gran = 32;
   int best = -1;
   double best_t = 0;
-  for (int nt = gran; nt <= cap + gran - 1; nt += gran) {
+  for (int nt = gran; nt <= 256 + gran - 1; nt += gran) {
     int w = nt;
     if (w >= N) w = N;          // single tile: N itself (any multiple of 16)
-    if (w > cap) break;
+    if (w > 256) break;
+    // the operand ring must hold >= 2 stages (>= 3 for K loops long enough to need the latency hiding) next to the
+    // staging slabs and the epilogue vectors (3xTF32 stages carry a lo plane of both operands)
+    const size_t stage = (size_t)(precise ? 2 : 1) * (16384 + 128 * (size_t)w);
+    const size_t avail = 227 * 1024 - (size_t)kEpiWarps * kSlabBytes - 24 * 1024;
+    const int stages = (int)(avail / stage);
+    if (stages < 2) {
+      if (w == N) break;
+      continue;
+    }
     const int n_tiles = (N + w - 1) / w;
     const long long tiles = (long long)m_tiles * n_tiles;
     const long long waves = (tiles + kNumSMs - 1) / kNumSMs;
-    const double bytes = (precise ? 2.0 : 1.0) * (16384.0 + 128.0 * w);
-    const double mma = (precise ? 3.0 : 1.0) * 2.0 * w;
-    const double per_kb = bytes / 53.0 > mma ? bytes / 53.0 : mma;
+    const double bytes = (precise ? 2.0 : 1.0) * (16384.0 + 128.0 * w);   // L2 -> shared memory per k-block
+    const double mma = (precise ? 3.0 : 1.0) * 2.0 * w;                    // tensor-pipe cycles per k-block
+    // shared-memory port (128 B/clk): TMA fill + operand reads of every MMA (4 KB of A + 32 B per column, 4 k-steps,
+    // x3 in the 3xTF32 mode) + the A pass (read the stage, write hi and lo)
+    const double port = (bytes + (precise ? 12.0 : 4.0) * (4096.0 + 32.0 * w) + (precise ? 49152.0 : 0.0)) / 128.0;
+    double per_kb = bytes / 53.0 > mma ? bytes / 53.0 : mma;
+    if (port > per_kb) per_kb = port;
+    if (stages == 2) per_kb *= 1.15;    // two stages hide less of the L2 latency
     const double t = (double)waves * ((double)k_blocks * per_kb + 12.0 * w + 1500.0);
     if (best < 0 || t < best_t * 0.999 || (t <= best_t * 1.001 && w > best)) best = w, best_t = t;
     if (w == N) break;
@@ -506,24 +659,33 @@ int packed_geometry(const stf_conv_args *a, int *Cp, int *Kp) {
 extern "C" int64_t stf_packed_conv_floats(const stf_conv_args *a) {
   int Cp, Kp;
   if (!a || packed_geometry(a, &Cp, &Kp) != STF_OK) return STF_E_ARG;
-  return (int64_t)(a->precision == STF_PREC_FP32 ? 2 : 1) * a->N * Kp + a->N;
+  return (int64_t)(a->precision == STF_PREC_FP32 ? 2 : 1) * a->N * Kp + 2 * (int64_t)a->N;
 }
 
-extern "C" int stf_pack_conv(const stf_conv_args *a, const float *weight, const float *bias, float *packed, void *stream) {
+extern "C" int stf_pack_conv(const stf_conv_args *a, const float *weight, const float *bias, const float *ln_gamma,
+                             const float *ln_beta, int scale_cols, float row_scale, float *packed, void *stream) {
   if (!a || !weight || !packed) return STF_E_ARG;
   if (!aligned16(packed)) return STF_E_ALIGN;
+  if ((ln_gamma == nullptr) != (ln_beta == nullptr)) return STF_E_ARG;
+  if (ln_gamma && (a->ksize != 1 || a->n_src != 1 || !a->has_ln)) return STF_E_ARG;
+  if (!ln_gamma && a->has_ln) return STF_E_ARG;
   PackParams P{};
   int rc = packed_geometry(a, &P.Cp, &P.Kp);
   if (rc != STF_OK) return rc;
   if (a->pixel_shuffle != 0 && (a->pixel_shuffle != 2 || a->N % 4)) return STF_E_SHAPE;
-  P.w = weight, P.bias = bias, P.out = packed, P.N = a->N, P.taps = a->ksize * a->ksize, P.n_src = a->n_src;
+  P.w = weight, P.bias = bias, P.gamma = ln_gamma, P.beta = ln_beta, P.out = packed, P.N = a->N;
+  P.taps = a->ksize * a->ksize, P.n_src = a->n_src;
   P.Ctot = 0;
   for (int s = 0; s < a->n_src; ++s) P.src_c[s] = a->src_channels[s], P.src_cp[s] = ceil32(a->src_channels[s]), P.Ctot += a->src_channels[s];
   P.shuffle_cout = a->pixel_shuffle ? a->N / 4 : 0;
   P.planes = a->precision == STF_PREC_FP32 ? 2 : 1;
+  P.scale_cols = scale_cols, P.row_scale = row_scale;
   const int64_t total = (int64_t)P.N * P.Kp;
   const int blocks = (int)((total + 255) / 256 < 2048 ? (total + 255) / 256 : 2048);
   pack_conv_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(P);
+  rc = check_launch();
+  if (rc != STF_OK) return rc;
+  pack_vectors_kernel<<<P.N, 128, 0, (cudaStream_t)stream>>>(P);
   return check_launch();
 }
 
@@ -578,6 +740,9 @@ extern "C" int stf_conv2d(const stf_conv_args *a, void *stream) {
       return STF_E_SHAPE;
   }
   P.bias = a->w_packed + (size_t)(1 + precise) * a->N * Kp;
+  P.svec = P.bias + a->N;
+  P.has_ln = a->has_ln ? 1 : 0, P.ln_eps = a->ln_eps, P.ln_k = a->src_channels[0];
+  if (P.has_ln && (a->ksize != 1 || a->n_src != 1)) return STF_E_ARG;
   P.shuffle_cout = shuffle_cout;
   P.cw = cw;
   const int n_maps = P.shuffle_cout ? 4 : 1;
@@ -594,7 +759,8 @@ extern "C" int stf_conv2d(const stf_conv_args *a, void *stream) {
       gdim[0] = (cuuint64_t)a->N, gdim[1] = (cuuint64_t)g.Wo, gdim[2] = (cuuint64_t)g.Ho, gdim[3] = (cuuint64_t)a->batch;
       gstr[0] = (cuuint64_t)a->ldy * 4, gstr[1] = (cuuint64_t)g.Wo * a->ldy * 4, gstr[2] = (cuuint64_t)g.Ho * g.Wo * a->ldy * 4;
     }
-    const cuuint32_t box[4] = {(cuuint32_t)P.cw, (cuuint32_t)g.TW, (cuuint32_t)g.TH, 1};
+    const int bw = g.TW < 32 ? g.TW : 32;   // one epilogue warp's 32 rows of the tile
+    const cuuint32_t box[4] = {(cuuint32_t)P.cw, (cuuint32_t)bw, (cuuint32_t)(32 / bw), 1};
     const cuuint32_t estr[4] = {1, 1, 1, 1};
     if (enc(&P.y_map[m], CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, base, gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
             P.cw == 32 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_NONE,
@@ -607,7 +773,8 @@ extern "C" int stf_conv2d(const stf_conv_args *a, void *stream) {
   P.m_tiles = P.tiles_per_img * a->batch;
   P.total_tiles = P.m_tiles * P.n_tiles;
   P.act = a->act;
-  if (a->act == 2) {
+  if (a->act < 0 || a->act > 3) return STF_E_ARG;
+  if (a->act >= 2) {
     if (!a->residual || a->pixel_shuffle || a->res_ld % 4 || !aligned16(a->residual)) return STF_E_ARG;
     P.residual = a->residual, P.res_ld = a->res_ld;
   }
@@ -619,18 +786,28 @@ extern "C" int stf_conv2d(const stf_conv_args *a, void *stream) {
   P.tmem_cols = cols;
   P.b_plane_bytes = (uint32_t)n_tile * 128u;
   P.stage_bytes = (uint32_t)(1 + precise) * (kAStageBytes + P.b_plane_bytes);
-  const size_t fixed = 1024 /*alignment slack*/ + 2 * kStagingBytes + (size_t)((a->N + 3) & ~3) * 4 + (3 * kMaxStages + 4) * 8 + 16;
+  // shared memory: operand ring first (as many stages as fit next to the minimum of 2 staging slabs per epilogue warp; the
+  // ring runs across tile boundaries, so short K loops prefetch the next tiles), what is left goes to more staging slabs
+  P.n_pad = ((P.n_tiles * n_tile + 31) & ~31) + 32;
+  const size_t small = 1024 /*alignment slack*/ + (size_t)P.n_pad * 4 * (P.has_ln ? 2 : 1) +
+                       (P.has_ln ? (size_t)kStatSlots * kTileM * 8 : 0) + (3 * kMaxStages + 4) * 8 + 16;
   const size_t cap = 227 * 1024;
-  int stages = (int)((cap - fixed) / P.stage_bytes);
+  int stages = (int)((cap - small - kEpiWarps * 1 * kSlabBytes) / P.stage_bytes);
   if (stages > kMaxStages) stages = kMaxStages;
-  if (stages > P.k_blocks) stages = P.k_blocks < 2 ? 2 : P.k_blocks;
   if (stages < 2) return STF_E_SHAPE;
   P.stages = stages;
+  int slabs = (int)((cap - small - (size_t)stages * P.stage_bytes) / (kEpiWarps * kSlabBytes));
+  if (slabs > kMaxSlabs) slabs = kMaxSlabs;
+  P.slabs = slabs;
+  static const int dbg = getenv("STF_B200_CONV_DEBUG") ? atoi(getenv("STF_B200_CONV_DEBUG")) : 0;
+  P.debug = dbg;
+  const size_t fixed = small + (size_t)kEpiWarps * slabs * kSlabBytes;
   const size_t smem = fixed + (size_t)stages * P.stage_bytes;
   const int grid = P.total_tiles < kNumSMs ? P.total_tiles : kNumSMs;
-  auto kern = precise ? conv_tf32_kernel<1> : conv_tf32_kernel<0>;
-  static std::once_flag attr_once[2];
-  std::call_once(attr_once[precise], [&] {
+  auto kern = precise ? (P.has_ln ? conv_tf32_kernel<1, 1> : conv_tf32_kernel<1, 0>)
+                      : (P.has_ln ? conv_tf32_kernel<0, 1> : conv_tf32_kernel<0, 0>);
+  static std::once_flag attr_once[4];
+  std::call_once(attr_once[precise * 2 + P.has_ln], [&] {
     (void)cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cap);
   });
   kern<<<grid, kThreads, smem, (cudaStream_t)stream>>>(P);

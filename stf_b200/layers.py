@@ -64,6 +64,17 @@ class _PackCache:
             self._key = key
         return self._val
 
+    def get_gemm(self, weight, bias=None, norm=None, row_scale=None):
+        """The same Linear (+ LayerNorm in front) packed for the TMA / tcgen05 GEMM engine (ops.gemm / stf_conv2d)."""
+        key = tuple((t.data_ptr(), t._version) for t in
+                    (weight, bias, None if norm is None else norm.weight, None if norm is None else norm.bias)
+                    if t is not None) + (ops.precision_code(), row_scale)
+        if key != getattr(self, "_key_g", None):
+            ln = None if norm is None else (norm.weight, norm.bias, norm.eps)
+            self._val_g = ops.PackedConv(weight, bias, prec=ops.precision_code(), ln=ln, row_scale=row_scale)
+            self._key_g = key
+        return self._val_g
+
     def get_t(self, weight):
         """Packed W^T (no bias, no LayerNorm): stf_linear on it computes dY . W, the input gradient of the Linear."""
         key = (weight.data_ptr(), weight._version, ops.precision_code())
@@ -106,6 +117,12 @@ class Mlp(nn.Module):
         _require_eval(self)
         shape = x.shape
         x2 = x.reshape(-1, shape[-1])
+        if ops.GEMM_ENGINE:   # both Linears on the TMA-fed GEMM engine (stf_conv2d, ksize 1): LN2 folded, GELU / shortcut fused
+            h = ops.gemm(x2, self._p1.get_gemm(self.fc1.weight, self.fc1.bias, norm), act="gelu")
+            res = None if residual is None else residual.reshape(-1, residual.shape[-1])
+            y = ops.gemm(h, self._p2.get_gemm(self.fc2.weight, self.fc2.bias), act=False if res is None else "residual",
+                         residual=res)
+            return y.reshape(*shape[:-1], y.shape[-1])
         h = ops.linear(x2, self._p1.get(self.fc1.weight, self.fc1.bias, norm), epilogue=_C.EPI_GELU)
         # h comes out of the GELU epilogue already rounded to TF32: fc2 skips its rounding pass
         if residual is None:
@@ -142,6 +159,17 @@ class WindowAttention(nn.Module):
         nn.init.trunc_normal_(self.relative_position_bias_table, std=0.02)
         self.softmax = nn.Softmax(dim=-1)
         self._pq, self._pp = _PackCache(), _PackCache()
+
+    def pad_qkv_row(self):
+        """qkv row of a pad token: zero after norm1 (stf.py:155-162) -> qkv = bias, q third scaled (stf.py:99)."""
+        b = self.qkv.bias
+        key = None if b is None else (b.data_ptr(), b._version)
+        if getattr(self, "_pad_key", 0) != key or self._pad_row.device != self.qkv.weight.device:
+            row = torch.zeros(3 * self.dim, dtype=torch.float32, device=self.qkv.weight.device) if b is None \
+                else b.detach().clone().float()
+            row[: self.dim] *= self.scale
+            self._pad_row, self._pad_key = row, key
+        return self._pad_row
 
     def packed_qkv(self, norm=None):
         return self._pq.get(self.qkv.weight, self.qkv.bias, norm)
@@ -195,6 +223,18 @@ class SwinTransformerBlock(nn.Module):
         x2 = x.reshape(B * L, C)
         if _grad_mode(self):
             return self._forward_train(x2, geom).reshape(B, L, C)
+        a = self.attn
+        if ops.GEMM_ENGINE and ws == 4 and C // self.num_heads == 16:
+            # Dense token-order GEMMs on the TMA-fed engine; partition / shift / pad / reverse live in the attention kernel:
+            #   qkv  = LN1(x) . Wqkv^T + b (q third pre-scaled)          -> stf_conv2d (ksize 1, LayerNorm folded)
+            #   o    = softmax(q k^T + bias + mask) v per shifted window -> stf_window_attention_tokens (tensor-core tiles)
+            #   x1   = x + o . Wproj^T + b                               -> stf_conv2d (residual epilogue)
+            qkv = ops.gemm(x2, a._pq.get_gemm(a.qkv.weight, a.qkv.bias, self.norm1, row_scale=(C, float(a.scale))))
+            pad = a.pad_qkv_row() if (Hp != H or Wp != W) else None
+            o = ops.window_attention_tokens(qkv, a.relative_position_bias_table, pad, B, H, W, C, self.num_heads, ws, shift)
+            x1 = ops.gemm(o, a._pp.get_gemm(a.proj.weight, a.proj.bias), act="residual", residual=x2)
+            y = self.mlp(x1, norm=self.norm2, residual=x1)
+            return y.reshape(B, L, C)
         qkv = ops.linear(x2, self.attn.packed_qkv(self.norm1), M=B * Hp * Wp, rows=_C.ROWS_WINDOW,
                          epilogue=_C.EPI_QKV, q_cols=C, q_scale=self.attn.scale, geom=geom)
         o = ops.window_attention_core(qkv, self.attn.relative_position_bias_table, B * (Hp // ws) * (Wp // ws), C,

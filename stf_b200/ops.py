@@ -372,28 +372,44 @@ def set_conv_precision(name):
 
 
 _conv_precision = _PRECISIONS[os.environ.get("STF_B200_CONV_PRECISION", "tf32").lower()]
+# Linear layers of the Swin blocks on the TMA / tcgen05 GEMM engine (stf_conv2d with ksize 1) instead of the cp.async-fed
+# stf_linear kernel; "0" keeps the older kernel (A/B measurements).
+GEMM_ENGINE = os.environ.get("STF_B200_GEMM_ENGINE", "1") != "0"
 
 
 class PackedConv:
     """An nn.Conv2d weight (N, sum C_s, k, k) + bias packed for stf_conv2d: K-major [N][tap][source][channel padded to 32]
     TF32 image(s) + bias, output channels in sub-pixel-major order when a PixelShuffle(2) follows."""
 
-    def __init__(self, weight, bias, src_channels, stride=1, pixel_shuffle=0, prec=None):
+    def __init__(self, weight, bias, src_channels=None, stride=1, pixel_shuffle=0, prec=None, ln=None, row_scale=None):
+        """weight: conv (N, C, k, k) or Linear (N, K); ln = (gamma, beta, eps) folds the LayerNorm in front of a Linear
+        through the GEMM; row_scale = (cols, factor) multiplies the first `cols` output features (q * d^-1/2)."""
         self.precision = _conv_precision if prec is None else int(prec)
         w = _dev(weight.detach().contiguous(), "weight")      # (N, C, k, k) in NCHW-contiguous order for the packer
+        if w.dim() == 2:
+            w = w.reshape(w.shape[0], w.shape[1], 1, 1)
         self.N, ctot, self.ksize, k2 = w.shape
+        if src_channels is None:
+            src_channels = (ctot,)
         if k2 != self.ksize or sum(src_channels) != ctot:
             raise ValueError("stf_conv2d: weight shape does not match the sources' channels")
         self.src_channels = tuple(int(c) for c in src_channels)
         self.stride, self.pixel_shuffle = int(stride), int(pixel_shuffle)
+        self.has_ln, self.ln_eps = ln is not None, 0.0 if ln is None else float(ln[2])
         b = None if bias is None else _dev(bias.detach().contiguous(), "bias")
+        g = be = None
+        if ln is not None:
+            g, be = _dev(ln[0].detach().contiguous(), "ln.weight"), _dev(ln[1].detach().contiguous(), "ln.bias")
+            if g.numel() != ctot or be.numel() != ctot or self.ksize != 1 or len(self.src_channels) != 1:
+                raise ValueError("stf_conv2d: a folded LayerNorm needs a Linear (ksize 1, one source) of matching width")
+        cols, factor = (0, 1.0) if row_scale is None else (int(row_scale[0]), float(row_scale[1]))
         a = self.args()
         n = int(_C.lib().stf_packed_conv_floats(ctypes.byref(a)))
         if n < 0:
             _C.check(n, "stf_packed_conv_floats")
         self.packed = torch.empty(n, dtype=torch.float32, device=w.device)
         _launch("pack_conv_kernel", 8 * w.numel(), _C.lib().stf_pack_conv, ctypes.byref(a), w.data_ptr(), _C.ptr(b),
-                self.packed.data_ptr(), _C.stream())
+                _C.ptr(g), _C.ptr(be), cols, factor, self.packed.data_ptr(), _C.stream())
 
     def args(self):
         a = _C.ConvArgs()
@@ -402,6 +418,7 @@ class PackedConv:
             a.src_channels[i] = c
         a.N, a.ksize, a.stride = self.N, self.ksize, self.stride
         a.pixel_shuffle, a.precision = self.pixel_shuffle, self.precision
+        a.has_ln, a.ln_eps = int(self.has_ln), self.ln_eps
         return a
 
 
@@ -439,13 +456,45 @@ def conv2d(srcs, pc, act=False, out=None, residual=None):
         raise ValueError(f"stf_conv2d: `out` must be an NHWC view of shape {shape}")
     a.w_packed = pc.packed.data_ptr()
     a.y, a.ldy = _nhwc(out, "out")
-    a.act = {False: 0, True: 1, None: 0, "gelu": 1, "lrp": 2}[act]
-    if a.act == 2:      # out <- residual + 0.5 * tanh(conv + bias); the residual defaults to the output's current content
+    a.act = {False: 0, True: 1, None: 0, "gelu": 1, "lrp": 2, "residual": 3}[act]
+    if a.act >= 2:      # out <- residual + 0.5 * tanh(conv + bias) / residual + conv + bias; default residual = out's content
         res = out if residual is None else residual
         a.residual, a.res_ld = _nhwc(res, "residual", shape[3])
     ctot = sum(pc.src_channels)
     nbytes = 4 * (B * H * W * ctot + pc.N * ctot * pc.ksize ** 2 + B * Ho * Wo * pc.N)
     _launch("conv_tf32_kernel", nbytes, _C.lib().stf_conv2d, ctypes.byref(a), _C.stream())
+    return out
+
+
+def gemm(x, pc, act=False, residual=None, out=None):
+    """Linear layer on the TMA / tcgen05 GEMM engine: act(LN?(x) . W^T + bias) for token-major x (M, K) -> (M, N).
+    The matrix is handed to stf_conv2d as the NHWC image (1, 1, M, K) (ksize 1): 128-row tiles, LayerNorm folded through the
+    GEMM, act in {False, True / "gelu", "residual"} with residual (M, N)."""
+    if x.dim() != 2 or x.stride(1) != 1:
+        raise ValueError("stf_b200.gemm: x must be a token-major (M, K) matrix")
+    M = x.shape[0]
+    x4 = x.as_strided((1, 1, M, x.shape[1]), (M * x.stride(0), M * x.stride(0), x.stride(0), 1))
+    o4 = r4 = None
+    if out is not None:
+        o4 = out.as_strided((1, 1, M, out.shape[1]), (M * out.stride(0), M * out.stride(0), out.stride(0), 1))
+    if residual is not None:
+        r4 = residual.as_strided((1, 1, M, residual.shape[1]),
+                                 (M * residual.stride(0), M * residual.stride(0), residual.stride(0), 1))
+    y = conv2d([x4], pc, act=act, out=o4, residual=r4)
+    return y.reshape(M, -1) if out is None else out
+
+
+def window_attention_tokens(qkv, bias_table, pad_qkv, B, H, W, C, heads, ws, shift):
+    """Attention core + partition / shift / pad / reverse on token-order qkv (B*H*W, 3C) -> (B*H*W, C)
+    (stf_window_attention_tokens in include/stf_b200.h); 4x4 windows, head_dim 16."""
+    qkv = _dev(qkv, "qkv")
+    bias_table = _dev(bias_table.detach(), "relative_position_bias_table")
+    out = torch.empty((qkv.shape[0], C), dtype=torch.float32, device=qkv.device)
+    if pad_qkv is not None:
+        pad_qkv = _dev(pad_qkv, "pad_qkv")
+    _launch("window_attention_tok_kernel", 4 * qkv.shape[0] * 4 * C, _C.lib().stf_window_attention_tokens, qkv.data_ptr(),
+            out.data_ptr(), bias_table.data_ptr(), _C.ptr(pad_qkv), int(B), int(H), int(W), int(C), int(heads), int(ws),
+            int(shift), _precision, _C.stream())
     return out
 
 
