@@ -15,7 +15,7 @@ _f32p = ctypes.POINTER(ctypes.c_float)
 _SYNC_LAUNCH = os.environ.get("STF_B200_SYNC_LAUNCH", "0") == "1"
 
 
-def _launch(kernel, nbytes, fn, *args):
+def _launch(kernel, nbytes, fn, *args, flops=0):
     """Call one C-ABI entry point; raise on a non-zero status.  `kernel` / `nbytes` name the CUDA kernel
     and its algorithmic bytes for profiler.capture()."""
     cap = profiler.ACTIVE
@@ -42,7 +42,7 @@ def _launch(kernel, nbytes, fn, *args):
         e0.record()
         rc = fn(*args)
         e1.record()
-        cap.add(kernel, nbytes, e0, e1)
+        cap.add(kernel, nbytes, e0, e1, flops)
     _C.check(rc, fn.__name__)
 
 
@@ -333,7 +333,7 @@ def linear(x, lin, *, M=None, rows=_C.ROWS_DENSE, epilogue=_C.EPI_STORE, residua
         a.batch, a.H, a.W, a.window, a.shift = (int(v) for v in geom)
     # algorithmic bytes: activations in + weights + outputs (+ residual read)
     nbytes = 4 * (a.M * a.K + a.N * a.K + a.M * a.N * (2 if residual is not None else 1))
-    _launch("linear_tf32_kernel", nbytes, _C.lib().stf_linear, ctypes.byref(a), _C.stream())
+    _launch("linear_tf32_kernel", nbytes, _C.lib().stf_linear, ctypes.byref(a), _C.stream(), flops=2 * a.M * a.N * a.K)
     return out
 
 
@@ -461,8 +461,10 @@ def conv2d(srcs, pc, act=False, out=None, residual=None):
         res = out if residual is None else residual
         a.residual, a.res_ld = _nhwc(res, "residual", shape[3])
     ctot = sum(pc.src_channels)
-    nbytes = 4 * (B * H * W * ctot + pc.N * ctot * pc.ksize ** 2 + B * Ho * Wo * pc.N)
-    _launch("conv_tf32_kernel", nbytes, _C.lib().stf_conv2d, ctypes.byref(a), _C.stream())
+    # algorithmic bytes: activations in + weights + outputs (+ the residual read)
+    nbytes = 4 * (B * H * W * ctot + pc.N * ctot * pc.ksize ** 2 + B * Ho * Wo * pc.N * (2 if a.act >= 2 else 1))
+    _launch("conv_tf32_kernel:linear" if pc.ksize == 1 else "conv_tf32_kernel:conv", nbytes, _C.lib().stf_conv2d,
+            ctypes.byref(a), _C.stream(), flops=2 * B * Ho * Wo * pc.N * ctot * pc.ksize ** 2)
     return out
 
 
@@ -494,7 +496,7 @@ def window_attention_tokens(qkv, bias_table, pad_qkv, B, H, W, C, heads, ws, shi
         pad_qkv = _dev(pad_qkv, "pad_qkv")
     _launch("window_attention_tok_kernel", 4 * qkv.shape[0] * 4 * C, _C.lib().stf_window_attention_tokens, qkv.data_ptr(),
             out.data_ptr(), bias_table.data_ptr(), _C.ptr(pad_qkv), int(B), int(H), int(W), int(C), int(heads), int(ws),
-            int(shift), _precision, _C.stream())
+            int(shift), _precision, _C.stream(), flops=4 * qkv.shape[0] * ws * ws * C)
     return out
 
 

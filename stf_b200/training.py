@@ -50,11 +50,14 @@ class GradientAllReduce:
     """Bucketed gradient averaging over the data-parallel group (the one collective of the training step).
 
     `attach()` registers post-accumulate hooks: as soon as the last gradient of a bucket has been produced by backward,
-    the bucket is packed and its all-reduce is launched asynchronously, so the transfers of the early buckets (the
-    synthesis transform and the conv stacks, whose gradients come first) run under the rest of the backward pass.
-    `__call__()` after backward launches whatever has not been launched, waits, and writes the averages back."""
+    its all-reduce is launched asynchronously, so the transfers of the early buckets (the synthesis transform and the conv
+    stacks, whose gradients come first) run under the rest of the backward pass.  `__call__()` after backward launches
+    whatever has not been launched and waits.
+    Gradients live IN the buckets (`grad_views=True`, default): every parameter's .grad is a view (with the parameter's own
+    strides) into its bucket's flat buffer, autograd accumulates into it in place, and NCCL reduces the flat buffer where it
+    lies -- no pack / unpack copies.  Use `zero_grad()` of this object instead of optimizer.zero_grad(set_to_none=True)."""
 
-    def __init__(self, params, bucket_mb=50.0, group=None):
+    def __init__(self, params, bucket_mb=50.0, group=None, grad_views=True):
         self.params = [p for p in params if p.requires_grad]
         self.group = group
         self.buckets, cur, size = [], [], 0
@@ -72,6 +75,20 @@ class GradientAllReduce:
         self._pending = [len(b) for b in self.buckets]
         self._works = [None] * len(self.buckets)
         self._hooks = []
+        self.grad_views = bool(grad_views)
+
+    def zero_grad(self):
+        """Zero the gradients in place (one fill per bucket) and (re)attach every .grad to its bucket view."""
+        if not self.grad_views:
+            for p in self.params:
+                p.grad = None
+            return
+        self._ensure_flat()
+        torch._foreach_zero_(self._flat)
+        for bucket, views in zip(self.buckets, self._views):
+            for p, v in zip(bucket, views):
+                if p.grad is None or p.grad.data_ptr() != v.data_ptr():
+                    p.grad = v
 
     def world(self):
         return dist.get_world_size(self.group) if dist.is_available() and dist.is_initialized() else 1
@@ -107,7 +124,12 @@ class GradientAllReduce:
             for flat, bucket in zip(self._flat, self.buckets):
                 views, off = [], 0
                 for p in bucket:
-                    views.append(flat[off:off + p.numel()].view_as(p))
+                    seg = flat[off:off + p.numel()]
+                    dense = p.is_contiguous() or sorted(p.stride(), reverse=True)[-1] == 1 and \
+                        p.numel() == 1 + sum((n - 1) * st for n, st in zip(p.shape, p.stride()))
+                    # the view carries the parameter's own strides (conv weights are channels_last): autograd accumulates
+                    # into it without a layout copy
+                    views.append(seg.as_strided(p.shape, p.stride()) if dense and not p.is_contiguous() else seg.view_as(p))
                     off += p.numel()
                 self._views.append(views)
 
@@ -115,10 +137,13 @@ class GradientAllReduce:
         # pack with ONE multi-tensor copy per bucket (743 parameters would otherwise be ~1500 tiny launches per step)
         self._ensure_flat()
         bucket, views, flat = self.buckets[k], self._views[k], self._flat[k]
-        for p in bucket:
-            if p.grad is None:
-                p.grad = torch.zeros_like(p)
-        torch._foreach_copy_(views, [p.grad for p in bucket])
+        stray = [(v, p.grad) for p, v in zip(bucket, views) if p.grad is not None and p.grad.data_ptr() != v.data_ptr()]
+        if stray:      # gradients that do not live in the bucket (grad_views off, or re-created by the caller): pack them
+            torch._foreach_copy_([v for v, _ in stray], [g for _, g in stray])
+        for p, v in zip(bucket, views):
+            if p.grad is None:        # no gradient this step (or the caller dropped it): contributes zeros
+                v.zero_()
+                p.grad = v
         flat.div_(self.world())
         self._works[k] = dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=self.group, async_op=True)
 
@@ -132,7 +157,9 @@ class GradientAllReduce:
                 self._launch(k)
         for k, bucket in enumerate(self.buckets):
             self._works[k].wait()
-            torch._foreach_copy_([p.grad for p in bucket], self._views[k])
+            stray = [(p.grad, v) for p, v in zip(bucket, self._views[k]) if p.grad.data_ptr() != v.data_ptr()]
+            if stray:
+                torch._foreach_copy_([g for g, _ in stray], [v for _, v in stray])
             nbytes += self._flat[k].numel() * 4
         self._armed = False
         self._works = [None] * len(self.buckets)
@@ -143,8 +170,12 @@ def train_step(net, x, criterion, optimizer, aux_optimizer, reducer=None, clip_m
     """One step of train.py:135-150.  Returns the criterion dict (+ "aux_loss").  `net` may be the bare model (with an
     optional GradientAllReduce `reducer`) or the model wrapped in torch DistributedDataParallel, as in train.py:363 (the
     custom autograd functions produce ordinary .grad tensors, so DDP's bucketed, overlapped all-reduce applies)."""
-    optimizer.zero_grad(set_to_none=True)
-    aux_optimizer.zero_grad(set_to_none=True)
+    if reducer is not None and reducer.grad_views:
+        reducer.zero_grad()               # gradients stay attached to the all-reduce buckets (no pack / unpack copies)
+        aux_optimizer.zero_grad(set_to_none=False)
+    else:
+        optimizer.zero_grad(set_to_none=True)
+        aux_optimizer.zero_grad(set_to_none=True)
     out = criterion(net(x) if noise is None else net(x, noise=noise), x)
     if reducer is not None:
         reducer.arm()

@@ -85,7 +85,7 @@ def test_shard_range_partitions_exactly():
         shard_range(4, 2, 2)
 
 
-def _train_worker(rank, world, port, q):
+def _train_worker(rank, world, port, q, views=False):
     """Data-parallel training step on gloo: each rank has its own half batch; after GradientAllReduce every rank must hold
     the gradient of the full-batch mean loss, and the optimizer steps must keep the replicas identical."""
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
@@ -104,7 +104,11 @@ def _train_worker(rank, world, port, q):
         assert len(red.buckets) >= 2
         lo, hi = rank * 4, rank * 4 + 4
         for _ in range(2):
-            opt.zero_grad()
+            if views:
+                red.zero_grad()        # gradients live in the all-reduce buckets: zeroed in place, reduced where they lie
+                assert all(p.grad.data_ptr() == v.data_ptr() for b, vs in zip(red.buckets, red._views) for p, v in zip(b, vs))
+            else:
+                opt.zero_grad()        # gradients re-created by autograd each step: packed into the buckets
             red.arm()
             torch.nn.functional.mse_loss(net(x[lo:hi]), y[lo:hi]).backward()
             nbytes = red()
@@ -117,11 +121,12 @@ def _train_worker(rank, world, port, q):
         dist.destroy_process_group()
 
 
-def test_two_rank_gradient_allreduce_equals_full_batch():
+@pytest.mark.parametrize("views", [False, True])
+def test_two_rank_gradient_allreduce_equals_full_batch(views):
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
     port = _free_port()
-    procs = [ctx.Process(target=_train_worker, args=(r, 2, port, q)) for r in range(2)]
+    procs = [ctx.Process(target=_train_worker, args=(r, 2, port, q, views)) for r in range(2)]
     for p in procs:
         p.start()
     got = sorted((q.get(timeout=120) for _ in range(2)), key=lambda t: t[0])
