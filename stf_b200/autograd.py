@@ -93,12 +93,12 @@ def wgrad(dy, x):
     with _tf32_matmul(True):
         if ops.precision() != "fp32":
             return dy.t().mm(x)
-        a, b = dy.t(), x
-        a_hi, b_hi = _tf32_trunc(a), _tf32_trunc(b)
-        a_lo, b_lo = a - a_hi, b - b_hi          # exact in fp32; the GEMM reads its upper 11 bits: x = hi + lo to 2^-22
-        out = a_hi.mm(b_hi)
-        out.addmm_(a_lo, b_hi)
-        out.addmm_(a_hi, b_lo)
+        # split in the operands' own layout (dy^T is a view: cuBLAS takes the transposed operand without a copy)
+        a_hi, b_hi = _tf32_trunc(dy), _tf32_trunc(x)
+        a_lo, b_lo = dy - a_hi, x - b_hi         # exact in fp32; the GEMM reads its upper 11 bits: x = hi + lo to 2^-22
+        out = a_hi.t().mm(b_hi)
+        out.addmm_(a_lo.t(), b_hi)
+        out.addmm_(a_hi.t(), b_lo)
         return out
 
 

@@ -46,6 +46,12 @@ constexpr int kTileM = 128;
 constexpr int kBlockK = 32;                       // floats per k-block = one 128-byte swizzle row
 constexpr uint32_t kAStageBytes = kTileM * 128;   // 16 KB
 constexpr int kMaxStages = 8;
+// Halo mode (3x3, stride 1): the A operand of all nine taps is ONE TMA load per 32-channel block -- the (TH + 2) x 16-pixel
+// halo of an 8-wide x 16-tall output tile; tap (ky, kx) is the same shared-memory tile read through a descriptor whose start
+// is shifted by (ky * 16 + kx) pixels (8-row core-matrix groups = the 8 pixels of one output row, group stride = one halo
+// row = 2048 B).  L2 -> shared-memory traffic of the A operand drops 4x (it bounds the kernel: ~53 B/clk/SM).
+constexpr int kHaloW = 16, kHaloTW = 8, kHaloTH = 16;
+constexpr uint32_t kHaloBytes = (kHaloTH + 2) * kHaloW * 128;   // 36 KB per 32-channel block
 constexpr int kEpiWarps = 8;   // two per TMEM lane quadrant (alternating column chunks): one warp per scheduler cannot hide its
                                // own ALU / LDS / MUFU latencies (measured: the GELU epilogue of a 192-column tile took 38 k cycles)
 constexpr int kThreads = 512;
@@ -76,7 +82,8 @@ struct ConvParams {
   const float *svec;                  // has_ln: s[N] = sum_k (gamma o W)[n][k]
   int shuffle_cout;                   // 0: plain store; else channels after PixelShuffle(2) (N = 4 * shuffle_cout)
   int cw;                             // store chunk width in channels: 32 (SWIZZLE_128B staging) or 16 (SWIZZLE_64B)
-  int stages;
+  int stages;                         // operand ring (halo mode: halo tiles)
+  int b_stages;                       // halo mode: weight-tile ring
   int slabs;                          // staging slabs per epilogue warp
   int debug;                          // bring-up (env STF_B200_CONV_DEBUG): 1 no stores, 2 no staging writes, 4 no epilogue math, 8 no A loads
   uint32_t idesc;
@@ -131,6 +138,19 @@ __device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t smem_addr) {
 
 // 32 lanes x 32 consecutive 32-bit columns -> 32 registers per thread; the second half is skipped (warp-uniformly) when
 // `second` is 0.  Loads and tcgen05.wait::ld sit in ONE asm statement, so no use of the outputs can be scheduled above the wait.
+// Same, for an operand whose 8-row groups are `sbo` bytes apart (and an explicit base_offset field [49,52), kept 0: see the
+// halo-mode MMA loop).
+__device__ __forceinline__ uint64_t umma_desc_sw128_ex(uint32_t smem_addr, uint32_t sbo, uint32_t base_offset) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr >> 4) & 0x3FFF);
+  d |= (uint64_t)1 << 16;
+  d |= (uint64_t)((sbo >> 4) & 0x3FFF) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)(base_offset & 7) << 49;
+  d |= (uint64_t)2 << 61;
+  return d;
+}
+
 __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t second, uint32_t (&r)[32]) {
   asm volatile(
       "{\n\t.reg .pred p;\n\t"
@@ -199,7 +219,7 @@ __device__ __forceinline__ void epi_math(const uint32_t (&r)[32], float (&v)[32]
 }
 
 // ---------------------------------------------------------------------------- the kernel
-template <int kPrecise, int kLn>
+template <int kPrecise, int kLn, int kHalo>
 __global__ void __launch_bounds__(kThreads, 1) conv_tf32_kernel(const __grid_constant__ ConvParams P) {
   constexpr bool kAPass = kPrecise || kLn;   // warps 8-11 touch every landed A stage (hi / lo split and / or row statistics)
   extern __shared__ uint8_t smem_raw[];
@@ -208,18 +228,21 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tf32_kernel(const __grid_con
   uint8_t *smem = smem_raw + ((1024u - (raw_u32 & 1023u)) & 1023u);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t S = (uint32_t)P.stages;
-  const uint32_t a_lo_off = kAStageBytes;                                  // precise: A lo plane behind A hi
-  const uint32_t b_off = kPrecise ? 2 * kAStageBytes : kAStageBytes;       // B hi plane
+  const uint32_t a_lo_off = kHalo ? kHaloBytes : kAStageBytes;             // precise: A lo plane behind A hi
+  const uint32_t b_off = kPrecise ? 2 * kAStageBytes : kAStageBytes;       // B hi plane (tap mode: behind the A planes of the stage)
   const uint32_t b_lo_off = b_off + P.b_plane_bytes;
+  const uint32_t SB = (uint32_t)P.b_stages;
+  const uint32_t b_stage_bytes = (uint32_t)(kPrecise ? 2 : 1) * P.b_plane_bytes;
   uint8_t *ring = smem;
-  uint8_t *staging = ring + (size_t)S * P.stage_bytes;   // [4 warps][slabs] x 4 KB, 1024-aligned (stage_bytes % 1024 == 0)
+  uint8_t *b_ring = ring + (size_t)S * P.stage_bytes;     // halo mode: the weight tiles have their own ring
+  uint8_t *staging = b_ring + (kHalo ? (size_t)SB * b_stage_bytes : 0);   // [8 warps][slabs] x 4 KB, 1024-aligned
   float *bias_s = reinterpret_cast<float *>(staging + (size_t)kEpiWarps * P.slabs * kSlabBytes);   // t[Npad] (bias, or beta.W^T + bias)
   float *svec_s = bias_s + P.n_pad;                                         // s[Npad] (LayerNorm fold); Npad covers every chunk, zero past N
   float2 *stats = reinterpret_cast<float2 *>(svec_s + (kLn ? P.n_pad : 0));   // [kStatSlots][128]
   uint64_t *bars = reinterpret_cast<uint64_t *>(stats + (kLn ? kStatSlots * kTileM : 0));
   uint64_t *full = bars, *empty = full + kMaxStages, *split = empty + kMaxStages, *acc_full = split + kMaxStages,
-           *acc_empty = acc_full + 2;
-  uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(acc_empty + 2);
+           *acc_empty = acc_full + 2, *full_b = acc_empty + 2, *empty_b = full_b + kMaxStages;
+  uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(empty_b + kMaxStages);
 
   for (int i = threadIdx.x; i < P.n_pad; i += kThreads) {
     bias_s[i] = (P.bias && i < P.N) ? __ldg(P.bias + i) : 0.f;
@@ -235,6 +258,11 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tf32_kernel(const __grid_con
       mbar_init(&acc_full[b], 1);
       mbar_init(&acc_empty[b], kEpiWarps);  // one arrival per epilogue warp
     }
+    if (kHalo)
+      for (uint32_t s = 0; s < SB; ++s) {
+        mbar_init(&full_b[s], 1);
+        mbar_init(&empty_b[s], 1);
+      }
     mbar_fence_init();
     for (int s = 0; s < P.n_src; ++s) tma_prefetch_desc(&P.a_map[s]);
     tma_prefetch_desc(&P.b_map[0]);
@@ -249,8 +277,13 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tf32_kernel(const __grid_con
 
   if (warp == kProducerWarp) {
     // =========================== TMA producer ===========================
-    if (lane == 0) {
+    // The whole warp runs the loop on warp-uniform values and ONE elected lane issues: ptxas then keeps tensor-map
+    // pointers, coordinates and barrier addresses in uniform registers.  (A lane-0-only loop made it wrap every TMA / MMA
+    // instruction in an ELECT + R2UR.BROADCAST "waterfall" loop: ~600 cycles of issue overhead per k-block, measured.)
+    {
+      const bool leader = elect_one();
       uint32_t st = 0, ph = 1;  // waiting on parity 1 of a fresh barrier returns immediately
+      uint32_t hb_st = 0, hb_ph = 1;
       const uint32_t tx_bytes = kAStageBytes + (uint32_t)(kPrecise ? 2 : 1) * P.b_plane_bytes;
       for (int tile = blockIdx.x; tile < P.total_tiles; tile += gridDim.x) {
         const int mt = tile / P.n_tiles, nt = tile - mt * P.n_tiles;
@@ -259,17 +292,51 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tf32_kernel(const __grid_con
         const int x0 = tx * P.TW * P.stride - P.pad, y0 = ty * P.TH * P.stride - P.pad;
         const int n0 = nt * P.n_tile;
         int kb = 0;
+        if (kHalo) {
+          // channel-block major: one halo tile per 32-channel block, then the nine weight tiles that read it
+          int cbg = 0;   // channel block index over the concatenated sources
+          for (int s = 0; s < P.n_src; ++s) {
+            for (int cb = 0; cb < P.src_kb[s]; ++cb, ++cbg) {
+              mbar_wait(&empty[st], ph);
+              if (leader) mbar_arrive_expect_tx(&full[st], kHaloBytes);
+              if (!leader) {
+              } else if (P.debug & 8) asm volatile("mbarrier.complete_tx.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(&full[st])), "r"(kHaloBytes) : "memory");
+              else tma_load_4d(smem_u32(ring) + st * P.stage_bytes, &P.a_map[s], &full[st], cb * kBlockK, x0, y0, b);
+              if (++st == S) st = 0, ph ^= 1u;
+              for (int tap = 0; tap < 9; ++tap) {
+                mbar_wait(&empty_b[hb_st], hb_ph);
+                const uint32_t bb = smem_u32(b_ring) + hb_st * b_stage_bytes;
+                if (leader) mbar_arrive_expect_tx(&full_b[hb_st], b_stage_bytes);
+                if (!leader) {
+                } else if (P.debug & 64) {
+                  asm volatile("mbarrier.complete_tx.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(&full_b[hb_st])), "r"(b_stage_bytes) : "memory");
+                } else {
+                  tma_load_2d(bb, &P.b_map[0], &full_b[hb_st], (tap * P.kb_per_tap + cbg) * kBlockK, n0);
+                  if (kPrecise) tma_load_2d(bb + P.b_plane_bytes, &P.b_map[1], &full_b[hb_st], (tap * P.kb_per_tap + cbg) * kBlockK, n0);
+                }
+                if (++hb_st == SB) hb_st = 0, hb_ph ^= 1u;
+              }
+            }
+          }
+          continue;
+        }
         for (int tap = 0; tap < P.ksize * P.ksize; ++tap) {
           const int ky = tap / P.ksize, kx = tap - ky * P.ksize;
           for (int s = 0; s < P.n_src; ++s) {
             for (int cb = 0; cb < P.src_kb[s]; ++cb, ++kb) {
               mbar_wait(&empty[st], ph);
               const uint32_t base = smem_u32(ring) + st * P.stage_bytes;
-              mbar_arrive_expect_tx(&full[st], tx_bytes);
-              if (P.debug & 8) asm volatile("mbarrier.complete_tx.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(&full[st])), "r"(kAStageBytes) : "memory");
+              if (leader) mbar_arrive_expect_tx(&full[st], tx_bytes);
+              if (!leader) {
+              } else if (P.debug & 8) asm volatile("mbarrier.complete_tx.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(&full[st])), "r"(kAStageBytes) : "memory");
               else tma_load_4d(base, &P.a_map[s], &full[st], cb * kBlockK, x0 + kx, y0 + ky, b);
-              tma_load_2d(base + b_off, &P.b_map[0], &full[st], kb * kBlockK, n0);
-              if (kPrecise) tma_load_2d(base + b_lo_off, &P.b_map[1], &full[st], kb * kBlockK, n0);
+              if (!leader) {
+              } else if (P.debug & 64) {
+                asm volatile("mbarrier.complete_tx.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(&full[st])), "r"(tx_bytes - kAStageBytes) : "memory");
+              } else {
+                tma_load_2d(base + b_off, &P.b_map[0], &full[st], kb * kBlockK, n0);
+                if (kPrecise) tma_load_2d(base + b_lo_off, &P.b_map[1], &full[st], kb * kBlockK, n0);
+              }
               if (++st == S) st = 0, ph ^= 1u;
             }
           }
@@ -278,14 +345,52 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tf32_kernel(const __grid_con
     }
   } else if (warp == kMmaWarp) {
     // =========================== MMA issuer ===========================
-    if (lane == 0) {
-      uint32_t st = 0, ph = 0;
+    // Whole warp, warp-uniform loop; one elected lane issues tcgen05.mma / commit (descriptors stay in uniform registers).
+    {
+      const bool leader = elect_one();
+      uint32_t st = 0, ph = 0, hb_st = 0, hb_ph = 0;
       int it = 0;
       for (int tile = blockIdx.x; tile < P.total_tiles; tile += gridDim.x, ++it) {
         const int buf = it & 1;
         mbar_wait(&acc_empty[buf], (((uint32_t)it >> 1) & 1u) ^ 1u);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + (uint32_t)(buf * P.acc_stride);
+        if (kHalo) {
+          for (int cbg = 0; cbg < P.kb_per_tap; ++cbg) {
+            mbar_wait(kAPass ? &split[st] : &full[st], ph);
+            const uint32_t hbase = smem_u32(ring) + st * P.stage_bytes;
+#pragma unroll   // (fully unrolled: ky / kx are constants, so the nine descriptors stay in the uniform datapath)
+            for (int tap = 0; tap < 9; ++tap) {
+              const int ky = tap / 3, kx = tap - ky * 3;
+              mbar_wait(&full_b[hb_st], hb_ph);
+              tc_fence_after();
+              // rows of the tap's A operand: output row g = halo row g + ky, pixels kx .. kx + 7 -> group stride = one halo row
+              const uint32_t a_addr = hbase + (uint32_t)((ky * kHaloW + kx) * 128);
+              // base_offset stays 0: measured on B200, the tensor core derives the swizzle phase from the absolute
+              // shared-memory address bits [7,10) -- the same rule the TMA write used -- so a start that is shifted by
+              // kx rows inside the 1024-byte atom reads back consistently (base_offset = kx gives wrong results).
+              const uint64_t da = umma_desc_sw128_ex(a_addr, kHaloW * 128, 0u);
+              const uint64_t dal = umma_desc_sw128_ex(a_addr + a_lo_off, kHaloW * 128, 0u);
+              const uint64_t db = umma_desc_sw128(smem_u32(b_ring) + hb_st * b_stage_bytes);
+#pragma unroll
+              for (int ks = 0; ks < kBlockK / 8; ++ks) {
+                const uint64_t dak = da + (uint64_t)(ks * 2), dbk = db + (uint64_t)(ks * 2);
+                if (leader) umma_tf32(d_tmem, dak, dbk, P.idesc, (cbg | tap | ks) ? 1u : 0u);
+                if (kPrecise && leader) {
+                  umma_tf32(d_tmem, dal + (uint64_t)(ks * 2), dbk, P.idesc, 1u);
+                  umma_tf32(d_tmem, dak, dbk + (uint64_t)(P.b_plane_bytes >> 4), P.idesc, 1u);
+                }
+              }
+              if (leader) umma_commit(&empty_b[hb_st]);
+              if (++hb_st == SB) hb_st = 0, hb_ph ^= 1u;
+            }
+            if (leader) umma_commit(&empty[st]);   // the halo tile is free when its nine taps have been read
+            if (++st == S) st = 0, ph ^= 1u;
+          }
+          if (leader) umma_commit(&acc_full[buf]);
+          __syncwarp();
+          continue;
+        }
         for (int kb = 0; kb < P.k_blocks; ++kb) {
           mbar_wait(kAPass ? &split[st] : &full[st], ph);   // (the A pass has waited for the stage's TMA bytes)
           tc_fence_after();
@@ -294,16 +399,17 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tf32_kernel(const __grid_con
 #pragma unroll
           for (int ks = 0; ks < kBlockK / 8; ++ks) {  // one MMA consumes K = 8 tf32 = 32 B of every row
             const uint64_t dak = da + (uint64_t)(ks * 2), dbk = db + (uint64_t)(ks * 2);
-            umma_tf32(d_tmem, dak, dbk, P.idesc, (kb | ks) ? 1u : 0u);
-            if (kPrecise) {  // 3xTF32: hi.hi + lo.hi + hi.lo (lo.lo is below fp32 round-off)
+            if (leader) umma_tf32(d_tmem, dak, dbk, P.idesc, (kb | ks) ? 1u : 0u);
+            if (kPrecise && leader) {  // 3xTF32: hi.hi + lo.hi + hi.lo (lo.lo is below fp32 round-off)
               umma_tf32(d_tmem, dak + (uint64_t)(a_lo_off >> 4), dbk, P.idesc, 1u);
               umma_tf32(d_tmem, dak, dbk + (uint64_t)(P.b_plane_bytes >> 4), P.idesc, 1u);
             }
           }
-          umma_commit(&empty[st]);  // frees the stage when the MMAs above have read it
+          if (leader) umma_commit(&empty[st]);  // frees the stage when the MMAs above have read it
           if (++st == S) st = 0, ph ^= 1u;
         }
-        umma_commit(&acc_full[buf]);
+        if (leader) umma_commit(&acc_full[buf]);
+        __syncwarp();
       }
     }
   } else if (warp >= kFirstEpiWarp && warp < kFirstEpiWarp + kEpiWarps) {
@@ -316,6 +422,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tf32_kernel(const __grid_con
     const int cw = P.cw;
     const uint32_t row_bytes = (uint32_t)cw * 4u;
     const uint32_t swz = cw == 32 ? (uint32_t)(row & 7) : (uint32_t)((row >> 1) & 3);
+    const bool epi_leader = elect_one();   // the lane that issues this warp's TMA stores (and owns its bulk groups)
     const int ew = warp - kFirstEpiWarp, half = ew >> 2;   // the two warps of a quadrant take even / odd chunks
     const uint32_t slab0 = smem_u32(staging) + (uint32_t)(ew * P.slabs) * kSlabBytes;
     const int sub_x = (quad * 32) % P.TW, sub_y = (quad * 32) / P.TW;
@@ -369,7 +476,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tf32_kernel(const __grid_con
             default: epi_math<kLn, 0>(r, v, bias_s + n0, svec_s + n0, mean, rstd, nullptr, 0); break;
           }
         }
-        if (lane == 0) {  // the store that last read this slab (`slabs` chunks of this warp ago) has finished reading it
+        if (epi_leader) {  // the store that last read this slab (`slabs` chunks of this warp ago) has finished reading it
           if (P.slabs == 1) bulk_wait_read<0>(); else if (P.slabs == 2) bulk_wait_read<1>();
           else if (P.slabs == 3) bulk_wait_read<2>(); else bulk_wait_read<3>();
         }
@@ -389,7 +496,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tf32_kernel(const __grid_con
         }
         fence_proxy_async_smem();
         __syncwarp();
-        if (lane == 0) {
+        if (epi_leader) {
           if (n0 >= P.N || (P.debug & 1)) {
             // chunk entirely past the last output channel (overhanging last column tile): nothing to store
           } else if (P.shuffle_cout) {
@@ -403,7 +510,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tf32_kernel(const __grid_con
         if (++slab == (uint32_t)P.slabs) slab = 0;
       }
     }
-    if (lane == 0) bulk_wait0();
+    if (epi_leader) bulk_wait0();
   } else if (kAPass && warp >= kFirstSplitWarp) {
     // =========================== A pass: hi / lo split (3xTF32) and LayerNorm row statistics ===========================
     // Element-wise on the landed A stage.  3xTF32: the raw fp32 stage IS the hi operand (the tensor core reads the upper 19
@@ -418,6 +525,24 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tf32_kernel(const __grid_con
     int it = 0;
     float shift0[8], sum[8], sq[8];
     for (int tile = blockIdx.x; tile < P.total_tiles; tile += gridDim.x, ++it) {
+      if (kHalo) {  // 3xTF32: split each landed halo tile once (it serves all nine taps)
+        for (int cbg = 0; cbg < P.kb_per_tap; ++cbg) {
+          mbar_wait(&full[st], ph);
+          const uint32_t base = smem_u32(ring) + st * P.stage_bytes + (uint32_t)st_thread * 16u;
+#pragma unroll 6
+          for (int i = 0; i < (int)(kHaloBytes / 2048); ++i) {
+            const uint32_t a = base + (uint32_t)i * 2048u;
+            const float4 x = lds128(a);
+            const float4 hi = make_float4(trunc_tf32(x.x), trunc_tf32(x.y), trunc_tf32(x.z), trunc_tf32(x.w));
+            sts128(a + a_lo_off, make_float4(x.x - hi.x, x.y - hi.y, x.z - hi.z, x.w - hi.w));
+          }
+          fence_proxy_async_smem();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&split[st]);
+          if (++st == S) st = 0, ph ^= 1u;
+        }
+        continue;
+      }
       for (int kb = 0; kb < P.k_blocks; ++kb) {
         mbar_wait(&full[st], ph);
         const uint32_t base = smem_u32(ring) + st * P.stage_bytes + (uint32_t)st_thread * 16u;
@@ -577,8 +702,13 @@ struct Geometry {
   int Ho, Wo, TW, TH, tiles_x, tiles_y;
 };
 
-Geometry geometry(int H, int W, int ksize, int stride) {
+Geometry geometry(int H, int W, int ksize, int stride, bool halo = false) {
   Geometry g;
+  if (halo) {   // 3x3 stride 1: 8-wide x 16-tall tiles (one 8-pixel core-matrix group per output row)
+    g.Ho = H, g.Wo = W, g.TW = kHaloTW, g.TH = kHaloTH;
+    g.tiles_x = (W + kHaloTW - 1) / kHaloTW, g.tiles_y = (H + kHaloTH - 1) / kHaloTH;
+    return g;
+  }
   const int pad = ksize / 2;
   g.Ho = (H + 2 * pad - ksize) / stride + 1;
   g.Wo = (W + 2 * pad - ksize) / stride + 1;
@@ -705,7 +835,11 @@ extern "C" int stf_conv2d(const stf_conv_args *a, void *stream) {
   const int cw = (!shuffle_cout || shuffle_cout % 32 == 0) ? 32 : 16;
   EncodeTiledFn enc = encode_fn();
   if (!enc) return STF_E_ARG;
-  const Geometry g = geometry(a->H, a->W, a->ksize, a->stride);
+  // halo mode: every 3x3 stride-1 convolution (STF_B200_CONV_HALO=0 keeps the tap-by-tap loads: A/B measurements)
+  static const bool halo_on = !(getenv("STF_B200_CONV_HALO") && atoi(getenv("STF_B200_CONV_HALO")) == 0);
+  // (single-pass mode only: in the 3xTF32 parity mode two halo tiles with their lo planes leave no room for the weight ring)
+  const bool halo = halo_on && a->ksize == 3 && a->stride == 1 && !a->has_ln && !precise;
+  const Geometry g = geometry(a->H, a->W, a->ksize, a->stride, halo);
   const int s = a->stride;
   const int n_tile = conv_n_tile(a->N, precise, cw, g.tiles_x * g.tiles_y * a->batch, (Cp / kBlockK) * a->ksize * a->ksize);
   if (n_tile < 0) return n_tile;
@@ -720,7 +854,8 @@ extern "C" int stf_conv2d(const stf_conv_args *a, void *stream) {
     const cuuint64_t gdim[4] = {(cuuint64_t)a->src_channels[i], (cuuint64_t)a->W, (cuuint64_t)a->H, (cuuint64_t)a->batch};
     const cuuint64_t gstr[3] = {(cuuint64_t)a->src_ld[i] * 4, (cuuint64_t)a->W * a->src_ld[i] * 4,
                                 (cuuint64_t)a->H * a->W * a->src_ld[i] * 4};
-    const cuuint32_t box[4] = {(cuuint32_t)kBlockK, (cuuint32_t)(g.TW * s), (cuuint32_t)(g.TH * s), 1};
+    const cuuint32_t box[4] = {(cuuint32_t)kBlockK, (cuuint32_t)(halo ? kHaloW : g.TW * s),
+                               (cuuint32_t)(halo ? kHaloTH + 2 : g.TH * s), 1};
     const cuuint32_t estr[4] = {1, (cuuint32_t)s, (cuuint32_t)s, 1};
     if (enc(&P.a_map[i], CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<float *>(a->src[i]), gdim, gstr, box, estr,
             CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
@@ -785,29 +920,48 @@ extern "C" int stf_conv2d(const stf_conv_args *a, void *stream) {
   while (cols < 2 * n_tile) cols <<= 1;
   P.tmem_cols = cols;
   P.b_plane_bytes = (uint32_t)n_tile * 128u;
-  P.stage_bytes = (uint32_t)(1 + precise) * (kAStageBytes + P.b_plane_bytes);
+  P.stage_bytes = halo ? (uint32_t)(1 + precise) * kHaloBytes : (uint32_t)(1 + precise) * (kAStageBytes + P.b_plane_bytes);
   // shared memory: operand ring first (as many stages as fit next to the minimum of 2 staging slabs per epilogue warp; the
   // ring runs across tile boundaries, so short K loops prefetch the next tiles), what is left goes to more staging slabs
   P.n_pad = ((P.n_tiles * n_tile + 31) & ~31) + 32;
   const size_t small = 1024 /*alignment slack*/ + (size_t)P.n_pad * 4 * (P.has_ln ? 2 : 1) +
-                       (P.has_ln ? (size_t)kStatSlots * kTileM * 8 : 0) + (3 * kMaxStages + 4) * 8 + 16;
+                       (P.has_ln ? (size_t)kStatSlots * kTileM * 8 : 0) + (5 * kMaxStages + 4) * 8 + 16;
   const size_t cap = 227 * 1024;
-  int stages = (int)((cap - small - kEpiWarps * 1 * kSlabBytes) / P.stage_bytes);
-  if (stages > kMaxStages) stages = kMaxStages;
-  if (stages < 2) return STF_E_SHAPE;
-  P.stages = stages;
-  int slabs = (int)((cap - small - (size_t)stages * P.stage_bytes) / (kEpiWarps * kSlabBytes));
+  int stages, b_stages = 0;
+  size_t ring_bytes;
+  if (halo) {
+    // two halo tiles (the next channel block lands while the nine taps of this one run), the rest of the ring memory in
+    // weight tiles (one per tap: at least 4 so that the producer runs half a channel block ahead of the tensor core)
+    const size_t b_stage = (size_t)(1 + precise) * P.b_plane_bytes;
+    stages = 2;
+    size_t left = cap - small - kEpiWarps * kSlabBytes - (size_t)stages * P.stage_bytes;
+    b_stages = (int)(left / b_stage);
+    if (b_stages > kMaxStages) b_stages = kMaxStages;
+    if (b_stages < 3) return STF_E_SHAPE;
+    if (b_stages >= 6 && (size_t)(stages + 1) * P.stage_bytes + 4 * b_stage + small + kEpiWarps * kSlabBytes <= cap)
+      stages = 3, b_stages = (int)((cap - small - kEpiWarps * kSlabBytes - 3 * (size_t)P.stage_bytes) / b_stage);
+    if (b_stages > kMaxStages) b_stages = kMaxStages;
+    ring_bytes = (size_t)stages * P.stage_bytes + (size_t)b_stages * b_stage;
+  } else {
+    stages = (int)((cap - small - kEpiWarps * 1 * kSlabBytes) / P.stage_bytes);
+    if (stages > kMaxStages) stages = kMaxStages;
+    if (stages < 2) return STF_E_SHAPE;
+    ring_bytes = (size_t)stages * P.stage_bytes;
+  }
+  P.stages = stages, P.b_stages = b_stages;
+  int slabs = (int)((cap - small - ring_bytes) / (kEpiWarps * kSlabBytes));
   if (slabs > kMaxSlabs) slabs = kMaxSlabs;
   P.slabs = slabs;
   static const int dbg = getenv("STF_B200_CONV_DEBUG") ? atoi(getenv("STF_B200_CONV_DEBUG")) : 0;
   P.debug = dbg;
   const size_t fixed = small + (size_t)kEpiWarps * slabs * kSlabBytes;
-  const size_t smem = fixed + (size_t)stages * P.stage_bytes;
+  const size_t smem = fixed + ring_bytes;
   const int grid = P.total_tiles < kNumSMs ? P.total_tiles : kNumSMs;
-  auto kern = precise ? (P.has_ln ? conv_tf32_kernel<1, 1> : conv_tf32_kernel<1, 0>)
-                      : (P.has_ln ? conv_tf32_kernel<0, 1> : conv_tf32_kernel<0, 0>);
-  static std::once_flag attr_once[4];
-  std::call_once(attr_once[precise * 2 + P.has_ln], [&] {
+  auto kern = halo ? (precise ? conv_tf32_kernel<1, 0, 1> : conv_tf32_kernel<0, 0, 1>)
+                   : precise ? (P.has_ln ? conv_tf32_kernel<1, 1, 0> : conv_tf32_kernel<1, 0, 0>)
+                             : (P.has_ln ? conv_tf32_kernel<0, 1, 0> : conv_tf32_kernel<0, 0, 0>);
+  static std::once_flag attr_once[6];
+  std::call_once(attr_once[halo ? 4 + precise : precise * 2 + P.has_ln], [&] {
     (void)cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cap);
   });
   kern<<<grid, kThreads, smem, (cudaStream_t)stream>>>(P);

@@ -1,7 +1,7 @@
 """Per-family summary of an ncu launch list of `python tools/one_step.py B` (developer tool).
 
     ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum,sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_elapsed,sm__inst_executed_pipe_tensor.sum \
-        --clock-control none --csv --log-file gpurun_out/r2_ncu_step.csv python tools/one_step.py 8
+        --clock-control none --profile-from-start off --csv --log-file gpurun_out/r2_ncu_step.csv python tools/one_step.py 8
     python tools/ncu_summary.py gpurun_out/r2_ncu_step.csv gpurun_out/one_step_families.json profiles/r2_ncu_step_summary.json
 
 The stf_b200 launches of the ncu list are matched, in order and per kernel name, with the family list the same command
@@ -74,7 +74,8 @@ def main():
     res = {"batch": fam["batch"], "precision": fam["precision"], "total_kernel_time_us": total_us,
            "how": "ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum,"
                   "sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_elapsed,sm__inst_executed_pipe_tensor.sum "
-                  "--clock-control none, python tools/one_step.py (one eager compress+decompress; cold-cache, serialised: shares)",
+                  "--clock-control none --profile-from-start off, python tools/one_step.py (the second of two eager compress+decompress steps; "
+                  "cold-cache, serialised: shares)",
            "families": dict(sorted(out.items(), key=lambda kv: -kv[1]["time_us"]))}
     json.dump(res, open(sys.argv[3], "w"), indent=1)
     for k, f in res["families"].items():

@@ -23,10 +23,15 @@ x = synthetic_image(B, bench.H, bench.W, seed=1).cuda()
 peaks = bench.load_peaks()
 passes = 3 if ops.precision() == "fp32" else 1
 ridge = peaks["tf32_tflops"] * 1e12 / passes / (peaks["hbm_gbs"] * 1e9)
+enc = net.compress(x)                       # warm step: weight packing, table set-up, cuDNN plans
+net.decompress(enc["strings"], enc["shape"])
+torch.cuda.synchronize()
+torch.cuda.profiler.start()                 # ncu --profile-from-start off: only the second step is profiled
 with profiler.capture() as prof:
     enc = net.compress(x)
     dec = net.decompress(enc["strings"], enc["shape"])
 torch.cuda.synchronize()
+torch.cuda.profiler.stop()
 order = []
 for name, nbytes, e0, e1, flops in prof.records:
     bound = "tensor" if flops and flops / max(nbytes, 1) > ridge else "hbm"
