@@ -617,56 +617,74 @@ class _SliceCodec(CompressionModel):
         h, w = zh * 4, zw * 4
         n = self.slice_channels * h * w
         S = self.num_slices
-        stream = torch.cuda.current_stream()
+        main = torch.cuda.current_stream()
         use_graphs = self._graphs_enabled()
 
         class Part:
             pass
 
+        # Every sub-batch decodes on its own CUDA stream, and the host serves them depth-first: the most advanced part
+        # whose device segment has finished gets its next slice decoded and its next segment launched; only when no part
+        # is ready does the host block (on the most advanced one).  The parts therefore drift apart instead of marching in
+        # lockstep, and the long last segment of an early part (slice 11 + the whole synthesis transform) runs on the
+        # device while the host is still decoding the slices of the later parts -- in lockstep the three synthesis
+        # transforms ran back to back at the end with the host idle.
         parts = []
         plans = self._plans("_dec_plans") if use_graphs else None
+        streams = self.__dict__.setdefault("_part_streams", {})
         for slot, (lo, hi) in enumerate(self._parts(B, use_graphs, _DEC_PARTS)):
             p = Part()
             p.B = hi - lo
+            p.stream = main if not use_graphs else streams.setdefault((str(device), slot), torch.cuda.Stream(device=device))
             p.segs, p.st = self._decode_plan(plans, slot, p.B, C, zh, zw, device) if use_graphs else (None, {"hw": (h, w)})
             p.decoders = _decoders(strings[0][lo:hi])
             p.sym_h, p.idx_h = self._host_buffers(("y", slot), p.B, n)
             p.zsym_h, _ = self._host_buffers(("z", slot), p.B, C * zh * zw)
             p.ev = torch.cuda.Event()
+            p.next = 1                      # next segment to launch (segment i consumes the symbols of slice i - 1)
             with _phase("dec.hyper"):
                 z_np = p.zsym_h.numpy()
                 z_idx = self._z_indexes((p.B, C, zh, zw))
                 ans.decode_batch(_decoders(strings[1][lo:hi]), z_table, [z_idx[b] for b in range(p.B)],
                                  outs=[z_np[b] for b in range(p.B)])
-                if use_graphs:
-                    idx = p.segs[0](p.zsym_h.reshape(p.B, C, zh, zw))
-                else:
-                    idx = self._dec_first(p.st, p.zsym_h.to(device, non_blocking=True).reshape(p.B, C, zh, zw))
-                p.idx_h.copy_(idx.reshape(p.B, n), non_blocking=True)
-                p.ev.record(stream)
-            parts.append(p)
-        # slice loop: while the host decodes slice i-1 of one part, the device runs the other part's segment
-        outs = [None] * len(parts)
-        for i in range(1, S + 1):
-            last = i == S
-            for k, p in enumerate(parts):
-                with _phase("dec.slices.gpu"):
-                    p.ev.synchronize()
-                with _phase("dec.slices.rans"):
-                    idx_np, sym_np = p.idx_h.numpy(), p.sym_h.numpy()
-                    ans.decode_batch(p.decoders, y_table, [idx_np[b] for b in range(p.B)],
-                                     outs=[sym_np[b] for b in range(p.B)])
-                with _phase("dec.synthesis" if last else "dec.slices.gpu"):
+                p.stream.wait_stream(main)
+                with torch.cuda.stream(p.stream):
                     if use_graphs:
-                        out = p.segs[i](p.sym_h)          # pinned host buffer -> the segment's static input
+                        idx = p.segs[0](p.zsym_h.reshape(p.B, C, zh, zw))
                     else:
-                        sym = p.sym_h.to(device, non_blocking=True)
-                        out = self._dec_last(p.st, sym) if last else self._dec_mid(p.st, i, sym)
-                    if last:
-                        outs[k] = out
-                    else:
-                        p.idx_h.copy_(out.reshape(p.B, n), non_blocking=True)
-                        p.ev.record(stream)
+                        idx = self._dec_first(p.st, p.zsym_h.to(device, non_blocking=True).reshape(p.B, C, zh, zw))
+                    p.idx_h.copy_(idx.reshape(p.B, n), non_blocking=True)
+                    p.ev.record(p.stream)
+            parts.append(p)
+        outs = [None] * len(parts)
+        todo = len(parts)
+        while todo:
+            ready = next((p for p in parts if p.next <= S and p.ev.query()), None)
+            if ready is None:               # nothing has landed yet: wait for the most advanced unfinished part
+                ready = next(p for p in parts if p.next <= S)
+                with _phase("dec.slices.gpu"):
+                    ready.ev.synchronize()
+            p, i = ready, ready.next
+            last = i == S
+            with _phase("dec.slices.rans"):
+                idx_np, sym_np = p.idx_h.numpy(), p.sym_h.numpy()
+                ans.decode_batch(p.decoders, y_table, [idx_np[b] for b in range(p.B)],
+                                 outs=[sym_np[b] for b in range(p.B)])
+            with _phase("dec.synthesis" if last else "dec.slices.gpu"), torch.cuda.stream(p.stream):
+                if use_graphs:
+                    out = p.segs[i](p.sym_h)          # pinned host buffer -> the segment's static input
+                else:
+                    sym = p.sym_h.to(device, non_blocking=True)
+                    out = self._dec_last(p.st, sym) if last else self._dec_mid(p.st, i, sym)
+                if last:
+                    outs[parts.index(p)] = out
+                    todo -= 1
+                else:
+                    p.idx_h.copy_(out.reshape(p.B, n), non_blocking=True)
+                    p.ev.record(p.stream)
+            p.next += 1
+        for p in parts:
+            main.wait_stream(p.stream)
         x_hat = torch.cat(outs, dim=0) if (len(outs) > 1 or use_graphs) else outs[0]
         return {"x_hat": x_hat}
 
