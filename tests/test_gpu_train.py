@@ -181,6 +181,54 @@ def test_train_step_runs_and_updates(golden_dir, train_kat):
     assert dec["x_hat"].shape == (1, 3, 64, 64)
 
 
+def test_eval_after_train_step_rebuilds_plans(golden_dir):
+    """train -> eval -> train -> eval, as train.py's test_epoch does after every epoch: CUDA-graph plans captured in the
+    first eval phase hold pointers to packed weight images / the bottleneck's parameter block / the scale table; after an
+    optimizer step they are stale.  The weights epoch must drop them: the graph path has to equal the eager path
+    (cuda_graphs=False) on the updated weights -- forward, strings and reconstruction -- and differ from the old outputs."""
+    import json
+    import os
+    from stf_b200.models import SymmetricalTransFormer
+    from stf_b200.training import RateDistortionLoss, configure_optimizers, train_step
+    spec = {k: (tuple(s), getattr(torch, d.split(".")[-1])) for k, (s, d) in
+            json.load(open(os.path.join(golden_dir, "stf_spec.json"))).items()}
+    net = SymmetricalTransFormer(drop_path_rate=0.0)
+    torch.nn.Module.load_state_dict(net, synthetic_state_dict(spec, 0), strict=False)
+    net = net.cuda().eval()
+    net.update(force=True)
+    x = synthetic_image(2, 64, 128, seed=21).cuda()
+    out0 = net(x)["x_hat"].clone()                       # captures the forward plan
+    enc0 = net.compress(x)                               # ... the encoder plan
+    dec0 = net.decompress(enc0["strings"], enc0["shape"])["x_hat"].clone()   # ... and the decoder segments
+    assert net.__dict__.get("_fwd_plans") and net.__dict__.get("_enc_plans") and net.__dict__.get("_dec_plans")
+    opt, aux = configure_optimizers(net, 1e-3, 1e-3)
+    net.train()
+    for _ in range(2):
+        train_step(net, x, RateDistortionLoss(0.0035), opt, aux)
+    net.eval()
+    net.update(force=True)
+    out1 = net(x)["x_hat"].clone()
+    enc1 = net.compress(x)
+    dec1 = net.decompress(enc1["strings"], enc1["shape"])["x_hat"].clone()
+    net.cuda_graphs = False                              # eager reference on the same (updated) weights
+    out_e = net(x)["x_hat"]
+    enc_e = net.compress(x)
+    dec_e = net.decompress(enc_e["strings"], enc_e["shape"])["x_hat"]
+    assert torch.equal(out1, out_e)
+    assert enc1["strings"] == enc_e["strings"]
+    assert torch.equal(dec1, dec_e)
+    assert not torch.equal(out1, out0) and enc1["strings"] != enc0["strings"]    # the weights really moved
+    # an optimizer step taken in eval mode (no train() call in between) is caught by the version counters alone
+    net.cuda_graphs = True
+    before = net.compress(x)["strings"]
+    with torch.no_grad():
+        for p_ in net.h_a.parameters():
+            p_.mul_(1.01)
+    after = net.compress(x)["strings"]
+    net.cuda_graphs = False
+    assert after == net.compress(x)["strings"] and after != before
+
+
 @pytest.mark.parametrize("C,ws,H,W", [(192, 8, 16, 24), (320, 4, 8, 12)])
 def test_win_based_attention_gradients(C, ws, H, W):
     """WACNN's attention blocks (64-token windows with head_dim 24, 16-token windows with head_dim 40; always shifted;
