@@ -53,6 +53,11 @@ struct stf_rans_table {
   std::vector<uint32_t> cdf;    // flattened valid CDF entries, row r: cdf[base[r] + r .. + sizes[r])
   std::vector<uint32_t> cbase;  // first cdf entry of each row
   std::vector<uint16_t> lut;    // rows * 256: symbol holding cumulative value (bucket << 8)
+  struct Row {                  // everything a coding step needs to know about a CDF row, one 16-byte load
+    int32_t offset, escape;     // symbol offset; escape symbol = size - 2
+    uint32_t base, cbase;       // first enc entry / first cdf entry of the row
+  };
+  std::vector<Row> row;
 };
 
 struct stf_rans_decoder {
@@ -104,11 +109,12 @@ inline void put_nibble(uint64_t &x, uint32_t *&w, uint32_t val) {
 
 // One symbol of one stream (returns false on an out-of-range index).
 inline bool encode_step(const stf_rans_table *t, int32_t sym, int32_t row, uint64_t &x, uint32_t *&w) {
-  if (row < 0 || row >= t->rows) return false;
-  const int32_t escape = t->sizes[row] - 2;
-  int32_t v = sym - t->offsets[row];
-  if (v >= 0 && v < escape) {
-    put_symbol(x, w, t->enc[t->base[row] + v]);
+  if ((uint32_t)row >= (uint32_t)t->rows) return false;
+  const stf_rans_table::Row ri = t->row[row];
+  const int32_t escape = ri.escape;
+  int32_t v = sym - ri.offset;
+  if ((uint32_t)v < (uint32_t)escape) {
+    put_symbol(x, w, t->enc[ri.base + v]);
     return true;
   }
   // escape: staged order is [escape symbol][count nibbles][value nibbles]; emit it reversed
@@ -119,7 +125,7 @@ inline bool encode_step(const stf_rans_table *t, int32_t sym, int32_t row, uint6
   int32_t full = nn / kNibbleMax, rest = nn % kNibbleMax;  // count = 15,15,...,rest
   put_nibble(x, w, (uint32_t)rest);
   for (int32_t j = 0; j < full; ++j) put_nibble(x, w, kNibbleMax);
-  put_symbol(x, w, t->enc[t->base[row] + escape]);
+  put_symbol(x, w, t->enc[ri.base + escape]);
   return true;
 }
 
@@ -138,27 +144,31 @@ int64_t encode_into(const stf_rans_table *t, const int32_t *symbols, const int32
   return encode_finish(x, w, buf_end);
 }
 
-// Two independent streams in lockstep: a stream is one serial dependency chain (state -> multiply-high -> state,
-// ~15 cycles per symbol), so a thread that owns two images interleaves them and the core overlaps the two chains.
-// Same bytes as two encode_into calls.
-void encode_into2(const stf_rans_table *t, const int32_t *const sym[2], const int32_t *const idx[2], const int64_t n[2],
-                  uint32_t *const buf_end[2], int64_t nb[2]) {
-  uint32_t *w0 = buf_end[0], *w1 = buf_end[1];
-  uint64_t x0 = kLow, x1 = kLow;
-  int64_t i0 = n[0] - 1, i1 = n[1] - 1;
+// W independent streams in lockstep: a stream is one serial dependency chain (state -> multiply-high -> state, ~15 cycles
+// per symbol), so a thread that owns W images interleaves them and the core overlaps the W chains (W = 2 or 4; with eight
+// ranks sharing a host each rank has a handful of threads for 21+ images).  Same bytes as W encode_into calls.
+template <int W>
+void encode_intoW(const stf_rans_table *t, const int32_t *const *sym, const int32_t *const *idx, const int64_t *n,
+                  uint32_t *const *buf_end, int64_t *nb) {
+  uint32_t *w[W];
+  uint64_t x[W];
+  int64_t i[W];
+  int64_t common = n[0];
+  for (int k = 0; k < W; ++k) {
+    w[k] = buf_end[k], x[k] = kLow, i[k] = n[k] - 1;
+    if (n[k] < common) common = n[k];
+  }
   bool ok = true;
-  for (; ok && i0 >= 0 && i1 >= 0; --i0, --i1) {
-    ok = encode_step(t, sym[0][i0], idx[0][i0], x0, w0);
-    ok = encode_step(t, sym[1][i1], idx[1][i1], x1, w1) && ok;
+  for (int64_t step = 0; ok && step < common; ++step) {
+#pragma GCC unroll 4
+    for (int k = 0; k < W; ++k) {
+      ok = encode_step(t, sym[k][i[k]], idx[k][i[k]], x[k], w[k]) && ok;
+      --i[k];
+    }
   }
-  for (; ok && i0 >= 0; --i0) ok = encode_step(t, sym[0][i0], idx[0][i0], x0, w0);
-  for (; ok && i1 >= 0; --i1) ok = encode_step(t, sym[1][i1], idx[1][i1], x1, w1);
-  if (!ok) {
-    nb[0] = nb[1] = STF_E_ARG;
-    return;
-  }
-  nb[0] = encode_finish(x0, w0, buf_end[0]);
-  nb[1] = encode_finish(x1, w1, buf_end[1]);
+  for (int k = 0; k < W; ++k)
+    for (; ok && i[k] >= 0; --i[k]) ok = encode_step(t, sym[k][i[k]], idx[k][i[k]], x[k], w[k]);
+  for (int k = 0; k < W; ++k) nb[k] = ok ? encode_finish(x[k], w[k], buf_end[k]) : (int64_t)STF_E_ARG;
 }
 
 inline bool refill(stf_rans_decoder *d, uint64_t &x) {
@@ -177,9 +187,10 @@ inline bool get_nibble(stf_rans_decoder *d, uint64_t &x, int32_t *val) {
 
 // One symbol of one stream.
 inline int decode_step(stf_rans_decoder *d, const stf_rans_table *t, int32_t row, uint64_t &x, int32_t *out) {
-  if (row < 0 || row >= t->rows) return STF_E_ARG;
-  const uint32_t *cdf = t->cdf.data() + t->cbase[row];
-  const int32_t escape = t->sizes[row] - 2;
+  if ((uint32_t)row >= (uint32_t)t->rows) return STF_E_ARG;
+  const stf_rans_table::Row ri = t->row[row];
+  const uint32_t *cdf = t->cdf.data() + ri.cbase;
+  const int32_t escape = ri.escape;
   const uint32_t cum = (uint32_t)x & (kProbScale - 1);
   uint32_t s = t->lut[(size_t)row * (1 << kLutBits) + (cum >> (kProbBits - kLutBits))];
   while (cdf[s + 1] <= cum) ++s;
@@ -203,7 +214,7 @@ inline int decode_step(stf_rans_decoder *d, const stf_rans_table *t, int32_t row
     v = raw >> 1;
     v = (raw & 1) ? -v - 1 : v + escape;
   }
-  *out = v + t->offsets[row];
+  *out = v + ri.offset;
   return STF_OK;
 }
 
@@ -217,25 +228,32 @@ int decode_run(stf_rans_decoder *d, const stf_rans_table *t, const int32_t *inde
   return STF_OK;
 }
 
-// Two decoders in lockstep (see encode_into2).
-void decode_run2(stf_rans_decoder *const d[2], const stf_rans_table *t, const int32_t *const idx[2], const int64_t n[2],
-                 int32_t *const out[2], int rc[2]) {
-  uint64_t x0 = d[0]->x, x1 = d[1]->x;
-  const int64_t m = n[0] < n[1] ? n[0] : n[1];
-  rc[0] = rc[1] = STF_OK;
+// W decoders in lockstep (see encode_intoW).
+template <int W>
+void decode_runW(stf_rans_decoder *const *d, const stf_rans_table *t, const int32_t *const *idx, const int64_t *n,
+                 int32_t *const *out, int *rc_out) {
+  uint64_t x[W];
+  int rc[W];   // local: the caller's status array is shared between threads (one cache line for several groups)
+  int64_t m = n[0];
+  for (int k = 0; k < W; ++k) {
+    x[k] = d[k]->x, rc[k] = STF_OK;
+    if (n[k] < m) m = n[k];
+  }
   int64_t i = 0;
-  for (; i < m; ++i) {
-    const int r0 = decode_step(d[0], t, idx[0][i], x0, out[0] + i);
-    const int r1 = decode_step(d[1], t, idx[1][i], x1, out[1] + i);
-    if (r0 | r1) {
-      rc[0] = r0, rc[1] = r1;
-      return;
+  int any = 0;
+  for (; i < m && !any; ++i) {
+#pragma GCC unroll 4
+    for (int k = 0; k < W; ++k) {
+      rc[k] = decode_step(d[k], t, idx[k][i], x[k], out[k] + i);
+      any |= rc[k];
     }
   }
-  for (int64_t j = i; j < n[0] && !rc[0]; ++j) rc[0] = decode_step(d[0], t, idx[0][j], x0, out[0] + j);
-  for (int64_t j = i; j < n[1] && !rc[1]; ++j) rc[1] = decode_step(d[1], t, idx[1][j], x1, out[1] + j);
-  if (!rc[0]) d[0]->x = x0;
-  if (!rc[1]) d[1]->x = x1;
+  if (!any)
+    for (int k = 0; k < W; ++k) {
+      for (int64_t j = i; j < n[k] && !rc[k]; ++j) rc[k] = decode_step(d[k], t, idx[k][j], x[k], out[k] + j);
+      if (!rc[k]) d[k]->x = x[k];
+    }
+  for (int k = 0; k < W; ++k) rc_out[k] = rc[k];
 }
 
 // Persistent worker pool: decode_batch is called once per slice (12-13 times per image batch), so
@@ -357,6 +375,7 @@ extern "C" stf_rans_table *stf_rans_table_create(const int32_t *cdf, int rows, i
     }
     t->base[r] = (uint32_t)t->enc.size();
     t->cbase[r] = (uint32_t)t->cdf.size();
+    t->row.push_back({offsets[r], sz - 2, t->base[r], t->cbase[r]});
     for (int j = 0; j < sz; ++j) t->cdf.push_back((uint32_t)c[j]);
     for (int j = 0; j + 1 < sz; ++j) {
       EncEntry e;
@@ -400,30 +419,34 @@ extern "C" int stf_rans_encode_batch(const stf_rans_table *t, int count, const i
                                      const int32_t *const *indexes, const int64_t *n, uint8_t *const *out,
                                      const int64_t *out_cap, int64_t *out_lens, int threads) {
   if (!t || count < 0 || !symbols || !indexes || !n || !out || !out_cap || !out_lens) return STF_E_ARG;
-  bool pairable = count > threads && threads >= 1;
-  for (int i = 0; pairable && i < count; ++i)
-    pairable = n[i] >= 0 && symbols[i] && indexes[i] && out[i] && out_cap[i] >= stf_rans_encode_bound(n[i]) &&
-               ((uintptr_t)out[i] & 3u) == 0;
-  if (!pairable) {
+  bool groupable = count > threads && threads >= 1;
+  for (int i = 0; groupable && i < count; ++i)
+    groupable = n[i] >= 0 && symbols[i] && indexes[i] && out[i] && out_cap[i] >= stf_rans_encode_bound(n[i]) &&
+                ((uintptr_t)out[i] & 3u) == 0;
+  if (!groupable) {
     parallel_for(count, threads,
                  [&](int i) { out_lens[i] = stf_rans_encode(t, symbols[i], indexes[i], n[i], out[i], out_cap[i]); });
-  } else {  // more images than threads: every task codes two images in lockstep, straight into the callers' buffers
-    parallel_for((count + 1) / 2, threads, [&](int j) {
-      const int a = 2 * j, b = 2 * j + 1;
-      if (b >= count) {
-        out_lens[a] = stf_rans_encode(t, symbols[a], indexes[a], n[a], out[a], out_cap[a]);
-        return;
-      }
-      const int32_t *const sy[2] = {symbols[a], symbols[b]}, *const ix[2] = {indexes[a], indexes[b]};
-      const int64_t nn[2] = {n[a], n[b]};
-      uint32_t *const end[2] = {reinterpret_cast<uint32_t *>(out[a]) + out_cap[a] / 4,
-                                reinterpret_cast<uint32_t *>(out[b]) + out_cap[b] / 4};
-      int64_t nb[2];
-      encode_into2(t, sy, ix, nn, end, nb);
-      for (int k = 0; k < 2; ++k) {
-        const int i = k ? b : a;
-        if (nb[k] > 0) memmove(out[i], reinterpret_cast<uint8_t *>(end[k]) - nb[k], (size_t)nb[k]);
-        out_lens[i] = nb[k];
+  } else {
+    // more images than threads: every task codes a group of 2 (or 4, from four images per thread on) images in lockstep,
+    // straight into the callers' buffers
+    const int G = count >= 4 * threads ? 4 : 2;
+    parallel_for((count + G - 1) / G, threads, [&](int j) {
+      const int a = G * j;
+      const int m = count - a < G ? count - a : G;
+      const int32_t *sy[4], *ix[4];
+      int64_t nn[4], nb[4];
+      uint32_t *end[4];
+      for (int k = 0; k < m; ++k)
+        sy[k] = symbols[a + k], ix[k] = indexes[a + k], nn[k] = n[a + k],
+        end[k] = reinterpret_cast<uint32_t *>(out[a + k]) + out_cap[a + k] / 4;
+      if (m == 4) encode_intoW<4>(t, sy, ix, nn, end, nb);
+      else if (m >= 2) {
+        encode_intoW<2>(t, sy, ix, nn, end, nb);
+        if (m == 3) nb[2] = encode_into(t, sy[2], ix[2], nn[2], end[2]);
+      } else nb[0] = encode_into(t, sy[0], ix[0], nn[0], end[0]);
+      for (int k = 0; k < m; ++k) {
+        if (nb[k] > 0) memmove(out[a + k], reinterpret_cast<uint8_t *>(end[k]) - nb[k], (size_t)nb[k]);
+        out_lens[a + k] = nb[k];
       }
     });
   }
@@ -472,24 +495,20 @@ extern "C" int stf_rans_decode_batch(stf_rans_decoder *const *d, const stf_rans_
                                      int32_t *const *symbols_out, int threads) {
   if (!d || !t || count < 0 || !indexes || !n || !symbols_out) return STF_E_ARG;
   std::vector<int> rc((size_t)count, 0);
-  bool pairable = count > threads && threads >= 1;
-  for (int i = 0; pairable && i < count; ++i) pairable = d[i] && n[i] >= 0 && indexes[i] && symbols_out[i];
-  if (!pairable) {
+  bool groupable = count > threads && threads >= 1;
+  for (int i = 0; groupable && i < count; ++i) groupable = d[i] && n[i] >= 0 && indexes[i] && symbols_out[i];
+  if (!groupable) {
     parallel_for(count, threads, [&](int i) { rc[i] = stf_rans_decode(d[i], t, indexes[i], n[i], symbols_out[i]); });
   } else {
-    parallel_for((count + 1) / 2, threads, [&](int j) {
-      const int a = 2 * j, b = 2 * j + 1;
-      if (b >= count) {
-        rc[a] = stf_rans_decode(d[a], t, indexes[a], n[a], symbols_out[a]);
-        return;
-      }
-      stf_rans_decoder *const dd[2] = {d[a], d[b]};
-      const int32_t *const ix[2] = {indexes[a], indexes[b]};
-      const int64_t nn[2] = {n[a], n[b]};
-      int32_t *const oo[2] = {symbols_out[a], symbols_out[b]};
-      int r2[2];
-      decode_run2(dd, t, ix, nn, oo, r2);
-      rc[a] = r2[0], rc[b] = r2[1];
+    const int G = count >= 4 * threads ? 4 : 2;
+    parallel_for((count + G - 1) / G, threads, [&](int j) {
+      const int a = G * j;
+      const int m = count - a < G ? count - a : G;
+      if (m == 4) decode_runW<4>(d + a, t, indexes + a, n + a, symbols_out + a, rc.data() + a);
+      else if (m >= 2) {
+        decode_runW<2>(d + a, t, indexes + a, n + a, symbols_out + a, rc.data() + a);
+        if (m == 3) rc[a + 2] = stf_rans_decode(d[a + 2], t, indexes[a + 2], n[a + 2], symbols_out[a + 2]);
+      } else rc[a] = stf_rans_decode(d[a], t, indexes[a], n[a], symbols_out[a]);
     });
   }
   for (int i = 0; i < count; ++i)

@@ -360,10 +360,10 @@ class _SliceCodec(CompressionModel):
                 return self._forward_eval(x)
             # one CUDA graph per input shape (~340 launches of ours + cuDNN, launch-bound when issued eagerly); the
             # returned tensors are clones: the graph's static outputs are overwritten by the next call
+            self._prepare_inference()          # (before the plan lookup: it re-lays-out conv weights, i.e. changes the epoch)
             plans = self._plans("_fwd_plans")
             key = tuple(x.shape)
             if not self._plan_slot(plans, key, 8):
-                self._prepare_inference()
 
                 def fn(t):
                     o = self._forward_eval(t)

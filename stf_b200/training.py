@@ -85,10 +85,14 @@ class GradientAllReduce:
             return
         self._ensure_flat()
         torch._foreach_zero_(self._flat)
-        for bucket, views in zip(self.buckets, self._views):
-            for p, v in zip(bucket, views):
-                if p.grad is None or p.grad.data_ptr() != v.data_ptr():
-                    p.grad = v
+        for bucket, views, flat in zip(self.buckets, self._views, self._flat):
+            off = 0
+            for j, p in enumerate(bucket):
+                if views[j].stride() != p.stride():      # the parameter was re-laid-out (channels_last) after the views were made
+                    views[j] = self._view(flat[off:off + p.numel()], p)
+                if p.grad is None or p.grad.data_ptr() != views[j].data_ptr() or p.grad.stride() != views[j].stride():
+                    p.grad = views[j]
+                off += p.numel()
 
     def world(self):
         return dist.get_world_size(self.group) if dist.is_available() and dist.is_initialized() else 1
@@ -116,6 +120,13 @@ class GradientAllReduce:
         if self._pending[k] == 0:
             self._launch(k)
 
+    @staticmethod
+    def _view(seg, p):
+        """View of a flat bucket segment with the parameter's own strides (conv weights are channels_last): autograd
+        accumulates into it without a layout copy."""
+        dense = p.numel() == 1 + sum((n - 1) * st for n, st in zip(p.shape, p.stride()))
+        return seg.as_strided(p.shape, p.stride()) if dense and not p.is_contiguous() else seg.view_as(p)
+
     def _ensure_flat(self):
         if self._flat is None:
             dev = self.params[0].device
@@ -124,12 +135,7 @@ class GradientAllReduce:
             for flat, bucket in zip(self._flat, self.buckets):
                 views, off = [], 0
                 for p in bucket:
-                    seg = flat[off:off + p.numel()]
-                    dense = p.is_contiguous() or sorted(p.stride(), reverse=True)[-1] == 1 and \
-                        p.numel() == 1 + sum((n - 1) * st for n, st in zip(p.shape, p.stride()))
-                    # the view carries the parameter's own strides (conv weights are channels_last): autograd accumulates
-                    # into it without a layout copy
-                    views.append(seg.as_strided(p.shape, p.stride()) if dense and not p.is_contiguous() else seg.view_as(p))
+                    views.append(self._view(flat[off:off + p.numel()], p))
                     off += p.numel()
                 self._views.append(views)
 
