@@ -160,6 +160,54 @@ class RansDecoder:
         return self.decode_stream(indexes, cdfs, cdfs_sizes, offsets)
 
 
+def _row_ptrs(a2d):
+    """ctypes array of the row addresses of a C-contiguous 2-D int32 array (no per-row numpy views / .ctypes objects)."""
+    if a2d.dtype != np.int32 or a2d.ndim != 2 or not a2d.flags.c_contiguous:
+        raise ValueError("expected a C-contiguous 2-D int32 array")
+    base, stride = a2d.ctypes.data, a2d.strides[0]
+    return (ctypes.c_void_p * a2d.shape[0])(*[base + i * stride for i in range(a2d.shape[0])])
+
+
+class DecodePlan:
+    """Repeated decode_batch calls on FIXED buffers (the slice loop of decompress(): 12 calls per sub-batch on the same pinned
+    index / symbol buffers): the ctypes argument arrays are built once, each run() is one C call."""
+
+    def __init__(self, decoders, table: RansTable, idx2d, out2d, threads=None):
+        count = len(decoders)
+        if idx2d.shape != out2d.shape or idx2d.shape[0] != count:
+            raise ValueError("index / output buffers must be (len(decoders), n)")
+        self._keep = (decoders, table, idx2d, out2d)
+        self._args = ((ctypes.c_void_p * count)(*[d._h for d in decoders]), table._h, count, _row_ptrs(idx2d),
+                      (ctypes.c_int64 * count)(*([idx2d.shape[1]] * count)), _row_ptrs(out2d), threads or default_threads())
+        self._fn = _C.lib().stf_rans_decode_batch
+
+    def run(self):
+        _C.check(self._fn(*self._args), "stf_rans_decode_batch")
+
+
+def encode_rows(table: RansTable, sym2d, idx2d, scratch=None, threads=None):
+    """encode_batch for the rows of two (B, n) int32 arrays; `scratch` (a dict kept by the caller) recycles the output
+    buffers between calls (8 n + 64 bytes per image otherwise freshly mapped every time).  -> list[bytes]."""
+    count, n = sym2d.shape
+    if idx2d.shape != sym2d.shape:
+        raise ValueError("symbols and indexes differ in shape")
+    L = _C.lib()
+    cap = int(L.stf_rans_encode_bound(n))
+    key = (count, cap)
+    if scratch is None:
+        scratch = {}
+    if scratch.get("key") != key:
+        out = np.empty((count, cap), dtype=np.uint8)
+        scratch.update(key=key, out=out, out_ptrs=(ctypes.c_void_p * count)(*[out.ctypes.data + i * cap for i in range(count)]),
+                       caps=(ctypes.c_int64 * count)(*([cap] * count)), ns=(ctypes.c_int64 * count)(*([n] * count)),
+                       lens=(ctypes.c_int64 * count)())
+    rc = L.stf_rans_encode_batch(table._h, count, _row_ptrs(sym2d), _row_ptrs(idx2d), scratch["ns"], scratch["out_ptrs"],
+                                 scratch["caps"], scratch["lens"], threads or default_threads())
+    _C.check(rc, "stf_rans_encode_batch")
+    out, lens = scratch["out"], scratch["lens"]
+    return [out[i, : lens[i]].tobytes() for i in range(count)]
+
+
 def decode_batch(decoders, table: RansTable, indexes, outs=None, threads=None):
     """Advance each decoder by len(indexes[i]) symbols in parallel; returns list of int32 arrays."""
     count = len(decoders)

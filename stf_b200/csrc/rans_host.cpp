@@ -427,26 +427,28 @@ extern "C" int stf_rans_encode_batch(const stf_rans_table *t, int count, const i
     parallel_for(count, threads,
                  [&](int i) { out_lens[i] = stf_rans_encode(t, symbols[i], indexes[i], n[i], out[i], out_cap[i]); });
   } else {
-    // more images than threads: every task codes a group of 2 (or 4, from four images per thread on) images in lockstep,
-    // straight into the callers' buffers
-    const int G = count >= 4 * threads ? 4 : 2;
-    parallel_for((count + G - 1) / G, threads, [&](int j) {
-      const int a = G * j;
-      const int m = count - a < G ? count - a : G;
-      const int32_t *sy[4], *ix[4];
-      int64_t nn[4], nb[4];
-      uint32_t *end[4];
-      for (int k = 0; k < m; ++k)
-        sy[k] = symbols[a + k], ix[k] = indexes[a + k], nn[k] = n[a + k],
-        end[k] = reinterpret_cast<uint32_t *>(out[a + k]) + out_cap[a + k] / 4;
-      if (m == 4) encode_intoW<4>(t, sy, ix, nn, end, nb);
-      else if (m >= 2) {
-        encode_intoW<2>(t, sy, ix, nn, end, nb);
-        if (m == 3) nb[2] = encode_into(t, sy[2], ix[2], nn[2], end[2]);
-      } else nb[0] = encode_into(t, sy[0], ix[0], nn[0], end[0]);
-      for (int k = 0; k < m; ++k) {
-        if (nb[k] > 0) memmove(out[a + k], reinterpret_cast<uint8_t *>(end[k]) - nb[k], (size_t)nb[k]);
-        out_lens[a + k] = nb[k];
+    // more images than threads: the images are split evenly over the threads (contiguous ranges whose sizes differ by at
+    // most one -- fixed groups of four would leave half the threads idle in the last round of 21 images on 4 threads) and
+    // every thread codes its range in lockstep groups of 4, 3, 2 or 1, straight into the callers' buffers
+    parallel_for(threads, threads, [&](int tix) {
+      const int lo = (int)((int64_t)count * tix / threads), hi = (int)((int64_t)count * (tix + 1) / threads);
+      for (int a = lo; a < hi;) {
+        const int m = hi - a < 4 ? hi - a : 4;
+        const int32_t *sy[4], *ix[4];
+        int64_t nn[4], nb[4];
+        uint32_t *end[4];
+        for (int k = 0; k < m; ++k)
+          sy[k] = symbols[a + k], ix[k] = indexes[a + k], nn[k] = n[a + k],
+          end[k] = reinterpret_cast<uint32_t *>(out[a + k]) + out_cap[a + k] / 4;
+        if (m == 4) encode_intoW<4>(t, sy, ix, nn, end, nb);
+        else if (m == 3) encode_intoW<3>(t, sy, ix, nn, end, nb);
+        else if (m == 2) encode_intoW<2>(t, sy, ix, nn, end, nb);
+        else nb[0] = encode_into(t, sy[0], ix[0], nn[0], end[0]);
+        for (int k = 0; k < m; ++k) {
+          if (nb[k] > 0) memmove(out[a + k], reinterpret_cast<uint8_t *>(end[k]) - nb[k], (size_t)nb[k]);
+          out_lens[a + k] = nb[k];
+        }
+        a += m;
       }
     });
   }
@@ -500,15 +502,18 @@ extern "C" int stf_rans_decode_batch(stf_rans_decoder *const *d, const stf_rans_
   if (!groupable) {
     parallel_for(count, threads, [&](int i) { rc[i] = stf_rans_decode(d[i], t, indexes[i], n[i], symbols_out[i]); });
   } else {
-    const int G = count >= 4 * threads ? 4 : 2;
-    parallel_for((count + G - 1) / G, threads, [&](int j) {
-      const int a = G * j;
-      const int m = count - a < G ? count - a : G;
-      if (m == 4) decode_runW<4>(d + a, t, indexes + a, n + a, symbols_out + a, rc.data() + a);
-      else if (m >= 2) {
-        decode_runW<2>(d + a, t, indexes + a, n + a, symbols_out + a, rc.data() + a);
-        if (m == 3) rc[a + 2] = stf_rans_decode(d[a + 2], t, indexes[a + 2], n[a + 2], symbols_out[a + 2]);
-      } else rc[a] = stf_rans_decode(d[a], t, indexes[a], n[a], symbols_out[a]);
+    parallel_for(threads, threads, [&](int tix) {   // even contiguous ranges, lockstep groups of 4 / 3 / 2 / 1 (see encode)
+      const int lo = (int)((int64_t)count * tix / threads), hi = (int)((int64_t)count * (tix + 1) / threads);
+      for (int a = lo; a < hi;) {
+        const int m = hi - a < 4 ? hi - a : 4;
+        int r[4];
+        if (m == 4) decode_runW<4>(d + a, t, indexes + a, n + a, symbols_out + a, r);
+        else if (m == 3) decode_runW<3>(d + a, t, indexes + a, n + a, symbols_out + a, r);
+        else if (m == 2) decode_runW<2>(d + a, t, indexes + a, n + a, symbols_out + a, r);
+        else r[0] = stf_rans_decode(d[a], t, indexes[a], n[a], symbols_out[a]);
+        for (int k = 0; k < m; ++k) rc[a + k] = r[k];
+        a += m;
+      }
     });
   }
   for (int i = 0; i < count; ++i)

@@ -48,6 +48,8 @@ _EB_MEDIAN = _C.STF_EB_MEDIAN_SLOT
 _PIPELINE_MIN_BATCH = int(os.environ.get("STF_B200_PIPELINE_MIN_BATCH", "16"))
 _PIPELINE_PARTS = int(os.environ.get("STF_B200_PIPELINE_PARTS", "0"))   # 0 = auto: 3 sub-batches from 48 images, else 2
 _DEC_PARTS = int(os.environ.get("STF_B200_DEC_PARTS", "0")) or None     # decompress(): sub-batches (default: same as compress)
+_PART_TAPER = float(os.environ.get("STF_B200_PART_TAPER", "0.75"))    # size of the last sub-batch relative to the first
+_DEC_LEAD = int(os.environ.get("STF_B200_DEC_LEAD", "3"))               # decompress(): slices a sub-batch may lead the next one by
 PHASE_TIMES = None   # set to a dict to collect a synchronised wall-clock breakdown (tools/phase_breakdown.py)
 
 
@@ -478,7 +480,13 @@ class _SliceCodec(CompressionModel):
         if not pipelined or B < _PIPELINE_MIN_BATCH:
             return [(0, B)]
         n = max(2, min(n_parts or _PIPELINE_PARTS or (3 if B >= 48 else 2), B // 8 if B >= 16 else 2))
-        bounds = [round(i * B / n) for i in range(n + 1)]
+        # tapered sizes (weights 1 .. _PART_TAPER from the first to the last part): the host work of the LAST part is the
+        # exposed tail of compress(), the device work of the FIRST part runs with an idle host
+        wts = [1.0 + (_PART_TAPER - 1.0) * i / (n - 1) for i in range(n)]
+        acc, bounds = 0.0, [0]
+        for w_ in wts:
+            acc += w_
+            bounds.append(round(B * acc / sum(wts)))
         return [(lo, hi) for lo, hi in zip(bounds, bounds[1:]) if hi > lo]
 
     @torch.no_grad()
@@ -512,16 +520,16 @@ class _SliceCodec(CompressionModel):
                 ev.record(stream)
             pending.append((ev, Bp, sym_h, idx_h, zsym_h, tuple(z_sym.shape)))
         y_strings, z_strings = [], []
-        for ev, Bp, sym_h, idx_h, zsym_h, zshape in pending:
+        for slot, (ev, Bp, sym_h, idx_h, zsym_h, zshape) in enumerate(pending):
             with _phase("enc.d2h"):
                 ev.synchronize()
             if debug is not None:
                 debug.update(symbols=sym_h.clone(), indexes=idx_h.clone(), z_symbols=zsym_h.clone())
             with _phase("enc.rans"):
-                s_np, i_np, z_np = sym_h.numpy(), idx_h.numpy(), zsym_h.numpy()
                 z_idx = self._z_indexes(tuple(zshape))
-                y_strings += ans.encode_batch(y_table, [s_np[b] for b in range(Bp)], [i_np[b] for b in range(Bp)])
-                z_strings += ans.encode_batch(z_table, [z_np[b] for b in range(Bp)], [z_idx[b] for b in range(Bp)])
+                scratch = self.__dict__.setdefault("_enc_scratch", {})
+                y_strings += ans.encode_rows(y_table, sym_h.numpy(), idx_h.numpy(), scratch.setdefault(("y", slot), {}))
+                z_strings += ans.encode_rows(z_table, zsym_h.numpy(), z_idx, scratch.setdefault(("z", slot), {}))
         return {"strings": [y_strings, z_strings], "shape": torch.Size(zshape[-2:])}
 
     def _z_indexes(self, zshape):
@@ -641,6 +649,7 @@ class _SliceCodec(CompressionModel):
             p.sym_h, p.idx_h = self._host_buffers(("y", slot), p.B, n)
             p.zsym_h, _ = self._host_buffers(("z", slot), p.B, C * zh * zw)
             p.ev = torch.cuda.Event()
+            p.plan = ans.DecodePlan(p.decoders, y_table, p.idx_h.numpy(), p.sym_h.numpy())
             p.next = 1                      # next segment to launch (segment i consumes the symbols of slice i - 1)
             with _phase("dec.hyper"):
                 z_np = p.zsym_h.numpy()
@@ -658,18 +667,26 @@ class _SliceCodec(CompressionModel):
             parts.append(p)
         outs = [None] * len(parts)
         todo = len(parts)
+        def may_lead(k):
+            """Part k may run at most _DEC_LEAD slices ahead of the next unfinished part: enough stagger for its synthesis
+            to overlap the later parts' slices, not so much that the last part ends up alone (host and device would then
+            alternate with nothing to overlap: measured with 4 host threads per rank)."""
+            later = next((q for q in parts[k + 1:] if q.next <= S), None)
+            return later is None or parts[k].next - later.next < _DEC_LEAD
+
         while todo:
-            ready = next((p for p in parts if p.next <= S and p.ev.query()), None)
-            if ready is None:               # nothing has landed yet: wait for the most advanced unfinished part
-                ready = next(p for p in parts if p.next <= S)
+            live = [k for k, p in enumerate(parts) if p.next <= S]
+            ready = next((parts[k] for k in live if may_lead(k) and parts[k].ev.query()), None)
+            if ready is None:
+                ready = next((parts[k] for k in live if parts[k].ev.query()), None)
+            if ready is None:               # nothing has landed yet: wait for the most advanced part that may proceed
+                ready = next((parts[k] for k in live if may_lead(k)), parts[live[0]])
                 with _phase("dec.slices.gpu"):
                     ready.ev.synchronize()
             p, i = ready, ready.next
             last = i == S
             with _phase("dec.slices.rans"):
-                idx_np, sym_np = p.idx_h.numpy(), p.sym_h.numpy()
-                ans.decode_batch(p.decoders, y_table, [idx_np[b] for b in range(p.B)],
-                                 outs=[sym_np[b] for b in range(p.B)])
+                p.plan.run()                # decoders advance by one slice: pinned indexes -> pinned symbols
             with _phase("dec.synthesis" if last else "dec.slices.gpu"), torch.cuda.stream(p.stream):
                 if use_graphs:
                     out = p.segs[i](p.sym_h)          # pinned host buffer -> the segment's static input

@@ -168,3 +168,33 @@ def test_pmf_to_quantized_cdf_matches_oracle():
     spike = np.zeros(300, np.float32)
     spike[150] = 1.0                                                          # many zero-mass symbols -> stealing
     assert ans.pmf_to_quantized_cdf(spike) == OE.pmf_to_quantized_cdf(spike).tolist()
+
+
+def test_rans_batch_grouping_matches_single_streams():
+    """encode_batch / decode_batch split the images evenly over the threads and code each thread's range in lockstep groups
+    of 4 / 3 / 2 / 1: whatever the (count, threads) combination, every string equals the single-stream encode and decodes
+    back (ragged lengths included)."""
+    from stf_b200 import ans
+    cdf, lens, offs = OE.gaussian_tables()
+    tab = ans.RansTable(cdf, lens, offs)
+    rng = np.random.default_rng(7)
+    table = OE.scale_table().numpy()
+    imgs = []
+    for i in range(11):
+        n = int(rng.integers(200, 3000))
+        ix = rng.integers(0, 64, size=n).astype(np.int32)
+        sy = np.rint(rng.standard_normal(n) * table[ix] * (3.0 if i % 3 == 0 else 1.0)).astype(np.int32)   # incl. escapes
+        imgs.append((sy, ix))
+    singles = [ans.encode_array(tab, sy, ix) for sy, ix in imgs]
+    for count in (1, 2, 3, 5, 7, 11):
+        for threads in (1, 2, 3, 4):
+            got = ans.encode_batch(tab, [s for s, _ in imgs[:count]], [i for _, i in imgs[:count]], threads=threads)
+            assert got == singles[:count], (count, threads)
+            decs = []
+            for s in got:
+                d = ans.RansDecoder()
+                d.set_stream(s)
+                decs.append(d)
+            outs = [np.empty(len(sy), dtype=np.int32) for sy, _ in imgs[:count]]
+            ans.decode_batch(decs, tab, [i for _, i in imgs[:count]], outs=outs, threads=threads)
+            assert all(np.array_equal(o, sy) for o, (sy, _) in zip(outs, imgs[:count])), (count, threads)
