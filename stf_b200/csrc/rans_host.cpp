@@ -34,6 +34,12 @@ constexpr uint32_t kNibbleBits = 4;
 constexpr int32_t kNibbleMax = 15;
 constexpr uint64_t kLow = 1ull << 31;  // RANS64_L
 constexpr int kLutBits = 8;
+// images one thread codes in lockstep (env STF_B200_RANS_LOCKSTEP, 1..8)
+static const int kMaxLockstep = [] {
+  const char *e = getenv("STF_B200_RANS_LOCKSTEP");
+  int v = e ? atoi(e) : 4;
+  return v < 1 ? 1 : (v > 8 ? 8 : v);
+}();
 
 struct EncEntry {
   uint64_t rcp;       // ceil(2^(63+shift) / freq), freq >= 2
@@ -160,7 +166,7 @@ void encode_intoW(const stf_rans_table *t, const int32_t *const *sym, const int3
   }
   bool ok = true;
   for (int64_t step = 0; ok && step < common; ++step) {
-#pragma GCC unroll 4
+#pragma GCC unroll 8
     for (int k = 0; k < W; ++k) {
       ok = encode_step(t, sym[k][i[k]], idx[k][i[k]], x[k], w[k]) && ok;
       --i[k];
@@ -242,7 +248,7 @@ void decode_runW(stf_rans_decoder *const *d, const stf_rans_table *t, const int3
   int64_t i = 0;
   int any = 0;
   for (; i < m && !any; ++i) {
-#pragma GCC unroll 4
+#pragma GCC unroll 8
     for (int k = 0; k < W; ++k) {
       rc[k] = decode_step(d[k], t, idx[k][i], x[k], out[k] + i);
       any |= rc[k];
@@ -433,14 +439,18 @@ extern "C" int stf_rans_encode_batch(const stf_rans_table *t, int count, const i
     parallel_for(threads, threads, [&](int tix) {
       const int lo = (int)((int64_t)count * tix / threads), hi = (int)((int64_t)count * (tix + 1) / threads);
       for (int a = lo; a < hi;) {
-        const int m = hi - a < 4 ? hi - a : 4;
-        const int32_t *sy[4], *ix[4];
-        int64_t nn[4], nb[4];
-        uint32_t *end[4];
+        const int m = hi - a < kMaxLockstep ? hi - a : kMaxLockstep;
+        const int32_t *sy[8], *ix[8];
+        int64_t nn[8], nb[8];
+        uint32_t *end[8];
         for (int k = 0; k < m; ++k)
           sy[k] = symbols[a + k], ix[k] = indexes[a + k], nn[k] = n[a + k],
           end[k] = reinterpret_cast<uint32_t *>(out[a + k]) + out_cap[a + k] / 4;
-        if (m == 4) encode_intoW<4>(t, sy, ix, nn, end, nb);
+        if (m == 8) encode_intoW<8>(t, sy, ix, nn, end, nb);
+        else if (m == 7) encode_intoW<7>(t, sy, ix, nn, end, nb);
+        else if (m == 6) encode_intoW<6>(t, sy, ix, nn, end, nb);
+        else if (m == 5) encode_intoW<5>(t, sy, ix, nn, end, nb);
+        else if (m == 4) encode_intoW<4>(t, sy, ix, nn, end, nb);
         else if (m == 3) encode_intoW<3>(t, sy, ix, nn, end, nb);
         else if (m == 2) encode_intoW<2>(t, sy, ix, nn, end, nb);
         else nb[0] = encode_into(t, sy[0], ix[0], nn[0], end[0]);
@@ -505,9 +515,13 @@ extern "C" int stf_rans_decode_batch(stf_rans_decoder *const *d, const stf_rans_
     parallel_for(threads, threads, [&](int tix) {   // even contiguous ranges, lockstep groups of 4 / 3 / 2 / 1 (see encode)
       const int lo = (int)((int64_t)count * tix / threads), hi = (int)((int64_t)count * (tix + 1) / threads);
       for (int a = lo; a < hi;) {
-        const int m = hi - a < 4 ? hi - a : 4;
-        int r[4];
-        if (m == 4) decode_runW<4>(d + a, t, indexes + a, n + a, symbols_out + a, r);
+        const int m = hi - a < kMaxLockstep ? hi - a : kMaxLockstep;
+        int r[8];
+        if (m == 8) decode_runW<8>(d + a, t, indexes + a, n + a, symbols_out + a, r);
+        else if (m == 7) decode_runW<7>(d + a, t, indexes + a, n + a, symbols_out + a, r);
+        else if (m == 6) decode_runW<6>(d + a, t, indexes + a, n + a, symbols_out + a, r);
+        else if (m == 5) decode_runW<5>(d + a, t, indexes + a, n + a, symbols_out + a, r);
+        else if (m == 4) decode_runW<4>(d + a, t, indexes + a, n + a, symbols_out + a, r);
         else if (m == 3) decode_runW<3>(d + a, t, indexes + a, n + a, symbols_out + a, r);
         else if (m == 2) decode_runW<2>(d + a, t, indexes + a, n + a, symbols_out + a, r);
         else r[0] = stf_rans_decode(d[a], t, indexes[a], n[a], symbols_out[a]);
