@@ -213,6 +213,7 @@ typedef struct {
   int window;             /* window size ws (WINDOW) */
   int shift;              /* cyclic shift (0 or ws/2) */
   int precision;          /* STF_PREC_*; must match the precision w_packed was packed with */
+  int max_ctas;           /* persistent grid size cap (0 = 148), see stf_conv_args */
 } stf_linear_args;
 
 /* Fused linear layer on tcgen05 tensor cores.  Replaces, depending on the arguments:
@@ -280,6 +281,9 @@ typedef struct {
   float ln_eps;               /* (row statistics gathered in-kernel while the rows stream through shared memory) */
   int precision;              /* STF_PREC_TF32: one MMA per k-step on the raw fp32 activations (what cuDNN's default TF32 */
                               /* convolutions do); STF_PREC_FP32: 3xTF32 split of both operands, fp32-grade */
+  int max_ctas;               /* persistent grid size cap (0 = one CTA per SM, 148).  A caller that runs long single-warp */
+                              /* kernels beside this one (the device rANS decoder of other sub-batches) leaves them an SM each: */
+                              /* a persistent CTA needs a whole SM's shared memory and would queue behind them */
 } stf_conv_args;
 /* Floats of the packed weight image: planes * N * Kp + 2 N, Kp = ksize^2 * sum_s ceil32(src_channels[s]). */
 int64_t stf_packed_conv_floats(const stf_conv_args *args);
@@ -401,6 +405,22 @@ int stf_rans_decode(stf_rans_decoder *d, const stf_rans_table *t, const int32_t 
 int stf_rans_decode_batch(stf_rans_decoder *const *d, const stf_rans_table *t, int count,
                           const int32_t *const *indexes, const int64_t *n,
                           int32_t *const *symbols_out, int threads);
+
+/* Device-side decoder for the slice loop of decompress() (stf.py:757-779): RansDecoder.set_stream + decode_stream
+ * (rans_interface.cpp:277-350, rans64.h:107-142) for `count` independent streams, lane b of a warp decoding stream b in
+ * lockstep -- same integers as stf_rans_decode, bit-identical symbols, no host round trip per slice.
+ *   table image: stf_rans_device_table_pack() writes stf_rans_device_table_bytes() bytes into a HOST buffer (row info, 256-bucket
+ *                LUTs, 16-bit CDFs); the caller copies it to the device once; the kernel keeps it in shared memory (<= 200 KB).
+ *   streams:     all streams back to back as 32-bit words (device), stream b = streams[stream_offsets[b] .. + stream_words[b]).
+ *   state:       state_x / state_pos / status [count] (device) carry the decoders between calls; first != 0 initialises them
+ *                from the streams (Rans64DecInit).  status[b]: 0, STF_E_STREAM (truncated stream) or STF_E_ARG (bad index).
+ *   per call:    n symbols per stream; indexes / symbols_out of stream b at + b * batch_stride (int32, device). */
+int64_t stf_rans_device_table_bytes(const stf_rans_table *t);
+int stf_rans_device_table_pack(const stf_rans_table *t, void *host_out);
+int stf_rans_decode_device(const void *table_dev, int64_t table_bytes, const uint32_t *streams, const int64_t *stream_offsets,
+                           const int32_t *stream_words, uint64_t *state_x, uint32_t *state_pos, int32_t *status, int first,
+                           const int32_t *indexes, int64_t idx_batch_stride, int32_t *symbols_out, int64_t sym_batch_stride,
+                           int count, int64_t n, void *stream);
 
 /* compressai._CXX.pmf_to_quantized_cdf (cpp_exts/ops/ops.cpp:24-81): cdf_out has n+1 entries. */
 int stf_pmf_to_quantized_cdf(const float *pmf, int n, int precision, uint32_t *cdf_out);

@@ -35,6 +35,7 @@ class LinearArgs(ctypes.Structure):
         ("rows", c_int), ("has_ln", c_int), ("x_is_tf32", c_int), ("ln_eps", c_f32),
         ("epilogue", c_int), ("residual", c_vp), ("q_cols", c_int), ("q_scale", c_f32),
         ("batch", c_int), ("H", c_int), ("W", c_int), ("window", c_int), ("shift", c_int), ("precision", c_int),
+        ("max_ctas", c_int),
     ]
 
 
@@ -45,7 +46,7 @@ class ConvArgs(ctypes.Structure):
         ("src", c_vp * 3), ("src_channels", c_int * 3), ("src_ld", c_int * 3),
         ("N", c_int), ("ksize", c_int), ("stride", c_int),
         ("w_packed", c_vp), ("y", c_vp), ("ldy", c_int), ("act", c_int), ("residual", c_vp), ("res_ld", c_int),
-        ("pixel_shuffle", c_int), ("has_ln", c_int), ("ln_eps", c_f32), ("precision", c_int),
+        ("pixel_shuffle", c_int), ("has_ln", c_int), ("ln_eps", c_f32), ("precision", c_int), ("max_ctas", c_int),
     ]
 
 
@@ -110,6 +111,10 @@ SIGNATURES = {
     "stf_rans_decode": (c_int, [c_vp, c_vp, c_vp, c_i64, c_vp]),
     "stf_rans_decode_batch": (c_int, [ctypes.POINTER(c_vp), c_vp, c_int, ctypes.POINTER(c_vp), ctypes.POINTER(c_i64),
                                       ctypes.POINTER(c_vp), c_int]),
+    "stf_rans_device_table_bytes": (c_i64, [c_vp]),
+    "stf_rans_device_table_pack": (c_int, [c_vp, c_vp]),
+    "stf_rans_decode_device": (c_int, [c_vp, c_i64, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_int, c_vp, c_i64, c_vp, c_i64, c_int,
+                                       c_i64, c_vp]),
     "stf_pmf_to_quantized_cdf": (c_int, [_f32p, c_int, c_int, ctypes.POINTER(ctypes.c_uint32)]),
 }
 

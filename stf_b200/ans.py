@@ -50,6 +50,21 @@ class RansTable:
         if h:
             self._destroy(h)
 
+    def device_image(self, device):
+        """The table packed for the device decoder (stf_rans_device_table_pack) as a CUDA uint8 tensor, cached per device."""
+        import torch
+        cache = self.__dict__.setdefault("_dev_images", {})
+        key = str(device)
+        if key not in cache:
+            L = _C.lib()
+            nbytes = int(L.stf_rans_device_table_bytes(self._h))
+            if nbytes <= 0:
+                _C.check(nbytes, "stf_rans_device_table_bytes")
+            host = np.zeros(nbytes, dtype=np.uint8)
+            _C.check(L.stf_rans_device_table_pack(self._h, host.ctypes.data), "stf_rans_device_table_pack")
+            cache[key] = torch.from_numpy(host).to(device)
+        return cache[key]
+
 
 def _table(cdfs, sizes, offsets):
     return cdfs if isinstance(cdfs, RansTable) else RansTable(cdfs, sizes, offsets)
@@ -230,3 +245,53 @@ def pmf_to_quantized_cdf(pmf, precision: int = 16):
                                            out.ctypes.data_as(ctypes.POINTER(ctypes.c_uint32)))
     _C.check(rc, "stf_pmf_to_quantized_cdf")
     return out.tolist()
+
+
+class DeviceStreams:
+    """The y-strings of one sub-batch staged for the device decoder: all streams back to back in ONE pinned host buffer of
+    fixed capacity (so that a CUDA graph can hold its device copy), word offsets / lengths, and the per-stream decoder state.
+    `load(strings)` refills the staging buffers (host side only); the H2D copies are issued by the caller's captured graph
+    or eagerly through `upload()`."""
+
+    def __init__(self, count, capacity_words, device):
+        import torch
+        self.count, self.capacity = int(count), int(capacity_words)
+        self.words_h = torch.empty(self.capacity, dtype=torch.int32, pin_memory=True)
+        self.meta_h = torch.empty((2, self.count), dtype=torch.int64, pin_memory=True)   # [0] offsets, [1] lengths
+        self.words = torch.empty(self.capacity, dtype=torch.int32, device=device)
+        self.meta = torch.empty((2, self.count), dtype=torch.int64, device=device)
+        self.lengths32 = torch.empty(self.count, dtype=torch.int32, device=device)
+        self.state_x = torch.zeros(self.count, dtype=torch.int64, device=device)
+        self.state_pos = torch.zeros(self.count, dtype=torch.int32, device=device)
+        self.status = torch.zeros(self.count, dtype=torch.int32, device=device)
+
+    def fits(self, strings):
+        return len(strings) == self.count and sum(len(s) for s in strings) // 4 + 2 * len(strings) <= self.capacity and \
+            all(len(s) % 4 == 0 and len(s) >= 8 for s in strings)
+
+    def load(self, strings):
+        wh, off = self.words_h.numpy(), 0
+        for b, s in enumerate(strings):
+            nw = len(s) // 4
+            wh[off:off + nw] = np.frombuffer(s, dtype=np.int32)
+            self.meta_h[0, b], self.meta_h[1, b] = off, nw
+            off += nw
+        self.used_words = off
+
+    def upload(self):
+        """H2D of the staged streams (stream-ordered on the current stream; capturable)."""
+        self.words.copy_(self.words_h, non_blocking=True)
+        self.meta.copy_(self.meta_h, non_blocking=True)
+        self.lengths32.copy_(self.meta[1])
+
+
+def decode_device(table: RansTable, ds: DeviceStreams, indexes, symbols_out, first):
+    """Advance the sub-batch's decoders by one slice on the device: indexes / symbols_out are (count, n) int32 CUDA tensors
+    (row b = stream b).  No host synchronisation; check ds.status after the last slice."""
+    from . import ops
+    img = table.device_image(indexes.device)
+    count, n = indexes.shape
+    ops._launch("rans_decode_kernel", 8 * count * n, _C.lib().stf_rans_decode_device, img.data_ptr(), img.numel(),
+                ds.words.data_ptr(), ds.meta[0].data_ptr(), ds.lengths32.data_ptr(), ds.state_x.data_ptr(),
+                ds.state_pos.data_ptr(), ds.status.data_ptr(), int(bool(first)), indexes.data_ptr(), indexes.stride(0),
+                symbols_out.data_ptr(), symbols_out.stride(0), count, n, _C.stream())

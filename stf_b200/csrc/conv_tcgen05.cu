@@ -956,7 +956,8 @@ extern "C" int stf_conv2d(const stf_conv_args *a, void *stream) {
   P.debug = dbg;
   const size_t fixed = small + (size_t)kEpiWarps * slabs * kSlabBytes;
   const size_t smem = fixed + ring_bytes;
-  const int grid = P.total_tiles < kNumSMs ? P.total_tiles : kNumSMs;
+  const int sms = a->max_ctas > 0 && a->max_ctas < kNumSMs ? a->max_ctas : kNumSMs;
+  const int grid = P.total_tiles < sms ? P.total_tiles : sms;
   auto kern = halo ? (precise ? conv_tf32_kernel<1, 0, 1> : conv_tf32_kernel<0, 0, 1>)
                    : precise ? (P.has_ln ? conv_tf32_kernel<1, 1, 0> : conv_tf32_kernel<1, 0, 0>)
                              : (P.has_ln ? conv_tf32_kernel<0, 1, 0> : conv_tf32_kernel<0, 0, 0>);

@@ -1053,7 +1053,8 @@ int launch_linear(const stf_linear_args *args, void *stream) {
     cudaError_t e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);  // idempotent, cheap
     if (e != cudaSuccess) return (int)e;
   }
-  int grid = P.total_tiles < kNumSMs ? P.total_tiles : kNumSMs;
+  const int sms = P.a.max_ctas > 0 && P.a.max_ctas < kNumSMs ? P.a.max_ctas : kNumSMs;
+  int grid = P.total_tiles < sms ? P.total_tiles : sms;
   if (P.pair) {
     const int pairs = P.total_tiles < kNumSMs / 2 ? P.total_tiles : kNumSMs / 2;   // total_tiles counts super tiles here
     grid = 2 * pairs;

@@ -11,7 +11,8 @@
 //   - int32 buffers in, bytes out: no Python lists, no per-call conversion of the 64x3133 table;
 //   - the encoder walks the symbols backwards and emits directly (no staged symbol vector);
 //   - x / freq is an exact multiply-shift with a per-symbol 64-bit reciprocal;
-//   - the decoder finds the symbol through a 256-bucket LUT per CDF row instead of a linear scan;
+//   - the decoder finds the symbol through a bucket LUT per CDF row (256 or 4096 buckets) instead of a linear scan;
+//   - renormalisation is branch-free on high-entropy runs (chosen per run, see kLutBitsWide);
 //   - independent streams (one per image) are coded on separate host threads.
 #include <stdlib.h>
 #include <string.h>
@@ -33,7 +34,14 @@ constexpr uint32_t kProbScale = 1u << kProbBits;
 constexpr uint32_t kNibbleBits = 4;
 constexpr int32_t kNibbleMax = 15;
 constexpr uint64_t kLow = 1ull << 31;  // RANS64_L
-constexpr int kLutBits = 8;
+// Decoder LUT resolution per CDF row: 256 buckets for rows of up to 256 symbols, 4096 for wider ones (16 cumulative counts
+// per bucket: the widest row of the scale table, 3133 symbols, then has < 1 symbol per bucket; with 256 buckets the scan behind
+// the LUT took ~6 dependent steps there and the decoder ran at 23 ns per symbol instead of 6).  Wide rows are also the
+// high-entropy ones (~log2(4.1 sigma) bits per symbol), where "does the state renormalise" is a coin flip: they take the
+// branch-free step, narrow rows the branchy one (well predicted there, and speculation past a predicted branch is cheaper
+// than a select in the dependency chain: 2.8 vs 4.2 ns per symbol at 0.3 bits per symbol).
+constexpr int kLutBitsNarrow = 8, kLutBitsWide = 12;
+constexpr int kWideRow = 40;   // symbols: sigma ~ 3, ~3.6 bits per symbol (below it the branchy decoder wins, at it they tie)
 // images one thread codes in lockstep (env STF_B200_RANS_LOCKSTEP, 1..8)
 static const int kMaxLockstep = [] {
   const char *e = getenv("STF_B200_RANS_LOCKSTEP");
@@ -41,13 +49,15 @@ static const int kMaxLockstep = [] {
   return v < 1 ? 1 : (v > 8 ? 8 : v);
 }();
 
-struct EncEntry {
-  uint64_t rcp;       // ceil(2^(63+shift) / freq), freq >= 2
-  uint32_t x_max_hi;  // renormalise when (x >> 47) >= freq  <=>  x >= 2^47 * freq
-  uint32_t start;
-  uint32_t cmpl;      // 65536 - freq
-  uint32_t shift;     // ceil(log2 freq) - 1; 0xFFFFFFFF marks freq == 1
+struct EncEntry {    // 16 bytes: the widest row (3133 symbols) is 50 KB, about one L1
+  uint64_t rcp;       // freq >= 2: ceil(2^(63+shift) / freq), so that x / freq == mulhi(x, rcp) >> shift exactly;
+                      // freq == 1: 2^64 - 1 with shift 0, so that the "quotient" is x - 1 (made up for by `bias`)
+  uint32_t bias;      // start (freq >= 2);  start + 65535 (freq == 1):  x + bias + (x - 1) * 65535 == x * 65536 + start
+  uint16_t cmpl;      // 65536 - freq (freq >= 1); the renormalisation bound is x >= 2^47 * freq <=> (x >> 47) >= 65536 - cmpl
+  uint8_t shift;      // ceil(log2 freq) - 1
+  uint8_t pad;
 };
+static_assert(sizeof(EncEntry) == 16, "EncEntry layout");
 
 }  // namespace
 
@@ -58,10 +68,13 @@ struct stf_rans_table {
   std::vector<EncEntry> enc;    // one per (row, symbol)
   std::vector<uint32_t> cdf;    // flattened valid CDF entries, row r: cdf[base[r] + r .. + sizes[r])
   std::vector<uint32_t> cbase;  // first cdf entry of each row
-  std::vector<uint16_t> lut;    // rows * 256: symbol holding cumulative value (bucket << 8)
+  // symbol holding cumulative value (bucket << (16 - bits)), per row: 256 buckets for the branchy step (5 KB per ten rows:
+  // stays in L1 when a run uses a handful of narrow rows), 4096 for the branch-free one (see kLutBitsWide)
+  std::vector<uint16_t> lut_narrow, lut_wide;
   struct Row {                  // everything a coding step needs to know about a CDF row, one 16-byte load
     int32_t offset, escape;     // symbol offset; escape symbol = size - 2
-    uint32_t base, cbase;       // first enc entry / first cdf entry of the row
+    uint32_t base;              // first enc entry of the row; its first cdf entry is base + row
+    uint32_t wide;              // 1: more than kWideRow symbols
   };
   std::vector<Row> row;
 };
@@ -75,33 +88,43 @@ struct stf_rans_decoder {
 namespace {
 
 inline void make_entry(EncEntry *e, uint32_t start, uint32_t freq) {
-  e->start = start;
-  e->cmpl = kProbScale - freq;
-  e->x_max_hi = freq;
+  e->cmpl = (uint16_t)(kProbScale - freq);
+  e->pad = 0;
   if (freq < 2) {
-    e->rcp = 0;
-    e->shift = 0xFFFFFFFFu;
+    e->rcp = ~0ull;
+    e->bias = start + kProbScale - 1;
+    e->shift = 0;
     return;
   }
   uint32_t sh = 0;
   while (freq > (1u << sh)) ++sh;  // sh = ceil(log2 freq) >= 1
   unsigned __int128 num = ((unsigned __int128)1 << (63 + sh)) + (freq - 1);
   e->rcp = (uint64_t)(num / freq);
-  e->shift = sh - 1;
+  e->bias = start;
+  e->shift = (uint8_t)(sh - 1);
 }
 
 // x <- C(s, x) for a modelled symbol; identical state sequence to Rans64EncPut (rans64.h:77-93).
+// Branch-free: whether a state renormalises (about every third symbol at 10 bits per symbol) is not predictable, and a
+// mispredicted branch costs more than the whole step.  The word is stored unconditionally below the write pointer, which
+// only moves when the store was real (the buffer bound, 8 bytes per symbol, always leaves that word free).
+template <bool kBranchFree>
 inline void put_symbol(uint64_t &x, uint32_t *&w, const EncEntry &e) {
-  if ((x >> 47) >= e.x_max_hi) {  // x >= ((L >> 16) << 32) * freq
-    *--w = (uint32_t)x;
-    x >>= 32;
+  if (!kBranchFree) {
+    if ((x >> 47) >= kProbScale - (uint32_t)e.cmpl) {
+      *--w = (uint32_t)x;
+      x >>= 32;
+    }
+    const uint64_t q = (uint64_t)(((unsigned __int128)x * e.rcp) >> 64) >> e.shift;
+    x = x + e.bias + q * e.cmpl;
+    return;
   }
-  uint64_t q;
-  if (e.shift == 0xFFFFFFFFu)
-    q = x;
-  else
-    q = (uint64_t)(((unsigned __int128)x * e.rcp) >> 64) >> e.shift;
-  x = x + e.start + q * e.cmpl;
+  const uint64_t need = (uint64_t)((x >> 47) >= kProbScale - (uint32_t)e.cmpl);  // x >= ((L >> 16) << 32) * freq
+  w[-1] = (uint32_t)x;
+  w -= need;
+  x >>= (need << 5);
+  const uint64_t q = (uint64_t)(((unsigned __int128)x * e.rcp) >> 64) >> e.shift;
+  x = x + e.bias + q * e.cmpl;
 }
 
 // Raw 4-bit value (Rans64EncPutBits, rans_interface.cpp:59-77): freq = 2^12, x_max = 2^59.
@@ -114,13 +137,14 @@ inline void put_nibble(uint64_t &x, uint32_t *&w, uint32_t val) {
 }
 
 // One symbol of one stream (returns false on an out-of-range index).
+template <bool kBranchFree>
 inline bool encode_step(const stf_rans_table *t, int32_t sym, int32_t row, uint64_t &x, uint32_t *&w) {
   if ((uint32_t)row >= (uint32_t)t->rows) return false;
   const stf_rans_table::Row ri = t->row[row];
   const int32_t escape = ri.escape;
   int32_t v = sym - ri.offset;
   if ((uint32_t)v < (uint32_t)escape) {
-    put_symbol(x, w, t->enc[ri.base + v]);
+    put_symbol<kBranchFree>(x, w, t->enc[ri.base + v]);
     return true;
   }
   // escape: staged order is [escape symbol][count nibbles][value nibbles]; emit it reversed
@@ -131,7 +155,7 @@ inline bool encode_step(const stf_rans_table *t, int32_t sym, int32_t row, uint6
   int32_t full = nn / kNibbleMax, rest = nn % kNibbleMax;  // count = 15,15,...,rest
   put_nibble(x, w, (uint32_t)rest);
   for (int32_t j = 0; j < full; ++j) put_nibble(x, w, kNibbleMax);
-  put_symbol(x, w, t->enc[ri.base + escape]);
+  put_symbol<false>(x, w, t->enc[ri.base + escape]);
   return true;
 }
 
@@ -141,21 +165,40 @@ inline int64_t encode_finish(uint64_t x, uint32_t *w, uint32_t *buf_end) {
   return (int64_t)(buf_end - w) * 4;
 }
 
-int64_t encode_into(const stf_rans_table *t, const int32_t *symbols, const int32_t *indexes, int64_t n,
-                    uint32_t *buf_end) {
+// Does a run of n symbols mostly use wide (high-entropy) rows?  64 evenly spaced samples.
+inline bool wide_run(const stf_rans_table *t, const int32_t *indexes, int64_t n) {
+  if (n <= 0) return false;
+  const int64_t stride = n / 64 > 0 ? n / 64 : 1;
+  int wide = 0, seen = 0;
+  for (int64_t i = 0; i < n && seen < 64; i += stride, ++seen) {
+    const int32_t row = indexes[i];
+    if ((uint32_t)row < (uint32_t)t->rows) wide += (int)t->row[row].wide;
+  }
+  return 4 * wide >= seen;
+}
+
+template <bool kBranchFree>
+__attribute__((noinline)) int64_t encode_into_impl(const stf_rans_table *t, const int32_t *symbols, const int32_t *indexes, int64_t n,
+                         uint32_t *buf_end) {
   uint32_t *w = buf_end;
   uint64_t x = kLow;
   for (int64_t i = n - 1; i >= 0; --i)
-    if (!encode_step(t, symbols[i], indexes[i], x, w)) return STF_E_ARG;
+    if (!encode_step<kBranchFree>(t, symbols[i], indexes[i], x, w)) return STF_E_ARG;
   return encode_finish(x, w, buf_end);
+}
+
+int64_t encode_into(const stf_rans_table *t, const int32_t *symbols, const int32_t *indexes, int64_t n,
+                    uint32_t *buf_end) {
+  return wide_run(t, indexes, n) ? encode_into_impl<true>(t, symbols, indexes, n, buf_end)
+                                 : encode_into_impl<false>(t, symbols, indexes, n, buf_end);
 }
 
 // W independent streams in lockstep: a stream is one serial dependency chain (state -> multiply-high -> state, ~15 cycles
 // per symbol), so a thread that owns W images interleaves them and the core overlaps the W chains (W = 2 or 4; with eight
 // ranks sharing a host each rank has a handful of threads for 21+ images).  Same bytes as W encode_into calls.
-template <int W>
-void encode_intoW(const stf_rans_table *t, const int32_t *const *sym, const int32_t *const *idx, const int64_t *n,
-                  uint32_t *const *buf_end, int64_t *nb) {
+template <int W, bool kBranchFree>
+__attribute__((noinline)) void encode_intoW_impl(const stf_rans_table *t, const int32_t *const *sym, const int32_t *const *idx, const int64_t *n,
+                       uint32_t *const *buf_end, int64_t *nb) {
   uint32_t *w[W];
   uint64_t x[W];
   int64_t i[W];
@@ -168,53 +211,88 @@ void encode_intoW(const stf_rans_table *t, const int32_t *const *sym, const int3
   for (int64_t step = 0; ok && step < common; ++step) {
 #pragma GCC unroll 8
     for (int k = 0; k < W; ++k) {
-      ok = encode_step(t, sym[k][i[k]], idx[k][i[k]], x[k], w[k]) && ok;
+      ok = encode_step<kBranchFree>(t, sym[k][i[k]], idx[k][i[k]], x[k], w[k]) && ok;
       --i[k];
     }
   }
   for (int k = 0; k < W; ++k)
-    for (; ok && i[k] >= 0; --i[k]) ok = encode_step(t, sym[k][i[k]], idx[k][i[k]], x[k], w[k]);
+    for (; ok && i[k] >= 0; --i[k]) ok = encode_step<kBranchFree>(t, sym[k][i[k]], idx[k][i[k]], x[k], w[k]);
   for (int k = 0; k < W; ++k) nb[k] = ok ? encode_finish(x[k], w[k], buf_end[k]) : (int64_t)STF_E_ARG;
 }
 
-inline bool refill(stf_rans_decoder *d, uint64_t &x) {
-  if (x < kLow) {
-    if (d->w >= d->end) return false;
-    x = (x << 32) | *d->w++;
+template <int W>
+void encode_intoW(const stf_rans_table *t, const int32_t *const *sym, const int32_t *const *idx, const int64_t *n,
+                  uint32_t *const *buf_end, int64_t *nb) {
+  if (wide_run(t, idx[0], n[0])) encode_intoW_impl<W, true>(t, sym, idx, n, buf_end, nb);
+  else encode_intoW_impl<W, false>(t, sym, idx, n, buf_end, nb);
+}
+
+// Decoder position kept in registers while a run is in flight (the decoder object is only read at the start of a run and
+// written back at its end).
+struct Cursor {
+  uint64_t x;
+  const uint32_t *w, *end;
+};
+
+inline bool refill(Cursor &c) {   // branchy form, for the rare paths (escape nibbles)
+  if (c.x < kLow) {
+    if (c.w >= c.end) return false;
+    c.x = (c.x << 32) | *c.w++;
   }
   return true;
 }
 
-inline bool get_nibble(stf_rans_decoder *d, uint64_t &x, int32_t *val) {
-  *val = (int32_t)(x & ((1u << kNibbleBits) - 1));
-  x >>= kNibbleBits;
-  return refill(d, x);
+inline bool get_nibble(Cursor &c, int32_t *val) {
+  *val = (int32_t)(c.x & ((1u << kNibbleBits) - 1));
+  c.x >>= kNibbleBits;
+  return refill(c);
 }
 
-// One symbol of one stream.
-inline int decode_step(stf_rans_decoder *d, const stf_rans_table *t, int32_t row, uint64_t &x, int32_t *out) {
+// One symbol of one stream.  The two data-dependent decisions of a step -- does the bucket's first symbol already hold
+// `cum`, does the state need a new word -- are taken without branches (at ~10 bits per symbol both are coin flips); only
+// the rare cases (a third symbol in a 16-count bucket, stream exhausted, escape) branch.
+template <bool kBranchFree>
+inline int decode_step(Cursor &c, const stf_rans_table *t, int32_t row, int32_t *out) {
   if ((uint32_t)row >= (uint32_t)t->rows) return STF_E_ARG;
   const stf_rans_table::Row ri = t->row[row];
-  const uint32_t *cdf = t->cdf.data() + ri.cbase;
+  const uint32_t *cdf = t->cdf.data() + ri.base + (uint32_t)row;
   const int32_t escape = ri.escape;
+  const uint64_t x = c.x;
   const uint32_t cum = (uint32_t)x & (kProbScale - 1);
-  uint32_t s = t->lut[(size_t)row * (1 << kLutBits) + (cum >> (kProbBits - kLutBits))];
-  while (cdf[s + 1] <= cum) ++s;
-  const uint32_t start = cdf[s], freq = cdf[s + 1] - start;
-  x = freq * (x >> kProbBits) + cum - start;  // Rans64DecAdvance, rans64.h:126-142
-  if (!refill(d, x)) return STF_E_STREAM;
+  uint32_t s;
+  if (kBranchFree) {
+    s = t->lut_wide[((size_t)row << kLutBitsWide) + (cum >> (kProbBits - kLutBitsWide))];
+    s += (uint32_t)(cdf[s + 1] <= cum);
+    while (cdf[s + 1] <= cum) ++s;
+    const uint32_t start = cdf[s], freq = cdf[s + 1] - start;
+    uint64_t nx = freq * (x >> kProbBits) + cum - start;  // Rans64DecAdvance, rans64.h:126-142
+    const uint64_t need = (uint64_t)(nx < kLow);            // Rans64DecRenorm
+    const bool have = c.w < c.end;
+    if (need && !have) return STF_E_STREAM;
+    const uint64_t word = have ? *c.w : 0u;
+    const uint64_t mask = 0 - need;
+    nx = ((nx << (need << 5)) | (word & mask));
+    c.w += need;
+    c.x = nx;
+  } else {
+    s = t->lut_narrow[((size_t)row << kLutBitsNarrow) + (cum >> (kProbBits - kLutBitsNarrow))];
+    while (cdf[s + 1] <= cum) ++s;
+    const uint32_t start = cdf[s], freq = cdf[s + 1] - start;
+    c.x = freq * (x >> kProbBits) + cum - start;
+    if (!refill(c)) return STF_E_STREAM;
+  }
   int32_t v = (int32_t)s;
   if (v == escape) {  // rans_interface.cpp:320-343
     int32_t nib, nn;
-    if (!get_nibble(d, x, &nib)) return STF_E_STREAM;
+    if (!get_nibble(c, &nib)) return STF_E_STREAM;
     nn = nib;
     while (nib == kNibbleMax) {
-      if (!get_nibble(d, x, &nib)) return STF_E_STREAM;
+      if (!get_nibble(c, &nib)) return STF_E_STREAM;
       nn += nib;
     }
     int32_t raw = 0;
     for (int32_t j = 0; j < nn; ++j) {
-      if (!get_nibble(d, x, &nib)) return STF_E_STREAM;
+      if (!get_nibble(c, &nib)) return STF_E_STREAM;
       if (j < 8) raw |= nib << (j * kNibbleBits);
     }
     v = raw >> 1;
@@ -224,25 +302,30 @@ inline int decode_step(stf_rans_decoder *d, const stf_rans_table *t, int32_t row
   return STF_OK;
 }
 
-int decode_run(stf_rans_decoder *d, const stf_rans_table *t, const int32_t *indexes, int64_t n, int32_t *out) {
-  uint64_t x = d->x;
+template <bool kBranchFree>
+__attribute__((noinline)) int decode_run_impl(stf_rans_decoder *d, const stf_rans_table *t, const int32_t *indexes, int64_t n, int32_t *out) {
+  Cursor c{d->x, d->w, d->end};
   for (int64_t i = 0; i < n; ++i) {
-    const int rc = decode_step(d, t, indexes[i], x, out + i);
+    const int rc = decode_step<kBranchFree>(c, t, indexes[i], out + i);
     if (rc) return rc;
   }
-  d->x = x;
+  d->x = c.x, d->w = c.w;
   return STF_OK;
 }
 
+int decode_run(stf_rans_decoder *d, const stf_rans_table *t, const int32_t *indexes, int64_t n, int32_t *out) {
+  return wide_run(t, indexes, n) ? decode_run_impl<true>(d, t, indexes, n, out) : decode_run_impl<false>(d, t, indexes, n, out);
+}
+
 // W decoders in lockstep (see encode_intoW).
-template <int W>
-void decode_runW(stf_rans_decoder *const *d, const stf_rans_table *t, const int32_t *const *idx, const int64_t *n,
-                 int32_t *const *out, int *rc_out) {
-  uint64_t x[W];
+template <int W, bool kBranchFree>
+__attribute__((noinline)) void decode_runW_impl(stf_rans_decoder *const *d, const stf_rans_table *t, const int32_t *const *idx, const int64_t *n,
+                      int32_t *const *out, int *rc_out) {
+  Cursor c[W];
   int rc[W];   // local: the caller's status array is shared between threads (one cache line for several groups)
   int64_t m = n[0];
   for (int k = 0; k < W; ++k) {
-    x[k] = d[k]->x, rc[k] = STF_OK;
+    c[k] = Cursor{d[k]->x, d[k]->w, d[k]->end}, rc[k] = STF_OK;
     if (n[k] < m) m = n[k];
   }
   int64_t i = 0;
@@ -250,16 +333,23 @@ void decode_runW(stf_rans_decoder *const *d, const stf_rans_table *t, const int3
   for (; i < m && !any; ++i) {
 #pragma GCC unroll 8
     for (int k = 0; k < W; ++k) {
-      rc[k] = decode_step(d[k], t, idx[k][i], x[k], out[k] + i);
+      rc[k] = decode_step<kBranchFree>(c[k], t, idx[k][i], out[k] + i);
       any |= rc[k];
     }
   }
   if (!any)
     for (int k = 0; k < W; ++k) {
-      for (int64_t j = i; j < n[k] && !rc[k]; ++j) rc[k] = decode_step(d[k], t, idx[k][j], x[k], out[k] + j);
-      if (!rc[k]) d[k]->x = x[k];
+      for (int64_t j = i; j < n[k] && !rc[k]; ++j) rc[k] = decode_step<kBranchFree>(c[k], t, idx[k][j], out[k] + j);
+      if (!rc[k]) d[k]->x = c[k].x, d[k]->w = c[k].w;
     }
   for (int k = 0; k < W; ++k) rc_out[k] = rc[k];
+}
+
+template <int W>
+void decode_runW(stf_rans_decoder *const *d, const stf_rans_table *t, const int32_t *const *idx, const int64_t *n,
+                 int32_t *const *out, int *rc_out) {
+  if (wide_run(t, idx[0], n[0])) decode_runW_impl<W, true>(d, t, idx, n, out, rc_out);
+  else decode_runW_impl<W, false>(d, t, idx, n, out, rc_out);
 }
 
 // Persistent worker pool: decode_batch is called once per slice (12-13 times per image batch), so
@@ -369,7 +459,6 @@ extern "C" stf_rans_table *stf_rans_table_create(const int32_t *cdf, int rows, i
   t->offsets.assign(offsets, offsets + rows);
   t->base.resize(rows);
   t->cbase.resize(rows);
-  t->lut.assign((size_t)rows << kLutBits, 0);
   for (int r = 0; r < rows; ++r) {
     const int32_t *c = cdf + (size_t)r * row_stride;
     const int sz = sizes[r];
@@ -381,24 +470,37 @@ extern "C" stf_rans_table *stf_rans_table_create(const int32_t *cdf, int rows, i
     }
     t->base[r] = (uint32_t)t->enc.size();
     t->cbase[r] = (uint32_t)t->cdf.size();
-    t->row.push_back({offsets[r], sz - 2, t->base[r], t->cbase[r]});
+    t->row.push_back({offsets[r], sz - 2, t->base[r], sz - 1 > kWideRow ? 1u : 0u});
     for (int j = 0; j < sz; ++j) t->cdf.push_back((uint32_t)c[j]);
     for (int j = 0; j + 1 < sz; ++j) {
       EncEntry e;
       make_entry(&e, (uint32_t)c[j], (uint32_t)(c[j + 1] - c[j]));
       t->enc.push_back(e);
     }
-    uint32_t s = 0;
-    for (uint32_t b = 0; b < (1u << kLutBits); ++b) {
-      const uint32_t cum = b << (kProbBits - kLutBits);
-      while ((uint32_t)c[s + 1] <= cum) ++s;
-      t->lut[((size_t)r << kLutBits) + b] = (uint16_t)s;
+    for (int pass = 0; pass < 2; ++pass) {
+      const int bits = pass ? kLutBitsWide : kLutBitsNarrow;
+      std::vector<uint16_t> &lut = pass ? t->lut_wide : t->lut_narrow;
+      lut.resize(((size_t)r + 1) << bits);
+      uint32_t s = 0;
+      for (uint32_t b = 0; b < (1u << bits); ++b) {
+        const uint32_t cum = b << (kProbBits - bits);
+        while ((uint32_t)c[s + 1] <= cum) ++s;
+        lut[((size_t)r << bits) + b] = (uint16_t)s;
+      }
     }
   }
   return t;
 }
 
 extern "C" void stf_rans_table_destroy(stf_rans_table *t) { delete t; }
+
+// (library-internal) read access for the device-table packer in csrc/rans_device.cu
+extern "C" int stf_rans_table_export(const stf_rans_table *t, int *rows, const int32_t **sizes, const int32_t **offsets,
+                                     const uint32_t **cdf, const uint32_t **cbase) {
+  if (!t) return STF_E_ARG;
+  *rows = t->rows, *sizes = t->sizes.data(), *offsets = t->offsets.data(), *cdf = t->cdf.data(), *cbase = t->cbase.data();
+  return STF_OK;
+}
 
 extern "C" int64_t stf_rans_encode_bound(int64_t n) { return n < 0 ? STF_E_ARG : 8 * n + 64; }
 

@@ -48,6 +48,9 @@ _EB_MEDIAN = _C.STF_EB_MEDIAN_SLOT
 _PIPELINE_MIN_BATCH = int(os.environ.get("STF_B200_PIPELINE_MIN_BATCH", "16"))
 _PIPELINE_PARTS = int(os.environ.get("STF_B200_PIPELINE_PARTS", "0"))   # 0 = auto: 3 sub-batches from 48 images, else 2
 _DEC_PARTS = int(os.environ.get("STF_B200_DEC_PARTS", "0")) or None     # decompress(): sub-batches (default: same as compress)
+# decompress(): rANS decoding of the y-strings on the device (one warp lane per image, no host round trip per slice) instead of
+# the host thread pool: "1" / "0", default "1"
+_DEVICE_DECODE = os.environ.get("STF_B200_DEVICE_DECODE", "0") != "0"
 _PART_TAPER = float(os.environ.get("STF_B200_PART_TAPER", "0.75"))    # size of the last sub-batch relative to the first
 _DEC_LEAD = int(os.environ.get("STF_B200_DEC_LEAD", "3"))               # decompress(): slices a sub-batch may lead the next one by
 PHASE_TIMES = None   # set to a dict to collect a synchronised wall-clock breakdown (tools/phase_breakdown.py)
@@ -627,6 +630,10 @@ class _SliceCodec(CompressionModel):
         S = self.num_slices
         main = torch.cuda.current_stream()
         use_graphs = self._graphs_enabled()
+        if _DEVICE_DECODE and PHASE_TIMES is None:
+            out = self._decompress_device(strings, B, C, zh, zw, device, use_graphs)
+            if out is not None:
+                return out
 
         class Part:
             pass
@@ -703,6 +710,84 @@ class _SliceCodec(CompressionModel):
         for p in parts:
             main.wait_stream(p.stream)
         x_hat = torch.cat(outs, dim=0) if (len(outs) > 1 or use_graphs) else outs[0]
+        return {"x_hat": x_hat}
+
+
+    # ------------------------------------------------------------------ decoder, rANS on the device
+    def _dec_all(self, st, ds, z_sym, reserve_sms=0):
+        """The whole decode of one sub-batch with NO host round trip: hyper-synthesis, then per slice parameters -> indexes
+        -> device rANS decode (lane b of one warp = image b) -> y_hat + LRP, then the synthesis transform.  The persistent
+        kernels leave `reserve_sms` SMs to the decoding warps of the sub-batches that run beside this one."""
+        y_table = self.gaussian_conditional.rans_table()
+        old_cap, ops.MAX_CTAS = ops.MAX_CTAS, ops.NUM_SMS - reserve_sms     # (baked into the captured launches)
+        try:
+            ds.upload()
+            idx = self._dec_first(st, z_sym)
+            for i in range(1, self.num_slices + 1):
+                sym = torch.empty_like(idx)
+                ans.decode_device(y_table, ds, idx, sym, first=(i == 1))
+                if i < self.num_slices:
+                    idx = self._dec_mid(st, i, sym)
+                else:
+                    return self._dec_last(st, sym), ds.status
+        finally:
+            ops.MAX_CTAS = old_cap
+
+    def _decompress_device(self, strings, B, C, zh, zw, device, use_graphs):
+        """decompress() with the y-strings decoded on the device.  Every sub-batch is ONE CUDA graph on its own stream (z is
+        decoded on the host first: 18 k symbols per image); the single decoding warp of a sub-batch runs concurrently with
+        the other sub-batches' convolutions, and no host thread is needed during the slice loop -- which is what bounded
+        the 8-GPU runs (4 host threads per rank).  Returns None when the strings do not fit the staging buffers of the cached
+        plan shape (the caller then takes the host path)."""
+        eb = self.entropy_bottleneck
+        z_table = eb.rans_table()
+        main = torch.cuda.current_stream()
+        plans = self._plans("_dec_plans")
+        streams = self.__dict__.setdefault("_part_streams", {})
+        jobs = []
+        part_list = self._parts(B, use_graphs, _DEC_PARTS)
+        reserve = len(part_list) if len(part_list) > 1 else 0
+        for slot, (lo, hi) in enumerate(part_list):
+            ys = strings[0][lo:hi]
+            if any(len(s_) % 4 or len(s_) < 8 for s_ in ys):
+                return None
+            Bp = hi - lo
+            need = sum(len(s_) for s_ in ys) // 4
+            cap = 1 << max(16, (need + need // 4).bit_length())          # words: next power of two above 1.25 x this call
+            key = ("dev", slot, Bp, zh, zw, cap, reserve)
+            if not self._plan_slot(plans, key, 12):
+                st = {"hw": (zh * 4, zw * 4)}
+                ds = ans.DeviceStreams(Bp, cap, device)
+                seg = None
+                if use_graphs:
+                    ds.load(ys)
+                    z0 = torch.zeros((Bp, C, zh, zw), dtype=torch.int32, device=device)
+                    seg = graphs.Segment(lambda t, st=st, ds=ds: self._dec_all(st, ds, t, reserve), [z0])
+                plans[key] = (seg, st, ds)
+            seg, st, ds = plans[key]
+            ds.load(ys)
+            zsym_h, _ = self._host_buffers(("z", slot), Bp, C * zh * zw)
+            z_np = zsym_h.numpy()
+            z_idx = self._z_indexes((Bp, C, zh, zw))
+            ans.decode_batch(_decoders(strings[1][lo:hi]), z_table, [z_idx[b] for b in range(Bp)],
+                             outs=[z_np[b] for b in range(Bp)])
+            stream = streams.setdefault((str(device), slot), torch.cuda.Stream(device=device)) if use_graphs else main
+            stream.wait_stream(main)
+            with torch.cuda.stream(stream):
+                z_in = zsym_h.reshape(Bp, C, zh, zw)
+                out, status = seg(z_in) if seg is not None else self._dec_all(st, ds, z_in.to(device, non_blocking=True), reserve)
+                status_h = self.__dict__.setdefault("_dec_status", {}).setdefault(
+                    (slot, Bp), torch.empty(Bp, dtype=torch.int32, pin_memory=True))
+                status_h.copy_(status, non_blocking=True)
+            jobs.append((stream, out, status_h))
+        for stream, _, _ in jobs:
+            main.wait_stream(stream)
+        x_hat = torch.cat([o for _, o, _ in jobs], dim=0) if (len(jobs) > 1 or use_graphs) else jobs[0][1]
+        main.synchronize()
+        for _, _, status_h in jobs:
+            bad = int(status_h.min())
+            if bad != 0:
+                raise ValueError("corrupt or truncated y bitstream" if bad == -6 else f"rANS device decoder failed ({bad})")
         return {"x_hat": x_hat}
 
 

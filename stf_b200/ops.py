@@ -324,6 +324,7 @@ def linear(x, lin, *, M=None, rows=_C.ROWS_DENSE, epilogue=_C.EPI_STORE, residua
     a.has_ln, a.ln_eps = int(lin.has_ln), lin.ln_eps
     a.x_is_tf32 = int(bool(x_is_tf32)) if lin.precision == _C.PREC_TF32 else 0
     a.precision = lin.precision
+    a.max_ctas = MAX_CTAS
     a.epilogue = epilogue
     if residual is not None:
         residual = _dev(residual, "residual")
@@ -375,6 +376,11 @@ _conv_precision = _PRECISIONS[os.environ.get("STF_B200_CONV_PRECISION", "tf32").
 # Linear layers of the Swin blocks on the TMA / tcgen05 GEMM engine (stf_conv2d with ksize 1) instead of the cp.async-fed
 # stf_linear kernel; "0" keeps the older kernel (A/B measurements).
 GEMM_ENGINE = os.environ.get("STF_B200_GEMM_ENGINE", "1") != "0"
+# Grid cap of the persistent kernels (0 = 148, one CTA per SM).  models.decompress() lowers it while device rANS decoders of
+# other sub-batches may be running: each of those is ONE warp on one SM for milliseconds, and a persistent CTA (a whole SM's
+# shared memory) assigned to that SM would wait for it -- head-of-line blocking of the entire kernel.
+MAX_CTAS = 0
+NUM_SMS = 148
 
 
 class PackedConv:
@@ -455,6 +461,7 @@ def conv2d(srcs, pc, act=False, out=None, residual=None):
     elif tuple(out.shape) != shape:
         raise ValueError(f"stf_conv2d: `out` must be an NHWC view of shape {shape}")
     a.w_packed = pc.packed.data_ptr()
+    a.max_ctas = MAX_CTAS
     a.y, a.ldy = _nhwc(out, "out")
     a.act = {False: 0, True: 1, None: 0, "gelu": 1, "lrp": 2, "residual": 3}[act]
     if a.act >= 2:      # out <- residual + 0.5 * tanh(conv + bias) / residual + conv + bias; default residual = out's content

@@ -107,6 +107,37 @@ def test_rans_vs_oracle_random(tables, n):
     assert np.array_equal(d.decode_stream_array(ix, tab), sy)
 
 
+@pytest.mark.parametrize("lo,hi", [(0, 20), (45, 64), (0, 64), (20, 34)])
+def test_rans_both_step_variants_match_oracle(tables, lo, hi):
+    """The codec picks its step per run from a sample of the indexes: branchy + 256-bucket LUT for runs of narrow CDF rows,
+    branch-free + 4096-bucket LUT for wide (high-entropy) ones.  Both must produce the oracle's bytes, single-stream and in
+    lockstep groups, including tail symbols of frequency 1 and escapes."""
+    cdf, lens, offs, tab = tables
+    rng = np.random.default_rng(lo * 64 + hi)
+    table = OE.scale_table().numpy()
+    syms, idxs = [], []
+    for i in range(5):
+        n = 3000 + 501 * i
+        ix = rng.integers(lo, hi, size=n).astype(np.int32)
+        sy = np.rint(rng.standard_normal(n) * table[ix] * (1.0 + i)).astype(np.int32)      # i >= 1: tails, then escapes
+        sy[::97] = rng.integers(-4000, 4000, size=sy[::97].size)
+        syms.append(sy), idxs.append(ix)
+    want = [OE.rans_encode(sy, ix, cdf, lens, offs) for sy, ix in zip(syms, idxs)]
+    assert [ans.encode_array(tab, sy, ix) for sy, ix in zip(syms, idxs)] == want
+    for threads in (1, 2):
+        assert ans.encode_batch(tab, syms, idxs, threads=threads) == want
+        decs = []
+        for b in want:
+            d = ans.RansDecoder()
+            d.set_stream(b)
+            decs.append(d)
+        outs = ans.decode_batch(decs, tab, idxs, threads=threads)
+        assert all(np.array_equal(o, s_) for o, s_ in zip(outs, syms))
+    d = ans.RansDecoder()
+    d.set_stream(want[0])
+    assert np.array_equal(d.decode_stream_array(idxs[0], tab), syms[0])
+
+
 def test_rans_batch_threads_identical(tables):
     cdf, lens, offs, tab = tables
     rng = np.random.default_rng(3)

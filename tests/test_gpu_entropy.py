@@ -253,3 +253,32 @@ def test_conv_glue_kernels_bias_gelu_and_layernorm():
         w, b = (1 + 0.1 * torch.randn(C, generator=g)).cuda(), (0.1 * torch.randn(C, generator=g)).cuda()
         ref = torch.nn.functional.layer_norm(x, (C,), w, b, 1e-5)
         assert float((ops.layernorm(x, w, b, 1e-5) - ref).abs().max()) <= 2e-6 * float(ref.abs().max())
+
+
+def test_device_rans_decoder_matches_host_decoder():
+    """stf_rans_decode_device (one warp lane per stream, state carried across calls) returns exactly the symbols that were
+    encoded -- i.e. what the host decoder / the reference's RansDecoder return -- incl. escape-coded outliers, ragged stream
+    lengths, more than 32 streams (two CTAs) and a truncated stream (status STF_E_STREAM, other streams unaffected)."""
+    from stf_b200 import ans
+    cdf, lens, offs = OE.gaussian_tables()
+    tab = ans.RansTable(cdf, lens, offs)
+    table = OE.scale_table().numpy()
+    rng = np.random.default_rng(11)
+    B, n, slices = 37, 6000, 3
+    ix = rng.integers(0, 64, size=(B, n * slices)).astype(np.int32)
+    sy = np.rint(rng.standard_normal((B, n * slices)) * table[ix] * 1.5).astype(np.int32)
+    sy[:, ::97] += 5000                                                   # escapes (nibble-coded bypass values)
+    strings = ans.encode_rows(tab, sy, ix)
+    strings[5] = strings[5][: len(strings[5]) // 2 // 4 * 4]              # truncated stream
+    ds = ans.DeviceStreams(B, sum(len(s) for s in strings) // 4 + 4 * B, "cuda")
+    assert ds.fits(strings)
+    ds.load(strings)
+    ds.upload()
+    idx_d = torch.from_numpy(ix).cuda()
+    out = torch.empty((B, n * slices), dtype=torch.int32, device="cuda")
+    for k in range(slices):
+        ans.decode_device(tab, ds, idx_d[:, k * n:(k + 1) * n], out[:, k * n:(k + 1) * n], first=(k == 0))
+    got, status = out.cpu().numpy(), ds.status.cpu().numpy()
+    ok = [b for b in range(B) if b != 5]
+    assert np.array_equal(got[ok], sy[ok])
+    assert (status[ok] == 0).all() and status[5] == -6
