@@ -75,7 +75,11 @@ int stf_gaussian_compress_step(const float *y, int64_t y_batch_stride, const flo
  *   else y != NULL                encode   (stf.py:717-722): -> symbols_out, indexes_out (if scales), y_hat (if non-NULL)
  *   else symbols_in != NULL       decode   (stf.py:770-772): y_hat = float(symbols_in) + means; + indexes_out if scales
  *   else                          indexes  (stf.py:767): scales -> indexes_out
- * Arithmetic is the NCHW kernels': identical bits for identical inputs.  channels <= 32. */
+ * Arithmetic is the NCHW kernels': identical bits for identical inputs.  channels <= 32.
+ * narrow != 0: symbols_out is an int16_t buffer and indexes_out a uint8_t buffer (strides still in elements) -- 3 instead
+ * of 8 bytes per symbol cross PCIe to the host coder (stf_rans_encode_batch_narrow / stf_rans_decode_batch_u8); *overflow
+ * (device int32, zeroed by the caller) is set to 1 when a symbol does not fit int16 or an index does not fit uint8, in
+ * which case the caller repeats the step with narrow == 0. */
 typedef struct {
   const float *y; int y_ld;
   const float *scales; int scales_ld;
@@ -88,6 +92,7 @@ typedef struct {
   const float *table_host; int levels;   /* HOST scale table (needed when indexes_out != NULL) */
   float scale_bound, lik_bound;
   int ste_round;                         /* forward: y_hat = ((round(t) - t) + t) + mu (ops/ops.py:34) */
+  int narrow; int32_t *overflow;         /* int16 symbols_out / uint8 indexes_out + device overflow flag (see above) */
 } stf_slice_args;
 int stf_slice_step_nhwc(const stf_slice_args *args, void *stream);
 
@@ -392,6 +397,10 @@ int64_t stf_rans_encode(const stf_rans_table *t, const int32_t *symbols, const i
 int stf_rans_encode_batch(const stf_rans_table *t, int count, const int32_t *const *symbols,
                           const int32_t *const *indexes, const int64_t *n, uint8_t *const *out,
                           const int64_t *out_cap, int64_t *out_lens, int threads);
+/* The same on the narrow transfer format of stf_slice_step_nhwc (int16 symbols, uint8 indexes); same bytes out. */
+int stf_rans_encode_batch_narrow(const stf_rans_table *t, int count, const int16_t *const *symbols,
+                                 const uint8_t *const *indexes, const int64_t *n, uint8_t *const *out,
+                                 const int64_t *out_cap, int64_t *out_lens, int threads);
 
 /* RansDecoder (rans_interface.cpp:277-350): set_stream + repeated decode_stream calls. */
 typedef struct stf_rans_decoder stf_rans_decoder;
@@ -405,6 +414,10 @@ int stf_rans_decode(stf_rans_decoder *d, const stf_rans_table *t, const int32_t 
 int stf_rans_decode_batch(stf_rans_decoder *const *d, const stf_rans_table *t, int count,
                           const int32_t *const *indexes, const int64_t *n,
                           int32_t *const *symbols_out, int threads);
+/* The same with uint8 indexes (symbols stay int32: what a stream decodes to is not bounded). */
+int stf_rans_decode_batch_u8(stf_rans_decoder *const *d, const stf_rans_table *t, int count,
+                             const uint8_t *const *indexes, const int64_t *n,
+                             int32_t *const *symbols_out, int threads);
 
 /* Device-side decoder for the slice loop of decompress() (stf.py:757-779): RansDecoder.set_stream + decode_stream
  * (rans_interface.cpp:277-350, rans64.h:107-142) for `count` independent streams, lane b of a warp decoding stream b in

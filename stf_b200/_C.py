@@ -59,6 +59,7 @@ class SliceArgs(ctypes.Structure):
         ("y_hat", c_vp), ("y_hat_ld", c_int), ("likelihood", c_vp), ("likelihood_batch_stride", c_i64),
         ("batch", c_int), ("channels", c_int), ("plane", c_i64),
         ("table_host", _f32p), ("levels", c_int), ("scale_bound", c_f32), ("lik_bound", c_f32), ("ste_round", c_int),
+        ("narrow", c_int), ("overflow", c_vp),
     ]
 
 
@@ -105,11 +106,15 @@ SIGNATURES = {
     "stf_rans_encode": (c_i64, [c_vp, c_vp, c_vp, c_i64, c_vp, c_i64]),
     "stf_rans_encode_batch": (c_int, [c_vp, c_int, ctypes.POINTER(c_vp), ctypes.POINTER(c_vp), ctypes.POINTER(c_i64),
                                       ctypes.POINTER(c_vp), ctypes.POINTER(c_i64), ctypes.POINTER(c_i64), c_int]),
+    "stf_rans_encode_batch_narrow": (c_int, [c_vp, c_int, ctypes.POINTER(c_vp), ctypes.POINTER(c_vp), ctypes.POINTER(c_i64),
+                                      ctypes.POINTER(c_vp), ctypes.POINTER(c_i64), ctypes.POINTER(c_i64), c_int]),
     "stf_rans_decoder_create": (c_vp, [c_vp, c_i64]),
     "stf_rans_decoder_create_view": (c_vp, [c_vp, c_i64]),
     "stf_rans_decoder_destroy": (None, [c_vp]),
     "stf_rans_decode": (c_int, [c_vp, c_vp, c_vp, c_i64, c_vp]),
     "stf_rans_decode_batch": (c_int, [ctypes.POINTER(c_vp), c_vp, c_int, ctypes.POINTER(c_vp), ctypes.POINTER(c_i64),
+                                      ctypes.POINTER(c_vp), c_int]),
+    "stf_rans_decode_batch_u8": (c_int, [ctypes.POINTER(c_vp), c_vp, c_int, ctypes.POINTER(c_vp), ctypes.POINTER(c_i64),
                                       ctypes.POINTER(c_vp), c_int]),
     "stf_rans_device_table_bytes": (c_i64, [c_vp]),
     "stf_rans_device_table_pack": (c_int, [c_vp, c_vp]),

@@ -176,9 +176,10 @@ class RansDecoder:
 
 
 def _row_ptrs(a2d):
-    """ctypes array of the row addresses of a C-contiguous 2-D int32 array (no per-row numpy views / .ctypes objects)."""
-    if a2d.dtype != np.int32 or a2d.ndim != 2 or not a2d.flags.c_contiguous:
-        raise ValueError("expected a C-contiguous 2-D int32 array")
+    """ctypes array of the row addresses of a C-contiguous 2-D array (no per-row numpy views / .ctypes objects); the caller
+    has checked the element type against the entry point it calls."""
+    if a2d.ndim != 2 or a2d.strides[1] != a2d.itemsize:
+        raise ValueError("expected a 2-D array with contiguous rows")
     base, stride = a2d.ctypes.data, a2d.strides[0]
     return (ctypes.c_void_p * a2d.shape[0])(*[base + i * stride for i in range(a2d.shape[0])])
 
@@ -191,22 +192,31 @@ class DecodePlan:
         count = len(decoders)
         if idx2d.shape != out2d.shape or idx2d.shape[0] != count:
             raise ValueError("index / output buffers must be (len(decoders), n)")
+        if out2d.dtype != np.int32 or idx2d.dtype not in (np.int32, np.uint8):
+            raise TypeError("indexes must be int32 or uint8, symbols int32")
         self._keep = (decoders, table, idx2d, out2d)
         self._args = ((ctypes.c_void_p * count)(*[d._h for d in decoders]), table._h, count, _row_ptrs(idx2d),
                       (ctypes.c_int64 * count)(*([idx2d.shape[1]] * count)), _row_ptrs(out2d), threads or default_threads())
-        self._fn = _C.lib().stf_rans_decode_batch
+        self._fn = _C.lib().stf_rans_decode_batch_u8 if idx2d.dtype == np.uint8 else _C.lib().stf_rans_decode_batch
 
     def run(self):
         _C.check(self._fn(*self._args), "stf_rans_decode_batch")
 
 
 def encode_rows(table: RansTable, sym2d, idx2d, scratch=None, threads=None):
-    """encode_batch for the rows of two (B, n) int32 arrays; `scratch` (a dict kept by the caller) recycles the output
-    buffers between calls (8 n + 64 bytes per image otherwise freshly mapped every time).  -> list[bytes]."""
+    """encode_batch for the rows of two (B, n) arrays -- int32 / int32, or the narrow transfer format int16 symbols / uint8
+    indexes; `scratch` (a dict kept by the caller) recycles the output buffers between calls (8 n + 64 bytes per image
+    otherwise freshly mapped every time).  -> list[bytes]."""
     count, n = sym2d.shape
     if idx2d.shape != sym2d.shape:
         raise ValueError("symbols and indexes differ in shape")
     L = _C.lib()
+    if sym2d.dtype == np.int16 and idx2d.dtype == np.uint8:
+        fn = L.stf_rans_encode_batch_narrow
+    elif sym2d.dtype == np.int32 and idx2d.dtype == np.int32:
+        fn = L.stf_rans_encode_batch
+    else:
+        raise TypeError(f"symbols / indexes must be int32 / int32 or int16 / uint8, got {sym2d.dtype} / {idx2d.dtype}")
     cap = int(L.stf_rans_encode_bound(n))
     key = (count, cap)
     if scratch is None:
@@ -216,8 +226,8 @@ def encode_rows(table: RansTable, sym2d, idx2d, scratch=None, threads=None):
         scratch.update(key=key, out=out, out_ptrs=(ctypes.c_void_p * count)(*[out.ctypes.data + i * cap for i in range(count)]),
                        caps=(ctypes.c_int64 * count)(*([cap] * count)), ns=(ctypes.c_int64 * count)(*([n] * count)),
                        lens=(ctypes.c_int64 * count)())
-    rc = L.stf_rans_encode_batch(table._h, count, _row_ptrs(sym2d), _row_ptrs(idx2d), scratch["ns"], scratch["out_ptrs"],
-                                 scratch["caps"], scratch["lens"], threads or default_threads())
+    rc = fn(table._h, count, _row_ptrs(sym2d), _row_ptrs(idx2d), scratch["ns"], scratch["out_ptrs"],
+            scratch["caps"], scratch["lens"], threads or default_threads())
     _C.check(rc, "stf_rans_encode_batch")
     out, lens = scratch["out"], scratch["lens"]
     return [out[i, : lens[i]].tobytes() for i in range(count)]

@@ -291,6 +291,8 @@ struct SliceNhwc {
   int C, plane;
   float scale_bound, lik_bound;
   int ste_round;
+  int narrow;            // symbols_out is int16_t*, indexes_out uint8_t* (3 instead of 8 bytes per symbol over PCIe)
+  int32_t *overflow;     // narrow: set to 1 when a symbol does not fit int16 or an index does not fit uint8
 };
 
 template <int kMode>  // index search as in compress_step_kernel
@@ -348,8 +350,23 @@ slice_step_nhwc_kernel(const SliceNhwc a, const __grid_constant__ ScaleTable tab
     if (p >= a.plane) continue;
     const int64_t o = (int64_t)c * a.plane + p;
     if (a.lik) a.lik[(int64_t)b * a.lik_bstride + o] = __int_as_float(tile_b[c][lane]);
-    if (a.sym_out) a.sym_out[(int64_t)b * a.out_bstride + o] = tile_a[c][lane];
-    if (a.idx_out) a.idx_out[(int64_t)b * a.out_bstride + o] = tile_b[c][lane];
+    if (!a.narrow) {
+      if (a.sym_out) a.sym_out[(int64_t)b * a.out_bstride + o] = tile_a[c][lane];
+      if (a.idx_out) a.idx_out[(int64_t)b * a.out_bstride + o] = tile_b[c][lane];
+    } else {
+      bool bad = false;
+      if (a.sym_out) {
+        const int32_t q = tile_a[c][lane];
+        bad = q != (int32_t)(int16_t)q;
+        reinterpret_cast<int16_t *>(a.sym_out)[(int64_t)b * a.out_bstride + o] = (int16_t)q;
+      }
+      if (a.idx_out) {
+        const int32_t ix = tile_b[c][lane];
+        bad = bad || (uint32_t)ix > 255u;
+        reinterpret_cast<uint8_t *>(a.idx_out)[(int64_t)b * a.out_bstride + o] = (uint8_t)ix;
+      }
+      if (bad) *a.overflow = 1;   // (benign race: every writer stores the same value)
+    }
   }
 }
 
@@ -536,6 +553,7 @@ extern "C" int stf_slice_step_nhwc(const stf_slice_args *a, void *stream) {
   if (decode_fin && !a->y_hat) return STF_E_ARG;
   if (!forward && !encode && !decode_fin && !(a->scales && a->indexes_out)) return STF_E_ARG;
   if (a->indexes_out && !a->scales) return STF_E_ARG;
+  if (a->narrow && !a->overflow) return STF_E_ARG;
   ScaleTable t;
   if (a->scales && a->indexes_out) {
     int rc = fill_table(&t, a->table_host, a->levels);
@@ -551,6 +569,7 @@ extern "C" int stf_slice_step_nhwc(const stf_slice_args *a, void *stream) {
   k.sym_out = encode ? a->symbols_out : nullptr, k.idx_out = forward ? nullptr : a->indexes_out, k.out_bstride = a->out_batch_stride;
   k.y_hat = a->y_hat, k.yh_ld = a->y_hat_ld, k.lik = a->likelihood, k.lik_bstride = a->likelihood_batch_stride;
   k.C = a->channels, k.plane = (int)a->plane, k.scale_bound = a->scale_bound, k.lik_bound = a->lik_bound, k.ste_round = a->ste_round;
+  k.narrow = a->narrow, k.overflow = a->overflow;
   dim3 grid((unsigned)((a->plane + 31) / 32), (unsigned)a->batch);
   cudaStream_t st = (cudaStream_t)stream;
   static const bool no_lut = getenv("STF_B200_NO_INDEX_LUT") != nullptr;

@@ -166,29 +166,30 @@ inline int64_t encode_finish(uint64_t x, uint32_t *w, uint32_t *buf_end) {
 }
 
 // Does a run of n symbols mostly use wide (high-entropy) rows?  64 evenly spaced samples.
-inline bool wide_run(const stf_rans_table *t, const int32_t *indexes, int64_t n) {
+template <class IdxT>
+inline bool wide_run(const stf_rans_table *t, const IdxT *indexes, int64_t n) {
   if (n <= 0) return false;
   const int64_t stride = n / 64 > 0 ? n / 64 : 1;
   int wide = 0, seen = 0;
   for (int64_t i = 0; i < n && seen < 64; i += stride, ++seen) {
-    const int32_t row = indexes[i];
+    const int32_t row = (int32_t)indexes[i];
     if ((uint32_t)row < (uint32_t)t->rows) wide += (int)t->row[row].wide;
   }
   return 4 * wide >= seen;
 }
 
-template <bool kBranchFree>
-__attribute__((noinline)) int64_t encode_into_impl(const stf_rans_table *t, const int32_t *symbols, const int32_t *indexes, int64_t n,
+template <bool kBranchFree, class SymT, class IdxT>
+__attribute__((noinline)) int64_t encode_into_impl(const stf_rans_table *t, const SymT *symbols, const IdxT *indexes, int64_t n,
                          uint32_t *buf_end) {
   uint32_t *w = buf_end;
   uint64_t x = kLow;
   for (int64_t i = n - 1; i >= 0; --i)
-    if (!encode_step<kBranchFree>(t, symbols[i], indexes[i], x, w)) return STF_E_ARG;
+    if (!encode_step<kBranchFree>(t, (int32_t)symbols[i], (int32_t)indexes[i], x, w)) return STF_E_ARG;
   return encode_finish(x, w, buf_end);
 }
 
-int64_t encode_into(const stf_rans_table *t, const int32_t *symbols, const int32_t *indexes, int64_t n,
-                    uint32_t *buf_end) {
+template <class SymT, class IdxT>
+int64_t encode_into(const stf_rans_table *t, const SymT *symbols, const IdxT *indexes, int64_t n, uint32_t *buf_end) {
   return wide_run(t, indexes, n) ? encode_into_impl<true>(t, symbols, indexes, n, buf_end)
                                  : encode_into_impl<false>(t, symbols, indexes, n, buf_end);
 }
@@ -196,8 +197,8 @@ int64_t encode_into(const stf_rans_table *t, const int32_t *symbols, const int32
 // W independent streams in lockstep: a stream is one serial dependency chain (state -> multiply-high -> state, ~15 cycles
 // per symbol), so a thread that owns W images interleaves them and the core overlaps the W chains (W = 2 or 4; with eight
 // ranks sharing a host each rank has a handful of threads for 21+ images).  Same bytes as W encode_into calls.
-template <int W, bool kBranchFree>
-__attribute__((noinline)) void encode_intoW_impl(const stf_rans_table *t, const int32_t *const *sym, const int32_t *const *idx, const int64_t *n,
+template <int W, bool kBranchFree, class SymT, class IdxT>
+__attribute__((noinline)) void encode_intoW_impl(const stf_rans_table *t, const SymT *const *sym, const IdxT *const *idx, const int64_t *n,
                        uint32_t *const *buf_end, int64_t *nb) {
   uint32_t *w[W];
   uint64_t x[W];
@@ -211,20 +212,20 @@ __attribute__((noinline)) void encode_intoW_impl(const stf_rans_table *t, const 
   for (int64_t step = 0; ok && step < common; ++step) {
 #pragma GCC unroll 8
     for (int k = 0; k < W; ++k) {
-      ok = encode_step<kBranchFree>(t, sym[k][i[k]], idx[k][i[k]], x[k], w[k]) && ok;
+      ok = encode_step<kBranchFree>(t, (int32_t)sym[k][i[k]], (int32_t)idx[k][i[k]], x[k], w[k]) && ok;
       --i[k];
     }
   }
   for (int k = 0; k < W; ++k)
-    for (; ok && i[k] >= 0; --i[k]) ok = encode_step<kBranchFree>(t, sym[k][i[k]], idx[k][i[k]], x[k], w[k]);
+    for (; ok && i[k] >= 0; --i[k]) ok = encode_step<kBranchFree>(t, (int32_t)sym[k][i[k]], (int32_t)idx[k][i[k]], x[k], w[k]);
   for (int k = 0; k < W; ++k) nb[k] = ok ? encode_finish(x[k], w[k], buf_end[k]) : (int64_t)STF_E_ARG;
 }
 
-template <int W>
-void encode_intoW(const stf_rans_table *t, const int32_t *const *sym, const int32_t *const *idx, const int64_t *n,
+template <int W, class SymT, class IdxT>
+void encode_intoW(const stf_rans_table *t, const SymT *const *sym, const IdxT *const *idx, const int64_t *n,
                   uint32_t *const *buf_end, int64_t *nb) {
-  if (wide_run(t, idx[0], n[0])) encode_intoW_impl<W, true>(t, sym, idx, n, buf_end, nb);
-  else encode_intoW_impl<W, false>(t, sym, idx, n, buf_end, nb);
+  if (wide_run(t, idx[0], n[0])) encode_intoW_impl<W, true, SymT, IdxT>(t, sym, idx, n, buf_end, nb);
+  else encode_intoW_impl<W, false, SymT, IdxT>(t, sym, idx, n, buf_end, nb);
 }
 
 // Decoder position kept in registers while a run is in flight (the decoder object is only read at the start of a run and
@@ -302,24 +303,26 @@ inline int decode_step(Cursor &c, const stf_rans_table *t, int32_t row, int32_t 
   return STF_OK;
 }
 
-template <bool kBranchFree>
-__attribute__((noinline)) int decode_run_impl(stf_rans_decoder *d, const stf_rans_table *t, const int32_t *indexes, int64_t n, int32_t *out) {
+template <bool kBranchFree, class IdxT>
+__attribute__((noinline)) int decode_run_impl(stf_rans_decoder *d, const stf_rans_table *t, const IdxT *indexes, int64_t n, int32_t *out) {
   Cursor c{d->x, d->w, d->end};
   for (int64_t i = 0; i < n; ++i) {
-    const int rc = decode_step<kBranchFree>(c, t, indexes[i], out + i);
+    const int rc = decode_step<kBranchFree>(c, t, (int32_t)indexes[i], out + i);
     if (rc) return rc;
   }
   d->x = c.x, d->w = c.w;
   return STF_OK;
 }
 
-int decode_run(stf_rans_decoder *d, const stf_rans_table *t, const int32_t *indexes, int64_t n, int32_t *out) {
-  return wide_run(t, indexes, n) ? decode_run_impl<true>(d, t, indexes, n, out) : decode_run_impl<false>(d, t, indexes, n, out);
+template <class IdxT>
+int decode_run(stf_rans_decoder *d, const stf_rans_table *t, const IdxT *indexes, int64_t n, int32_t *out) {
+  return wide_run(t, indexes, n) ? decode_run_impl<true, IdxT>(d, t, indexes, n, out)
+                                 : decode_run_impl<false, IdxT>(d, t, indexes, n, out);
 }
 
 // W decoders in lockstep (see encode_intoW).
-template <int W, bool kBranchFree>
-__attribute__((noinline)) void decode_runW_impl(stf_rans_decoder *const *d, const stf_rans_table *t, const int32_t *const *idx, const int64_t *n,
+template <int W, bool kBranchFree, class IdxT>
+__attribute__((noinline)) void decode_runW_impl(stf_rans_decoder *const *d, const stf_rans_table *t, const IdxT *const *idx, const int64_t *n,
                       int32_t *const *out, int *rc_out) {
   Cursor c[W];
   int rc[W];   // local: the caller's status array is shared between threads (one cache line for several groups)
@@ -333,23 +336,23 @@ __attribute__((noinline)) void decode_runW_impl(stf_rans_decoder *const *d, cons
   for (; i < m && !any; ++i) {
 #pragma GCC unroll 8
     for (int k = 0; k < W; ++k) {
-      rc[k] = decode_step<kBranchFree>(c[k], t, idx[k][i], out[k] + i);
+      rc[k] = decode_step<kBranchFree>(c[k], t, (int32_t)idx[k][i], out[k] + i);
       any |= rc[k];
     }
   }
   if (!any)
     for (int k = 0; k < W; ++k) {
-      for (int64_t j = i; j < n[k] && !rc[k]; ++j) rc[k] = decode_step<kBranchFree>(c[k], t, idx[k][j], out[k] + j);
+      for (int64_t j = i; j < n[k] && !rc[k]; ++j) rc[k] = decode_step<kBranchFree>(c[k], t, (int32_t)idx[k][j], out[k] + j);
       if (!rc[k]) d[k]->x = c[k].x, d[k]->w = c[k].w;
     }
   for (int k = 0; k < W; ++k) rc_out[k] = rc[k];
 }
 
-template <int W>
-void decode_runW(stf_rans_decoder *const *d, const stf_rans_table *t, const int32_t *const *idx, const int64_t *n,
+template <int W, class IdxT>
+void decode_runW(stf_rans_decoder *const *d, const stf_rans_table *t, const IdxT *const *idx, const int64_t *n,
                  int32_t *const *out, int *rc_out) {
-  if (wide_run(t, idx[0], n[0])) decode_runW_impl<W, true>(d, t, idx, n, out, rc_out);
-  else decode_runW_impl<W, false>(d, t, idx, n, out, rc_out);
+  if (wide_run(t, idx[0], n[0])) decode_runW_impl<W, true, IdxT>(d, t, idx, n, out, rc_out);
+  else decode_runW_impl<W, false, IdxT>(d, t, idx, n, out, rc_out);
 }
 
 // Persistent worker pool: decode_batch is called once per slice (12-13 times per image batch), so
@@ -504,8 +507,11 @@ extern "C" int stf_rans_table_export(const stf_rans_table *t, int *rows, const i
 
 extern "C" int64_t stf_rans_encode_bound(int64_t n) { return n < 0 ? STF_E_ARG : 8 * n + 64; }
 
-extern "C" int64_t stf_rans_encode(const stf_rans_table *t, const int32_t *symbols, const int32_t *indexes,
-                                   int64_t n, uint8_t *out, int64_t out_cap) {
+namespace {
+
+template <class SymT, class IdxT>
+int64_t encode_one(const stf_rans_table *t, const SymT *symbols, const IdxT *indexes, int64_t n, uint8_t *out,
+                   int64_t out_cap) {
   if (!t || !out || n < 0 || (n > 0 && (!symbols || !indexes))) return STF_E_ARG;
   const int64_t bound = stf_rans_encode_bound(n);
   if (out_cap >= bound && ((uintptr_t)out & 3u) == 0) {  // code straight into the caller's buffer
@@ -523,9 +529,9 @@ extern "C" int64_t stf_rans_encode(const stf_rans_table *t, const int32_t *symbo
   return nb;
 }
 
-extern "C" int stf_rans_encode_batch(const stf_rans_table *t, int count, const int32_t *const *symbols,
-                                     const int32_t *const *indexes, const int64_t *n, uint8_t *const *out,
-                                     const int64_t *out_cap, int64_t *out_lens, int threads) {
+template <class SymT, class IdxT>
+int encode_batch(const stf_rans_table *t, int count, const SymT *const *symbols, const IdxT *const *indexes,
+                 const int64_t *n, uint8_t *const *out, const int64_t *out_cap, int64_t *out_lens, int threads) {
   if (!t || count < 0 || !symbols || !indexes || !n || !out || !out_cap || !out_lens) return STF_E_ARG;
   bool groupable = count > threads && threads >= 1;
   for (int i = 0; groupable && i < count; ++i)
@@ -533,7 +539,7 @@ extern "C" int stf_rans_encode_batch(const stf_rans_table *t, int count, const i
                 ((uintptr_t)out[i] & 3u) == 0;
   if (!groupable) {
     parallel_for(count, threads,
-                 [&](int i) { out_lens[i] = stf_rans_encode(t, symbols[i], indexes[i], n[i], out[i], out_cap[i]); });
+                 [&](int i) { out_lens[i] = encode_one(t, symbols[i], indexes[i], n[i], out[i], out_cap[i]); });
   } else {
     // more images than threads: the images are split evenly over the threads (contiguous ranges whose sizes differ by at
     // most one -- fixed groups of four would leave half the threads idle in the last round of 21 images on 4 threads) and
@@ -542,7 +548,8 @@ extern "C" int stf_rans_encode_batch(const stf_rans_table *t, int count, const i
       const int lo = (int)((int64_t)count * tix / threads), hi = (int)((int64_t)count * (tix + 1) / threads);
       for (int a = lo; a < hi;) {
         const int m = hi - a < kMaxLockstep ? hi - a : kMaxLockstep;
-        const int32_t *sy[8], *ix[8];
+        const SymT *sy[8];
+        const IdxT *ix[8];
         int64_t nn[8], nb[8];
         uint32_t *end[8];
         for (int k = 0; k < m; ++k)
@@ -567,6 +574,63 @@ extern "C" int stf_rans_encode_batch(const stf_rans_table *t, int count, const i
   for (int i = 0; i < count; ++i)
     if (out_lens[i] < 0) return (int)out_lens[i];
   return STF_OK;
+}
+
+template <class IdxT>
+int decode_batch(stf_rans_decoder *const *d, const stf_rans_table *t, int count, const IdxT *const *indexes,
+                 const int64_t *n, int32_t *const *symbols_out, int threads) {
+  if (!d || !t || count < 0 || !indexes || !n || !symbols_out) return STF_E_ARG;
+  std::vector<int> rc((size_t)count, 0);
+  bool groupable = count > threads && threads >= 1;
+  for (int i = 0; i < count; ++i) {
+    const bool ok = d[i] && n[i] >= 0 && (n[i] == 0 || (indexes[i] && symbols_out[i]));
+    if (!ok) return STF_E_ARG;
+  }
+  if (!groupable) {
+    parallel_for(count, threads, [&](int i) { rc[i] = decode_run(d[i], t, indexes[i], n[i], symbols_out[i]); });
+  } else {
+    parallel_for(threads, threads, [&](int tix) {   // even contiguous ranges, lockstep groups of 4 / 3 / 2 / 1 (see encode)
+      const int lo = (int)((int64_t)count * tix / threads), hi = (int)((int64_t)count * (tix + 1) / threads);
+      for (int a = lo; a < hi;) {
+        const int m = hi - a < kMaxLockstep ? hi - a : kMaxLockstep;
+        int r[8];
+        if (m == 8) decode_runW<8>(d + a, t, indexes + a, n + a, symbols_out + a, r);
+        else if (m == 7) decode_runW<7>(d + a, t, indexes + a, n + a, symbols_out + a, r);
+        else if (m == 6) decode_runW<6>(d + a, t, indexes + a, n + a, symbols_out + a, r);
+        else if (m == 5) decode_runW<5>(d + a, t, indexes + a, n + a, symbols_out + a, r);
+        else if (m == 4) decode_runW<4>(d + a, t, indexes + a, n + a, symbols_out + a, r);
+        else if (m == 3) decode_runW<3>(d + a, t, indexes + a, n + a, symbols_out + a, r);
+        else if (m == 2) decode_runW<2>(d + a, t, indexes + a, n + a, symbols_out + a, r);
+        else r[0] = decode_run(d[a], t, indexes[a], n[a], symbols_out[a]);
+        for (int k = 0; k < m; ++k) rc[a + k] = r[k];
+        a += m;
+      }
+    });
+  }
+  for (int i = 0; i < count; ++i)
+    if (rc[i]) return rc[i];
+  return STF_OK;
+}
+
+}  // namespace
+
+extern "C" int64_t stf_rans_encode(const stf_rans_table *t, const int32_t *symbols, const int32_t *indexes,
+                                   int64_t n, uint8_t *out, int64_t out_cap) {
+  return encode_one(t, symbols, indexes, n, out, out_cap);
+}
+
+extern "C" int stf_rans_encode_batch(const stf_rans_table *t, int count, const int32_t *const *symbols,
+                                     const int32_t *const *indexes, const int64_t *n, uint8_t *const *out,
+                                     const int64_t *out_cap, int64_t *out_lens, int threads) {
+  return encode_batch(t, count, symbols, indexes, n, out, out_cap, out_lens, threads);
+}
+
+// The same coder on the narrow transfer format of stf_slice_step_nhwc (int16 symbols, uint8 indexes: 3 instead of 8 bytes
+// per symbol over PCIe and through the host caches).  Same bytes out.
+extern "C" int stf_rans_encode_batch_narrow(const stf_rans_table *t, int count, const int16_t *const *symbols,
+                                            const uint8_t *const *indexes, const int64_t *n, uint8_t *const *out,
+                                            const int64_t *out_cap, int64_t *out_lens, int threads) {
+  return encode_batch(t, count, symbols, indexes, n, out, out_cap, out_lens, threads);
 }
 
 extern "C" stf_rans_decoder *stf_rans_decoder_create(const uint8_t *stream, int64_t nbytes) {
@@ -607,34 +671,15 @@ extern "C" int stf_rans_decode(stf_rans_decoder *d, const stf_rans_table *t, con
 extern "C" int stf_rans_decode_batch(stf_rans_decoder *const *d, const stf_rans_table *t, int count,
                                      const int32_t *const *indexes, const int64_t *n,
                                      int32_t *const *symbols_out, int threads) {
-  if (!d || !t || count < 0 || !indexes || !n || !symbols_out) return STF_E_ARG;
-  std::vector<int> rc((size_t)count, 0);
-  bool groupable = count > threads && threads >= 1;
-  for (int i = 0; groupable && i < count; ++i) groupable = d[i] && n[i] >= 0 && indexes[i] && symbols_out[i];
-  if (!groupable) {
-    parallel_for(count, threads, [&](int i) { rc[i] = stf_rans_decode(d[i], t, indexes[i], n[i], symbols_out[i]); });
-  } else {
-    parallel_for(threads, threads, [&](int tix) {   // even contiguous ranges, lockstep groups of 4 / 3 / 2 / 1 (see encode)
-      const int lo = (int)((int64_t)count * tix / threads), hi = (int)((int64_t)count * (tix + 1) / threads);
-      for (int a = lo; a < hi;) {
-        const int m = hi - a < kMaxLockstep ? hi - a : kMaxLockstep;
-        int r[8];
-        if (m == 8) decode_runW<8>(d + a, t, indexes + a, n + a, symbols_out + a, r);
-        else if (m == 7) decode_runW<7>(d + a, t, indexes + a, n + a, symbols_out + a, r);
-        else if (m == 6) decode_runW<6>(d + a, t, indexes + a, n + a, symbols_out + a, r);
-        else if (m == 5) decode_runW<5>(d + a, t, indexes + a, n + a, symbols_out + a, r);
-        else if (m == 4) decode_runW<4>(d + a, t, indexes + a, n + a, symbols_out + a, r);
-        else if (m == 3) decode_runW<3>(d + a, t, indexes + a, n + a, symbols_out + a, r);
-        else if (m == 2) decode_runW<2>(d + a, t, indexes + a, n + a, symbols_out + a, r);
-        else r[0] = stf_rans_decode(d[a], t, indexes[a], n[a], symbols_out[a]);
-        for (int k = 0; k < m; ++k) rc[a + k] = r[k];
-        a += m;
-      }
-    });
-  }
-  for (int i = 0; i < count; ++i)
-    if (rc[i]) return rc[i];
-  return STF_OK;
+  return decode_batch(d, t, count, indexes, n, symbols_out, threads);
+}
+
+// uint8 indexes (a quarter of the device -> host bytes of every slice of decompress()); symbols stay int32: what a
+// stream decodes to is not bounded.
+extern "C" int stf_rans_decode_batch_u8(stf_rans_decoder *const *d, const stf_rans_table *t, int count,
+                                        const uint8_t *const *indexes, const int64_t *n,
+                                        int32_t *const *symbols_out, int threads) {
+  return decode_batch(d, t, count, indexes, n, symbols_out, threads);
 }
 
 extern "C" int stf_pmf_to_quantized_cdf(const float *pmf, int n, int precision, uint32_t *cdf) {

@@ -25,13 +25,13 @@ batch-1 call on that image gives (asserted in tests/test_gpu_codec.py); for batc
 reference's structure.
 """
 import math
+import os
+import time
 
 import numpy as np
 import torch
 import torch.nn as nn
 import torch.nn.functional as F
-
-import os
 
 from . import _C, ans, graphs, ops
 from .entropy_models import EntropyBottleneck, GaussianConditional, LowerBound
@@ -51,9 +51,46 @@ _DEC_PARTS = int(os.environ.get("STF_B200_DEC_PARTS", "0")) or None     # decomp
 # decompress(): rANS decoding of the y-strings on the device (one warp lane per image, no host round trip per slice) instead of
 # the host thread pool: "1" / "0", default "1"
 _DEVICE_DECODE = os.environ.get("STF_B200_DEVICE_DECODE", "0") != "0"
+# symbols / indexes cross PCIe as int16 / uint8 (3 instead of 8 bytes per symbol; D2H measured at 8.8 GiB/s per rank with
+# eight ranks copying at once, against 26 GiB/s H2D) -- "0" keeps int32 / int32
+_NARROW = os.environ.get("STF_B200_NARROW_TRANSFER", "1") != "0"
+def _split_env(name):
+    v = os.environ.get(name, "")
+    return [float(t) for t in v.split(",")] if v else None
+
+
+# explicit relative sub-batch sizes, first to last, e.g. "3,5,4" (overrides the tapered default below)
+_ENC_SPLIT, _DEC_SPLIT = _split_env("STF_B200_ENC_SPLIT"), _split_env("STF_B200_DEC_SPLIT")
 _PART_TAPER = float(os.environ.get("STF_B200_PART_TAPER", "0.75"))    # size of the last sub-batch relative to the first
 _DEC_LEAD = int(os.environ.get("STF_B200_DEC_LEAD", "3"))               # decompress(): slices a sub-batch may lead the next one by
+TRACE = None         # set to a list to collect a host / device timeline of the pipelined step (tools/timeline.py)
 PHASE_TIMES = None   # set to a dict to collect a synchronised wall-clock breakdown (tools/phase_breakdown.py)
+
+
+class _trace:
+    """`with _trace("name", part, slice, device=bool):` -- no-op unless TRACE is a list.  Host spans are perf_counter pairs;
+    device spans are CUDA event pairs recorded on the current stream (resolved by tools/timeline.py after a sync)."""
+
+    def __init__(self, name, part=0, step=0, device=False):
+        self.key, self.device = (name, part, step), device
+
+    def __enter__(self):
+        if TRACE is not None:
+            if self.device:
+                self.e0 = torch.cuda.Event(enable_timing=True)
+                self.e0.record()
+            self.t0 = time.perf_counter()
+        return self
+
+    def __exit__(self, *exc):
+        if TRACE is not None:
+            t1 = time.perf_counter()
+            TRACE.append(("host",) + self.key + (self.t0, t1))
+            if self.device:
+                e1 = torch.cuda.Event(enable_timing=True)
+                e1.record()
+                TRACE.append(("dev",) + self.key + (self.e0, e1))
+        return False
 
 
 class _phase:
@@ -439,8 +476,10 @@ class _SliceCodec(CompressionModel):
         return out
 
     # ------------------------------------------------------------------ encoder
-    def _encode_gpu(self, x, keep=None):
-        """All device work of compress(): x -> (y symbols, y indexes, z symbols), each (B, n) / (B, C, h, w) int32.
+    def _encode_gpu(self, x, keep=None, narrow=False):
+        """All device work of compress(): x -> (y symbols, y indexes, z symbols, overflow flag); y symbols / indexes are
+        (B, n) int32 / int32, or int16 / uint8 with `narrow` (the flag, one int32, is then set when a value did not fit
+        and the caller repeats the call wide); z symbols (B, C, h, w) int32.
         No host synchronisation inside: capturable as one CUDA graph."""
         gc, eb = self.gaussian_conditional, self.entropy_bottleneck
         with _phase("enc.analysis"):
@@ -454,8 +493,9 @@ class _SliceCodec(CompressionModel):
             latent_scales, latent_means = self._hyper_synthesis(z_hat)
             self._check_latent(latent_means, y.shape)
         Cs, plane = self.slice_channels, h * w
-        sym = torch.empty((B, M * plane), dtype=torch.int32, device=y.device)
-        idx = torch.empty((B, M * plane), dtype=torch.int32, device=y.device)
+        sym = torch.empty((B, M * plane), dtype=torch.int16 if narrow else torch.int32, device=y.device)
+        idx = torch.empty((B, M * plane), dtype=torch.uint8 if narrow else torch.int32, device=y.device)
+        ovf = torch.zeros(1, dtype=torch.int32, device=y.device)
         table = gc.host_scale_table()
         y_hat = torch.empty_like(y)
         with _phase("enc.slices"):
@@ -464,18 +504,18 @@ class _SliceCodec(CompressionModel):
                 need = self._needed_as_support(i) or keep is not None
                 ops.slice_step_nhwc(y=y[..., Cs * i: Cs * (i + 1)], scales=scale, means=mu, symbols_out=sym, indexes_out=idx,
                                     out_offset=i * Cs * plane, y_hat=y_hat[..., Cs * i: Cs * (i + 1)] if need else None,
-                                    table=table, scale_bound=gc.scale_bound_value())
+                                    table=table, scale_bound=gc.scale_bound_value(), overflow=ovf)
                 if need:   # later slices are never read again in compress(): their LRP stacks are dead work
                     self._lrp(i, latent_means, y_hat)
         if keep is not None:
             keep.update(y=y.permute(0, 3, 1, 2).contiguous(), z=z, y_hat=y_hat.permute(0, 3, 1, 2).contiguous())
-        return sym, idx, z_sym
+        return sym, idx, z_sym, ovf
 
     def _graphs_enabled(self):
         return self.__dict__.get("cuda_graphs", _GRAPHS_DEFAULT) and PHASE_TIMES is None
 
     @staticmethod
-    def _parts(B, pipelined, n_parts=None):
+    def _parts(B, pipelined, n_parts=None, weights=None):
         """Image ranges coded as independent sub-batches.  Two parts let the host rANS work of one part overlap
         the device work of the other (the device runs part B while the host codes part A, and vice versa); from 48
         images three parts shorten the exposed rANS tail of the last part further while each part still fills the GPU
@@ -486,49 +526,73 @@ class _SliceCodec(CompressionModel):
         # tapered sizes (weights 1 .. _PART_TAPER from the first to the last part): the host work of the LAST part is the
         # exposed tail of compress(), the device work of the FIRST part runs with an idle host
         wts = [1.0 + (_PART_TAPER - 1.0) * i / (n - 1) for i in range(n)]
+        if weights and B >= 8 * len(weights):
+            wts = list(weights)
         acc, bounds = 0.0, [0]
         for w_ in wts:
             acc += w_
             bounds.append(round(B * acc / sum(wts)))
         return [(lo, hi) for lo, hi in zip(bounds, bounds[1:]) if hi > lo]
 
+    def _enc_parts(self, B, pipelined=True):
+        """compress(): 7 : 6 : 3 from 48 images (batch 64 -> 28 / 24 / 12).  The host codes part k while the device runs part
+        k + 1, so only the LAST part's rANS is exposed: a small last part, not so small that its device work stops filling the
+        GPU (measured at batch 64, 16 / 4 host threads: 24/22/18 82.9 / 86.2 ms, 28/24/12 78.6 / 84.2 ms, 12/20/20/12 80.9 / 83.4)."""
+        return self._parts(B, pipelined, weights=_ENC_SPLIT or ((7.0, 6.0, 3.0) if B >= 48 else None))
+
+    def _dec_parts(self, B, pipelined=True):
+        """decompress(): tapered thirds; with few host threads (eight ranks sharing a host) the slice loop is bound by the
+        host decoder, and four parts of 4 : 5 : 4 : 3 give the device its synthesis work earlier and leave a shorter tail
+        (4 threads, batch 64: 102.7 -> 97.5 ms; 16 threads: no difference)."""
+        w = _DEC_SPLIT
+        if w is None and _DEC_PARTS is None and B >= 56 and ans.default_threads() < 8:
+            w = (4.0, 5.0, 4.0, 3.0)
+        return self._parts(B, pipelined, len(w) if w else _DEC_PARTS, weights=w)
+
     @torch.no_grad()
-    def compress(self, x, debug=None):
+    def compress(self, x, debug=None, _wide=False):
         gc, eb = self.gaussian_conditional, self.entropy_bottleneck
         y_table, z_table = gc.rans_table(), eb.rans_table()
         self._prepare_inference()
         x = x.contiguous()
         use_graphs = debug is None and self._graphs_enabled()
-        parts = self._parts(x.shape[0], use_graphs)
+        narrow = _NARROW and not _wide and debug is None and gc.host_scale_table().size <= 256
+        parts = self._enc_parts(x.shape[0], use_graphs)
         stream = torch.cuda.current_stream()
         pending = []
         plans = self._plans("_enc_plans") if use_graphs else None      # (validated against the weights epoch once per call)
         for slot, (lo, hi) in enumerate(parts):
             xp = x[lo:hi]
-            if use_graphs:
-                key = tuple(xp.shape)
-                if not self._plan_slot(plans, key, 8):
-                    plans[key] = graphs.Segment(lambda t: self._encode_gpu(t), [xp])
-                sym, idx, z_sym = plans[key](xp)
-            else:
-                sym, idx, z_sym = self._encode_gpu(xp, keep=debug)
+            with _trace("enc.gpu", slot, 0, device=True):
+                if use_graphs:
+                    key = tuple(xp.shape) + (narrow,)
+                    if not self._plan_slot(plans, key, 8):
+                        plans[key] = graphs.Segment(lambda t: self._encode_gpu(t, narrow=narrow), [xp])
+                    sym, idx, z_sym, ovf = plans[key](xp)
+                else:
+                    sym, idx, z_sym, ovf = self._encode_gpu(xp, keep=debug, narrow=narrow)
             Bp, total = sym.shape
-            with _phase("enc.d2h"):
-                sym_h, idx_h = self._host_buffers(("y", slot), Bp, total)
-                zsym_h, _ = self._host_buffers(("z", slot), Bp, z_sym[0].numel())
+            with _phase("enc.d2h"), _trace("enc.d2h", slot, 0, device=True):
+                sym_h, idx_h = self._host_buffers(("y", slot), Bp, total, (sym.dtype, idx.dtype))
+                zsym_h, ovf_h = self._host_buffers(("z", slot), Bp, z_sym[0].numel())
                 sym_h.copy_(sym, non_blocking=True)      # stream-ordered before the next part's replay
                 idx_h.copy_(idx, non_blocking=True)      # overwrites the plan's static outputs
                 zsym_h.copy_(z_sym.reshape(Bp, -1), non_blocking=True)
+                ovf_h[0, :1].copy_(ovf, non_blocking=True)
                 ev = torch.cuda.Event()
                 ev.record(stream)
-            pending.append((ev, Bp, sym_h, idx_h, zsym_h, tuple(z_sym.shape)))
+            pending.append((ev, Bp, sym_h, idx_h, zsym_h, tuple(z_sym.shape), ovf_h))
         y_strings, z_strings = [], []
-        for slot, (ev, Bp, sym_h, idx_h, zsym_h, zshape) in enumerate(pending):
-            with _phase("enc.d2h"):
+        for slot, (ev, Bp, sym_h, idx_h, zsym_h, zshape, ovf_h) in enumerate(pending):
+            with _phase("enc.d2h"), _trace("enc.wait", slot):
                 ev.synchronize()
+            if narrow and int(ovf_h[0, 0]) != 0:
+                # a symbol beyond int16 (latents of natural images are O(100)): code this call again on int32 buffers
+                stream.synchronize()
+                return self.compress(x, _wide=True)
             if debug is not None:
                 debug.update(symbols=sym_h.clone(), indexes=idx_h.clone(), z_symbols=zsym_h.clone())
-            with _phase("enc.rans"):
+            with _phase("enc.rans"), _trace("enc.rans", slot):
                 z_idx = self._z_indexes(tuple(zshape))
                 scratch = self.__dict__.setdefault("_enc_scratch", {})
                 y_strings += ans.encode_rows(y_table, sym_h.numpy(), idx_h.numpy(), scratch.setdefault(("y", slot), {}))
@@ -544,15 +608,17 @@ class _SliceCodec(CompressionModel):
             cache[zshape] = self.entropy_bottleneck._build_indexes(zshape).reshape(zshape[0], -1).numpy().copy()
         return cache[zshape]
 
-    def _host_buffers(self, tag, B, n):
-        """Pinned int32 staging buffer pair, cached per (tag, shape): cudaHostAlloc is slow."""
+    def _host_buffers(self, tag, B, n, dtypes=(torch.int32, torch.int32)):
+        """Pinned staging buffer pair (int32 unless `dtypes` says otherwise), cached per (tag, shape, dtypes): cudaHostAlloc
+        is slow (1.8 ms per call with eight ranks on one host), so every user has its own tag -- compress() and decompress()
+        shared one in round 1 and evicted each other's buffers every call."""
         cache = self.__dict__.setdefault("_pinned", {})
-        key = (tag, B, n)
+        key = (tag, B, n, tuple(dtypes))
         if key not in cache:
             for k in [k for k in cache if k[0] == tag]:
                 del cache[k]
-            cache[key] = (torch.empty((B, n), dtype=torch.int32, pin_memory=True),
-                          torch.empty((B, n), dtype=torch.int32, pin_memory=True))
+            cache[key] = (torch.empty((B, n), dtype=dtypes[0], pin_memory=True),
+                          torch.empty((B, n), dtype=dtypes[1], pin_memory=True))
         return cache[key]
 
     # ------------------------------------------------------------------ decoder
@@ -568,6 +634,7 @@ class _SliceCodec(CompressionModel):
         z_hat = ops.dequantize(z_sym.reshape(B, -1), 0, medians).reshape(z_sym.shape)
         st["scales"], st["means"] = self._hyper_synthesis(z_hat)
         st["y_hat"] = torch.empty_like(st["means"])
+        st["ovf"] = torch.zeros(1, dtype=torch.int32, device=z_hat.device)   # (never set: <= 256 scale levels, checked by the caller)
         return self._dec_params(st, 0)
 
     def _dec_params(self, st, i):
@@ -576,8 +643,9 @@ class _SliceCodec(CompressionModel):
         # per-slice entries keep every segment idempotent on `st` (graph warm-up runs a segment several times)
         st["mu", i], scale = self._slice_params(i, st["means"], st["scales"], st["y_hat"])
         B, h, w, Cs = scale.shape
-        idx = torch.empty((B, Cs * h * w), dtype=torch.int32, device=scale.device)
-        ops.slice_step_nhwc(scales=scale, indexes_out=idx, table=gc.host_scale_table(), scale_bound=gc.scale_bound_value())
+        idx = torch.empty((B, Cs * h * w), dtype=torch.uint8 if st.get("narrow") else torch.int32, device=scale.device)
+        ops.slice_step_nhwc(scales=scale, indexes_out=idx, table=gc.host_scale_table(), scale_bound=gc.scale_bound_value(),
+                            overflow=st["ovf"])
         return idx
 
     def _dec_slice(self, st, i, sym_prev):
@@ -595,14 +663,14 @@ class _SliceCodec(CompressionModel):
         self._dec_slice(st, self.num_slices, sym_prev)
         return self._synthesis_nhwc(st["y_hat"]).clamp_(0, 1)
 
-    def _decode_plan(self, plans, slot, B, C, zh, zw, device):
+    def _decode_plan(self, plans, slot, B, C, zh, zw, device, narrow=False):
         """13 CUDA-graph segments on one shared memory pool, captured once per (slot, B, z shape)."""
-        key = (slot, B, zh, zw)
+        key = (slot, B, zh, zw, narrow)
         if self._plan_slot(plans, key, 12):
             return plans[key]
         h, w = zh * 4, zw * 4
         n = self.slice_channels * h * w
-        st = {"hw": (h, w)}
+        st = {"hw": (h, w), "narrow": narrow}
         z0 = torch.zeros((B, C, zh, zw), dtype=torch.int32, device=device)
         s0 = torch.zeros((B, n), dtype=torch.int32, device=device)
         segs = [graphs.Segment(lambda t: self._dec_first(st, t), [z0])]
@@ -630,6 +698,7 @@ class _SliceCodec(CompressionModel):
         S = self.num_slices
         main = torch.cuda.current_stream()
         use_graphs = self._graphs_enabled()
+        narrow = _NARROW and gc.host_scale_table().size <= 256       # indexes come back as uint8
         if _DEVICE_DECODE and PHASE_TIMES is None:
             out = self._decompress_device(strings, B, C, zh, zw, device, use_graphs)
             if out is not None:
@@ -647,18 +716,19 @@ class _SliceCodec(CompressionModel):
         parts = []
         plans = self._plans("_dec_plans") if use_graphs else None
         streams = self.__dict__.setdefault("_part_streams", {})
-        for slot, (lo, hi) in enumerate(self._parts(B, use_graphs, _DEC_PARTS)):
+        for slot, (lo, hi) in enumerate(self._dec_parts(B, use_graphs)):
             p = Part()
             p.B = hi - lo
             p.stream = main if not use_graphs else streams.setdefault((str(device), slot), torch.cuda.Stream(device=device))
-            p.segs, p.st = self._decode_plan(plans, slot, p.B, C, zh, zw, device) if use_graphs else (None, {"hw": (h, w)})
+            p.segs, p.st = self._decode_plan(plans, slot, p.B, C, zh, zw, device, narrow) if use_graphs else \
+                (None, {"hw": (h, w), "narrow": narrow})
             p.decoders = _decoders(strings[0][lo:hi])
-            p.sym_h, p.idx_h = self._host_buffers(("y", slot), p.B, n)
-            p.zsym_h, _ = self._host_buffers(("z", slot), p.B, C * zh * zw)
+            p.sym_h, p.idx_h = self._host_buffers(("y_dec", slot), p.B, n, (torch.int32, torch.uint8 if narrow else torch.int32))
+            p.zsym_h, _ = self._host_buffers(("z_dec", slot), p.B, C * zh * zw)
             p.ev = torch.cuda.Event()
             p.plan = ans.DecodePlan(p.decoders, y_table, p.idx_h.numpy(), p.sym_h.numpy())
             p.next = 1                      # next segment to launch (segment i consumes the symbols of slice i - 1)
-            with _phase("dec.hyper"):
+            with _phase("dec.hyper"), _trace("dec.first", slot):
                 z_np = p.zsym_h.numpy()
                 z_idx = self._z_indexes((p.B, C, zh, zw))
                 ans.decode_batch(_decoders(strings[1][lo:hi]), z_table, [z_idx[b] for b in range(p.B)],
@@ -688,13 +758,14 @@ class _SliceCodec(CompressionModel):
                 ready = next((parts[k] for k in live if parts[k].ev.query()), None)
             if ready is None:               # nothing has landed yet: wait for the most advanced part that may proceed
                 ready = next((parts[k] for k in live if may_lead(k)), parts[live[0]])
-                with _phase("dec.slices.gpu"):
+                with _phase("dec.slices.gpu"), _trace("dec.wait", parts.index(ready), ready.next):
                     ready.ev.synchronize()
             p, i = ready, ready.next
             last = i == S
-            with _phase("dec.slices.rans"):
+            with _phase("dec.slices.rans"), _trace("dec.rans", parts.index(p), i):
                 p.plan.run()                # decoders advance by one slice: pinned indexes -> pinned symbols
-            with _phase("dec.synthesis" if last else "dec.slices.gpu"), torch.cuda.stream(p.stream):
+            with _phase("dec.synthesis" if last else "dec.slices.gpu"), torch.cuda.stream(p.stream), \
+                    _trace("dec.seg", parts.index(p), i, device=True):
                 if use_graphs:
                     out = p.segs[i](p.sym_h)          # pinned host buffer -> the segment's static input
                 else:
@@ -745,7 +816,7 @@ class _SliceCodec(CompressionModel):
         plans = self._plans("_dec_plans")
         streams = self.__dict__.setdefault("_part_streams", {})
         jobs = []
-        part_list = self._parts(B, use_graphs, _DEC_PARTS)
+        part_list = self._dec_parts(B, use_graphs)
         reserve = len(part_list) if len(part_list) > 1 else 0
         for slot, (lo, hi) in enumerate(part_list):
             ys = strings[0][lo:hi]
@@ -766,7 +837,7 @@ class _SliceCodec(CompressionModel):
                 plans[key] = (seg, st, ds)
             seg, st, ds = plans[key]
             ds.load(ys)
-            zsym_h, _ = self._host_buffers(("z", slot), Bp, C * zh * zw)
+            zsym_h, _ = self._host_buffers(("z_dec", slot), Bp, C * zh * zw)
             z_np = zsym_h.numpy()
             z_idx = self._z_indexes((Bp, C, zh, zw))
             ans.decode_batch(_decoders(strings[1][lo:hi]), z_table, [z_idx[b] for b in range(Bp)],

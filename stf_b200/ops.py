@@ -191,13 +191,15 @@ def _nhwc(t, name, C=None):
 
 def slice_step_nhwc(*, y=None, scales=None, means=None, symbols_in=None, sym_in_offset=0, symbols_out=None,
                     indexes_out=None, out_offset=0, y_hat=None, likelihood=None, lik_offset=0, table=None,
-                    scale_bound=0.11, lik_bound=1e-9, ste_round=False):
+                    scale_bound=0.11, lik_bound=1e-9, ste_round=False, overflow=None):
     """One slice step on NHWC operands (stf_slice_step_nhwc in include/stf_b200.h).
 
     y / scales / means / y_hat: (B, h, w, C<=32) NHWC views (channel slices of wider tensors are fine; y_hat is written).
     symbols_in / symbols_out / indexes_out: (B, total) int32 buffers in coding order, the slice at element offset
     sym_in_offset / out_offset of every row.  likelihood: (B, M, h, w) NCHW tensor, the slice at channel lik_offset.
-    The step (forward / encode / decode / indexes) follows from which arguments are given."""
+    The step (forward / encode / decode / indexes) follows from which arguments are given.
+    Narrow outputs: symbols_out int16 and / or indexes_out uint8 (both narrow when both are given) with `overflow`, a
+    zero-initialised int32 CUDA tensor of one element that the kernel sets when a value does not fit."""
     ref = next(t for t in (y, scales, means, y_hat) if t is not None)
     B, h, w, C = ref.shape
     plane = h * w
@@ -210,17 +212,22 @@ def slice_step_nhwc(*, y=None, scales=None, means=None, symbols_in=None, sym_in_
         symbols_in = _dev(symbols_in, "symbols_in", torch.int32)
         a.symbols_in, a.symbols_in_batch_stride = symbols_in.data_ptr() + 4 * sym_in_offset, symbols_in.shape[1]
     total = None
-    for name, buf in (("symbols_out", symbols_out), ("indexes_out", indexes_out)):
-        if buf is None:
-            continue
-        buf = _dev(buf, name, torch.int32)
+    outs = [(n_, b_, w_, nd_) for n_, b_, w_, nd_ in (("symbols_out", symbols_out, torch.int32, torch.int16),
+                                                       ("indexes_out", indexes_out, torch.int32, torch.uint8)) if b_ is not None]
+    narrow = bool(outs) and all(b_.dtype == nd_ for _, b_, _, nd_ in outs)
+    for name, buf, wide_dt, narrow_dt in outs:
+        buf = _dev(buf, name, narrow_dt if narrow else wide_dt)
         if total is not None and buf.shape[1] != total:
             raise ValueError("symbols_out and indexes_out must have the same row length")
         total = buf.shape[1]
         if out_offset + C * plane > total:
             raise ValueError(f"{name} buffer too small")
-        setattr(a, name, buf.data_ptr() + 4 * out_offset)
+        setattr(a, name, buf.data_ptr() + buf.element_size() * out_offset)
     a.out_batch_stride = total or 0
+    if narrow:
+        if overflow is None:
+            raise ValueError("narrow symbols_out / indexes_out need an `overflow` flag tensor")
+        a.narrow, a.overflow = 1, _dev(overflow, "overflow", torch.int32).data_ptr()
     if likelihood is not None:
         likelihood = _dev(likelihood, "likelihood")
         a.likelihood = likelihood.data_ptr() + 4 * lik_offset * plane

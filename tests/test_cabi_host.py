@@ -138,6 +138,37 @@ def test_rans_both_step_variants_match_oracle(tables, lo, hi):
     assert np.array_equal(d.decode_stream_array(idxs[0], tab), syms[0])
 
 
+def test_rans_narrow_transfer_format_same_bytes(tables):
+    """stf_rans_encode_batch_narrow (int16 symbols, uint8 indexes) and stf_rans_decode_batch_u8 give the bytes / symbols of
+    the int32 entry points (narrow and wide runs, escapes within int16, ragged lockstep groups)."""
+    cdf, lens, offs, tab = tables
+    rng = np.random.default_rng(21)
+    table = OE.scale_table().numpy()
+    B, n = 7, 2500
+    for lo, hi in ((0, 20), (30, 64)):
+        ix = rng.integers(lo, hi, size=(B, n)).astype(np.int32)
+        sy = np.rint(rng.standard_normal((B, n)) * table[ix] * 2.0).astype(np.int32)
+        sy[:, ::53] = rng.integers(-30000, 30000, size=sy[:, ::53].shape)
+        want = [ans.encode_array(tab, sy[b], ix[b]) for b in range(B)]
+        for threads in (1, 2, 8):
+            assert ans.encode_rows(tab, sy, ix, threads=threads) == want
+            assert ans.encode_rows(tab, sy.astype(np.int16), ix.astype(np.uint8), threads=threads) == want
+            decs = []
+            for s_ in want:
+                d = ans.RansDecoder()
+                d.set_stream(s_)
+                decs.append(d)
+            out = np.empty((B, n), dtype=np.int32)
+            half = n // 2
+            ix8 = ix.astype(np.uint8)
+            ans.DecodePlan(decs, tab, np.ascontiguousarray(ix8[:, :half]), out[:, :half].copy(), threads=threads).run()
+            plan = ans.DecodePlan(decs, tab, np.ascontiguousarray(ix8[:, half:]), np.empty((B, n - half), np.int32), threads=threads)
+            plan.run()
+            assert np.array_equal(plan._keep[3], sy[:, half:])
+    with pytest.raises(TypeError):
+        ans.encode_rows(tab, sy.astype(np.int16), ix)
+
+
 def test_rans_batch_threads_identical(tables):
     cdf, lens, offs, tab = tables
     rng = np.random.default_rng(3)

@@ -207,13 +207,15 @@ def test_pipelined_halves_equal_single_part(golden_dir, monkeypatch):
 
 
 def test_three_ragged_sub_batches_from_48_images(golden_dir):
-    """From 48 images compress / decompress run three pipelined sub-batches (50 images -> 19 + 17 + 14): every image's
+    """From 48 images compress / decompress run three pipelined sub-batches (50 images -> 22 + 19 + 9 / 19 + 17 + 14): every image's
     own stream decodes to what a batch-1 compress / decompress of that image gives (up to cuDNN's per-batch algorithm
     choice), and the decoder's reconstruction equals the forward pass."""
     from stf_b200 import models as M
     net, _ = _build(golden_dir, "stf")
-    assert [hi - lo for lo, hi in net._parts(50, True)] == [19, 17, 14]          # tapered: the last part's rANS is the exposed tail
+    assert [hi - lo for lo, hi in net._enc_parts(50)] == [22, 19, 9]             # small last part: its rANS is the exposed tail
+    assert [hi - lo for lo, hi in net._parts(50, True)] == [19, 17, 14]          # decompress(): tapered thirds
     assert [hi - lo for lo, hi in net._parts(64, True)] == [24, 22, 18] and len(net._parts(32, True)) == 2
+    assert [hi - lo for lo, hi in net._enc_parts(64)] == [28, 24, 12] and len(net._enc_parts(32)) == 2
     x = torch.cat([synthetic_image(1, 64, 64, seed=100 + s) for s in range(50)]).cuda()
     enc = net.compress(x)
     assert [len(g) for g in enc["strings"]] == [50, 50]
@@ -221,7 +223,7 @@ def test_three_ragged_sub_batches_from_48_images(golden_dir):
     fwd = net(x)["x_hat"].clamp(0, 1)                                  # ONE batch of 50: other geometry, same results
     per_image = (dec - fwd).abs().flatten(1).max(dim=1).values
     assert per_image.max().item() < 1e-4, per_image.max().item()
-    for i in (0, 18, 19, 35, 36, 49):                                  # first / last image of every sub-batch
+    for i in (0, 18, 19, 21, 22, 40, 41, 49):                          # first / last image of every sub-batch (either split)
         e1 = net.compress(x[i:i + 1])
         assert e1["strings"][0][0] == enc["strings"][0][i] and e1["strings"][1][0] == enc["strings"][1][i], i
         d1 = net.decompress(e1["strings"], e1["shape"])["x_hat"]
@@ -242,3 +244,35 @@ def test_cuda_graph_path_equals_eager(golden_dir):
     dec_e = net.decompress(enc_e["strings"], enc_e["shape"])["x_hat"]
     assert enc_e["strings"] == enc_g["strings"]
     assert torch.equal(dec_e, dec_g)
+
+
+def test_narrow_transfer_format_same_strings_and_int16_overflow_falls_back(golden_dir, monkeypatch):
+    """Symbols / indexes cross PCIe as int16 / uint8 by default: same strings and reconstruction as the int32 path; an
+    image whose latents do not fit int16 makes compress() repeat the call on int32 buffers (same strings as a wide run)."""
+    from stf_b200 import models as M
+    net, _ = _build(golden_dir, "stf")
+    x = torch.cat([synthetic_image(1, 64, 128, seed=40 + s) for s in range(3)]).cuda()
+    assert M._NARROW
+    enc_n = net.compress(x)
+    dec_n = net.decompress(enc_n["strings"], enc_n["shape"])["x_hat"].clone()
+    assert any(k[3] == (torch.int16, torch.uint8) for k in net._pinned if k[0][0] == "y")
+    assert any(k[3] == (torch.int32, torch.uint8) for k in net._pinned if k[0][0] == "y_dec")
+    monkeypatch.setattr(M, "_NARROW", False)
+    enc_w = net.compress(x)
+    dec_w = net.decompress(enc_w["strings"], enc_w["shape"])["x_hat"].clone()
+    assert enc_w["strings"] == enc_n["strings"] and torch.equal(dec_w, dec_n)
+    net.cuda_graphs = False
+    analysis = net._analysis_nhwc                     # latents far beyond int16: scale the analysis transform's output
+    monkeypatch.setattr(net, "_analysis_nhwc", lambda t: analysis(t) * 2.0e4)
+    big = x
+    enc_big_w = net.compress(big)
+    assert enc_big_w["strings"] != enc_w["strings"]
+    monkeypatch.setattr(M, "_NARROW", True)
+    calls = []
+    orig = net._encode_gpu
+    monkeypatch.setattr(net, "_encode_gpu", lambda t, keep=None, narrow=False: (calls.append(narrow), orig(t, keep=keep, narrow=narrow))[1])
+    enc_big_n = net.compress(big)
+    assert calls == [True, False], calls              # narrow attempt, then the wide repeat
+    assert enc_big_n["strings"] == enc_big_w["strings"]
+    dec_big = net.decompress(enc_big_n["strings"], enc_big_n["shape"])["x_hat"]
+    assert torch.isfinite(dec_big).all()

@@ -192,16 +192,16 @@ def test_config3_stf_768x512_vs_oracle(golden_dir, mode):
 
 
 def test_config3_image_out_of_batch64_equals_batch1_and_oracle(golden_dir):
-    """The bench configuration itself (batch 64 -> three pipelined sub-batches of 24 / 22 / 18, CUDA graphs, default
+    """The bench configuration itself (batch 64 -> three pipelined sub-batches of 28 / 24 / 12, CUDA graphs, default
     precision): the strings of one image taken out of the batch are byte-identical to a batch-1 compress of that image (no
     kernel upstream of a bitstream depends on the batch geometry), they decode alone, and they agree with the oracle's
     coding of the same image within the default-mode flip bound."""
     from oracle import codec as OC
     net = _net(golden_dir, "stf")
     x = torch.cat([synthetic_image(1, 512, 768, seed=300 + s) for s in range(64)])
-    assert [hi - lo for lo, hi in net._parts(64, True)] == [24, 22, 18]
+    assert [hi - lo for lo, hi in net._enc_parts(64)] == [28, 24, 12]
     enc = net.compress(x.cuda())
-    for i in (0, 23, 24, 45, 46, 63):                              # first / last image of every sub-batch
+    for i in (0, 27, 28, 51, 52, 63):                              # first / last image of every sub-batch
         e1 = net.compress(x[i:i + 1].cuda())
         assert e1["strings"][0][0] == enc["strings"][0][i] and e1["strings"][1][0] == enc["strings"][1][i], i
     i = 43

@@ -282,3 +282,38 @@ def test_device_rans_decoder_matches_host_decoder():
     ok = [b for b in range(B) if b != 5]
     assert np.array_equal(got[ok], sy[ok])
     assert (status[ok] == 0).all() and status[5] == -6
+
+
+def test_slice_step_narrow_outputs_equal_wide_and_flag_overflow():
+    """stf_slice_step_nhwc with int16 symbols / uint8 indexes (the 3-byte-per-symbol transfer format): same values as the
+    int32 outputs, at a non-zero output offset; a symbol beyond int16 sets the overflow flag (and only then)."""
+    from stf_b200 import ops
+    from stf_b200.models import get_scale_table
+    torch.manual_seed(3)
+    B, h, w, C = 3, 9, 7, 32                       # ragged: plane 63 is not a multiple of the 32-pixel tile
+    y = (torch.randn(B, h, w, C, device="cuda") * 40).contiguous()
+    mu = torch.randn(B, h, w, C, device="cuda")
+    sc = (torch.rand(B, h, w, C, device="cuda") * 60 + 0.05).contiguous()
+    table = get_scale_table()
+    total, off = 2 * C * h * w, C * h * w
+    sym32 = torch.zeros((B, total), dtype=torch.int32, device="cuda")
+    idx32 = torch.zeros_like(sym32)
+    ops.slice_step_nhwc(y=y, scales=sc, means=mu, symbols_out=sym32, indexes_out=idx32, out_offset=off, table=table)
+    sym16 = torch.zeros((B, total), dtype=torch.int16, device="cuda")
+    idx8 = torch.zeros((B, total), dtype=torch.uint8, device="cuda")
+    ovf = torch.zeros(1, dtype=torch.int32, device="cuda")
+    ops.slice_step_nhwc(y=y, scales=sc, means=mu, symbols_out=sym16, indexes_out=idx8, out_offset=off, table=table, overflow=ovf)
+    assert int(ovf.item()) == 0
+    assert torch.equal(sym16.int(), sym32) and torch.equal(idx8.int(), idx32)
+    assert int(sym32[:, off:].abs().max()) > 50 and int(idx32.max()) > 40 and not sym32[:, :off].any()
+    # indexes only (the decoder's step)
+    idx8b = torch.zeros((B, C * h * w), dtype=torch.uint8, device="cuda")
+    ops.slice_step_nhwc(scales=sc, indexes_out=idx8b, table=table, overflow=ovf)
+    assert int(ovf.item()) == 0 and torch.equal(idx8b.int(), idx32[:, off:])
+    # overflow: one latent beyond int16
+    y2 = y.clone()
+    y2[1, 4, 3, 17] = 40000.0
+    ops.slice_step_nhwc(y=y2, scales=sc, means=mu, symbols_out=sym16, indexes_out=idx8, out_offset=off, table=table, overflow=ovf)
+    assert int(ovf.item()) == 1
+    with pytest.raises(ValueError):
+        ops.slice_step_nhwc(y=y, scales=sc, means=mu, symbols_out=sym16, indexes_out=idx8, out_offset=off, table=table)
