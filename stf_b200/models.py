@@ -61,6 +61,9 @@ def _split_env(name):
 
 # explicit relative sub-batch sizes, first to last, e.g. "3,5,4" (overrides the tapered default below)
 _ENC_SPLIT, _DEC_SPLIT = _split_env("STF_B200_ENC_SPLIT"), _split_env("STF_B200_DEC_SPLIT")
+# CTA cap of each of the two conv stacks of a slice (parallel graph branches): half the SMs each, so that the latency-bound
+# small layers of the two stacks overlap instead of queueing behind each other (batch 64: -1.3 ms per step; 0 = no cap)
+_SLICE_CTAS = int(os.environ.get("STF_B200_SLICE_CTAS", "74"))
 _PART_TAPER = float(os.environ.get("STF_B200_PART_TAPER", "0.75"))    # size of the last sub-batch relative to the first
 _DEC_LEAD = int(os.environ.get("STF_B200_DEC_LEAD", "3"))               # decompress(): slices a sub-batch may lead the next one by
 TRACE = None         # set to a list to collect a host / device timeline of the pipelined step (tools/timeline.py)
@@ -344,9 +347,13 @@ class _SliceCodec(CompressionModel):
         main = torch.cuda.current_stream()
         side = self._side_stream(main.device)
         side.wait_stream(main)
-        with torch.cuda.stream(side):
-            scale = self._conv_stack(self.cc_scale_transforms[i], [latent_scales] + extra)
-        mu = self._conv_stack(self.cc_mean_transforms[i], [latent_means] + extra)
+        old_cap, ops.MAX_CTAS = ops.MAX_CTAS, _SLICE_CTAS or ops.MAX_CTAS
+        try:
+            with torch.cuda.stream(side):
+                scale = self._conv_stack(self.cc_scale_transforms[i], [latent_scales] + extra)
+            mu = self._conv_stack(self.cc_mean_transforms[i], [latent_means] + extra)
+        finally:
+            ops.MAX_CTAS = old_cap
         main.wait_stream(side)
         scale.record_stream(main)
         return mu, scale
