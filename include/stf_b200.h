@@ -252,6 +252,22 @@ int stf_window_attention(const float *qkv, float *out, const float *bias_table, 
 int stf_window_attention_tokens(const float *qkv, float *out, const float *bias_table, const float *pad_qkv, int batch,
                                 int H, int W, int C, int heads, int ws, int shift, int precision, void *stream);
 
+/* Fused Swin MLP half-block (stf.py:196-197 with Mlp = stf.py:25-40):
+ *   y = x + fc2( GELU( fc1( LayerNorm(x) ) ) )      x, y: (M tokens, C) fp32 rows of x_ld / y_ld floats; hidden = fc1 width
+ * One kernel per 128-token tile: the hidden activations stay in shared memory / TMEM (HBM sees x in and y out only).
+ * w1_packed / w2_packed: stf_pack_conv images (ksize 1) of fc1 -- with the LayerNorm folded, has_ln -- and fc2, packed for the
+ * precision of this call.  C: multiple of 16, <= 192; hidden: multiple of 32.  y may alias x. */
+typedef struct {
+  const float *x; int x_ld;
+  float *y; int y_ld;
+  int64_t M; int C, hidden;
+  const float *w1_packed, *w2_packed;
+  float ln_eps;
+  int precision;                        /* STF_PREC_FP32 (3xTF32) or STF_PREC_TF32 */
+  int max_ctas;                         /* > 0: cap the persistent grid */
+} stf_mlp_args;
+int stf_swin_mlp(const stf_mlp_args *args, void *stream);
+
 /* ------------------------------------------------------------------------------------------
  * Convolution stacks either side of the entropy kernels: the five-layer 3x3 cc_mean / cc_scale /
  * lrp stacks of the slice loop (stf.py:510-548 called at :613-633, :706-729, :757-779; cnn.py:89-127), the hyperprior

@@ -63,6 +63,14 @@ class SliceArgs(ctypes.Structure):
     ]
 
 
+class MlpArgs(ctypes.Structure):
+    """struct stf_mlp_args (include/stf_b200.h)."""
+    _fields_ = [
+        ("x", c_vp), ("x_ld", c_int), ("y", c_vp), ("y_ld", c_int), ("M", c_i64), ("C", c_int), ("hidden", c_int),
+        ("w1_packed", c_vp), ("w2_packed", c_vp), ("ln_eps", c_f32), ("precision", c_int), ("max_ctas", c_int),
+    ]
+
+
 # name -> (restype, argtypes); mirrors include/stf_b200.h one to one (tests check the export list)
 SIGNATURES = {
     "stf_version": (ctypes.c_char_p, []),
@@ -82,6 +90,7 @@ SIGNATURES = {
     "stf_pack_linear": (c_int, [c_vp, c_vp, c_vp, c_vp, c_vp, c_int, c_int, c_int, c_vp]),
     "stf_linear": (c_int, [ctypes.POINTER(LinearArgs), c_vp]),
     "stf_window_attention": (c_int, [c_vp, c_vp, c_vp, c_vp, c_int, c_i64, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_vp]),
+    "stf_swin_mlp": (c_int, [ctypes.POINTER(MlpArgs), c_vp]),
     "stf_window_attention_tokens": (c_int, [c_vp, c_vp, c_vp, c_vp, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_vp]),
     "stf_packed_conv_floats": (c_i64, [ctypes.POINTER(ConvArgs)]),
     "stf_pack_conv": (c_int, [ctypes.POINTER(ConvArgs), c_vp, c_vp, c_vp, c_vp, c_int, c_f32, c_vp, c_vp]),

@@ -15,7 +15,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIBDIR = os.path.join(HERE, "lib")
 LIB = os.path.join(LIBDIR, "libstf_b200.so")
-SOURCES = ["entropy_kernels.cu", "linear_tcgen05.cu", "window_attention.cu", "train_kernels.cu", "conv_glue.cu", "conv_tcgen05.cu", "rans_device.cu", "rans_host.cpp"]
+SOURCES = ["entropy_kernels.cu", "linear_tcgen05.cu", "window_attention.cu", "train_kernels.cu", "conv_glue.cu", "conv_tcgen05.cu", "mlp_tcgen05.cu", "rans_device.cu", "rans_host.cpp"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
     "-Xcompiler", "-fPIC,-O3,-fvisibility=default", "--use_fast_math=false",

@@ -1,0 +1,576 @@
+// Fused Swin MLP half-block on 5th-gen tensor cores:
+//
+//   Y = X + fc2( GELU( fc1( LayerNorm(X) ) ) )            X, Y: (M tokens, C) fp32, hidden = 4 C
+//
+// Replaces (reference memory4963/STF): `x = x + self.drop_path(self.mlp(self.norm2(x)))` (compressai/models/stf.py:196-197)
+// with Mlp = fc1 -> GELU -> fc2 (stf.py:25-40), i.e. nn.LayerNorm + two nn.Linear + nn.GELU + the shortcut add.
+//
+// Why one kernel: at C = 48 / 96 (the full-resolution stages: 6.3 M / 1.6 M tokens per batch of 64 images) the two Linear
+// launches are HBM-bound on the HIDDEN activations -- fc1 writes 16 C bytes per token and fc2 reads them back, against the
+// 8 C bytes of X in and Y out that the algorithm needs.  Here a 128-token tile never leaves the SM, and the hidden
+// activations never leave TENSOR MEMORY:
+//   X tile  --TMA-->  shared memory (raw fp32 = TF32 hi operand; lo plane + LayerNorm row statistics by the A-pass warps)
+//   GEMM1   D1[128 x 64] = X . W1c^T           one 64-column chunk of the hidden layer at a time; TMEM, double buffered
+//   epi 1   tcgen05.ld -> LN fold + bias + exact-erf GELU -> tcgen05.st: the chunk goes back into TMEM in place (hi = the
+//           raw fp32 value, of which the tensor core reads the upper 19 bits) with its lo part (3xTF32) in the columns behind
+//   GEMM2   D2[128 x C] += Hc . W2c^T          A operand read from TMEM (tcgen05.mma with [a_tmem]), W2c from shared memory
+//   epi 2   + bias + shortcut (the raw X tile, still in shared memory) -> global
+// HBM sees 8 C bytes per token; the weights stream from L2 once per tile.  The first version kept the hidden chunk in shared
+// memory as GEMM2's A operand in 32-column chunks: every tcgen05.mma reads its whole A tile (128 rows x 32 B = 4 KB) through
+// the 128 B/clk shared-memory port whatever N is, so N = 32 / 48 MMAs ran at 40-48 clk each and the kernel was 1.6x SLOWER than
+// the two launches (4.9 vs 3.1 ms at C = 48); with A in TMEM GEMM2 only reads the small weight tile, and GEMM1 uses N = 64.
+// The hidden layer is never rounded to anything coarser than the GEMM mode's own operand precision (3xTF32: hi + lo), so
+// results match the two-launch path to fp32 round-off; the K order of both GEMMs is fixed, hence batch-invariant like the rest.
+//
+// Warp roles (640 threads, one persistent CTA per SM): warp 0 TMA producer (X, W1), warp 1 MMA issuer (+ TMEM alloc), warp 2 TMA
+// producer (W2), warps 4-11 epilogue 1 (warp & 3 = TMEM lane quadrant, two warps per quadrant on the two halves of a chunk),
+// warps 12-15 A pass, warps 16-19 epilogue 2 (the output tile of tile i leaves while epilogue 1 is on tile i + 1).  All waits
+// are mbarrier.test_wait spins: every hand-off here is on a per-chunk critical path.
+// Measured (B200, 6.3 M tokens, C = 48; tools/bench_mlp.py): 3xTF32 2.90 ms against 3.09 ms for the two launches, single-pass
+// TF32 2.20 against 2.83 ms; C = 96 (1.6 M tokens): 2.19 / 1.87 ms and 1.24 / 1.47 ms.  The kernel is bound by the MMA issuer:
+// 126 small tcgen05.mma per tile (N = 64 / 48, K = 8) at ~90-100 cycles each, clock64-traced -- not by HBM (0.83 TB/s
+// algorithmic) and not by accumulator dependencies (separate accumulators for the hi and lo passes change nothing).
+#include <cuda.h>
+#include <math.h>
+#include <stdlib.h>
+
+#include <mutex>
+
+#include "common.cuh"
+#include "sm100.cuh"
+
+namespace stf {
+namespace {
+
+using namespace sm100;
+
+constexpr int kTileM = 128;
+constexpr int kBlockK = 32;                      // floats per k-block = one 128-byte swizzle row
+constexpr uint32_t kABlockBytes = kTileM * 128;  // 16 KB: 128 rows x one k-block
+constexpr int kChunk = 64;                       // hidden columns per chunk = two k-blocks of GEMM2
+constexpr uint32_t kW1BlockBytes = kChunk * 128; // 8 KB: 64 weight rows x one k-block
+constexpr int kThreads = 640;
+constexpr int kProducerWarp = 0, kMmaWarp = 1, kW2Warp = 2, kFirstEpiWarp = 4, kEpiWarps = 8, kFirstSplitWarp = 12, kFirstOutWarp = 16,
+              kOutWarps = 4;
+constexpr int kMaxSlots = 2;
+constexpr uint32_t kHBufCols = 2 * kChunk;       // TMEM columns per hidden buffer: D1 / H hi, H lo
+constexpr uint32_t kD2Col0 = 2 * kHBufCols;      // D2 buffer b: columns [256 + b * C, ...)
+
+struct MlpParams {
+  alignas(64) CUtensorMap x_map;       // [M][C], box [32][128]
+  alignas(64) CUtensorMap w1_map[2];   // hi, lo: [hidden][Kp1], box [32][64]
+  alignas(64) CUtensorMap w2_map[2];   // hi, lo: [C][hidden], box [32][C]
+  const float *t1, *s1, *t2;           // fc1: t = beta.W^T + bias, s = row sums of gamma o W (LayerNorm fold); fc2: bias
+  float *y;
+  int y_ld;
+  int64_t M;
+  int m_tiles, C, hidden, kb1, nch, ln_pad, k1_steps;
+  float ln_eps;
+  uint32_t idesc1, idesc2;
+  int x_bufs, w1_slots, w2_slots, tmem_cols;
+  uint32_t x_bytes, w1_plane_bytes, w2_block_bytes, w2_plane_bytes;
+  int debug;   // bring-up ablations (env STF_B200_MLP_DEBUG): 1 no GELU math, 4 no stores, 8 no A pass, 16 no MMAs, 32 no weight loads,
+               // 64 plain arrives instead of tcgen05.commit (with 16); outputs are garbage
+};
+
+__device__ __forceinline__ void tma_load_2d(uint32_t smem_dst, const CUtensorMap *map, uint64_t *bar, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(smem_dst),
+      "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap *map) {
+  asm volatile("prefetch.tensormap [%0];" ::"l"(map) : "memory");
+}
+// K-major SWIZZLE_128B operand descriptor (see csrc/conv_tcgen05.cu: rows of 128 B, 8-row atoms of 1024 B).
+__device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t smem_addr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr >> 4) & 0x3FFF);
+  d |= (uint64_t)1 << 16;
+  d |= (uint64_t)(1024 >> 4) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)2 << 61;
+  return d;
+}
+// D[tmem] (+)= A[tmem] . B[smem]^T: the A operand (128 lanes = rows, one 32-bit column per K element) comes from tensor memory.
+__device__ __forceinline__ void umma_tf32_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n\t}" ::"r"(d_tmem),
+      "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// 32 lanes x 16 consecutive 32-bit columns <- 16 registers per thread
+__device__ __forceinline__ void tmem_st16(uint32_t taddr, const float (&v)[16]) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16};" ::"r"(taddr),
+      "r"(__float_as_uint(v[0])), "r"(__float_as_uint(v[1])), "r"(__float_as_uint(v[2])), "r"(__float_as_uint(v[3])),
+      "r"(__float_as_uint(v[4])), "r"(__float_as_uint(v[5])), "r"(__float_as_uint(v[6])), "r"(__float_as_uint(v[7])),
+      "r"(__float_as_uint(v[8])), "r"(__float_as_uint(v[9])), "r"(__float_as_uint(v[10])), "r"(__float_as_uint(v[11])),
+      "r"(__float_as_uint(v[12])), "r"(__float_as_uint(v[13])), "r"(__float_as_uint(v[14])), "r"(__float_as_uint(v[15]))
+      : "memory");
+}
+__device__ __forceinline__ void tmem_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ float4 lds128(uint32_t addr) {
+  float4 v;
+  asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
+  return v;
+}
+__device__ __forceinline__ void sts128(uint32_t addr, float4 v) {
+  asm volatile("st.shared.v4.f32 [%0], {%1,%2,%3,%4};" ::"r"(addr), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+}
+// Exact-erf GELU, the evaluation of the two-launch path (csrc/conv_tcgen05.cu: Abramowitz-Stegun 7.1.26).
+__device__ __forceinline__ float gelu_erf(float x) {
+  const float ax = fabsf(x) * 0.70710678118654752440f;
+  float t;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(t) : "f"(fmaf(0.3275911f, ax, 1.0f)));
+  float p = fmaf(t, 1.061405429f, -1.453152027f);
+  p = fmaf(t, p, 1.421413741f);
+  p = fmaf(t, p, -0.284496736f);
+  p = fmaf(t, p, 0.254829592f);
+  const float e = __expf(-ax * ax);
+  const float erf_abs = fmaf(-p * t, e, 1.0f);
+  return 0.5f * x * (1.0f + copysignf(erf_abs, x));
+}
+__device__ __forceinline__ float trunc_tf32(float x) { return __uint_as_float(__float_as_uint(x) & 0xFFFFE000u); }
+
+// kC = C at compile time: the MMA issuer's loops unroll and every operand descriptor is a base (one per call) plus a
+// constant -- with run-time loop bounds the issuing warp spent ~2000 cycles of dependent integer instructions per chunk on
+// descriptor arithmetic, more than the MMAs themselves take (measured with clock64 traces; the kernel was bound by that warp).
+template <int kPrecise, int kC>
+__global__ void __launch_bounds__(kThreads, 1) swin_mlp_kernel(const __grid_constant__ MlpParams P) {
+  constexpr int kKb1 = (kC + kBlockK - 1) / kBlockK, kK1Steps = (kC + 7) / 8;
+  constexpr uint32_t kXBytes = kKb1 * kABlockBytes, kW1PlaneBytes = kKb1 * kW1BlockBytes;
+  constexpr uint32_t kW2BlockBytes = kC * 128u, kW2PlaneBytes = (kChunk / kBlockK) * kW2BlockBytes;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw_u32 = smem_u32(smem_raw);
+  uint8_t *smem = smem_raw + ((1024u - (raw_u32 & 1023u)) & 1023u);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  constexpr uint32_t kPlanes = kPrecise ? 2 : 1;
+  // ---- shared-memory carve-up (every operand region is a multiple of 1024 bytes)
+  uint8_t *x_raw = smem;                                                    // [x_bufs][kb1 x 16 KB]
+  uint8_t *x_lo = x_raw + (size_t)P.x_bufs * kXBytes;                     // [kb1 x 16 KB]                  (3xTF32)
+  uint8_t *w1_ring = x_lo + (kPrecise ? kXBytes : 0);                     // [w1_slots][planes x kb1 x 8 KB]
+  uint8_t *w2_ring = w1_ring + (size_t)P.w1_slots * kPlanes * kW1PlaneBytes;   // [w2_slots][planes x 2 x C x 128 B]
+  float *t1_s = reinterpret_cast<float *>(w2_ring + (size_t)P.w2_slots * kPlanes * kW2PlaneBytes);
+  float *s1_s = t1_s + P.hidden;
+  float *t2_s = s1_s + P.hidden;
+  float2 *stats = reinterpret_cast<float2 *>(t2_s + ((kC + 31) & ~31));   // [x_bufs][128] (mean, rstd)
+  uint64_t *bars = reinterpret_cast<uint64_t *>(stats + (size_t)P.x_bufs * kTileM);
+  uint64_t *x_full = bars, *x_ready = x_full + kMaxSlots, *x_empty = x_ready + kMaxSlots, *g1_done = x_empty + kMaxSlots,
+           *w1_full = g1_done + 1, *w1_empty = w1_full + kMaxSlots, *w2_full = w1_empty + kMaxSlots,
+           *w2_empty = w2_full + kMaxSlots, *d1_full = w2_empty + kMaxSlots, *h_full = d1_full + 2, *d2_full = h_full + 2,
+           *d2_empty = d2_full + 2;
+  uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(d2_empty + 2);
+
+  for (int i = threadIdx.x; i < P.hidden; i += kThreads) t1_s[i] = __ldg(P.t1 + i), s1_s[i] = __ldg(P.s1 + i);
+  for (int i = threadIdx.x; i < kC; i += kThreads) t2_s[i] = __ldg(P.t2 + i);
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < kMaxSlots; ++s) {
+      mbar_init(&x_full[s], 1), mbar_init(&x_ready[s], 4), mbar_init(&x_empty[s], kOutWarps);
+      mbar_init(&w1_full[s], 1), mbar_init(&w1_empty[s], 1), mbar_init(&w2_full[s], 1), mbar_init(&w2_empty[s], 1);
+      mbar_init(&d1_full[s], 1), mbar_init(&h_full[s], kEpiWarps);
+      mbar_init(&d2_full[s], 1), mbar_init(&d2_empty[s], kOutWarps);
+    }
+    mbar_init(g1_done, 1);
+    mbar_fence_init();
+    tma_prefetch_desc(&P.x_map);
+    tma_prefetch_desc(&P.w1_map[0]);
+    tma_prefetch_desc(&P.w2_map[0]);
+    if (kPrecise) tma_prefetch_desc(&P.w1_map[1]), tma_prefetch_desc(&P.w2_map[1]);
+  }
+  if (warp == kMmaWarp) tmem_alloc(tmem_slot, (uint32_t)P.tmem_cols);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const int n_my = (P.m_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;   // tiles of this CTA
+  const uint32_t XB = (uint32_t)P.x_bufs, S1 = (uint32_t)P.w1_slots, S2 = (uint32_t)P.w2_slots;
+  const uint32_t w1_slot_bytes = kPlanes * kW1PlaneBytes, w2_slot_bytes = kPlanes * kW2PlaneBytes;
+
+  if (warp == kProducerWarp) {
+    // =========================== TMA producer: X tiles and fc1 weight chunks (whole warp, one elected lane issues) ===========
+    const bool leader = elect_one();
+    auto load_x = [&](int ti) {
+      const uint32_t xb = (uint32_t)ti % XB, u = (uint32_t)ti / XB;
+      mbar_wait_spin(&x_empty[xb], (u & 1u) ^ 1u);
+      if (leader) {
+        mbar_arrive_expect_tx(&x_full[xb], kXBytes);
+        const int row0 = ((int)blockIdx.x + ti * (int)gridDim.x) * kTileM;
+        for (int kb = 0; kb < kKb1; ++kb)
+          tma_load_2d(smem_u32(x_raw) + xb * kXBytes + (uint32_t)kb * kABlockBytes, &P.x_map, &x_full[xb], kb * kBlockK, row0);
+      }
+      __syncwarp();
+    };
+    if (n_my > 0) load_x(0);
+    uint32_t g = 0;
+    for (int ti = 0; ti < n_my; ++ti) {
+      if (XB == 1 && ti > 0) load_x(ti);
+      for (int j = 0; j < P.nch; ++j, ++g) {
+        const uint32_t s1 = g % S1, u1 = g / S1;
+        mbar_wait_spin(&w1_empty[s1], (u1 & 1u) ^ 1u);
+        if (leader && (P.debug & 32)) {
+          mbar_arrive(&w1_full[s1]);
+        } else if (leader) {
+          mbar_arrive_expect_tx(&w1_full[s1], w1_slot_bytes);
+          const uint32_t base = smem_u32(w1_ring) + s1 * w1_slot_bytes;
+          for (int kb = 0; kb < kKb1; ++kb) {
+            tma_load_2d(base + (uint32_t)kb * kW1BlockBytes, &P.w1_map[0], &w1_full[s1], kb * kBlockK, j * kChunk);
+            if (kPrecise)
+              tma_load_2d(base + kW1PlaneBytes + (uint32_t)kb * kW1BlockBytes, &P.w1_map[1], &w1_full[s1], kb * kBlockK, j * kChunk);
+          }
+        }
+        __syncwarp();
+        // next tile's X lands under this tile's chunks; issued one chunk in: its buffer is released by the previous tile's
+        // epilogue 2, which runs while the MMA warp is on this tile's first chunk
+        if (j == (P.nch > 1 ? 1 : 0) && XB == 2 && ti + 1 < n_my) load_x(ti + 1);
+      }
+    }
+  } else if (warp == kW2Warp) {
+    // =========================== TMA producer of the fc2 weight chunks ===========================
+    const bool leader = elect_one();
+    const uint32_t G = (uint32_t)n_my * (uint32_t)P.nch;
+    for (uint32_t g = 0; g < G; ++g) {
+      const uint32_t j = g % (uint32_t)P.nch, s2 = g % S2, u2 = g / S2;
+      mbar_wait_spin(&w2_empty[s2], (u2 & 1u) ^ 1u);
+      if (leader && (P.debug & 32)) {
+        mbar_arrive(&w2_full[s2]);
+      } else if (leader) {
+        mbar_arrive_expect_tx(&w2_full[s2], w2_slot_bytes);
+        const uint32_t base = smem_u32(w2_ring) + s2 * w2_slot_bytes;
+        for (int kb = 0; kb < kChunk / kBlockK; ++kb) {
+          tma_load_2d(base + (uint32_t)kb * kW2BlockBytes, &P.w2_map[0], &w2_full[s2], (int)j * kChunk + kb * kBlockK, 0);
+          if (kPrecise)
+            tma_load_2d(base + kW2PlaneBytes + (uint32_t)kb * kW2BlockBytes, &P.w2_map[1], &w2_full[s2],
+                        (int)j * kChunk + kb * kBlockK, 0);
+        }
+      }
+      __syncwarp();
+    }
+  } else if (warp == kMmaWarp) {
+    // =========================== MMA issuer ===========================
+    // tcgen05.mma instructions of one thread execute in issue order, so GEMM1 of chunk g + 2 (which overwrites the TMEM
+    // buffer of chunk g) needs no barrier against GEMM2 of chunk g (which reads it): it is issued behind it.
+    const bool leader = elect_one();
+    const uint32_t G = (uint32_t)n_my * (uint32_t)P.nch;
+    const bool cross = XB == 2;   // GEMM1 of the next tile's first chunk ahead of this tile's last GEMM2
+    auto gemm1 = [&](uint32_t g) {
+      const uint32_t ti = g / (uint32_t)P.nch, j = g - ti * (uint32_t)P.nch;
+      const uint32_t xb = ti % XB, b = g & 1u, s1 = g % S1;
+      if (j == 0) mbar_wait_spin(&x_ready[xb], (ti / XB) & 1u);
+      mbar_wait_spin(&w1_full[s1], (g / S1) & 1u);
+      tc_fence_after();
+      const uint64_t da0 = umma_desc_sw128(smem_u32(x_raw) + xb * kXBytes), dal0 = umma_desc_sw128(smem_u32(x_lo));
+      const uint64_t db0 = umma_desc_sw128(smem_u32(w1_ring) + s1 * w1_slot_bytes);
+      const uint32_t d = tmem_base + b * kHBufCols;
+      if (leader && !(P.debug & 16)) {
+#pragma unroll
+        for (int k8 = 0; k8 < kK1Steps; ++k8) {   // k-steps of 8 over the real K (the zero padding of the last k-block is skipped)
+          constexpr uint32_t kA = kABlockBytes >> 4, kB = kW1BlockBytes >> 4;
+          const uint64_t ao = (uint64_t)((k8 >> 2) * kA + (k8 & 3) * 2), bo = (uint64_t)((k8 >> 2) * kB + (k8 & 3) * 2);
+          umma_tf32(d, da0 + ao, db0 + bo, P.idesc1, k8 ? 1u : 0u);
+          if (kPrecise) {   // 3xTF32: hi.hi + lo.hi + hi.lo
+            umma_tf32(d, dal0 + ao, db0 + bo, P.idesc1, 1u);
+            umma_tf32(d, da0 + ao, db0 + bo + (uint64_t)(kW1PlaneBytes >> 4), P.idesc1, 1u);
+          }
+        }
+      }
+      if (leader && (P.debug & 64)) {
+        mbar_arrive(&w1_empty[s1]);
+        mbar_arrive(&d1_full[b]);
+        if (j == (uint32_t)P.nch - 1) mbar_arrive(g1_done);
+      } else if (leader) {
+        umma_commit(&w1_empty[s1]);
+        umma_commit(&d1_full[b]);
+        if (j == (uint32_t)P.nch - 1) umma_commit(g1_done);   // the tile's X planes have been read by every GEMM1
+      }
+      __syncwarp();
+    };
+    auto gemm2 = [&](uint32_t g) {
+      const uint32_t ti = g / (uint32_t)P.nch, j = g - ti * (uint32_t)P.nch;
+      const uint32_t b = g & 1u, s2 = g % S2, tb = ti & 1u;
+      if (j == 0) mbar_wait_spin(&d2_empty[tb], ((ti >> 1) & 1u) ^ 1u);
+      mbar_wait_spin(&w2_full[s2], (g / S2) & 1u);
+      mbar_wait_spin(&h_full[b], (g >> 1) & 1u);
+      tc_fence_after();
+      const uint32_t a_hi = tmem_base + b * kHBufCols, a_lo = a_hi + (uint32_t)kChunk;
+      const uint64_t db0 = umma_desc_sw128(smem_u32(w2_ring) + s2 * w2_slot_bytes);
+      const uint32_t d = tmem_base + kD2Col0 + tb * (uint32_t)kC;
+      if (leader && !(P.debug & 16)) {
+#pragma unroll
+        for (int k8 = 0; k8 < kChunk / 8; ++k8) {
+          const uint64_t bo = (uint64_t)((k8 >> 2) * (kW2BlockBytes >> 4) + (k8 & 3) * 2);
+          umma_tf32_ts(d, a_hi + (uint32_t)(k8 * 8), db0 + bo, P.idesc2, (j | (uint32_t)k8) ? 1u : 0u);
+          if (kPrecise) {
+            umma_tf32_ts(d, a_lo + (uint32_t)(k8 * 8), db0 + bo, P.idesc2, 1u);
+            umma_tf32_ts(d, a_hi + (uint32_t)(k8 * 8), db0 + bo + (uint64_t)(kW2PlaneBytes >> 4), P.idesc2, 1u);
+          }
+        }
+      }
+      if (leader && (P.debug & 64)) {
+        mbar_arrive(&w2_empty[s2]);
+        if (j == (uint32_t)P.nch - 1) mbar_arrive(&d2_full[tb]);
+      } else if (leader) {
+        umma_commit(&w2_empty[s2]);
+        if (j == (uint32_t)P.nch - 1) umma_commit(&d2_full[tb]);
+      }
+      __syncwarp();
+    };
+    if (G > 0) gemm1(0);
+    for (uint32_t g = 0; g < G; ++g) {
+      const bool next_is_new_tile = (g + 1) % (uint32_t)P.nch == 0;
+      const bool defer = !cross && next_is_new_tile;   // one X buffer: the next tile's X cannot land before this tile's epilogue
+      if (!defer && g + 1 < G) gemm1(g + 1);
+      gemm2(g);
+      if (defer && g + 1 < G) gemm1(g + 1);
+    }
+  } else if (warp >= kFirstEpiWarp && warp < kFirstEpiWarp + kEpiWarps) {
+    // =========================== epilogue ===========================
+    const int quad = warp & 3, half = (warp - kFirstEpiWarp) >> 2;
+    const int row = quad * 32 + lane;
+    const uint32_t t_lane = tmem_base + ((uint32_t)(quad * 32) << 16);
+    uint32_t g = 0;
+    for (int ti = 0; ti < n_my; ++ti) {
+      const uint32_t xb = (uint32_t)ti % XB;
+      float mean = 0.f, rstd = 1.f;
+      for (int j = 0; j < P.nch; ++j, ++g) {
+        const uint32_t b = g & 1u;
+        mbar_wait_spin(&d1_full[b], (g >> 1) & 1u);
+        tc_fence_after();
+        if (j == 0) {   // (written by the A pass before it published the tile; GEMM1 waited for that)
+          const float2 st2 = stats[xb * kTileM + row];
+          mean = st2.x, rstd = st2.y;
+        }
+#pragma unroll
+        for (int part = 0; part < kChunk / 32; ++part) {   // this warp's half of the chunk, 16 columns at a time
+          const uint32_t col = (uint32_t)(half * (kChunk / 2) + part * 16);
+          const uint32_t taddr = t_lane + b * kHBufCols + col;
+          float v[16], lo[16];
+          tmem_ld16(taddr, v);
+          const int n0 = j * kChunk + (int)col;
+#pragma unroll
+          for (int q = 0; q < 16; q += 4) {
+            const float4 t4 = *reinterpret_cast<const float4 *>(t1_s + n0 + q), s4 = *reinterpret_cast<const float4 *>(s1_s + n0 + q);
+            const float tt[4] = {t4.x, t4.y, t4.z, t4.w}, ss[4] = {s4.x, s4.y, s4.z, s4.w};
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              const float a = fmaf(rstd, v[q + e] - mean * ss[e], tt[e]);
+              const float gl = (P.debug & 1) ? a : gelu_erf(a);
+              v[q + e] = gl;                                   // the tensor core reads the upper 19 bits: hi = trunc_tf32(gl)
+              if (kPrecise) lo[q + e] = gl - trunc_tf32(gl);
+            }
+          }
+          tmem_st16(taddr, v);                                 // in place: the accumulator columns become GEMM2's A operand
+          if (kPrecise) tmem_st16(taddr + (uint32_t)kChunk, lo);
+        }
+        tmem_wait_st();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&h_full[b]);
+      }
+    }
+  } else if (warp >= kFirstOutWarp && warp < kFirstOutWarp + kOutWarps) {
+    // =========================== epilogue 2 (its own warps: the D2 tile of tile i leaves while epilogue 1 is on tile i + 1) =====
+    const int quad = warp & 3;
+    const int row = quad * 32 + lane;
+    const uint32_t swz = (uint32_t)(row & 7);
+    const uint32_t t_lane = tmem_base + ((uint32_t)(quad * 32) << 16);
+    for (int ti = 0; ti < n_my; ++ti) {
+      const uint32_t xb = (uint32_t)ti % XB, tb = (uint32_t)ti & 1u;
+      // ---- epilogue 2: D2 + bias + shortcut -> global
+      mbar_wait_spin(&d2_full[tb], ((uint32_t)ti >> 1) & 1u);
+      tc_fence_after();
+      mbar_wait_spin(&x_full[xb], ((uint32_t)ti / XB) & 1u);   // (long complete: acquire of the TMA-written X tile for the shortcut)
+      const int64_t m = ((int64_t)blockIdx.x + (int64_t)ti * gridDim.x) * kTileM + row;
+      const int groups = kC / 16;
+      const uint32_t xrow = smem_u32(x_raw) + xb * kXBytes + (uint32_t)row * 128u;
+      for (int gq = 0; gq < groups; ++gq) {
+        float v[16];
+        tmem_ld16(t_lane + kD2Col0 + tb * (uint32_t)kC + (uint32_t)(gq * 16), v);
+        const int c0 = gq * 16;
+        const uint32_t xk = xrow + (uint32_t)(c0 / kBlockK) * kABlockBytes;
+        const uint32_t chunk0 = (uint32_t)(c0 % kBlockK) / 4u;
+        float *yrow = P.y + m * P.y_ld + c0;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          const float4 xr = lds128(xk + (((chunk0 + (uint32_t)k) ^ swz) << 4));
+          const float4 b4 = *reinterpret_cast<const float4 *>(t2_s + c0 + 4 * k);
+          const float4 o = make_float4(xr.x + (v[4 * k] + b4.x), xr.y + (v[4 * k + 1] + b4.y), xr.z + (v[4 * k + 2] + b4.z),
+                                       xr.w + (v[4 * k + 3] + b4.w));
+          if (m < P.M && (!(P.debug & 4) || o.x == 1.2345e-30f)) *reinterpret_cast<float4 *>(yrow + 4 * k) = o;
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) {
+        mbar_arrive(&d2_empty[tb]);
+        mbar_arrive(&x_empty[xb]);
+      }
+    }
+  } else if (warp >= kFirstSplitWarp && warp < kFirstSplitWarp + 4) {
+    // =========================== A pass: LayerNorm row statistics (+ lo plane for 3xTF32) ===========================
+    const int st_thread = threadIdx.x - kFirstSplitWarp * 32;  // 0..127: 16-byte position st_thread % 8 of rows st_thread / 8 + 16 i
+    const int grp_lane0 = lane & ~7;
+    const int first_pos = (st_thread >> 3) & 7;                // swizzled position of the row's logical chunk 0 (row & 7)
+    float shift0[8], sum[8], sq[8];
+    for (int ti = 0; ti < n_my; ++ti) {
+      const uint32_t xb = (uint32_t)ti % XB;
+      mbar_wait_spin(&x_full[xb], ((uint32_t)ti / XB) & 1u);
+      if (kPrecise && ti > 0) mbar_wait_spin(g1_done, (uint32_t)(ti - 1) & 1u);   // the lo plane is free: GEMM1 of the previous tile is done
+      for (int kb = 0; kb < ((P.debug & 8) ? 0 : kKb1); ++kb) {
+        const uint32_t base = smem_u32(x_raw) + xb * kXBytes + (uint32_t)kb * kABlockBytes + (uint32_t)st_thread * 16u;
+        const uint32_t lo_base = smem_u32(x_lo) + (uint32_t)kb * kABlockBytes + (uint32_t)st_thread * 16u;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const float4 x = lds128(base + (uint32_t)i * 2048u);
+          if (kb == 0) {
+            shift0[i] = __shfl_sync(0xffffffffu, x.x, grp_lane0 + first_pos);
+            sum[i] = 0.f, sq[i] = 0.f;
+          }
+          const float dx = x.x - shift0[i], dy = x.y - shift0[i], dz = x.z - shift0[i], dw = x.w - shift0[i];
+          sum[i] += (dx + dy) + (dz + dw);
+          sq[i] += (dx * dx + dy * dy) + (dz * dz + dw * dw);
+          if (kPrecise) {
+            const float4 hi = make_float4(trunc_tf32(x.x), trunc_tf32(x.y), trunc_tf32(x.z), trunc_tf32(x.w));
+            sts128(lo_base + (uint32_t)i * 2048u, make_float4(x.x - hi.x, x.y - hi.y, x.z - hi.z, x.w - hi.w));
+          }
+        }
+      }
+      const float inv_k = 1.0f / (float)kC;
+      const float pad = (float)P.ln_pad;   // zero-filled columns past C in the last k-block: each added (0 - shift)^n
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        float s1 = sum[i], s2 = sq[i];
+        s1 += __shfl_xor_sync(0xffffffffu, s1, 1);
+        s2 += __shfl_xor_sync(0xffffffffu, s2, 1);
+        s1 += __shfl_xor_sync(0xffffffffu, s1, 2);
+        s2 += __shfl_xor_sync(0xffffffffu, s2, 2);
+        s1 += __shfl_xor_sync(0xffffffffu, s1, 4);
+        s2 += __shfl_xor_sync(0xffffffffu, s2, 4);
+        s1 += pad * shift0[i];
+        s2 -= pad * shift0[i] * shift0[i];
+        if ((lane & 7) == 0) {
+          const float md = s1 * inv_k;
+          const float var = fmaxf(s2 * inv_k - md * md, 0.f);
+          stats[xb * kTileM + (st_thread >> 3) + 16 * i] = make_float2(shift0[i] + md, rsqrtf(var + P.ln_eps));
+        }
+      }
+      if (kPrecise) fence_proxy_async_smem();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&x_ready[xb]);
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == kMmaWarp) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, (uint32_t)P.tmem_cols);
+  }
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
+                                  const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    void *p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(p);
+    (void)cudaGetLastError();
+  });
+  return fn;
+}
+
+bool map_2d(EncodeTiledFn enc, CUtensorMap *map, const float *base, uint64_t cols, uint64_t rows, uint64_t ld, uint32_t box_cols,
+            uint32_t box_rows) {
+  const cuuint64_t gdim[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+  const cuuint64_t gstr[1] = {(cuuint64_t)ld * 4};
+  const cuuint32_t box[2] = {box_cols, box_rows};
+  const cuuint32_t estr[2] = {1, 1};
+  return enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float *>(base), gdim, gstr, box, estr,
+             CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+             CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
+}  // namespace
+
+// w1_packed / w2_packed: stf_pack_conv images of fc1 (ksize 1, LayerNorm folded: has_ln) and fc2 (ksize 1) in the precision
+// of this call: [planes][N][Kp] t[N] s[N].
+extern "C" int stf_swin_mlp(const stf_mlp_args *a, void *stream) {
+  if (!a || !a->x || !a->y || !a->w1_packed || !a->w2_packed) return STF_E_ARG;
+  if (a->M <= 0 || a->C <= 0 || a->hidden <= 0) return STF_E_SHAPE;
+  // C: a multiple of 16 (the N of GEMM2); hidden: whole 32-column chunks; both TMEM accumulators of GEMM2 next to D1
+  if (a->C % 16 || a->C > 128 || a->hidden % kChunk || a->hidden > 1024) return STF_E_SHAPE;
+  if (a->x_ld % 4 || a->y_ld % 4 || a->x_ld < a->C || a->y_ld < a->C || !aligned16(a->x) || !aligned16(a->y) ||
+      !aligned16(a->w1_packed) || !aligned16(a->w2_packed))
+    return STF_E_ALIGN;
+  const int precise = a->precision == STF_PREC_FP32 ? 1 : 0;
+  EncodeTiledFn enc = encode_fn();
+  if (!enc) return STF_E_ARG;
+  MlpParams P{};
+  const int kb1 = (a->C + kBlockK - 1) / kBlockK, Kp1 = kb1 * kBlockK, Kp2 = a->hidden;
+  P.M = a->M, P.C = a->C, P.hidden = a->hidden, P.kb1 = kb1, P.nch = a->hidden / kChunk, P.ln_pad = Kp1 - a->C;
+  P.k1_steps = (a->C + 7) / 8;
+  P.m_tiles = (int)((a->M + kTileM - 1) / kTileM);
+  P.ln_eps = a->ln_eps;
+  P.y = a->y, P.y_ld = a->y_ld;
+  if (!map_2d(enc, &P.x_map, a->x, (uint64_t)a->C, (uint64_t)a->M, (uint64_t)a->x_ld, kBlockK, kTileM)) return STF_E_SHAPE;
+  for (int p = 0; p < 1 + precise; ++p) {
+    if (!map_2d(enc, &P.w1_map[p], a->w1_packed + (size_t)p * a->hidden * Kp1, (uint64_t)Kp1, (uint64_t)a->hidden, (uint64_t)Kp1,
+                kBlockK, kChunk))
+      return STF_E_SHAPE;
+    if (!map_2d(enc, &P.w2_map[p], a->w2_packed + (size_t)p * a->C * Kp2, (uint64_t)Kp2, (uint64_t)a->C, (uint64_t)Kp2, kBlockK,
+                (uint32_t)a->C))
+      return STF_E_SHAPE;
+  }
+  P.t1 = a->w1_packed + (size_t)(1 + precise) * a->hidden * Kp1;
+  P.s1 = P.t1 + a->hidden;
+  P.t2 = a->w2_packed + (size_t)(1 + precise) * a->C * Kp2;
+  P.idesc1 = umma_idesc_tf32(kTileM, kChunk);
+  P.idesc2 = umma_idesc_tf32(kTileM, a->C);
+  int cols = 32;
+  while (cols < (int)kD2Col0 + 2 * a->C) cols <<= 1;
+  if (cols > 512) return STF_E_SHAPE;
+  P.tmem_cols = cols;
+  P.x_bytes = (uint32_t)kb1 * kABlockBytes;
+  P.w1_plane_bytes = (uint32_t)kb1 * kW1BlockBytes;
+  P.w2_block_bytes = (uint32_t)a->C * 128u;
+  P.w2_plane_bytes = (uint32_t)(kChunk / kBlockK) * P.w2_block_bytes;
+  const size_t planes = 1 + precise;
+  const size_t small = 1024 + (size_t)(2 * a->hidden + ((a->C + 31) & ~31)) * 4 + 2 * kTileM * 8 + 40 * 8 + 16;
+  const size_t cap = 227 * 1024;
+  // buffers, most wanted first: two weight slots each (the next chunk's weights land under this chunk's MMAs), then the second
+  // X buffer (the next tile's X lands under this tile)
+  const int cfgs[4][3] = {{2, 2, 2}, {1, 2, 2}, {1, 2, 1}, {1, 1, 1}};   // x_bufs, w1_slots, w2_slots
+  size_t smem = 0;
+  bool ok = false;
+  for (int c = 0; c < 4 && !ok; ++c) {
+    P.x_bufs = cfgs[c][0], P.w1_slots = cfgs[c][1], P.w2_slots = cfgs[c][2];
+    smem = small + (size_t)P.x_bufs * P.x_bytes + (precise ? P.x_bytes : 0) +
+           (size_t)P.w1_slots * planes * P.w1_plane_bytes + (size_t)P.w2_slots * planes * P.w2_plane_bytes;
+    ok = smem <= cap;
+  }
+  if (!ok) return STF_E_SHAPE;
+  static const int dbg = getenv("STF_B200_MLP_DEBUG") ? atoi(getenv("STF_B200_MLP_DEBUG")) : 0;
+  P.debug = dbg;
+  const int sms = a->max_ctas > 0 && a->max_ctas < kNumSMs ? a->max_ctas : kNumSMs;
+  const int grid = P.m_tiles < sms ? P.m_tiles : sms;
+  void (*kern)(MlpParams) = nullptr;
+  int which = 0;
+  if (a->C == 48) kern = precise ? swin_mlp_kernel<1, 48> : swin_mlp_kernel<0, 48>, which = precise;
+  else if (a->C == 96) kern = precise ? swin_mlp_kernel<1, 96> : swin_mlp_kernel<0, 96>, which = 2 + precise;
+  else return STF_E_SHAPE;   // (the Swin stages this kernel pays for; wider layers are tensor-bound in the two-launch form)
+  static std::once_flag attr_once[4];
+  std::call_once(attr_once[which], [&] { (void)cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cap); });
+  kern<<<grid, kThreads, smem, (cudaStream_t)stream>>>(P);
+  return check_launch();
+}
+
+}  // namespace stf

@@ -117,6 +117,12 @@ class Mlp(nn.Module):
         _require_eval(self)
         shape = x.shape
         x2 = x.reshape(-1, shape[-1])
+        if ops.GEMM_ENGINE and norm is not None and residual is x and ops.mlp_fusable(shape[-1], self.fc1.out_features) \
+                and self.fc2.out_features == shape[-1]:
+            # x + fc2(GELU(fc1(LN2(x)))) in ONE kernel: the hidden activations stay on the SM (stf_swin_mlp)
+            y = ops.swin_mlp(x2, self._p1.get_gemm(self.fc1.weight, self.fc1.bias, norm),
+                             self._p2.get_gemm(self.fc2.weight, self.fc2.bias))
+            return y.reshape(shape)
         if ops.GEMM_ENGINE:   # both Linears on the TMA-fed GEMM engine (stf_conv2d, ksize 1): LN2 folded, GELU / shortcut fused
             h = ops.gemm(x2, self._p1.get_gemm(self.fc1.weight, self.fc1.bias, norm), act="gelu")
             res = None if residual is None else residual.reshape(-1, residual.shape[-1])

@@ -386,6 +386,8 @@ GEMM_ENGINE = os.environ.get("STF_B200_GEMM_ENGINE", "1") != "0"
 # Grid cap of the persistent kernels (0 = 148, one CTA per SM).  models.decompress() lowers it while device rANS decoders of
 # other sub-batches may be running: each of those is ONE warp on one SM for milliseconds, and a persistent CTA (a whole SM's
 # shared memory) assigned to that SM would wait for it -- head-of-line blocking of the entire kernel.
+FUSED_MLP = os.environ.get("STF_B200_FUSED_MLP", "1") != "0"
+FUSED_MLP_MAX_C = int(os.environ.get("STF_B200_FUSED_MLP_MAX_C", "96"))
 MAX_CTAS = 0
 NUM_SMS = 148
 
@@ -498,6 +500,34 @@ def gemm(x, pc, act=False, residual=None, out=None):
                                  (M * residual.stride(0), M * residual.stride(0), residual.stride(0), 1))
     y = conv2d([x4], pc, act=act, out=o4, residual=r4)
     return y.reshape(M, -1) if out is None else out
+
+
+def swin_mlp(x, pc1, pc2, out=None):
+    """x + fc2(GELU(fc1(LayerNorm(x)))) for token-major x (M, C) in ONE kernel (stf_swin_mlp): the hidden activations never
+    reach HBM.  pc1: PackedConv of fc1 with the LayerNorm folded (ln=...), pc2: PackedConv of fc2, both in the current
+    precision.  out: optional (M, C) destination (may be x)."""
+    if x.dim() != 2 or x.stride(1) != 1 or not x.is_cuda or x.dtype != torch.float32:
+        raise ValueError("stf_b200.swin_mlp: x must be a token-major CUDA fp32 (M, C) matrix")
+    M, C = x.shape
+    if not pc1.has_ln or pc1.ksize != 1 or pc2.ksize != 1 or pc1.src_channels != (C,) or pc2.N != C or \
+            pc2.src_channels != (pc1.N,) or pc1.precision != pc2.precision:
+        raise ValueError("stf_b200.swin_mlp: fc1 must carry the folded LayerNorm and fc2 must map hidden -> C")
+    if out is None:
+        out = torch.empty((M, C), dtype=torch.float32, device=x.device)
+    a = _C.MlpArgs()
+    a.x, a.x_ld, a.y, a.y_ld = x.data_ptr(), x.stride(0), out.data_ptr(), out.stride(0)
+    a.M, a.C, a.hidden = M, C, pc1.N
+    a.w1_packed, a.w2_packed = pc1.packed.data_ptr(), pc2.packed.data_ptr()
+    a.ln_eps, a.precision, a.max_ctas = pc1.ln_eps, pc1.precision, MAX_CTAS
+    _launch("swin_mlp_kernel", 8 * M * C, _C.lib().stf_swin_mlp, ctypes.byref(a), _C.stream(), flops=4 * M * C * pc1.N)
+    return out
+
+
+def mlp_fusable(C, hidden):
+    """Shapes stf_swin_mlp takes and where it pays (tools/bench_mlp.py): C = 48 in both GEMM modes (2.90 vs 3.09 ms per
+    6.3 M tokens in the 3xTF32 mode, 2.20 vs 2.83 ms single-pass), C = 96 in the single-pass mode only (1.24 vs 1.47 ms; in
+    the 3xTF32 mode the two-launch form wins there, 1.87 vs 2.19 ms)."""
+    return FUSED_MLP and hidden == 4 * C and (C == 48 or (C == 96 and _precision == 0)) and C <= FUSED_MLP_MAX_C
 
 
 def window_attention_tokens(qkv, bias_table, pad_qkv, B, H, W, C, heads, ws, shift):

@@ -309,3 +309,37 @@ def test_pair_mode_clusters_match_single_cta(tmp_path):
     env = dict(os.environ, STF_B200_PAIR="1")
     out = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, timeout=300)
     assert out.returncode == 0 and "pair mode ok" in out.stdout, out.stdout + out.stderr
+
+
+@pytest.mark.parametrize("C,M,prec", [(48, 128 * 5 + 37, "fp32"), (48, 300, "tf32"), (96, 128 * 3 + 1, "fp32"), (48, 128 * 400, "fp32")])
+def test_fused_swin_mlp_matches_float64_and_two_launch_path(C, M, prec):
+    """stf_swin_mlp: x + fc2(GELU(fc1(LN(x)))) in one kernel (hidden activations on the SM) against a float64 evaluation of
+    the reference's formula (stf.py:25-40, 196-197) and against the two-launch GEMM-engine path; ragged last tile, several
+    tiles per CTA (the operand rings wrap), in place."""
+    from stf_b200 import ops
+    old = ops.precision()
+    ops.set_precision(prec)
+    try:
+        torch.manual_seed(C + M)
+        hid = 4 * C
+        x = (torch.randn(M, C, device="cuda") * 1.5 + 0.3).contiguous()
+        g, be = torch.rand(C, device="cuda") + 0.5, torch.randn(C, device="cuda") * 0.1
+        w1, b1 = torch.randn(hid, C, device="cuda") / C ** 0.5, torch.randn(hid, device="cuda") * 0.1
+        w2, b2 = torch.randn(C, hid, device="cuda") / hid ** 0.5, torch.randn(C, device="cuda") * 0.1
+        pc1 = ops.PackedConv(w1, b1, prec=ops.precision_code(), ln=(g, be, 1e-5))
+        pc2 = ops.PackedConv(w2, b2, prec=ops.precision_code())
+        y = ops.swin_mlp(x, pc1, pc2)
+        xd = x.double()
+        ln = torch.nn.functional.layer_norm(xd, (C,), g.double(), be.double(), 1e-5)
+        ref = xd + torch.nn.functional.gelu(ln @ w1.double().t() + b1.double()) @ w2.double().t() + b2.double()
+        two = ops.gemm(ops.gemm(x, pc1, act="gelu"), pc2, act="residual", residual=x)
+        tol = 2e-5 if prec == "fp32" else 6e-3
+        scale = ref.abs().max().item()
+        assert (y.double() - ref).abs().max().item() <= tol * scale, ((y.double() - ref).abs().max().item(), scale)
+        assert torch.equal(y, two), (y - two).abs().max().item()    # same K order, same epilogue arithmetic: the same bits
+        y2 = x.clone()
+        ops.swin_mlp(y2, pc1, pc2, out=y2)                               # in place
+        assert torch.equal(y2, y)
+        assert torch.equal(ops.swin_mlp(x[: 128 * 2 + 5], pc1, pc2), y[: 128 * 2 + 5])   # rows do not depend on M
+    finally:
+        ops.set_precision(old)
