@@ -14,7 +14,7 @@ import re
 import sys
 
 KEYS = {"conv_tf32_kernel": "conv_tf32_kernel", "window_attention_tok_kernel": "window_attention_tok_kernel",
-        "linear_tf32_kernel": "linear_tf32_kernel", "patch_embed_kernel": "patch_embed_kernel",
+        "linear_tf32_kernel": "linear_tf32_kernel", "patch_embed_kernel": "patch_embed_kernel", "swin_mlp_kernel": "swin_mlp_kernel",
         "slice_step_nhwc_kernel": "slice_step_nhwc_kernel", "entropy_bottleneck_kernel": "entropy_bottleneck_kernel",
         "dequantize_kernel": "dequantize_kernel", "window_attention16_kernel": "window_attention_kernel",
         "window_attention64_kernel": "window_attention_kernel"}
