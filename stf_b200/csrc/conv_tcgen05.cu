@@ -244,10 +244,6 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tf32_kernel(const __grid_con
            *acc_empty = acc_full + 2, *full_b = acc_empty + 2, *empty_b = full_b + kMaxStages;
   uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(empty_b + kMaxStages);
 
-  for (int i = threadIdx.x; i < P.n_pad; i += kThreads) {
-    bias_s[i] = (P.bias && i < P.N) ? __ldg(P.bias + i) : 0.f;
-    if (kLn) svec_s[i] = i < P.N ? __ldg(P.svec + i) : 0.f;
-  }
   if (threadIdx.x == 0) {
     for (uint32_t s = 0; s < S; ++s) {
       mbar_init(&full[s], 1);    // the producer's arrive.expect_tx (+ TMA transaction bytes)
@@ -414,6 +410,14 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tf32_kernel(const __grid_con
     }
   } else if (warp >= kFirstEpiWarp && warp < kFirstEpiWarp + kEpiWarps) {
     // =========================== epilogue ===========================
+    // The epilogue vectors are loaded here, by the warps that use them, behind the CTA-wide start barrier: the producer's
+    // first TMA loads no longer wait for these global loads (~0.7 us on the critical path of every launch; the slice loop
+    // launches ~1000 short kernels per batch).
+    for (int i = threadIdx.x - kFirstEpiWarp * 32; i < P.n_pad; i += kEpiWarps * 32) {
+      bias_s[i] = (P.bias && i < P.N) ? __ldg(P.bias + i) : 0.f;
+      if (kLn) svec_s[i] = i < P.N ? __ldg(P.svec + i) : 0.f;
+    }
+    named_bar_sync(1, kEpiWarps * 32);
     const int quad = warp & 3;
     const int row = quad * 32 + lane;  // TMEM lane == tile row == pixel (row / TW, row % TW) of the tile box
     // Each epilogue warp stores its own 32 rows: a private ring of `slabs` staging slabs and its own bulk-store groups
@@ -510,7 +514,8 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tf32_kernel(const __grid_con
         if (++slab == (uint32_t)P.slabs) slab = 0;
       }
     }
-    if (epi_leader) bulk_wait0();
+    // the staging slabs must outlive the stores' READS only; the writes are complete (and visible) when the grid has finished
+    if (epi_leader) bulk_wait_read<0>();
   } else if (kAPass && warp >= kFirstSplitWarp) {
     // =========================== A pass: hi / lo split (3xTF32) and LayerNorm row statistics ===========================
     // Element-wise on the landed A stage.  3xTF32: the raw fp32 stage IS the hi operand (the tensor core reads the upper 19
