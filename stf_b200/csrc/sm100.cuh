@@ -78,9 +78,10 @@ __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
   }
 }
 
-// Latency-critical hand-offs (a consumer that is woken once per short pipeline step): non-blocking probes in a tight
-// loop.  try_wait parks the thread for an implementation-defined time when the phase is pending, and the wake-up after the
-// completing arrival measured ~0.5 us on B200 -- twice per 32-column chunk that was the whole run time of the fused MLP kernel.
+// Non-blocking probes (mbarrier.test_wait) in a tight loop, for hand-offs that sit on a short per-step critical path (the
+// fused MLP kernel: two hand-offs per 64-column chunk).  try_wait may park the thread for an implementation-defined time when
+// the phase is pending; measured on B200 the two variants performed the same in that kernel (the MMA issuer bound it), so
+// this is a choice of semantics -- never parked -- not a measured win.
 __device__ __forceinline__ void mbar_wait_spin(uint64_t *bar, uint32_t parity) {
   const uint32_t addr = smem_u32(bar);
   long long t0 = 0;
