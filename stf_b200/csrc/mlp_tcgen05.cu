@@ -24,12 +24,14 @@
 //
 // Warp roles (640 threads, one persistent CTA per SM): warp 0 TMA producer (X, W1), warp 1 MMA issuer (+ TMEM alloc), warp 2 TMA
 // producer (W2), warps 4-11 epilogue 1 (warp & 3 = TMEM lane quadrant, two warps per quadrant on the two halves of a chunk),
-// warps 12-15 A pass, warps 16-19 epilogue 2 (the output tile of tile i leaves while epilogue 1 is on tile i + 1).  All waits
-// are mbarrier.test_wait spins: every hand-off here is on a per-chunk critical path.
-// Measured (B200, 6.3 M tokens, C = 48; tools/bench_mlp.py): 3xTF32 2.90 ms against 3.09 ms for the two launches, single-pass
-// TF32 2.20 against 2.83 ms; C = 96 (1.6 M tokens): 2.19 / 1.87 ms and 1.24 / 1.47 ms.  The kernel is bound by the MMA issuer:
-// 126 small tcgen05.mma per tile (N = 64 / 48, K = 8) at ~90-100 cycles each, clock64-traced -- not by HBM (0.83 TB/s
-// algorithmic) and not by accumulator dependencies (separate accumulators for the hi and lo passes change nothing).
+// warps 12-15 A pass, warps 16-19 epilogue 2 (the output tile of tile i leaves while epilogue 1 is on tile i + 1).  The waits
+// of the MMA issuer are mbarrier.test_wait spins; every other role parks in try_wait (or sleeps): an ncu source view of the
+// all-spin version showed 52 % of the kernel's instructions in wait loops, taking issue slots from the MMA issuer's scheduler.
+// Measured (B200, 6.3 M tokens, C = 48; tools/bench_mlp.py): 3xTF32 2.79 ms against 3.09-3.17 ms for the two launches, single-pass
+// TF32 2.08 against 2.79 ms; C = 96 (1.6 M tokens): 2.15 / 1.87 ms and 1.22 / 1.46 ms.  The kernel is bound by the MMA issuer:
+// 126 small tcgen05.mma per tile (N = 64 / 48, K = 8) issued ~90-100 cycles apart (clock64 traces) while the tensor pipe
+// itself is active 21 % of the time (ncu: ~27 cycles per MMA, the hardware floor) -- not by HBM (0.87 TB/s algorithmic) and
+// not by accumulator dependencies (separate accumulators for the hi and lo passes change nothing).
 #include <cuda.h>
 #include <math.h>
 #include <stdlib.h>
@@ -194,7 +196,7 @@ __global__ void __launch_bounds__(kThreads, 1) swin_mlp_kernel(const __grid_cons
     const bool leader = elect_one();
     auto load_x = [&](int ti) {
       const uint32_t xb = (uint32_t)ti % XB, u = (uint32_t)ti / XB;
-      mbar_wait_spin(&x_empty[xb], (u & 1u) ^ 1u);
+      mbar_wait(&x_empty[xb], (u & 1u) ^ 1u);
       if (leader) {
         mbar_arrive_expect_tx(&x_full[xb], kXBytes);
         const int row0 = ((int)blockIdx.x + ti * (int)gridDim.x) * kTileM;
@@ -209,7 +211,7 @@ __global__ void __launch_bounds__(kThreads, 1) swin_mlp_kernel(const __grid_cons
       if (XB == 1 && ti > 0) load_x(ti);
       for (int j = 0; j < P.nch; ++j, ++g) {
         const uint32_t s1 = g % S1, u1 = g / S1;
-        mbar_wait_spin(&w1_empty[s1], (u1 & 1u) ^ 1u);
+        mbar_wait(&w1_empty[s1], (u1 & 1u) ^ 1u);
         if (leader && (P.debug & 32)) {
           mbar_arrive(&w1_full[s1]);
         } else if (leader) {
@@ -233,7 +235,7 @@ __global__ void __launch_bounds__(kThreads, 1) swin_mlp_kernel(const __grid_cons
     const uint32_t G = (uint32_t)n_my * (uint32_t)P.nch;
     for (uint32_t g = 0; g < G; ++g) {
       const uint32_t j = g % (uint32_t)P.nch, s2 = g % S2, u2 = g / S2;
-      mbar_wait_spin(&w2_empty[s2], (u2 & 1u) ^ 1u);
+      mbar_wait(&w2_empty[s2], (u2 & 1u) ^ 1u);
       if (leader && (P.debug & 32)) {
         mbar_arrive(&w2_full[s2]);
       } else if (leader) {
@@ -336,7 +338,7 @@ __global__ void __launch_bounds__(kThreads, 1) swin_mlp_kernel(const __grid_cons
       float mean = 0.f, rstd = 1.f;
       for (int j = 0; j < P.nch; ++j, ++g) {
         const uint32_t b = g & 1u;
-        mbar_wait_spin(&d1_full[b], (g >> 1) & 1u);
+        mbar_wait(&d1_full[b], (g >> 1) & 1u);
         tc_fence_after();
         if (j == 0) {   // (written by the A pass before it published the tile; GEMM1 waited for that)
           const float2 st2 = stats[xb * kTileM + row];
@@ -379,9 +381,9 @@ __global__ void __launch_bounds__(kThreads, 1) swin_mlp_kernel(const __grid_cons
     for (int ti = 0; ti < n_my; ++ti) {
       const uint32_t xb = (uint32_t)ti % XB, tb = (uint32_t)ti & 1u;
       // ---- epilogue 2: D2 + bias + shortcut -> global
-      mbar_wait_spin(&d2_full[tb], ((uint32_t)ti >> 1) & 1u);
+      mbar_wait_relaxed(&d2_full[tb], ((uint32_t)ti >> 1) & 1u);
       tc_fence_after();
-      mbar_wait_spin(&x_full[xb], ((uint32_t)ti / XB) & 1u);   // (long complete: acquire of the TMA-written X tile for the shortcut)
+      mbar_wait(&x_full[xb], ((uint32_t)ti / XB) & 1u);   // (long complete: acquire of the TMA-written X tile for the shortcut)
       const int64_t m = ((int64_t)blockIdx.x + (int64_t)ti * gridDim.x) * kTileM + row;
       const int groups = kC / 16;
       const uint32_t xrow = smem_u32(x_raw) + xb * kXBytes + (uint32_t)row * 128u;
@@ -416,8 +418,8 @@ __global__ void __launch_bounds__(kThreads, 1) swin_mlp_kernel(const __grid_cons
     float shift0[8], sum[8], sq[8];
     for (int ti = 0; ti < n_my; ++ti) {
       const uint32_t xb = (uint32_t)ti % XB;
-      mbar_wait_spin(&x_full[xb], ((uint32_t)ti / XB) & 1u);
-      if (kPrecise && ti > 0) mbar_wait_spin(g1_done, (uint32_t)(ti - 1) & 1u);   // the lo plane is free: GEMM1 of the previous tile is done
+      mbar_wait(&x_full[xb], ((uint32_t)ti / XB) & 1u);
+      if (kPrecise && ti > 0) mbar_wait(g1_done, (uint32_t)(ti - 1) & 1u);   // the lo plane is free: GEMM1 of the previous tile is done
       for (int kb = 0; kb < ((P.debug & 8) ? 0 : kKb1); ++kb) {
         const uint32_t base = smem_u32(x_raw) + xb * kXBytes + (uint32_t)kb * kABlockBytes + (uint32_t)st_thread * 16u;
         const uint32_t lo_base = smem_u32(x_lo) + (uint32_t)kb * kABlockBytes + (uint32_t)st_thread * 16u;
