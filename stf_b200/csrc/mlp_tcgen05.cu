@@ -56,7 +56,6 @@ constexpr int kProducerWarp = 0, kMmaWarp = 1, kW2Warp = 2, kFirstEpiWarp = 4, k
               kOutWarps = 4;
 constexpr int kMaxSlots = 2;
 constexpr uint32_t kHBufCols = 2 * kChunk;       // TMEM columns per hidden buffer: D1 / H hi, H lo
-constexpr uint32_t kD2Col0 = 2 * kHBufCols;      // D2 buffer b: columns [256 + b * C, ...)
 
 struct MlpParams {
   alignas(64) CUtensorMap x_map;       // [M][C], box [32][128]
@@ -145,6 +144,10 @@ __global__ void __launch_bounds__(kThreads, 1) swin_mlp_kernel(const __grid_cons
   constexpr int kKb1 = (kC + kBlockK - 1) / kBlockK, kK1Steps = (kC + 7) / 8;
   constexpr uint32_t kXBytes = kKb1 * kABlockBytes, kW1PlaneBytes = kKb1 * kW1BlockBytes;
   constexpr uint32_t kW2BlockBytes = kC * 128u, kW2PlaneBytes = (kChunk / kBlockK) * kW2BlockBytes;
+  // hidden-chunk buffers in TMEM (D1 / H hi + H lo, 128 columns each) and how far GEMM1 runs ahead of GEMM2.  Two buffers,
+  // one chunk ahead: three buffers (GEMM1 two chunks ahead; they fit next to both D2 tiles up to C = 64) measured SLOWER,
+  // 3.28 vs 2.79 ms -- GEMM2 of chunk g then queues behind two GEMM1s in the in-order tensor pipe.
+  constexpr uint32_t kBufs = 2, kAhead = kBufs - 1, kD2Col0 = kBufs * kHBufCols;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw_u32 = smem_u32(smem_raw);
   uint8_t *smem = smem_raw + ((1024u - (raw_u32 & 1023u)) & 1023u);
@@ -162,7 +165,7 @@ __global__ void __launch_bounds__(kThreads, 1) swin_mlp_kernel(const __grid_cons
   uint64_t *bars = reinterpret_cast<uint64_t *>(stats + (size_t)P.x_bufs * kTileM);
   uint64_t *x_full = bars, *x_ready = x_full + kMaxSlots, *x_empty = x_ready + kMaxSlots, *g1_done = x_empty + kMaxSlots,
            *w1_full = g1_done + 1, *w1_empty = w1_full + kMaxSlots, *w2_full = w1_empty + kMaxSlots,
-           *w2_empty = w2_full + kMaxSlots, *d1_full = w2_empty + kMaxSlots, *h_full = d1_full + 2, *d2_full = h_full + 2,
+           *w2_empty = w2_full + kMaxSlots, *d1_full = w2_empty + kMaxSlots, *h_full = d1_full + 3, *d2_full = h_full + 3,
            *d2_empty = d2_full + 2;
   uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(d2_empty + 2);
 
@@ -172,9 +175,9 @@ __global__ void __launch_bounds__(kThreads, 1) swin_mlp_kernel(const __grid_cons
     for (int s = 0; s < kMaxSlots; ++s) {
       mbar_init(&x_full[s], 1), mbar_init(&x_ready[s], 4), mbar_init(&x_empty[s], kOutWarps);
       mbar_init(&w1_full[s], 1), mbar_init(&w1_empty[s], 1), mbar_init(&w2_full[s], 1), mbar_init(&w2_empty[s], 1);
-      mbar_init(&d1_full[s], 1), mbar_init(&h_full[s], kEpiWarps);
       mbar_init(&d2_full[s], 1), mbar_init(&d2_empty[s], kOutWarps);
     }
+    for (int s = 0; s < 3; ++s) mbar_init(&d1_full[s], 1), mbar_init(&h_full[s], kEpiWarps);
     mbar_init(g1_done, 1);
     mbar_fence_init();
     tma_prefetch_desc(&P.x_map);
@@ -259,7 +262,7 @@ __global__ void __launch_bounds__(kThreads, 1) swin_mlp_kernel(const __grid_cons
     const bool cross = XB == 2;   // GEMM1 of the next tile's first chunk ahead of this tile's last GEMM2
     auto gemm1 = [&](uint32_t g) {
       const uint32_t ti = g / (uint32_t)P.nch, j = g - ti * (uint32_t)P.nch;
-      const uint32_t xb = ti % XB, b = g & 1u, s1 = g % S1;
+      const uint32_t xb = ti % XB, b = g % kBufs, s1 = g % S1;
       if (j == 0) mbar_wait_spin(&x_ready[xb], (ti / XB) & 1u);
       mbar_wait_spin(&w1_full[s1], (g / S1) & 1u);
       tc_fence_after();
@@ -291,10 +294,10 @@ __global__ void __launch_bounds__(kThreads, 1) swin_mlp_kernel(const __grid_cons
     };
     auto gemm2 = [&](uint32_t g) {
       const uint32_t ti = g / (uint32_t)P.nch, j = g - ti * (uint32_t)P.nch;
-      const uint32_t b = g & 1u, s2 = g % S2, tb = ti & 1u;
+      const uint32_t b = g % kBufs, s2 = g % S2, tb = ti & 1u;
       if (j == 0) mbar_wait_spin(&d2_empty[tb], ((ti >> 1) & 1u) ^ 1u);
       mbar_wait_spin(&w2_full[s2], (g / S2) & 1u);
-      mbar_wait_spin(&h_full[b], (g >> 1) & 1u);
+      mbar_wait_spin(&h_full[b], (g / kBufs) & 1u);
       tc_fence_after();
       const uint32_t a_hi = tmem_base + b * kHBufCols, a_lo = a_hi + (uint32_t)kChunk;
       const uint64_t db0 = umma_desc_sw128(smem_u32(w2_ring) + s2 * w2_slot_bytes);
@@ -319,13 +322,20 @@ __global__ void __launch_bounds__(kThreads, 1) swin_mlp_kernel(const __grid_cons
       }
       __syncwarp();
     };
-    if (G > 0) gemm1(0);
-    for (uint32_t g = 0; g < G; ++g) {
-      const bool next_is_new_tile = (g + 1) % (uint32_t)P.nch == 0;
-      const bool defer = !cross && next_is_new_tile;   // one X buffer: the next tile's X cannot land before this tile's epilogue
-      if (!defer && g + 1 < G) gemm1(g + 1);
-      gemm2(g);
-      if (defer && g + 1 < G) gemm1(g + 1);
+    if (cross) {
+      for (uint32_t i = 0; i < kAhead && i < G; ++i) gemm1(i);
+      for (uint32_t g = 0; g < G; ++g) {
+        if (g + kAhead < G) gemm1(g + kAhead);
+        gemm2(g);
+      }
+    } else {   // one X buffer: the next tile's X cannot land before this tile's epilogue 2, i.e. behind its last GEMM2
+      if (G > 0) gemm1(0);
+      for (uint32_t g = 0; g < G; ++g) {
+        const bool defer = (g + 1) % (uint32_t)P.nch == 0;
+        if (!defer && g + 1 < G) gemm1(g + 1);
+        gemm2(g);
+        if (defer && g + 1 < G) gemm1(g + 1);
+      }
     }
   } else if (warp >= kFirstEpiWarp && warp < kFirstEpiWarp + kEpiWarps) {
     // =========================== epilogue ===========================
@@ -337,8 +347,8 @@ __global__ void __launch_bounds__(kThreads, 1) swin_mlp_kernel(const __grid_cons
       const uint32_t xb = (uint32_t)ti % XB;
       float mean = 0.f, rstd = 1.f;
       for (int j = 0; j < P.nch; ++j, ++g) {
-        const uint32_t b = g & 1u;
-        mbar_wait(&d1_full[b], (g >> 1) & 1u);
+        const uint32_t b = g % kBufs;
+        mbar_wait(&d1_full[b], (g / kBufs) & 1u);
         tc_fence_after();
         if (j == 0) {   // (written by the A pass before it published the tile; GEMM1 waited for that)
           const float2 st2 = stats[xb * kTileM + row];
@@ -538,7 +548,7 @@ extern "C" int stf_swin_mlp(const stf_mlp_args *a, void *stream) {
   P.idesc1 = umma_idesc_tf32(kTileM, kChunk);
   P.idesc2 = umma_idesc_tf32(kTileM, a->C);
   int cols = 32;
-  while (cols < (int)kD2Col0 + 2 * a->C) cols <<= 1;
+  while (cols < 2 * (int)kHBufCols + 2 * a->C) cols <<= 1;
   if (cols > 512) return STF_E_SHAPE;
   P.tmem_cols = cols;
   P.x_bytes = (uint32_t)kb1 * kABlockBytes;
