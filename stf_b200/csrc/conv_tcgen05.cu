@@ -35,6 +35,7 @@
 #include <mutex>
 
 #include "common.cuh"
+#include "epilogue_math.cuh"
 #include "sm100.cuh"
 
 namespace stf {
@@ -175,21 +176,6 @@ __device__ __forceinline__ void sts128(uint32_t addr, float4 v) {
   asm volatile("st.shared.v4.f32 [%0], {%1,%2,%3,%4};" ::"r"(addr), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
 }
 
-// Exact-erf GELU (nn.GELU default): same evaluation as the linear kernel's epilogue (Abramowitz-Stegun 7.1.26,
-// |abs error| <= 1.5e-7, branch-free).
-__device__ __forceinline__ float gelu_erf(float x) {
-  const float ax = fabsf(x) * 0.70710678118654752440f;
-  float t;
-  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(t) : "f"(fmaf(0.3275911f, ax, 1.0f)));
-  float p = fmaf(t, 1.061405429f, -1.453152027f);
-  p = fmaf(t, p, 1.421413741f);
-  p = fmaf(t, p, -0.284496736f);
-  p = fmaf(t, p, 0.254829592f);
-  const float e = __expf(-ax * ax);
-  const float erf_abs = fmaf(-p * t, e, 1.0f);
-  return 0.5f * x * (1.0f + copysignf(erf_abs, x));
-}
-
 __device__ __forceinline__ float trunc_tf32(float x) { return __uint_as_float(__float_as_uint(x) & 0xFFFFE000u); }
 
 // Epilogue math of one chunk (32 accumulator columns of one row), act fixed at compile time: the 32 element chains are
@@ -199,6 +185,26 @@ template <int kLn, int kAct>
 __device__ __forceinline__ void epi_math(const uint32_t (&r)[32], float (&v)[32], const float *__restrict__ tv,
                                          const float *__restrict__ sv, float mean, float rstd,
                                          const float *__restrict__ res_row, int res_cols) {
+  using namespace epi;
+  if (kAct == 1) {   // GELU (every conv stack layer but the last, fc1): pairs of columns on the packed fp32 pipe
+    const uint64_t nmean2 = dup2(-mean), rstd2 = dup2(rstd);
+#pragma unroll
+    for (int j = 0; j < 32; j += 4) {
+      const float4 t4 = *reinterpret_cast<const float4 *>(tv + j);
+      float4 s4 = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (kLn) s4 = *reinterpret_cast<const float4 *>(sv + j);
+#pragma unroll
+      for (int q = 0; q < 4; q += 2) {
+        const uint64_t acc = pack2(__uint_as_float(r[j + q]), __uint_as_float(r[j + q + 1]));
+        const uint64_t t2 = q ? pack2(t4.z, t4.w) : pack2(t4.x, t4.y);
+        uint64_t a;
+        if (kLn) a = fma2(rstd2, fma2(nmean2, q ? pack2(s4.z, s4.w) : pack2(s4.x, s4.y), acc), t2);   // rstd (acc - mean s) + t
+        else a = add2(acc, t2);
+        unpack2(gelu_erf2(a), v[j + q], v[j + q + 1]);
+      }
+    }
+    return;
+  }
 #pragma unroll
   for (int j = 0; j < 32; j += 4) {
     const float4 t4 = *reinterpret_cast<const float4 *>(tv + j);
@@ -210,8 +216,7 @@ __device__ __forceinline__ void epi_math(const uint32_t (&r)[32], float (&v)[32]
     for (int q = 0; q < 4; ++q) {
       float a = __uint_as_float(r[j + q]);
       a = kLn ? fmaf(rstd, a - mean * ss[q], tt[q]) : a + tt[q];
-      if (kAct == 1) a = gelu_erf(a);
-      else if (kAct == 2) a = rr[q] + 0.5f * tanhf(a);
+      if (kAct == 2) a = rr[q] + 0.5f * tanhf(a);
       else if (kAct == 3) a = rr[q] + a;
       v[j + q] = a;
     }

@@ -39,6 +39,7 @@
 #include <mutex>
 
 #include "common.cuh"
+#include "epilogue_math.cuh"
 #include "sm100.cuh"
 
 namespace stf {
@@ -120,19 +121,6 @@ __device__ __forceinline__ float4 lds128(uint32_t addr) {
 }
 __device__ __forceinline__ void sts128(uint32_t addr, float4 v) {
   asm volatile("st.shared.v4.f32 [%0], {%1,%2,%3,%4};" ::"r"(addr), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
-}
-// Exact-erf GELU, the evaluation of the two-launch path (csrc/conv_tcgen05.cu: Abramowitz-Stegun 7.1.26).
-__device__ __forceinline__ float gelu_erf(float x) {
-  const float ax = fabsf(x) * 0.70710678118654752440f;
-  float t;
-  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(t) : "f"(fmaf(0.3275911f, ax, 1.0f)));
-  float p = fmaf(t, 1.061405429f, -1.453152027f);
-  p = fmaf(t, p, 1.421413741f);
-  p = fmaf(t, p, -0.284496736f);
-  p = fmaf(t, p, 0.254829592f);
-  const float e = __expf(-ax * ax);
-  const float erf_abs = fmaf(-p * t, e, 1.0f);
-  return 0.5f * x * (1.0f + copysignf(erf_abs, x));
 }
 __device__ __forceinline__ float trunc_tf32(float x) { return __uint_as_float(__float_as_uint(x) & 0xFFFFE000u); }
 
@@ -361,16 +349,18 @@ __global__ void __launch_bounds__(kThreads, 1) swin_mlp_kernel(const __grid_cons
           float v[16], lo[16];
           tmem_ld16(taddr, v);
           const int n0 = j * kChunk + (int)col;
+          const uint64_t nmean2 = epi::dup2(-mean), rstd2 = epi::dup2(rstd);
 #pragma unroll
           for (int q = 0; q < 16; q += 4) {
             const float4 t4 = *reinterpret_cast<const float4 *>(t1_s + n0 + q), s4 = *reinterpret_cast<const float4 *>(s1_s + n0 + q);
-            const float tt[4] = {t4.x, t4.y, t4.z, t4.w}, ss[4] = {s4.x, s4.y, s4.z, s4.w};
 #pragma unroll
-            for (int e = 0; e < 4; ++e) {
-              const float a = fmaf(rstd, v[q + e] - mean * ss[e], tt[e]);
-              const float gl = (P.debug & 1) ? a : gelu_erf(a);
-              v[q + e] = gl;                                   // the tensor core reads the upper 19 bits: hi = trunc_tf32(gl)
-              if (kPrecise) lo[q + e] = gl - trunc_tf32(gl);
+            for (int e = 0; e < 4; e += 2) {   // pairs of columns on the packed fp32 pipe: the arithmetic of epi_math<1, 1>
+              const uint64_t acc = epi::pack2(v[q + e], v[q + e + 1]);
+              const uint64_t a = epi::fma2(rstd2, epi::fma2(nmean2, e ? epi::pack2(s4.z, s4.w) : epi::pack2(s4.x, s4.y), acc),
+                                           e ? epi::pack2(t4.z, t4.w) : epi::pack2(t4.x, t4.y));
+              if (P.debug & 1) epi::unpack2(a, v[q + e], v[q + e + 1]);
+              else epi::unpack2(epi::gelu_erf2(a), v[q + e], v[q + e + 1]);   // the tensor core reads the upper 19 bits: hi = trunc_tf32
+              if (kPrecise) lo[q + e] = v[q + e] - trunc_tf32(v[q + e]), lo[q + e + 1] = v[q + e + 1] - trunc_tf32(v[q + e + 1]);
             }
           }
           tmem_st16(taddr, v);                                 // in place: the accumulator columns become GEMM2's A operand
