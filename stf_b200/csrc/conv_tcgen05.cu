@@ -73,6 +73,7 @@ struct ConvParams {
   int n_src;
   int src_kb[kMaxSrc];                // 32-channel k-blocks per tap of each source
   int kb_per_tap, k_blocks, ksize, pad, stride;
+  int tail_ksteps;                    // k-steps of 8 with real data in the LAST k-block (4 unless a Linear layer's K % 32 != 0)
   int N, n_tile, n_tiles, n_pad;      // n_pad = n_tiles * n_tile rounded up to 32: length of the shared-memory epilogue vectors
   int TW, TH, tiles_x, tiles_y, tiles_per_img, m_tiles, total_tiles;
   int act;                            // 0 none, 1 exact-erf GELU, 2 residual + 0.5 * tanh(.)  (the LRP tail, stf.py:631-633),
@@ -399,6 +400,9 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tf32_kernel(const __grid_con
           const uint64_t da = umma_desc_sw128(base), db = umma_desc_sw128(base + b_off);
 #pragma unroll
           for (int ks = 0; ks < kBlockK / 8; ++ks) {  // one MMA consumes K = 8 tf32 = 32 B of every row
+            // Linear layers whose K is not a multiple of 32 (C = 48: 16 real columns in the last k-block): the k-steps that
+            // only hold TMA zero fill add +0 to every accumulator -- skipped (6 instead of 8 k-steps at C = 48)
+            if (kb == P.k_blocks - 1 && ks >= P.tail_ksteps) break;
             const uint64_t dak = da + (uint64_t)(ks * 2), dbk = db + (uint64_t)(ks * 2);
             if (leader) umma_tf32(d_tmem, dak, dbk, P.idesc, (kb | ks) ? 1u : 0u);
             if (kPrecise && leader) {  // 3xTF32: hi.hi + lo.hi + hi.lo (lo.lo is below fp32 round-off)
@@ -874,6 +878,8 @@ extern "C" int stf_conv2d(const stf_conv_args *a, void *stream) {
   }
   P.ksize = a->ksize, P.pad = a->ksize / 2, P.stride = s;
   P.k_blocks = P.kb_per_tap * a->ksize * a->ksize;
+  P.tail_ksteps = 4;
+  if (a->ksize == 1 && a->n_src == 1 && a->src_channels[0] % kBlockK) P.tail_ksteps = (a->src_channels[0] % kBlockK + 7) / 8;
   for (int p = 0; p < 1 + precise; ++p) {
     const cuuint64_t gdim[2] = {(cuuint64_t)Kp, (cuuint64_t)a->N};
     const cuuint64_t gstr[1] = {(cuuint64_t)Kp * 4};
