@@ -671,7 +671,9 @@ __global__ void __launch_bounds__(192, 4) window_attention_tok_kernel(const Attn
     asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst), "r"(src), "r"((uint32_t)(C * 4))
                  : "memory");
     asm volatile("cp.async.bulk.commit_group;" ::: "memory");
-    asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+    // the staging rows must outlive the copies' READS only: the CTA leaves (and the next one starts its gather) while the
+    // rows are still on their way to HBM; the writes are complete when the grid is
+    asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
   }
 }
 
