@@ -595,15 +595,17 @@ __global__ void __launch_bounds__(192, 4) window_attention_tok_kernel(const Attn
     // + relative-position bias + shifted-window mask (stf.py:100-110, 316-334); thread holds rows r0 = gid, r1 = gid + 8 and
     // keys m = 8 nt + 2 tig + {0, 1}
     int wy = 0, wx = 0;
+    bool edge = false;   // only the last window row / column of the shifted frame mixes regions (every other label is 0)
     if (P.shift > 0) {
       const int wi = (int)(win % P.nW);
       wy = wi / P.nWw, wx = wi - wy * P.nWw;
+      edge = wy == P.Hp / WS - 1 || wx == P.nWw - 1;
     }
     auto label = [&](int n) -> int {
       const int hs = wy * WS + (n >> 2), wsft = wx * WS + (n & 3);
       return 3 * (hs < P.Hp - WS ? 0 : (hs < P.Hp - P.shift ? 1 : 2)) + (wsft < P.Wp - WS ? 0 : (wsft < P.Wp - P.shift ? 1 : 2));
     };
-    const int lab_r0 = P.shift > 0 ? label(gid) : 0, lab_r1 = P.shift > 0 ? label(gid + 8) : 0;
+    const int lab_r0 = edge ? label(gid) : 0, lab_r1 = edge ? label(gid + 8) : 0;
     float mx0 = -INFINITY, mx1 = -INFINITY;
 #pragma unroll
     for (int nt = 0; nt < 2; ++nt)
@@ -614,7 +616,7 @@ __global__ void __launch_bounds__(192, 4) window_attention_tok_kernel(const Attn
         const int rel0 = ((gid >> 2) - hm + WS - 1) * (2 * WS - 1) + ((gid & 3) - wm + WS - 1);
         const int rel1 = (((gid + 8) >> 2) - hm + WS - 1) * (2 * WS - 1) + (((gid + 8) & 3) - wm + WS - 1);
         float v0 = s[nt][e] + tbl[rel0 * heads + head], v1 = s[nt][2 + e] + tbl[rel1 * heads + head];
-        if (P.shift > 0) {
+        if (edge) {
           const int lm = label(m);
           if (lm != lab_r0) v0 += kMaskValue;
           if (lm != lab_r1) v1 += kMaskValue;
